@@ -1,0 +1,123 @@
+// Host-side handle, memory layout of the arena / workspace / replay ring, error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/sacb200.h"
+#include "common.cuh"
+
+namespace sacb {
+
+void set_error(const std::string &msg);
+int fail(int code, const std::string &msg);
+
+#define SACB_CUDA(call)                                                                              \
+    do {                                                                                             \
+        cudaError_t _e = (call);                                                                     \
+        if (_e != cudaSuccess)                                                                       \
+            return ::sacb::fail(SACB_ERR_DEVICE, std::string(#call) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+// ---- one network inside the arena ----------------------------------------------------------------------------
+// API tensor order = Module.parameters() order (fc1.weight, fc1.bias, ..., see sacb200.h).  Policy heads are
+// stored fused: head.w [2A,H] = mean.weight rows then log_std.weight rows, head.b [2A] likewise.
+struct NetLayout {
+    int n_hidden = 0, in_dim = 0, hidden = 0, out_dim = 0;   // out_dim: 1 (Q) or 2A (policy head)
+    bool is_policy = false;
+    int64_t w[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};         // hidden layer l (0-based) weight [H,in_l] / bias [H]
+    int64_t w_out = 0, b_out = 0;                             // output layer / fused heads
+    int64_t size = 0;                                         // floats, multiple of 32
+    int in_of(int l) const { return l == 0 ? in_dim : hidden; }
+    int n_tensors() const { return is_policy ? 2 * n_hidden + 4 : 2 * n_hidden + 2; }
+    // API tensor -> (offset in net, rows, cols)
+    void tensor(int t, int64_t &off, int64_t &rows, int64_t &cols) const;
+};
+
+struct Layout {
+    int obs = 0, act = 0, hidden = 0, n_hidden = 0, maxB = 0, ldx = 0;
+    NetLayout pol, q;
+    // arena (per agent): scalars | params pol,q1,q2,q1t,q2t | m pol,q1,q2 | v pol,q1,q2 | grad pol,q1,q2
+    int64_t scalars = 0;
+    int64_t param[5] = {0, 0, 0, 0, 0};
+    int64_t adam_m[3] = {0, 0, 0}, adam_v[3] = {0, 0, 0}, grad[3] = {0, 0, 0};
+    int64_t grad_scalars = 0;       // exported log_alpha gradient
+    int64_t arena_size = 0;
+    // workspace (per agent)
+    int64_t X = 0, r = 0, d = 0, isw = 0, y = 0, td = 0, dq[2] = {0, 0}, dqa[2] = {0, 0}, logp = 0, eps = 0;
+    int64_t head_raw = 0, g_head = 0, da[2] = {0, 0}, wsnap[2] = {0, 0};
+    int64_t hp[4] = {0, 0, 0, 0}, dhp[4] = {0, 0, 0, 0};                 // policy activations [2B,H] / grads [B,H]
+    int64_t ht[2][4], hc[2][4], ha[2][4], dhc[2][4], dha[2][4];          // [B,H]
+    int64_t ws_size = 0;
+    void build(int obs, int act, int hidden, int n_hidden, int maxB);
+};
+
+struct ProgramKey {
+    int B, with_gather, export_grads, device_eps, use_isw, dp_phase;
+    bool operator<(const ProgramKey &o) const {
+        return std::tie(B, with_gather, export_grads, device_eps, use_isw, dp_phase) <
+               std::tie(o.B, o.with_gather, o.export_grads, o.device_eps, o.use_isw, o.dp_phase);
+    }
+};
+
+struct ProgramInst {
+    std::vector<Task> tasks;
+    std::vector<Stage> stages;
+    std::vector<int> stage_has_gemm;
+    Task *d_tasks = nullptr;
+    Stage *d_stages = nullptr;
+    Program prog{};
+    cudaGraphExec_t graph = nullptr;
+    int n_tiles_total = 0, max_stage_tiles = 0;
+    int kernels_per_step = 0;
+};
+
+}  // namespace sacb
+
+struct sacb_handle_s {
+    sacb_config cfg;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    sacb::Layout L;
+    float *arena = nullptr, *ws = nullptr;
+    unsigned int *barrier = nullptr;
+    int32_t *error_flag = nullptr;
+    int32_t *slots = nullptr;            // [n_agents, maxB] physical ring slots of the current minibatch
+    int32_t *slots_staged = nullptr;     // pre-staged index sets (sacb_stage_indices)
+    int64_t staged_steps = 0, staged_next = 0, staged_B = 0;
+    std::map<sacb::ProgramKey, sacb::ProgramInst> programs;
+    int64_t kernel_launches = 0;
+    int coop_blocks_per_sm = 0;
+    // ---- replay (replay.cu) ----
+    float *ring = nullptr;
+    int64_t ring_row = 0;                // floats per transition: [s | s2 | a | r | d] padded to 4
+    std::vector<int64_t> r_len, r_pos, r_head;   // per agent: count, next write slot, slot of the oldest entry
+    float *stage_rows = nullptr;         // device staging for pushes
+    int64_t stage_rows_cap = 0;
+    // PER
+    float *prio = nullptr, *p_alpha = nullptr;   // [n_agents, capacity]
+    std::vector<int64_t> per_frame;
+    void *per_ws = nullptr;                      // scan workspace (see replay.cu)
+    int64_t *last_idx_dev = nullptr;             // [n_agents, maxB] logical indices of the last sample
+    float *last_w_dev = nullptr;
+    sacb_per_stats per_stats{};
+    // pinned host staging
+    float *pin = nullptr;
+    int64_t pin_floats = 0;
+};
+
+namespace sacb {
+// program.cu
+int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out);
+int launch_program(sacb_handle h, ProgramInst &p);
+void free_programs(sacb_handle h);
+int check_error_flag(sacb_handle h);
+// replay.cu
+int replay_create(sacb_handle h);
+void replay_destroy(sacb_handle h);
+}  // namespace sacb

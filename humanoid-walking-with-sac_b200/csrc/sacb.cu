@@ -1,0 +1,329 @@
+// C-ABI entry points: handle life cycle, state_dict plumbing, update_parameters, select_action, timing.
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+
+#include "handle.h"
+#include "gemm.cuh"
+
+namespace sacb {
+static thread_local std::string g_err;
+void set_error(const std::string &m) { g_err = m; }
+int fail(int code, const std::string &m) { g_err = m; return code; }
+int init_kernel_attributes(sacb_handle h);
+}  // namespace sacb
+using namespace sacb;
+
+extern "C" const char *sacb_last_error(void) { return g_err.c_str(); }
+extern "C" const char *sacb_version(void) { return "sacb200 0.1 (sm_100a)"; }
+
+extern "C" void sacb_default_config(sacb_config *c) {
+    memset(c, 0, sizeof(*c));
+    c->hidden_dim = 256; c->n_hidden = 2;
+    c->gamma = 0.99f; c->tau = 0.005f; c->lr = 3e-4f; c->alpha0 = 0.2f; c->auto_entropy = 1;   // sac_imp.py:13-18
+    c->action_scale = 0.4f; c->action_bias = 0.0f;                                                // networks_model1.py:52-55
+    c->replay_kind = SACB_REPLAY_UNIFORM; c->capacity = 1000000;                                  // replay_buffer.py:7
+    c->per_alpha = 0.6f; c->per_beta_start = 0.4f; c->per_beta_frames = 100000;                   // replay_buffer.py:26
+    c->max_batch = 256; c->n_agents = 1;
+    c->math_mode = SACB_MATH_TF32; c->launch_mode = SACB_LAUNCH_STAGED; c->device = 0; c->seed = 0x5ac0b200ull;
+}
+
+extern "C" int sacb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        cudaDeviceProp p;
+        if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ok++;
+    }
+    return ok;
+}
+
+static int scalars_init(sacb_handle h) {
+    std::vector<float> sc(32, 0.f);
+    sc[SC_ALPHA0] = sc[SC_ALPHA1] = h->cfg.alpha0;     // python float 0.2 until the first update (quirk Q1)
+    for (int a = 0; a < h->cfg.n_agents; a++)
+        SACB_CUDA(cudaMemcpyAsync(h->arena + a * h->L.arena_size + h->L.scalars, sc.data(), 32 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    return cudaStreamSynchronize(h->stream) == cudaSuccess ? SACB_OK : SACB_ERR_DEVICE;
+}
+
+extern "C" int sacb_create(const sacb_config *cfg, sacb_handle *out) {
+    if (!cfg || !out) return fail(SACB_ERR_ARG, "null argument");
+    if (cfg->obs_dim < 1 || cfg->act_dim < 1 || cfg->hidden_dim < 8 || cfg->hidden_dim % 4) return fail(SACB_ERR_ARG, "bad dims (hidden_dim must be a multiple of 4)");
+    if (cfg->n_hidden != 2 && cfg->n_hidden != 3) return fail(SACB_ERR_ARG, "n_hidden must be 2 (networks_model1) or 3 (networks_model2)");
+    if (cfg->max_batch < 1 || cfg->n_agents < 1 || cfg->capacity < 1) return fail(SACB_ERR_ARG, "bad max_batch / n_agents / capacity");
+    if (2 * cfg->act_dim > 256) return fail(SACB_ERR_ARG, "act_dim > 128 unsupported");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device >= ndev) { cudaGetLastError(); return fail(SACB_ERR_DEVICE, "no CUDA device: this library has no CPU fallback"); }
+    cudaDeviceProp prop;
+    SACB_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10) return fail(SACB_ERR_DEVICE, "device is not sm_100 (B200): kernels are compiled for sm_100a only");
+    SACB_CUDA(cudaSetDevice(cfg->device));
+    sacb_handle h = new sacb_handle_s();
+    h->cfg = *cfg;
+    h->sm_count = prop.multiProcessorCount;
+    h->L.build(cfg->obs_dim, cfg->act_dim, cfg->hidden_dim, cfg->n_hidden, cfg->max_batch);
+    const int n = cfg->n_agents;
+    auto bail = [&](int rc) { sacb_destroy(h); return rc; };
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(SACB_ERR_DEVICE, "stream create failed"));
+    if (cudaMalloc(&h->arena, sizeof(float) * h->L.arena_size * n) != cudaSuccess ||
+        cudaMalloc(&h->ws, sizeof(float) * h->L.ws_size * n) != cudaSuccess ||
+        cudaMalloc(&h->barrier, 64) != cudaSuccess || cudaMalloc(&h->error_flag, 64) != cudaSuccess ||
+        cudaMalloc(&h->slots, sizeof(int32_t) * cfg->max_batch * n) != cudaSuccess)
+        return bail(fail(SACB_ERR_NOMEM, "device allocation failed"));
+    cudaMemsetAsync(h->arena, 0, sizeof(float) * h->L.arena_size * n, h->stream);
+    cudaMemsetAsync(h->ws, 0, sizeof(float) * h->L.ws_size * n, h->stream);
+    cudaMemsetAsync(h->barrier, 0, 64, h->stream);
+    cudaMemsetAsync(h->error_flag, 0, 64, h->stream);
+    cudaMemsetAsync(h->slots, 0, sizeof(int32_t) * cfg->max_batch * n, h->stream);
+    int rc = scalars_init(h);
+    if (rc) return bail(fail(rc, "scalar init failed"));
+    rc = init_kernel_attributes(h);
+    if (rc) return bail(rc);
+    rc = replay_create(h);
+    if (rc) return bail(rc);
+    h->pin_floats = (int64_t)cfg->max_batch * (2 * cfg->obs_dim + 3 * cfg->act_dim + 8) + 64;
+    if (cudaMallocHost(&h->pin, sizeof(float) * h->pin_floats) != cudaSuccess) return bail(fail(SACB_ERR_NOMEM, "pinned allocation failed"));
+    *out = h;
+    return SACB_OK;
+}
+
+extern "C" int sacb_destroy(sacb_handle h) {
+    if (!h) return SACB_OK;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    free_programs(h);
+    replay_destroy(h);
+    cudaFree(h->arena); cudaFree(h->ws); cudaFree(h->barrier); cudaFree(h->error_flag); cudaFree(h->slots); cudaFree(h->slots_staged);
+    if (h->pin) cudaFreeHost(h->pin);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return SACB_OK;
+}
+
+extern "C" int sacb_synchronize(sacb_handle h) {
+    if (!h) return fail(SACB_ERR_ARG, "null handle");
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    return check_error_flag(h);
+}
+
+// ---- state_dict plumbing -----------------------------------------------------------------------------------------
+static const NetLayout &net_layout(sacb_handle h, int net) { return net == SACB_NET_POLICY ? h->L.pol : h->L.q; }
+
+extern "C" int sacb_num_tensors(sacb_handle h, int net) {
+    if (!h || net < 0 || net > 4) return fail(SACB_ERR_ARG, "bad net id");
+    return net_layout(h, net).n_tensors();
+}
+
+static int tensor_offset(sacb_handle h, int agent, int net, int slot, int tensor, int64_t *off, int64_t *n) {
+    if (!h || net < 0 || net > 4 || agent < 0 || agent >= h->cfg.n_agents) return fail(SACB_ERR_ARG, "bad net / agent id");
+    const NetLayout &nl = net_layout(h, net);
+    if (tensor < 0 || tensor >= nl.n_tensors()) return fail(SACB_ERR_ARG, "bad tensor index");
+    int64_t o, r, c;
+    nl.tensor(tensor, o, r, c);
+    int64_t base;
+    if (slot == SACB_SLOT_PARAM) base = h->L.param[net];
+    else {
+        if (net > SACB_NET_Q2) return fail(SACB_ERR_ARG, "target networks have no optimizer state");
+        base = slot == SACB_SLOT_ADAM_M ? h->L.adam_m[net] : slot == SACB_SLOT_ADAM_V ? h->L.adam_v[net] : h->L.grad[net];
+        if (slot < 0 || slot > SACB_SLOT_GRAD) return fail(SACB_ERR_ARG, "bad slot");
+    }
+    *off = (int64_t)agent * h->L.arena_size + base + o;
+    *n = r * c;
+    return SACB_OK;
+}
+
+extern "C" int sacb_tensor_info(sacb_handle h, int net, int tensor, int64_t *rows, int64_t *cols, int64_t *arena_offset) {
+    if (!h || net < 0 || net > 4) return fail(SACB_ERR_ARG, "bad net id");
+    const NetLayout &nl = net_layout(h, net);
+    if (tensor < 0 || tensor >= nl.n_tensors()) return fail(SACB_ERR_ARG, "bad tensor index");
+    int64_t o, r, c;
+    nl.tensor(tensor, o, r, c);
+    if (rows) *rows = r;
+    if (cols) *cols = c;
+    if (arena_offset) *arena_offset = h->L.param[net] + o;
+    return SACB_OK;
+}
+
+extern "C" int sacb_tensor_dev(sacb_handle h, int agent, int net, int slot, int tensor, void **dev_ptr) {
+    int64_t off, n;
+    int rc = tensor_offset(h, agent, net, slot, tensor, &off, &n);
+    if (rc) return rc;
+    *dev_ptr = h->arena + off;
+    return SACB_OK;
+}
+
+extern "C" int sacb_import_tensor(sacb_handle h, int agent, int net, int slot, int tensor, const float *src, int64_t n) {
+    int64_t off, cnt;
+    int rc = tensor_offset(h, agent, net, slot, tensor, &off, &cnt);
+    if (rc) return rc;
+    if (n != cnt) return fail(SACB_ERR_ARG, "tensor size mismatch");
+    SACB_CUDA(cudaMemcpyAsync(h->arena + off, src, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    return SACB_OK;
+}
+
+extern "C" int sacb_export_tensor(sacb_handle h, int agent, int net, int slot, int tensor, float *dst, int64_t n) {
+    int64_t off, cnt;
+    int rc = tensor_offset(h, agent, net, slot, tensor, &off, &cnt);
+    if (rc) return rc;
+    if (n != cnt) return fail(SACB_ERR_ARG, "tensor size mismatch");
+    SACB_CUDA(cudaMemcpyAsync(dst, h->arena + off, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    return SACB_OK;
+}
+
+static inline int64_t f2i(float f) { int32_t i; memcpy(&i, &f, 4); return i; }
+static inline float i2f(int64_t v) { int32_t i = (int32_t)v; float f; memcpy(&f, &i, 4); return f; }
+
+extern "C" int sacb_get_scalars(sacb_handle h, int agent, sacb_scalars *out) {
+    if (!h || !out || agent < 0 || agent >= h->cfg.n_agents) return fail(SACB_ERR_ARG, "bad argument");
+    float sc[32];
+    SACB_CUDA(cudaMemcpyAsync(sc, h->arena + agent * h->L.arena_size + h->L.scalars, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    out->n_updates = f2i(sc[SC_N_UPDATES]);
+    out->log_alpha = sc[SC_LOG_ALPHA]; out->log_alpha_m = sc[SC_LOG_ALPHA_M]; out->log_alpha_v = sc[SC_LOG_ALPHA_V];
+    out->alpha = sc[SC_ALPHA0 + (out->n_updates & 1)];
+    out->step_policy = f2i(sc[SC_STEP_POLICY]); out->step_q1 = f2i(sc[SC_STEP_Q1]); out->step_q2 = f2i(sc[SC_STEP_Q2]);
+    out->step_alpha = f2i(sc[SC_STEP_ALPHA]);
+    return SACB_OK;
+}
+
+extern "C" int sacb_set_scalars(sacb_handle h, int agent, const sacb_scalars *in) {
+    if (!h || !in || agent < 0 || agent >= h->cfg.n_agents) return fail(SACB_ERR_ARG, "bad argument");
+    float sc[32];
+    float *dev = h->arena + agent * h->L.arena_size + h->L.scalars;
+    SACB_CUDA(cudaMemcpyAsync(sc, dev, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    sc[SC_LOG_ALPHA] = in->log_alpha; sc[SC_LOG_ALPHA_M] = in->log_alpha_m; sc[SC_LOG_ALPHA_V] = in->log_alpha_v;
+    sc[SC_ALPHA0] = sc[SC_ALPHA1] = in->alpha;
+    sc[SC_STEP_POLICY] = i2f(in->step_policy); sc[SC_STEP_Q1] = i2f(in->step_q1); sc[SC_STEP_Q2] = i2f(in->step_q2);
+    sc[SC_STEP_ALPHA] = i2f(in->step_alpha); sc[SC_N_UPDATES] = i2f(in->n_updates);
+    SACB_CUDA(cudaMemcpyAsync(dev, sc, sizeof(sc), cudaMemcpyHostToDevice, h->stream));
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    return SACB_OK;
+}
+
+extern "C" int sacb_get_losses(sacb_handle h, int agent, float *losses_out) {
+    if (!h || !losses_out || agent < 0 || agent >= h->cfg.n_agents) return fail(SACB_ERR_ARG, "bad argument");
+    SACB_CUDA(cudaMemcpyAsync(losses_out, h->arena + agent * h->L.arena_size + h->L.scalars + SC_LOSS_Q1, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    return check_error_flag(h);
+}
+
+// ---- update_parameters ---------------------------------------------------------------------------------------------
+static int upload_eps(sacb_handle h, int agent, int64_t B, const float *eps_next, const float *eps_cur) {
+    float *ws = h->ws + agent * h->L.ws_size;
+    const int64_t n = B * h->cfg.act_dim;
+    if (eps_next) SACB_CUDA(cudaMemcpyAsync(ws + h->L.eps, eps_next, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    if (eps_cur) SACB_CUDA(cudaMemcpyAsync(ws + h->L.eps + n, eps_cur, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+    return SACB_OK;
+}
+
+static int finish_update(sacb_handle h, float *losses_out, uint32_t flags) {
+    if (flags & SACB_NO_LOSS_READBACK) return SACB_OK;
+    if (losses_out) return sacb_get_losses(h, 0, losses_out);     // 3 floats D2H + sync: the `.item()` calls of sac_imp.py:141-143
+    return sacb_synchronize(h);
+}
+
+extern "C" int sacb_update_batch(sacb_handle h, int64_t B, const float *s, const float *a, const float *r, const float *s2,
+                                 const float *done, const float *isw, const float *eps_next, const float *eps_cur,
+                                 float *losses_out, float *td_abs_out, uint32_t flags) {
+    if (!h || !s || !a || !r || !s2 || !done) return fail(SACB_ERR_ARG, "null minibatch pointer");
+    if (h->cfg.n_agents != 1) return fail(SACB_ERR_ARG, "sacb_update_batch drives a single agent");
+    if ((eps_next == nullptr) != (eps_cur == nullptr)) return fail(SACB_ERR_ARG, "pass both eps arrays or neither");
+    const Layout &L = h->L;
+    if (B < 1 || B > L.maxB) return fail(SACB_ERR_ARG, "batch size out of range");
+    float *ws = h->ws;
+    const size_t ldx = sizeof(float) * L.ldx, wo = sizeof(float) * L.obs, wa = sizeof(float) * L.act;
+    float *X2 = ws + L.X, *X1 = X2 + B * L.ldx, *X3 = X1 + B * L.ldx;
+    SACB_CUDA(cudaMemcpy2DAsync(X2, ldx, s2, wo, wo, B, cudaMemcpyHostToDevice, h->stream));
+    SACB_CUDA(cudaMemcpy2DAsync(X1, ldx, s, wo, wo, B, cudaMemcpyHostToDevice, h->stream));
+    SACB_CUDA(cudaMemcpy2DAsync(X3, ldx, s, wo, wo, B, cudaMemcpyHostToDevice, h->stream));
+    SACB_CUDA(cudaMemcpy2DAsync(X1 + L.obs, ldx, a, wa, wa, B, cudaMemcpyHostToDevice, h->stream));
+    SACB_CUDA(cudaMemcpyAsync(ws + L.r, r, sizeof(float) * B, cudaMemcpyHostToDevice, h->stream));
+    SACB_CUDA(cudaMemcpyAsync(ws + L.d, done, sizeof(float) * B, cudaMemcpyHostToDevice, h->stream));
+    if (isw) SACB_CUDA(cudaMemcpyAsync(ws + L.isw, isw, sizeof(float) * B, cudaMemcpyHostToDevice, h->stream));
+    int rc = upload_eps(h, 0, B, eps_next, eps_cur);
+    if (rc) return rc;
+    ProgramKey key{(int)B, 0, (flags & SACB_EXPORT_GRADS) ? 1 : 0, eps_next ? 0 : 1, isw ? 1 : 0, -1};
+    ProgramInst *p;
+    rc = get_program(h, key, &p);
+    if (rc) return rc;
+    rc = launch_program(h, *p);
+    if (rc) return rc;
+    if (td_abs_out) {
+        SACB_CUDA(cudaMemcpyAsync(td_abs_out, ws + L.td, sizeof(float) * B, cudaMemcpyDeviceToHost, h->stream));
+        SACB_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    return finish_update(h, losses_out, flags);
+}
+
+namespace sacb { int replay_stage_slots(sacb_handle h, const int64_t *idx, int64_t B); }
+
+extern "C" int sacb_update(sacb_handle h, int64_t B, const int64_t *idx, const float *eps_next, const float *eps_cur,
+                           float *losses_out, uint32_t flags) {
+    if (!h) return fail(SACB_ERR_ARG, "null handle");
+    if (B < 1 || B > h->L.maxB) return fail(SACB_ERR_ARG, "batch size out of range");
+    if ((eps_next == nullptr) != (eps_cur == nullptr)) return fail(SACB_ERR_ARG, "pass both eps arrays or neither");
+    int rc;
+    if (idx) {
+        rc = replay_stage_slots(h, idx, B);
+        if (rc) return rc;
+    } else if (h->staged_steps > 0 && !(flags & SACB_USE_LAST_SAMPLE)) {
+        const int64_t k = h->staged_next % h->staged_steps;
+        h->staged_next++;
+        SACB_CUDA(cudaMemcpyAsync(h->slots, h->slots_staged + k * h->cfg.n_agents * h->staged_B, sizeof(int32_t) * h->staged_B * h->cfg.n_agents,
+                                  cudaMemcpyDeviceToDevice, h->stream));
+    } else if (!(flags & SACB_USE_LAST_SAMPLE)) {
+        return fail(SACB_ERR_ARG, "no indices: pass idx, stage them, or set SACB_USE_LAST_SAMPLE");
+    }
+    if (eps_next) for (int a = 0; a < h->cfg.n_agents; a++) {
+        const int64_t n = B * h->cfg.act_dim;
+        rc = upload_eps(h, a, B, eps_next + a * n, eps_cur + a * n);
+        if (rc) return rc;
+    }
+    const int use_isw = (h->cfg.per_weighted_loss && h->cfg.replay_kind == SACB_REPLAY_PER) ? 1 : 0;
+    ProgramKey key{(int)B, 1, (flags & SACB_EXPORT_GRADS) ? 1 : 0, eps_next ? 0 : 1, use_isw, -1};
+    ProgramInst *p;
+    rc = get_program(h, key, &p);
+    if (rc) return rc;
+    rc = launch_program(h, *p);
+    if (rc) return rc;
+    return finish_update(h, losses_out, flags);
+}
+
+// ---- instrumentation ---------------------------------------------------------------------------------------------
+extern "C" int sacb_get_stats(sacb_handle h, sacb_stats *out) {
+    if (!h || !out) return fail(SACB_ERR_ARG, "null argument");
+    memset(out, 0, sizeof(*out));
+    out->kernel_launches = h->kernel_launches;
+    out->sm_count = h->sm_count; out->block = kThreads;
+    out->smem_bytes = h->cfg.math_mode == SACB_MATH_TF32 ? kTcSmemBytes : kSimtSmemBytes;
+    for (auto &kv : h->programs) {
+        out->n_stages = (int)kv.second.stages.size(); out->n_tasks = (int)kv.second.tasks.size();
+        out->n_tiles = kv.second.n_tiles_total; out->grid = kv.second.max_stage_tiles;
+    }
+    return SACB_OK;
+}
+
+extern "C" int sacb_time_update(sacb_handle h, int64_t B, int iters, float *ms_per_step) {
+    if (!h || !ms_per_step || iters < 1) return fail(SACB_ERR_ARG, "bad argument");
+    ProgramKey key{(int)B, 0, 0, 1, 0, -1};
+    ProgramInst *p;
+    int rc = get_program(h, key, &p);
+    if (rc) return rc;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 3; i++) if ((rc = launch_program(h, *p))) return rc;
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    cudaEventRecord(e0, h->stream);
+    for (int i = 0; i < iters; i++) if ((rc = launch_program(h, *p))) return rc;
+    cudaEventRecord(e1, h->stream);
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_per_step = ms / iters;
+    return check_error_flag(h);
+}

@@ -1,0 +1,275 @@
+// Non-GEMM tile tasks of the SAC update program (sampling, losses, bias / output-layer optimiser steps).
+// Slot meaning of Task::p / i / f is documented per task; the host builder (program.cu) fills them.
+#pragma once
+#include "gemm.cuh"
+
+namespace sacb {
+
+// ---- Philox4x32-10 (Salmon et al. 2011) for production-mode eps draws --------------------------------------
+__device__ __forceinline__ void philox4x32(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t stream, uint32_t step, uint32_t row, uint32_t col) {
+    uint32_t c[4] = {row, col, step, stream};
+    philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const float u1 = ((float)(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float u2 = ((float)(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float row_dot(const float *h, const float *w, int n, int lane) {
+    float s = 0.f;
+    for (int j = lane; j < n; j += 32) s = fmaf(ldcg(h + j), ldcg(w + j), s);
+    return warp_sum(s);
+}
+
+// tanh-Gaussian sample of one action component: networks_model1.py:83-96 == networks_model2.py:104-117
+struct SampleElem { float action, logp, y, std, in_range; };
+__device__ __forceinline__ SampleElem sample_elem(float mean, float ls_raw, float eps, float scale, float bias) {
+    SampleElem o;
+    const float ls = fminf(fmaxf(ls_raw, kLogStdMin), kLogStdMax);     // torch.clamp(log_std, -20, 2)
+    o.in_range = (ls_raw >= kLogStdMin && ls_raw <= kLogStdMax) ? 1.f : 0.f;
+    o.std = expf(ls);
+    const float x = mean + eps * o.std;                                  // Normal.rsample
+    o.y = tanhf(x);
+    o.action = o.y * scale + bias;
+    const float var = o.std * o.std;
+    const float d = x - mean;
+    float lp = -(d * d) / (2.f * var) - logf(o.std) - kLogSqrt2Pi;      // Normal.log_prob
+    lp -= logf(scale * (1.f - o.y * o.y) + kSquashEps);
+    o.logp = lp;
+    return o;
+}
+
+// T_GATHER: p0=Xall [3B,ldx] ; p1=r ; p2=d ; i0=B i1=obs i2=act i3=ldx ; ring row = [s | s2 | a | r | d]
+//   rows [0,B) <- (s2, .)   rows [B,2B) <- (s, a)   rows [2B,3B) <- (s, .)
+__device__ __forceinline__ void task_gather(const Task &t, int tile, const Program &P, int agent) {
+    const int B = t.i[0], obs = t.i[1], act = t.i[2], ldx = t.i[3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = tile * (kThreads / 32) + warp;
+    if (b >= B) return;
+    float *X = resolve(t.p[0], P.bases, agent);
+    const int slot = P.slots[(int64_t)agent * P.slots_stride + b];
+    const float *row = P.ring + agent * P.ring_agent_stride + (int64_t)slot * P.ring_row;
+    float *x2 = X + (int64_t)b * ldx, *x1 = X + (int64_t)(B + b) * ldx, *x3 = X + (int64_t)(2 * B + b) * ldx;
+    for (int j = lane; j < obs; j += 32) {
+        const float s = __ldcs(row + j), s2 = __ldcs(row + obs + j);
+        x1[j] = s; x3[j] = s; x2[j] = s2;
+    }
+    for (int j = lane; j < act; j += 32) x1[obs + j] = __ldcs(row + 2 * obs + j);
+    if (lane == 0) {
+        resolve(t.p[1], P.bases, agent)[b] = row[2 * obs + act];
+        resolve(t.p[2], P.bases, agent)[b] = row[2 * obs + act + 1];
+    }
+}
+
+// T_SAMPLE: p0=head_raw [2B,2A] (mean | log_std_raw) ; p1=eps [2B,A] (null -> Philox) ; p2=Xall ; p3=logp [2B]
+//   i0=B i1=A i2=obs i3=ldx ; f0=scale f1=bias.  row j<B: next-state sample -> X2[j,obs:] ; j>=B: current -> X3[j-B,obs:]
+__device__ __forceinline__ void task_sample(const Task &t, int tile, const Program &P, int agent, const float *scalars, uint64_t seed) {
+    const int B = t.i[0], A = t.i[1], obs = t.i[2], ldx = t.i[3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = tile * (kThreads / 32) + warp;
+    if (j >= 2 * B) return;
+    const float *head = resolve(t.p[0], P.bases, agent) + (int64_t)j * 2 * A;
+    float *eps = resolve(t.p[1], P.bases, agent);
+    float *X = resolve(t.p[2], P.bases, agent);
+    float *dst = (j < B) ? X + (int64_t)j * ldx + obs : X + (int64_t)(2 * B + (j - B)) * ldx + obs;
+    const uint32_t step = (uint32_t)__float_as_int(ldcg(scalars + SC_N_UPDATES));
+    float lp = 0.f;
+    for (int a = lane; a < A; a += 32) {
+        float e;
+        if (t.i[4]) {   // production mode: draw on device and keep the draw for the backward pass
+            e = philox_normal(seed, (uint32_t)agent, step, (uint32_t)j, (uint32_t)a);
+            eps[(int64_t)j * A + a] = e;
+        } else {
+            e = ldcg(eps + (int64_t)j * A + a);
+        }
+        const SampleElem s = sample_elem(ldcg(head + a), ldcg(head + A + a), e, t.f[0], t.f[1]);
+        dst[a] = s.action;
+        lp += s.logp;
+    }
+    lp = warp_sum(lp);
+    if (lane == 0) resolve(t.p[3], P.bases, agent)[j] = lp;
+}
+
+// T_TARGET_LOSS (one tile): Bellman target + critic MSE + dL/dq   (sac_imp.py:92-105)
+//   p0,p1 = last hidden activations of q1_target,q2_target on (s2,a2) [B,H] ; p2,p3 = of q1,q2 on (s,a)
+//   p4..p7 = output-layer weights [H] of q1t,q2t,q1,q2 ; p8..p11 = their biases [1]
+//   p12=r p13=d p14=logp_next p15=is_weights(null -> 1) ; outputs p16=y p17=dq1 p18=dq2 p19=td (|q1-y|)
+//   p[20],p[21] = snapshot copies of the q1,q2 output weights read by the rank-1 operand transforms
+//   i0=B i1=H ; f0=gamma
+__device__ __forceinline__ void task_target_loss(const Task &t, const Program &P, int agent, float *scalars, float *smem) {
+    const int B = t.i[0], H = t.i[1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = kThreads / 32;
+    const float *h[4], *w[4], *bo[4];
+    for (int k = 0; k < 4; k++) {
+        h[k] = resolve(t.p[k], P.bases, agent); w[k] = resolve(t.p[4 + k], P.bases, agent); bo[k] = resolve(t.p[8 + k], P.bases, agent);
+    }
+    const float *r = resolve(t.p[12], P.bases, agent), *d = resolve(t.p[13], P.bases, agent);
+    const float *lpn = resolve(t.p[14], P.bases, agent), *isw = resolve(t.p[15], P.bases, agent);
+    float *y = resolve(t.p[16], P.bases, agent), *dq1 = resolve(t.p[17], P.bases, agent), *dq2 = resolve(t.p[18], P.bases, agent);
+    float *td = resolve(t.p[19], P.bases, agent);
+    float *snap1 = resolve(t.p[20], P.bases, agent), *snap2 = resolve(t.p[21], P.bases, agent);
+    const int n_upd = __float_as_int(ldcg(scalars + SC_N_UPDATES));
+    const float alpha = ldcg(scalars + SC_ALPHA0 + (n_upd & 1));
+    for (int j = threadIdx.x; j < H; j += kThreads) { snap1[j] = ldcg(w[2] + j); snap2[j] = ldcg(w[3] + j); }
+    float l1 = 0.f, l2 = 0.f;
+    for (int b = warp; b < B; b += nw) {
+        float q[4];
+        for (int k = 0; k < 4; k++) q[k] = row_dot(h[k] + (int64_t)b * H, w[k], H, lane) + ldcg(bo[k]);
+        if (lane == 0) {
+            const float qn = fminf(q[0], q[1]);
+            const float vt = qn - alpha * ldcg(lpn + b);                          // sac_imp.py:97
+            const float yy = ldcg(r + b) + (1.f - ldcg(d + b)) * t.f[0] * vt;     // sac_imp.py:98
+            const float wgt = isw ? ldcg(isw + b) : 1.f;
+            const float e1 = q[2] - yy, e2 = q[3] - yy;
+            y[b] = yy;
+            dq1[b] = 2.f * wgt * e1 / (float)B;                                   // d mean((q-y)^2) / dq
+            dq2[b] = 2.f * wgt * e2 / (float)B;
+            td[b] = fabsf(e1);
+            l1 += wgt * e1 * e1; l2 += wgt * e2 * e2;
+        }
+    }
+    if (lane == 0) { smem[warp] = l1; smem[nw + warp] = l2; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int i = 0; i < nw; i++) { s1 += smem[i]; s2 += smem[nw + i]; }
+        scalars[SC_LOSS_Q1] = s1 / (float)B;
+        scalars[SC_LOSS_Q2] = s2 / (float)B;
+    }
+    __syncthreads();
+}
+
+// T_ACTOR_LOSS (one tile): policy loss, min-Q routing, temperature loss + its Adam step (sac_imp.py:117-135)
+//   p0,p1 = last hidden activations of q1,q2 on (s, a_new) ; p2,p3 = output weights ; p4,p5 = output biases
+//   p6=logp_cur ; outputs p7=dqa1 p8=dqa2 ; p9 = exported log_alpha gradient (null unless DP)
+//   i0=B i1=H i2=auto_entropy i3=apply ; f0=target_entropy f1=lr
+__device__ __forceinline__ void task_actor_loss(const Task &t, const Program &P, int agent, float *scalars, float *smem) {
+    const int B = t.i[0], H = t.i[1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = kThreads / 32;
+    const float *h1 = resolve(t.p[0], P.bases, agent), *h2 = resolve(t.p[1], P.bases, agent);
+    const float *w1 = resolve(t.p[2], P.bases, agent), *w2 = resolve(t.p[3], P.bases, agent);
+    const float b1 = ldcg(resolve(t.p[4], P.bases, agent)), b2 = ldcg(resolve(t.p[5], P.bases, agent));
+    const float *lp = resolve(t.p[6], P.bases, agent);
+    float *dqa1 = resolve(t.p[7], P.bases, agent), *dqa2 = resolve(t.p[8], P.bases, agent);
+    const int n_upd = __float_as_int(ldcg(scalars + SC_N_UPDATES));
+    const float alpha = ldcg(scalars + SC_ALPHA0 + (n_upd & 1));
+    float pl = 0.f, ent = 0.f;
+    for (int b = warp; b < B; b += nw) {
+        const float q1 = row_dot(h1 + (int64_t)b * H, w1, H, lane) + b1;
+        const float q2 = row_dot(h2 + (int64_t)b * H, w2, H, lane) + b2;
+        if (lane == 0) {
+            const float l = ldcg(lp + b);
+            pl += alpha * l - fminf(q1, q2);                                       // sac_imp.py:119-121
+            const float sel = q1 < q2 ? 1.f : (q1 == q2 ? 0.5f : 0.f);             // torch.minimum backward
+            dqa1[b] = -sel / (float)B;
+            dqa2[b] = -(1.f - sel) / (float)B;
+            ent += l + t.f[0];
+        }
+    }
+    if (lane == 0) { smem[warp] = pl; smem[nw + warp] = ent; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float s1 = 0.f, s2 = 0.f;
+        for (int i = 0; i < nw; i++) { s1 += smem[i]; s2 += smem[nw + i]; }
+        scalars[SC_LOSS_PI] = s1 / (float)B;
+        float alpha_next = alpha;
+        if (t.i[2]) {
+            const float la = scalars[SC_LOG_ALPHA];
+            const float g = -(s2 / (float)B);                                      // d(-mean(log_alpha*(logp+H_t)))/dlog_alpha
+            scalars[SC_LOSS_ALPHA] = la * g;
+            float *gexp = resolve(t.p[9], P.bases, agent);
+            float ss, bs;
+            adam_factors(__float_as_int(scalars[SC_STEP_ALPHA]), t.f[1], ss, bs);
+            adam_element(g, &scalars[SC_LOG_ALPHA], &scalars[SC_LOG_ALPHA_M], &scalars[SC_LOG_ALPHA_V], nullptr, gexp, t.i[3], ss, bs, 0.f);
+            alpha_next = expf(scalars[SC_LOG_ALPHA]);                              // self.alpha = self.log_alpha.exp()
+        }
+        scalars[SC_ALPHA0 + ((n_upd + 1) & 1)] = alpha_next;
+    }
+    __syncthreads();
+}
+
+// T_SAMPLE_BWD: p0=da1 p1=da2 [B,A] ; p2=head_raw rows of the current-state sample ; p3=eps_cur ; p4=g_head [B,2A]
+//   i0=B i1=A ; f0=scale f1=bias    (closed form of SURVEY 3.3)
+__device__ __forceinline__ void task_sample_bwd(const Task &t, int tile, const Program &P, int agent, const float *scalars) {
+    const int B = t.i[0], A = t.i[1];
+    const int idx = tile * kThreads + threadIdx.x;
+    if (idx >= B * A) return;
+    const int b = idx / A, a = idx % A;
+    const int n_upd = __float_as_int(ldcg(scalars + SC_N_UPDATES));
+    const float alpha = ldcg(scalars + SC_ALPHA0 + (n_upd & 1));
+    const float *head = resolve(t.p[2], P.bases, agent) + (int64_t)b * 2 * A;
+    const float eps = ldcg(resolve(t.p[3], P.bases, agent) + idx);
+    const SampleElem s = sample_elem(ldcg(head + a), ldcg(head + A + a), eps, t.f[0], t.f[1]);
+    const float da = ldcg(resolve(t.p[0], P.bases, agent) + idx) + ldcg(resolve(t.p[1], P.bases, agent) + idx);
+    const float sc = t.f[0], omy2 = 1.f - s.y * s.y, aB = alpha / (float)B;
+    const float g_u = da * sc * omy2 + aB * (2.f * sc * s.y * omy2) / (sc * omy2 + kSquashEps);
+    float *g = resolve(t.p[4], P.bases, agent) + (int64_t)b * 2 * A;
+    g[a] = g_u;
+    g[A + a] = (g_u * s.std * eps - aB) * s.in_range;
+}
+
+// T_OUT_ADAM: Q output layer (Linear(H,1)).  p0=h_L [B,H] p1=dq [B] ; p2..p6 = w,m,v,wt,gexp [H] ; p7..p11 = same for bias
+//   i0=B i1=H i2=step_slot i3=apply ; f0=lr f1=tau.   one thread per column; tile 0 thread 0 also does the bias
+__device__ __forceinline__ void task_out_adam(const Task &t, int tile, const Program &P, int agent, const float *scalars) {
+    const int B = t.i[0], H = t.i[1];
+    const int n = tile * kThreads + threadIdx.x;
+    const float *h = resolve(t.p[0], P.bases, agent), *dq = resolve(t.p[1], P.bases, agent);
+    float ss, bs;
+    adam_factors(__float_as_int(ldcg(scalars + t.i[2])), t.f[0], ss, bs);
+    if (n < H) {
+        float g = 0.f;
+        for (int b = 0; b < B; b++) g = fmaf(ldcg(dq + b), ldcg(h + (int64_t)b * H + n), g);
+        float *wt = resolve(t.p[5], P.bases, agent), *ge = resolve(t.p[6], P.bases, agent);
+        adam_element(g, resolve(t.p[2], P.bases, agent) + n, resolve(t.p[3], P.bases, agent) + n, resolve(t.p[4], P.bases, agent) + n,
+                     wt ? wt + n : nullptr, ge ? ge + n : nullptr, t.i[3], ss, bs, t.f[1]);
+    }
+    if (tile == 0 && threadIdx.x == 0) {
+        float g = 0.f;
+        for (int b = 0; b < B; b++) g += ldcg(dq + b);
+        adam_element(g, resolve(t.p[7], P.bases, agent), resolve(t.p[8], P.bases, agent), resolve(t.p[9], P.bases, agent),
+                     resolve(t.p[10], P.bases, agent), resolve(t.p[11], P.bases, agent), t.i[3], ss, bs, t.f[1]);
+    }
+}
+
+// T_BIAS_ADAM: db[n] = sum_b dh[b,n], dh described by Task::A (K-major [B,N], optional rank-1 transform).
+//   p0..p4 = b,m,v,bt,gexp ; i0=B i1=N i2=step_slot i3=apply ; f0=lr f1=tau
+__device__ __forceinline__ void task_bias_adam(const Task &t, int tile, const Program &P, int agent, const float *scalars) {
+    const int B = t.i[0], N = t.i[1];
+    const int n = tile * kThreads + threadIdx.x;
+    if (n >= N) return;
+    const OperandR A = resolve_operand(t.A, P.bases, agent);
+    float g = 0.f;
+    for (int b = 0; b < B; b++) g += operand_at(A, b, n);
+    float ss, bs;
+    adam_factors(__float_as_int(ldcg(scalars + t.i[2])), t.f[0], ss, bs);
+    float *bt = resolve(t.p[3], P.bases, agent), *ge = resolve(t.p[4], P.bases, agent);
+    adam_element(g, resolve(t.p[0], P.bases, agent) + n, resolve(t.p[1], P.bases, agent) + n, resolve(t.p[2], P.bases, agent) + n,
+                 bt ? bt + n : nullptr, ge ? ge + n : nullptr, t.i[3], ss, bs, t.f[1]);
+}
+
+// T_FINISH: optimizer step counters (+1 each, sac_imp.py:109,113,125,134) and the update counter
+__device__ __forceinline__ void task_finish(const Task &t, float *scalars) {
+    if (threadIdx.x == 0) {
+        const int slots[4] = {SC_STEP_POLICY, SC_STEP_Q1, SC_STEP_Q2, SC_STEP_ALPHA};
+        for (int k = 0; k < 4; k++)
+            if (t.i[k]) scalars[slots[k]] = __int_as_float(__float_as_int(scalars[slots[k]]) + 1);
+        scalars[SC_N_UPDATES] = __int_as_float(__float_as_int(scalars[SC_N_UPDATES]) + 1);
+    }
+}
+
+}  // namespace sacb

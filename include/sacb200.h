@@ -1,0 +1,184 @@
+/* sacb200.h -- C ABI of the B200-native SAC learner hot path (libsacb200.so).
+ *
+ * The reference (FilippoCrc/Humanoid-walking-with-SAC) is pure Python: it has no FFI.  Its boundary for
+ * this path is the Python class API of sac_imp.SAC, replay_buffer.ReplayBuffer and
+ * replay_buffer.PrioritizedReplayBuffer.  Each entry point below names the reference method it serves
+ * (paths relative to the reference checkout); the Python mirror classes in
+ * humanoid-walking-with-sac_b200/{sac_imp,replay_buffer}.py bind them through ctypes.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative sacb_status otherwise; sacb_last_error() gives text.
+ *   - all pointers are HOST pointers owned by the caller unless the name ends in _dev.
+ *   - float = IEEE binary32, idx = int64 (numpy default), uniforms = binary64 (RandomState.random_sample).
+ *   - one handle = one agent population on one GPU (n_agents >= 1), one private CUDA stream; calls on a
+ *     handle are not re-entrant (the reference is single-threaded, trainer.py:182-205).
+ *   - there is NO CPU fallback: if no sm_100 device is present sacb_create fails with SACB_ERR_DEVICE.
+ */
+#ifndef SACB200_H
+#define SACB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct sacb_handle_s *sacb_handle;
+
+typedef enum {
+    SACB_OK = 0,
+    SACB_ERR_ARG = -1,       /* bad argument / shape (Python shim raises ValueError) */
+    SACB_ERR_DEVICE = -2,    /* no usable sm_100 device / CUDA failure (RuntimeError) */
+    SACB_ERR_STATE = -3,     /* e.g. sample larger than population (ValueError, as random.sample does) */
+    SACB_ERR_NOMEM = -4
+} sacb_status;
+
+/* GEMM arithmetic of the update: */
+enum { SACB_MATH_FP32 = 0,   /* CUDA-core FFMA, fp32 in / fp32 accumulate (strict-parity mode)            */
+       SACB_MATH_TF32 = 1 }; /* tcgen05.mma kind::tf32, fp32 operands read as tf32, fp32 accumulate in TMEM */
+
+/* how one update step is launched: */
+enum { SACB_LAUNCH_STAGED = 0,     /* one kernel per dependency stage, whole step captured in one CUDA graph */
+       SACB_LAUNCH_PERSISTENT = 1 }; /* ONE cooperative launch per step, grid barriers between stages        */
+
+enum { SACB_NET_POLICY = 0, SACB_NET_Q1 = 1, SACB_NET_Q2 = 2, SACB_NET_Q1_TARGET = 3, SACB_NET_Q2_TARGET = 4 };
+enum { SACB_SLOT_PARAM = 0, SACB_SLOT_ADAM_M = 1, SACB_SLOT_ADAM_V = 2, SACB_SLOT_GRAD = 3 };
+enum { SACB_REPLAY_UNIFORM = 0, SACB_REPLAY_PER = 1 };
+
+/* Constructor arguments of sac_imp.SAC.__init__ (sac_imp.py:9-52) + the network variant it imports
+ * (sac_imp.py:4: networks_model1 = 2 hidden layers, networks_model2 = 3) + replay_buffer.py ctor args. */
+typedef struct {
+    int32_t obs_dim, act_dim, hidden_dim;
+    int32_t n_hidden;              /* 2 (networks_model1.py:15-17) or 3 (networks_model2.py:24-27) */
+    float gamma, tau, lr, alpha0;  /* sac_imp.py:13-17 */
+    int32_t auto_entropy;          /* sac_imp.py:18 */
+    float action_scale, action_bias; /* networks_model1.py:52-55 */
+    int32_t replay_kind;           /* SACB_REPLAY_* */
+    int64_t capacity;              /* replay_buffer.py:7 / :26 */
+    float per_alpha, per_beta_start; /* replay_buffer.py:26 */
+    int64_t per_beta_frames;
+    int32_t max_batch;             /* largest batch_size update/sample will be called with */
+    int32_t n_agents;              /* independent agents (population mode, BASELINE.json configs[4]); 1 = reference */
+    int32_t math_mode;             /* SACB_MATH_* */
+    int32_t launch_mode;           /* SACB_LAUNCH_* */
+    int32_t device;                /* CUDA ordinal */
+    uint64_t seed;                 /* Philox key for on-device eps / index draws (production mode) */
+    int32_t per_weighted_loss;     /* extension: IS-weighted critic loss + |td| priority write-back */
+    int32_t reserved[7];
+} sacb_config;
+
+void sacb_default_config(sacb_config *cfg);
+const char *sacb_last_error(void);
+const char *sacb_version(void);
+/* number of CUDA devices usable by this library (sm_100); 0 if none. */
+int sacb_device_count(void);
+
+/* SAC.__init__ (sac_imp.py:9-52): allocates arena (params, targets, Adam m/v), workspaces, replay ring.
+ * Parameters start at zero: the host shim uploads the initial weights with sacb_import_tensor. */
+int sacb_create(const sacb_config *cfg, sacb_handle *out);
+int sacb_destroy(sacb_handle h);
+int sacb_synchronize(sacb_handle h);
+
+/* ---- state_dict plumbing: SAC.save/load/save_checkpoint/load_checkpoint (sac_imp.py:154-233) -------------
+ * tensor index = position in Module.parameters() order (fc1.weight, fc1.bias, ..., see sacb_tensor_info). */
+int sacb_num_tensors(sacb_handle h, int net);
+int sacb_tensor_info(sacb_handle h, int net, int tensor, int64_t *rows, int64_t *cols, int64_t *arena_offset);
+/* device pointer of a tensor (agent-major arenas): lets the host alias it as a torch tensor (zero copy). */
+int sacb_tensor_dev(sacb_handle h, int agent, int net, int slot, int tensor, void **dev_ptr);
+int sacb_import_tensor(sacb_handle h, int agent, int net, int slot, int tensor, const float *src, int64_t n);
+int sacb_export_tensor(sacb_handle h, int agent, int net, int slot, int tensor, float *dst, int64_t n);
+/* scalars: log_alpha + its Adam state (sac_imp.py:48-49), alpha (:23,:135), per-optimizer step counts. */
+typedef struct {
+    float log_alpha, alpha, log_alpha_m, log_alpha_v;
+    int64_t step_policy, step_q1, step_q2, step_alpha, n_updates;
+} sacb_scalars;
+int sacb_get_scalars(sacb_handle h, int agent, sacb_scalars *out);
+int sacb_set_scalars(sacb_handle h, int agent, const sacb_scalars *in);
+
+/* ---- replay: ReplayBuffer.push / PrioritizedReplayBuffer.push (replay_buffer.py:10-11, :36-46) ----------
+ * n transitions, row-major float32 (the cast of sac_imp.py:81-85 happens in the shim); done as 0/1 floats. */
+int sacb_push(sacb_handle h, int agent, const float *s, const float *a, const float *r, const float *s2,
+              const float *done, int64_t n);
+/* same, rows already packed by the caller as [s | s2 | a | r | d] padded to sacb_row_floats(): one H2D copy */
+int sacb_push_rows(sacb_handle h, int agent, const float *rows, int64_t n);
+int64_t sacb_row_floats(sacb_handle h);
+int64_t sacb_len(sacb_handle h, int agent);                     /* __len__ (replay_buffer.py:21, :89) */
+/* read back transitions by LOGICAL index (uniform: j-th oldest, deque order; PER: list position). */
+int sacb_read_transitions(sacb_handle h, int agent, const int64_t *idx, int64_t n, float *s, float *a,
+                          float *r, float *s2, float *done);
+int sacb_clear_replay(sacb_handle h, int agent);
+
+/* ReplayBuffer.sample (replay_buffer.py:13-19): gather rows idx[0..B) (logical indices drawn by the caller,
+ * e.g. random.sample(range(len), B) -- identical picks and RNG consumption to random.sample(deque, B)). */
+int sacb_sample_uniform(sacb_handle h, int agent, const int64_t *idx, int64_t B, float *s, float *a, float *r,
+                        float *s2, float *done);
+
+/* PrioritizedReplayBuffer.sample (replay_buffer.py:48-82).  u = B float64 uniforms (what
+ * np.random.random_sample(B) returns inside np.random.choice); NULL => drawn on device (Philox).
+ * Outputs may be NULL to leave results on the device for sacb_update(..., SACB_USE_LAST_SAMPLE). */
+int sacb_per_sample(sacb_handle h, int agent, const double *u, int64_t B, int64_t *idx_out, float *weights_out,
+                    float *s, float *a, float *r, float *s2, float *done);
+/* PrioritizedReplayBuffer.update_priorities (replay_buffer.py:84-87): sequential semantics, last duplicate wins. */
+int sacb_per_update(sacb_handle h, int agent, const int64_t *idx, const float *prio, int64_t B);
+/* same with prio already = float32(priority + 1e-6) computed by the caller in float64 (float64 inputs) */
+int sacb_per_update_final(sacb_handle h, int agent, const int64_t *idx, const float *prio_final, int64_t B);
+/* fused path: priorities <- |q1 - y| of the last update (extension), indices of the last sample */
+int sacb_per_update_from_td(sacb_handle h, int agent, int64_t B);
+/* test hooks: read / overwrite the priority table and the p**alpha table (float32 pow is libm dependent). */
+int sacb_per_get_priorities(sacb_handle h, int agent, float *prio, int64_t n);
+int sacb_per_set_priorities(sacb_handle h, int agent, const float *prio, const float *p_alpha_or_null, int64_t n);
+typedef struct { int64_t frame, pos, len, n_fine, n_flagged, n_exact_fallbacks; float total_f32; double cdf_last; } sacb_per_stats;
+int sacb_per_get_stats(sacb_handle h, int agent, sacb_per_stats *out);
+int sacb_per_set_frame(sacb_handle h, int agent, int64_t frame);
+
+/* ---- SAC.update_parameters (sac_imp.py:74-144) --------------------------------------------------------- */
+enum {
+    SACB_USE_LAST_SAMPLE = 1,  /* minibatch = rows chosen by the last sacb_per_sample / sacb_stage_indices */
+    SACB_NO_LOSS_READBACK = 2, /* do not sync / copy the three loss scalars (throughput mode)                 */
+    SACB_EXPORT_GRADS = 4      /* keep the critic/policy gradients in the SACB_SLOT_GRAD arena (tests)        */
+};
+/* idx: B logical indices (NULL => SACB_USE_LAST_SAMPLE or, for the uniform buffer, an on-device draw);
+ * eps_next / eps_cur: [B, act] N(0,1) draws of the two policy.sample calls (sac_imp.py:89, :116), NULL => Philox;
+ * losses_out[3] = q1_loss, q2_loss, policy_loss (sac_imp.py:140-144). */
+int sacb_update(sacb_handle h, int64_t B, const int64_t *idx, const float *eps_next, const float *eps_cur,
+                float *losses_out, uint32_t flags);
+/* update on a caller-supplied minibatch (no replay involved): test / bench entry. */
+int sacb_update_batch(sacb_handle h, int64_t B, const float *s, const float *a, const float *r, const float *s2,
+                      const float *done, const float *is_weights_or_null, const float *eps_next,
+                      const float *eps_cur, float *losses_out, float *td_abs_out_or_null, uint32_t flags);
+/* pre-stage indices for the next n_steps updates on the device (bench "inputs resident in HBM"). */
+int sacb_stage_indices(sacb_handle h, const int64_t *idx, int64_t B, int64_t n_steps);
+int sacb_get_losses(sacb_handle h, int agent, float *losses_out);
+
+/* ---- SAC.select_action (sac_imp.py:54-72) -------------------------------------------------------------- */
+int sacb_select_action(sacb_handle h, int agent, const float *obs, int evaluate, const float *eps_or_null,
+                       float *action_out);
+
+/* ---- networks as callables (QNetwork.forward, GaussianPolicy.forward / .sample) on n rows -------------- */
+int sacb_q_forward(sacb_handle h, int agent, int net, const float *s, const float *a, int64_t n, float *q_out);
+int sacb_policy_forward(sacb_handle h, int agent, const float *s, int64_t n, float *mean_out, float *log_std_out);
+
+/* ---- data-parallel mode (BASELINE.json configs[3]): gradients are exported, all-reduced by the host over
+ * NCCL (torch.distributed), then applied.  phase 0 = critics (sac_imp.py:101-113), 1 = actor+alpha (:116-135). */
+int sacb_dp_backward(sacb_handle h, int phase, int64_t B_local, int64_t B_global);
+int sacb_dp_apply(sacb_handle h, int phase);
+int sacb_dp_grad_buffer(sacb_handle h, int phase, void **dev_ptr, int64_t *n_floats);
+
+/* ---- instrumentation ---------------------------------------------------------------------------------- */
+typedef struct {
+    int64_t kernel_launches;   /* kernels of this library launched since create (graph nodes counted per replay) */
+    int32_t n_stages, n_tasks, n_tiles;    /* of the current update program */
+    int32_t grid, block, smem_bytes, sm_count;
+} sacb_stats;
+int sacb_get_stats(sacb_handle h, sacb_stats *out);
+/* time `iters` replays of the update step with CUDA events on the handle's stream; returns ms per step. */
+int sacb_time_update(sacb_handle h, int64_t B, int iters, float *ms_per_step);
+/* device time of every stage kernel of one step (STAGED mode), in microseconds; n = min(cap, n_stages). */
+int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap);
+/* standalone GEMM self-test of the tensor-core tile against the FFMA tile; returns max |diff| / max |ref|. */
+int sacb_selftest_gemm(int device, int M, int N, int K, int a_mn_major, int b_mn_major, float *rel_err_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SACB200_H */

@@ -1,0 +1,150 @@
+"""GPU parity of the replay buffers through the C ABI: bit-exact for indices, priorities and stored rows.
+Reference: replay_buffer.py:5-22 (uniform deque) and :25-90 (prioritized)."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import per_oracle as PO
+from tests.golden import cases
+from tests.test_oracle_per_golden import ulp_diff
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def hw():
+    import humanoid_walking_with_sac_b200 as hw
+    return hw
+
+
+def filled_per(hw, case, bulk):
+    tr = cases.per_transitions(case)
+    buf = hw.PrioritizedReplayBuffer(case["capacity"])
+    if bulk:
+        for lo in range(0, case["n"], 700):      # odd chunking: exercises ring wrap inside a bulk push
+            hi = min(case["n"], lo + 700)
+            buf.push_many(tr["s"][lo:hi], tr["a"][lo:hi], tr["r"][lo:hi], tr["s2"][lo:hi], tr["d"][lo:hi])
+    else:
+        for i in range(case["n"]):
+            buf.push(tr["s"][i], tr["a"][i], tr["r"][i], tr["s2"][i], bool(tr["d"][i]))
+    return buf, tr
+
+
+@pytest.mark.parametrize("name", list(cases.PER_CASES))
+def test_per_matches_reference_golden(hw, name):
+    case = cases.PER_CASES[name]
+    g = np.load(os.path.join(GOLD, f"per_{name}.npz"))
+    buf, tr = filled_per(hw, case, bulk=case["n"] > 2000)
+    assert len(buf) == min(case["n"], case["capacity"])
+    np.testing.assert_array_equal(buf.priorities, g["prio_after_push"])          # max-priority rule, :38
+    assert buf.pos == int(g["pos_after_push"])
+    m = min(case["n"], case["capacity"])
+    pri = np.zeros(case["capacity"], np.float32)
+    pri[:m] = cases.per_priorities(case)[:m]
+    pa = np.zeros(case["capacity"], np.float32)
+    pa[:m] = g["p_alpha"]                                                       # numpy's own p**alpha (ISA dependent)
+    buf.set_priorities(pri, pa)
+    k = min(case["batch"], m)
+    for call in range(case["calls"]):
+        u = PO.uniform_draws(case["seed"] * 10 + call, k)
+        s, a, r, s2, d, idx, w = buf.sample(case["batch"], u=u)
+        np.testing.assert_array_equal(idx, g["idx"][call])                       # BIT-EXACT indices
+        assert ulp_diff(w, g["weights"][call]).max() <= 16                       # two float32 pow + divide by the max
+        if call == 0:
+            np.testing.assert_array_equal(r, g["sample0/r"])
+            np.testing.assert_array_equal(s, g["sample0/s"])
+            np.testing.assert_array_equal(d, g["sample0/d"])
+    assert buf.frame == 1 + case["calls"]
+    buf.update_priorities(g["upd_idx"], torch.from_numpy(cases.per_td(case)[: g["upd_idx"].size]))
+    np.testing.assert_array_equal(buf.priorities, g["prio_after_update"])        # BIT-EXACT priorities, last duplicate wins
+    buf.push(tr["s"][0], tr["a"][0], tr["r"][0], tr["s2"][0], False)
+    np.testing.assert_array_equal(buf.priorities, g["prio_after_push2"])
+    assert buf.pos == int(g["pos_after_push2"])
+
+
+@pytest.mark.parametrize("dist,n", [("halfnormal", 100003), ("floor1pct", 250000), ("lognormal3", 1000000), ("halfnormal", 1000000), ("fresh", 1000000)])
+def test_per_bit_exact_vs_oracle_large(hw, dist, n):
+    """BASELINE.json sizes (up to 1 M): indices bit-exact against the C oracle on the same p**alpha table,
+    including the adversarial priority sets of SURVEY H6.4 that defeat a naive parallel scan."""
+    case = dict(n=n, capacity=n, batch=256, seed=31, dist=dist)
+    rng = np.random.RandomState(9)
+    buf = hw.PrioritizedReplayBuffer(n)
+    buf.push_many(rng.standard_normal((8, 2)), rng.standard_normal((8, 1)), np.zeros(8), rng.standard_normal((8, 2)), np.zeros(8))
+    lib, N = hw._native.lib(), hw._native
+    # fill the ring cheaply: only the tables matter for this test
+    rows = np.zeros((n - 8, int(lib.sacb_row_floats(buf._h))), np.float32)
+    N.check(lib.sacb_push_rows(buf._h, 0, N.ptr(rows), n - 8))
+    pri = cases.per_priorities(case)
+    pa = (pri ** np.float32(0.6)).astype(np.float32)
+    buf.set_priorities(pri, pa)
+    assert PO.pairwise_sum(pa) == pa.sum()
+    for call in range(3):
+        u = rng.random_sample(256)
+        *_, idx, w = buf.sample(256, u=u)
+        ref_idx, ref_w = PO.sample(pa, u, PO.beta(1 + call))
+        np.testing.assert_array_equal(idx, ref_idx)
+        assert ulp_diff(w, ref_w).max() <= 16
+    st = buf._stats()
+    assert st.total_f32 == pa.sum()                                              # numpy pairwise tree reproduced exactly
+    # device powf vs numpy's: documented <= 2 ulp
+    buf.set_priorities(pri)
+    *_, idx2, _ = buf.sample(256, u=u)
+    assert np.mean(idx2 == ref_idx) > 0.99
+
+
+def test_per_ambiguous_samples_take_the_exact_path(hw):
+    """u placed exactly ON cdf boundaries: the certified fast path must flag them and the sequential pass decides."""
+    n = 50000
+    case = dict(n=n, capacity=n, batch=256, seed=41, dist="floor1pct")
+    pri = cases.per_priorities(case)
+    pa = (pri ** np.float32(0.6)).astype(np.float32)
+    buf = hw.PrioritizedReplayBuffer(n)
+    lib, N = hw._native.lib(), hw._native
+    buf.push_many(np.zeros((1, 2)), np.zeros((1, 1)), np.zeros(1), np.zeros((1, 2)), np.zeros(1))
+    rows = np.zeros((n - 1, int(lib.sacb_row_floats(buf._h))), np.float32)
+    N.check(lib.sacb_push_rows(buf._h, 0, N.ptr(rows), n - 1))
+    buf.set_priorities(pri, pa)
+    _, _, _, cdf = PO.sample(pa, np.array([0.5]), 0.4, want_tables=True)
+    pick = np.random.RandomState(1).randint(0, n - 1, 256)
+    u = cdf[pick].copy()
+    u[::2] = np.nextafter(u[::2], 0.0)
+    *_, idx, _ = buf.sample(256, u=u)
+    ref_idx, _ = PO.sample(pa, u, 0.4)
+    np.testing.assert_array_equal(idx, ref_idx)
+    assert buf._stats().n_flagged > 0 and buf._stats().n_exact_fallbacks >= 1
+
+
+@pytest.mark.parametrize("name", list(cases.UNIFORM_CASES))
+def test_uniform_buffer_matches_reference_golden(hw, name):
+    case = cases.UNIFORM_CASES[name]
+    g = np.load(os.path.join(GOLD, f"uniform_{name}.npz"))
+    buf = hw.ReplayBuffer(case["capacity"])
+    for i in range(case["n"]):
+        buf.push(np.full(3, i, np.float32), np.full(2, -i, np.float32), float(i), np.full(3, i + 0.5, np.float32), i % 5 == 0)
+    assert len(buf) == int(g["len"])
+    random.seed(case["seed"])
+    for call in range(case["calls"]):
+        s, a, r, s2, d = buf.sample(case["batch"])
+        np.testing.assert_array_equal(r.astype(np.int64), g["r_ids"][call])     # same picks as random.sample(deque, k)
+        if call == 0:
+            np.testing.assert_array_equal(s, g["s"])
+            np.testing.assert_array_equal(a, g["a"])
+            np.testing.assert_array_equal(s2, g["s2"])
+            np.testing.assert_array_equal(d.astype(bool), g["d"])
+    with pytest.raises(ValueError):
+        buf.sample(len(buf) + 1)                                                 # random.sample's error
+
+
+def test_buffer_attribute_round_trip(hw):
+    buf = hw.ReplayBuffer(50)
+    for i in range(70):
+        buf.push(np.full(4, i), np.full(2, i), i, np.full(4, i + 1), i % 3 == 0)
+    dq = buf.buffer
+    assert len(dq) == 50 and dq.maxlen == 50 and dq[0][2] == 20.0 and dq[-1][2] == 69.0 and dq[1][4] is True
+    other = hw.ReplayBuffer(50)
+    other.buffer = dq
+    assert len(other) == 50 and other.buffer[7][2] == dq[7][2]

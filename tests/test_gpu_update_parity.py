@@ -1,0 +1,136 @@
+"""GPU parity of SAC.update_parameters (reference sac_imp.py:74-144) through the C ABI.
+
+Chain of evidence: live reference --(tests/golden/*.npz)--> numpy oracle (test_oracle_update_golden.py)
+and here: CUDA path vs the oracle on the same seeded inputs AND vs the golden vectors directly.
+Tolerances: fp32 (FFMA) mode 2e-4 (fp32 reassociation only); tf32 (tcgen05, fp32 accumulate) mode 1e-3 on
+losses and alpha, 4e-3 norm-wise on gradients (two tf32-rounded operands per product, ~20 chained GEMMs).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import sac_oracle_np as O
+from tests.golden import cases
+from tests.util import batch_of, make_agent, net_params, relerr
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+TOL = {"fp32": dict(loss=2e-4, grad=2e-4, adam=4e-4), "tf32": dict(loss=1e-3, grad=4e-3, adam=8e-3)}
+CASES = [c for c in cases.UPDATE_CASES if not cases.UPDATE_CASES[c].get("loose")]
+
+
+@pytest.fixture(scope="module")
+def hw():
+    import humanoid_walking_with_sac_b200 as hw
+    return hw
+
+
+def run_case(hw, name, math, launch):
+    case = cases.UPDATE_CASES[name]
+    tol = TOL[math]
+    g = np.load(os.path.join(GOLD, f"update_{name}.npz"))
+    agent, st = make_agent(hw, case, math=math, launch=launch)
+    for step in range(case["steps"]):
+        b = batch_of(case, step)
+        ref_losses, aux = O.update_parameters(st, b, return_aux=True)
+        got = agent.update_from_batch(b, eps=(b["eps_next"], b["eps_cur"]), export_grads=True)
+        for k in ("q1_loss", "q2_loss", "policy_loss"):
+            assert abs(got[k] - ref_losses[k]) <= tol["loss"] * abs(ref_losses[k]) + 1e-6, (step, k, got[k], ref_losses[k])
+        # golden (live reference) losses as well
+        np.testing.assert_allclose([got["q1_loss"], got["q2_loss"], got["policy_loss"]], g["losses"][step], rtol=2 * tol["loss"], atol=1e-6)
+        for net in ("q1", "q2", "policy"):
+            gg = agent.exported_grads(net)
+            for nm, ref in aux[f"{net}_grads"].items():
+                assert relerr(gg[nm], ref) < tol["grad"], (step, net, nm, relerr(gg[nm], ref))
+                if step == 0:
+                    gold = g[f"gradsum/{net}/{nm}"]
+                    assert abs(np.linalg.norm(gg[nm].astype(np.float64)) - gold[1]) <= 2 * tol["grad"] * gold[1] + 1e-12
+        a = agent.alpha
+        a = float(a) if not hasattr(a, "item") else float(a.item())
+        assert abs(a - st.alpha) <= 1e-5 * abs(st.alpha), (a, st.alpha)
+        np.testing.assert_allclose(a, g["alphas"][step], rtol=2e-5)
+    # post-update state: Adam moves every weight by ~lr per step whatever |g| is -> compare in units of lr
+    budget = (0.02 if math == "fp32" else 0.25) * st.lr * case["steps"] + 1e-7
+    for net in ("policy", "q1", "q2", "q1_target", "q2_target"):
+        mine = net_params(agent, net)
+        for nm, ref in getattr(st, net).items():
+            frac_bad = np.mean(np.abs(mine[nm] - ref) > budget)
+            assert frac_bad < (1e-4 if math == "fp32" else 2e-3), (net, nm, frac_bad, np.abs(mine[nm] - ref).max())
+            assert np.abs(mine[nm].ravel()[:64] - g[f"paramhead/{net}/{nm}"]).max() < 2.1 * st.lr * case["steps"]
+    for net, opt in (("policy", st.policy_opt), ("q1", st.q1_opt), ("q2", st.q2_opt)):
+        sd = getattr(agent, f"{net}_optimizer").state_dict()
+        names = list(getattr(st, net).keys())
+        for i, nm in enumerate(names):
+            assert int(sd["state"][i]["step"]) == case["steps"]
+            assert relerr(sd["state"][i]["exp_avg"].cpu().numpy(), opt.m[nm]) < tol["adam"], (net, nm)
+            assert relerr(sd["state"][i]["exp_avg_sq"].cpu().numpy(), opt.v[nm]) < 2 * tol["adam"], (net, nm)
+    return agent
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_update_fp32_staged(hw, name):
+    run_case(hw, name, "fp32", "staged")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_update_tf32_staged(hw, name):
+    run_case(hw, name, "tf32", "staged")
+
+
+@pytest.mark.parametrize("name", ["tiny_m2", "c1_bipedal_m1", "c2_humanoid_m2"])
+@pytest.mark.parametrize("math", ["fp32", "tf32"])
+def test_update_persistent_single_launch(hw, name, math):
+    """ONE cooperative launch per step (grid barriers between stages) gives the same step as the staged graph."""
+    agent = run_case(hw, name, math, "persistent")
+    assert agent.stats()["n_stages"] >= 17
+
+
+def test_persistent_equals_staged_bitwise(hw):
+    case = cases.UPDATE_CASES["c1_bipedal_m1"]
+    outs = []
+    for launch in ("staged", "persistent"):
+        agent, _ = make_agent(hw, case, math="fp32", launch=launch)
+        for step in range(2):
+            b = batch_of(case, step)
+            agent.update_from_batch(b, eps=(b["eps_next"], b["eps_cur"]))
+        outs.append({n: net_params(agent, n) for n in ("policy", "q1", "q2_target")})
+    for n in outs[0]:
+        for k in outs[0][n]:
+            np.testing.assert_array_equal(outs[0][n][k], outs[1][n][k])
+
+
+def test_saturated_case_loose(hw):
+    """|x_t| up to ~20: the reference's own fp32 result moves by 1e-2 with a 1-ulp change of tanh (oracle header)."""
+    case = cases.UPDATE_CASES["humanoid_m1_saturated"]
+    g = np.load(os.path.join(GOLD, "update_humanoid_m1_saturated.npz"))
+    agent, st = make_agent(hw, case, math="fp32")
+    b = batch_of(case, 0)
+    got = agent.update_from_batch(b, eps=(b["eps_next"], b["eps_cur"]))
+    np.testing.assert_allclose([got["q1_loss"], got["q2_loss"], got["policy_loss"]], g["losses"][0], rtol=2e-2)
+
+
+def test_per_weighted_loss_extension(hw):
+    """IS-weighted critic loss (extension H10) against the oracle's per_weights path."""
+    case = cases.UPDATE_CASES["tiny_m2"]
+    agent, st = make_agent(hw, case, math="fp32")
+    b = batch_of(case, 0)
+    w = np.random.RandomState(5).uniform(0.2, 1.0, case["batch"]).astype(np.float32)
+    ref = O.update_parameters(st, b, per_weights=w)
+    got, td = agent.update_from_batch(b, eps=(b["eps_next"], b["eps_cur"]), is_weights=w, want_td=True)
+    for k in ref:
+        assert abs(got[k] - ref[k]) <= 2e-4 * abs(ref[k]) + 1e-6
+    assert td.shape == (case["batch"],) and np.all(td >= 0)
+
+
+def test_device_eps_mode_runs_and_learns(hw):
+    """Production mode: eps drawn on the device (Philox); losses finite, critic loss decreases on a fixed batch."""
+    case = cases.UPDATE_CASES["c1_bipedal_m1"]
+    agent, _ = make_agent(hw, case, math="tf32")
+    b = batch_of(case, 0)
+    l0 = agent.update_from_batch(b)
+    for _ in range(30):
+        l1 = agent.update_from_batch(b)
+    assert np.isfinite(list(l1.values())).all()
+    assert l1["q1_loss"] < l0["q1_loss"]

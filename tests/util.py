@@ -1,0 +1,33 @@
+"""Shared helpers of the GPU parity tests: load an oracle state into the product SAC, compare tensors."""
+import numpy as np
+import torch
+
+from oracle import sac_oracle_np as O
+
+
+def relerr(a, b):
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def make_agent(hw, case, math="fp32", launch="staged", **kw):
+    """Product SAC holding exactly the numpy-seeded weights of oracle make_state(case)."""
+    hw.use_networks("model1" if case["n_hidden"] == 2 else "model2")
+    st = O.make_state(case["obs"], case["act"], case["hidden"], case["n_hidden"], seed=case["seed"],
+                      bias_scale=case.get("bias_scale", 0.0), head_scale=case.get("head_scale", 1.0),
+                      automatic_entropy_tuning=case.get("auto_entropy", True))
+    agent = hw.SAC(case["obs"], case["act"], hidden_dim=case["hidden"], device="cuda", math=math, launch=launch,
+                   automatic_entropy_tuning=case.get("auto_entropy", True), max_batch=max(case["batch"], 16),
+                   capacity=kw.pop("capacity", 4096), seed=1234, **kw)
+    for net in ("policy", "q1", "q2", "q1_target", "q2_target"):
+        getattr(agent, net).load_state_dict({k: torch.from_numpy(v.copy()) for k, v in getattr(st, net).items()})
+    return agent, st
+
+
+def batch_of(case, step):
+    return O.make_batch(case["obs"], case["act"], case["batch"], seed=case["seed"] * 100 + step)
+
+
+def net_params(agent, net):
+    return {k: v.detach().cpu().numpy() for k, v in getattr(agent, net).state_dict().items()}
