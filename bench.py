@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""SAC learner hot-path benchmark (BASELINE.json metric: SAC updates/sec, Humanoid-v5 shape, B=256; PER samples/sec).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (N=1) = BASELINE.json configs[1]: Humanoid-v5 SAC update (obs 348, act 17, 3x512 networks_model2 MLPs,
+batch 256) over a 1M-transition prioritized replay ring resident in HBM.  One STEP = what the trainer loop does
+per environment step on the learner side: prioritized sample of 256 (index draw + IS weights + gather) -> one
+full update_parameters (target, twin-critic, actor, temperature, Adam, Polyak) -> priority write-back.
+
+  value : steps/s with every input resident in HBM (uniforms / eps drawn on device), CUDA events on the
+          library's stream, no host sync inside the timed region.
+  e2e   : steps/s through the public API (`replay_buffer.push` of one fresh transition + `update_parameters(256)`
+          with host-drawn uniforms copied H2D and the three losses read back D2H every step).
+  N>1   : independent replicas (one agent per GPU, no collective: the single-agent path does not shard), weak scaling.
+  --impl reference : the CPU restatement of the reference (numpy/OpenBLAS update + C PER sampler) on the host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+OBS, ACT, HID, NH, B = 348, 17, 512, 3, 256
+CAPACITY = 1_000_000
+FLOP_PER_UPDATE = 5.382e9          # fwd + necessary bwd, B=256, C2 shapes
+WORKLOAD = "Humanoid-v5 SAC update obs348/act17/hidden512x3 (networks_model2) B=256 + 1M-transition prioritized replay"
+
+
+def synth_transitions(n, seed):
+    rng = np.random.RandomState(seed)
+    s = rng.standard_normal((n, OBS)).astype(np.float32)
+    a = rng.uniform(-0.4, 0.4, (n, ACT)).astype(np.float32)
+    r = rng.standard_normal(n).astype(np.float32)
+    s2 = rng.standard_normal((n, OBS)).astype(np.float32)
+    d = (rng.uniform(size=n) < 0.01).astype(np.float32)
+    return s, a, r, s2, d
+
+
+def synth_priorities(n, seed):
+    return (np.abs(np.random.RandomState(seed).standard_normal(n)) + 1e-6).astype(np.float32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu):
+        self.rows, self.gpu, self.proc = [], gpu, None
+
+    def __enter__(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p, "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm: CPU restatement of the reference on the host cores (the oracle; bench is allowed to time it)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_reference(steps, warmup, n_per=CAPACITY, seed=0):
+    from oracle import per_oracle as PO
+    from oracle import sac_oracle_np as O
+    st = O.make_state(OBS, ACT, HID, NH, seed=seed, head_scale=0.25)
+    pri = synth_priorities(n_per, seed)
+    pa = PO.pow_alpha(pri)
+    s, a, r, s2, d = synth_transitions(8192, seed)      # the gather source: contents do not change the arithmetic
+    rng = np.random.RandomState(seed + 1)
+
+    def step(i):
+        u = rng.random_sample(B)
+        idx, w = PO.sample(pa, u, PO.beta(1 + i))                                  # replay_buffer.py:48-68 at N = 1M
+        j = idx % 8192
+        batch = dict(s=s[j], a=a[j], r=r[j], s2=s2[j], d=d[j],
+                     eps_next=rng.standard_normal((B, ACT)).astype(np.float32), eps_cur=rng.standard_normal((B, ACT)).astype(np.float32))
+        _, aux = O.update_parameters(st, batch, return_aux=True)                    # sac_imp.py:74-144
+        td = np.abs(aux["td1"]).astype(np.float32)
+        PO.update_priorities(pri, idx, td)                                          # replay_buffer.py:84-87
+        pa[idx] = PO.pow_alpha(pri[idx])
+
+    for i in range(warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        step(warmup + i)
+    dt = time.perf_counter() - t0
+    try:
+        from threadpoolctl import threadpool_info
+        cores = max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        cores = os.cpu_count()
+    return steps / dt, dt / steps * 1e3, cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(3, min(args.steps, 60))
+    warmup = max(1, min(args.warmup, 3))
+    ups, ms, cores = cpu_reference(steps, warmup)
+    sample = f"{steps} steps of the full workload (PER sample at N=1M + update + priority write-back), {warmup} warm-up"
+    line = {"impl": "reference", "metric": "SAC updates/sec (Humanoid-v5 shape, B=256, 1M-transition PER)", "value": ups, "unit": "updates/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD, "host": "cpu"},
+            "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+def build_agent(hw, device, launch, math, seed):
+    import torch
+    hw.use_networks("model2")
+    torch.manual_seed(seed)
+    agent = hw.SAC(OBS, ACT, hidden_dim=HID, device=f"cuda:{device}", replay="per", capacity=CAPACITY, max_batch=B,
+                   math=math, launch=launch, seed=seed, per_weighted_loss=True)
+    # shrink the policy heads like the parity cases do: keeps tanh out of saturation on N(0,1) observations
+    with torch.no_grad():
+        agent.policy.mean.weight.mul_(0.25)
+        agent.policy.log_std.weight.mul_(0.25)
+    chunk = 125_000
+    s, a, r, s2, d = synth_transitions(chunk, seed)
+    for _ in range(CAPACITY // chunk):
+        agent.replay_buffer.push_many(s, a, r, s2, d)
+    agent.replay_buffer.set_priorities(synth_priorities(CAPACITY, seed))
+    return agent
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import humanoid_walking_with_sac_b200 as hw
+    N = hw._native
+    lib = N.lib()
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    agent = build_agent(hw, local, args.launch, args.math, seed=rank)
+    h = agent._h
+
+    def device_step():
+        N.check(lib.sacb_per_sample(h, 0, None, B, None, None, None, None, None, None, None))
+        N.check(lib.sacb_update(h, B, None, None, None, None, N.USE_LAST_SAMPLE | N.NO_LOSS_READBACK))
+        N.check(lib.sacb_per_update_from_td(h, 0, B))
+
+    def barrier():
+        agent.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        device_step()
+    barrier()
+    st0 = agent.stats()["kernel_launches"]
+    ms = ctypes.c_float()
+    with ClockSampler(local) as clk:
+        N.check(lib.sacb_timer_start(h))
+        for _ in range(args.steps):
+            device_step()
+        N.check(lib.sacb_timer_stop(h, ctypes.byref(ms)))
+        time.sleep(0.15)
+    barrier()
+    launches = agent.stats()["kernel_launches"] - st0
+    t = torch.tensor([ms.value], device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * args.steps / (ms_total * 1e-3)
+
+    # ---- roofline of the dominant kernel (the update program) measured live: update-only replays on the same stream
+    upd_ms = ctypes.c_float()
+    N.check(lib.sacb_time_update(h, B, max(50, args.steps), ctypes.byref(upd_ms)))
+    stage_us = (ctypes.c_float * 64)()
+    n_st = lib.sacb_time_stages(h, B, stage_us, 64)
+    per_ms = ctypes.c_float()
+    N.check(lib.sacb_timer_start(h))
+    for _ in range(args.steps):
+        N.check(lib.sacb_per_sample(h, 0, None, B, None, None, None, None, None, None, None))
+    N.check(lib.sacb_timer_stop(h, ctypes.byref(per_ms)))
+    per_call_ms = per_ms.value / args.steps
+    peaks, peak_src = measured_peaks()
+    achieved_tf = FLOP_PER_UPDATE / (upd_ms.value * 1e-3) / 1e12
+    peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+                "kernel": "sac_update_kernel (one fused update program: %d launches/step in '%s' mode)" % (1 if args.launch == "persistent" else n_st, args.launch),
+                "ms_per_launch_sum": upd_ms.value, "peak_source": peak_src + " bf16 dense, sustained (tf32 operands run at half that rate)",
+                "note": "single-agent B=256 is latency/occupancy bound (SURVEY 8d): ~20 dependent GEMM stages of <=0.3 GFLOP",
+                "stage_us": [round(float(stage_us[i]), 2) for i in range(max(0, min(n_st, 64)))],
+                "per_sample": {"ms_per_call": per_call_ms, "samples_per_s": B / (per_call_ms * 1e-3),
+                               "achieved_GBps": (3 * 4.0 * CAPACITY + B * 4 * (2 * OBS + ACT + 2)) / (per_call_ms * 1e-3) / 1e9,
+                               "peak_GBps": float(peaks.get("hbm_gbs", 6650.0)), "algorithmic_bytes": "3 passes over p_alpha (4 B x N) + B rows"}}
+
+    # ---- e2e through the public API: push one transition, update_parameters(256) with host uniforms, losses read back
+    s1, a1, r1, s21, d1 = synth_transitions(args.steps + 8, 12345 + rank)
+    row_bytes = int(lib.sacb_row_floats(h)) * 4
+    for i in range(3):
+        agent.replay_buffer.push(s1[i], a1[i], r1[i], s21[i], bool(d1[i]))
+        agent.update_parameters(B)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        agent.replay_buffer.push(s1[i], a1[i], float(r1[i]), s21[i], bool(d1[i]))
+        out = agent.update_parameters(B)
+    agent.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = world * args.steps / float(te.item())
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        ups, cms, cores = cpu_reference(steps=40, warmup=2)
+        cpu = {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port",
+               "sample": "40 steps of the full workload on the host (numpy/OpenBLAS restatement of sac_imp.py:74-144 + C restatement of replay_buffer.py:48-87 at N=1M)"}
+
+    if rank == 0:
+        line = {"metric": "SAC updates/sec (Humanoid-v5 shape, B=256, 1M-transition PER)", "value": value, "unit": "updates/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "tf32 operands / f32 accumulate" if args.math == "tf32" else "f32",
+                "data": "synthetic",
+                "config": {"workload": WORKLOAD, "launch": args.launch, "math": args.math, "replicas": world,
+                           "l2_policy": "inputs larger than L2: 1M-row ring (2.9 GB) + 4 MB priority table re-read every step; weights/Adam state (63 MB) stay L2 resident by design"},
+                "e2e": {"value": e2e, "unit": "updates/s", "h2d_bytes_per_step": row_bytes + 8 * B, "d2h_bytes_per_step": 12},
+                "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu,
+                "per_samples_per_s": B / (per_call_ms * 1e-3), "last_losses": out}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--launch", default=os.environ.get("SACB_LAUNCH", "staged"), choices=["staged", "persistent"])
+    ap.add_argument("--math", default=os.environ.get("SACB_MATH", "tf32"), choices=["tf32", "fp32"])
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -97,6 +97,8 @@ SIGNATURES = {
     "sacb_dp_apply": (I, [H, I]),
     "sacb_dp_grad_buffer": (I, [H, I, ctypes.POINTER(ctypes.c_void_p), c_i64p]),
     "sacb_get_stats": (I, [H, ctypes.POINTER(Stats)]),
+    "sacb_timer_start": (I, [H]),
+    "sacb_timer_stop": (I, [H, c_f32p]),
     "sacb_time_update": (I, [H, I64, I, c_f32p]),
     "sacb_time_stages": (I, [H, I64, c_f32p, I]),
     "sacb_selftest_gemm": (I, [I, I, I, I, I, I, c_f32p]),

@@ -327,3 +327,19 @@ extern "C" int sacb_time_update(sacb_handle h, int64_t B, int iters, float *ms_p
     *ms_per_step = ms / iters;
     return check_error_flag(h);
 }
+
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+extern "C" int sacb_timer_start(sacb_handle h) {
+    if (!h) return fail(SACB_ERR_ARG, "null handle");
+    if (!g_ev0) { SACB_CUDA(cudaEventCreate(&g_ev0)); SACB_CUDA(cudaEventCreate(&g_ev1)); }
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    SACB_CUDA(cudaEventRecord(g_ev0, h->stream));
+    return SACB_OK;
+}
+extern "C" int sacb_timer_stop(sacb_handle h, float *ms_out) {
+    if (!h || !ms_out || !g_ev0) return fail(SACB_ERR_ARG, "timer not started");
+    SACB_CUDA(cudaEventRecord(g_ev1, h->stream));
+    SACB_CUDA(cudaEventSynchronize(g_ev1));
+    SACB_CUDA(cudaEventElapsedTime(ms_out, g_ev0, g_ev1));
+    return check_error_flag(h);
+}

@@ -171,6 +171,9 @@ typedef struct {
     int32_t grid, block, smem_bytes, sm_count;
 } sacb_stats;
 int sacb_get_stats(sacb_handle h, sacb_stats *out);
+/* CUDA-event stopwatch on the handle's stream (torch.cuda.Event only sees torch's stream). */
+int sacb_timer_start(sacb_handle h);
+int sacb_timer_stop(sacb_handle h, float *ms_out);
 /* time `iters` replays of the update step with CUDA events on the handle's stream; returns ms per step. */
 int sacb_time_update(sacb_handle h, int64_t B, int iters, float *ms_per_step);
 /* device time of every stage kernel of one step (STAGED mode), in microseconds; n = min(cap, n_stages). */

@@ -4,9 +4,9 @@ set -u
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1 || { tail -20 gpurun_out/build.log; exit 1; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.log 2>&1
-timeout 300 python -m pytest tests/test_gpu_gemm.py -m gpu -x -q > gpurun_out/gemm.log 2>&1; echo "gemm rc=$?" | tee -a gpurun_out/summary.log
+timeout 300 python -X faulthandler -m pytest tests/test_gpu_gemm.py -m gpu -q -p no:cacheprovider --timeout=120 > gpurun_out/gemm.log 2>&1; echo "gemm rc=$?" | tee -a gpurun_out/summary.log
 tail -5 gpurun_out/gemm.log
-timeout 1200 python -m pytest tests -m gpu -q -x --deselect tests/test_gpu_gemm.py > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/summary.log
+timeout 1500 python -X faulthandler -m pytest tests -m gpu -q --maxfail=25 -p no:cacheprovider --timeout=300 --deselect tests/test_gpu_gemm.py > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?" | tee -a gpurun_out/summary.log
 tail -30 gpurun_out/pytest.log
 if [ -f bench.py ]; then
   timeout 600 python bench.py --steps 200 --warmup 20 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?" | tee -a gpurun_out/summary.log
