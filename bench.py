@@ -265,7 +265,7 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": "SAC updates/sec (Humanoid-v5 shape, B=256, 1M-transition PER)", "value": value, "unit": "updates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "tf32 operands / f32 accumulate" if args.math == "tf32" else "f32",
+                "scaling": "weak", "vs_baseline": None, "dtype": {"tf32x3": "f32 (error-compensated tf32 pairs on tcgen05, f32 accumulate)", "tf32": "tf32 operands / f32 accumulate", "fp32": "f32"}[args.math],
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "launch": args.launch, "math": args.math, "replicas": world,
                            "l2_policy": "inputs larger than L2: 1M-row ring (2.9 GB) + 4 MB priority table re-read every step; weights/Adam state (63 MB) stay L2 resident by design"},
@@ -284,7 +284,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--launch", default=os.environ.get("SACB_LAUNCH", "staged"), choices=["staged", "persistent"])
-    ap.add_argument("--math", default=os.environ.get("SACB_MATH", "tf32"), choices=["tf32", "fp32"])
+    ap.add_argument("--math", default=os.environ.get("SACB_MATH", "tf32x3"), choices=["tf32x3", "tf32", "fp32"])
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -133,7 +133,9 @@ constexpr int kSM = 64, kSN = 64, kSK = 16;
 // tcgen05 path: 128 x kTN output tile, K blocks of 32 fp32 (=128 B, one SWIZZLE_128B row)
 constexpr int kTM = 128, kTN = 64, kTK = 32, kTStages = 4;
 constexpr int kTcStageBytes = (kTM + kTN) * kTK * 4;              // 24 KB
-constexpr int kTcSmemBytes = kTStages * kTcStageBytes + 1024;      // + alignment slack
+constexpr int kTcXformBytes = (128 + 2048) * 4;                   // rank-1 transform vectors (gemm.cuh: xr, xk)
+__host__ __device__ constexpr int tc_smem_bytes(int split) { return kTStages * split * kTcStageBytes + kTcXformBytes + 1024; }
+constexpr int kTcSmemBytes = tc_smem_bytes(1);
 constexpr int kSimtSmemBytes = 2 * kSK * (kSM + 4) * 4;
 
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }

@@ -142,22 +142,28 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_selftest_kernel(Task t, Agen
     __shared__ uint32_t s_tmem;
     tc::TcState st;
     st.g = 0; st.accum_uses = 0; st.tmem_base = 0; st.empty_bar = s_bars; st.accum_bar = s_bars + kTStages;
+    constexpr int kSplit = kMath == SACB_MATH_TF32X3 ? 2 : 1;
+    constexpr bool kTc = kMath != SACB_MATH_FP32;
     st.tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    if (kMath == SACB_MATH_TF32) {
+    st.xr = reinterpret_cast<float *>(st.tiles + kTStages * kSplit * kTcStageBytes);
+    st.xk = st.xr + kTM;
+    if (kTc) {
         if (threadIdx.x == 0) { for (int i = 0; i <= kTStages; i++) tc::mbar_init(&s_bars[i], 1); tc::fence_barrier_init(); tc::fence_proxy_async(); }
         if (threadIdx.x < 32) tc::tmem_alloc(&s_tmem, kTN);
         tc::tc_fence_before(); __syncthreads(); tc::tc_fence_after();
         st.tmem_base = s_tmem;
     }
     for (int tile = blockIdx.x; tile < t.n_tiles; tile += gridDim.x) {
-        if (kMath == SACB_MATH_TF32) gemm_tile_tc(t, tile, bases, 0, nullptr, st, error_flag);
+        if (kTc) gemm_tile_tc<kSplit>(t, tile, bases, 0, nullptr, st, error_flag);
         else gemm_tile_ffma(t, tile, bases, 0, nullptr, reinterpret_cast<float *>(smem_raw));
     }
-    if (kMath == SACB_MATH_TF32) { tc::tc_fence_before(); __syncthreads(); if (threadIdx.x < 32) tc::tmem_dealloc(st.tmem_base, kTN); }
+    if (kTc) { tc::tc_fence_before(); __syncthreads(); if (threadIdx.x < 32) tc::tmem_dealloc(st.tmem_base, kTN); }
 }
 }  // namespace sacb
 
-extern "C" int sacb_selftest_gemm(int device, int M, int N, int K, int a_mn, int b_mn, float *rel_err_out) {
+extern "C" int sacb_selftest_gemm(int device, int M, int N, int K, int a_mn, int b_mn_and_mode, float *rel_err_out) {
+    // b_mn_and_mode: bit 0 = B operand MN-major, bit 1 = use the error-compensated 3xTF32 tile instead of plain tf32
+    const int b_mn = b_mn_and_mode & 1, x3 = (b_mn_and_mode >> 1) & 1;
     if (M < 1 || N < 1 || K < 1 || !rel_err_out) return fail(SACB_ERR_ARG, "bad argument");
     SACB_CUDA(cudaSetDevice(device));
     const int lda = a_mn ? (int)align_up(M, 4) + 4 : (int)align_up(K, 4) + 4, ldb = b_mn ? (int)align_up(N, 4) + 4 : (int)align_up(K, 4) + 4;
@@ -187,9 +193,14 @@ extern "C" int sacb_selftest_gemm(int device, int M, int N, int K, int a_mn, int
         return t;
     };
     Task t0 = mk(kSM, kSN, oc0), t1 = mk(kTM, kTN, oc1);
-    SACB_CUDA(cudaFuncSetAttribute(gemm_selftest_kernel<SACB_MATH_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
     gemm_selftest_kernel<SACB_MATH_FP32><<<t0.n_tiles, kThreads, kSimtSmemBytes>>>(t0, bases, flag);
-    gemm_selftest_kernel<SACB_MATH_TF32><<<std::min(t1.n_tiles, 148), kThreads, kTcSmemBytes>>>(t1, bases, flag);
+    if (x3) {
+        SACB_CUDA(cudaFuncSetAttribute(gemm_selftest_kernel<SACB_MATH_TF32X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(2)));
+        gemm_selftest_kernel<SACB_MATH_TF32X3><<<std::min(t1.n_tiles, 148), kThreads, tc_smem_bytes(2)>>>(t1, bases, flag);
+    } else {
+        SACB_CUDA(cudaFuncSetAttribute(gemm_selftest_kernel<SACB_MATH_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(1)));
+        gemm_selftest_kernel<SACB_MATH_TF32><<<std::min(t1.n_tiles, 148), kThreads, tc_smem_bytes(1)>>>(t1, bases, flag);
+    }
     SACB_CUDA(cudaDeviceSynchronize());
     int hf = 0;
     SACB_CUDA(cudaMemcpy(&hf, flag, sizeof(int), cudaMemcpyDeviceToHost));

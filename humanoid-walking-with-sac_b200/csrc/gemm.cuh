@@ -236,7 +236,9 @@ __device__ __forceinline__ float to_tf32(float x) {
 }
 __device__ __forceinline__ float4 to_tf32(float4 v) { return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w)); }
 
-// 4 consecutive-k values of logical row r (k = kk .. kk+3) of an operand; zero outside [0,R) x [0,K)
+// 4 consecutive-k RAW values of logical row r (k = kk .. kk+3) of an operand; zero outside [0,R) x [0,K).
+// Pure loads: nothing here consumes the data, so the loads of k-block kb+2 stay in flight while kb is stored
+// and multiplied (the rank-1 transform and the tf32 rounding happen at store time).
 __device__ __forceinline__ float4 load_chunk(const OperandR &o, bool vec_ok, int r, int R, int kk, int K) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r >= R || kk >= K) return v;
@@ -250,36 +252,25 @@ __device__ __forceinline__ float4 load_chunk(const OperandR &o, bool vec_ok, int
             if (kk + 2 < K) v.z = ldcg(src + 2);
             if (kk + 3 < K) v.w = ldcg(src + 3);
         }
-        if (o.xform) {   // storage (row, col) = (r, kk+j)
-            const float rv = ldcg(o.rvec + r);
-            v.x = v.x > 0.f ? rv * ldcg(o.cvec + kk) : 0.f;
-            v.y = (kk + 1 < K && v.y > 0.f) ? rv * ldcg(o.cvec + kk + 1) : 0.f;
-            v.z = (kk + 2 < K && v.z > 0.f) ? rv * ldcg(o.cvec + kk + 2) : 0.f;
-            v.w = (kk + 3 < K && v.w > 0.f) ? rv * ldcg(o.cvec + kk + 3) : 0.f;
-        }
     } else {
         const float *src = o.p + (int64_t)kk * o.ld + r;       // storage (row, col) = (kk+j, r): coalesced over r
         v.x = ldcg(src);
         if (kk + 1 < K) v.y = ldcg(src + o.ld);
         if (kk + 2 < K) v.z = ldcg(src + 2 * (int64_t)o.ld);
         if (kk + 3 < K) v.w = ldcg(src + 3 * (int64_t)o.ld);
-        if (o.xform) {
-            const float cv = ldcg(o.cvec + r);
-            v.x = v.x > 0.f ? ldcg(o.rvec + kk) * cv : 0.f;
-            v.y = (kk + 1 < K && v.y > 0.f) ? ldcg(o.rvec + kk + 1) * cv : 0.f;
-            v.z = (kk + 2 < K && v.z > 0.f) ? ldcg(o.rvec + kk + 2) * cv : 0.f;
-            v.w = (kk + 3 < K && v.w > 0.f) ? ldcg(o.rvec + kk + 3) * cv : 0.f;
-        }
     }
-    return to_tf32(v);
+    return v;
 }
+
+constexpr int kXkMax = 2048;     // longest K a rank-1 transformed operand may have (hidden_dim / batch)
 
 // per-CTA state that survives across tiles (persistent kernel): pipeline position and TMEM base
 struct TcState {
     uint32_t tmem_base;
     uint32_t g;            // k-blocks issued so far (stage = g % kTStages)
     uint32_t accum_uses;   // completed tiles (parity of the accumulator barrier)
-    uint8_t *tiles;        // 1024-aligned operand ring: kTStages x (A 16 KB | B 8 KB)
+    uint8_t *tiles;        // 1024-aligned operand ring: kTStages x kSplit x (A 16 KB | B 8 KB)
+    float *xr, *xk;        // rank-1 transform vectors of the current tile: by tile row [kTM], by k [kXkMax]
     uint64_t *empty_bar;   // [kTStages]
     uint64_t *accum_bar;
 };
@@ -311,22 +302,44 @@ __device__ __forceinline__ void load_kblock(Regs &rg, const OperandR &A, const O
     }
 }
 
-__device__ __forceinline__ void store_kblock(const Regs &rg, const OperandR &A, const OperandR &B, uint8_t *stage) {
+// hi = rna_tf32(x) ; lo = rna_tf32(x - hi): x = hi + lo up to 2^-22 |x|  (error-compensated "3xTF32")
+template <int kSplit>
+__device__ __forceinline__ void store_chunk(uint8_t *tile, int tile_bytes, uint32_t off, float4 v) {
+    const float4 hi = to_tf32(v);
+    *reinterpret_cast<float4 *>(tile + off) = hi;
+    if (kSplit == 2) {
+        const float4 lo = to_tf32(make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w));
+        *reinterpret_cast<float4 *>(tile + tile_bytes + off) = lo;
+    }
+}
+
+// stage layout: [A_hi 16K | B_hi 8K] (+ [A_lo | B_lo] when kSplit == 2)
+template <int kSplit>
+__device__ __forceinline__ void store_kblock(const Regs &rg, const OperandR &A, const OperandR &B, uint8_t *stage, const TcState &st, int k0) {
     const int tid = threadIdx.x;
+    constexpr int kHalf = (kTM + kTN) * kTK * 4;
 #pragma unroll
     for (int e = 0; e < kAChunks; e++) {
         int r, c; chunk_coords(A.mn_major, tid + e * kThreads, kTM, r, c);
-        *reinterpret_cast<float4 *>(stage + sw128_chunk_off(r, c)) = rg.a[e];
+        float4 v = rg.a[e];
+        if (A.xform) {      // dq[b] * w_out[n] * relu'(h[b,n]) with the two vectors staged in shared memory
+            const float xr = st.xr[r];
+            const float *xk = st.xk + k0 + 4 * c;
+            v.x = v.x > 0.f ? xr * xk[0] : 0.f; v.y = v.y > 0.f ? xr * xk[1] : 0.f;
+            v.z = v.z > 0.f ? xr * xk[2] : 0.f; v.w = v.w > 0.f ? xr * xk[3] : 0.f;
+        }
+        store_chunk<kSplit>(stage, kHalf, sw128_chunk_off(r, c), v);
     }
 #pragma unroll
     for (int e = 0; e < kBChunks; e++) {
         int r, c; chunk_coords(B.mn_major, tid + e * kThreads, kTN, r, c);
-        *reinterpret_cast<float4 *>(stage + kTM * kTK * 4 + sw128_chunk_off(r, c)) = rg.b[e];
+        store_chunk<kSplit>(stage, kHalf, kTM * kTK * 4 + sw128_chunk_off(r, c), rg.b[e]);
     }
 }
 
 }  // namespace tc
 
+template <int kSplit>
 __device__ __forceinline__ void gemm_tile_tc(const Task &t, int tile, const AgentBases &bases, int agent,
                                              const float *scalars, tc::TcState &st, int *error_flag) {
     using namespace tc;
@@ -339,17 +352,25 @@ __device__ __forceinline__ void gemm_tile_tc(const Task &t, int tile, const Agen
     const bool bvec = !B.mn_major && (B.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(B.p) & 15) == 0);
     const int nkb = cdiv(t.K, kTK);
     constexpr uint32_t idesc = make_idesc(kTM, kTN);
+    constexpr int kStageBytes = kSplit * kTcStageBytes;
+    constexpr int kHalf = kTcStageBytes;
 
     Regs r0, r1;
     load_kblock(r0, A, B, avec, bvec, m0, n0, t.M, t.N, t.K, 0);
     if (nkb > 1) load_kblock(r1, A, B, avec, bvec, m0, n0, t.M, t.N, t.K, kTK);
+    if (A.xform) {   // vectors of the rank-1 operand: one indexed by the tile row, one by k (storage row/col depend on the major)
+        const float *by_row = A.mn_major ? A.cvec : A.rvec, *by_k = A.mn_major ? A.rvec : A.cvec;
+        for (int i = tid; i < kTM; i += kThreads) st.xr[i] = (m0 + i < t.M) ? ldcg(by_row + m0 + i) : 0.f;
+        for (int i = tid; i < nkb * kTK; i += kThreads) st.xk[i] = (i < t.K) ? ldcg(by_k + i) : 0.f;
+        __syncthreads();
+    }
 
     auto step = [&](Regs &rg, int kb) {
         const uint32_t g = st.g + kb;
         const uint32_t s = g % kTStages;
-        uint8_t *stage = st.tiles + s * kTcStageBytes;
+        uint8_t *stage = st.tiles + s * kStageBytes;
         if (g >= kTStages) mbar_wait(&st.empty_bar[s], ((g / kTStages) - 1) & 1, error_flag);   // MMAs that read this slot are done
-        store_kblock(rg, A, B, stage);
+        store_kblock<kSplit>(rg, A, B, stage, st, kb * kTK);
         if (kb + 2 < nkb) load_kblock(rg, A, B, avec, bvec, m0, n0, t.M, t.N, t.K, (kb + 2) * kTK);
         fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         __syncthreads();
@@ -357,8 +378,16 @@ __device__ __forceinline__ void gemm_tile_tc(const Task &t, int tile, const Agen
             tc_fence_after();
             const uint32_t sa = smem_u32(stage), sb = sa + kTM * kTK * 4;
 #pragma unroll
-            for (int kk = 0; kk < kTK / 8; kk++)   // UMMA_K = 8 tf32 = 32 B: advance the start address inside the swizzled row
-                umma_tf32(st.tmem_base, make_desc(sa + kk * 32), make_desc(sb + kk * 32), idesc, (kb | kk) ? 1u : 0u);
+            for (int kk = 0; kk < kTK / 8; kk++) {  // UMMA_K = 8 tf32 = 32 B: advance the start address inside the swizzled row
+                const uint64_t da = make_desc(sa + kk * 32), db = make_desc(sb + kk * 32);
+                if (kSplit == 2) {   // small terms first: a_lo*b_hi + a_hi*b_lo, then a_hi*b_hi
+                    umma_tf32(st.tmem_base, make_desc(sa + kHalf + kk * 32), db, idesc, (kb | kk) ? 1u : 0u);
+                    umma_tf32(st.tmem_base, da, make_desc(sb + kHalf + kk * 32), idesc, 1u);
+                    umma_tf32(st.tmem_base, da, db, idesc, 1u);
+                } else {
+                    umma_tf32(st.tmem_base, da, db, idesc, (kb | kk) ? 1u : 0u);
+                }
+            }
             umma_commit(&st.empty_bar[s]);
             if (kb == nkb - 1) umma_commit(st.accum_bar);
         }

@@ -50,7 +50,7 @@ struct Layout {
     int64_t arena_size = 0;
     // workspace (per agent)
     int64_t X = 0, r = 0, d = 0, isw = 0, y = 0, td = 0, dq[2] = {0, 0}, dqa[2] = {0, 0}, logp = 0, eps = 0;
-    int64_t head_raw = 0, g_head = 0, da[2] = {0, 0}, wsnap[2] = {0, 0};
+    int64_t head_raw = 0, g_head = 0, da[2] = {0, 0}, wsnap[2] = {0, 0}, loss_part = 0, aloss_part = 0;
     int64_t hp[4] = {0, 0, 0, 0}, dhp[4] = {0, 0, 0, 0};                 // policy activations [2B,H] / grads [B,H]
     int64_t ht[2][4], hc[2][4], ha[2][4], dhc[2][4], dha[2][4];          // [B,H]
     int64_t ws_size = 0;
@@ -112,6 +112,10 @@ struct sacb_handle_s {
 };
 
 namespace sacb {
+inline bool math_is_tc(int m) { return m != SACB_MATH_FP32; }
+inline int math_split(int m) { return m == SACB_MATH_TF32X3 ? 2 : 1; }
+inline size_t math_smem(int m) { return math_is_tc(m) ? (size_t)tc_smem_bytes(math_split(m)) : (size_t)kSimtSmemBytes; }
+const void *update_kernel_for(int math_mode);
 // program.cu
 int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out);
 int launch_program(sacb_handle h, ProgramInst &p);

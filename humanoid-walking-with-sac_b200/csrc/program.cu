@@ -73,6 +73,7 @@ void Layout::build(int obs_, int act_, int hidden_, int n_hidden_, int maxB_) {
     head_raw = take(2 * B * 2 * A); g_head = take(B * 2 * A);
     da[0] = take(B * A); da[1] = take(B * A);
     wsnap[0] = take(H); wsnap[1] = take(H);
+    loss_part = take(2 * ((B + 7) / 8) + 8); aloss_part = take(2 * ((B + 7) / 8) + 8);
     for (int l = 0; l < n_hidden; l++) { hp[l] = take(2 * B * H); dhp[l] = take(B * H); }
     for (int k = 0; k < 2; k++)
         for (int l = 0; l < n_hidden; l++) {
@@ -108,13 +109,17 @@ sac_update_kernel(const Program P, const int stage_begin, const int stage_end, c
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint64_t s_bars[kTStages + 1];
     __shared__ uint32_t s_tmem;
-    __shared__ float s_red[2 * (kThreads / 32)];
+    __shared__ float s_red[kThreads];
 
     tc::TcState st;
     st.g = 0; st.accum_uses = 0; st.tmem_base = 0;
     st.empty_bar = s_bars; st.accum_bar = s_bars + kTStages;
+    constexpr int kSplit = kMath == SACB_MATH_TF32X3 ? 2 : 1;
+    constexpr bool kTc = kMath != SACB_MATH_FP32;
     st.tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    if (kMath == SACB_MATH_TF32 && tc_setup) {
+    st.xr = reinterpret_cast<float *>(st.tiles + kTStages * kSplit * kTcStageBytes);
+    st.xk = st.xr + kTM;
+    if (kTc && tc_setup) {
         if (threadIdx.x == 0) {
             for (int i = 0; i <= kTStages; i++) tc::mbar_init(&s_bars[i], 1);
             tc::fence_barrier_init();
@@ -140,17 +145,17 @@ sac_update_kernel(const Program P, const int stage_begin, const int stage_end, c
             float *scalars = resolve(P.scalars, P.bases, agent);
             switch (t.type) {
                 case T_GEMM:
-                    if (kMath == SACB_MATH_TF32) gemm_tile_tc(t, tile, P.bases, agent, scalars, st, P.error_flag);
+                    if (kTc) gemm_tile_tc<kSplit>(t, tile, P.bases, agent, scalars, st, P.error_flag);
                     else gemm_tile_ffma(t, tile, P.bases, agent, scalars, reinterpret_cast<float *>(smem_raw));
                     break;
                 case T_GATHER: task_gather(t, tile, P, agent); break;
                 case T_SAMPLE: task_sample(t, tile, P, agent, scalars, seed); break;
-                case T_TARGET_LOSS: task_target_loss(t, P, agent, scalars, s_red); break;
-                case T_ACTOR_LOSS: task_actor_loss(t, P, agent, scalars, s_red); break;
+                case T_TARGET_LOSS: task_target_loss(t, tile, P, agent, scalars, s_red); break;
+                case T_ACTOR_LOSS: task_actor_loss(t, tile, P, agent, scalars, s_red); break;
                 case T_SAMPLE_BWD: task_sample_bwd(t, tile, P, agent, scalars); break;
-                case T_OUT_ADAM: task_out_adam(t, tile, P, agent, scalars); break;
-                case T_BIAS_ADAM: task_bias_adam(t, tile, P, agent, scalars); break;
-                case T_FINISH: task_finish(t, scalars); break;
+                case T_OUT_ADAM: task_out_adam(t, tile, P, agent, scalars, s_red); break;
+                case T_BIAS_ADAM: task_bias_adam(t, tile, P, agent, scalars, s_red); break;
+                case T_FINISH: task_finish(t, P, agent, scalars); break;
             }
         }
         if (s + 1 < stage_end) {
@@ -159,7 +164,7 @@ sac_update_kernel(const Program P, const int stage_begin, const int stage_end, c
         }
     }
 
-    if (kMath == SACB_MATH_TF32 && tc_setup) {
+    if (kTc && tc_setup) {
         tc::tc_fence_before();
         __syncthreads();
         if (threadIdx.x < 32) tc::tmem_dealloc(st.tmem_base, kTN);
@@ -182,7 +187,7 @@ struct Builder {
     bool stage_open = false;
 
     Builder(sacb_handle h_, const ProgramKey &k) : h(h_), L(h_->L), key(k) {
-        if (h->cfg.math_mode == SACB_MATH_TF32) { tm = kTM; tn = kTN; } else { tm = kSM; tn = kSN; }
+        if (math_is_tc(h->cfg.math_mode)) { tm = kTM; tn = kTN; } else { tm = kSM; tn = kSN; }
     }
     static Ref A(int64_t off) { return make_ref(0, off); }
     static Ref W(int64_t off) { return make_ref(1, off); }
@@ -247,7 +252,7 @@ struct Builder {
         AdamArgs a = adam_args(net, b_off);
         t.p[0] = a.w; t.p[1] = a.m; t.p[2] = a.v; t.p[3] = a.wt; t.p[4] = a.gexp;
         t.i[0] = Bn; t.i[1] = N; t.i[2] = a.step_slot; t.i[3] = a.apply; t.f[0] = a.lr; t.f[1] = a.tau;
-        add(t, cdiv(N, kThreads));
+        add(t, cdiv(N, 32));
     }
 
     void build() {
@@ -305,9 +310,9 @@ struct Builder {
                 for (int k = 0; k < 4; k++) { t.p[4 + k] = A(L.param[nets[k]] + Q.w_out); t.p[8 + k] = A(L.param[nets[k]] + Q.b_out); }
                 t.p[12] = W(L.r); t.p[13] = W(L.d); t.p[14] = W(L.logp); t.p[15] = key.use_isw ? W(L.isw) : null_ref();
                 t.p[16] = W(L.y); t.p[17] = W(L.dq[0]); t.p[18] = W(L.dq[1]); t.p[19] = W(L.td);
-                t.p[20] = W(L.wsnap[0]); t.p[21] = W(L.wsnap[1]);
+                t.p[20] = W(L.wsnap[0]); t.p[21] = W(L.wsnap[1]); t.p[22] = W(L.loss_part);
                 t.i[0] = B; t.i[1] = H; t.f[0] = h->cfg.gamma;
-                add(t, 1);
+                add(t, cdiv(B, kThreads / 32));
             }
             // ---- critic backward.  dh of the last hidden layer is the implicit rank-1 operand dq * w_out * relu' ------
             //   stage s (1..nh): dX of layer l = nh-s (0-based, only while l >= 1) ; dW/db of layer l+1 ; last stage: dW/db of layer 0
@@ -337,7 +342,7 @@ struct Builder {
                         t.p[2] = aw.w; t.p[3] = aw.m; t.p[4] = aw.v; t.p[5] = aw.wt; t.p[6] = aw.gexp;
                         t.p[7] = ab.w; t.p[8] = ab.m; t.p[9] = ab.v; t.p[10] = ab.wt; t.p[11] = ab.gexp;
                         t.i[0] = B; t.i[1] = H; t.i[2] = aw.step_slot; t.i[3] = aw.apply; t.f[0] = aw.lr; t.f[1] = aw.tau;
-                        add(t, cdiv(H, kThreads));
+                        add(t, cdiv(H, 32));
                     }
                 }
             }
@@ -357,11 +362,9 @@ struct Builder {
                 t.p[0] = W(L.ha[0][nh - 1]); t.p[1] = W(L.ha[1][nh - 1]);
                 t.p[2] = A(L.param[1] + Q.w_out); t.p[3] = A(L.param[2] + Q.w_out);
                 t.p[4] = A(L.param[1] + Q.b_out); t.p[5] = A(L.param[2] + Q.b_out);
-                t.p[6] = W(L.logp + B); t.p[7] = W(L.dqa[0]); t.p[8] = W(L.dqa[1]);
-                t.p[9] = exporting() ? A(L.grad_scalars) : null_ref();
-                t.i[0] = B; t.i[1] = H; t.i[2] = h->cfg.auto_entropy; t.i[3] = apply() ? 1 : 0;
-                t.f[0] = -(float)act; t.f[1] = h->cfg.lr;
-                add(t, 1);
+                t.p[6] = W(L.logp + B); t.p[7] = W(L.dqa[0]); t.p[8] = W(L.dqa[1]); t.p[9] = W(L.aloss_part);
+                t.i[0] = B; t.i[1] = H; t.f[0] = -(float)act;
+                add(t, cdiv(B, kThreads / 32));
             }
             // ---- dL/da through both critics (input gradients only: the Q weights are constants here, quirk Q2) -------
             for (int s = 1; s <= nh; s++) {
@@ -413,10 +416,16 @@ struct Builder {
                 }
             }
         }
-        if (apply()) {   // own stage: the Adam epilogues of the previous stage still read the step counters
+        {   // own stage: the Adam epilogues of the previous stage still read the step counters
             begin_stage();
             Task t = blank(T_FINISH);
-            t.i[0] = 1; t.i[1] = 1; t.i[2] = 1; t.i[3] = h->cfg.auto_entropy;
+            const int ap = apply() ? 1 : 0;
+            t.p[0] = critics ? W(L.loss_part) : null_ref();
+            t.p[1] = actor ? W(L.aloss_part) : null_ref();
+            t.p[2] = exporting() ? A(L.grad_scalars) : null_ref();
+            t.i[0] = ap; t.i[1] = ap; t.i[2] = ap; t.i[3] = ap && h->cfg.auto_entropy; t.i[4] = ap;
+            t.i[5] = cdiv(B, kThreads / 32); t.i[6] = h->cfg.auto_entropy; t.i[7] = ap;
+            t.f[0] = h->cfg.lr; t.f[1] = (float)B;
             add(t, 1);
         }
     }
@@ -445,14 +454,14 @@ int check_error_flag(sacb_handle h) {
 }
 
 static int launch_range(sacb_handle h, ProgramInst &p, int s0, int s1, bool cooperative) {
-    const bool tf32 = h->cfg.math_mode == SACB_MATH_TF32;
+    const bool tf32 = math_is_tc(h->cfg.math_mode);
     int needs_tc = 0, max_tiles = 1;
     for (int s = s0; s < s1; s++) { needs_tc |= p.stage_has_gemm[s]; max_tiles = std::max(max_tiles, p.stages[s].n_tiles * h->cfg.n_agents); }
-    const size_t smem = tf32 ? (size_t)kTcSmemBytes : (size_t)kSimtSmemBytes;
+    const size_t smem = math_smem(h->cfg.math_mode);
     uint64_t seed = h->cfg.seed;
     int tc_setup = tf32 ? needs_tc : 0;
     void *args[] = {(void *)&p.prog, (void *)&s0, (void *)&s1, (void *)&tc_setup, (void *)&seed};
-    const void *fn = tf32 ? (const void *)sac_update_kernel<SACB_MATH_TF32> : (const void *)sac_update_kernel<SACB_MATH_FP32>;
+    const void *fn = update_kernel_for(h->cfg.math_mode);
     if (cooperative) {
         const int grid = std::min(max_tiles, h->sm_count * h->coop_blocks_per_sm);
         SACB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, h->stream));
@@ -542,13 +551,12 @@ extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap
         cudaEventRecord(ev[0], h->stream);
         for (int s = 0; s < (int)p->stages.size(); s++) {
             // force the staged form regardless of launch_mode: this is a per-stage profile
-            const bool tf32 = h->cfg.math_mode == SACB_MATH_TF32;
+            const bool tf32 = math_is_tc(h->cfg.math_mode);
             int s0 = s, s1 = s + 1, tc_setup = tf32 ? p->stage_has_gemm[s] : 0;
             uint64_t seed = h->cfg.seed;
             void *args[] = {(void *)&p->prog, (void *)&s0, (void *)&s1, (void *)&tc_setup, (void *)&seed};
-            const void *fn = tf32 ? (const void *)sac_update_kernel<SACB_MATH_TF32> : (const void *)sac_update_kernel<SACB_MATH_FP32>;
-            SACB_CUDA(cudaLaunchKernel(fn, dim3(std::max(1, p->stages[s].n_tiles * h->cfg.n_agents)), dim3(kThreads), args,
-                                       tf32 ? (size_t)kTcSmemBytes : (size_t)kSimtSmemBytes, h->stream));
+            SACB_CUDA(cudaLaunchKernel(update_kernel_for(h->cfg.math_mode), dim3(std::max(1, p->stages[s].n_tiles * h->cfg.n_agents)), dim3(kThreads), args,
+                                       math_smem(h->cfg.math_mode), h->stream));
             cudaEventRecord(ev[s + 1], h->stream);
         }
         SACB_CUDA(cudaStreamSynchronize(h->stream));
@@ -562,14 +570,19 @@ extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap
 }
 
 namespace sacb {
+const void *update_kernel_for(int m) {
+    return m == SACB_MATH_TF32X3 ? (const void *)sac_update_kernel<SACB_MATH_TF32X3>
+         : m == SACB_MATH_TF32   ? (const void *)sac_update_kernel<SACB_MATH_TF32>
+                                 : (const void *)sac_update_kernel<SACB_MATH_FP32>;
+}
 int init_kernel_attributes(sacb_handle h) {
-    SACB_CUDA(cudaFuncSetAttribute(sac_update_kernel<SACB_MATH_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
-    SACB_CUDA(cudaFuncSetAttribute(sac_update_kernel<SACB_MATH_FP32>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSimtSmemBytes));
+    const int m = h->cfg.math_mode;
+    if (m < 0 || m > SACB_MATH_TF32X3) return fail(SACB_ERR_ARG, "bad math_mode");
+    if (math_is_tc(m) && (h->cfg.hidden_dim > tc::kXkMax || h->cfg.max_batch > tc::kXkMax)) return fail(SACB_ERR_ARG, "tensor-core modes need hidden_dim, max_batch <= 2048");
+    SACB_CUDA(cudaFuncSetAttribute(update_kernel_for(m), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)math_smem(m)));
     int nb = 0;
-    const bool tf32 = h->cfg.math_mode == SACB_MATH_TF32;
-    if (tf32) SACB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sac_update_kernel<SACB_MATH_TF32>, kThreads, kTcSmemBytes));
-    else SACB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, sac_update_kernel<SACB_MATH_FP32>, kThreads, kSimtSmemBytes));
-    h->coop_blocks_per_sm = std::max(1, std::min(nb, tf32 ? 2 : 4));
+    SACB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, update_kernel_for(m), kThreads, math_smem(m)));
+    h->coop_blocks_per_sm = std::max(1, std::min(nb, math_is_tc(m) ? 2 : 4));
     return SACB_OK;
 }
 }  // namespace sacb

@@ -25,7 +25,7 @@ extern "C" void sacb_default_config(sacb_config *c) {
     c->replay_kind = SACB_REPLAY_UNIFORM; c->capacity = 1000000;                                  // replay_buffer.py:7
     c->per_alpha = 0.6f; c->per_beta_start = 0.4f; c->per_beta_frames = 100000;                   // replay_buffer.py:26
     c->max_batch = 256; c->n_agents = 1;
-    c->math_mode = SACB_MATH_TF32; c->launch_mode = SACB_LAUNCH_STAGED; c->device = 0; c->seed = 0x5ac0b200ull;
+    c->math_mode = SACB_MATH_TF32X3; c->launch_mode = SACB_LAUNCH_STAGED; c->device = 0; c->seed = 0x5ac0b200ull;
 }
 
 extern "C" int sacb_device_count(void) {
@@ -299,7 +299,7 @@ extern "C" int sacb_get_stats(sacb_handle h, sacb_stats *out) {
     memset(out, 0, sizeof(*out));
     out->kernel_launches = h->kernel_launches;
     out->sm_count = h->sm_count; out->block = kThreads;
-    out->smem_bytes = h->cfg.math_mode == SACB_MATH_TF32 ? kTcSmemBytes : kSimtSmemBytes;
+    out->smem_bytes = (int)math_smem(h->cfg.math_mode);
     for (auto &kv : h->programs) {
         out->n_stages = (int)kv.second.stages.size(); out->n_tasks = (int)kv.second.tasks.size();
         out->n_tiles = kv.second.n_tiles_total; out->grid = kv.second.max_stage_tiles;

@@ -34,8 +34,10 @@ typedef enum {
 } sacb_status;
 
 /* GEMM arithmetic of the update: */
-enum { SACB_MATH_FP32 = 0,   /* CUDA-core FFMA, fp32 in / fp32 accumulate (strict-parity mode)            */
-       SACB_MATH_TF32 = 1 }; /* tcgen05.mma kind::tf32, fp32 operands read as tf32, fp32 accumulate in TMEM */
+enum { SACB_MATH_FP32 = 0,   /* CUDA-core FFMA, fp32 in / fp32 accumulate (strict-parity mode)              */
+       SACB_MATH_TF32 = 1,   /* tcgen05.mma kind::tf32, operands rounded to tf32 once, fp32 accumulate in TMEM */
+       SACB_MATH_TF32X3 = 2  /* tcgen05.mma kind::tf32 on error-compensated operand pairs (x = hi + lo):
+                                a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32 accumulate: fp32-level accuracy (default) */ };
 
 /* how one update step is launched: */
 enum { SACB_LAUNCH_STAGED = 0,     /* one kernel per dependency stage, whole step captured in one CUDA graph */

@@ -99,7 +99,7 @@ def test_per_bit_exact_vs_oracle_large(hw, dist, n):
 def test_per_ambiguous_samples_take_the_exact_path(hw):
     """u placed exactly ON cdf boundaries: the certified fast path must flag them and the sequential pass decides."""
     n = 50000
-    case = dict(n=n, capacity=n, batch=256, seed=41, dist="floor1pct")
+    case = dict(n=n, capacity=n, batch=256, seed=41, dist="lognormal3")     # tiny probabilities: bits below 2^-52 ("fine" elements)
     pri = cases.per_priorities(case)
     pa = (pri ** np.float32(0.6)).astype(np.float32)
     buf = hw.PrioritizedReplayBuffer(n)
@@ -115,7 +115,8 @@ def test_per_ambiguous_samples_take_the_exact_path(hw):
     *_, idx, _ = buf.sample(256, u=u)
     ref_idx, _ = PO.sample(pa, u, 0.4)
     np.testing.assert_array_equal(idx, ref_idx)
-    assert buf._stats().n_flagged > 0 and buf._stats().n_exact_fallbacks >= 1
+    st = buf._stats()
+    assert st.n_fine > 0 and st.n_flagged > 0 and st.n_exact_fallbacks >= 1, (st.n_fine, st.n_flagged, st.n_exact_fallbacks)
 
 
 @pytest.mark.parametrize("name", list(cases.UNIFORM_CASES))
