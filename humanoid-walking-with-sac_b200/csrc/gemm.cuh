@@ -168,6 +168,7 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // bounded wait: a lost arrival must surface as an error, never as a hung GPU box
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int *error_flag) {
     const uint32_t addr = smem_u32(bar);
+#pragma unroll 1
     for (uint32_t it = 0; it < (1u << 22); ++it) {
         uint32_t done;
         asm volatile(
@@ -236,32 +237,6 @@ __device__ __forceinline__ float to_tf32(float x) {
 }
 __device__ __forceinline__ float4 to_tf32(float4 v) { return make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w)); }
 
-// 4 consecutive-k RAW values of logical row r (k = kk .. kk+3) of an operand; zero outside [0,R) x [0,K).
-// Pure loads: nothing here consumes the data, so the loads of k-block kb+2 stay in flight while kb is stored
-// and multiplied (the rank-1 transform and the tf32 rounding happen at store time).
-__device__ __forceinline__ float4 load_chunk(const OperandR &o, bool vec_ok, int r, int R, int kk, int K) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r >= R || kk >= K) return v;
-    if (!o.mn_major) {
-        const float *src = o.p + (int64_t)r * o.ld + kk;
-        if (vec_ok && kk + 3 < K) {
-            v = __ldcg(reinterpret_cast<const float4 *>(src));
-        } else {
-            v.x = ldcg(src);
-            if (kk + 1 < K) v.y = ldcg(src + 1);
-            if (kk + 2 < K) v.z = ldcg(src + 2);
-            if (kk + 3 < K) v.w = ldcg(src + 3);
-        }
-    } else {
-        const float *src = o.p + (int64_t)kk * o.ld + r;       // storage (row, col) = (kk+j, r): coalesced over r
-        v.x = ldcg(src);
-        if (kk + 1 < K) v.y = ldcg(src + o.ld);
-        if (kk + 2 < K) v.z = ldcg(src + 2 * (int64_t)o.ld);
-        if (kk + 3 < K) v.w = ldcg(src + 3 * (int64_t)o.ld);
-    }
-    return v;
-}
-
 constexpr int kXkMax = 2048;     // longest K a rank-1 transformed operand may have (hidden_dim / batch)
 
 // per-CTA state that survives across tiles (persistent kernel): pipeline position and TMEM base
@@ -275,114 +250,144 @@ struct TcState {
     uint64_t *accum_bar;
 };
 
+// how a thread fetches its 16-byte chunks (4 consecutive k of one operand row) from global memory
+enum FillMode { FILL_KVEC = 0,   // K contiguous, 16 B aligned rows: one LDG.128
+                FILL_KSCALAR,    // K contiguous, unaligned rows (e.g. ld = 365): 4 x LDG.32
+                FILL_MN };       // MN contiguous ([K, MN] storage): 4 x LDG.32 at stride ld, coalesced across the warp
+
 constexpr int kAChunks = kTM * (kTK / 4) / kThreads;   // 4 x 16 B per thread per k-block
 constexpr int kBChunks = kTN * (kTK / 4) / kThreads;   // 2
+
+// chunk idx -> (row r, 16-byte chunk c) of the operand tile; the mapping keeps global loads coalesced:
+// K-major: 8 consecutive threads read one row's 128 B; MN-major: 32 consecutive threads read 32 consecutive rows
+template <int MODE, int ROWS>
+__device__ __forceinline__ void chunk_rc(int idx, int &r, int &c) {
+    if (MODE == FILL_MN) { c = idx / ROWS; r = idx % ROWS; } else { r = idx >> 3; c = idx & 7; }
+}
+
+// pointer to element (row, k = 4c) of k-block 0, or nullptr when the row lies outside the operand
+template <int MODE, int ROWS>
+__device__ __forceinline__ const float *chunk_src(const OperandR &o, int idx, int row0, int R) {
+    int r, c; chunk_rc<MODE, ROWS>(idx, r, c);
+    const int row = row0 + r;
+    if (row >= R) return nullptr;
+    return (MODE == FILL_MN) ? o.p + (int64_t)(4 * c) * o.ld + row : o.p + (int64_t)row * o.ld + 4 * c;
+}
+
+// 4 consecutive-k RAW values; kvalid = how many of them lie inside [0,K) (>= 4: all).  Pure loads: nothing here
+// consumes the data, so they stay in flight while earlier k-blocks are stored and multiplied.
+template <int MODE>
+__device__ __forceinline__ float4 load_chunk(const float *src, int64_t ld, int kvalid) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (src == nullptr || kvalid <= 0) return v;
+    if (MODE == FILL_KVEC) {          // rows are 16 B aligned and ld >= roundup4(K): a straddling chunk stays inside the row
+        v = __ldcg(reinterpret_cast<const float4 *>(src));
+        if (kvalid < 4) { if (kvalid < 2) v.y = 0.f; if (kvalid < 3) v.z = 0.f; v.w = 0.f; }
+    } else {
+        const int64_t st = (MODE == FILL_MN) ? ld : 1;
+        v.x = ldcg(src);
+        if (kvalid > 1) v.y = ldcg(src + st);
+        if (kvalid > 2) v.z = ldcg(src + 2 * st);
+        if (kvalid > 3) v.w = ldcg(src + 3 * st);
+    }
+    return v;
+}
 
 struct Regs {
     float4 a[kAChunks];
     float4 b[kBChunks];
 };
 
-__device__ __forceinline__ void chunk_coords(bool mn_major, int idx, int rows, int &r, int &c) {
-    if (!mn_major) { r = idx >> 3; c = idx & 7; } else { c = idx / rows; r = idx % rows; }
-}
-
-__device__ __forceinline__ void load_kblock(Regs &rg, const OperandR &A, const OperandR &B, bool avec, bool bvec,
-                                            int m0, int n0, int M, int N, int K, int k0) {
-    const int tid = threadIdx.x;
-#pragma unroll
-    for (int e = 0; e < kAChunks; e++) {
-        int r, c; chunk_coords(A.mn_major, tid + e * kThreads, kTM, r, c);
-        rg.a[e] = load_chunk(A, avec, m0 + r, M, k0 + 4 * c, K);
-    }
-#pragma unroll
-    for (int e = 0; e < kBChunks; e++) {
-        int r, c; chunk_coords(B.mn_major, tid + e * kThreads, kTN, r, c);
-        rg.b[e] = load_chunk(B, bvec, n0 + r, N, k0 + 4 * c, K);
-    }
-}
-
 // hi = rna_tf32(x) ; lo = rna_tf32(x - hi): x = hi + lo up to 2^-22 |x|  (error-compensated "3xTF32")
+__device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
 template <int kSplit>
-__device__ __forceinline__ void store_chunk(uint8_t *tile, int tile_bytes, uint32_t off, float4 v) {
+__device__ __forceinline__ void store_chunk(uint32_t tile_saddr, uint32_t off, float4 v) {
     const float4 hi = to_tf32(v);
-    *reinterpret_cast<float4 *>(tile + off) = hi;
+    sts128(tile_saddr + off, hi);
     if (kSplit == 2) {
         const float4 lo = to_tf32(make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w));
-        *reinterpret_cast<float4 *>(tile + tile_bytes + off) = lo;
+        sts128(tile_saddr + kTcStageBytes + off, lo);
     }
 }
 
+// ---- main loop of one output tile: global -> registers (2 k-blocks ahead) -> swizzled smem -> tcgen05.mma -> TMEM ----
 // stage layout: [A_hi 16K | B_hi 8K] (+ [A_lo | B_lo] when kSplit == 2)
-template <int kSplit>
-__device__ __forceinline__ void store_kblock(const Regs &rg, const OperandR &A, const OperandR &B, uint8_t *stage, const TcState &st, int k0) {
+template <int kSplit, int AM, int BM>
+__device__ __forceinline__ void tc_mainloop(const OperandR &A, const OperandR &B, int m0, int n0, int M, int N, int K,
+                                            TcState &st, int *error_flag) {
     const int tid = threadIdx.x;
-    constexpr int kHalf = (kTM + kTN) * kTK * 4;
-#pragma unroll
-    for (int e = 0; e < kAChunks; e++) {
-        int r, c; chunk_coords(A.mn_major, tid + e * kThreads, kTM, r, c);
-        float4 v = rg.a[e];
-        if (A.xform) {      // dq[b] * w_out[n] * relu'(h[b,n]) with the two vectors staged in shared memory
-            const float xr = st.xr[r];
-            const float *xk = st.xk + k0 + 4 * c;
-            v.x = v.x > 0.f ? xr * xk[0] : 0.f; v.y = v.y > 0.f ? xr * xk[1] : 0.f;
-            v.z = v.z > 0.f ? xr * xk[2] : 0.f; v.w = v.w > 0.f ? xr * xk[3] : 0.f;
-        }
-        store_chunk<kSplit>(stage, kHalf, sw128_chunk_off(r, c), v);
-    }
-#pragma unroll
-    for (int e = 0; e < kBChunks; e++) {
-        int r, c; chunk_coords(B.mn_major, tid + e * kThreads, kTN, r, c);
-        store_chunk<kSplit>(stage, kHalf, kTM * kTK * 4 + sw128_chunk_off(r, c), rg.b[e]);
-    }
-}
-
-}  // namespace tc
-
-template <int kSplit>
-__device__ __forceinline__ void gemm_tile_tc(const Task &t, int tile, const AgentBases &bases, int agent,
-                                             const float *scalars, tc::TcState &st, int *error_flag) {
-    using namespace tc;
-    const OperandR A = resolve_operand(t.A, bases, agent), B = resolve_operand(t.B, bases, agent);
-    const EpiR epi = resolve_epilogue(t, bases, agent, scalars);
-    const int tm = tile / t.tiles_n, tn = tile % t.tiles_n;
-    const int m0 = tm * kTM, n0 = tn * kTN;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const bool avec = !A.mn_major && (A.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(A.p) & 15) == 0);
-    const bool bvec = !B.mn_major && (B.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(B.p) & 15) == 0);
-    const int nkb = cdiv(t.K, kTK);
     constexpr uint32_t idesc = make_idesc(kTM, kTN);
     constexpr int kStageBytes = kSplit * kTcStageBytes;
-    constexpr int kHalf = kTcStageBytes;
+    const int nkb = cdiv(K, kTK);
+    const int64_t lda = A.ld, ldb = B.ld;
+    const int64_t adv_a = (AM == FILL_MN) ? (int64_t)kTK * lda : kTK, adv_b = (BM == FILL_MN) ? (int64_t)kTK * ldb : kTK;
 
-    Regs r0, r1;
-    load_kblock(r0, A, B, avec, bvec, m0, n0, t.M, t.N, t.K, 0);
-    if (nkb > 1) load_kblock(r1, A, B, avec, bvec, m0, n0, t.M, t.N, t.K, kTK);
+    const float *pa[kAChunks], *pb[kBChunks];
+#pragma unroll
+    for (int e = 0; e < kAChunks; e++) pa[e] = chunk_src<AM, kTM>(A, tid + e * kThreads, m0, M);
+#pragma unroll
+    for (int e = 0; e < kBChunks; e++) pb[e] = chunk_src<BM, kTN>(B, tid + e * kThreads, n0, N);
+
     if (A.xform) {   // vectors of the rank-1 operand: one indexed by the tile row, one by k (storage row/col depend on the major)
         const float *by_row = A.mn_major ? A.cvec : A.rvec, *by_k = A.mn_major ? A.rvec : A.cvec;
-        for (int i = tid; i < kTM; i += kThreads) st.xr[i] = (m0 + i < t.M) ? ldcg(by_row + m0 + i) : 0.f;
-        for (int i = tid; i < nkb * kTK; i += kThreads) st.xk[i] = (i < t.K) ? ldcg(by_k + i) : 0.f;
+        for (int i = tid; i < kTM; i += kThreads) st.xr[i] = (m0 + i < M) ? ldcg(by_row + m0 + i) : 0.f;
+        for (int i = tid; i < nkb * kTK; i += kThreads) st.xk[i] = (i < K) ? ldcg(by_k + i) : 0.f;
         __syncthreads();
     }
 
-    auto step = [&](Regs &rg, int kb) {
+    auto load = [&](Regs &rg, int kb) {       // issues the loads of k-block kb and advances the chunk pointers
+        const int krem = K - kb * kTK;
+#pragma unroll
+        for (int e = 0; e < kAChunks; e++) {
+            int r, c; chunk_rc<AM, kTM>(tid + e * kThreads, r, c);
+            rg.a[e] = load_chunk<AM>(pa[e], lda, krem - 4 * c);
+            if (pa[e]) pa[e] += adv_a;
+        }
+#pragma unroll
+        for (int e = 0; e < kBChunks; e++) {
+            int r, c; chunk_rc<BM, kTN>(tid + e * kThreads, r, c);
+            rg.b[e] = load_chunk<BM>(pb[e], ldb, krem - 4 * c);
+            if (pb[e]) pb[e] += adv_b;
+        }
+    };
+    auto consume = [&](Regs &rg, int kb) {    // registers -> swizzled smem (+ transform, tf32 split) -> MMAs of k-block kb
         const uint32_t g = st.g + kb;
         const uint32_t s = g % kTStages;
-        uint8_t *stage = st.tiles + s * kStageBytes;
+        const uint32_t stage = smem_u32(st.tiles) + s * kStageBytes;
         if (g >= kTStages) mbar_wait(&st.empty_bar[s], ((g / kTStages) - 1) & 1, error_flag);   // MMAs that read this slot are done
-        store_kblock<kSplit>(rg, A, B, stage, st, kb * kTK);
-        if (kb + 2 < nkb) load_kblock(rg, A, B, avec, bvec, m0, n0, t.M, t.N, t.K, (kb + 2) * kTK);
+#pragma unroll
+        for (int e = 0; e < kAChunks; e++) {
+            int r, c; chunk_rc<AM, kTM>(tid + e * kThreads, r, c);
+            float4 v = rg.a[e];
+            if (A.xform) {      // dq[b] * w_out[n] * relu'(h[b,n]) with the two vectors staged in shared memory
+                const float xr = st.xr[r];
+                const float4 xk = *reinterpret_cast<const float4 *>(st.xk + kb * kTK + 4 * c);
+                v.x = v.x > 0.f ? xr * xk.x : 0.f; v.y = v.y > 0.f ? xr * xk.y : 0.f;
+                v.z = v.z > 0.f ? xr * xk.z : 0.f; v.w = v.w > 0.f ? xr * xk.w : 0.f;
+            }
+            store_chunk<kSplit>(stage, sw128_chunk_off(r, c), v);
+        }
+#pragma unroll
+        for (int e = 0; e < kBChunks; e++) {
+            int r, c; chunk_rc<BM, kTN>(tid + e * kThreads, r, c);
+            store_chunk<kSplit>(stage, kTM * kTK * 4 + sw128_chunk_off(r, c), rg.b[e]);
+        }
         fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+    };
+    auto issue = [&](int kb) {
         __syncthreads();
         if (tid == 0) {
+            const uint32_t s = (st.g + kb) % kTStages;
             tc_fence_after();
-            const uint32_t sa = smem_u32(stage), sb = sa + kTM * kTK * 4;
+            const uint32_t sa = smem_u32(st.tiles + s * kStageBytes), sb = sa + kTM * kTK * 4;
 #pragma unroll
             for (int kk = 0; kk < kTK / 8; kk++) {  // UMMA_K = 8 tf32 = 32 B: advance the start address inside the swizzled row
                 const uint64_t da = make_desc(sa + kk * 32), db = make_desc(sb + kk * 32);
                 if (kSplit == 2) {   // small terms first: a_lo*b_hi + a_hi*b_lo, then a_hi*b_hi
-                    umma_tf32(st.tmem_base, make_desc(sa + kHalf + kk * 32), db, idesc, (kb | kk) ? 1u : 0u);
-                    umma_tf32(st.tmem_base, da, make_desc(sb + kHalf + kk * 32), idesc, 1u);
+                    umma_tf32(st.tmem_base, make_desc(sa + kTcStageBytes + kk * 32), db, idesc, (kb | kk) ? 1u : 0u);
+                    umma_tf32(st.tmem_base, da, make_desc(sb + kTcStageBytes + kk * 32), idesc, 1u);
                     umma_tf32(st.tmem_base, da, db, idesc, 1u);
                 } else {
                     umma_tf32(st.tmem_base, da, db, idesc, (kb | kk) ? 1u : 0u);
@@ -392,27 +397,129 @@ __device__ __forceinline__ void gemm_tile_tc(const Task &t, int tile, const Agen
             if (kb == nkb - 1) umma_commit(st.accum_bar);
         }
     };
-    for (int kb = 0; kb < nkb; kb += 2) {
-        step(r0, kb);
-        if (kb + 1 < nkb) step(r1, kb + 1);
+
+    // two register sets, two k-blocks in flight; the first pass (it = -2) only primes the loads
+    Regs r0, r1;
+    for (int it = -2; it < nkb; it += 2) {
+        if (it >= 0) consume(r0, it);
+        if (it + 2 < nkb) load(r0, it + 2);
+        if (it >= 0) issue(it);
+        if (it + 1 >= 0 && it + 1 < nkb) consume(r1, it + 1);
+        if (it + 3 < nkb) load(r1, it + 3);
+        if (it + 1 >= 0 && it + 1 < nkb) issue(it + 1);
     }
     st.g += nkb;
+}
 
-    // ---- epilogue: TMEM -> registers -> global.  warp w owns TMEM lanes 32*(w%4).., column half w/4
+// ---- epilogue of one thread: 16 consecutive columns of one output row; loads batched ahead of any store ----
+template <int EPI>
+__device__ __forceinline__ void epilogue16(const EpiR &e, int m, int n, const float (&acc)[16]) {
+    if (m >= e.M || n >= e.N) return;
+    const bool full = n + 15 < e.N;
+    if (EPI == EPI_ADAM) {
+#pragma unroll 1
+        for (int h8 = 0; h8 < 16; h8 += 8) {        // two batches of 8 columns: loads of a batch are issued before its stores
+            const int64_t o = (int64_t)m * e.N + n + h8;
+            float w[8], mm[8], vv[8], wt[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const bool ok = (full || n + h8 + j < e.N) && e.apply;
+                w[j] = ok ? __ldcg(e.w + o + j) : 0.f;
+                mm[j] = ok ? __ldcg(e.m + o + j) : 0.f;
+                vv[j] = ok ? __ldcg(e.v + o + j) : 0.f;
+                wt[j] = (ok && e.wt) ? __ldcg(e.wt + o + j) : 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (!(full || n + h8 + j < e.N)) continue;
+                const float g = acc[h8 + j];
+                if (e.gexp) e.gexp[o + j] = g;
+                if (!e.apply) continue;
+                const float m1 = mm[j] + (1.0f - kBeta1) * (g - mm[j]);
+                const float v1 = vv[j] * kBeta2 + (1.0f - kBeta2) * g * g;
+                const float w1 = w[j] - e.step_size * (m1 / (sqrtf(v1) / e.bc2_sqrt + kAdamEps));
+                e.m[o + j] = m1; e.v[o + j] = v1; e.w[o + j] = w1;
+                if (e.wt) e.wt[o + j] = wt[j] * (1.0f - e.tau) + w1 * e.tau;
+            }
+        }
+        return;
+    }
+    float aux[16];
+    if (EPI == EPI_BIAS || EPI == EPI_BIAS_RELU) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) aux[j] = (full || n + j < e.N) ? ldcg(e.bias + n + j) : 0.f;
+    } else if (EPI == EPI_MASK) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) aux[j] = (full || n + j < e.N) ? ldcg(e.mask + (int64_t)m * e.ld_mask + n + j) : 0.f;
+    } else if (EPI == EPI_STORE) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) aux[j] = (e.accumulate && (full || n + j < e.N)) ? __ldcg(e.C + (int64_t)m * e.ldc + n + j) : 0.f;
+    }
+    float out[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        if (EPI == EPI_BIAS) out[j] = acc[j] + aux[j];
+        else if (EPI == EPI_BIAS_RELU) out[j] = fmaxf(acc[j] + aux[j], 0.f);
+        else if (EPI == EPI_MASK) out[j] = aux[j] > 0.f ? acc[j] : 0.f;
+        else out[j] = acc[j] + aux[j];
+    }
+    float *c = e.C + (int64_t)m * e.ldc + n;
+    if (full && (e.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(c) & 15) == 0)) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(c + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 16; j++) if (full || n + j < e.N) c[j] = out[j];
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void tc_epilogue(const EpiR &epi, int m0, int n0, TcState &st, int *error_flag) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     mbar_wait(st.accum_bar, st.accum_uses & 1, error_flag);
     st.accum_uses++;
     tc_fence_after();
-    const int row = (warp & 3) * 32 + lane;
+    const int row = (warp & 3) * 32 + lane;          // warp w owns TMEM lanes 32*(w%4).., column half w/4
     const int colh = (warp >> 2) * (kTN / 2);
-#pragma unroll
+#pragma unroll 1
     for (int cc = 0; cc < kTN / 2; cc += 16) {
         float v[16];
         tmem_ld16(st.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(colh + cc), v);
-#pragma unroll
-        for (int j = 0; j < 16; j++) epilogue_element(epi, m0 + row, n0 + colh + cc + j, v[j]);
+        epilogue16<EPI>(epi, m0 + row, n0 + colh + cc, v);
     }
     tc_fence_before();
     __syncthreads();     // all TMEM reads retired before the next tile's first MMA overwrites the accumulator
+}
+
+}  // namespace tc
+
+template <int kSplit>
+__device__ __forceinline__ void gemm_tile_tc(const Task &t, int tile, const AgentBases &bases, int agent,
+                                             const float *scalars, tc::TcState &st, int *error_flag) {
+    using namespace tc;
+    const int tm = tile / t.tiles_n, tn = tile % t.tiles_n;
+    const int m0 = tm * kTM, n0 = tn * kTN;
+    {
+        const OperandR A = resolve_operand(t.A, bases, agent), B = resolve_operand(t.B, bases, agent);
+        auto aligned = [](const OperandR &o) { return (o.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(o.p) & 15) == 0); };
+        // operand fetch modes that occur in the update program: activations / gradients are always 16 B aligned
+        // (K-major vector or MN-major); weights may have unaligned rows (Q fc1: ld = obs+act)
+        if (!A.mn_major) {
+            if (B.mn_major) tc_mainloop<kSplit, FILL_KVEC, FILL_MN>(A, B, m0, n0, t.M, t.N, t.K, st, error_flag);
+            else if (aligned(B)) tc_mainloop<kSplit, FILL_KVEC, FILL_KVEC>(A, B, m0, n0, t.M, t.N, t.K, st, error_flag);
+            else tc_mainloop<kSplit, FILL_KVEC, FILL_KSCALAR>(A, B, m0, n0, t.M, t.N, t.K, st, error_flag);
+        } else {
+            tc_mainloop<kSplit, FILL_MN, FILL_MN>(A, B, m0, n0, t.M, t.N, t.K, st, error_flag);
+        }
+    }
+    const EpiR epi = resolve_epilogue(t, bases, agent, scalars);
+    switch (t.epi) {
+        case EPI_STORE: tc_epilogue<EPI_STORE>(epi, m0, n0, st, error_flag); break;
+        case EPI_BIAS: tc_epilogue<EPI_BIAS>(epi, m0, n0, st, error_flag); break;
+        case EPI_BIAS_RELU: tc_epilogue<EPI_BIAS_RELU>(epi, m0, n0, st, error_flag); break;
+        case EPI_MASK: tc_epilogue<EPI_MASK>(epi, m0, n0, st, error_flag); break;
+        default: tc_epilogue<EPI_ADAM>(epi, m0, n0, st, error_flag); break;
+    }
 }
 
 }  // namespace sacb
