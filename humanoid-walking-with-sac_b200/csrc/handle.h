@@ -40,7 +40,7 @@ struct NetLayout {
 };
 
 struct Layout {
-    int obs = 0, act = 0, hidden = 0, n_hidden = 0, maxB = 0, ldx = 0;
+    int obs = 0, act = 0, hidden = 0, n_hidden = 0, maxB = 0, ldx = 0, ldg = 0;   // ldg: row stride of g_head (2A padded to 4)
     NetLayout pol, q;
     // arena (per agent): scalars | params pol,q1,q2,q1t,q2t | m pol,q1,q2 | v pol,q1,q2 | grad pol,q1,q2
     int64_t scalars = 0;

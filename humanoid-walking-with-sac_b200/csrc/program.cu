@@ -70,7 +70,7 @@ void Layout::build(int obs_, int act_, int hidden_, int n_hidden_, int maxB_) {
     r = take(B); d = take(B); isw = take(B); y = take(B); td = take(B);
     dq[0] = take(B); dq[1] = take(B); dqa[0] = take(B); dqa[1] = take(B);
     logp = take(2 * B); eps = take(2 * B * A);
-    head_raw = take(2 * B * 2 * A); g_head = take(B * 2 * A);
+    head_raw = take(2 * B * 2 * A); ldg = (int)align_up(2 * A, 4); g_head = take(B * ldg);
     da[0] = take(B * A); da[1] = take(B * A);
     wsnap[0] = take(H); wsnap[1] = take(H);
     loss_part = take(2 * ((B + 7) / 8) + 8); aloss_part = take(2 * ((B + 7) / 8) + 8);
@@ -256,7 +256,7 @@ struct Builder {
     }
 
     void build() {
-        const int B = key.B, H = L.hidden, nh = L.n_hidden, obs = L.obs, act = L.act, ldx = L.ldx, A2 = 2 * act;
+        const int B = key.B, H = L.hidden, nh = L.n_hidden, obs = L.obs, act = L.act, ldx = L.ldx, A2 = 2 * act, ldg = L.ldg;
         const NetLayout &P = L.pol, &Q = L.q;
         const Ref X2 = W(L.X), X1 = W(L.X + (int64_t)B * ldx), X3 = W(L.X + (int64_t)2 * B * ldx);
         const bool critics = key.dp_phase != 1, actor = key.dp_phase != 0;
@@ -385,7 +385,7 @@ struct Builder {
                 Task t = blank(T_SAMPLE_BWD);
                 t.p[0] = W(L.da[0]); t.p[1] = W(L.da[1]); t.p[2] = W(L.head_raw + (int64_t)B * A2); t.p[3] = W(L.eps + (int64_t)B * act);
                 t.p[4] = W(L.g_head);
-                t.i[0] = B; t.i[1] = act; t.f[0] = h->cfg.action_scale; t.f[1] = h->cfg.action_bias;
+                t.i[0] = B; t.i[1] = act; t.i[2] = ldg; t.f[0] = h->cfg.action_scale; t.f[1] = h->cfg.action_bias;
                 add(t, cdiv(B * act, kThreads));
             }
             // ---- policy backward (current-state rows B..2B of the policy activations) --------------------------------
@@ -394,7 +394,7 @@ struct Builder {
             for (int s = 0; s <= nh; s++) {
                 begin_stage();
                 if (s == 0) {
-                    gemm(op(W(L.g_head), A2, 0), op(A(L.param[0] + P.w_out), H, 1), B, H, A2,
+                    gemm(op(W(L.g_head), ldg, 0), op(A(L.param[0] + P.w_out), H, 1), B, H, A2,
                          epi_mask(W(L.dhp[nh - 1]), H, hp_cur(nh - 1), H));
                 } else {
                     const int l = nh - s;      // dh_l available; produce dh_{l-1} (if l >= 1)
@@ -402,8 +402,8 @@ struct Builder {
                         gemm(op(W(L.dhp[l]), H, 0), op(A(L.param[0] + P.w[l]), H, 1), B, H, H,
                              epi_mask(W(L.dhp[l - 1]), H, hp_cur(l - 1), H));
                     if (s == 1) {              // heads: dW = g^T h_{nh-1}
-                        gemm(op(W(L.g_head), A2, 1), op(hp_cur(nh - 1), H, 1), A2, H, B, epi_adam(0, P.w_out));
-                        bias_adam(0, P.b_out, op(W(L.g_head), A2, 0), B, A2);
+                        gemm(op(W(L.g_head), ldg, 1), op(hp_cur(nh - 1), H, 1), A2, H, B, epi_adam(0, P.w_out));
+                        bias_adam(0, P.b_out, op(W(L.g_head), ldg, 0), B, A2);
                     } else {
                         const int lw = l + 1;  // dW of the layer whose dX ran in the previous stage
                         gemm(op(W(L.dhp[lw]), H, 1), op(hp_cur(lw - 1), H, 1), H, H, B, epi_adam(0, P.w[lw]));

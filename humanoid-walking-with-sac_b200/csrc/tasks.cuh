@@ -227,8 +227,8 @@ __device__ __forceinline__ void task_actor_loss(const Task &t, int tile, const P
     __syncthreads();
 }
 
-// T_SAMPLE_BWD: p0=da1 p1=da2 [B,A] ; p2=head_raw rows of the current-state sample ; p3=eps_cur ; p4=g_head [B,2A]
-//   i0=B i1=A ; f0=scale f1=bias    (closed form of SURVEY 3.3)
+// T_SAMPLE_BWD: p0=da1 p1=da2 [B,A] ; p2=head_raw rows of the current-state sample ; p3=eps_cur ; p4=g_head [B,ldg]
+//   i0=B i1=A i2=ldg (row stride of g_head, 16 B aligned) ; f0=scale f1=bias    (closed form of SURVEY 3.3)
 __device__ __forceinline__ void task_sample_bwd(const Task &t, int tile, const Program &P, int agent, const float *scalars) {
     const int B = t.i[0], A = t.i[1];
     const int idx = tile * kThreads + threadIdx.x;
@@ -242,7 +242,7 @@ __device__ __forceinline__ void task_sample_bwd(const Task &t, int tile, const P
     const float da = ldcg(resolve(t.p[0], P.bases, agent) + idx) + ldcg(resolve(t.p[1], P.bases, agent) + idx);
     const float sc = t.f[0], omy2 = 1.f - s.y * s.y, aB = alpha / (float)B;
     const float g_u = da * sc * omy2 + aB * (2.f * sc * s.y * omy2) / (sc * omy2 + kSquashEps);
-    float *g = resolve(t.p[4], P.bases, agent) + (int64_t)b * 2 * A;
+    float *g = resolve(t.p[4], P.bases, agent) + (int64_t)b * t.i[2];
     g[a] = g_u;
     g[A + a] = (g_u * s.std * eps - aB) * s.in_range;
 }
