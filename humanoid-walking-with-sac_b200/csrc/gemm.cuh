@@ -281,8 +281,7 @@ __device__ __forceinline__ float4 load_chunk(const float *src, int64_t ld, int k
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (src == nullptr || kvalid <= 0) return v;
     if (MODE == FILL_KVEC) {          // rows are 16 B aligned and ld >= roundup4(K): a straddling chunk stays inside the row
-        v = __ldcg(reinterpret_cast<const float4 *>(src));
-        if (kvalid < 4) { if (kvalid < 2) v.y = 0.f; if (kvalid < 3) v.z = 0.f; v.w = 0.f; }
+        v = __ldcg(reinterpret_cast<const float4 *>(src));    // lanes beyond K are zeroed at consume time (never touch v here)
     } else {
         const int64_t st = (MODE == FILL_MN) ? ld : 1;
         v.x = ldcg(src);
@@ -357,10 +356,17 @@ __device__ __forceinline__ void tc_mainloop(const OperandR &A, const OperandR &B
         const uint32_t s = g % kTStages;
         const uint32_t stage = smem_u32(st.tiles) + s * kStageBytes;
         if (g >= kTStages) mbar_wait(&st.empty_bar[s], ((g / kTStages) - 1) & 1, error_flag);   // MMAs that read this slot are done
+        const int krem = K - kb * kTK;
+        const bool ktail = krem < kTK;          // last, partial k-block: vector loads may carry lanes beyond K
+        auto clip = [&](float4 &v, int c) {
+            const int kv = krem - 4 * c;
+            if (kv < 4) { if (kv < 1) v.x = 0.f; if (kv < 2) v.y = 0.f; if (kv < 3) v.z = 0.f; v.w = 0.f; }
+        };
 #pragma unroll
         for (int e = 0; e < kAChunks; e++) {
             int r, c; chunk_rc<AM, kTM>(tid + e * kThreads, r, c);
             float4 v = rg.a[e];
+            if (AM == FILL_KVEC && ktail) clip(v, c);
             if (A.xform) {      // dq[b] * w_out[n] * relu'(h[b,n]) with the two vectors staged in shared memory
                 const float xr = st.xr[r];
                 const float4 xk = *reinterpret_cast<const float4 *>(st.xk + kb * kTK + 4 * c);
@@ -372,7 +378,9 @@ __device__ __forceinline__ void tc_mainloop(const OperandR &A, const OperandR &B
 #pragma unroll
         for (int e = 0; e < kBChunks; e++) {
             int r, c; chunk_rc<BM, kTN>(tid + e * kThreads, r, c);
-            store_chunk<kSplit>(stage, kTM * kTK * 4 + sw128_chunk_off(r, c), rg.b[e]);
+            float4 v = rg.b[e];
+            if (BM == FILL_KVEC && ktail) clip(v, c);
+            store_chunk<kSplit>(stage, kTM * kTK * 4 + sw128_chunk_off(r, c), v);
         }
         fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     };

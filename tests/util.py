@@ -31,3 +31,21 @@ def batch_of(case, step):
 
 def net_params(agent, net):
     return {k: v.detach().cpu().numpy() for k, v in getattr(agent, net).state_dict().items()}
+
+
+def grad_close(got, ref, tol, max_flips=2):
+    """Gradient parity that tolerates a couple of ReLU mask flips.
+
+    A hidden unit whose pre-activation lies within rounding (~1e-6) of zero for one sample is on for one
+    summation order and off for another; the reference itself flips such units when its BLAS changes.  One flip
+    moves one row of that layer's weight gradient (and one bias entry) by O(1/B).  So: every row of the tensor must
+    match within `tol` (relative to the RMS row norm) except at most `max_flips` rows, and the whole tensor within 5e-2."""
+    got = np.asarray(got, np.float64).reshape(np.asarray(ref).shape)
+    ref = np.asarray(ref, np.float64)
+    g2, r2 = (got.reshape(got.shape[0], -1), ref.reshape(ref.shape[0], -1)) if ref.ndim == 2 and ref.shape[0] > 1 else (got.reshape(-1, 1), ref.reshape(-1, 1))
+    row_err = np.linalg.norm(g2 - r2, axis=1)
+    scale = max(np.sqrt(np.mean(np.sum(r2 * r2, axis=1))), 1e-30)
+    bad = int(np.sum(row_err > tol * scale * max(1.0, np.sqrt(r2.shape[0]) / 4)))
+    overall = relerr(got, ref)
+    ok = overall < tol or (bad <= max_flips and overall < 5e-2)
+    return ok, overall, bad

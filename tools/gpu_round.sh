@@ -12,3 +12,8 @@ if [ -f bench.py ]; then
   timeout 600 python bench.py --steps 200 --warmup 20 > gpurun_out/bench.log 2> gpurun_out/bench.err; echo "bench rc=$?" | tee -a gpurun_out/summary.log
   tail -3 gpurun_out/bench.log; tail -5 gpurun_out/bench.err
 fi
+if [ "${PROFILE:-0}" = "1" ]; then
+  rm -f gpurun_out/*.ncu-rep
+  python tools/profile_update.py tf32x3 staged 3 > gpurun_out/prof_plain.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:sac_update_kernel -s 26 -c 1 -o gpurun_out/prof_fwd python tools/profile_update.py tf32x3 staged 3 > gpurun_out/ncu1.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:sac_update_kernel -s 35 -c 1 -o gpurun_out/prof_bwd python tools/profile_update.py tf32x3 staged 3 > gpurun_out/ncu2.log 2>&1
+fi
