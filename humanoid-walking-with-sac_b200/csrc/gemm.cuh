@@ -112,7 +112,8 @@ __device__ __forceinline__ void gemm_tile_ffma(const Task &t, int tile, const Ag
     const int m0 = tm * kSM, n0 = tn * kSN;
     float(*As)[kSM + 4] = reinterpret_cast<float(*)[kSM + 4]>(smem);
     float(*Bs)[kSN + 4] = reinterpret_cast<float(*)[kSN + 4]>(smem + kSK * (kSM + 4));
-    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int tid = threadIdx.x, ty = (tid >> 4) & 15, tx = tid & 15;
+    const bool worker = tid < 256;       // 16 x 16 threads x (4 x 4) outputs; the other warps only help with the loads
     float acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; i++)
@@ -121,7 +122,7 @@ __device__ __forceinline__ void gemm_tile_ffma(const Task &t, int tile, const Ag
 
     for (int k0 = 0; k0 < t.K; k0 += kSK) {
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
+        for (int e = 0; e < kSM * kSK / kThreads; e++) {
             const int idx = tid + e * kThreads;
             int r, k;
             if (!A.mn_major) { r = idx >> 4; k = idx & 15; } else { k = idx >> 6; r = idx & 63; }
@@ -131,7 +132,7 @@ __device__ __forceinline__ void gemm_tile_ffma(const Task &t, int tile, const Ag
         }
         __syncthreads();
 #pragma unroll
-        for (int k = 0; k < kSK; k++) {
+        for (int k = 0; k < kSK && worker; k++) {
             const float4 a = *reinterpret_cast<const float4 *>(&As[k][ty * 4]);
             const float4 b = *reinterpret_cast<const float4 *>(&Bs[k][tx * 4]);
             const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
@@ -142,10 +143,12 @@ __device__ __forceinline__ void gemm_tile_ffma(const Task &t, int tile, const Ag
         }
         __syncthreads();
     }
+    if (worker) {
 #pragma unroll
-    for (int i = 0; i < 4; i++)
+        for (int i = 0; i < 4; i++)
 #pragma unroll
-        for (int j = 0; j < 4; j++) epilogue_element(epi, m0 + ty * 4 + i, n0 + tx * 4 + j, acc[i][j]);
+            for (int j = 0; j < 4; j++) epilogue_element(epi, m0 + ty * 4 + i, n0 + tx * 4 + j, acc[i][j]);
+    }
 }
 
 // ============================================================================================================
@@ -182,6 +185,11 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int *e
     return false;
 }
 
+__device__ __forceinline__ bool elect_one() {      // one lane of a converged warp
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -255,8 +263,10 @@ enum FillMode { FILL_KVEC = 0,   // K contiguous, 16 B aligned rows: one LDG.128
                 FILL_KSCALAR,    // K contiguous, unaligned rows (e.g. ld = 365): 4 x LDG.32
                 FILL_MN };       // MN contiguous ([K, MN] storage): 4 x LDG.32 at stride ld, coalesced across the warp
 
-constexpr int kAChunks = kTM * (kTK / 4) / kThreads;   // 4 x 16 B per thread per k-block
-constexpr int kBChunks = kTN * (kTK / 4) / kThreads;   // 2
+constexpr int kAChunks = kTM * (kTK / 4) / kThreads;   // 16-byte chunks per thread per k-block (2 with 512 threads)
+constexpr int kBChunks = kTN * (kTK / 4) / kThreads;   // 1
+constexpr int kDepth = 4;                              // k-blocks of global loads in flight per thread (register sets)
+static_assert(kAChunks >= 1 && kBChunks >= 1 && kDepth <= kTStages, "tile / thread geometry");
 
 // chunk idx -> (row r, 16-byte chunk c) of the operand tile; the mapping keeps global loads coalesced:
 // K-major: 8 consecutive threads read one row's 128 B; MN-major: 32 consecutive threads read 32 consecutive rows
@@ -265,30 +275,27 @@ __device__ __forceinline__ void chunk_rc(int idx, int &r, int &c) {
     if (MODE == FILL_MN) { c = idx / ROWS; r = idx % ROWS; } else { r = idx >> 3; c = idx & 7; }
 }
 
-// pointer to element (row, k = 4c) of k-block 0, or nullptr when the row lies outside the operand
-template <int MODE, int ROWS>
-__device__ __forceinline__ const float *chunk_src(const OperandR &o, int idx, int row0, int R) {
-    int r, c; chunk_rc<MODE, ROWS>(idx, r, c);
-    const int row = row0 + r;
-    if (row >= R) return nullptr;
-    return (MODE == FILL_MN) ? o.p + (int64_t)(4 * c) * o.ld + row : o.p + (int64_t)row * o.ld + 4 * c;
-}
-
-// 4 consecutive-k RAW values; kvalid = how many of them lie inside [0,K) (>= 4: all).  Pure loads: nothing here
-// consumes the data, so they stay in flight while earlier k-blocks are stored and multiplied.
+// full k-block: pure loads -- nothing may consume the data here, or the loads stop overlapping the MMAs
 template <int MODE>
-__device__ __forceinline__ float4 load_chunk(const float *src, int64_t ld, int kvalid) {
+__device__ __forceinline__ float4 load_full(const float *src, int64_t ld) {
+    float4 v;
+    if (MODE == FILL_KVEC) v = __ldcg(reinterpret_cast<const float4 *>(src));
+    else if (MODE == FILL_KSCALAR) { v.x = ldcg(src); v.y = ldcg(src + 1); v.z = ldcg(src + 2); v.w = ldcg(src + 3); }
+    else { v.x = ldcg(src); v.y = ldcg(src + ld); v.z = ldcg(src + 2 * ld); v.w = ldcg(src + 3 * ld); }
+    return v;
+}
+// last, partial k-block: kv = number of the chunk's 4 values that lie inside [0,K).  A K-major vector chunk is read whole
+// (rows are 16 B aligned and ld >= roundup4(K)); its lanes beyond K are cleared at consume time.
+template <int MODE>
+__device__ __forceinline__ float4 load_tail(const float *src, int64_t ld, int kv) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (src == nullptr || kvalid <= 0) return v;
-    if (MODE == FILL_KVEC) {          // rows are 16 B aligned and ld >= roundup4(K): a straddling chunk stays inside the row
-        v = __ldcg(reinterpret_cast<const float4 *>(src));    // lanes beyond K are zeroed at consume time (never touch v here)
-    } else {
-        const int64_t st = (MODE == FILL_MN) ? ld : 1;
-        v.x = ldcg(src);
-        if (kvalid > 1) v.y = ldcg(src + st);
-        if (kvalid > 2) v.z = ldcg(src + 2 * st);
-        if (kvalid > 3) v.w = ldcg(src + 3 * st);
-    }
+    if (kv <= 0) return v;
+    if (MODE == FILL_KVEC) return __ldcg(reinterpret_cast<const float4 *>(src));
+    const int64_t st = (MODE == FILL_MN) ? ld : 1;
+    v.x = ldcg(src);
+    if (kv > 1) v.y = ldcg(src + st);
+    if (kv > 2) v.z = ldcg(src + 2 * st);
+    if (kv > 3) v.w = ldcg(src + 3 * st);
     return v;
 }
 
@@ -297,105 +304,112 @@ struct Regs {
     float4 b[kBChunks];
 };
 
-// hi = rna_tf32(x) ; lo = rna_tf32(x - hi): x = hi + lo up to 2^-22 |x|  (error-compensated "3xTF32")
 __device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
+// error-compensated "3xTF32": hi = x with the 13 low mantissa bits cleared (exactly what the tensor core would read),
+// lo = x - hi (exact in fp32, |lo| < 2^-10 |x|; the tensor core reads its top 11 bits) => x = hi + lo up to 2^-20 |x|.
+// Single-pass mode stores x as is (the MMA ignores the low 13 bits).
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 template <int kSplit>
-__device__ __forceinline__ void store_chunk(uint32_t tile_saddr, uint32_t off, float4 v) {
-    const float4 hi = to_tf32(v);
-    sts128(tile_saddr + off, hi);
+__device__ __forceinline__ void store_chunk(uint32_t saddr, float4 v) {
     if (kSplit == 2) {
-        const float4 lo = to_tf32(make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w));
-        sts128(tile_saddr + kTcStageBytes + off, lo);
+        const float4 hi = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+        sts128(saddr, hi);
+        sts128(saddr + kTcStageBytes, make_float4(v.x - hi.x, v.y - hi.y, v.z - hi.z, v.w - hi.w));
+    } else {
+        sts128(saddr, v);
     }
 }
 
-// ---- main loop of one output tile: global -> registers (2 k-blocks ahead) -> swizzled smem -> tcgen05.mma -> TMEM ----
-// stage layout: [A_hi 16K | B_hi 8K] (+ [A_lo | B_lo] when kSplit == 2)
-template <int kSplit, int AM, int BM>
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+
+// ---- main loop of one output tile: global -> registers (kDepth k-blocks ahead) -> swizzled smem -> tcgen05.mma -> TMEM
+// stage layout: [A_hi 16K | B_hi 8K] (+ [A_lo | B_lo] when kSplit == 2).  XF: operand A carries the rank-1 transform.
+// The steady-state loop only sees full k-blocks; a partial last k-block (K % 32 != 0) is handled once, after it.
+template <int kSplit, int AM, int BM, bool XF>
 __device__ __forceinline__ void tc_mainloop(const OperandR &A, const OperandR &B, int m0, int n0, int M, int N, int K,
                                             TcState &st, int *error_flag) {
     const int tid = threadIdx.x;
     constexpr uint32_t idesc = make_idesc(kTM, kTN);
     constexpr int kStageBytes = kSplit * kTcStageBytes;
-    const int nkb = cdiv(K, kTK);
+    const int nfull = K / kTK, krem = K - nfull * kTK, nkb = nfull + (krem ? 1 : 0);
     const int64_t lda = A.ld, ldb = B.ld;
     const int64_t adv_a = (AM == FILL_MN) ? (int64_t)kTK * lda : kTK, adv_b = (BM == FILL_MN) ? (int64_t)kTK * ldb : kTK;
+    const uint32_t tiles = smem_u32(st.tiles), xk_s = smem_u32(st.xk);
+    const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform: keeps the MMA operands in uniform registers
+    const uint32_t g0 = st.g;
 
+    // loop-invariant per-chunk state: source pointer (a row outside the operand is never dereferenced), smem offset
     const float *pa[kAChunks], *pb[kBChunks];
+    uint32_t sa[kAChunks], sb[kBChunks];
+    int ca[kAChunks], cb[kBChunks];
+    bool va[kAChunks], vb[kBChunks];
+    float xr[kAChunks];
 #pragma unroll
-    for (int e = 0; e < kAChunks; e++) pa[e] = chunk_src<AM, kTM>(A, tid + e * kThreads, m0, M);
+    for (int e = 0; e < kAChunks; e++) {
+        int r; chunk_rc<AM, kTM>(tid + e * kThreads, r, ca[e]);
+        va[e] = m0 + r < M;
+        pa[e] = (AM == FILL_MN) ? A.p + (int64_t)(4 * ca[e]) * lda + (m0 + r) : A.p + (int64_t)(m0 + r) * lda + 4 * ca[e];
+        sa[e] = sw128_chunk_off(r, ca[e]);
+        xr[e] = 0.f;
+        if (XF) xr[e] = va[e] ? ldcg((A.mn_major ? A.cvec : A.rvec) + m0 + r) : 0.f;    // vector indexed by the tile row
+    }
 #pragma unroll
-    for (int e = 0; e < kBChunks; e++) pb[e] = chunk_src<BM, kTN>(B, tid + e * kThreads, n0, N);
-
-    if (A.xform) {   // vectors of the rank-1 operand: one indexed by the tile row, one by k (storage row/col depend on the major)
-        const float *by_row = A.mn_major ? A.cvec : A.rvec, *by_k = A.mn_major ? A.rvec : A.cvec;
-        for (int i = tid; i < kTM; i += kThreads) st.xr[i] = (m0 + i < M) ? ldcg(by_row + m0 + i) : 0.f;
+    for (int e = 0; e < kBChunks; e++) {
+        int r; chunk_rc<BM, kTN>(tid + e * kThreads, r, cb[e]);
+        vb[e] = n0 + r < N;
+        pb[e] = (BM == FILL_MN) ? B.p + (int64_t)(4 * cb[e]) * ldb + (n0 + r) : B.p + (int64_t)(n0 + r) * ldb + 4 * cb[e];
+        sb[e] = kTM * kTK * 4 + sw128_chunk_off(r, cb[e]);
+    }
+    if (XF) {   // vector indexed by k, staged once per tile
+        const float *by_k = A.mn_major ? A.rvec : A.cvec;
         for (int i = tid; i < nkb * kTK; i += kThreads) st.xk[i] = (i < K) ? ldcg(by_k + i) : 0.f;
         __syncthreads();
     }
 
-    auto load = [&](Regs &rg, int kb) {       // issues the loads of k-block kb and advances the chunk pointers
-        const int krem = K - kb * kTK;
+    auto load_next = [&](Regs &rg) {       // pure loads of the next full k-block (chunk pointers advance by one k-block)
 #pragma unroll
-        for (int e = 0; e < kAChunks; e++) {
-            int r, c; chunk_rc<AM, kTM>(tid + e * kThreads, r, c);
-            rg.a[e] = load_chunk<AM>(pa[e], lda, krem - 4 * c);
-            if (pa[e]) pa[e] += adv_a;
-        }
+        for (int e = 0; e < kAChunks; e++) { rg.a[e] = va[e] ? load_full<AM>(pa[e], lda) : make_float4(0.f, 0.f, 0.f, 0.f); pa[e] += adv_a; }
 #pragma unroll
-        for (int e = 0; e < kBChunks; e++) {
-            int r, c; chunk_rc<BM, kTN>(tid + e * kThreads, r, c);
-            rg.b[e] = load_chunk<BM>(pb[e], ldb, krem - 4 * c);
-            if (pb[e]) pb[e] += adv_b;
-        }
+        for (int e = 0; e < kBChunks; e++) { rg.b[e] = vb[e] ? load_full<BM>(pb[e], ldb) : make_float4(0.f, 0.f, 0.f, 0.f); pb[e] += adv_b; }
     };
-    auto consume = [&](Regs &rg, int kb) {    // registers -> swizzled smem (+ transform, tf32 split) -> MMAs of k-block kb
-        const uint32_t g = st.g + kb;
+    auto consume = [&](const Regs &rg, int kb) {    // registers -> (transform, tf32 split) -> swizzled smem
+        const uint32_t g = g0 + kb;
         const uint32_t s = g % kTStages;
-        const uint32_t stage = smem_u32(st.tiles) + s * kStageBytes;
+        const uint32_t stage = tiles + s * kStageBytes;
         if (g >= kTStages) mbar_wait(&st.empty_bar[s], ((g / kTStages) - 1) & 1, error_flag);   // MMAs that read this slot are done
-        const int krem = K - kb * kTK;
-        const bool ktail = krem < kTK;          // last, partial k-block: vector loads may carry lanes beyond K
-        auto clip = [&](float4 &v, int c) {
-            const int kv = krem - 4 * c;
-            if (kv < 4) { if (kv < 1) v.x = 0.f; if (kv < 2) v.y = 0.f; if (kv < 3) v.z = 0.f; v.w = 0.f; }
-        };
 #pragma unroll
         for (int e = 0; e < kAChunks; e++) {
-            int r, c; chunk_rc<AM, kTM>(tid + e * kThreads, r, c);
             float4 v = rg.a[e];
-            if (AM == FILL_KVEC && ktail) clip(v, c);
-            if (A.xform) {      // dq[b] * w_out[n] * relu'(h[b,n]) with the two vectors staged in shared memory
-                const float xr = st.xr[r];
-                const float4 xk = *reinterpret_cast<const float4 *>(st.xk + kb * kTK + 4 * c);
-                v.x = v.x > 0.f ? xr * xk.x : 0.f; v.y = v.y > 0.f ? xr * xk.y : 0.f;
-                v.z = v.z > 0.f ? xr * xk.z : 0.f; v.w = v.w > 0.f ? xr * xk.w : 0.f;
+            if (XF) {      // dq[b] * w_out[n] * relu'(h[b,n]): row factor in a register, k factors in shared memory
+                const float4 xk = lds128(xk_s + (kb * kTK + 4 * ca[e]) * 4);
+                v.x = v.x > 0.f ? xr[e] * xk.x : 0.f; v.y = v.y > 0.f ? xr[e] * xk.y : 0.f;
+                v.z = v.z > 0.f ? xr[e] * xk.z : 0.f; v.w = v.w > 0.f ? xr[e] * xk.w : 0.f;
             }
-            store_chunk<kSplit>(stage, sw128_chunk_off(r, c), v);
+            store_chunk<kSplit>(stage + sa[e], v);
         }
 #pragma unroll
-        for (int e = 0; e < kBChunks; e++) {
-            int r, c; chunk_rc<BM, kTN>(tid + e * kThreads, r, c);
-            float4 v = rg.b[e];
-            if (BM == FILL_KVEC && ktail) clip(v, c);
-            store_chunk<kSplit>(stage, kTM * kTK * 4 + sw128_chunk_off(r, c), v);
-        }
+        for (int e = 0; e < kBChunks; e++) store_chunk<kSplit>(stage + sb[e], rg.b[e]);
         fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
     };
-    auto issue = [&](int kb) {
+    auto issue = [&](int kb) {             // all smem writes of k-block kb done -> one elected lane issues its MMAs
         __syncthreads();
-        if (tid == 0) {
-            const uint32_t s = (st.g + kb) % kTStages;
+        if (warp_u == 0 && elect_one()) {
+            const uint32_t s = (g0 + kb) % kTStages;
             tc_fence_after();
-            const uint32_t sa = smem_u32(st.tiles + s * kStageBytes), sb = sa + kTM * kTK * 4;
+            const uint64_t d0 = make_desc(tiles + s * kStageBytes);        // A_hi of this stage; the others are constant offsets
+            constexpr uint64_t kB = (kTM * kTK * 4) >> 4, kLo = kTcStageBytes >> 4;
 #pragma unroll
             for (int kk = 0; kk < kTK / 8; kk++) {  // UMMA_K = 8 tf32 = 32 B: advance the start address inside the swizzled row
-                const uint64_t da = make_desc(sa + kk * 32), db = make_desc(sb + kk * 32);
+                const uint64_t da = d0 + 2 * kk, db = d0 + kB + 2 * kk;
                 if (kSplit == 2) {   // small terms first: a_lo*b_hi + a_hi*b_lo, then a_hi*b_hi
-                    umma_tf32(st.tmem_base, make_desc(sa + kTcStageBytes + kk * 32), db, idesc, (kb | kk) ? 1u : 0u);
-                    umma_tf32(st.tmem_base, da, make_desc(sb + kTcStageBytes + kk * 32), idesc, 1u);
+                    umma_tf32(st.tmem_base, da + kLo, db, idesc, (kb | kk) ? 1u : 0u);
+                    umma_tf32(st.tmem_base, da, db + kLo, idesc, 1u);
                     umma_tf32(st.tmem_base, da, db, idesc, 1u);
                 } else {
                     umma_tf32(st.tmem_base, da, db, idesc, (kb | kk) ? 1u : 0u);
@@ -406,15 +420,43 @@ __device__ __forceinline__ void tc_mainloop(const OperandR &A, const OperandR &B
         }
     };
 
-    // two register sets, two k-blocks in flight; the first pass (it = -2) only primes the loads
-    Regs r0, r1;
-    for (int it = -2; it < nkb; it += 2) {
-        if (it >= 0) consume(r0, it);
-        if (it + 2 < nkb) load(r0, it + 2);
-        if (it >= 0) issue(it);
-        if (it + 1 >= 0 && it + 1 < nkb) consume(r1, it + 1);
-        if (it + 3 < nkb) load(r1, it + 3);
-        if (it + 1 >= 0 && it + 1 < nkb) issue(it + 1);
+    // kDepth (= 4) named register sets = 4 k-blocks of loads in flight (named, not an array: keeps them in registers)
+    Regs r0, r1, r2, r3;
+    if (0 < nfull) load_next(r0);
+    if (1 < nfull) load_next(r1);
+    if (2 < nfull) load_next(r2);
+    if (3 < nfull) load_next(r3);
+#define SACB_KBLOCK(R, KB)                                   \
+    if ((KB) < nfull) {                                      \
+        consume(R, (KB));                                    \
+        if ((KB) + kDepth < nfull) load_next(R);             \
+        issue((KB));                                         \
+    }
+    for (int kb0 = 0; kb0 < nfull; kb0 += kDepth) {
+        SACB_KBLOCK(r0, kb0)
+        SACB_KBLOCK(r1, kb0 + 1)
+        SACB_KBLOCK(r2, kb0 + 2)
+        SACB_KBLOCK(r3, kb0 + 3)
+    }
+#undef SACB_KBLOCK
+    if (krem) {     // partial last k-block: guarded loads, lanes beyond K cleared, no prefetch (one exposed latency per tile)
+        Regs t;
+#pragma unroll
+        for (int e = 0; e < kAChunks; e++) {
+            const int kv = krem - 4 * ca[e];
+            float4 v = va[e] ? load_tail<AM>(pa[e], lda, kv) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kv < 4) { if (kv < 1) v.x = 0.f; if (kv < 2) v.y = 0.f; if (kv < 3) v.z = 0.f; v.w = 0.f; }
+            t.a[e] = v;
+        }
+#pragma unroll
+        for (int e = 0; e < kBChunks; e++) {
+            const int kv = krem - 4 * cb[e];
+            float4 v = vb[e] ? load_tail<BM>(pb[e], ldb, kv) : make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kv < 4) { if (kv < 1) v.x = 0.f; if (kv < 2) v.y = 0.f; if (kv < 3) v.z = 0.f; v.w = 0.f; }
+            t.b[e] = v;
+        }
+        consume(t, nfull);
+        issue(nfull);
     }
     st.g += nkb;
 }
@@ -487,10 +529,11 @@ __device__ __forceinline__ void tc_epilogue(const EpiR &epi, int m0, int n0, TcS
     mbar_wait(st.accum_bar, st.accum_uses & 1, error_flag);
     st.accum_uses++;
     tc_fence_after();
-    const int row = (warp & 3) * 32 + lane;          // warp w owns TMEM lanes 32*(w%4).., column half w/4
-    const int colh = (warp >> 2) * (kTN / 2);
+    const int row = (warp & 3) * 32 + lane;          // warp w owns TMEM lanes 32*(w%4).., column group w/4
+    constexpr int kColsPerWarp = kTN / (kThreads / 128);
+    const int colh = (warp >> 2) * kColsPerWarp;
 #pragma unroll 1
-    for (int cc = 0; cc < kTN / 2; cc += 16) {
+    for (int cc = 0; cc < kColsPerWarp; cc += 16) {
         float v[16];
         tmem_ld16(st.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(colh + cc), v);
         epilogue16<EPI>(epi, m0 + row, n0 + colh + cc, v);
@@ -509,16 +552,18 @@ __device__ __forceinline__ void gemm_tile_tc(const Task &t, int tile, const Agen
     const int m0 = tm * kTM, n0 = tn * kTN;
     {
         const OperandR A = resolve_operand(t.A, bases, agent), B = resolve_operand(t.B, bases, agent);
-        auto aligned = [](const OperandR &o) { return (o.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(o.p) & 15) == 0); };
-        // operand fetch modes that occur in the update program: activations / gradients are always 16 B aligned
-        // (K-major vector or MN-major); weights may have unaligned rows (Q fc1: ld = obs+act)
+        const bool b_aligned = (B.ld % 4 == 0) && ((reinterpret_cast<uintptr_t>(B.p) & 15) == 0);
+        // operand fetch modes that occur in the update program (the builder keeps every K-major A operand 16 B aligned;
+        // weights as the K-major B operand may have unaligned rows, e.g. Q fc1 with ld = obs+act)
+#define SACB_ML(AM_, BM_, XF_) tc_mainloop<kSplit, AM_, BM_, XF_>(A, B, m0, n0, t.M, t.N, t.K, st, error_flag)
         if (!A.mn_major) {
-            if (B.mn_major) tc_mainloop<kSplit, FILL_KVEC, FILL_MN>(A, B, m0, n0, t.M, t.N, t.K, st, error_flag);
-            else if (aligned(B)) tc_mainloop<kSplit, FILL_KVEC, FILL_KVEC>(A, B, m0, n0, t.M, t.N, t.K, st, error_flag);
-            else tc_mainloop<kSplit, FILL_KVEC, FILL_KSCALAR>(A, B, m0, n0, t.M, t.N, t.K, st, error_flag);
+            if (B.mn_major) { if (A.xform) SACB_ML(FILL_KVEC, FILL_MN, true); else SACB_ML(FILL_KVEC, FILL_MN, false); }
+            else if (b_aligned) SACB_ML(FILL_KVEC, FILL_KVEC, false);
+            else SACB_ML(FILL_KVEC, FILL_KSCALAR, false);
         } else {
-            tc_mainloop<kSplit, FILL_MN, FILL_MN>(A, B, m0, n0, t.M, t.N, t.K, st, error_flag);
+            if (A.xform) SACB_ML(FILL_MN, FILL_MN, true); else SACB_ML(FILL_MN, FILL_MN, false);
         }
+#undef SACB_ML
     }
     const EpiR epi = resolve_epilogue(t, bases, agent, scalars);
     switch (t.epi) {

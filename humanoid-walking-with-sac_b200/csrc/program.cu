@@ -155,7 +155,7 @@ sac_update_kernel(const Program P, const int stage_begin, const int stage_end, c
                 case T_SAMPLE_BWD: task_sample_bwd(t, tile, P, agent, scalars); break;
                 case T_OUT_ADAM: task_out_adam(t, tile, P, agent, scalars, s_red); break;
                 case T_BIAS_ADAM: task_bias_adam(t, tile, P, agent, scalars, s_red); break;
-                case T_FINISH: task_finish(t, P, agent, scalars); break;
+                case T_FINISH: task_finish(t, P, agent, scalars, s_red); break;
             }
         }
         if (s + 1 < stage_end) {

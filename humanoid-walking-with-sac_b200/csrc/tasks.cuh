@@ -247,25 +247,26 @@ __device__ __forceinline__ void task_sample_bwd(const Task &t, int tile, const P
     g[A + a] = (g_u * s.std * eps - aB) * s.in_range;
 }
 
-// column sums over the batch for 32 columns per tile: thread (cg = tid & 31, rg = tid >> 5) adds rows rg, rg+8, ...
+// column sums over the batch for 32 columns per tile: thread (cg = tid & 31, rg = tid >> 5) adds rows rg, rg+G, ...
 // (loads unrolled 8 deep), the 8 row groups are then combined in shared memory in a fixed order
 template <class F>
 __device__ __forceinline__ float colsum32(int B, float *smem, F value_at) {
+    constexpr int G = kThreads / 32;       // row groups
     const int cg = threadIdx.x & 31, rg = threadIdx.x >> 5;
     float acc = 0.f;
     int b = rg;
-    for (; b + 56 < B; b += 64) {
+    for (; b + 7 * G < B; b += 8 * G) {
         float v[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) v[u] = value_at(b + 8 * u);
+        for (int u = 0; u < 8; u++) v[u] = value_at(b + G * u);
 #pragma unroll
         for (int u = 0; u < 8; u++) acc += v[u];
     }
-    for (; b < B; b += 8) acc += value_at(b);
+    for (; b < B; b += G) acc += value_at(b);
     smem[rg * 32 + cg] = acc;
     __syncthreads();
     float tot = 0.f;
-    if (rg == 0) for (int g = 0; g < 8; g++) tot += smem[g * 32 + cg];
+    if (rg == 0) for (int g = 0; g < G; g++) tot += smem[g * 32 + cg];
     __syncthreads();
     return tot;     // valid for rg == 0
 }
@@ -320,19 +321,25 @@ __device__ __forceinline__ void task_bias_adam(const Task &t, int tile, const Pr
 //   p0 = critic partials [nt,2] (null: skip) ; p1 = actor partials [nt,2] (null: skip) ; p2 = exported log_alpha gradient (or null)
 //   i0..i3 = bump step_policy,q1,q2,alpha ; i4 = bump n_updates ; i5 = n_tiles of the partial arrays ; i6 = auto_entropy ; i7 = apply
 //   f0 = lr ; f1 = B
-__device__ __forceinline__ void task_finish(const Task &t, const Program &P, int agent, float *scalars) {
-    if (threadIdx.x != 0) return;
+__device__ __forceinline__ void task_finish(const Task &t, const Program &P, int agent, float *scalars, float *smem) {
     const int nt = t.i[5];
     const float Bf = t.f[1];
     const float *cp = resolve(t.p[0], P.bases, agent), *ap = resolve(t.p[1], P.bases, agent);
+    // partials fetched in parallel, then summed in tile order by one thread (deterministic)
+    for (int i = threadIdx.x; i < 2 * nt && i < kThreads / 2; i += blockDim.x) {
+        smem[i] = cp ? ldcg(cp + i) : 0.f;
+        smem[kThreads / 2 + i] = ap ? ldcg(ap + i) : 0.f;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
     if (cp) {
         float s1 = 0.f, s2 = 0.f;
-        for (int i = 0; i < nt; i++) { s1 += ldcg(cp + 2 * i); s2 += ldcg(cp + 2 * i + 1); }
+        for (int i = 0; i < nt; i++) { s1 += smem[2 * i]; s2 += smem[2 * i + 1]; }
         scalars[SC_LOSS_Q1] = s1 / Bf; scalars[SC_LOSS_Q2] = s2 / Bf;
     }
     if (ap) {
         float s1 = 0.f, s2 = 0.f;
-        for (int i = 0; i < nt; i++) { s1 += ldcg(ap + 2 * i); s2 += ldcg(ap + 2 * i + 1); }
+        for (int i = 0; i < nt; i++) { s1 += smem[kThreads / 2 + 2 * i]; s2 += smem[kThreads / 2 + 2 * i + 1]; }
         scalars[SC_LOSS_PI] = s1 / Bf;
         const int n_upd = __float_as_int(scalars[SC_N_UPDATES]);
         float alpha_next = scalars[SC_ALPHA0 + (n_upd & 1)];
