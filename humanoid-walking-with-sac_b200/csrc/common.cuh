@@ -124,10 +124,11 @@ struct Program {
     const int32_t *slots;     // physical ring slots of the minibatch rows [n_agents, B]
     int32_t slots_stride; int32_t pad1;
     int32_t *error_flag;      // set by watchdogs (mbarrier / grid barrier timeouts)
+    unsigned long long *trace; // optional [grid][8] globaltimer stamps of each CTA's first tile (profiling aid), or null
 };
 
 // ---- tile geometry ----------------------------------------------------------------------------------------
-constexpr int kThreads = 256;
+constexpr int kThreads = 512;
 // FFMA path
 constexpr int kSM = 64, kSN = 64, kSK = 16;
 // tcgen05 path: 128 x kTN output tile, K blocks of 32 fp32 (=128 B, one SWIZZLE_128B row)

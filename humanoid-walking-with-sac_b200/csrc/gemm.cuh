@@ -254,40 +254,36 @@ struct TcState {
     uint32_t accum_uses;   // completed tiles (parity of the accumulator barrier)
     uint8_t *tiles;        // 1024-aligned operand ring: kTStages x kSplit x (A 16 KB | B 8 KB)
     float *xr, *xk;        // rank-1 transform vectors of the current tile: by tile row [kTM], by k [kXkMax]
-    uint64_t *empty_bar;   // [kTStages]
-    uint64_t *accum_bar;
+    uint64_t *full_bar;    // [kTStages]  loader warp -> MMA warp: the k-block is in shared memory
+    uint64_t *empty_bar;   // [kTStages]  tcgen05.commit -> loader warps: the MMAs that read the slot are done
+    uint64_t *accum_bar;   //             tcgen05.commit -> everyone: the accumulator tile is complete
+    unsigned long long *trace;   // optional per-CTA timestamps (profiling aid)
 };
 
-// how a thread fetches its 16-byte chunks (4 consecutive k of one operand row) from global memory
+// how a lane fetches a 16-byte chunk (4 consecutive k of one operand row) from global memory
 enum FillMode { FILL_KVEC = 0,   // K contiguous, 16 B aligned rows: one LDG.128
                 FILL_KSCALAR,    // K contiguous, unaligned rows (e.g. ld = 365): 4 x LDG.32
                 FILL_MN };       // MN contiguous ([K, MN] storage): 4 x LDG.32 at stride ld, coalesced across the warp
 
-constexpr int kAChunks = kTM * (kTK / 4) / kThreads;   // 16-byte chunks per thread per k-block (2 with 512 threads)
-constexpr int kBChunks = kTN * (kTK / 4) / kThreads;   // 1
-constexpr int kDepth = 4;                              // k-blocks of global loads in flight per thread (register sets)
-static_assert(kAChunks >= 1 && kBChunks >= 1 && kDepth <= kTStages, "tile / thread geometry");
+constexpr int kWarps = kThreads / 32;
+constexpr int kLoaders = kWarps - 1;                       // loader warps; the last warp issues the MMAs
+constexpr int kChunksA = kTM * (kTK / 4);                  // 1024 16-byte chunks of A per k-block
+constexpr int kChunksAB = (kTM + kTN) * (kTK / 4);         // 1536 with B
+constexpr int kPassChunks = 12;                            // chunks a lane keeps in flight per pass
+constexpr int kPasses = kChunksAB / (32 * kPassChunks);    // 4
+static_assert(kPasses * 32 * kPassChunks == kChunksAB, "pass geometry");
 
 // chunk idx -> (row r, 16-byte chunk c) of the operand tile; the mapping keeps global loads coalesced:
-// K-major: 8 consecutive threads read one row's 128 B; MN-major: 32 consecutive threads read 32 consecutive rows
+// K-major: 8 consecutive lanes read one row's 128 B; MN-major: 32 consecutive lanes read 32 consecutive rows
 template <int MODE, int ROWS>
 __device__ __forceinline__ void chunk_rc(int idx, int &r, int &c) {
     if (MODE == FILL_MN) { c = idx / ROWS; r = idx % ROWS; } else { r = idx >> 3; c = idx & 7; }
 }
 
-// full k-block: pure loads -- nothing may consume the data here, or the loads stop overlapping the MMAs
+// kv = how many of the chunk's 4 values lie inside [0,K) (>= 4: all).  Pure loads.  A K-major vector chunk is read
+// whole (rows are 16 B aligned and ld >= roundup4(K)); its lanes beyond K are cleared when it is stored.
 template <int MODE>
-__device__ __forceinline__ float4 load_full(const float *src, int64_t ld) {
-    float4 v;
-    if (MODE == FILL_KVEC) v = __ldcg(reinterpret_cast<const float4 *>(src));
-    else if (MODE == FILL_KSCALAR) { v.x = ldcg(src); v.y = ldcg(src + 1); v.z = ldcg(src + 2); v.w = ldcg(src + 3); }
-    else { v.x = ldcg(src); v.y = ldcg(src + ld); v.z = ldcg(src + 2 * ld); v.w = ldcg(src + 3 * ld); }
-    return v;
-}
-// last, partial k-block: kv = number of the chunk's 4 values that lie inside [0,K).  A K-major vector chunk is read whole
-// (rows are 16 B aligned and ld >= roundup4(K)); its lanes beyond K are cleared at consume time.
-template <int MODE>
-__device__ __forceinline__ float4 load_tail(const float *src, int64_t ld, int kv) {
+__device__ __forceinline__ float4 load_chunk(const float *src, int64_t ld, int kv) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (kv <= 0) return v;
     if (MODE == FILL_KVEC) return __ldcg(reinterpret_cast<const float4 *>(src));
@@ -299,13 +295,21 @@ __device__ __forceinline__ float4 load_tail(const float *src, int64_t ld, int kv
     return v;
 }
 
-struct Regs {
-    float4 a[kAChunks];
-    float4 b[kBChunks];
-};
-
 __device__ __forceinline__ void sts128(uint32_t saddr, float4 v) {
     asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 // error-compensated "3xTF32": hi = x with the 13 low mantissa bits cleared (exactly what the tensor core would read),
 // lo = x - hi (exact in fp32, |lo| < 2^-10 |x|; the tensor core reads its top 11 bits) => x = hi + lo up to 2^-20 |x|.
@@ -322,141 +326,115 @@ __device__ __forceinline__ void store_chunk(uint32_t saddr, float4 v) {
     }
 }
 
-__device__ __forceinline__ float4 lds128(uint32_t saddr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
-    return v;
-}
-
-// ---- main loop of one output tile: global -> registers (kDepth k-blocks ahead) -> swizzled smem -> tcgen05.mma -> TMEM
+// ---- main loop of one output tile -------------------------------------------------------------------------------
+// Latency-parallel producer/consumer pipeline without any CTA-wide barrier:
+//   * each of the kLoaders loader warps owns whole k-blocks (kb = w, w + kLoaders, ...): global -> registers (12 x 16 B
+//     per lane in flight, 4 passes) -> [rank-1 transform, tf32 hi/lo split] -> swizzled smem stage -> fence -> arrive(full)
+//     so up to kLoaders k-blocks of global loads are in flight per SM and nobody waits on anybody else's loads
+//   * the MMA warp waits full[stage], one elected lane issues the tcgen05.mma's, tcgen05.commit frees the stage (empty)
 // stage layout: [A_hi 16K | B_hi 8K] (+ [A_lo | B_lo] when kSplit == 2).  XF: operand A carries the rank-1 transform.
-// The steady-state loop only sees full k-blocks; a partial last k-block (K % 32 != 0) is handled once, after it.
 template <int kSplit, int AM, int BM, bool XF>
 __device__ __forceinline__ void tc_mainloop(const OperandR &A, const OperandR &B, int m0, int n0, int M, int N, int K,
                                             TcState &st, int *error_flag) {
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
     constexpr uint32_t idesc = make_idesc(kTM, kTN);
     constexpr int kStageBytes = kSplit * kTcStageBytes;
-    const int nfull = K / kTK, krem = K - nfull * kTK, nkb = nfull + (krem ? 1 : 0);
-    const int64_t lda = A.ld, ldb = B.ld;
-    const int64_t adv_a = (AM == FILL_MN) ? (int64_t)kTK * lda : kTK, adv_b = (BM == FILL_MN) ? (int64_t)kTK * ldb : kTK;
-    const uint32_t tiles = smem_u32(st.tiles), xk_s = smem_u32(st.xk);
-    const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform: keeps the MMA operands in uniform registers
+    const int nkb = cdiv(K, kTK);
+    const uint32_t tiles = smem_u32(st.tiles), xk_s = smem_u32(st.xk), xr_s = smem_u32(st.xr);
+    const int warp_u = __shfl_sync(0xffffffffu, tid >> 5, 0);     // warp-uniform role index
     const uint32_t g0 = st.g;
 
-    // loop-invariant per-chunk state: source pointer (a row outside the operand is never dereferenced), smem offset
-    const float *pa[kAChunks], *pb[kBChunks];
-    uint32_t sa[kAChunks], sb[kBChunks];
-    int ca[kAChunks], cb[kBChunks];
-    bool va[kAChunks], vb[kBChunks];
-    float xr[kAChunks];
-#pragma unroll
-    for (int e = 0; e < kAChunks; e++) {
-        int r; chunk_rc<AM, kTM>(tid + e * kThreads, r, ca[e]);
-        va[e] = m0 + r < M;
-        pa[e] = (AM == FILL_MN) ? A.p + (int64_t)(4 * ca[e]) * lda + (m0 + r) : A.p + (int64_t)(m0 + r) * lda + 4 * ca[e];
-        sa[e] = sw128_chunk_off(r, ca[e]);
-        xr[e] = 0.f;
-        if (XF) xr[e] = va[e] ? ldcg((A.mn_major ? A.cvec : A.rvec) + m0 + r) : 0.f;    // vector indexed by the tile row
-    }
-#pragma unroll
-    for (int e = 0; e < kBChunks; e++) {
-        int r; chunk_rc<BM, kTN>(tid + e * kThreads, r, cb[e]);
-        vb[e] = n0 + r < N;
-        pb[e] = (BM == FILL_MN) ? B.p + (int64_t)(4 * cb[e]) * ldb + (n0 + r) : B.p + (int64_t)(n0 + r) * ldb + 4 * cb[e];
-        sb[e] = kTM * kTK * 4 + sw128_chunk_off(r, cb[e]);
-    }
-    if (XF) {   // vector indexed by k, staged once per tile
-        const float *by_k = A.mn_major ? A.rvec : A.cvec;
+    if (XF) {   // rank-1 operand: vector indexed by the tile row and vector indexed by k, staged once per tile
+        const float *by_row = A.mn_major ? A.cvec : A.rvec, *by_k = A.mn_major ? A.rvec : A.cvec;
+        for (int i = tid; i < kTM; i += kThreads) st.xr[i] = (m0 + i < M) ? ldcg(by_row + m0 + i) : 0.f;
         for (int i = tid; i < nkb * kTK; i += kThreads) st.xk[i] = (i < K) ? ldcg(by_k + i) : 0.f;
         __syncthreads();
     }
 
-    auto load_next = [&](Regs &rg) {       // pure loads of the next full k-block (chunk pointers advance by one k-block)
+    if (warp_u < kLoaders) {
+        for (int kb = warp_u; kb < nkb; kb += kLoaders) {
+            const uint32_t g = g0 + kb, s = g % kTStages;
+            const uint32_t stage = tiles + s * kStageBytes;
+            const int k0 = kb * kTK, krem = K - k0;          // krem >= 32: full k-block
+#pragma unroll 1
+            for (int pass = 0; pass < kPasses; pass++) {
+                float4 v[kPassChunks];
+                // ---- issue all loads of the pass -----------------------------------------------------------------
 #pragma unroll
-        for (int e = 0; e < kAChunks; e++) { rg.a[e] = va[e] ? load_full<AM>(pa[e], lda) : make_float4(0.f, 0.f, 0.f, 0.f); pa[e] += adv_a; }
+                for (int j = 0; j < kPassChunks; j++) {
+                    const int i = (pass * kPassChunks + j) * 32 + lane;
+                    int r, c;
+                    if (i < kChunksA) {
+                        chunk_rc<AM, kTM>(i, r, c);
+                        const int row = m0 + r;
+                        const float *src = (AM == FILL_MN) ? A.p + (int64_t)(k0 + 4 * c) * A.ld + row : A.p + (int64_t)row * A.ld + k0 + 4 * c;
+                        v[j] = load_chunk<AM>(src, A.ld, row < M ? krem - 4 * c : 0);
+                    } else {
+                        chunk_rc<BM, kTN>(i - kChunksA, r, c);
+                        const int row = n0 + r;
+                        const float *src = (BM == FILL_MN) ? B.p + (int64_t)(k0 + 4 * c) * B.ld + row : B.p + (int64_t)row * B.ld + k0 + 4 * c;
+                        v[j] = load_chunk<BM>(src, B.ld, row < N ? krem - 4 * c : 0);
+                    }
+                }
+                // the MMAs that last read this stage must be done before it is overwritten (loads are already in flight)
+                if (pass == 0 && g >= kTStages) mbar_wait(&st.empty_bar[s], ((g / kTStages) - 1) & 1, error_flag);
+                // ---- transform + store ---------------------------------------------------------------------------
 #pragma unroll
-        for (int e = 0; e < kBChunks; e++) { rg.b[e] = vb[e] ? load_full<BM>(pb[e], ldb) : make_float4(0.f, 0.f, 0.f, 0.f); pb[e] += adv_b; }
-    };
-    auto consume = [&](const Regs &rg, int kb) {    // registers -> (transform, tf32 split) -> swizzled smem
-        const uint32_t g = g0 + kb;
-        const uint32_t s = g % kTStages;
-        const uint32_t stage = tiles + s * kStageBytes;
-        if (g >= kTStages) mbar_wait(&st.empty_bar[s], ((g / kTStages) - 1) & 1, error_flag);   // MMAs that read this slot are done
-#pragma unroll
-        for (int e = 0; e < kAChunks; e++) {
-            float4 v = rg.a[e];
-            if (XF) {      // dq[b] * w_out[n] * relu'(h[b,n]): row factor in a register, k factors in shared memory
-                const float4 xk = lds128(xk_s + (kb * kTK + 4 * ca[e]) * 4);
-                v.x = v.x > 0.f ? xr[e] * xk.x : 0.f; v.y = v.y > 0.f ? xr[e] * xk.y : 0.f;
-                v.z = v.z > 0.f ? xr[e] * xk.z : 0.f; v.w = v.w > 0.f ? xr[e] * xk.w : 0.f;
-            }
-            store_chunk<kSplit>(stage + sa[e], v);
-        }
-#pragma unroll
-        for (int e = 0; e < kBChunks; e++) store_chunk<kSplit>(stage + sb[e], rg.b[e]);
-        fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-    };
-    auto issue = [&](int kb) {             // all smem writes of k-block kb done -> one elected lane issues its MMAs
-        __syncthreads();
-        if (warp_u == 0 && elect_one()) {
-            const uint32_t s = (g0 + kb) % kTStages;
-            tc_fence_after();
-            const uint64_t d0 = make_desc(tiles + s * kStageBytes);        // A_hi of this stage; the others are constant offsets
-            constexpr uint64_t kB = (kTM * kTK * 4) >> 4, kLo = kTcStageBytes >> 4;
-#pragma unroll
-            for (int kk = 0; kk < kTK / 8; kk++) {  // UMMA_K = 8 tf32 = 32 B: advance the start address inside the swizzled row
-                const uint64_t da = d0 + 2 * kk, db = d0 + kB + 2 * kk;
-                if (kSplit == 2) {   // small terms first: a_lo*b_hi + a_hi*b_lo, then a_hi*b_hi
-                    umma_tf32(st.tmem_base, da + kLo, db, idesc, (kb | kk) ? 1u : 0u);
-                    umma_tf32(st.tmem_base, da, db + kLo, idesc, 1u);
-                    umma_tf32(st.tmem_base, da, db, idesc, 1u);
-                } else {
-                    umma_tf32(st.tmem_base, da, db, idesc, (kb | kk) ? 1u : 0u);
+                for (int j = 0; j < kPassChunks; j++) {
+                    const int i = (pass * kPassChunks + j) * 32 + lane;
+                    int r, c;
+                    float4 x = v[j];
+                    if (i < kChunksA) {
+                        chunk_rc<AM, kTM>(i, r, c);
+                        if (AM == FILL_KVEC && krem < kTK) {     // lanes of a vector chunk beyond K
+                            const int kv = krem - 4 * c;
+                            if (kv < 4) { if (kv < 1) x.x = 0.f; if (kv < 2) x.y = 0.f; if (kv < 3) x.z = 0.f; x.w = 0.f; }
+                        }
+                        if (XF) {      // dq[b] * w_out[n] * relu'(h[b,n])
+                            const float xr = lds32(xr_s + 4 * r);
+                            const float4 xk = lds128(xk_s + 4 * (k0 + 4 * c));
+                            x.x = x.x > 0.f ? xr * xk.x : 0.f; x.y = x.y > 0.f ? xr * xk.y : 0.f;
+                            x.z = x.z > 0.f ? xr * xk.z : 0.f; x.w = x.w > 0.f ? xr * xk.w : 0.f;
+                        }
+                        store_chunk<kSplit>(stage + sw128_chunk_off(r, c), x);
+                    } else {
+                        chunk_rc<BM, kTN>(i - kChunksA, r, c);
+                        if (BM == FILL_KVEC && krem < kTK) {
+                            const int kv = krem - 4 * c;
+                            if (kv < 4) { if (kv < 1) x.x = 0.f; if (kv < 2) x.y = 0.f; if (kv < 3) x.z = 0.f; x.w = 0.f; }
+                        }
+                        store_chunk<kSplit>(stage + kTM * kTK * 4 + sw128_chunk_off(r, c), x);
+                    }
                 }
             }
-            umma_commit(&st.empty_bar[s]);
-            if (kb == nkb - 1) umma_commit(st.accum_bar);
+            fence_proxy_async();          // this lane's generic-proxy smem writes -> visible to the tensor-core (async) proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&st.full_bar[s]);
         }
-    };
-
-    // kDepth (= 4) named register sets = 4 k-blocks of loads in flight (named, not an array: keeps them in registers)
-    Regs r0, r1, r2, r3;
-    if (0 < nfull) load_next(r0);
-    if (1 < nfull) load_next(r1);
-    if (2 < nfull) load_next(r2);
-    if (3 < nfull) load_next(r3);
-#define SACB_KBLOCK(R, KB)                                   \
-    if ((KB) < nfull) {                                      \
-        consume(R, (KB));                                    \
-        if ((KB) + kDepth < nfull) load_next(R);             \
-        issue((KB));                                         \
-    }
-    for (int kb0 = 0; kb0 < nfull; kb0 += kDepth) {
-        SACB_KBLOCK(r0, kb0)
-        SACB_KBLOCK(r1, kb0 + 1)
-        SACB_KBLOCK(r2, kb0 + 2)
-        SACB_KBLOCK(r3, kb0 + 3)
-    }
-#undef SACB_KBLOCK
-    if (krem) {     // partial last k-block: guarded loads, lanes beyond K cleared, no prefetch (one exposed latency per tile)
-        Regs t;
+    } else {
+        for (int kb = 0; kb < nkb; kb++) {
+            const uint32_t g = g0 + kb, s = g % kTStages;
+            mbar_wait(&st.full_bar[s], (g / kTStages) & 1, error_flag);
+            if (elect_one()) {
+                tc_fence_after();
+                const uint64_t d0 = make_desc(tiles + s * kStageBytes);        // A_hi of this stage; the others are constant offsets
+                constexpr uint64_t kB = (kTM * kTK * 4) >> 4, kLo = kTcStageBytes >> 4;
 #pragma unroll
-        for (int e = 0; e < kAChunks; e++) {
-            const int kv = krem - 4 * ca[e];
-            float4 v = va[e] ? load_tail<AM>(pa[e], lda, kv) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kv < 4) { if (kv < 1) v.x = 0.f; if (kv < 2) v.y = 0.f; if (kv < 3) v.z = 0.f; v.w = 0.f; }
-            t.a[e] = v;
+                for (int kk = 0; kk < kTK / 8; kk++) {  // UMMA_K = 8 tf32 = 32 B: advance the start address inside the swizzled row
+                    const uint64_t da = d0 + 2 * kk, db = d0 + kB + 2 * kk;
+                    if (kSplit == 2) {   // small terms first: a_lo*b_hi + a_hi*b_lo, then a_hi*b_hi
+                        umma_tf32(st.tmem_base, da + kLo, db, idesc, (kb | kk) ? 1u : 0u);
+                        umma_tf32(st.tmem_base, da, db + kLo, idesc, 1u);
+                        umma_tf32(st.tmem_base, da, db, idesc, 1u);
+                    } else {
+                        umma_tf32(st.tmem_base, da, db, idesc, (kb | kk) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&st.empty_bar[s]);
+                if (kb == nkb - 1) umma_commit(st.accum_bar);
+            }
+            __syncwarp();
         }
-#pragma unroll
-        for (int e = 0; e < kBChunks; e++) {
-            const int kv = krem - 4 * cb[e];
-            float4 v = vb[e] ? load_tail<BM>(pb[e], ldb, kv) : make_float4(0.f, 0.f, 0.f, 0.f);
-            if (kv < 4) { if (kv < 1) v.x = 0.f; if (kv < 2) v.y = 0.f; if (kv < 3) v.z = 0.f; v.w = 0.f; }
-            t.b[e] = v;
-        }
-        consume(t, nfull);
-        issue(nfull);
     }
     st.g += nkb;
 }
@@ -565,6 +543,14 @@ __device__ __forceinline__ void gemm_tile_tc(const Task &t, int tile, const Agen
         }
 #undef SACB_ML
     }
+    auto stamp = [&](int slot) {
+        if (st.trace && threadIdx.x == 0 && tile == (int)blockIdx.x - t.tile_begin) {
+            unsigned long long ts;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
+            st.trace[(size_t)blockIdx.x * 8 + slot] = ts;
+        }
+    };
+    stamp(2);
     const EpiR epi = resolve_epilogue(t, bases, agent, scalars);
     switch (t.epi) {
         case EPI_STORE: tc_epilogue<EPI_STORE>(epi, m0, n0, st, error_flag); break;
@@ -573,6 +559,7 @@ __device__ __forceinline__ void gemm_tile_tc(const Task &t, int tile, const Agen
         case EPI_MASK: tc_epilogue<EPI_MASK>(epi, m0, n0, st, error_flag); break;
         default: tc_epilogue<EPI_ADAM>(epi, m0, n0, st, error_flag); break;
     }
+    stamp(3);
 }
 
 }  // namespace sacb

@@ -6,6 +6,7 @@
 #include <tuple>
 #include <cstring>
 #include <cstdio>
+#include <cstdlib>
 
 #include "handle.h"
 #include "tasks.cuh"
@@ -107,13 +108,21 @@ template <int kMath>
 __global__ void __launch_bounds__(kThreads, 1)
 sac_update_kernel(const Program P, const int stage_begin, const int stage_end, const int tc_setup, const uint64_t seed) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ uint64_t s_bars[kTStages + 1];
+    __shared__ uint64_t s_bars[2 * kTStages + 1];
     __shared__ uint32_t s_tmem;
     __shared__ float s_red[kThreads];
 
+    auto stamp = [&](int slot) {
+        if (P.trace && threadIdx.x == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            P.trace[(size_t)blockIdx.x * 8 + slot] = t;
+        }
+    };
+    stamp(0);
     tc::TcState st;
     st.g = 0; st.accum_uses = 0; st.tmem_base = 0;
-    st.empty_bar = s_bars; st.accum_bar = s_bars + kTStages;
+    st.full_bar = s_bars; st.empty_bar = s_bars + kTStages; st.accum_bar = s_bars + 2 * kTStages; st.trace = P.trace;
     constexpr int kSplit = kMath == SACB_MATH_TF32X3 ? 2 : 1;
     constexpr bool kTc = kMath != SACB_MATH_FP32;
     st.tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -121,7 +130,7 @@ sac_update_kernel(const Program P, const int stage_begin, const int stage_end, c
     st.xk = st.xr + kTM;
     if (kTc && tc_setup) {
         if (threadIdx.x == 0) {
-            for (int i = 0; i <= kTStages; i++) tc::mbar_init(&s_bars[i], 1);
+            for (int i = 0; i <= 2 * kTStages; i++) tc::mbar_init(&s_bars[i], 1);
             tc::fence_barrier_init();
             tc::fence_proxy_async();
         }
@@ -132,6 +141,7 @@ sac_update_kernel(const Program P, const int stage_begin, const int stage_end, c
         st.tmem_base = s_tmem;
     }
 
+    stamp(1);
     unsigned int bar_target = 0;
     for (int s = stage_begin; s < stage_end; s++) {
         const Stage sg = P.stages[s];
@@ -157,6 +167,7 @@ sac_update_kernel(const Program P, const int stage_begin, const int stage_end, c
                 case T_BIAS_ADAM: task_bias_adam(t, tile, P, agent, scalars, s_red); break;
                 case T_FINISH: task_finish(t, P, agent, scalars, s_red); break;
             }
+            if (wi == (int)blockIdx.x) stamp(4);
         }
         if (s + 1 < stage_end) {
             bar_target += gridDim.x;
@@ -169,6 +180,7 @@ sac_update_kernel(const Program P, const int stage_begin, const int stage_end, c
         __syncthreads();
         if (threadIdx.x < 32) tc::tmem_dealloc(st.tmem_base, kTN);
     }
+    stamp(5);
 }
 
 // ================================================================================================================
@@ -505,6 +517,7 @@ int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out) {
     P.ring = h->ring; P.ring_agent_stride = h->cfg.capacity * h->ring_row; P.ring_row = (int32_t)h->ring_row;
     P.slots = h->slots; P.slots_stride = h->cfg.max_batch;
     P.error_flag = h->error_flag;
+    P.trace = nullptr;
     p.kernels_per_step = h->cfg.launch_mode == SACB_LAUNCH_PERSISTENT ? 1 : (int)p.stages.size();
 
     // capture one step into a CUDA graph (stage kernels, or memset + the single cooperative launch)
@@ -542,6 +555,10 @@ extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap
     ProgramInst *p;
     int rc = get_program(h, key, &p);
     if (rc) return rc;
+    const bool trace = getenv("SACB_TRACE") != nullptr;
+    unsigned long long *d_trace = nullptr;
+    std::vector<unsigned long long> h_trace;
+    if (trace) { SACB_CUDA(cudaMalloc(&d_trace, sizeof(unsigned long long) * 8 * 4096)); p->prog.trace = d_trace; h_trace.resize(8 * 4096); }
     const int n = std::min<int>(cap, (int)p->stages.size());
     std::vector<cudaEvent_t> ev(p->stages.size() + 1);
     for (auto &e : ev) cudaEventCreate(&e);
@@ -558,12 +575,26 @@ extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap
             SACB_CUDA(cudaLaunchKernel(update_kernel_for(h->cfg.math_mode), dim3(std::max(1, p->stages[s].n_tiles * h->cfg.n_agents)), dim3(kThreads), args,
                                        math_smem(h->cfg.math_mode), h->stream));
             cudaEventRecord(ev[s + 1], h->stream);
+            if (trace && r == reps + 2) {
+                SACB_CUDA(cudaStreamSynchronize(h->stream));
+                const int grid = std::max(1, p->stages[s].n_tiles * h->cfg.n_agents);
+                SACB_CUDA(cudaMemcpy(h_trace.data(), d_trace, sizeof(unsigned long long) * 8 * std::min(grid, 4096), cudaMemcpyDeviceToHost));
+                double a[8] = {0}; unsigned long long t0 = ~0ull, t5 = 0;
+                const int g = std::min(grid, 4096);
+                for (int b = 0; b < g; b++) { t0 = std::min(t0, h_trace[b * 8]); t5 = std::max(t5, h_trace[b * 8 + 5]);
+                    a[1] += (double)(h_trace[b * 8 + 1] - h_trace[b * 8]); a[2] += (double)(h_trace[b * 8 + 2] - h_trace[b * 8 + 1]);
+                    a[3] += (double)(h_trace[b * 8 + 3] - h_trace[b * 8 + 2]); a[4] += (double)(h_trace[b * 8 + 4] - h_trace[b * 8 + 1]);
+                    a[5] += (double)(h_trace[b * 8 + 5] - h_trace[b * 8 + 4]); }
+                fprintf(stderr, "[trace] stage %2d grid %4d has_gemm %d  span %.2f us | per-CTA avg: setup %.2f  mainloop %.2f  epilogue %.2f  tile %.2f  teardown %.2f us\n",
+                        s, grid, p->stage_has_gemm[s], (t5 - t0) * 1e-3, a[1] / g * 1e-3, a[2] / g * 1e-3, a[3] / g * 1e-3, a[4] / g * 1e-3, a[5] / g * 1e-3);
+            }
         }
         SACB_CUDA(cudaStreamSynchronize(h->stream));
         if (r >= 3)
             for (int s = 0; s < (int)p->stages.size(); s++) { float ms; cudaEventElapsedTime(&ms, ev[s], ev[s + 1]); acc[s] += ms * 1000.f / reps; }
     }
     for (int s = 0; s < n; s++) us_out[s] = acc[s];
+    if (trace) { p->prog.trace = nullptr; cudaFree(d_trace); }
     for (auto &e : ev) cudaEventDestroy(e);
     h->kernel_launches += (int64_t)(reps + 3) * p->stages.size();
     return (int)p->stages.size();
