@@ -140,15 +140,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_selftest_kernel(Task t, Agen
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint64_t s_bars[2 * kTStages + 1];
     __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_consumed;
     tc::TcState st;
-    st.g = 0; st.accum_uses = 0; st.tmem_base = 0; st.full_bar = s_bars; st.empty_bar = s_bars + kTStages; st.accum_bar = s_bars + 2 * kTStages; st.trace = nullptr;
+    st.g = 0; st.accum_uses = 0; st.tmem_base = 0; st.full_bar = s_bars; st.empty_bar = s_bars + kTStages; st.accum_bar = s_bars + 2 * kTStages; st.consumed = &s_consumed; st.trace = nullptr;
     constexpr int kSplit = kMath == SACB_MATH_TF32X3 ? 2 : 1;
     constexpr bool kTc = kMath != SACB_MATH_FP32;
     st.tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     st.xr = reinterpret_cast<float *>(st.tiles + kTStages * kSplit * kTcStageBytes);
     st.xk = st.xr + kTM;
     if (kTc) {
-        if (threadIdx.x == 0) { for (int i = 0; i <= 2 * kTStages; i++) tc::mbar_init(&s_bars[i], 1); tc::fence_barrier_init(); tc::fence_proxy_async(); }
+        if (threadIdx.x == 0) { for (int i = 0; i <= 2 * kTStages; i++) tc::mbar_init(&s_bars[i], 1);
+            s_consumed = 0; tc::fence_barrier_init(); tc::fence_proxy_async(); }
         if (threadIdx.x < 32) tc::tmem_alloc(&s_tmem, kTN);
         tc::tc_fence_before(); __syncthreads(); tc::tc_fence_after();
         st.tmem_base = s_tmem;

@@ -168,21 +168,38 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// bounded wait: a lost arrival must surface as an error, never as a hung GPU box
+// bounded wait (~0.5 s): a lost arrival must surface as an error, never as a hung GPU box
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int *error_flag) {
     const uint32_t addr = smem_u32(bar);
 #pragma unroll 1
-    for (uint32_t it = 0; it < (1u << 22); ++it) {
+    for (uint32_t it = 0; it < (1u << 23); ++it) {
         uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) return true;
+        if (it > 64) __nanosleep(32);
     }
     if (error_flag) atomicExch(error_flag, 1);
     return false;
+}
+// bounded spin on a monotonically increasing shared-memory counter (written with st.release by the MMA warp)
+__device__ __forceinline__ bool counter_wait(const uint32_t *ctr, uint32_t target, int *error_flag) {
+    const uint32_t addr = smem_u32(ctr);
+#pragma unroll 1
+    for (uint32_t it = 0; it < (1u << 23); ++it) {
+        uint32_t v;
+        asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+        if ((int32_t)(v - target) >= 0) return true;
+        if (it > 64) __nanosleep(32);
+    }
+    if (error_flag) atomicExch(error_flag, 1);
+    return false;
+}
+__device__ __forceinline__ void counter_publish(uint32_t *ctr, uint32_t v) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(ctr)), "r"(v) : "memory");
 }
 
 __device__ __forceinline__ bool elect_one() {      // one lane of a converged warp
@@ -257,6 +274,7 @@ struct TcState {
     uint64_t *full_bar;    // [kTStages]  loader warp -> MMA warp: the k-block is in shared memory
     uint64_t *empty_bar;   // [kTStages]  tcgen05.commit -> loader warps: the MMAs that read the slot are done
     uint64_t *accum_bar;   //             tcgen05.commit -> everyone: the accumulator tile is complete
+    uint32_t *consumed;    // k-blocks whose MMAs have completed (monotonic; published by the MMA warp, polled by loaders)
     unsigned long long *trace;   // optional per-CTA timestamps (profiling aid)
 };
 
@@ -331,7 +349,9 @@ __device__ __forceinline__ void store_chunk(uint32_t saddr, float4 v) {
 //   * each of the kLoaders loader warps owns whole k-blocks (kb = w, w + kLoaders, ...): global -> registers (12 x 16 B
 //     per lane in flight, 4 passes) -> [rank-1 transform, tf32 hi/lo split] -> swizzled smem stage -> fence -> arrive(full)
 //     so up to kLoaders k-blocks of global loads are in flight per SM and nobody waits on anybody else's loads
-//   * the MMA warp waits full[stage], one elected lane issues the tcgen05.mma's, tcgen05.commit frees the stage (empty)
+//   * the MMA warp waits full[stage], one elected lane issues the tcgen05.mma's, tcgen05.commit -> empty[stage]
+//   * mbarrier phases only carry one parity bit, and loaders run many k-blocks ahead, so loaders never wait on empty[]
+//     themselves: the MMA warp (the only, in-order waiter of empty[]) publishes a monotonic `consumed` counter instead
 // stage layout: [A_hi 16K | B_hi 8K] (+ [A_lo | B_lo] when kSplit == 2).  XF: operand A carries the rank-1 transform.
 template <int kSplit, int AM, int BM, bool XF>
 __device__ __forceinline__ void tc_mainloop(const OperandR &A, const OperandR &B, int m0, int n0, int M, int N, int K,
@@ -377,7 +397,7 @@ __device__ __forceinline__ void tc_mainloop(const OperandR &A, const OperandR &B
                     }
                 }
                 // the MMAs that last read this stage must be done before it is overwritten (loads are already in flight)
-                if (pass == 0 && g >= kTStages) mbar_wait(&st.empty_bar[s], ((g / kTStages) - 1) & 1, error_flag);
+                if (pass == 0 && g >= kTStages) counter_wait(st.consumed, g - kTStages + 1, error_flag);
                 // ---- transform + store ---------------------------------------------------------------------------
 #pragma unroll
                 for (int j = 0; j < kPassChunks; j++) {
@@ -412,7 +432,14 @@ __device__ __forceinline__ void tc_mainloop(const OperandR &A, const OperandR &B
             if (lane == 0) mbar_arrive(&st.full_bar[s]);
         }
     } else {
-        for (int kb = 0; kb < nkb; kb++) {
+        constexpr int kLag = 2;      // retire two k-blocks behind the issue point: the tensor pipe always has work queued
+        for (int kb = 0; kb < nkb + kLag; kb++) {
+            if (kb >= kLag) {    // retire k-block kb-kLag: its MMAs are done -> its stage may be refilled
+                const uint32_t gp = g0 + kb - kLag;
+                mbar_wait(&st.empty_bar[gp % kTStages], (gp / kTStages) & 1, error_flag);
+                if (lane == 0) counter_publish(st.consumed, gp + 1);
+            }
+            if (kb >= nkb) continue;
             const uint32_t g = g0 + kb, s = g % kTStages;
             mbar_wait(&st.full_bar[s], (g / kTStages) & 1, error_flag);
             if (elect_one()) {

@@ -110,6 +110,7 @@ sac_update_kernel(const Program P, const int stage_begin, const int stage_end, c
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint64_t s_bars[2 * kTStages + 1];
     __shared__ uint32_t s_tmem;
+    __shared__ uint32_t s_consumed;
     __shared__ float s_red[kThreads];
 
     auto stamp = [&](int slot) {
@@ -122,7 +123,7 @@ sac_update_kernel(const Program P, const int stage_begin, const int stage_end, c
     stamp(0);
     tc::TcState st;
     st.g = 0; st.accum_uses = 0; st.tmem_base = 0;
-    st.full_bar = s_bars; st.empty_bar = s_bars + kTStages; st.accum_bar = s_bars + 2 * kTStages; st.trace = P.trace;
+    st.full_bar = s_bars; st.empty_bar = s_bars + kTStages; st.accum_bar = s_bars + 2 * kTStages; st.consumed = &s_consumed; st.trace = P.trace;
     constexpr int kSplit = kMath == SACB_MATH_TF32X3 ? 2 : 1;
     constexpr bool kTc = kMath != SACB_MATH_FP32;
     st.tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -131,6 +132,7 @@ sac_update_kernel(const Program P, const int stage_begin, const int stage_end, c
     if (kTc && tc_setup) {
         if (threadIdx.x == 0) {
             for (int i = 0; i <= 2 * kTStages; i++) tc::mbar_init(&s_bars[i], 1);
+            s_consumed = 0;
             tc::fence_barrier_init();
             tc::fence_proxy_async();
         }
