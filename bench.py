@@ -231,7 +231,7 @@ def run_ours(args):
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
                 "kernel": "sac_update_kernel (one fused update program: %d launches/step in '%s' mode)" % (1 if args.launch == "persistent" else n_st, args.launch),
-                "ms_per_launch_sum": upd_ms.value, "peak_source": peak_src + " bf16 dense, sustained (tf32 operands run at half that rate)",
+                "ms_per_launch_sum": upd_ms.value, "peak_source": peak_src + " bf16 dense, sustained (each product costs 3 bf16 MMAs: algorithmic FLOPs are counted once)",
                 "note": "single-agent B=256 is latency/occupancy bound (SURVEY 8d): ~20 dependent GEMM stages of <=0.3 GFLOP",
                 "stage_us": [round(float(stage_us[i]), 2) for i in range(max(0, min(n_st, 64)))],
                 "per_sample": {"ms_per_call": per_call_ms, "samples_per_s": B / (per_call_ms * 1e-3),
@@ -265,7 +265,7 @@ def run_ours(args):
     if rank == 0:
         line = {"metric": "SAC updates/sec (Humanoid-v5 shape, B=256, 1M-transition PER)", "value": value, "unit": "updates/s", "n_gpus": world,
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": {"tf32x3": "f32 (error-compensated tf32 pairs on tcgen05, f32 accumulate)", "tf32": "tf32 operands / f32 accumulate", "fp32": "f32"}[args.math],
+                "scaling": "weak", "vs_baseline": None, "dtype": {"bf16x3": "f32 (bf16 hi/lo operand pairs, 3 tcgen05 MMAs per product, f32 accumulate in TMEM; f32 master weights / Adam)", "fp32": "f32 (FFMA on the bf16-pair operands)"}[args.math],
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "launch": args.launch, "math": args.math, "replicas": world,
                            "l2_policy": "inputs larger than L2: 1M-row ring (2.9 GB) + 4 MB priority table re-read every step; weights/Adam state (63 MB) stay L2 resident by design"},
@@ -284,7 +284,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--launch", default=os.environ.get("SACB_LAUNCH", "staged"), choices=["staged", "persistent"])
-    ap.add_argument("--math", default=os.environ.get("SACB_MATH", "tf32x3"), choices=["tf32x3", "tf32", "fp32"])
+    ap.add_argument("--math", default=os.environ.get("SACB_MATH", "bf16x3"), choices=["bf16x3", "fp32"])
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -16,7 +16,7 @@ c_f64p = ctypes.POINTER(ctypes.c_double)
 c_i64p = ctypes.POINTER(ctypes.c_int64)
 
 OK, ERR_ARG, ERR_DEVICE, ERR_STATE, ERR_NOMEM = 0, -1, -2, -3, -4
-MATH_FP32, MATH_TF32, MATH_TF32X3 = 0, 1, 2
+MATH_FP32, MATH_BF16X3 = 0, 1
 LAUNCH_STAGED, LAUNCH_PERSISTENT = 0, 1
 NET_POLICY, NET_Q1, NET_Q2, NET_Q1_TARGET, NET_Q2_TARGET = range(5)
 SLOT_PARAM, SLOT_ADAM_M, SLOT_ADAM_V, SLOT_GRAD = range(4)
@@ -101,7 +101,8 @@ SIGNATURES = {
     "sacb_timer_stop": (I, [H, c_f32p]),
     "sacb_time_update": (I, [H, I64, I, c_f32p]),
     "sacb_time_stages": (I, [H, I64, c_f32p, I]),
-    "sacb_selftest_gemm": (I, [I, I, I, I, I, I, c_f32p]),
+    "sacb_debug_read_activation": (I, [H, I, I, I, I, I64, c_f32p]),
+    "sacb_selftest_gemm": (I, [I, I, I, I, I, I, I, c_f32p]),
 }
 
 _lib = None

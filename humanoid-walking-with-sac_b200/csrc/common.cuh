@@ -1,7 +1,16 @@
 // Shared device/host definitions of the SAC update "program": a static list of tile tasks grouped into
 // dependency stages.  The same task code runs (a) as one kernel per stage inside a CUDA graph and
 // (b) inside ONE persistent cooperative launch with grid barriers between stages.
+//
+// Operand storage ("pair matrix", PM): every matrix a GEMM reads -- minibatch inputs, activations, activation
+// gradients and a shadow of every hidden/head weight -- is kept in HBM/L2 as two bf16 planes, hi = bf16(x) and
+// lo = bf16(x - hi), each row-major [rows, ld] with ld a multiple of 8 (16 B).  x ~= hi + lo to 2^-17 relative.
+// TMA moves 128-byte-swizzled boxes of both planes straight into shared memory; the tensor core then forms
+// a*b as  a_lo*b_hi + a_hi*b_lo + a_hi*b_hi  (three kind::f16 MMAs, fp32 accumulate in TMEM).  The fp32
+// master weights, Adam moments and all scalars/vectors stay fp32.
 #pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -14,7 +23,7 @@ constexpr float kLogSqrt2Pi = 0.91893853320467274178f;     // torch Normal.log_p
 constexpr float kBeta1 = 0.9f, kBeta2 = 0.999f, kAdamEps = 1e-8f;  // torch.optim.Adam defaults (sac_imp.py:39-41)
 
 // ---- a pointer that is valid for every agent of a population: region base + offset ----------------------
-// region 0 = arena (params, targets, Adam state, scalars), region 1 = workspace (minibatch, activations)
+// region 0 = arena (params, targets, Adam state, weight shadows, scalars), region 1 = workspace
 struct Ref {
     int64_t v;   // -1 = null ; bit 62 = region ; low bits = float offset
 };
@@ -33,6 +42,23 @@ __device__ __forceinline__ float *resolve(Ref r, const AgentBases &b, int agent)
     return ((r.v >> 62) & 1) ? b.ws + agent * b.ws_stride + off : b.arena + agent * b.arena_stride + off;
 }
 
+// ---- pair-matrix view: rows [row0, row0+R) of a PM; `base` points at element (0,0) of the view's hi plane ----
+struct PmRef {
+    Ref base;            // float-unit offset of the first hi element of the view (16 B aligned)
+    int32_t ld;          // bf16 elements between rows (multiple of 8)
+    int32_t pad;
+    int64_t plane;       // bf16 elements from a hi element to its lo element
+};
+struct Pm {              // resolved for one agent
+    __nv_bfloat16 *hi;
+    int ld;
+    int64_t plane;
+};
+__device__ __forceinline__ Pm resolve_pm(const PmRef &r, const AgentBases &b, int agent) {
+    Pm p; p.hi = reinterpret_cast<__nv_bfloat16 *>(resolve(r.base, b, agent)); p.ld = r.ld; p.plane = r.plane; return p;
+}
+__host__ __device__ inline PmRef null_pm() { PmRef r; r.base = null_ref(); r.ld = 0; r.pad = 0; r.plane = 0; return r; }
+
 // ---- scalars kept per agent in the arena (offsets in floats from the scalar block) ----------------------
 enum ScalarSlot {
     SC_LOG_ALPHA = 0, SC_LOG_ALPHA_M, SC_LOG_ALPHA_V,
@@ -42,50 +68,51 @@ enum ScalarSlot {
     SC_COUNT = 16
 };
 
-// ---- GEMM operand ---------------------------------------------------------------------------------------
-// logical operand X[R, K] (R = M for A, N for B).  mn_major = 0: stored row-major [R, K] (K contiguous);
-// mn_major = 1: stored row-major [K, R] (R contiguous) -> the smem fill transposes.
-// xform = 1: value = (src > 0) ? rvec[storage_row] * cvec[storage_col] : 0   (implicit dL/dh of the last
-// hidden layer: dq[b] * w_out[n] * relu'(h[b,n]); never materialised)
+// ---- GEMM operand: logical X[R, K] (R = M for A, N for B) held in a PM -----------------------------------
+// mn_major = 0: the PM stores [R, K] (K contiguous);  mn_major = 1: the PM stores [K, R] (R contiguous) and the
+// tensor core reads it transposed (UMMA MN-major descriptor) -- nothing is ever transposed in memory.
 struct Operand {
-    Ref ptr;
-    int32_t ld;
+    PmRef pm;
     int32_t mn_major;
-    int32_t xform;
-    int32_t pad;
-    Ref rvec, cvec;
+    int32_t r0;          // the operand is rows [r0, r0+R) of the view along its M/N dimension.  TMA needs the byte offset of
+                         // a box along the contiguous dimension to be a multiple of 16: r0 % 8 == 0 when mn_major = 1
 };
 
 enum TaskType : int32_t {
     T_GEMM = 0,
-    T_GATHER,        // replay ring rows -> minibatch matrices
+    T_SHADOW,        // fp32 master weights -> bf16 hi/lo shadow PMs (start of every step)
+    T_GATHER,        // replay ring rows -> minibatch PMs
     T_SAMPLE,        // policy head outputs -> tanh-Gaussian sample + log-prob     (networks_model1.py:78-99)
-    T_TARGET_LOSS,   // Bellman target + twin critic MSE + dL/dq                   (sac_imp.py:92-105)
-    T_ACTOR_LOSS,    // policy loss, min-Q routing, alpha loss + alpha Adam        (sac_imp.py:117-135)
+    T_TARGET_LOSS,   // Bellman target + twin critic MSE + dL/dq + dL/dh_last      (sac_imp.py:92-105)
+    T_ACTOR_LOSS,    // policy loss, min-Q routing + dL/dh_last                    (sac_imp.py:117-121)
     T_SAMPLE_BWD,    // dL/da -> dL/dmean, dL/dlog_std                             
     T_OUT_ADAM,      // Q output layer: dW=dq^T h, db=sum dq, Adam, Polyak
     T_BIAS_ADAM,     // hidden-layer bias: db = colsum(dh), Adam, Polyak
-    T_FINISH         // bump step counters
+    T_FINISH         // loss scalars, temperature step (sac_imp.py:128-135), step counters
 };
 
 enum Epilogue : int32_t {
-    EPI_STORE = 0,       // C = acc
-    EPI_BIAS,            // C = acc + bias[n]
-    EPI_BIAS_RELU,       // C = relu(acc + bias[n])
-    EPI_MASK,            // C = acc * (mask[m,n] > 0)
-    EPI_ADAM             // acc = dW tile: Adam on W (+ Polyak into Wt, + optional grad export)
+    EPI_F32 = 0,         // C[fp32] = acc (+ bias[n])
+    EPI_BIAS_RELU,       // PM  = relu(acc + bias[n])
+    EPI_MASK,            // PM  = acc * (mask_hi[m,n] > 0)
+    EPI_ADAM             // acc = dW tile: Adam on W (+ Polyak into Wt, + shadow PM refresh, + optional grad export)
 };
 
 struct AdamArgs {
     Ref w, m, v;        // same shape as the GEMM output, ld = N
     Ref wt;             // Polyak target (null for the policy)
     Ref gexp;           // gradient export (null unless SACB_EXPORT_GRADS / data-parallel mode)
+    PmRef shadow;       // bf16 pair shadow of w refreshed in place (null: not needed before the next step)
+    PmRef shadow2;      // second shadow holding only columns >= shadow2_col0 of w (the action block of a critic's fc1)
+    int32_t shadow2_col0, pad0;
     int32_t step_slot;  // ScalarSlot of the optimizer step counter (value BEFORE this step's increment)
     int32_t apply;      // 0 = only export the gradient (data-parallel backward), 1 = apply Adam
     float lr, tau;
 };
 
-struct Task {
+struct alignas(64) Task {
+    // TMA descriptors of the two GEMM operands: dims {cols, rows, plane(2), agent}, SWIZZLE_128B, bf16
+    CUtensorMap tmA, tmB;
     int32_t type;
     int32_t tile_begin;       // first tile of this task inside its stage
     int32_t n_tiles;
@@ -94,13 +121,14 @@ struct Task {
     Operand A, B;
     int32_t M, N, K;
     int32_t epi;
-    Ref C; int32_t ldc;
-    int32_t accumulate;       // EPI_STORE: C += acc
+    Ref C; int32_t ldc;       // EPI_F32
+    PmRef Cpm;                // EPI_BIAS_RELU / EPI_MASK
     Ref bias;
-    Ref mask; int32_t ld_mask;
+    PmRef mask;
     AdamArgs adam;
     // --- elementwise tasks: generic slots (meaning depends on type, see tasks.cuh)
     Ref p[24];
+    PmRef pm[6];
     int32_t i[8];
     float f[6];
 };
@@ -129,14 +157,14 @@ struct Program {
 
 // ---- tile geometry ----------------------------------------------------------------------------------------
 constexpr int kThreads = 512;
-// FFMA path
+// FFMA path (checker / strict mode)
 constexpr int kSM = 64, kSN = 64, kSK = 16;
-// tcgen05 path: 128 x kTN output tile, K blocks of 32 fp32 (=128 B, one SWIZZLE_128B row)
-constexpr int kTM = 128, kTN = 64, kTK = 32, kTStages = 4;
-constexpr int kTcStageBytes = (kTM + kTN) * kTK * 4;              // 24 KB
-constexpr int kTcXformBytes = (128 + 2048) * 4;                   // rank-1 transform vectors (gemm.cuh: xr, xk)
-__host__ __device__ constexpr int tc_smem_bytes(int split) { return kTStages * split * kTcStageBytes + kTcXformBytes + 1024; }
-constexpr int kTcSmemBytes = tc_smem_bytes(1);
+// tcgen05 path: 128 x 64 output tile, K blocks of 64 bf16 (= 128 B, one SWIZZLE_128B row), both planes per stage
+constexpr int kTM = 128, kTN = 64, kTK = 64, kTStages = 4;
+constexpr int kTcABytes = kTM * kTK * 2 * 2;                      // hi + lo planes of the A tile: 32 KB
+constexpr int kTcBBytes = kTN * kTK * 2 * 2;                      // 16 KB
+constexpr int kTcStageBytes = kTcABytes + kTcBBytes;              // 48 KB
+constexpr int kTcSmemBytes = kTStages * kTcStageBytes + 1024;     // + slack for the 1024 B alignment of the ring
 constexpr int kSimtSmemBytes = 2 * kSK * (kSM + 4) * 4;
 
 __host__ __device__ inline int cdiv(int a, int b) { return (a + b - 1) / b; }

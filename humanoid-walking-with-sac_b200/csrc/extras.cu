@@ -133,92 +133,106 @@ extern "C" int sacb_policy_forward(sacb_handle h, int agent, const float *s, int
 
 // ---- data-parallel mode: implemented in dp.cu ---------------------------------------------------------------------
 
-// ---- self test: tensor-core tile vs FFMA tile on random operands ------------------------------------------------
+// ---- self test: TMA + tcgen05 tile vs FFMA tile vs host float64, all on the same bf16-pair operands ------------------
 namespace sacb {
 template <int kMath>
-__global__ void __launch_bounds__(kThreads, 1) gemm_selftest_kernel(Task t, AgentBases bases, int *error_flag) {
+__global__ void __launch_bounds__(kThreads, 1) gemm_selftest_kernel(const Task *tp, AgentBases bases, int *error_flag) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint64_t s_bars[2 * kTStages + 1];
     __shared__ uint32_t s_tmem;
-    __shared__ uint32_t s_consumed;
+    const Task &t = *tp;
     tc::TcState st;
-    st.g = 0; st.accum_uses = 0; st.tmem_base = 0; st.full_bar = s_bars; st.empty_bar = s_bars + kTStages; st.accum_bar = s_bars + 2 * kTStages; st.consumed = &s_consumed; st.trace = nullptr;
-    constexpr int kSplit = kMath == SACB_MATH_TF32X3 ? 2 : 1;
+    st.g = 0; st.accum_uses = 0; st.tmem_base = 0; st.full_bar = s_bars; st.empty_bar = s_bars + kTStages; st.accum_bar = s_bars + 2 * kTStages; st.trace = nullptr;
     constexpr bool kTc = kMath != SACB_MATH_FP32;
     st.tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    st.xr = reinterpret_cast<float *>(st.tiles + kTStages * kSplit * kTcStageBytes);
-    st.xk = st.xr + kTM;
     if (kTc) {
-        if (threadIdx.x == 0) { for (int i = 0; i <= 2 * kTStages; i++) tc::mbar_init(&s_bars[i], 1);
-            s_consumed = 0; tc::fence_barrier_init(); tc::fence_proxy_async(); }
+        if (threadIdx.x == 0) { for (int i = 0; i <= 2 * kTStages; i++) tc::mbar_init(&s_bars[i], 1); tc::fence_barrier_init(); }
         if (threadIdx.x < 32) tc::tmem_alloc(&s_tmem, kTN);
         tc::tc_fence_before(); __syncthreads(); tc::tc_fence_after();
         st.tmem_base = s_tmem;
     }
     for (int tile = blockIdx.x; tile < t.n_tiles; tile += gridDim.x) {
-        if (kTc) gemm_tile_tc<kSplit>(t, tile, bases, 0, nullptr, st, error_flag);
+        if (kTc) gemm_tile_tc(t, tile, bases, 0, nullptr, st, error_flag);
         else gemm_tile_ffma(t, tile, bases, 0, nullptr, reinterpret_cast<float *>(smem_raw));
     }
     if (kTc) { tc::tc_fence_before(); __syncthreads(); if (threadIdx.x < 32) tc::tmem_dealloc(st.tmem_base, kTN); }
 }
+
+static uint16_t host_bf16_rn(float x) {
+    uint32_t u; memcpy(&u, &x, 4);
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+static float host_bf16_to_float(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
 }  // namespace sacb
 
-extern "C" int sacb_selftest_gemm(int device, int M, int N, int K, int a_mn, int b_mn_and_mode, float *rel_err_out) {
-    // b_mn_and_mode: bit 0 = B operand MN-major, bit 1 = use the error-compensated 3xTF32 tile instead of plain tf32
-    const int b_mn = b_mn_and_mode & 1, x3 = (b_mn_and_mode >> 1) & 1;
-    if (M < 1 || N < 1 || K < 1 || !rel_err_out) return fail(SACB_ERR_ARG, "bad argument");
+extern "C" int sacb_selftest_gemm(int device, int M, int N, int K, int a_mn, int b_mn, int b_r0, float *rel_err_out) {
+    if (M < 1 || N < 1 || K < 1 || b_r0 < 0 || (b_mn && b_r0 % 8) || !rel_err_out) return fail(SACB_ERR_ARG, "bad argument (an MN-major operand offset must be a multiple of 8)");
     SACB_CUDA(cudaSetDevice(device));
-    const int lda = a_mn ? (int)align_up(M, 4) + 4 : (int)align_up(K, 4) + 4, ldb = b_mn ? (int)align_up(N, 4) + 4 : (int)align_up(K, 4) + 4;
-    const int64_t na = (int64_t)(a_mn ? K : M) * lda, nb = (int64_t)(b_mn ? K : N) * ldb, nc = (int64_t)M * N;
-    std::vector<float> ha(na), hb(nb), c0(nc), c1(nc);
+    // stored shapes: K-major [R, K], MN-major [K, R]; the B matrix has b_r0 leading rows/columns that are not part of the operand
+    const int NB = N + b_r0;
+    const int a_rows = a_mn ? K : M, a_cols = a_mn ? M : K, b_rows = b_mn ? K : NB, b_cols = b_mn ? NB : K;
+    const int lda = (int)align_up(a_cols, 8) + 8, ldb = (int)align_up(b_cols, 8) + 8;
+    const int64_t na = (int64_t)a_rows * lda, nb = (int64_t)b_rows * ldb, nc = (int64_t)M * N;
+    std::vector<uint16_t> pa(2 * na, 0), pb(2 * nb, 0);
+    std::vector<float> va(na, 0.f), vb(nb, 0.f), c0(nc), c1(nc);     // values the pairs actually represent (hi + lo)
     uint32_t s = 12345u;
     auto rnd = [&]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
-    for (auto &v : ha) v = rnd();
-    for (auto &v : hb) v = rnd();
-    float *d;
-    const int64_t total = na + nb + 2 * nc + 64;
+    auto fill = [&](std::vector<uint16_t> &p, std::vector<float> &v, int rows, int cols, int ld, int64_t n) {
+        for (int r = 0; r < rows; r++)
+            for (int c = 0; c < ld; c++) {     // the padding columns hold garbage on purpose: the TMA extent must hide them
+                const float x = rnd();
+                const uint16_t hi = host_bf16_rn(x), lo = host_bf16_rn(x - host_bf16_to_float(hi));
+                p[(int64_t)r * ld + c] = hi; p[n + (int64_t)r * ld + c] = lo;
+                if (c < cols) v[(int64_t)r * ld + c] = host_bf16_to_float(hi) + host_bf16_to_float(lo);
+            }
+    };
+    fill(pa, va, a_rows, a_cols, lda, na);
+    fill(pb, vb, b_rows, b_cols, ldb, nb);
+    // device buffer in float units: [PM A | PM B | C0 | C1]
+    const int64_t oa = 0, ob = align_up(na, 32), oc0 = ob + align_up(nb, 32), oc1 = oc0 + align_up(nc, 32), total = oc1 + align_up(nc, 32);
+    float *d; Task *d_tasks; int *flag;
     SACB_CUDA(cudaMalloc(&d, sizeof(float) * total));
     SACB_CUDA(cudaMemset(d, 0, sizeof(float) * total));
-    int *flag;
+    SACB_CUDA(cudaMalloc(&d_tasks, 2 * sizeof(Task)));
     SACB_CUDA(cudaMalloc(&flag, 64)); SACB_CUDA(cudaMemset(flag, 0, 64));
-    const int64_t oa = 0, ob = align_up(na, 4), oc0 = ob + align_up(nb, 4), oc1 = oc0 + align_up(nc, 4);
-    SACB_CUDA(cudaMemcpy(d + oa, ha.data(), sizeof(float) * na, cudaMemcpyHostToDevice));
-    SACB_CUDA(cudaMemcpy(d + ob, hb.data(), sizeof(float) * nb, cudaMemcpyHostToDevice));
+    SACB_CUDA(cudaMemcpy(d + oa, pa.data(), 2 * na * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    SACB_CUDA(cudaMemcpy(d + ob, pb.data(), 2 * nb * sizeof(uint16_t), cudaMemcpyHostToDevice));
     AgentBases bases{d, d, 0, 0};
-    auto mk = [&](int tm, int tn, int64_t oc) {
-        Task t; memset(&t, 0, sizeof(t));
-        t.type = T_GEMM; t.M = M; t.N = N; t.K = K; t.epi = EPI_STORE;
-        t.A.ptr = make_ref(0, oa); t.A.ld = lda; t.A.mn_major = a_mn; t.A.rvec = t.A.cvec = null_ref();
-        t.B.ptr = make_ref(0, ob); t.B.ld = ldb; t.B.mn_major = b_mn; t.B.rvec = t.B.cvec = null_ref();
-        t.C = make_ref(0, oc); t.ldc = N; t.bias = t.mask = null_ref();
+    Task tk[2];
+    for (int v = 0; v < 2; v++) {
+        Task &t = tk[v]; memset(&t, 0, sizeof(t));
+        const int tm = v ? kTM : kSM, tn = v ? kTN : kSN;
+        t.type = T_GEMM; t.M = M; t.N = N; t.K = K; t.epi = EPI_F32;
+        t.A.pm.base = make_ref(0, oa); t.A.pm.ld = lda; t.A.pm.plane = na; t.A.mn_major = a_mn; t.A.r0 = 0;
+        t.B.pm.base = make_ref(0, ob); t.B.pm.ld = ldb; t.B.pm.plane = nb; t.B.mn_major = b_mn; t.B.r0 = b_r0;
+        t.C = make_ref(0, v ? oc1 : oc0); t.ldc = N; t.bias = null_ref();
+        t.Cpm = t.mask = null_pm(); t.adam.shadow = t.adam.shadow2 = null_pm();
         t.tiles_m = cdiv(M, tm); t.tiles_n = cdiv(N, tn); t.n_tiles = t.tiles_m * t.tiles_n;
-        return t;
-    };
-    Task t0 = mk(kSM, kSN, oc0), t1 = mk(kTM, kTN, oc1);
-    gemm_selftest_kernel<SACB_MATH_FP32><<<t0.n_tiles, kThreads, kSimtSmemBytes>>>(t0, bases, flag);
-    if (x3) {
-        SACB_CUDA(cudaFuncSetAttribute(gemm_selftest_kernel<SACB_MATH_TF32X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(2)));
-        gemm_selftest_kernel<SACB_MATH_TF32X3><<<std::min(t1.n_tiles, 148), kThreads, tc_smem_bytes(2)>>>(t1, bases, flag);
-    } else {
-        SACB_CUDA(cudaFuncSetAttribute(gemm_selftest_kernel<SACB_MATH_TF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc_smem_bytes(1)));
-        gemm_selftest_kernel<SACB_MATH_TF32><<<std::min(t1.n_tiles, 148), kThreads, tc_smem_bytes(1)>>>(t1, bases, flag);
     }
+    int rc = make_pm_tensor_map(&tk[1].tmA, d + oa, a_cols, a_rows, lda, na, 0, 1, a_mn ? 64 : kTM);
+    if (rc == SACB_OK) rc = make_pm_tensor_map(&tk[1].tmB, d + ob, b_cols, b_rows, ldb, nb, 0, 1, 64);
+    if (rc) { cudaFree(d); cudaFree(d_tasks); cudaFree(flag); return rc; }
+    SACB_CUDA(cudaMemcpy(d_tasks, tk, sizeof(tk), cudaMemcpyHostToDevice));
+    gemm_selftest_kernel<SACB_MATH_FP32><<<tk[0].n_tiles, kThreads, kSimtSmemBytes>>>(d_tasks, bases, flag);
+    SACB_CUDA(cudaFuncSetAttribute(gemm_selftest_kernel<SACB_MATH_BF16X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes));
+    gemm_selftest_kernel<SACB_MATH_BF16X3><<<std::min(tk[1].n_tiles, 148), kThreads, kTcSmemBytes>>>(d_tasks + 1, bases, flag);
     SACB_CUDA(cudaDeviceSynchronize());
     int hf = 0;
     SACB_CUDA(cudaMemcpy(&hf, flag, sizeof(int), cudaMemcpyDeviceToHost));
     SACB_CUDA(cudaMemcpy(c0.data(), d + oc0, sizeof(float) * nc, cudaMemcpyDeviceToHost));
     SACB_CUDA(cudaMemcpy(c1.data(), d + oc1, sizeof(float) * nc, cudaMemcpyDeviceToHost));
-    cudaFree(d); cudaFree(flag);
+    cudaFree(d); cudaFree(d_tasks); cudaFree(flag);
     // host reference in double on a sample of entries pins the FFMA tile itself
     double maxref = 0, maxdiff = 0, maxdiff_host = 0;
     for (int64_t i = 0; i < nc; i++) { maxref = std::max(maxref, (double)fabsf(c0[i])); maxdiff = std::max(maxdiff, (double)fabsf(c0[i] - c1[i])); }
     for (int64_t i = 0; i < nc; i += std::max<int64_t>(1, nc / 257)) {
-        const int m = (int)(i / N), n = (int)(i % N);
+        const int m = (int)(i / N), n = (int)(i % N) + b_r0;
         double acc = 0;
-        for (int k = 0; k < K; k++) acc += (double)(a_mn ? ha[(int64_t)k * lda + m] : ha[(int64_t)m * lda + k]) * (double)(b_mn ? hb[(int64_t)k * ldb + n] : hb[(int64_t)n * ldb + k]);
+        for (int k = 0; k < K; k++) acc += (double)(a_mn ? va[(int64_t)k * lda + m] : va[(int64_t)m * lda + k]) * (double)(b_mn ? vb[(int64_t)k * ldb + n] : vb[(int64_t)n * ldb + k]);
         maxdiff_host = std::max(maxdiff_host, fabs(acc - (double)c0[i]));
     }
-    if (hf) return fail(SACB_ERR_DEVICE, "tcgen05 pipeline watchdog fired in the self test");
+    if (hf) return fail(SACB_ERR_DEVICE, "tcgen05 / TMA pipeline watchdog fired in the self test");
     if (maxdiff_host > 1e-4 * std::max(1.0, maxref)) return fail(SACB_ERR_DEVICE, "FFMA tile disagrees with the host reference");
     *rel_err_out = (float)(maxdiff / std::max(maxref, 1e-30));
     return SACB_OK;

@@ -33,6 +33,12 @@ struct NetLayout {
     int64_t w[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};         // hidden layer l (0-based) weight [H,in_l] / bias [H]
     int64_t w_out = 0, b_out = 0;                             // output layer / fused heads
     int64_t size = 0;                                         // floats, multiple of 32
+    // bf16 hi/lo shadow PMs of the GEMM weights (offsets in floats inside the net's shadow block):
+    // hidden layer l: [hidden, sh_ld[l]] ; policy heads: [2A, hidden] (Q output layers are read as fp32 vectors)
+    // critics additionally keep the action block fc1.weight[:, obs:] as its own PM [hidden, sh_act_ld] (TMA boxes must
+    // start 16 B aligned along the contiguous dimension, column `obs` of the full shadow generally does not)
+    int64_t sh_w[4] = {0, 0, 0, 0}, sh_out = 0, sh_act = 0, sh_size = 0;
+    int sh_ld[4] = {0, 0, 0, 0}, sh_act_ld = 0;
     int in_of(int l) const { return l == 0 ? in_dim : hidden; }
     int n_tensors() const { return is_policy ? 2 * n_hidden + 4 : 2 * n_hidden + 2; }
     // API tensor -> (offset in net, rows, cols)
@@ -40,19 +46,24 @@ struct NetLayout {
 };
 
 struct Layout {
-    int obs = 0, act = 0, hidden = 0, n_hidden = 0, maxB = 0, ldx = 0, ldg = 0;   // ldg: row stride of g_head (2A padded to 4)
+    int obs = 0, act = 0, hidden = 0, n_hidden = 0, maxB = 0;
+    int ldx = 0, ldg = 0;           // row strides (bf16 elements, multiples of 8) of the X and g_head PMs
     NetLayout pol, q;
-    // arena (per agent): scalars | params pol,q1,q2,q1t,q2t | m pol,q1,q2 | v pol,q1,q2 | grad pol,q1,q2
+    // arena (per agent): scalars | params pol,q1,q2,q1t,q2t | m pol,q1,q2 | v pol,q1,q2 | grad pol,q1,q2 | shadows x5
     int64_t scalars = 0;
     int64_t param[5] = {0, 0, 0, 0, 0};
+    int64_t shadow[5] = {0, 0, 0, 0, 0};
     int64_t adam_m[3] = {0, 0, 0}, adam_v[3] = {0, 0, 0}, grad[3] = {0, 0, 0};
     int64_t grad_scalars = 0;       // exported log_alpha gradient
     int64_t arena_size = 0;
     // workspace (per agent)
-    int64_t X = 0, r = 0, d = 0, isw = 0, y = 0, td = 0, dq[2] = {0, 0}, dqa[2] = {0, 0}, logp = 0, eps = 0;
-    int64_t head_raw = 0, g_head = 0, da[2] = {0, 0}, wsnap[2] = {0, 0}, loss_part = 0, aloss_part = 0;
-    int64_t hp[4] = {0, 0, 0, 0}, dhp[4] = {0, 0, 0, 0};                 // policy activations [2B,H] / grads [B,H]
-    int64_t ht[2][4], hc[2][4], ha[2][4], dhc[2][4], dha[2][4];          // [B,H]
+    // fp32 vectors / small matrices
+    int64_t r = 0, d = 0, isw = 0, y = 0, td = 0, dq[2] = {0, 0}, logp = 0, eps = 0;
+    int64_t head_raw = 0, da[2] = {0, 0}, loss_part = 0, aloss_part = 0;
+    // pair matrices (float offsets of the hi plane; the lo plane follows the whole hi plane, sized for maxB rows)
+    int64_t X = 0, g_head = 0;                                           // [3*maxB, ldx], [maxB, ldg]
+    int64_t hp[4] = {0, 0, 0, 0}, dhp[4] = {0, 0, 0, 0};                 // policy activations [2*maxB,H] / grads [maxB,H]
+    int64_t ht[2][4], hc[2][4], ha[2][4], dhc[2][4], dha[2][4];          // [maxB,H]
     int64_t ws_size = 0;
     void build(int obs, int act, int hidden, int n_hidden, int maxB);
 };
@@ -88,6 +99,7 @@ struct sacb_handle_s {
     unsigned int *barrier = nullptr;
     int32_t *error_flag = nullptr;
     int32_t *slots = nullptr;            // [n_agents, maxB] physical ring slots of the current minibatch
+    int32_t *slots_identity = nullptr;   // 0..maxB-1: "gather" straight from the upload staging rows (sacb_update_batch)
     int32_t *slots_staged = nullptr;     // pre-staged index sets (sacb_stage_indices)
     int64_t staged_steps = 0, staged_next = 0, staged_B = 0;
     std::map<sacb::ProgramKey, sacb::ProgramInst> programs;
@@ -109,12 +121,17 @@ struct sacb_handle_s {
     // pinned host staging
     float *pin = nullptr;
     int64_t pin_floats = 0;
+    float *pin_rows = nullptr;           // packed minibatch rows of sacb_update_batch
+    int64_t pin_rows_cap = 0;
 };
 
 namespace sacb {
 inline bool math_is_tc(int m) { return m != SACB_MATH_FP32; }
-inline int math_split(int m) { return m == SACB_MATH_TF32X3 ? 2 : 1; }
-inline size_t math_smem(int m) { return math_is_tc(m) ? (size_t)tc_smem_bytes(math_split(m)) : (size_t)kSimtSmemBytes; }
+inline size_t math_smem(int m) { return math_is_tc(m) ? (size_t)kTcSmemBytes : (size_t)kSimtSmemBytes; }
+// TMA descriptor of a pair-matrix view (program.cu): dims {cols, rows, 2 planes, n_agents}, box {64, box_rows, 2, 1},
+// bf16, SWIZZLE_128B.  base = device pointer of the view's first hi element for agent 0.
+int make_pm_tensor_map(CUtensorMap *out, const void *base, int64_t cols, int64_t rows, int64_t ld, int64_t plane_elems,
+                       int64_t agent_stride_bytes, int n_agents, int box_rows);
 const void *update_kernel_for(int math_mode);
 // program.cu
 int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out);

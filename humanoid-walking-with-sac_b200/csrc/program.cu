@@ -3,6 +3,8 @@
 // Reference semantics: sac_imp.SAC.update_parameters (sac_imp.py:74-144), in its order of operations
 // (SURVEY 3.2): target with pre-step policy/targets -> twin critic MSE + Adam -> actor through the UPDATED
 // critics + Adam -> temperature + Adam -> Polyak.
+#include <algorithm>
+#include <string>
 #include <tuple>
 #include <cstring>
 #include <cstdio>
@@ -36,7 +38,7 @@ void NetLayout::tensor(int t, int64_t &off, int64_t &rows, int64_t &cols) const 
     }
 }
 
-static void build_net(NetLayout &n, bool is_policy, int in_dim, int hidden, int n_hidden, int out_dim) {
+static void build_net(NetLayout &n, bool is_policy, int in_dim, int hidden, int n_hidden, int out_dim, int act_cols) {
     n.is_policy = is_policy; n.in_dim = in_dim; n.hidden = hidden; n.n_hidden = n_hidden; n.out_dim = out_dim;
     int64_t o = 0;
     for (int l = 0; l < n_hidden; l++) {
@@ -46,13 +48,25 @@ static void build_net(NetLayout &n, bool is_policy, int in_dim, int hidden, int 
     n.w_out = o; o = align_up(o + (int64_t)out_dim * hidden, 4);
     n.b_out = o; o = align_up(o + out_dim, 4);
     n.size = align_up(o, 32);
+    // shadows: a PM of R rows and row stride ld (bf16) takes R*ld floats (two planes of R*ld bf16)
+    o = 0;
+    for (int l = 0; l < n_hidden; l++) {
+        n.sh_ld[l] = (int)align_up(n.in_of(l), 8);
+        n.sh_w[l] = o; o = align_up(o + (int64_t)hidden * n.sh_ld[l], 32);
+    }
+    n.sh_out = o;
+    if (is_policy) o = align_up(o + (int64_t)out_dim * hidden, 32);
+    n.sh_act = o; n.sh_act_ld = (int)align_up(std::max(act_cols, 1), 8);
+    if (!is_policy) o = align_up(o + (int64_t)hidden * n.sh_act_ld, 32);
+    n.sh_size = align_up(o, 32);
 }
 
 void Layout::build(int obs_, int act_, int hidden_, int n_hidden_, int maxB_) {
     obs = obs_; act = act_; hidden = hidden_; n_hidden = n_hidden_; maxB = maxB_;
-    ldx = (int)align_up(obs + act, 4);
-    build_net(pol, true, obs, hidden, n_hidden, 2 * act);
-    build_net(q, false, obs + act, hidden, n_hidden, 1);
+    ldx = (int)align_up(obs + act, 8);
+    ldg = (int)align_up(2 * act, 8);
+    build_net(pol, true, obs, hidden, n_hidden, 2 * act, 0);
+    build_net(q, false, obs + act, hidden, n_hidden, 1, act);
     int64_t o = 0;
     scalars = o; o += 32;
     param[0] = o; o += pol.size;
@@ -62,6 +76,8 @@ void Layout::build(int obs_, int act_, int hidden_, int n_hidden_, int maxB_) {
     for (int k = 0; k < 3; k++) { adam_v[k] = o; o += sz[k]; }
     for (int k = 0; k < 3; k++) { grad[k] = o; o += sz[k]; }
     grad_scalars = o; o += 32;
+    shadow[0] = o; o += pol.sh_size;
+    for (int k = 1; k < 5; k++) { shadow[k] = o; o += q.sh_size; }
     arena_size = align_up(o, 64);
     // workspace
     const int64_t B = maxB, H = hidden, A = act;
@@ -69,12 +85,11 @@ void Layout::build(int obs_, int act_, int hidden_, int n_hidden_, int maxB_) {
     o = 0;
     X = take(3 * B * ldx);
     r = take(B); d = take(B); isw = take(B); y = take(B); td = take(B);
-    dq[0] = take(B); dq[1] = take(B); dqa[0] = take(B); dqa[1] = take(B);
+    dq[0] = take(B); dq[1] = take(B);
     logp = take(2 * B); eps = take(2 * B * A);
-    head_raw = take(2 * B * 2 * A); ldg = (int)align_up(2 * A, 4); g_head = take(B * ldg);
+    head_raw = take(2 * B * 2 * A); g_head = take(B * ldg);
     da[0] = take(B * A); da[1] = take(B * A);
-    wsnap[0] = take(H); wsnap[1] = take(H);
-    loss_part = take(2 * ((B + 7) / 8) + 8); aloss_part = take(2 * ((B + 7) / 8) + 8);
+    loss_part = take(2 * ((B + kLossRows - 1) / kLossRows) + 8); aloss_part = take(2 * ((B + kLossRows - 1) / kLossRows) + 8);
     for (int l = 0; l < n_hidden; l++) { hp[l] = take(2 * B * H); dhp[l] = take(B * H); }
     for (int k = 0; k < 2; k++)
         for (int l = 0; l < n_hidden; l++) {
@@ -85,9 +100,45 @@ void Layout::build(int obs_, int act_, int hidden_, int n_hidden_, int maxB_) {
 }
 
 // ================================================================================================================
+// TMA descriptors
+// ================================================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {     // resolved through the runtime: the library does not link libcuda (it must load on GPU-less build hosts)
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+int make_pm_tensor_map(CUtensorMap *out, const void *base, int64_t cols, int64_t rows, int64_t ld, int64_t plane_elems,
+                       int64_t agent_stride_bytes, int n_agents, int box_rows) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(SACB_ERR_DEVICE, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+    if (ld % 8 || plane_elems % 8 || agent_stride_bytes % 16 || (reinterpret_cast<uintptr_t>(base) & 15))
+        return fail(SACB_ERR_ARG, "pair matrix is not 16-byte aligned for TMA");
+    const cuuint64_t dims[4] = {(cuuint64_t)cols, (cuuint64_t)rows, 2, (cuuint64_t)n_agents};
+    const cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)plane_elems * 2, (cuuint64_t)std::max<int64_t>(agent_stride_bytes, 16)};
+    const cuuint32_t box[4] = {64, (cuuint32_t)box_rows, 2, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(SACB_ERR_DEVICE, "cuTensorMapEncodeTiled failed (code " + std::to_string((int)r) + ")");
+    return SACB_OK;
+}
+
+// ================================================================================================================
 // kernel
 // ================================================================================================================
 __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int target, int *error_flag) {
+    // writers: generic-proxy global stores of this stage must be visible to the TMA (async proxy) reads of the next
+    tc::fence_proxy_async();
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -102,6 +153,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
         __threadfence();
     }
     __syncthreads();
+    tc::fence_proxy_async();
 }
 
 template <int kMath>
@@ -110,7 +162,6 @@ sac_update_kernel(const Program P, const int stage_begin, const int stage_end, c
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint64_t s_bars[2 * kTStages + 1];
     __shared__ uint32_t s_tmem;
-    __shared__ uint32_t s_consumed;
     __shared__ float s_red[kThreads];
 
     auto stamp = [&](int slot) {
@@ -123,18 +174,13 @@ sac_update_kernel(const Program P, const int stage_begin, const int stage_end, c
     stamp(0);
     tc::TcState st;
     st.g = 0; st.accum_uses = 0; st.tmem_base = 0;
-    st.full_bar = s_bars; st.empty_bar = s_bars + kTStages; st.accum_bar = s_bars + 2 * kTStages; st.consumed = &s_consumed; st.trace = P.trace;
-    constexpr int kSplit = kMath == SACB_MATH_TF32X3 ? 2 : 1;
+    st.full_bar = s_bars; st.empty_bar = s_bars + kTStages; st.accum_bar = s_bars + 2 * kTStages; st.trace = P.trace;
     constexpr bool kTc = kMath != SACB_MATH_FP32;
     st.tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    st.xr = reinterpret_cast<float *>(st.tiles + kTStages * kSplit * kTcStageBytes);
-    st.xk = st.xr + kTM;
     if (kTc && tc_setup) {
         if (threadIdx.x == 0) {
             for (int i = 0; i <= 2 * kTStages; i++) tc::mbar_init(&s_bars[i], 1);
-            s_consumed = 0;
             tc::fence_barrier_init();
-            tc::fence_proxy_async();
         }
         if (threadIdx.x < 32) tc::tmem_alloc(&s_tmem, kTN);
         tc::tc_fence_before();
@@ -157,9 +203,10 @@ sac_update_kernel(const Program P, const int stage_begin, const int stage_end, c
             float *scalars = resolve(P.scalars, P.bases, agent);
             switch (t.type) {
                 case T_GEMM:
-                    if (kTc) gemm_tile_tc<kSplit>(t, tile, P.bases, agent, scalars, st, P.error_flag);
+                    if (kTc) gemm_tile_tc(t, tile, P.bases, agent, scalars, st, P.error_flag);
                     else gemm_tile_ffma(t, tile, P.bases, agent, scalars, reinterpret_cast<float *>(smem_raw));
                     break;
+                case T_SHADOW: task_shadow(t, tile, P, agent); break;
                 case T_GATHER: task_gather(t, tile, P, agent); break;
                 case T_SAMPLE: task_sample(t, tile, P, agent, scalars, seed); break;
                 case T_TARGET_LOSS: task_target_loss(t, tile, P, agent, scalars, s_red); break;
@@ -190,6 +237,12 @@ sac_update_kernel(const Program P, const int stage_begin, const int stage_end, c
 // ================================================================================================================
 namespace {
 
+// a pair-matrix view together with its logical extent (what the TMA descriptor is built from)
+struct PmView {
+    PmRef ref;
+    int rows, cols;     // stored extent of the view: rows x cols valid elements
+};
+
 struct Builder {
     sacb_handle h;
     const Layout &L;
@@ -198,13 +251,36 @@ struct Builder {
     std::vector<Stage> stages;
     std::vector<int> has_gemm;
     int tm, tn;   // GEMM tile dims of the math mode
-    bool stage_open = false;
+    int rc = SACB_OK;
 
     Builder(sacb_handle h_, const ProgramKey &k) : h(h_), L(h_->L), key(k) {
         if (math_is_tc(h->cfg.math_mode)) { tm = kTM; tn = kTN; } else { tm = kSM; tn = kSN; }
     }
     static Ref A(int64_t off) { return make_ref(0, off); }
     static Ref W(int64_t off) { return make_ref(1, off); }
+
+    // view of rows [row0, row0+rows) x cols of a PM whose hi plane starts at float offset `off` of `region`,
+    // has row stride ld and `plane_rows` rows per plane
+    static PmView view(int region, int64_t off, int ld, int64_t plane_rows, int row0, int rows, int cols) {
+        PmView v;
+        v.ref.base = make_ref(region, off + (int64_t)row0 * ld / 2);
+        v.ref.ld = ld; v.ref.pad = 0; v.ref.plane = plane_rows * ld;
+        v.rows = rows; v.cols = cols;
+        return v;
+    }
+    // activations / gradients [B,H] in the workspace (planes sized for maxB rows)
+    PmView hview(int64_t off, int rows, int row0 = 0, int plane_mult = 1) const {
+        return view(1, off, L.hidden, (int64_t)plane_mult * L.maxB, row0, rows, L.hidden);
+    }
+    PmView xrows(int row0, int rows, int cols) const { return view(1, L.X, L.ldx, 3 * (int64_t)L.maxB, row0, rows, cols); }
+    PmView ghead(int rows) const { return view(1, L.g_head, L.ldg, L.maxB, 0, rows, 2 * L.act); }
+    // weight shadows in the arena
+    PmView wsh(int net, int l) const {
+        const NetLayout &n = net == 0 ? L.pol : L.q;
+        return view(0, L.shadow[net] + n.sh_w[l], n.sh_ld[l], L.hidden, 0, L.hidden, n.in_of(l));
+    }
+    PmView wsh_act(int net) const { return view(0, L.shadow[net] + L.q.sh_act, L.q.sh_act_ld, L.hidden, 0, L.hidden, L.act); }
+    PmView wsh_head() const { return view(0, L.shadow[0] + L.pol.sh_out, L.hidden, 2 * L.act, 0, 2 * L.act, L.hidden); }
 
     void begin_stage() {
         Stage s{}; s.task_begin = (int)tasks.size(); s.task_end = s.task_begin; s.n_tiles = 0;
@@ -213,10 +289,12 @@ struct Builder {
     Task blank(int type) {
         Task t; memset(&t, 0, sizeof(t));
         t.type = type;
-        t.C = t.bias = t.mask = null_ref();
-        t.A.ptr = t.A.rvec = t.A.cvec = t.B.ptr = t.B.rvec = t.B.cvec = null_ref();
+        t.C = t.bias = null_ref();
+        t.Cpm = t.mask = t.A.pm = t.B.pm = null_pm();
         t.adam.w = t.adam.m = t.adam.v = t.adam.wt = t.adam.gexp = null_ref();
+        t.adam.shadow = t.adam.shadow2 = null_pm();
         for (auto &p : t.p) p = null_ref();
+        for (auto &p : t.pm) p = null_pm();
         return t;
     }
     void add(Task t, int n_tiles) {
@@ -226,23 +304,32 @@ struct Builder {
         if (t.type == T_GEMM) has_gemm.back() = 1;
         tasks.push_back(t);
     }
-    static Operand op(Ref p, int ld, int mn_major) {
-        Operand o; memset(&o, 0, sizeof(o));
-        o.ptr = p; o.ld = ld; o.mn_major = mn_major; o.xform = 0; o.rvec = o.cvec = null_ref();
-        return o;
+    void *dev_ptr(Ref r) const {
+        const int64_t off = r.v & ((1ll << 62) - 1);
+        return ((r.v >> 62) & 1) ? (void *)(h->ws + off) : (void *)(h->arena + off);
     }
-    static Operand op_rank1(Ref h, int ld, int mn_major, Ref rvec, Ref cvec) {
-        Operand o = op(h, ld, mn_major); o.xform = 1; o.rvec = rvec; o.cvec = cvec; return o;
-    }
-    void gemm(Operand a, Operand b, int M, int N, int K, Task t) {
-        t.type = T_GEMM; t.A = a; t.B = b; t.M = M; t.N = N; t.K = K;
+    int64_t agent_stride_bytes(Ref r) const { return (((r.v >> 62) & 1) ? L.ws_size : L.arena_size) * (int64_t)sizeof(float); }
+
+    // C[M,N] = A[M,K] . B[N,K]^T with A, B taken from PM views.  mn_major = 0: the view stores [R, K]; 1: it stores [K, R].
+    // b_r0: the B operand is rows/columns [b_r0, b_r0+N) of the view along its N dimension (TMA boxes need no alignment).
+    void gemm(const PmView &a, int a_mn, const PmView &b, int b_mn, int M, int N, int K, Task t, int b_r0 = 0) {
+        t.type = T_GEMM; t.M = M; t.N = N; t.K = K;
+        t.A.pm = a.ref; t.A.mn_major = a_mn; t.A.r0 = 0; t.B.pm = b.ref; t.B.mn_major = b_mn; t.B.r0 = b_r0;
         t.tiles_m = cdiv(M, tm); t.tiles_n = cdiv(N, tn);
+        if (math_is_tc(h->cfg.math_mode) && rc == SACB_OK) {
+            // stored extents: K-major [R, K] -> cols = K ; MN-major [K, R] -> cols = R.  TMA zero-fills beyond them.
+            const int a_cols = a_mn ? M : K, a_rows = a_mn ? K : M, b_cols = b_mn ? b_r0 + N : K, b_rows = b_mn ? K : b_r0 + N;
+            rc = make_pm_tensor_map(&t.tmA, dev_ptr(a.ref.base), a_cols, a_rows, a.ref.ld, a.ref.plane, agent_stride_bytes(a.ref.base),
+                                    h->cfg.n_agents, a_mn ? 64 : kTM);
+            if (rc == SACB_OK)
+                rc = make_pm_tensor_map(&t.tmB, dev_ptr(b.ref.base), b_cols, b_rows, b.ref.ld, b.ref.plane, agent_stride_bytes(b.ref.base),
+                                        h->cfg.n_agents, 64);
+        }
         add(t, t.tiles_m * t.tiles_n);
     }
-    Task epi_bias_relu(Ref C, int ldc, Ref bias) { Task t = blank(T_GEMM); t.epi = EPI_BIAS_RELU; t.C = C; t.ldc = ldc; t.bias = bias; return t; }
-    Task epi_bias(Ref C, int ldc, Ref bias) { Task t = blank(T_GEMM); t.epi = EPI_BIAS; t.C = C; t.ldc = ldc; t.bias = bias; return t; }
-    Task epi_mask(Ref C, int ldc, Ref mask, int ldm) { Task t = blank(T_GEMM); t.epi = EPI_MASK; t.C = C; t.ldc = ldc; t.mask = mask; t.ld_mask = ldm; return t; }
-    Task epi_store(Ref C, int ldc) { Task t = blank(T_GEMM); t.epi = EPI_STORE; t.C = C; t.ldc = ldc; return t; }
+    Task epi_bias_relu(const PmView &C, Ref bias) { Task t = blank(T_GEMM); t.epi = EPI_BIAS_RELU; t.Cpm = C.ref; t.bias = bias; return t; }
+    Task epi_mask(const PmView &C, const PmView &mask) { Task t = blank(T_GEMM); t.epi = EPI_MASK; t.Cpm = C.ref; t.mask = mask.ref; return t; }
+    Task epi_f32(Ref C, int ldc, Ref bias) { Task t = blank(T_GEMM); t.epi = EPI_F32; t.C = C; t.ldc = ldc; t.bias = bias; return t; }
 
     // which optimizer a trainable net (0 policy, 1 q1, 2 q2) uses
     static int step_slot(int net) { return net == 0 ? SC_STEP_POLICY : (net == 1 ? SC_STEP_Q1 : SC_STEP_Q2); }
@@ -254,56 +341,80 @@ struct Builder {
         a.w = A(L.param[net] + off_in_net); a.m = A(L.adam_m[net] + off_in_net); a.v = A(L.adam_v[net] + off_in_net);
         a.wt = net == 0 ? null_ref() : A(L.param[net + 2] + off_in_net);     // q1 -> q1_target, q2 -> q2_target
         a.gexp = exporting() ? A(L.grad[net] + off_in_net) : null_ref();
+        a.shadow = a.shadow2 = null_pm(); a.shadow2_col0 = 0; a.pad0 = 0;
         a.step_slot = step_slot(net); a.apply = apply() ? 1 : 0;
         a.lr = h->cfg.lr; a.tau = h->cfg.tau;
         return a;
     }
-    Task epi_adam(int net, int64_t off_in_net) { Task t = blank(T_GEMM); t.epi = EPI_ADAM; t.adam = adam_args(net, off_in_net); return t; }
+    // dW epilogue of hidden layer `layer`: the critics are read again (post-step) by the actor phase of the SAME update,
+    // so their shadows are refreshed in the epilogue; policy / target shadows are refreshed at the start of the next step
+    Task epi_adam(int net, int layer) {
+        const NetLayout &n = net == 0 ? L.pol : L.q;
+        Task t = blank(T_GEMM); t.epi = EPI_ADAM; t.adam = adam_args(net, n.w[layer]);
+        if (net != 0) t.adam.shadow = wsh(net, layer).ref;
+        if (net != 0 && layer == 0) { t.adam.shadow2 = wsh_act(net).ref; t.adam.shadow2_col0 = L.obs; }
+        return t;
+    }
 
-    void bias_adam(int net, int64_t b_off, Operand dh, int Bn, int N) {
+    void bias_adam(int net, int64_t b_off, const PmView &dh, int Bn, int N) {
         Task t = blank(T_BIAS_ADAM);
-        t.A = dh;
+        t.pm[0] = dh.ref;
         AdamArgs a = adam_args(net, b_off);
         t.p[0] = a.w; t.p[1] = a.m; t.p[2] = a.v; t.p[3] = a.wt; t.p[4] = a.gexp;
         t.i[0] = Bn; t.i[1] = N; t.i[2] = a.step_slot; t.i[3] = a.apply; t.f[0] = a.lr; t.f[1] = a.tau;
         add(t, cdiv(N, 32));
     }
+    // shadow of columns [col0, col0+dst.cols) of the fp32 matrix at w_off (row stride src_ld)
+    void shadow_task(int net, int64_t w_off, const PmView &dst, int src_ld, int col0 = 0) {
+        Task t = blank(T_SHADOW);
+        t.p[0] = A(L.param[net] + w_off); t.pm[0] = dst.ref; t.i[0] = dst.rows; t.i[1] = dst.cols; t.i[2] = col0; t.i[3] = src_ld;
+        add(t, cdiv(dst.rows, kShadowRows));
+    }
 
     void build() {
-        const int B = key.B, H = L.hidden, nh = L.n_hidden, obs = L.obs, act = L.act, ldx = L.ldx, A2 = 2 * act, ldg = L.ldg;
+        const int B = key.B, H = L.hidden, nh = L.n_hidden, obs = L.obs, act = L.act, A2 = 2 * act;
         const NetLayout &P = L.pol, &Q = L.q;
-        const Ref X2 = W(L.X), X1 = W(L.X + (int64_t)B * ldx), X3 = W(L.X + (int64_t)2 * B * ldx);
         const bool critics = key.dp_phase != 1, actor = key.dp_phase != 0;
+        // X PM rows: [0,B) = (s2, a2)   [B,2B) = (s, a)   [2B,3B) = (s, a_new)
+        auto X2 = [&](int cols) { return xrows(0, B, cols); };
+        auto X1 = [&](int cols) { return xrows(B, B, cols); };
+        auto X3 = [&](int cols) { return xrows(2 * B, B, cols); };
 
-        // ---- stage: gather ------------------------------------------------------------------------------------
+        // ---- stage: weight shadows (+ minibatch gather) --------------------------------------------------------
+        begin_stage();
+        for (int net = 0; net < 5; net++) {
+            if (!critics && (net == 3 || net == 4)) continue;      // the actor phase does not read the targets
+            const NetLayout &n = net == 0 ? P : Q;
+            for (int l = 0; l < nh; l++) shadow_task(net, n.w[l], wsh(net, l), n.in_of(l));
+            if (net == 0) shadow_task(0, P.w_out, wsh_head(), H);
+            if ((net == 1 || net == 2) && actor) shadow_task(net, Q.w[0], wsh_act(net), obs + act, obs);
+        }
         if (key.with_gather && critics) {
-            begin_stage();
             Task t = blank(T_GATHER);
-            t.p[0] = W(L.X); t.p[1] = W(L.r); t.p[2] = W(L.d);
-            t.i[0] = B; t.i[1] = obs; t.i[2] = act; t.i[3] = ldx;
-            add(t, cdiv(B, kThreads / 32));
+            t.pm[0] = xrows(0, 3 * B, L.ldx).ref; t.p[0] = W(L.r); t.p[1] = W(L.d);
+            t.i[0] = B; t.i[1] = obs; t.i[2] = act;
+            add(t, cdiv(B, 4));
         }
         if (critics) {
             // ---- policy forward on [s2 ; s] (M = 2B) + critic forward on (s,a), layer by layer ---------------------
             for (int l = 0; l < nh; l++) {
                 begin_stage();
                 const int in_p = P.in_of(l), in_q = Q.in_of(l);
-                gemm(l == 0 ? op(X2, ldx, 0) : op(W(L.hp[l - 1]), H, 0), op(A(L.param[0] + P.w[l]), in_p, 0), 2 * B, H, in_p,
-                     epi_bias_relu(W(L.hp[l]), H, A(L.param[0] + P.b[l])));
+                gemm(l == 0 ? xrows(0, 2 * B, obs) : hview(L.hp[l - 1], 2 * B, 0, 2), 0, wsh(0, l), 0, 2 * B, H, in_p,
+                     epi_bias_relu(hview(L.hp[l], 2 * B, 0, 2), A(L.param[0] + P.b[l])));
                 for (int k = 0; k < 2; k++)
-                    gemm(l == 0 ? op(X1, ldx, 0) : op(W(L.hc[k][l - 1]), H, 0), op(A(L.param[1 + k] + Q.w[l]), in_q, 0), B, H, in_q,
-                         epi_bias_relu(W(L.hc[k][l]), H, A(L.param[1 + k] + Q.b[l])));
+                    gemm(l == 0 ? X1(obs + act) : hview(L.hc[k][l - 1], B), 0, wsh(1 + k, l), 0, B, H, in_q,
+                         epi_bias_relu(hview(L.hc[k][l], B), A(L.param[1 + k] + Q.b[l])));
             }
-            // ---- policy heads -> head_raw [2B, 2A] -----------------------------------------------------------------
+            // ---- policy heads -> head_raw [2B, 2A] (fp32) ------------------------------------------------------------
             begin_stage();
-            gemm(op(W(L.hp[nh - 1]), H, 0), op(A(L.param[0] + P.w_out), H, 0), 2 * B, A2, H,
-                 epi_bias(W(L.head_raw), A2, A(L.param[0] + P.b_out)));
+            gemm(hview(L.hp[nh - 1], 2 * B, 0, 2), 0, wsh_head(), 0, 2 * B, A2, H, epi_f32(W(L.head_raw), A2, A(L.param[0] + P.b_out)));
             // ---- reparameterised sample + log-prob for both batches -------------------------------------------------
             begin_stage();
             {
                 Task t = blank(T_SAMPLE);
-                t.p[0] = W(L.head_raw); t.p[1] = W(L.eps); t.p[2] = W(L.X); t.p[3] = W(L.logp);
-                t.i[0] = B; t.i[1] = act; t.i[2] = obs; t.i[3] = ldx; t.i[4] = key.device_eps;
+                t.p[0] = W(L.head_raw); t.p[1] = W(L.eps); t.pm[0] = xrows(0, 3 * B, L.ldx).ref; t.p[3] = W(L.logp);
+                t.i[0] = B; t.i[1] = act; t.i[2] = obs; t.i[4] = key.device_eps;
                 t.f[0] = h->cfg.action_scale; t.f[1] = h->cfg.action_bias;
                 add(t, cdiv(2 * B, kThreads / 32));
             }
@@ -312,47 +423,44 @@ struct Builder {
                 begin_stage();
                 const int in_q = Q.in_of(l);
                 for (int k = 0; k < 2; k++)
-                    gemm(l == 0 ? op(X2, ldx, 0) : op(W(L.ht[k][l - 1]), H, 0), op(A(L.param[3 + k] + Q.w[l]), in_q, 0), B, H, in_q,
-                         epi_bias_relu(W(L.ht[k][l]), H, A(L.param[3 + k] + Q.b[l])));
+                    gemm(l == 0 ? X2(obs + act) : hview(L.ht[k][l - 1], B), 0, wsh(3 + k, l), 0, B, H, in_q,
+                         epi_bias_relu(hview(L.ht[k][l], B), A(L.param[3 + k] + Q.b[l])));
             }
-            // ---- Bellman target, critic losses, dL/dq ---------------------------------------------------------------
+            // ---- Bellman target, critic losses, dL/dq, dL/dh of the last hidden layer --------------------------------
             begin_stage();
             {
                 Task t = blank(T_TARGET_LOSS);
-                t.p[0] = W(L.ht[0][nh - 1]); t.p[1] = W(L.ht[1][nh - 1]); t.p[2] = W(L.hc[0][nh - 1]); t.p[3] = W(L.hc[1][nh - 1]);
+                t.pm[0] = hview(L.ht[0][nh - 1], B).ref; t.pm[1] = hview(L.ht[1][nh - 1], B).ref;
+                t.pm[2] = hview(L.hc[0][nh - 1], B).ref; t.pm[3] = hview(L.hc[1][nh - 1], B).ref;
+                t.pm[4] = hview(L.dhc[0][nh - 1], B).ref; t.pm[5] = hview(L.dhc[1][nh - 1], B).ref;
                 const int nets[4] = {3, 4, 1, 2};
                 for (int k = 0; k < 4; k++) { t.p[4 + k] = A(L.param[nets[k]] + Q.w_out); t.p[8 + k] = A(L.param[nets[k]] + Q.b_out); }
                 t.p[12] = W(L.r); t.p[13] = W(L.d); t.p[14] = W(L.logp); t.p[15] = key.use_isw ? W(L.isw) : null_ref();
                 t.p[16] = W(L.y); t.p[17] = W(L.dq[0]); t.p[18] = W(L.dq[1]); t.p[19] = W(L.td);
-                t.p[20] = W(L.wsnap[0]); t.p[21] = W(L.wsnap[1]); t.p[22] = W(L.loss_part);
+                t.p[22] = W(L.loss_part);
                 t.i[0] = B; t.i[1] = H; t.f[0] = h->cfg.gamma;
-                add(t, cdiv(B, kThreads / 32));
+                add(t, cdiv(B, kLossRows));
             }
-            // ---- critic backward.  dh of the last hidden layer is the implicit rank-1 operand dq * w_out * relu' ------
+            // ---- critic backward --------------------------------------------------------------------------------------
             //   stage s (1..nh): dX of layer l = nh-s (0-based, only while l >= 1) ; dW/db of layer l+1 ; last stage: dW/db of layer 0
             for (int s = 1; s <= nh; s++) {
                 begin_stage();
                 const int l = nh - s;          // layer whose dX is produced now (needs dh_l, writes dh_{l-1})
                 for (int k = 0; k < 2; k++) {
                     const int net = 1 + k;
-                    auto dh = [&](int layer, int mn_major) {   // dL/dh_layer as [B,H] operand
-                        return layer == nh - 1 ? op_rank1(W(L.hc[k][nh - 1]), H, mn_major, W(L.dq[k]), W(L.wsnap[k]))
-                                               : op(W(L.dhc[k][layer]), H, mn_major);
-                    };
                     if (l >= 1)   // dh_{l-1} = (dh_l . W_l) * relu'(h_{l-1})
-                        gemm(dh(l, 0), op(A(L.param[net] + Q.w[l]), Q.in_of(l), 1), B, Q.in_of(l), H,
-                             epi_mask(W(L.dhc[k][l - 1]), H, W(L.hc[k][l - 1]), H));
-                    auto dW = [&](int layer) {   // dW_layer = dh_layer^T . x_layer ; fused Adam + Polyak
+                        gemm(hview(L.dhc[k][l], B), 0, wsh(net, l), 1, B, Q.in_of(l), H, epi_mask(hview(L.dhc[k][l - 1], B), hview(L.hc[k][l - 1], B)));
+                    auto dW = [&](int layer) {   // dW_layer = dh_layer^T . x_layer ; fused Adam + Polyak + shadow refresh
                         const int in = Q.in_of(layer);
-                        gemm(dh(layer, 1), layer == 0 ? op(X1, ldx, 1) : op(W(L.hc[k][layer - 1]), H, 1), H, in, B, epi_adam(net, Q.w[layer]));
-                        bias_adam(net, Q.b[layer], dh(layer, 0), B, H);
+                        gemm(hview(L.dhc[k][layer], B), 1, layer == 0 ? X1(in) : hview(L.hc[k][layer - 1], B), 1, H, in, B, epi_adam(net, layer));
+                        bias_adam(net, Q.b[layer], hview(L.dhc[k][layer], B), B, H);
                     };
                     if (l + 1 <= nh - 1) dW(l + 1);
                     if (s == nh) dW(0);
-                    if (s == 1) {   // output layer (reads the live w_out; the rank-1 transforms read the snapshot)
+                    if (s == 1) {   // output layer
                         Task t = blank(T_OUT_ADAM);
                         AdamArgs aw = adam_args(net, Q.w_out), ab = adam_args(net, Q.b_out);
-                        t.p[0] = W(L.hc[k][nh - 1]); t.p[1] = W(L.dq[k]);
+                        t.pm[0] = hview(L.hc[k][nh - 1], B).ref; t.p[1] = W(L.dq[k]);
                         t.p[2] = aw.w; t.p[3] = aw.m; t.p[4] = aw.v; t.p[5] = aw.wt; t.p[6] = aw.gexp;
                         t.p[7] = ab.w; t.p[8] = ab.m; t.p[9] = ab.v; t.p[10] = ab.wt; t.p[11] = ab.gexp;
                         t.i[0] = B; t.i[1] = H; t.i[2] = aw.step_slot; t.i[3] = aw.apply; t.f[0] = aw.lr; t.f[1] = aw.tau;
@@ -367,18 +475,19 @@ struct Builder {
                 begin_stage();
                 const int in_q = Q.in_of(l);
                 for (int k = 0; k < 2; k++)
-                    gemm(l == 0 ? op(X3, ldx, 0) : op(W(L.ha[k][l - 1]), H, 0), op(A(L.param[1 + k] + Q.w[l]), in_q, 0), B, H, in_q,
-                         epi_bias_relu(W(L.ha[k][l]), H, A(L.param[1 + k] + Q.b[l])));
+                    gemm(l == 0 ? X3(obs + act) : hview(L.ha[k][l - 1], B), 0, wsh(1 + k, l), 0, B, H, in_q,
+                         epi_bias_relu(hview(L.ha[k][l], B), A(L.param[1 + k] + Q.b[l])));
             }
             begin_stage();
             {
                 Task t = blank(T_ACTOR_LOSS);
-                t.p[0] = W(L.ha[0][nh - 1]); t.p[1] = W(L.ha[1][nh - 1]);
+                t.pm[0] = hview(L.ha[0][nh - 1], B).ref; t.pm[1] = hview(L.ha[1][nh - 1], B).ref;
+                t.pm[2] = hview(L.dha[0][nh - 1], B).ref; t.pm[3] = hview(L.dha[1][nh - 1], B).ref;
                 t.p[2] = A(L.param[1] + Q.w_out); t.p[3] = A(L.param[2] + Q.w_out);
                 t.p[4] = A(L.param[1] + Q.b_out); t.p[5] = A(L.param[2] + Q.b_out);
-                t.p[6] = W(L.logp + B); t.p[7] = W(L.dqa[0]); t.p[8] = W(L.dqa[1]); t.p[9] = W(L.aloss_part);
+                t.p[6] = W(L.logp + B); t.p[9] = W(L.aloss_part);
                 t.i[0] = B; t.i[1] = H; t.f[0] = -(float)act;
-                add(t, cdiv(B, kThreads / 32));
+                add(t, cdiv(B, kLossRows));
             }
             // ---- dL/da through both critics (input gradients only: the Q weights are constants here, quirk Q2) -------
             for (int s = 1; s <= nh; s++) {
@@ -386,46 +495,43 @@ struct Builder {
                 const int l = nh - s;
                 for (int k = 0; k < 2; k++) {
                     const int net = 1 + k;
-                    Operand dh = l == nh - 1 ? op_rank1(W(L.ha[k][nh - 1]), H, 0, W(L.dqa[k]), A(L.param[net] + Q.w_out))
-                                             : op(W(L.dha[k][l]), H, 0);
                     if (l >= 1)
-                        gemm(dh, op(A(L.param[net] + Q.w[l]), H, 1), B, H, H, epi_mask(W(L.dha[k][l - 1]), H, W(L.ha[k][l - 1]), H));
-                    else   // layer 0: only the action columns of W_0 [H, obs+act]
-                        gemm(dh, op(A(L.param[net] + Q.w[0] + obs), obs + act, 1), B, act, H, epi_store(W(L.da[k]), act));
+                        gemm(hview(L.dha[k][l], B), 0, wsh(net, l), 1, B, H, H, epi_mask(hview(L.dha[k][l - 1], B), hview(L.ha[k][l - 1], B)));
+                    else   // layer 0: only the action columns [obs, obs+act) of W_0 [H, obs+act] (their own shadow PM)
+                        gemm(hview(L.dha[k][0], B), 0, wsh_act(net), 1, B, act, H, epi_f32(W(L.da[k]), act, null_ref()));
                 }
             }
             begin_stage();
             {
                 Task t = blank(T_SAMPLE_BWD);
                 t.p[0] = W(L.da[0]); t.p[1] = W(L.da[1]); t.p[2] = W(L.head_raw + (int64_t)B * A2); t.p[3] = W(L.eps + (int64_t)B * act);
-                t.p[4] = W(L.g_head);
-                t.i[0] = B; t.i[1] = act; t.i[2] = ldg; t.f[0] = h->cfg.action_scale; t.f[1] = h->cfg.action_bias;
+                t.pm[0] = ghead(B).ref;
+                t.i[0] = B; t.i[1] = act; t.f[0] = h->cfg.action_scale; t.f[1] = h->cfg.action_bias;
                 add(t, cdiv(B * act, kThreads));
             }
             // ---- policy backward (current-state rows B..2B of the policy activations) --------------------------------
             //   stage 0: dh_{nh-1} from the heads ; stage s: dh_{nh-1-s}, dW of the layer above ; last: dW_0
-            auto hp_cur = [&](int l) { return W(L.hp[l] + (int64_t)B * H); };
+            auto hp_cur = [&](int l) { return hview(L.hp[l], B, B, 2); };
             for (int s = 0; s <= nh; s++) {
                 begin_stage();
                 if (s == 0) {
-                    gemm(op(W(L.g_head), ldg, 0), op(A(L.param[0] + P.w_out), H, 1), B, H, A2,
-                         epi_mask(W(L.dhp[nh - 1]), H, hp_cur(nh - 1), H));
+                    gemm(ghead(B), 0, wsh_head(), 1, B, H, A2, epi_mask(hview(L.dhp[nh - 1], B), hp_cur(nh - 1)));
                 } else {
                     const int l = nh - s;      // dh_l available; produce dh_{l-1} (if l >= 1)
                     if (l >= 1)
-                        gemm(op(W(L.dhp[l]), H, 0), op(A(L.param[0] + P.w[l]), H, 1), B, H, H,
-                             epi_mask(W(L.dhp[l - 1]), H, hp_cur(l - 1), H));
+                        gemm(hview(L.dhp[l], B), 0, wsh(0, l), 1, B, H, H, epi_mask(hview(L.dhp[l - 1], B), hp_cur(l - 1)));
                     if (s == 1) {              // heads: dW = g^T h_{nh-1}
-                        gemm(op(W(L.g_head), ldg, 1), op(hp_cur(nh - 1), H, 1), A2, H, B, epi_adam(0, P.w_out));
-                        bias_adam(0, P.b_out, op(W(L.g_head), ldg, 0), B, A2);
+                        Task t = blank(T_GEMM); t.epi = EPI_ADAM; t.adam = adam_args(0, P.w_out);
+                        gemm(ghead(B), 1, hp_cur(nh - 1), 1, A2, H, B, t);
+                        bias_adam(0, P.b_out, ghead(B), B, A2);
                     } else {
                         const int lw = l + 1;  // dW of the layer whose dX ran in the previous stage
-                        gemm(op(W(L.dhp[lw]), H, 1), op(hp_cur(lw - 1), H, 1), H, H, B, epi_adam(0, P.w[lw]));
-                        bias_adam(0, P.b[lw], op(W(L.dhp[lw]), H, 0), B, H);
+                        gemm(hview(L.dhp[lw], B), 1, hp_cur(lw - 1), 1, H, H, B, epi_adam(0, lw));
+                        bias_adam(0, P.b[lw], hview(L.dhp[lw], B), B, H);
                     }
                     if (s == nh) {
-                        gemm(op(W(L.dhp[0]), H, 1), op(X1, ldx, 1), H, obs, B, epi_adam(0, P.w[0]));
-                        bias_adam(0, P.b[0], op(W(L.dhp[0]), H, 0), B, H);
+                        gemm(hview(L.dhp[0], B), 1, X1(obs), 1, H, obs, B, epi_adam(0, 0));
+                        bias_adam(0, P.b[0], hview(L.dhp[0], B), B, H);
                     }
                 }
             }
@@ -438,11 +544,12 @@ struct Builder {
             t.p[1] = actor ? W(L.aloss_part) : null_ref();
             t.p[2] = exporting() ? A(L.grad_scalars) : null_ref();
             t.i[0] = ap; t.i[1] = ap; t.i[2] = ap; t.i[3] = ap && h->cfg.auto_entropy; t.i[4] = ap;
-            t.i[5] = cdiv(B, kThreads / 32); t.i[6] = h->cfg.auto_entropy; t.i[7] = ap;
+            t.i[5] = cdiv(B, kLossRows); t.i[6] = h->cfg.auto_entropy; t.i[7] = ap;
             t.f[0] = h->cfg.lr; t.f[1] = (float)B;
             add(t, 1);
         }
     }
+
 };
 
 }  // namespace
@@ -503,6 +610,7 @@ int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out) {
     if (key.B < 1 || key.B > h->cfg.max_batch) return fail(SACB_ERR_ARG, "batch size exceeds max_batch of the handle");
     Builder b(h, key);
     b.build();
+    if (b.rc != SACB_OK) return b.rc;
     ProgramInst &p = h->programs[key];
     p.tasks = b.tasks; p.stages = b.stages; p.stage_has_gemm = b.has_gemm;
     for (auto &s : p.stages) { p.n_tiles_total += s.n_tiles; p.max_stage_tiles = std::max(p.max_stage_tiles, s.n_tiles); }
@@ -516,8 +624,12 @@ int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out) {
     P.bases.arena = h->arena; P.bases.ws = h->ws; P.bases.arena_stride = h->L.arena_size; P.bases.ws_stride = h->L.ws_size;
     P.scalars = make_ref(0, h->L.scalars);
     P.barrier = h->barrier;
-    P.ring = h->ring; P.ring_agent_stride = h->cfg.capacity * h->ring_row; P.ring_row = (int32_t)h->ring_row;
-    P.slots = h->slots; P.slots_stride = h->cfg.max_batch;
+    if (key.with_gather == 2) {   // minibatch supplied by the caller: rows staged in upload order (sacb_update_batch)
+        P.ring = h->stage_rows; P.ring_agent_stride = 0; P.slots = h->slots_identity;
+    } else {
+        P.ring = h->ring; P.ring_agent_stride = h->cfg.capacity * h->ring_row; P.slots = h->slots;
+    }
+    P.ring_row = (int32_t)h->ring_row; P.slots_stride = h->cfg.max_batch;
     P.error_flag = h->error_flag;
     P.trace = nullptr;
     p.kernels_per_step = h->cfg.launch_mode == SACB_LAUNCH_PERSISTENT ? 1 : (int)p.stages.size();
@@ -581,14 +693,18 @@ extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap
                 SACB_CUDA(cudaStreamSynchronize(h->stream));
                 const int grid = std::max(1, p->stages[s].n_tiles * h->cfg.n_agents);
                 SACB_CUDA(cudaMemcpy(h_trace.data(), d_trace, sizeof(unsigned long long) * 8 * std::min(grid, 4096), cudaMemcpyDeviceToHost));
-                double a[8] = {0}; unsigned long long t0 = ~0ull, t5 = 0;
+                double a[8] = {0}, mx_tile = 0, mx_main = 0; unsigned long long t0 = ~0ull, t0max = 0, t5 = 0;
                 const int g = std::min(grid, 4096);
-                for (int b = 0; b < g; b++) { t0 = std::min(t0, h_trace[b * 8]); t5 = std::max(t5, h_trace[b * 8 + 5]);
-                    a[1] += (double)(h_trace[b * 8 + 1] - h_trace[b * 8]); a[2] += (double)(h_trace[b * 8 + 2] - h_trace[b * 8 + 1]);
-                    a[3] += (double)(h_trace[b * 8 + 3] - h_trace[b * 8 + 2]); a[4] += (double)(h_trace[b * 8 + 4] - h_trace[b * 8 + 1]);
-                    a[5] += (double)(h_trace[b * 8 + 5] - h_trace[b * 8 + 4]); }
-                fprintf(stderr, "[trace] stage %2d grid %4d has_gemm %d  span %.2f us | per-CTA avg: setup %.2f  mainloop %.2f  epilogue %.2f  tile %.2f  teardown %.2f us\n",
-                        s, grid, p->stage_has_gemm[s], (t5 - t0) * 1e-3, a[1] / g * 1e-3, a[2] / g * 1e-3, a[3] / g * 1e-3, a[4] / g * 1e-3, a[5] / g * 1e-3);
+                for (int b = 0; b < g; b++) {
+                    const unsigned long long *q = &h_trace[b * 8];
+                    t0 = std::min(t0, q[0]); t0max = std::max(t0max, q[0]); t5 = std::max(t5, q[5]);
+                    a[1] += (double)(q[1] - q[0]); a[4] += (double)(q[4] - q[1]); a[5] += (double)(q[5] - q[4]);
+                    mx_tile = std::max(mx_tile, (double)(q[4] - q[1]));
+                    if (p->stage_has_gemm[s]) { a[2] += (double)(q[2] - q[1]); a[3] += (double)(q[3] - q[2]); mx_main = std::max(mx_main, (double)(q[2] - q[1])); }
+                }
+                fprintf(stderr, "[trace] stage %2d grid %4d gemm %d span %6.2f us start-skew %5.2f | per-CTA avg: setup %.2f mainloop %.2f (max %.2f) epilogue %.2f tile %.2f (max %.2f) teardown %.2f\n",
+                        s, grid, p->stage_has_gemm[s], (t5 - t0) * 1e-3, (t0max - t0) * 1e-3, a[1] / g * 1e-3, a[2] / g * 1e-3, mx_main * 1e-3, a[3] / g * 1e-3,
+                        a[4] / g * 1e-3, mx_tile * 1e-3, a[5] / g * 1e-3);
             }
         }
         SACB_CUDA(cudaStreamSynchronize(h->stream));
@@ -604,14 +720,11 @@ extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap
 
 namespace sacb {
 const void *update_kernel_for(int m) {
-    return m == SACB_MATH_TF32X3 ? (const void *)sac_update_kernel<SACB_MATH_TF32X3>
-         : m == SACB_MATH_TF32   ? (const void *)sac_update_kernel<SACB_MATH_TF32>
-                                 : (const void *)sac_update_kernel<SACB_MATH_FP32>;
+    return m == SACB_MATH_BF16X3 ? (const void *)sac_update_kernel<SACB_MATH_BF16X3> : (const void *)sac_update_kernel<SACB_MATH_FP32>;
 }
 int init_kernel_attributes(sacb_handle h) {
     const int m = h->cfg.math_mode;
-    if (m < 0 || m > SACB_MATH_TF32X3) return fail(SACB_ERR_ARG, "bad math_mode");
-    if (math_is_tc(m) && (h->cfg.hidden_dim > tc::kXkMax || h->cfg.max_batch > tc::kXkMax)) return fail(SACB_ERR_ARG, "tensor-core modes need hidden_dim, max_batch <= 2048");
+    if (m != SACB_MATH_FP32 && m != SACB_MATH_BF16X3) return fail(SACB_ERR_ARG, "bad math_mode");
     SACB_CUDA(cudaFuncSetAttribute(update_kernel_for(m), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)math_smem(m)));
     int nb = 0;
     SACB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, update_kernel_for(m), kThreads, math_smem(m)));

@@ -2,6 +2,7 @@
 #include <cstdio>
 #include <cstring>
 #include <algorithm>
+#include <vector>
 
 #include "handle.h"
 #include "gemm.cuh"
@@ -25,7 +26,7 @@ extern "C" void sacb_default_config(sacb_config *c) {
     c->replay_kind = SACB_REPLAY_UNIFORM; c->capacity = 1000000;                                  // replay_buffer.py:7
     c->per_alpha = 0.6f; c->per_beta_start = 0.4f; c->per_beta_frames = 100000;                   // replay_buffer.py:26
     c->max_batch = 256; c->n_agents = 1;
-    c->math_mode = SACB_MATH_TF32X3; c->launch_mode = SACB_LAUNCH_STAGED; c->device = 0; c->seed = 0x5ac0b200ull;
+    c->math_mode = SACB_MATH_BF16X3; c->launch_mode = SACB_LAUNCH_STAGED; c->device = 0; c->seed = 0x5ac0b200ull;
 }
 
 extern "C" int sacb_device_count(void) {
@@ -49,7 +50,7 @@ static int scalars_init(sacb_handle h) {
 
 extern "C" int sacb_create(const sacb_config *cfg, sacb_handle *out) {
     if (!cfg || !out) return fail(SACB_ERR_ARG, "null argument");
-    if (cfg->obs_dim < 1 || cfg->act_dim < 1 || cfg->hidden_dim < 8 || cfg->hidden_dim % 4) return fail(SACB_ERR_ARG, "bad dims (hidden_dim must be a multiple of 4)");
+    if (cfg->obs_dim < 1 || cfg->act_dim < 1 || cfg->hidden_dim < 8 || cfg->hidden_dim % 8) return fail(SACB_ERR_ARG, "bad dims (hidden_dim must be a multiple of 8)");
     if (cfg->n_hidden != 2 && cfg->n_hidden != 3) return fail(SACB_ERR_ARG, "n_hidden must be 2 (networks_model1) or 3 (networks_model2)");
     if (cfg->max_batch < 1 || cfg->n_agents < 1 || cfg->capacity < 1) return fail(SACB_ERR_ARG, "bad max_batch / n_agents / capacity");
     if (2 * cfg->act_dim > 256) return fail(SACB_ERR_ARG, "act_dim > 128 unsupported");
@@ -69,8 +70,15 @@ extern "C" int sacb_create(const sacb_config *cfg, sacb_handle *out) {
     if (cudaMalloc(&h->arena, sizeof(float) * h->L.arena_size * n) != cudaSuccess ||
         cudaMalloc(&h->ws, sizeof(float) * h->L.ws_size * n) != cudaSuccess ||
         cudaMalloc(&h->barrier, 64) != cudaSuccess || cudaMalloc(&h->error_flag, 64) != cudaSuccess ||
-        cudaMalloc(&h->slots, sizeof(int32_t) * cfg->max_batch * n) != cudaSuccess)
+        cudaMalloc(&h->slots, sizeof(int32_t) * cfg->max_batch * n) != cudaSuccess ||
+        cudaMalloc(&h->slots_identity, sizeof(int32_t) * cfg->max_batch) != cudaSuccess)
         return bail(fail(SACB_ERR_NOMEM, "device allocation failed"));
+    {
+        std::vector<int32_t> ident(cfg->max_batch);
+        for (int i = 0; i < cfg->max_batch; i++) ident[i] = i;
+        cudaMemcpyAsync(h->slots_identity, ident.data(), sizeof(int32_t) * cfg->max_batch, cudaMemcpyHostToDevice, h->stream);
+        cudaStreamSynchronize(h->stream);
+    }
     cudaMemsetAsync(h->arena, 0, sizeof(float) * h->L.arena_size * n, h->stream);
     cudaMemsetAsync(h->ws, 0, sizeof(float) * h->L.ws_size * n, h->stream);
     cudaMemsetAsync(h->barrier, 0, 64, h->stream);
@@ -94,8 +102,9 @@ extern "C" int sacb_destroy(sacb_handle h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_programs(h);
     replay_destroy(h);
-    cudaFree(h->arena); cudaFree(h->ws); cudaFree(h->barrier); cudaFree(h->error_flag); cudaFree(h->slots); cudaFree(h->slots_staged);
+    cudaFree(h->arena); cudaFree(h->ws); cudaFree(h->barrier); cudaFree(h->error_flag); cudaFree(h->slots); cudaFree(h->slots_identity); cudaFree(h->slots_staged);
     if (h->pin) cudaFreeHost(h->pin);
+    if (h->pin_rows) cudaFreeHost(h->pin_rows);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return SACB_OK;
@@ -235,18 +244,30 @@ extern "C" int sacb_update_batch(sacb_handle h, int64_t B, const float *s, const
     const Layout &L = h->L;
     if (B < 1 || B > L.maxB) return fail(SACB_ERR_ARG, "batch size out of range");
     float *ws = h->ws;
-    const size_t ldx = sizeof(float) * L.ldx, wo = sizeof(float) * L.obs, wa = sizeof(float) * L.act;
-    float *X2 = ws + L.X, *X1 = X2 + B * L.ldx, *X3 = X1 + B * L.ldx;
-    SACB_CUDA(cudaMemcpy2DAsync(X2, ldx, s2, wo, wo, B, cudaMemcpyHostToDevice, h->stream));
-    SACB_CUDA(cudaMemcpy2DAsync(X1, ldx, s, wo, wo, B, cudaMemcpyHostToDevice, h->stream));
-    SACB_CUDA(cudaMemcpy2DAsync(X3, ldx, s, wo, wo, B, cudaMemcpyHostToDevice, h->stream));
-    SACB_CUDA(cudaMemcpy2DAsync(X1 + L.obs, ldx, a, wa, wa, B, cudaMemcpyHostToDevice, h->stream));
-    SACB_CUDA(cudaMemcpyAsync(ws + L.r, r, sizeof(float) * B, cudaMemcpyHostToDevice, h->stream));
-    SACB_CUDA(cudaMemcpyAsync(ws + L.d, done, sizeof(float) * B, cudaMemcpyHostToDevice, h->stream));
+    // pack the minibatch as replay rows [s | s2 | a | r | d] in pinned memory, one H2D copy into the staging rows;
+    // the program's gather stage (slots = identity) then builds the bf16 pair operands exactly as it does from the ring
+    const int64_t row = h->ring_row;
+    if (B > h->stage_rows_cap) return fail(SACB_ERR_ARG, "batch exceeds the staging capacity");
+    if (h->pin_rows_cap < B) {
+        if (h->pin_rows) cudaFreeHost(h->pin_rows);
+        h->pin_rows = nullptr; h->pin_rows_cap = 0;
+        if (cudaMallocHost(&h->pin_rows, sizeof(float) * row * B) != cudaSuccess) return fail(SACB_ERR_NOMEM, "pinned allocation failed");
+        h->pin_rows_cap = B;
+    }
+    SACB_CUDA(cudaStreamSynchronize(h->stream));     // the previous upload out of the pinned rows has completed
+    for (int64_t b = 0; b < B; b++) {
+        float *dst = h->pin_rows + b * row;
+        memcpy(dst, s + b * L.obs, sizeof(float) * L.obs);
+        memcpy(dst + L.obs, s2 + b * L.obs, sizeof(float) * L.obs);
+        memcpy(dst + 2 * L.obs, a + b * L.act, sizeof(float) * L.act);
+        dst[2 * L.obs + L.act] = r[b];
+        dst[2 * L.obs + L.act + 1] = done[b];
+    }
+    SACB_CUDA(cudaMemcpyAsync(h->stage_rows, h->pin_rows, sizeof(float) * row * B, cudaMemcpyHostToDevice, h->stream));
     if (isw) SACB_CUDA(cudaMemcpyAsync(ws + L.isw, isw, sizeof(float) * B, cudaMemcpyHostToDevice, h->stream));
     int rc = upload_eps(h, 0, B, eps_next, eps_cur);
     if (rc) return rc;
-    ProgramKey key{(int)B, 0, (flags & SACB_EXPORT_GRADS) ? 1 : 0, eps_next ? 0 : 1, isw ? 1 : 0, -1};
+    ProgramKey key{(int)B, 2, (flags & SACB_EXPORT_GRADS) ? 1 : 0, eps_next ? 0 : 1, isw ? 1 : 0, -1};
     ProgramInst *p;
     rc = get_program(h, key, &p);
     if (rc) return rc;
@@ -291,6 +312,30 @@ extern "C" int sacb_update(sacb_handle h, int64_t B, const int64_t *idx, const f
     rc = launch_program(h, *p);
     if (rc) return rc;
     return finish_update(h, losses_out, flags);
+}
+
+// ---- test hook: read back a hidden activation matrix of the last update ----------------------------------------------
+extern "C" int sacb_debug_read_activation(sacb_handle h, int agent, int group, int k, int layer, int64_t B, float *out) {
+    if (!h || !out || agent < 0 || agent >= h->cfg.n_agents || group < 0 || group > 3 || k < 0 || k > 1 || layer < 0 || layer >= h->L.n_hidden ||
+        B < 1 || B > h->L.maxB)
+        return fail(SACB_ERR_ARG, "bad argument");
+    const Layout &L = h->L;
+    const int64_t H = L.hidden, maxB = L.maxB;
+    int64_t off, plane, row0 = 0;
+    if (group == 0) { off = L.hp[layer]; plane = 2 * maxB * H; row0 = B; }          // rows [B, 2B) = current states
+    else { off = group == 1 ? L.hc[k][layer] : group == 2 ? L.ha[k][layer] : L.ht[k][layer]; plane = maxB * H; }
+    const uint16_t *base = reinterpret_cast<const uint16_t *>(h->ws + agent * L.ws_size + off) + row0 * H;
+    std::vector<uint16_t> hi(B * H), lo(B * H);
+    SACB_CUDA(cudaMemcpyAsync(hi.data(), base, sizeof(uint16_t) * B * H, cudaMemcpyDeviceToHost, h->stream));
+    SACB_CUDA(cudaMemcpyAsync(lo.data(), base + plane, sizeof(uint16_t) * B * H, cudaMemcpyDeviceToHost, h->stream));
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    for (int64_t i = 0; i < B * H; i++) {
+        uint32_t a = (uint32_t)hi[i] << 16, b = (uint32_t)lo[i] << 16;
+        float fa, fb;
+        memcpy(&fa, &a, 4); memcpy(&fb, &b, 4);
+        out[i] = fa + fb;
+    }
+    return SACB_OK;
 }
 
 // ---- instrumentation ---------------------------------------------------------------------------------------------

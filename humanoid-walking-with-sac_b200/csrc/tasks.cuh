@@ -1,5 +1,6 @@
-// Non-GEMM tile tasks of the SAC update program (sampling, losses, bias / output-layer optimiser steps).
-// Slot meaning of Task::p / i / f is documented per task; the host builder (program.cu) fills them.
+// Non-GEMM tile tasks of the SAC update program (weight shadows, gather, sampling, losses, bias / output-layer
+// optimiser steps).  Slot meaning of Task::p / pm / i / f is documented per task; the host builder (program.cu)
+// fills them.  Matrices that feed a GEMM are pair matrices (bf16 hi/lo planes, common.cuh).
 #pragma once
 #include "gemm.cuh"
 
@@ -30,12 +31,6 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-__device__ __forceinline__ float row_dot(const float *h, const float *w, int n, int lane) {
-    float s = 0.f;
-    for (int j = lane; j < n; j += 32) s = fmaf(ldcg(h + j), ldcg(w + j), s);
-    return warp_sum(s);
-}
-
 // tanh-Gaussian sample of one action component: networks_model1.py:83-96 == networks_model2.py:104-117
 struct SampleElem { float action, logp, y, std, in_range; };
 __device__ __forceinline__ SampleElem sample_elem(float mean, float ls_raw, float eps, float scale, float bias) {
@@ -54,38 +49,74 @@ __device__ __forceinline__ SampleElem sample_elem(float mean, float ls_raw, floa
     return o;
 }
 
-// T_GATHER: p0=Xall [3B,ldx] ; p1=r ; p2=d ; i0=B i1=obs i2=act i3=ldx ; ring row = [s | s2 | a | r | d] (16 B aligned)
-//   rows [0,B) <- (s2, .)   rows [B,2B) <- (s, a)   rows [2B,3B) <- (s, .)
-// one warp per sampled row: the whole row is fetched with 128-bit streaming loads issued back to back
-__device__ __forceinline__ void task_gather(const Task &t, int tile, const Program &P, int agent) {
-    const int B = t.i[0], obs = t.i[1], act = t.i[2], ldx = t.i[3];
+constexpr int kShadowRows = 64;      // weight rows per T_SHADOW tile (4 per warp)
+constexpr int kLossRows = 4;         // batch rows per T_TARGET_LOSS / T_ACTOR_LOSS tile (4 warps per row)
+
+// T_SHADOW: p0 = fp32 weight matrix (row stride i3) ; pm0 = shadow PM of its columns [i2, i2+i1) ; i0=rows i1=cols.  One warp per row.
+// Runs at the start of every step, so weights written from outside the update (load_state_dict through the
+// aliased torch tensors, checkpoint loads, the data-parallel apply kernel) are always picked up.
+__device__ __forceinline__ void task_shadow(const Task &t, int tile, const Program &P, int agent) {
+    const int rows = t.i[0], cols = t.i[1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int b = tile * (kThreads / 32) + warp;
+    const Pm dst = resolve_pm(t.pm[0], P.bases, agent);
+    const float *src0 = resolve(t.p[0], P.bases, agent) + t.i[2];
+    const bool even = ((t.i[3] | t.i[2]) & 1) == 0;     // every row starts 8 B aligned in src and 4 B aligned in dst
+#pragma unroll 1
+    for (int i = 0; i < kShadowRows / (kThreads / 32); i++) {
+        const int r = tile * kShadowRows + i * (kThreads / 32) + warp;
+        if (r >= rows) return;
+        const float *src = src0 + (int64_t)r * t.i[3];
+        __nv_bfloat16 *q = dst.hi + (int64_t)r * dst.ld;
+        if (even) {
+            for (int c = 2 * lane; c < cols; c += 64) {
+                float2 x = __ldcg(reinterpret_cast<const float2 *>(src + c));
+                if (c + 1 >= cols) x.y = 0.f;
+                uint32_t hi, lo;
+                split_pack2(x.x, x.y, hi, lo);
+                *reinterpret_cast<uint32_t *>(q + c) = hi;
+                *reinterpret_cast<uint32_t *>(q + c + dst.plane) = lo;
+            }
+        } else {
+            for (int c = lane; c < cols; c += 32) {
+                __nv_bfloat16 h, l;
+                split_bf16(ldcg(src + c), h, l);
+                q[c] = h; q[c + dst.plane] = l;
+            }
+        }
+    }
+}
+
+// T_GATHER: pm0 = X PM [3B, ldx] ; p0=r ; p1=d ; i0=B i1=obs i2=act ; ring row = [s | s2 | a | r | d] (16 B aligned)
+//   rows [0,B) <- (s2, .)   rows [B,2B) <- (s, a)   rows [2B,3B) <- (s, .)
+// four warps per sampled row, four rows per tile: 128-bit streaming loads issued back to back, bf16 pair stores
+__device__ __forceinline__ void task_gather(const Task &t, int tile, const Program &P, int agent) {
+    const int B = t.i[0], obs = t.i[1], act = t.i[2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int b = tile * 4 + (warp >> 2), part = warp & 3;
     if (b >= B) return;
-    float *X = resolve(t.p[0], P.bases, agent);
+    const Pm X = resolve_pm(t.pm[0], P.bases, agent);
     const int slot = P.slots[(int64_t)agent * P.slots_stride + b];
     const float4 *row = reinterpret_cast<const float4 *>(P.ring + agent * P.ring_agent_stride + (int64_t)slot * P.ring_row);
-    float *x2 = X + (int64_t)b * ldx, *x1 = X + (int64_t)(B + b) * ldx, *x3 = X + (int64_t)(2 * B + b) * ldx;
-    float *rr = resolve(t.p[1], P.bases, agent), *dd = resolve(t.p[2], P.bases, agent);
+    float *rr = resolve(t.p[0], P.bases, agent), *dd = resolve(t.p[1], P.bases, agent);
     const int nvec = P.ring_row >> 2;
-    for (int v0 = 0; v0 < nvec; v0 += 32 * 8) {
-        float4 buf[8];
+    for (int v0 = 0; v0 < nvec; v0 += 128 * 4) {
+        float4 buf[4];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int v = v0 + u * 32 + lane;
+        for (int u = 0; u < 4; u++) {
+            const int v = v0 + u * 128 + part * 32 + lane;
             buf[u] = v < nvec ? __ldcs(row + v) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const int v = v0 + u * 32 + lane;
+        for (int u = 0; u < 4; u++) {
+            const int v = v0 + u * 128 + part * 32 + lane;
             if (v >= nvec) continue;
             const float e[4] = {buf[u].x, buf[u].y, buf[u].z, buf[u].w};
 #pragma unroll
             for (int q = 0; q < 4; q++) {
                 const int j = 4 * v + q;
-                if (j < obs) { x1[j] = e[q]; x3[j] = e[q]; }
-                else if (j < 2 * obs) x2[j - obs] = e[q];
-                else if (j < 2 * obs + act) x1[obs + (j - 2 * obs)] = e[q];
+                if (j < obs) { pm_store(X, B + b, j, e[q]); pm_store(X, 2 * B + b, j, e[q]); }
+                else if (j < 2 * obs) pm_store(X, b, j - obs, e[q]);
+                else if (j < 2 * obs + act) pm_store(X, B + b, obs + (j - 2 * obs), e[q]);
                 else if (j == 2 * obs + act) rr[b] = e[q];
                 else if (j == 2 * obs + act + 1) dd[b] = e[q];
             }
@@ -93,17 +124,18 @@ __device__ __forceinline__ void task_gather(const Task &t, int tile, const Progr
     }
 }
 
-// T_SAMPLE: p0=head_raw [2B,2A] (mean | log_std_raw) ; p1=eps [2B,A] (null -> Philox) ; p2=Xall ; p3=logp [2B]
-//   i0=B i1=A i2=obs i3=ldx ; f0=scale f1=bias.  row j<B: next-state sample -> X2[j,obs:] ; j>=B: current -> X3[j-B,obs:]
+// T_SAMPLE: p0=head_raw [2B,2A] (mean | log_std_raw) ; p1=eps [2B,A] (i4: 1 -> Philox draw, kept for the backward) ;
+//   pm0 = X PM ; p3=logp [2B] ; i0=B i1=A i2=obs ; f0=scale f1=bias.
+//   row j<B: next-state sample -> X[j, obs:] ; j>=B: current-state sample -> X[2B + (j-B), obs:]
 __device__ __forceinline__ void task_sample(const Task &t, int tile, const Program &P, int agent, const float *scalars, uint64_t seed) {
-    const int B = t.i[0], A = t.i[1], obs = t.i[2], ldx = t.i[3];
+    const int B = t.i[0], A = t.i[1], obs = t.i[2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = tile * (kThreads / 32) + warp;
     if (j >= 2 * B) return;
     const float *head = resolve(t.p[0], P.bases, agent) + (int64_t)j * 2 * A;
     float *eps = resolve(t.p[1], P.bases, agent);
-    float *X = resolve(t.p[2], P.bases, agent);
-    float *dst = (j < B) ? X + (int64_t)j * ldx + obs : X + (int64_t)(2 * B + (j - B)) * ldx + obs;
+    const Pm X = resolve_pm(t.pm[0], P.bases, agent);
+    const int xrow = j < B ? j : 2 * B + (j - B);
     const uint32_t step = (uint32_t)__float_as_int(ldcg(scalars + SC_N_UPDATES));
     float lp = 0.f;
     for (int a = lane; a < A; a += 32) {
@@ -115,120 +147,144 @@ __device__ __forceinline__ void task_sample(const Task &t, int tile, const Progr
             e = ldcg(eps + (int64_t)j * A + a);
         }
         const SampleElem s = sample_elem(ldcg(head + a), ldcg(head + A + a), e, t.f[0], t.f[1]);
-        dst[a] = s.action;
+        pm_store(X, xrow, obs + a, s.action);
         lp += s.logp;
     }
     lp = warp_sum(lp);
     if (lane == 0) resolve(t.p[3], P.bases, agent)[j] = lp;
 }
 
-// dot products of one activation row with up to 4 weight vectors, 128-bit loads, all issued before use
-template <int NV>
-__device__ __forceinline__ void row_dots(const float *(&h)[NV], const float *(&w)[NV], int64_t row_off, int n, int lane, float (&out)[NV]) {
-#pragma unroll
-    for (int k = 0; k < NV; k++) out[k] = 0.f;
-    for (int j = lane * 4; j < n; j += 128) {
-        float4 hv[NV], wv[NV];
-#pragma unroll
-        for (int k = 0; k < NV; k++) {
-            hv[k] = __ldcg(reinterpret_cast<const float4 *>(h[k] + row_off + j));
-            wv[k] = __ldcg(reinterpret_cast<const float4 *>(w[k] + j));
-        }
-#pragma unroll
-        for (int k = 0; k < NV; k++) out[k] += hv[k].x * wv[k].x + hv[k].y * wv[k].y + hv[k].z * wv[k].z + hv[k].w * wv[k].w;
+// dot product of one PM activation row with an fp32 weight vector (H % 8 == 0): 8 elements per lane per trip
+__device__ __forceinline__ float row_dot(const Pm &h, const float *w, int64_t row, int n, int lane) {
+    float s = 0.f;
+    for (int j = lane * 8; j < n; j += 256) {
+        float hv[8];
+        pm_load8(h, row, j, hv);
+        const float4 w0 = __ldcg(reinterpret_cast<const float4 *>(w + j)), w1 = __ldcg(reinterpret_cast<const float4 *>(w + j + 4));
+        s += hv[0] * w0.x + hv[1] * w0.y + hv[2] * w0.z + hv[3] * w0.w + hv[4] * w1.x + hv[5] * w1.y + hv[6] * w1.z + hv[7] * w1.w;
     }
-#pragma unroll
-    for (int k = 0; k < NV; k++) out[k] = warp_sum(out[k]);
+    return warp_sum(s);
 }
 
-// T_TARGET_LOSS (one warp per row, 8 rows per tile): Bellman target + critic MSE terms + dL/dq   (sac_imp.py:92-105)
-//   p0,p1 = last hidden activations of q1_target,q2_target on (s2,a2) [B,H] ; p2,p3 = of q1,q2 on (s,a)
+// dL/dh of the last hidden layer of a critic: dq[b] * w_out[n] * relu'(h[b,n]), written as a PM row (H % 8 == 0)
+__device__ __forceinline__ void write_dh_last(const Pm &dh, const Pm &h, const float *w_out, int64_t row, int n, int lane, float dq) {
+    for (int j = lane * 8; j < n; j += 256) {
+        const uint4 hh = __ldcg(reinterpret_cast<const uint4 *>(h.hi + row * h.ld + j));     // sign of the activation: hi plane
+        const uint32_t hw[4] = {hh.x, hh.y, hh.z, hh.w};
+        const float4 w0 = __ldcg(reinterpret_cast<const float4 *>(w_out + j)), w1 = __ldcg(reinterpret_cast<const float4 *>(w_out + j + 4));
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const float g0 = bf16_bits_to_float(hw[i] & 0xFFFFu) > 0.f ? dq * wv[2 * i] : 0.f;
+            const float g1 = bf16_bits_to_float(hw[i] >> 16) > 0.f ? dq * wv[2 * i + 1] : 0.f;
+            split_pack2(g0, g1, hi[i], lo[i]);
+        }
+        __nv_bfloat16 *q = dh.hi + row * dh.ld + j;
+        *reinterpret_cast<uint4 *>(q) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4 *>(q + dh.plane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+}
+
+// T_TARGET_LOSS: Bellman target + critic MSE terms + dL/dq   (sac_imp.py:92-105).  kLossRows rows per tile, 4 warps per row:
+// warp k of a row forms the output-layer dot product of net k, one thread per row then does the scalar arithmetic,
+// warps 2,3 finally write dL/dh of the last hidden layer of q1,q2.
+//   pm0,pm1 = last hidden activations of q1_target,q2_target on (s2,a2) [B,H] ; pm2,pm3 = of q1,q2 on (s,a)
 //   p4..p7 = output-layer weights [H] of q1t,q2t,q1,q2 ; p8..p11 = their biases [1]
 //   p12=r p13=d p14=logp_next p15=is_weights(null -> 1) ; outputs p16=y p17=dq1 p18=dq2 p19=td (|q1-y|)
-//   p[20],p[21] = snapshot copies of the q1,q2 output weights read by the rank-1 operand transforms
+//   pm4,pm5 = dL/dh of the last hidden layer of q1,q2 [B,H] (consumed by the critic backward GEMMs)
 //   p[22] = per-tile partial sums of w*(q-y)^2 [n_tiles, 2] (summed in tile order by T_FINISH: deterministic)
-//   i0=B i1=H ; f0=gamma.   H % 4 == 0 (checked at create)
+//   i0=B i1=H ; f0=gamma
 __device__ __forceinline__ void task_target_loss(const Task &t, int tile, const Program &P, int agent, const float *scalars, float *smem) {
     const int B = t.i[0], H = t.i[1];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = kThreads / 32;
-    const float *h[4], *w[4];
-    for (int k = 0; k < 4; k++) { h[k] = resolve(t.p[k], P.bases, agent); w[k] = resolve(t.p[4 + k], P.bases, agent); }
-    if (tile == 0) {
-        float *snap1 = resolve(t.p[20], P.bases, agent), *snap2 = resolve(t.p[21], P.bases, agent);
-        for (int j = threadIdx.x; j < H; j += kThreads) { snap1[j] = ldcg(w[2] + j); snap2[j] = ldcg(w[3] + j); }
-    }
-    const int b = tile * nw + warp;
-    float l1 = 0.f, l2 = 0.f;
-    if (b < B) {
-        float q[4];
-        row_dots<4>(h, w, (int64_t)b * H, H, lane, q);
-        if (lane == 0) {
-            for (int k = 0; k < 4; k++) q[k] += ldcg(resolve(t.p[8 + k], P.bases, agent));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rt = warp >> 2, k = warp & 3, b = tile * kLossRows + rt;
+    float *sq = smem, *sd = smem + 16, *sl = smem + 24;      // dots [4 rows][4 nets], dq [4][2], loss terms [4][2]
+    const Pm h = resolve_pm(t.pm[k], P.bases, agent);
+    const float *w = resolve(t.p[4 + k], P.bases, agent);
+    const float q = b < B ? row_dot(h, w, b, H, lane) : 0.f;
+    if (lane == 0) sq[warp] = q;
+    __syncthreads();
+    if (threadIdx.x < kLossRows) {
+        const int r = threadIdx.x, br = tile * kLossRows + r;
+        float l1 = 0.f, l2 = 0.f, dq1 = 0.f, dq2 = 0.f;
+        if (br < B) {
+            float qq[4];
+            for (int j = 0; j < 4; j++) qq[j] = sq[r * 4 + j] + ldcg(resolve(t.p[8 + j], P.bases, agent));
             const int n_upd = __float_as_int(ldcg(scalars + SC_N_UPDATES));
             const float alpha = ldcg(scalars + SC_ALPHA0 + (n_upd & 1));
             const float *isw = resolve(t.p[15], P.bases, agent);
-            const float qn = fminf(q[0], q[1]);
-            const float vt = qn - alpha * ldcg(resolve(t.p[14], P.bases, agent) + b);                                   // sac_imp.py:97
-            const float yy = ldcg(resolve(t.p[12], P.bases, agent) + b) + (1.f - ldcg(resolve(t.p[13], P.bases, agent) + b)) * t.f[0] * vt;   // :98
-            const float wgt = isw ? ldcg(isw + b) : 1.f;
-            const float e1 = q[2] - yy, e2 = q[3] - yy;
-            resolve(t.p[16], P.bases, agent)[b] = yy;
-            resolve(t.p[17], P.bases, agent)[b] = 2.f * wgt * e1 / (float)B;                                          // d mean((q-y)^2) / dq
-            resolve(t.p[18], P.bases, agent)[b] = 2.f * wgt * e2 / (float)B;
-            resolve(t.p[19], P.bases, agent)[b] = fabsf(e1);
+            const float qn = fminf(qq[0], qq[1]);
+            const float vt = qn - alpha * ldcg(resolve(t.p[14], P.bases, agent) + br);                                   // sac_imp.py:97
+            const float yy = ldcg(resolve(t.p[12], P.bases, agent) + br) + (1.f - ldcg(resolve(t.p[13], P.bases, agent) + br)) * t.f[0] * vt;   // :98
+            const float wgt = isw ? ldcg(isw + br) : 1.f;
+            const float e1 = qq[2] - yy, e2 = qq[3] - yy;
+            dq1 = 2.f * wgt * e1 / (float)B;                                                                          // d mean((q-y)^2) / dq
+            dq2 = 2.f * wgt * e2 / (float)B;
+            resolve(t.p[16], P.bases, agent)[br] = yy;
+            resolve(t.p[17], P.bases, agent)[br] = dq1;
+            resolve(t.p[18], P.bases, agent)[br] = dq2;
+            resolve(t.p[19], P.bases, agent)[br] = fabsf(e1);
             l1 = wgt * e1 * e1; l2 = wgt * e2 * e2;
         }
+        sd[2 * r] = dq1; sd[2 * r + 1] = dq2; sl[2 * r] = l1; sl[2 * r + 1] = l2;
     }
-    if (lane == 0) { smem[warp] = l1; smem[nw + warp] = l2; }
     __syncthreads();
+    if (b < B && k >= 2) write_dh_last(resolve_pm(t.pm[2 + k], P.bases, agent), h, w, b, H, lane, sd[2 * rt + (k - 2)]);
     if (threadIdx.x == 0) {
         float s1 = 0.f, s2 = 0.f;
-        for (int i = 0; i < nw; i++) { s1 += smem[i]; s2 += smem[nw + i]; }
+        for (int i = 0; i < kLossRows; i++) { s1 += sl[2 * i]; s2 += sl[2 * i + 1]; }
         float *part = resolve(t.p[22], P.bases, agent);
         part[2 * tile] = s1; part[2 * tile + 1] = s2;
     }
     __syncthreads();
 }
 
-// T_ACTOR_LOSS (one warp per row): policy-loss terms and min-Q routing (sac_imp.py:117-121)
-//   p0,p1 = last hidden activations of q1,q2 on (s, a_new) ; p2,p3 = output weights ; p4,p5 = output biases
-//   p6=logp_cur ; outputs p7=dqa1 p8=dqa2 ; p9 = per-tile partials [n_tiles,2]: sum(alpha*logp - minq), sum(logp + target_entropy)
+// T_ACTOR_LOSS: policy-loss terms and min-Q routing (sac_imp.py:117-121).  Same tiling: warps 0,1 of a row form the two
+// dot products, warps 2,3 write dL/dh of the last hidden layer of q1,q2.
+//   pm0,pm1 = last hidden activations of q1,q2 on (s, a_new) ; p2,p3 = output weights ; p4,p5 = output biases
+//   p6=logp_cur ; pm2,pm3 = dL/dh of the last hidden layer of q1,q2 (the Q weights are constants here, quirk Q2)
+//   p9 = per-tile partials [n_tiles,2]: sum(alpha*logp - minq), sum(logp + target_entropy)
 //   i0=B i1=H ; f0=target_entropy
 __device__ __forceinline__ void task_actor_loss(const Task &t, int tile, const Program &P, int agent, const float *scalars, float *smem) {
     const int B = t.i[0], H = t.i[1];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = kThreads / 32;
-    const float *h[2] = {resolve(t.p[0], P.bases, agent), resolve(t.p[1], P.bases, agent)};
-    const float *w[2] = {resolve(t.p[2], P.bases, agent), resolve(t.p[3], P.bases, agent)};
-    const int b = tile * nw + warp;
-    float pl = 0.f, ent = 0.f;
-    if (b < B) {
-        float q[2];
-        row_dots<2>(h, w, (int64_t)b * H, H, lane, q);
-        if (lane == 0) {
-            const float q1 = q[0] + ldcg(resolve(t.p[4], P.bases, agent)), q2 = q[1] + ldcg(resolve(t.p[5], P.bases, agent));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int rt = warp >> 2, k = warp & 3, b = tile * kLossRows + rt;
+    float *sq = smem, *sd = smem + 16, *sl = smem + 24;
+    const Pm h = resolve_pm(t.pm[k & 1], P.bases, agent);
+    const float *w = resolve(t.p[2 + (k & 1)], P.bases, agent);
+    const float q = (b < B && k < 2) ? row_dot(h, w, b, H, lane) : 0.f;
+    if (lane == 0) sq[warp] = q;
+    __syncthreads();
+    if (threadIdx.x < kLossRows) {
+        const int r = threadIdx.x, br = tile * kLossRows + r;
+        float pl = 0.f, ent = 0.f, d1 = 0.f, d2 = 0.f;
+        if (br < B) {
+            const float q1 = sq[r * 4] + ldcg(resolve(t.p[4], P.bases, agent)), q2 = sq[r * 4 + 1] + ldcg(resolve(t.p[5], P.bases, agent));
             const int n_upd = __float_as_int(ldcg(scalars + SC_N_UPDATES));
             const float alpha = ldcg(scalars + SC_ALPHA0 + (n_upd & 1));
-            const float l = ldcg(resolve(t.p[6], P.bases, agent) + b);
+            const float l = ldcg(resolve(t.p[6], P.bases, agent) + br);
             pl = alpha * l - fminf(q1, q2);                                          // sac_imp.py:119-121
             const float sel = q1 < q2 ? 1.f : (q1 == q2 ? 0.5f : 0.f);               // torch.minimum backward
-            resolve(t.p[7], P.bases, agent)[b] = -sel / (float)B;
-            resolve(t.p[8], P.bases, agent)[b] = -(1.f - sel) / (float)B;
+            d1 = -sel / (float)B;
+            d2 = -(1.f - sel) / (float)B;
             ent = l + t.f[0];
         }
+        sd[2 * r] = d1; sd[2 * r + 1] = d2; sl[2 * r] = pl; sl[2 * r + 1] = ent;
     }
-    if (lane == 0) { smem[warp] = pl; smem[nw + warp] = ent; }
     __syncthreads();
+    if (b < B && k >= 2) write_dh_last(resolve_pm(t.pm[k], P.bases, agent), h, w, b, H, lane, sd[2 * rt + (k - 2)]);
     if (threadIdx.x == 0) {
         float s1 = 0.f, s2 = 0.f;
-        for (int i = 0; i < nw; i++) { s1 += smem[i]; s2 += smem[nw + i]; }
+        for (int i = 0; i < kLossRows; i++) { s1 += sl[2 * i]; s2 += sl[2 * i + 1]; }
         float *part = resolve(t.p[9], P.bases, agent);
         part[2 * tile] = s1; part[2 * tile + 1] = s2;
     }
     __syncthreads();
 }
 
-// T_SAMPLE_BWD: p0=da1 p1=da2 [B,A] ; p2=head_raw rows of the current-state sample ; p3=eps_cur ; p4=g_head [B,ldg]
-//   i0=B i1=A i2=ldg (row stride of g_head, 16 B aligned) ; f0=scale f1=bias    (closed form of SURVEY 3.3)
+// T_SAMPLE_BWD: p0=da1 p1=da2 [B,A] ; p2=head_raw rows of the current-state sample ; p3=eps_cur ; pm0=g_head PM [B,2A]
+//   i0=B i1=A ; f0=scale f1=bias    (closed form of SURVEY 3.3)
 __device__ __forceinline__ void task_sample_bwd(const Task &t, int tile, const Program &P, int agent, const float *scalars) {
     const int B = t.i[0], A = t.i[1];
     const int idx = tile * kThreads + threadIdx.x;
@@ -242,13 +298,13 @@ __device__ __forceinline__ void task_sample_bwd(const Task &t, int tile, const P
     const float da = ldcg(resolve(t.p[0], P.bases, agent) + idx) + ldcg(resolve(t.p[1], P.bases, agent) + idx);
     const float sc = t.f[0], omy2 = 1.f - s.y * s.y, aB = alpha / (float)B;
     const float g_u = da * sc * omy2 + aB * (2.f * sc * s.y * omy2) / (sc * omy2 + kSquashEps);
-    float *g = resolve(t.p[4], P.bases, agent) + (int64_t)b * t.i[2];
-    g[a] = g_u;
-    g[A + a] = (g_u * s.std * eps - aB) * s.in_range;
+    const Pm g = resolve_pm(t.pm[0], P.bases, agent);
+    pm_store(g, b, a, g_u);
+    pm_store(g, b, A + a, (g_u * s.std * eps - aB) * s.in_range);
 }
 
 // column sums over the batch for 32 columns per tile: thread (cg = tid & 31, rg = tid >> 5) adds rows rg, rg+G, ...
-// (loads unrolled 8 deep), the 8 row groups are then combined in shared memory in a fixed order
+// (loads unrolled 8 deep), the row groups are then combined in shared memory in a fixed order
 template <class F>
 __device__ __forceinline__ float colsum32(int B, float *smem, F value_at) {
     constexpr int G = kThreads / 32;       // row groups
@@ -271,15 +327,16 @@ __device__ __forceinline__ float colsum32(int B, float *smem, F value_at) {
     return tot;     // valid for rg == 0
 }
 
-// T_OUT_ADAM: Q output layer (Linear(H,1)).  p0=h_L [B,H] p1=dq [B] ; p2..p6 = w,m,v,wt,gexp [H] ; p7..p11 = same for bias
+// T_OUT_ADAM: Q output layer (Linear(H,1)).  pm0=h_L PM [B,H] p1=dq [B] ; p2..p6 = w,m,v,wt,gexp [H] ; p7..p11 = same for bias
 //   i0=B i1=H i2=step_slot i3=apply ; f0=lr f1=tau.   32 columns per tile; tile 0 also does the bias
 __device__ __forceinline__ void task_out_adam(const Task &t, int tile, const Program &P, int agent, const float *scalars, float *smem) {
     const int B = t.i[0], H = t.i[1];
     const int n = tile * 32 + (threadIdx.x & 31);
-    const float *h = resolve(t.p[0], P.bases, agent), *dq = resolve(t.p[1], P.bases, agent);
+    const Pm h = resolve_pm(t.pm[0], P.bases, agent);
+    const float *dq = resolve(t.p[1], P.bases, agent);
     float ss, bs;
     adam_factors(__float_as_int(ldcg(scalars + t.i[2])), t.f[0], ss, bs);
-    const float g = colsum32(B, smem, [&](int b) { return n < H ? ldcg(dq + b) * ldcg(h + (int64_t)b * H + n) : 0.f; });
+    const float g = colsum32(B, smem, [&](int b) { return n < H ? ldcg(dq + b) * pm_load(h, b, n) : 0.f; });
     if (threadIdx.x < 32 && n < H) {
         float *wt = resolve(t.p[5], P.bases, agent), *ge = resolve(t.p[6], P.bases, agent);
         adam_element(g, resolve(t.p[2], P.bases, agent) + n, resolve(t.p[3], P.bases, agent) + n, resolve(t.p[4], P.bases, agent) + n,
@@ -295,18 +352,13 @@ __device__ __forceinline__ void task_out_adam(const Task &t, int tile, const Pro
     }
 }
 
-// T_BIAS_ADAM: db[n] = sum_b dh[b,n], dh described by Task::A (K-major [B,N], optional rank-1 transform).
-//   p0..p4 = b,m,v,bt,gexp ; i0=B i1=N i2=step_slot i3=apply ; f0=lr f1=tau.   32 columns per tile
+// T_BIAS_ADAM: db[n] = sum_b dh[b,n].  pm0 = dh PM [B,N] ; p0..p4 = b,m,v,bt,gexp ; i0=B i1=N i2=step_slot i3=apply ;
+//   f0=lr f1=tau.   32 columns per tile
 __device__ __forceinline__ void task_bias_adam(const Task &t, int tile, const Program &P, int agent, const float *scalars, float *smem) {
     const int B = t.i[0], N = t.i[1];
     const int n = tile * 32 + (threadIdx.x & 31);
-    const OperandR A = resolve_operand(t.A, P.bases, agent);
-    const float cv = (A.xform && n < N) ? ldcg(A.cvec + n) : 0.f;
-    const float g = colsum32(B, smem, [&](int b) {
-        if (n >= N) return 0.f;
-        const float v = ldcg(A.p + (int64_t)b * A.ld + n);
-        return A.xform ? (v > 0.f ? ldcg(A.rvec + b) * cv : 0.f) : v;
-    });
+    const Pm dh = resolve_pm(t.pm[0], P.bases, agent);
+    const float g = colsum32(B, smem, [&](int b) { return n < N ? pm_load(dh, b, n) : 0.f; });
     if (threadIdx.x < 32 && n < N) {
         float ss, bs;
         adam_factors(__float_as_int(ldcg(scalars + t.i[2])), t.f[0], ss, bs);
@@ -325,21 +377,28 @@ __device__ __forceinline__ void task_finish(const Task &t, const Program &P, int
     const int nt = t.i[5];
     const float Bf = t.f[1];
     const float *cp = resolve(t.p[0], P.bases, agent), *ap = resolve(t.p[1], P.bases, agent);
-    // partials fetched in parallel, then summed in tile order by one thread (deterministic)
-    for (int i = threadIdx.x; i < 2 * nt && i < kThreads / 2; i += blockDim.x) {
-        smem[i] = cp ? ldcg(cp + i) : 0.f;
-        smem[kThreads / 2 + i] = ap ? ldcg(ap + i) : 0.f;
+    // deterministic two-level sum: 128 threads each add a contiguous run of tile partials in tile order (one tile
+    // each while nt <= 128), thread 0 then adds the 128 run sums in order
+    constexpr int kRuns = kThreads / 4;
+    if ((int)threadIdx.x < kRuns) {
+        const int c = cdiv(nt, kRuns), i0 = threadIdx.x * c, i1 = min(nt, i0 + c);
+        float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
+        for (int i = i0; i < i1; i++) {
+            if (cp) { a1 += ldcg(cp + 2 * i); a2 += ldcg(cp + 2 * i + 1); }
+            if (ap) { b1 += ldcg(ap + 2 * i); b2 += ldcg(ap + 2 * i + 1); }
+        }
+        smem[threadIdx.x] = a1; smem[kRuns + threadIdx.x] = a2; smem[2 * kRuns + threadIdx.x] = b1; smem[3 * kRuns + threadIdx.x] = b2;
     }
     __syncthreads();
     if (threadIdx.x != 0) return;
     if (cp) {
         float s1 = 0.f, s2 = 0.f;
-        for (int i = 0; i < nt; i++) { s1 += smem[2 * i]; s2 += smem[2 * i + 1]; }
+        for (int i = 0; i < kRuns; i++) { s1 += smem[i]; s2 += smem[kRuns + i]; }
         scalars[SC_LOSS_Q1] = s1 / Bf; scalars[SC_LOSS_Q2] = s2 / Bf;
     }
     if (ap) {
         float s1 = 0.f, s2 = 0.f;
-        for (int i = 0; i < nt; i++) { s1 += smem[kThreads / 2 + 2 * i]; s2 += smem[kThreads / 2 + 2 * i + 1]; }
+        for (int i = 0; i < kRuns; i++) { s1 += smem[2 * kRuns + i]; s2 += smem[3 * kRuns + i]; }
         scalars[SC_LOSS_PI] = s1 / Bf;
         const int n_upd = __float_as_int(scalars[SC_N_UPDATES]);
         float alpha_next = scalars[SC_ALPHA0 + (n_upd & 1)];

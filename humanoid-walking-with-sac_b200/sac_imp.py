@@ -87,7 +87,7 @@ class SAC:
 
     def __init__(self, state_dim, action_dim, hidden_dim=256, gamma=0.99, tau=0.005, lr=3e-4, alpha=0.2,
                  automatic_entropy_tuning=True, device="cuda" if torch.cuda.is_available() else "cpu", *,
-                 replay="uniform", capacity=1000000, max_batch=256, math="tf32x3", launch="staged", seed=None,
+                 replay="uniform", capacity=1000000, max_batch=256, math="bf16x3", launch="staged", seed=None,
                  per_alpha=0.6, per_beta_start=0.4, per_beta_frames=100000, per_weighted_loss=False, action_bounds=None):
         if not str(device).startswith("cuda"):
             raise RuntimeError("this SAC runs on a B200 only (device='cuda[:i]'); there is no CPU path")
@@ -118,7 +118,7 @@ class SAC:
         cfg.capacity, cfg.max_batch, cfg.n_agents, cfg.device = capacity, max_batch, 1, dev_index
         cfg.per_alpha, cfg.per_beta_start, cfg.per_beta_frames = per_alpha, per_beta_start, per_beta_frames
         cfg.per_weighted_loss = int(bool(per_weighted_loss))
-        cfg.math_mode = {"tf32": N.MATH_TF32, "fp32": N.MATH_FP32, "tf32x3": N.MATH_TF32X3}[math]
+        cfg.math_mode = {"fp32": N.MATH_FP32, "bf16x3": N.MATH_BF16X3}[math]
         cfg.launch_mode = {"staged": N.LAUNCH_STAGED, "persistent": N.LAUNCH_PERSISTENT}[launch]
         cfg.seed = random.getrandbits(63) if seed is None else int(seed)
         self._cfg = cfg

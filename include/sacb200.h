@@ -33,11 +33,11 @@ typedef enum {
     SACB_ERR_NOMEM = -4
 } sacb_status;
 
-/* GEMM arithmetic of the update: */
-enum { SACB_MATH_FP32 = 0,   /* CUDA-core FFMA, fp32 in / fp32 accumulate (strict-parity mode)              */
-       SACB_MATH_TF32 = 1,   /* tcgen05.mma kind::tf32, operands rounded to tf32 once, fp32 accumulate in TMEM */
-       SACB_MATH_TF32X3 = 2  /* tcgen05.mma kind::tf32 on error-compensated operand pairs (x = hi + lo):
-                                a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32 accumulate: fp32-level accuracy (default) */ };
+/* GEMM arithmetic of the update.  Every GEMM operand (minibatch, activations, gradients, weight shadows) is stored
+ * as a bf16 hi/lo pair (x ~= hi + lo, 2^-17 relative); master weights, Adam state and accumulators are fp32. */
+enum { SACB_MATH_FP32 = 0,    /* CUDA-core FFMA on the pair operands, fp32 products and accumulate (checker / strict mode) */
+       SACB_MATH_BF16X3 = 1   /* TMA-fed tcgen05.mma kind::f16: a_lo*b_hi + a_hi*b_lo + a_hi*b_hi, fp32 accumulate in TMEM
+                                 (default; agrees with SACB_MATH_FP32 to ~1e-5 relative) */ };
 
 /* how one update step is launched: */
 enum { SACB_LAUNCH_STAGED = 0,     /* one kernel per dependency stage, whole step captured in one CUDA graph */
@@ -180,8 +180,14 @@ int sacb_timer_stop(sacb_handle h, float *ms_out);
 int sacb_time_update(sacb_handle h, int64_t B, int iters, float *ms_per_step);
 /* device time of every stage kernel of one step (STAGED mode), in microseconds; n = min(cap, n_stages). */
 int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap);
-/* standalone GEMM self-test of the tensor-core tile against the FFMA tile; returns max |diff| / max |ref|. */
-int sacb_selftest_gemm(int device, int M, int N, int K, int a_mn_major, int b_mn_major, float *rel_err_out);
+/* test hook: a hidden activation matrix [B, hidden] of the LAST update (bf16 pair reconstructed to float32).
+ * group 0: policy layer `layer` on the current states (sac_imp.py:116) ; 1: critic k (0 = q1, 1 = q2) on (s, a) (:101-102) ;
+ * 2: updated critic k on (s, a_new) (:117-118) ; 3: target critic k on (s2, a2) (:92-93).  The parity tests use the signs
+ * (ReLU masks) to make the comparison with the oracle independent of pre-activations that round to either side of zero. */
+int sacb_debug_read_activation(sacb_handle h, int agent, int group, int k, int layer, int64_t B, float *out);
+/* standalone GEMM self-test of the TMA + tcgen05 tile against the FFMA tile and a host float64 product of the same
+ * bf16-pair operands; returns max |diff| / max |ref|.  b_r0 = row/column offset of the B operand inside its matrix. */
+int sacb_selftest_gemm(int device, int M, int N, int K, int a_mn_major, int b_mn_major, int b_r0, float *rel_err_out);
 
 #ifdef __cplusplus
 }

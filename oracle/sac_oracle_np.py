@@ -170,37 +170,75 @@ def make_batch(obs, act, batch, seed=0, dtype=np.float32):
 # --------------------------------------------------------------------------------------------
 # networks
 # --------------------------------------------------------------------------------------------
-def q_forward(P, s, a, n_hidden, keep=False):
+class ReluHint:
+    """Optional tie-break for ReLU masks (test infrastructure, not part of the reference).
+
+    relu'(z) is discontinuous at z = 0: a pre-activation that lies within rounding of zero is "on" in one
+    correct implementation and "off" in another (the reference itself flips such units between BLAS builds),
+    and one flipped unit moves a whole row of a weight gradient by O(1/B).  A hint carries the masks another
+    implementation used; the oracle adopts them ONLY where its own |z| < band * rms(z) and records every unit
+    outside that band where the two disagree (`mismatch`, must stay 0 for parity)."""
+
+    def __init__(self, masks, band=1e-4, band_by_tag=None):
+        self.masks, self.band = masks, band        # masks[(tag, layer)] -> bool [B, H]
+        self.band_by_tag = band_by_tag or {}       # wider band for passes that run on freshly Adam-stepped weights
+        self.adopted = 0                           # units inside the band whose hinted mask differs from z > 0
+        self.ambiguous = 0                         # units inside the band
+        self.mismatch = 0                          # units OUTSIDE the band where the hint disagrees
+
+    def mask(self, tag, layer, z):
+        own = z > 0
+        hint = self.masks.get((tag, layer))
+        if hint is None:
+            return own
+        hint = np.asarray(hint, bool).reshape(z.shape)
+        inside = np.abs(z) < self.band_by_tag.get(tag, self.band) * max(float(np.sqrt(np.mean(z.astype(np.float64) ** 2))), 1e-30)
+        self.ambiguous += int(inside.sum())
+        self.adopted += int((inside & (hint != own)).sum())
+        self.mismatch += int((~inside & (hint != own)).sum())
+        return np.where(inside, hint, own)
+
+
+def _hidden(P, x, n_hidden, hint, tag):
+    """(Linear + ReLU) x n_hidden.  Returns the layer inputs/outputs `acts` and the ReLU masks `masks`
+    (masks[i-1] belongs to fc{i}); without a hint masks == (acts > 0), i.e. exactly F.relu and its backward."""
+    acts, masks = [x], []
+    for i in range(1, n_hidden + 1):
+        z = x @ P[f"fc{i}.weight"].T + P[f"fc{i}.bias"]
+        if hint is None:
+            x = np.maximum(z, 0)
+            masks.append(x > 0)
+        else:
+            m = hint.mask(tag, i, z)
+            x = np.where(m, z, 0).astype(z.dtype)
+            masks.append(m)
+        acts.append(x)
+    return x, acts, masks
+
+
+def q_forward(P, s, a, n_hidden, keep=False, hint=None, tag=None):
     """QNetwork.forward: networks_model1.py:27-33 / networks_model2.py:37-46.  cat(s,a) -> (Linear+ReLU)xn -> Linear(H,1)."""
-    x = np.concatenate([s, a], axis=-1)
-    acts = [x]
-    for i in range(1, n_hidden + 1):
-        x = np.maximum(x @ P[f"fc{i}.weight"].T + P[f"fc{i}.bias"], 0)
-        acts.append(x)
+    x, acts, masks = _hidden(P, np.concatenate([s, a], axis=-1), n_hidden, hint, tag)
     q = x @ P[f"fc{n_hidden + 1}.weight"].T + P[f"fc{n_hidden + 1}.bias"]      # [B,1]
-    return (q, acts) if keep else q
+    return (q, (acts, masks)) if keep else q
 
 
-def policy_forward(P, s, n_hidden, keep=False):
+def policy_forward(P, s, n_hidden, keep=False, hint=None, tag=None):
     """GaussianPolicy.forward: networks_model1.py:65-76 / networks_model2.py:85-97."""
-    x = s
-    acts = [x]
-    for i in range(1, n_hidden + 1):
-        x = np.maximum(x @ P[f"fc{i}.weight"].T + P[f"fc{i}.bias"], 0)
-        acts.append(x)
+    x, acts, masks = _hidden(P, s, n_hidden, hint, tag)
     mean = x @ P["mean.weight"].T + P["mean.bias"]
     ls_raw = x @ P["log_std.weight"].T + P["log_std.bias"]
     log_std = np.clip(ls_raw, LOG_STD_MIN, LOG_STD_MAX)
     if keep:
-        return mean, log_std, ls_raw, acts
+        return mean, log_std, ls_raw, (acts, masks)
     return mean, log_std
 
 
-def policy_sample(P, s, eps, n_hidden, scale, bias, keep=False):
+def policy_sample(P, s, eps, n_hidden, scale, bias, keep=False, hint=None, tag=None):
     """GaussianPolicy.sample: networks_model1.py:78-99 == networks_model2.py:99-120, with the N(0,1) draw
     of `Normal.rsample` (x_t = mean + eps*std) supplied by the caller."""
     dt = s.dtype.type
-    mean, log_std, ls_raw, acts = policy_forward(P, s, n_hidden, keep=True)
+    mean, log_std, ls_raw, acts = policy_forward(P, s, n_hidden, keep=True, hint=hint, tag=tag)
     std = np.exp(log_std)
     x_t = mean + eps * std
     y_t = np.tanh(x_t)
@@ -229,8 +267,9 @@ def select_action(st: SACState, state, evaluate=False, eps=None):
 # --------------------------------------------------------------------------------------------
 # backward pieces (hand-written; validated against the reference's autograd in make_golden.py)
 # --------------------------------------------------------------------------------------------
-def q_backward(P, acts, dq, n_hidden, need_dw=True):
+def q_backward(P, acts_masks, dq, n_hidden, need_dw=True):
     """Backward of q_forward given dL/dq [B,1].  Returns (grads or None, dL/dx of the cat(s,a) input)."""
+    acts, masks = acts_masks
     grads = {}
     L = n_hidden + 1
     g = dq
@@ -242,22 +281,23 @@ def q_backward(P, acts, dq, n_hidden, need_dw=True):
             grads[f"fc{i}.bias"] = g.sum(axis=0)
         g = g @ W
         if i > 1:
-            g = g * (x_in > 0)
+            g = g * masks[i - 2]          # relu'(z_{i-1}) == (x_in > 0) unless a ReluHint overrode it
     return (grads if need_dw else None), g
 
 
-def policy_backward(P, acts, g_mean, g_ls, n_hidden):
+def policy_backward(P, acts_masks, g_mean, g_ls, n_hidden):
+    acts, masks = acts_masks
     grads = {
         "mean.weight": g_mean.T @ acts[-1], "mean.bias": g_mean.sum(axis=0),
         "log_std.weight": g_ls.T @ acts[-1], "log_std.bias": g_ls.sum(axis=0),
     }
-    g = (g_mean @ P["mean.weight"] + g_ls @ P["log_std.weight"]) * (acts[-1] > 0)
+    g = (g_mean @ P["mean.weight"] + g_ls @ P["log_std.weight"]) * masks[-1]
     for i in range(n_hidden, 0, -1):
         x_in = acts[i - 1]
         grads[f"fc{i}.weight"] = g.T @ x_in
         grads[f"fc{i}.bias"] = g.sum(axis=0)
         if i > 1:
-            g = (g @ P[f"fc{i}.weight"]) * (x_in > 0)
+            g = (g @ P[f"fc{i}.weight"]) * masks[i - 2]
     return grads
 
 
@@ -291,11 +331,14 @@ def polyak(target, online, tau):
 # --------------------------------------------------------------------------------------------
 # the learner step
 # --------------------------------------------------------------------------------------------
-def update_parameters(st: SACState, batch, per_weights: Optional[np.ndarray] = None, return_aux=False):
+def update_parameters(st: SACState, batch, per_weights: Optional[np.ndarray] = None, return_aux=False,
+                      relu_hint: Optional[ReluHint] = None):
     """SAC.update_parameters: sac_imp.py:74-144, same order of operations.
 
     `batch` = dict(s,a,r,s2,d,eps_next,eps_cur); r,d are [B] and are unsqueezed as at sac_imp.py:83,85.
     `per_weights` (extension H10, not in the reference): IS weights w[B]; critic loss becomes mean(w (q-y)^2).
+    `relu_hint` (test infrastructure): masks of another implementation for the three passes that are differentiated,
+    tags 'q1'/'q2' (critics on (s,a)), 'q1a'/'q2a' (updated critics on (s,a_new)), 'policy' (policy on s); see ReluHint.
     Returns {'q1_loss','q2_loss','policy_loss'} (+ aux dict with grads/targets/td when return_aux)."""
     dt = st.dtype
     s, a, s2 = batch["s"].astype(dt), batch["a"].astype(dt), batch["s2"].astype(dt)
@@ -319,7 +362,7 @@ def update_parameters(st: SACState, batch, per_weights: Optional[np.ndarray] = N
     w = None if per_weights is None else per_weights.astype(dt)[:, None]
     td = []
     for name, P, opt in (("q1", st.q1, st.q1_opt), ("q2", st.q2, st.q2_opt)):
-        qp, acts = q_forward(P, s, a, nh, keep=True)
+        qp, acts = q_forward(P, s, a, nh, keep=True, hint=relu_hint, tag=name)
         diff = qp - y
         td.append(diff[:, 0].copy())
         if w is None:
@@ -333,9 +376,10 @@ def update_parameters(st: SACState, batch, per_weights: Optional[np.ndarray] = N
         adam_step(P, grads, opt, st.lr)
 
     # -- actor  sac_imp.py:116-125 (uses the UPDATED q1,q2; alpha and Q weights are constants here, quirk Q2)
-    an, logp, pk = policy_sample(st.policy, s, batch["eps_cur"].astype(dt), nh, st.action_scale, st.action_bias, keep=True)
-    q1p, acts1 = q_forward(st.q1, s, an, nh, keep=True)
-    q2p, acts2 = q_forward(st.q2, s, an, nh, keep=True)
+    an, logp, pk = policy_sample(st.policy, s, batch["eps_cur"].astype(dt), nh, st.action_scale, st.action_bias, keep=True,
+                                 hint=relu_hint, tag="policy")
+    q1p, acts1 = q_forward(st.q1, s, an, nh, keep=True, hint=relu_hint, tag="q1a")
+    q2p, acts2 = q_forward(st.q2, s, an, nh, keep=True, hint=relu_hint, tag="q2a")
     qmin = np.minimum(q1p, q2p)
     losses["policy_loss"] = float(np.mean(alpha * logp - qmin))
     # d(-mean(min))/dq_k : routed to the smaller Q, exact ties split 1/2-1/2 (torch.minimum backward)

@@ -2,11 +2,10 @@
 
 Chain of evidence: live reference --(tests/golden/*.npz)--> numpy oracle (test_oracle_update_golden.py)
 and here: CUDA path vs the oracle on the same seeded inputs AND vs the golden vectors directly.
-Tolerances (relative; the north star asks for 1e-3):
-  fp32   (FFMA tile)                                   2e-4  -- fp32 reassociation only
-  tf32x3 (tcgen05, error-compensated tf32 pairs, DEFAULT) 3e-4  -- operands split hi+lo, 3 MMAs, fp32 accumulate in TMEM
-  tf32   (tcgen05, operands rounded to tf32 once)      loose -- (q - y) cancels, so 5e-4 operand rounding shows up as
-                                                        percent-level gradient noise; kept as an opt-in speed mode
+Tolerances (relative; the north star asks for 1e-3).  Both modes read the SAME bf16 hi/lo pair operands
+(2^-17 relative storage rounding of activations / weight shadows; master weights, Adam state, accumulators fp32):
+  fp32   (FFMA tile, fp32 products)                          3e-4
+  bf16x3 (TMA + tcgen05, 3 MMAs per product, DEFAULT)        3e-4
 """
 import os
 
@@ -15,14 +14,13 @@ import pytest
 
 from oracle import sac_oracle_np as O
 from tests.golden import cases
-from tests.util import batch_of, grad_close, make_agent, net_params, relerr
+from tests.util import batch_of, grad_close, make_agent, net_params, relerr, relu_hint
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 
-TOL = {"fp32": dict(loss=2e-4, grad=2e-4, adam=4e-4, frac=1e-3, budget=0.02),
-       "tf32x3": dict(loss=3e-4, grad=3e-4, adam=6e-4, frac=1e-3, budget=0.02),
-       "tf32": dict(loss=1e-2, grad=2.5e-1, adam=2.5e-1, frac=5e-2, budget=0.5)}
+TOL = {"fp32": dict(loss=3e-4, grad=3e-4, adam=6e-4, frac=5e-3, budget=0.02),
+       "bf16x3": dict(loss=3e-4, grad=3e-4, adam=6e-4, frac=5e-3, budget=0.02)}
 CASES = [c for c in cases.UPDATE_CASES if not cases.UPDATE_CASES[c].get("loose")]
 
 
@@ -39,8 +37,12 @@ def run_case(hw, name, math, launch):
     agent, st = make_agent(hw, case, math=math, launch=launch)
     for step in range(case["steps"]):
         b = batch_of(case, step)
-        ref_losses, aux = O.update_parameters(st, b, return_aux=True)
         got = agent.update_from_batch(b, eps=(b["eps_next"], b["eps_cur"]), export_grads=True)
+        # ReLU masks: the oracle keeps its own mask wherever |z| >= 1e-4 rms(z) and there the device must agree exactly
+        hint = relu_hint(agent, case)
+        ref_losses, aux = O.update_parameters(st, b, return_aux=True, relu_hint=hint)
+        assert hint.mismatch == 0, (step, hint.mismatch, hint.adopted, hint.ambiguous)
+        assert hint.adopted <= 64, (hint.adopted, hint.ambiguous)       # a handful of genuine ties per update, not a drift
         for k in ("q1_loss", "q2_loss", "policy_loss"):
             assert abs(got[k] - ref_losses[k]) <= tol["loss"] * abs(ref_losses[k]) + 1e-6, (step, k, got[k], ref_losses[k])
         # golden (live reference) losses as well
@@ -48,7 +50,7 @@ def run_case(hw, name, math, launch):
         for net in ("q1", "q2", "policy"):
             gg = agent.exported_grads(net)
             for nm, ref in aux[f"{net}_grads"].items():
-                ok, overall, bad = grad_close(gg[nm], ref, tol["grad"])
+                ok, overall, bad = grad_close(gg[nm], ref, tol["grad"], max_flips=0)
                 assert ok, (step, net, nm, overall, bad)
                 if step == 0:
                     gold = g[f"gradsum/{net}/{nm}"]
@@ -57,8 +59,6 @@ def run_case(hw, name, math, launch):
         a = float(a) if not hasattr(a, "item") else float(a.item())
         assert abs(a - st.alpha) <= 1e-5 * abs(st.alpha), (a, st.alpha)
         np.testing.assert_allclose(a, g["alphas"][step], rtol=2e-5)
-    if math == "tf32":
-        return agent
     # post-update state: Adam moves every weight by ~lr per step whatever |g| is -> compare in units of lr
     budget = tol["budget"] * st.lr * case["steps"] + 1e-7
     for net in ("policy", "q1", "q2", "q1_target", "q2_target"):
@@ -72,8 +72,8 @@ def run_case(hw, name, math, launch):
         names = list(getattr(st, net).keys())
         for i, nm in enumerate(names):
             assert int(sd["state"][i]["step"]) == case["steps"]
-            assert grad_close(sd["state"][i]["exp_avg"].cpu().numpy(), opt.m[nm], tol["adam"], max_flips=2 * case["steps"])[0], (net, nm)
-            assert grad_close(sd["state"][i]["exp_avg_sq"].cpu().numpy(), opt.v[nm], 2 * tol["adam"], max_flips=2 * case["steps"])[0], (net, nm)
+            assert grad_close(sd["state"][i]["exp_avg"].cpu().numpy(), opt.m[nm], tol["adam"], max_flips=0)[0], (net, nm)
+            assert grad_close(sd["state"][i]["exp_avg_sq"].cpu().numpy(), opt.v[nm], 2 * tol["adam"], max_flips=0)[0], (net, nm)
     return agent
 
 
@@ -83,17 +83,12 @@ def test_update_fp32_staged(hw, name):
 
 
 @pytest.mark.parametrize("name", CASES)
-def test_update_tf32x3_staged(hw, name):
-    run_case(hw, name, "tf32x3", "staged")
+def test_update_bf16x3_staged(hw, name):
+    run_case(hw, name, "bf16x3", "staged")
 
 
 @pytest.mark.parametrize("name", ["tiny_m2", "c1_bipedal_m1", "c2_humanoid_m2"])
-def test_update_tf32_single_pass_loose(hw, name):
-    run_case(hw, name, "tf32", "staged")
-
-
-@pytest.mark.parametrize("name", ["tiny_m2", "c1_bipedal_m1", "c2_humanoid_m2"])
-@pytest.mark.parametrize("math", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("math", ["fp32", "bf16x3"])
 def test_update_persistent_single_launch(hw, name, math):
     """ONE cooperative launch per step (grid barriers between stages) gives the same step as the staged graph."""
     agent = run_case(hw, name, math, "persistent")
@@ -140,7 +135,7 @@ def test_per_weighted_loss_extension(hw):
 def test_device_eps_mode_runs_and_learns(hw):
     """Production mode: eps drawn on the device (Philox); losses finite, critic loss decreases on a fixed batch."""
     case = cases.UPDATE_CASES["c1_bipedal_m1"]
-    agent, _ = make_agent(hw, case, math="tf32x3")
+    agent, _ = make_agent(hw, case, math="bf16x3")
     b = batch_of(case, 0)
     l0 = agent.update_from_batch(b)
     for _ in range(30):

@@ -25,6 +25,25 @@ def make_agent(hw, case, math="fp32", launch="staged", **kw):
     return agent, st
 
 
+def relu_hint(agent, case, band=1e-4, band_post_adam=1e-2):
+    """ReLU masks the device used in the last update (tests/oracle ReluHint): the three differentiated passes.
+
+    band: |z| < 1e-4 rms(z) may take either sign (bf16-pair operand storage, 2^-16 per element).  The actor phase
+    evaluates the critics right AFTER their Adam step (sac_imp.py:109,113 -> :117-118): a weight whose gradient is
+    within rounding of zero moves by +lr or -lr (early Adam steps are sign-like), shifting a pre-activation by up to
+    2*lr*|x|; those two passes get the wider band."""
+    import ctypes
+    from humanoid_walking_with_sac_b200 import _native as N
+    B, H, nh = case["batch"], case["hidden"], case["n_hidden"]
+    masks = {}
+    buf = np.empty((B, H), np.float32)
+    for layer in range(nh):
+        for tag, group, k in (("policy", 0, 0), ("q1", 1, 0), ("q2", 1, 1), ("q1a", 2, 0), ("q2a", 2, 1)):
+            N.check(N.lib().sacb_debug_read_activation(agent._h, 0, group, k, layer, B, N.ptr(buf)))
+            masks[(tag, layer + 1)] = buf > 0
+    return O.ReluHint(masks, band, {"q1a": band_post_adam, "q2a": band_post_adam})
+
+
 def batch_of(case, step):
     return O.make_batch(case["obs"], case["act"], case["batch"], seed=case["seed"] * 100 + step)
 

@@ -6,7 +6,7 @@ import humanoid_walking_with_sac_b200 as hw
 from tests.golden import cases
 from tests.util import batch_of, make_agent
 
-math = sys.argv[1] if len(sys.argv) > 1 else "tf32x3"
+math = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
 launch = sys.argv[2] if len(sys.argv) > 2 else "staged"
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 case = cases.UPDATE_CASES["c2_humanoid_m2"]

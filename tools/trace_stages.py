@@ -4,7 +4,7 @@ os.environ["SACB_TRACE"] = "1"
 import humanoid_walking_with_sac_b200 as hw
 from tests.golden import cases
 from tests.util import batch_of, make_agent
-math = sys.argv[1] if len(sys.argv) > 1 else "tf32x3"
+math = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
 case = cases.UPDATE_CASES["c2_humanoid_m2"]
 agent, st = make_agent(hw, case, math=math)
 b = batch_of(case, 0)
