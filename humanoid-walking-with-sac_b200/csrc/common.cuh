@@ -65,7 +65,10 @@ enum ScalarSlot {
     SC_ALPHA0, SC_ALPHA1,            // alpha used by step t = SC_ALPHA0 + (n_updates & 1); written for t+1 into the other
     SC_STEP_POLICY, SC_STEP_Q1, SC_STEP_Q2, SC_STEP_ALPHA, SC_N_UPDATES,   // stored as int32 bit patterns
     SC_LOSS_Q1, SC_LOSS_Q2, SC_LOSS_PI, SC_LOSS_ALPHA,
-    SC_COUNT = 16
+    SC_COUNT = 16,
+    // Adam bias-correction factors of the NEXT step of each optimizer, refreshed whenever a step counter changes
+    // (T_FINISH, sacb_set_scalars, the data-parallel apply): [SC_FAC0 + 2*(step_slot - SC_STEP_POLICY)] = step_size, +1 = sqrt(bc2)
+    SC_FAC0 = 16
 };
 
 // ---- GEMM operand: logical X[R, K] (R = M for A, N for B) held in a PM -----------------------------------
@@ -133,10 +136,12 @@ struct alignas(64) Task {
     float f[6];
 };
 
+constexpr int kMaxStageTasks = 28;
 struct Stage {
     int32_t task_begin, task_end;
     int32_t n_tiles;          // per agent
     int32_t pad;
+    int32_t tile_begin[kMaxStageTasks];   // first tile of each task of the stage (copy of Task::tile_begin: one load finds the task)
 };
 
 struct Program {
@@ -152,11 +157,12 @@ struct Program {
     const int32_t *slots;     // physical ring slots of the minibatch rows [n_agents, B]
     int32_t slots_stride; int32_t pad1;
     int32_t *error_flag;      // set by watchdogs (mbarrier / grid barrier timeouts)
-    unsigned long long *trace; // optional [grid][8] globaltimer stamps of each CTA's first tile (profiling aid), or null
+    unsigned long long *trace; // optional [grid][kTraceSlots] globaltimer stamps of each CTA's first tile (profiling aid), or null
 };
 
 // ---- tile geometry ----------------------------------------------------------------------------------------
 constexpr int kThreads = 512;
+constexpr int kTraceSlots = 64;   // 0..5 kernel phases, 6 accumulator ready, 16+kb TMA issue of k-block kb, 32+kb its arrival (kb < 16)
 // FFMA path (checker / strict mode)
 constexpr int kSM = 64, kSN = 64, kSK = 16;
 // tcgen05 path: 128 x 64 output tile, K blocks of 64 bf16 (= 128 B, one SWIZZLE_128B row), both planes per stage

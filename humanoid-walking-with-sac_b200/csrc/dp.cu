@@ -9,7 +9,7 @@ namespace sacb {
 
 __global__ void dp_apply_kernel(float *w, float *m, float *v, float *wt, const float *g, int64_t n, float scale, const float *scalars, int step_slot, float lr, float tau) {
     float ss, bs;
-    adam_factors(__float_as_int(scalars[step_slot]), lr, ss, bs);
+    adam_factors_cached(scalars, step_slot, ss, bs);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
         adam_element(g[i] * scale, w + i, m + i, v + i, wt ? wt + i : nullptr, nullptr, 1, ss, bs, tau);
 }
@@ -17,20 +17,27 @@ __global__ void dp_apply_kernel(float *w, float *m, float *v, float *wt, const f
 __global__ void dp_finish_kernel(float *scalars, const float *g_scalars, int phase, int auto_entropy, float lr) {
     if (threadIdx.x || blockIdx.x) return;
     if (phase == 0) {
-        scalars[SC_STEP_Q1] = __int_as_float(__float_as_int(scalars[SC_STEP_Q1]) + 1);
-        scalars[SC_STEP_Q2] = __int_as_float(__float_as_int(scalars[SC_STEP_Q2]) + 1);
+        for (int slot = SC_STEP_Q1; slot <= SC_STEP_Q2; slot++) {
+            const int step = __float_as_int(scalars[slot]) + 1;
+            scalars[slot] = __int_as_float(step);
+            adam_factors_store(scalars, slot, step, lr);
+        }
     } else {
         const int n_upd = __float_as_int(scalars[SC_N_UPDATES]);
         float alpha_next = scalars[SC_ALPHA0 + (n_upd & 1)];
         if (auto_entropy) {
             float ss, bs;
-            adam_factors(__float_as_int(scalars[SC_STEP_ALPHA]), lr, ss, bs);
+            adam_factors_cached(scalars, SC_STEP_ALPHA, ss, bs);
             adam_element(g_scalars[0], &scalars[SC_LOG_ALPHA], &scalars[SC_LOG_ALPHA_M], &scalars[SC_LOG_ALPHA_V], nullptr, nullptr, 1, ss, bs, 0.f);
             alpha_next = expf(scalars[SC_LOG_ALPHA]);
-            scalars[SC_STEP_ALPHA] = __int_as_float(__float_as_int(scalars[SC_STEP_ALPHA]) + 1);
+            const int step = __float_as_int(scalars[SC_STEP_ALPHA]) + 1;
+            scalars[SC_STEP_ALPHA] = __int_as_float(step);
+            adam_factors_store(scalars, SC_STEP_ALPHA, step, lr);
         }
         scalars[SC_ALPHA0 + ((n_upd + 1) & 1)] = alpha_next;
-        scalars[SC_STEP_POLICY] = __int_as_float(__float_as_int(scalars[SC_STEP_POLICY]) + 1);
+        const int pstep = __float_as_int(scalars[SC_STEP_POLICY]) + 1;
+        scalars[SC_STEP_POLICY] = __int_as_float(pstep);
+        adam_factors_store(scalars, SC_STEP_POLICY, pstep, lr);
         scalars[SC_N_UPDATES] = __int_as_float(n_upd + 1);
     }
 }

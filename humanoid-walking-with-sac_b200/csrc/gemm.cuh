@@ -59,16 +59,24 @@ struct EpiR {
     Pm shadow, shadow2;
     int shadow2_col0;
     int apply;
-    float step_size, bc2_sqrt, tau;
+    float step_size, bc2_sqrt, inv_bc2_sqrt, tau;
 };
 
-// Adam bias corrections for step t (torch/optim/adam.py::_single_tensor_adam): python floats = double
-__device__ __forceinline__ void adam_factors(int step_before, float lr, float &step_size, float &bc2_sqrt) {
+// Adam bias corrections for step t (torch/optim/adam.py::_single_tensor_adam): python floats = double.  Double-precision
+// pow is slow on this part, so it runs once per optimizer per update (T_FINISH) and the tiles read the cached pair.
+__host__ __device__ inline void adam_factors(int step_before, float lr, float &step_size, float &bc2_sqrt) {
     const double t = (double)(step_before + 1);
     const double bc1 = 1.0 - pow((double)0.9, t);
     const double bc2 = 1.0 - pow((double)0.999, t);
     step_size = (float)((double)lr / bc1);
     bc2_sqrt = (float)sqrt(bc2);
+}
+__device__ __forceinline__ void adam_factors_cached(const float *scalars, int step_slot, float &step_size, float &bc2_sqrt) {
+    const float2 f = __ldcg(reinterpret_cast<const float2 *>(scalars + SC_FAC0 + 2 * (step_slot - SC_STEP_POLICY)));
+    step_size = f.x; bc2_sqrt = f.y;
+}
+__host__ __device__ inline void adam_factors_store(float *scalars, int step_slot, int step, float lr) {
+    adam_factors(step, lr, scalars[SC_FAC0 + 2 * (step_slot - SC_STEP_POLICY)], scalars[SC_FAC0 + 2 * (step_slot - SC_STEP_POLICY) + 1]);
 }
 
 // one Adam element update (+ Polyak, sac_imp.py:146-152); returns the new weight
@@ -109,7 +117,7 @@ __device__ __forceinline__ EpiR resolve_epilogue(const Task &t, const AgentBases
     e.Cpm = resolve_pm(t.Cpm, b, agent);
     e.bias = resolve(t.bias, b, agent);
     e.mask = resolve_pm(t.mask, b, agent);
-    e.w = e.m = e.v = e.wt = e.gexp = nullptr; e.apply = 0; e.step_size = e.bc2_sqrt = 0.f; e.tau = 0.f;
+    e.w = e.m = e.v = e.wt = e.gexp = nullptr; e.apply = 0; e.step_size = e.bc2_sqrt = e.inv_bc2_sqrt = 0.f; e.tau = 0.f;
     e.shadow.hi = nullptr; e.shadow.ld = 0; e.shadow.plane = 0;
     e.shadow2 = e.shadow; e.shadow2_col0 = 0;
     if (t.epi == EPI_ADAM) {
@@ -118,7 +126,8 @@ __device__ __forceinline__ EpiR resolve_epilogue(const Task &t, const AgentBases
         e.shadow = resolve_pm(t.adam.shadow, b, agent);
         e.shadow2 = resolve_pm(t.adam.shadow2, b, agent); e.shadow2_col0 = t.adam.shadow2_col0;
         e.apply = t.adam.apply; e.tau = t.adam.tau;
-        adam_factors(__float_as_int(ldcg(scalars + t.adam.step_slot)), t.adam.lr, e.step_size, e.bc2_sqrt);
+        adam_factors_cached(scalars, t.adam.step_slot, e.step_size, e.bc2_sqrt);
+        e.inv_bc2_sqrt = 1.0f / e.bc2_sqrt;
     }
     return e;
 }
@@ -192,22 +201,27 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 // generic-proxy writes (st.global / st.shared) -> visible to the async proxy (TMA, tensor core)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// same, shared memory only (does not wait for outstanding global stores)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// bounded wait (~0.5 s): a lost arrival must surface as an error, never as a hung GPU box
+// bounded wait: try_wait suspends the thread in hardware (no issue-slot burning spin next to the TMA / MMA warps) and
+// returns after a system-defined time limit; a lost arrival surfaces as an error after ~1 s, never as a hung GPU box
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity, int *error_flag) {
     const uint32_t addr = smem_u32(bar);
+    long long t0 = 0;
 #pragma unroll 1
-    for (uint32_t it = 0; it < (1u << 23); ++it) {
+    for (uint32_t it = 0;; ++it) {
         uint32_t done;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) return true;
-        if (it > 256) __nanosleep(32);
+        if (it == 0) t0 = clock64();
+        else if (clock64() - t0 > 2000000000ll) break;
     }
     if (error_flag) atomicExch(error_flag, 1);
     return false;
@@ -286,6 +300,7 @@ struct TcState {
     uint64_t *empty_bar;   // [kTStages]  tcgen05.commit -> TMA warp: the MMAs that read the slot are done
     uint64_t *accum_bar;   //             tcgen05.commit -> everyone: the accumulator tile is complete
     unsigned long long *trace;   // optional per-CTA timestamps (profiling aid)
+    const CUtensorMap *tmA, *tmB; // descriptors of the current task in GLOBAL memory (the task's other fields are read from a smem copy)
 };
 
 // ---- main loop of one output tile: warp 0 = TMA producer, warp 1 = MMA issuer ----------------------------------
@@ -293,8 +308,15 @@ struct TcState {
 //   K-major  A: one box {64 k, 128 rows, 2 planes}            -> [hi 16 KB][lo 16 KB]
 //   MN-major A: two boxes {64 m, 64 k, 2 planes} (m groups)   -> [hi g0 8K][lo g0 8K][hi g1 8K][lo g1 8K]
 //   B (either major): one box {64, 64, 2}                     -> [hi 8 KB][lo 8 KB]
-__device__ __forceinline__ void tc_mainloop(const Task &t, int m0, int n0, int agent, TcState &st, int *error_flag) {
+__device__ __forceinline__ void trace_stamp(unsigned long long *trace, int slot) {
+    unsigned long long ts;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
+    trace[(size_t)blockIdx.x * kTraceSlots + slot] = ts;
+}
+
+__device__ __forceinline__ void tc_mainloop(const Task &t, int m0, int n0, int agent, TcState &st, int *error_flag, bool traced) {
     const int warp = threadIdx.x >> 5;
+    if (traced && threadIdx.x == 0) trace_stamp(st.trace, 12);
     const int nkb = cdiv(t.K, kTK);
     const uint32_t tiles = smem_u32(st.tiles);
     const int a_mn = t.A.mn_major, b_mn = t.B.mn_major;
@@ -304,17 +326,18 @@ __device__ __forceinline__ void tc_mainloop(const Task &t, int m0, int n0, int a
             for (int kb = 0; kb < nkb; kb++) {
                 const uint32_t g = g0 + kb, s = g % kTStages;
                 mbar_wait(&st.empty_bar[s], ((g / kTStages) & 1) ^ 1, error_flag);
+                if (traced && kb < 16) trace_stamp(st.trace, 16 + kb);
                 mbar_arrive_expect_tx(&st.full_bar[s], kTcStageBytes);
                 const uint32_t sa = tiles + s * kTcStageBytes, sb = sa + kTcABytes;
                 const int k0 = kb * kTK, ma = t.A.r0 + m0, nb = t.B.r0 + n0;
                 if (!a_mn) {
-                    tma_load_4d(&t.tmA, &st.full_bar[s], sa, k0, ma, 0, agent);
+                    tma_load_4d(st.tmA, &st.full_bar[s], sa, k0, ma, 0, agent);
                 } else {
-                    tma_load_4d(&t.tmA, &st.full_bar[s], sa, ma, k0, 0, agent);
-                    tma_load_4d(&t.tmA, &st.full_bar[s], sa + kTcABytes / 2, ma + 64, k0, 0, agent);
+                    tma_load_4d(st.tmA, &st.full_bar[s], sa, ma, k0, 0, agent);
+                    tma_load_4d(st.tmA, &st.full_bar[s], sa + kTcABytes / 2, ma + 64, k0, 0, agent);
                 }
-                if (!b_mn) tma_load_4d(&t.tmB, &st.full_bar[s], sb, k0, nb, 0, agent);
-                else tma_load_4d(&t.tmB, &st.full_bar[s], sb, nb, k0, 0, agent);
+                if (!b_mn) tma_load_4d(st.tmB, &st.full_bar[s], sb, k0, nb, 0, agent);
+                else tma_load_4d(st.tmB, &st.full_bar[s], sb, nb, k0, 0, agent);
             }
         }
         __syncwarp();
@@ -328,6 +351,7 @@ __device__ __forceinline__ void tc_mainloop(const Task &t, int m0, int n0, int a
             const uint32_t g = g0 + kb, s = g % kTStages;
             mbar_wait(&st.full_bar[s], (g / kTStages) & 1, error_flag);
             tc_fence_after();
+            if (traced && kb < 16 && (threadIdx.x & 31) == 0) trace_stamp(st.trace, 32 + kb);
             if (elect_one()) {
                 const uint32_t sa = tiles + s * kTcStageBytes, sb = sa + kTcABytes;
 #pragma unroll
@@ -371,77 +395,132 @@ __device__ __forceinline__ void store_pm4(const Pm &p, int m, int n, int N, cons
     }
 }
 
+// Adam (+ Polyak, + shadow refresh) on one weight element; g = gradient
+struct AdamOut { float m, v, w, t; };
+__device__ __forceinline__ AdamOut adam_math(const EpiR &e, float g, float w, float m, float v, float wt) {
+    AdamOut o;
+    o.m = m + (1.0f - kBeta1) * (g - m);                                  // exp_avg.lerp_(grad, 1 - beta1)
+    o.v = v * kBeta2 + (1.0f - kBeta2) * g * g;                           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
+    o.w = w - e.step_size * __fdividef(o.m, __fsqrt_rn(o.v) * e.inv_bc2_sqrt + kAdamEps);     // <= 2 ulp from the IEEE form
+    o.t = wt * (1.0f - e.tau) + o.w * e.tau;                              // target <- target*(1-tau) + param*tau  (sac_imp.py:146-152)
+    return o;
+}
+
+// EPI_ADAM phase 2.  The weight matrix is contiguous [M, N] fp32 (it is aliased by the torch parameter), so when N % 4 != 0
+// a row starts at any 4-byte phase.
+//   pass A: per row the 16 threads take 4-column groups that start at the first 16-byte aligned column of THAT row inside
+//           the tile (a0 = 0..3): every w / m / v / target access is an aligned 128-bit access, all loads before any store
+//   pass B: the columns no aligned group covers (a0 leading ones, <= 3 trailing ones), one element per thread
+//   both passes leave the new weights in the staging tile; pass C writes the bf16 pair shadows from there with the
+//   tile-aligned mapping (the shadow rows are padded to 16 B)
+__device__ __forceinline__ void adam_epilogue_tile(const EpiR &e, float *Cs, int m0, int n0) {
+    const int tid = threadIdx.x;
+    const int ncols = min(kTN, e.N - n0);      // valid columns of this tile (> 0)
+    {   // ---- pass A
+        const int j16 = tid & 15, r0 = tid >> 4;
+        int mrow[4], c[4];
+        bool vec[4];
+        float4 w[4], mm[4], vv[4], wt[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            mrow[i] = m0 + 32 * i + r0;
+            const int a0 = (4 - (int)(((int64_t)mrow[i] * e.N + n0) & 3)) & 3;
+            c[i] = a0 + 4 * j16;
+            vec[i] = mrow[i] < e.M && c[i] + 3 < ncols;
+            w[i] = mm[i] = vv[i] = wt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (vec[i] && e.apply) {
+                const int64_t o = (int64_t)mrow[i] * e.N + n0 + c[i];
+                w[i] = __ldcg(reinterpret_cast<const float4 *>(e.w + o));
+                mm[i] = __ldcg(reinterpret_cast<const float4 *>(e.m + o));
+                vv[i] = __ldcg(reinterpret_cast<const float4 *>(e.v + o));
+                if (e.wt) wt[i] = __ldcg(reinterpret_cast<const float4 *>(e.wt + o));
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (!vec[i]) continue;
+            float *cs = Cs + (32 * i + r0) * kCsLd + c[i];
+            const int64_t o = (int64_t)mrow[i] * e.N + n0 + c[i];
+            const float g[4] = {cs[0], cs[1], cs[2], cs[3]};
+            if (e.gexp) *reinterpret_cast<float4 *>(e.gexp + o) = make_float4(g[0], g[1], g[2], g[3]);
+            if (!e.apply) continue;
+            const AdamOut a = adam_math(e, g[0], w[i].x, mm[i].x, vv[i].x, wt[i].x), b = adam_math(e, g[1], w[i].y, mm[i].y, vv[i].y, wt[i].y);
+            const AdamOut cc = adam_math(e, g[2], w[i].z, mm[i].z, vv[i].z, wt[i].z), d = adam_math(e, g[3], w[i].w, mm[i].w, vv[i].w, wt[i].w);
+            *reinterpret_cast<float4 *>(e.m + o) = make_float4(a.m, b.m, cc.m, d.m);
+            *reinterpret_cast<float4 *>(e.v + o) = make_float4(a.v, b.v, cc.v, d.v);
+            *reinterpret_cast<float4 *>(e.w + o) = make_float4(a.w, b.w, cc.w, d.w);
+            if (e.wt) *reinterpret_cast<float4 *>(e.wt + o) = make_float4(a.t, b.t, cc.t, d.t);
+            cs[0] = a.w; cs[1] = b.w; cs[2] = cc.w; cs[3] = d.w;
+        }
+    }
+    if (e.N % 4 != 0 || ncols < kTN) {   // ---- pass B (warp-uniform condition): thread (row = tid / 4, q = tid % 4)
+        const int row = tid >> 2, q = tid & 3, m = m0 + row;
+        if (m < e.M) {
+            const int a0 = (4 - (int)(((int64_t)m * e.N + n0) & 3)) & 3;
+            const int nv = ncols > a0 ? (ncols - a0) >> 2 : 0, tail0 = a0 + 4 * nv;
+            int col[2];
+            int cnt = 0;
+            if (q < min(a0, ncols)) col[cnt++] = q;                 // leading columns [0, a0)
+            if (tail0 + q < ncols) col[cnt++] = tail0 + q;         // trailing columns [tail0, ncols)
+            float w[2], mm[2], vv[2], wt[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                w[u] = mm[u] = vv[u] = wt[u] = 0.f;
+                if (u < cnt && e.apply) {
+                    const int64_t o = (int64_t)m * e.N + n0 + col[u];
+                    w[u] = __ldcg(e.w + o); mm[u] = __ldcg(e.m + o); vv[u] = __ldcg(e.v + o);
+                    if (e.wt) wt[u] = __ldcg(e.wt + o);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                if (u >= cnt) continue;
+                const int64_t o = (int64_t)m * e.N + n0 + col[u];
+                float *cs = Cs + row * kCsLd + col[u];
+                const float g = *cs;
+                if (e.gexp) e.gexp[o] = g;
+                if (!e.apply) continue;
+                const AdamOut r = adam_math(e, g, w[u], mm[u], vv[u], wt[u]);
+                e.m[o] = r.m; e.v[o] = r.v; e.w[o] = r.w;
+                if (e.wt) e.wt[o] = r.t;
+                *cs = r.w;
+            }
+        }
+    }
+    if (!e.apply || (!e.shadow.hi && !e.shadow2.hi)) return;
+    __syncthreads();                     // ---- pass C: the staging tile now holds the new weights
+    {
+        const int c4 = (tid & 15) * 4, r0 = tid >> 4;
+        if (c4 >= ncols) return;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int m = m0 + 32 * i + r0;
+            if (m >= e.M) continue;
+            const float4 v4 = *reinterpret_cast<const float4 *>(Cs + (32 * i + r0) * kCsLd + c4);
+            const float w1[4] = {v4.x, v4.y, v4.z, v4.w};
+            const int n = n0 + c4;
+            if (e.shadow.hi) store_pm4(e.shadow, m, n, e.N, w1);
+            if (e.shadow2.hi && n + 3 >= e.shadow2_col0) {
+                if (n >= e.shadow2_col0 && ((n - e.shadow2_col0) & 3) == 0) {
+                    store_pm4(e.shadow2, m, n - e.shadow2_col0, e.N - e.shadow2_col0, w1);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (n + j >= e.shadow2_col0 && n + j < e.N) pm_store(e.shadow2, m, n + j - e.shadow2_col0, w1[j]);
+                }
+            }
+        }
+    }
+}
+
 // R rows (m[i]) x 4 columns starting at n; acc[i] = the staged accumulators.  All global loads are issued before any store.
 template <int EPI, int R>
-__device__ __forceinline__ void epilogue_rows4(const EpiR &e, const int (&m)[R], int n, const float4 (&acc4)[R]) {
+__device__ __forceinline__ void epilogue_rows4(const EpiR &e, const int (&m)[R], int n, const float4 (&acc4)[R], unsigned long long *tr) {
     if (n >= e.N) return;
     const bool full = n + 3 < e.N;
     float acc[R][4];
 #pragma unroll
     for (int i = 0; i < R; i++) { acc[i][0] = acc4[i].x; acc[i][1] = acc4[i].y; acc[i][2] = acc4[i].z; acc[i][3] = acc4[i].w; }
-    if (EPI == EPI_ADAM) {
-        const bool vec = full && (e.N % 4 == 0);
-        float w[R][4], mm[R][4], vv[R][4], wt[R][4];
-#pragma unroll
-        for (int i = 0; i < R; i++) {
-            const bool rok = m[i] < e.M && e.apply;
-            const int64_t o = (int64_t)m[i] * e.N + n;
-            if (rok && vec) {
-                const float4 a = __ldcg(reinterpret_cast<const float4 *>(e.w + o)), b = __ldcg(reinterpret_cast<const float4 *>(e.m + o));
-                const float4 c = __ldcg(reinterpret_cast<const float4 *>(e.v + o));
-                const float4 d = e.wt ? __ldcg(reinterpret_cast<const float4 *>(e.wt + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                w[i][0] = a.x; w[i][1] = a.y; w[i][2] = a.z; w[i][3] = a.w; mm[i][0] = b.x; mm[i][1] = b.y; mm[i][2] = b.z; mm[i][3] = b.w;
-                vv[i][0] = c.x; vv[i][1] = c.y; vv[i][2] = c.z; vv[i][3] = c.w; wt[i][0] = d.x; wt[i][1] = d.y; wt[i][2] = d.z; wt[i][3] = d.w;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const bool ok = rok && n + j < e.N;
-                    w[i][j] = ok ? __ldcg(e.w + o + j) : 0.f; mm[i][j] = ok ? __ldcg(e.m + o + j) : 0.f;
-                    vv[i][j] = ok ? __ldcg(e.v + o + j) : 0.f; wt[i][j] = (ok && e.wt) ? __ldcg(e.wt + o + j) : 0.f;
-                }
-            }
-        }
-#pragma unroll
-        for (int i = 0; i < R; i++) {
-            if (m[i] >= e.M) continue;
-            const int64_t o = (int64_t)m[i] * e.N + n;
-            float m1[4], v1[4], w1[4], t1[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float g = acc[i][j];
-                m1[j] = mm[i][j] + (1.0f - kBeta1) * (g - mm[i][j]);
-                v1[j] = vv[i][j] * kBeta2 + (1.0f - kBeta2) * g * g;
-                w1[j] = w[i][j] - e.step_size * (m1[j] / (sqrtf(v1[j]) / e.bc2_sqrt + kAdamEps));
-                t1[j] = wt[i][j] * (1.0f - e.tau) + w1[j] * e.tau;
-            }
-            if (vec) {
-                if (e.gexp) *reinterpret_cast<float4 *>(e.gexp + o) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-                if (e.apply) {
-                    *reinterpret_cast<float4 *>(e.m + o) = make_float4(m1[0], m1[1], m1[2], m1[3]);
-                    *reinterpret_cast<float4 *>(e.v + o) = make_float4(v1[0], v1[1], v1[2], v1[3]);
-                    *reinterpret_cast<float4 *>(e.w + o) = make_float4(w1[0], w1[1], w1[2], w1[3]);
-                    if (e.wt) *reinterpret_cast<float4 *>(e.wt + o) = make_float4(t1[0], t1[1], t1[2], t1[3]);
-                }
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    if (n + j >= e.N) continue;
-                    if (e.gexp) e.gexp[o + j] = acc[i][j];
-                    if (!e.apply) continue;
-                    e.m[o + j] = m1[j]; e.v[o + j] = v1[j]; e.w[o + j] = w1[j];
-                    if (e.wt) e.wt[o + j] = t1[j];
-                }
-            }
-            if (!e.apply) continue;
-            if (e.shadow.hi) store_pm4(e.shadow, m[i], n, e.N, w1);
-            if (e.shadow2.hi && n + 3 >= e.shadow2_col0) {
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (n + j >= e.shadow2_col0 && n + j < e.N) pm_store(e.shadow2, m[i], n + j - e.shadow2_col0, w1[j]);
-            }
-        }
-        return;
-    }
     float aux[R][4];
 #pragma unroll
     for (int i = 0; i < R; i++) {
@@ -458,11 +537,23 @@ __device__ __forceinline__ void epilogue_rows4(const EpiR &e, const int (&m)[R],
 #pragma unroll
                 for (int j = 0; j < 4; j++) aux[i][j] = (n + j < e.N) ? __bfloat162float(q[j]) : 0.f;
             }
-        } else if (e.bias) {
+        } else if (e.bias && i == 0) {       // the bias depends on the column only (arena vectors are 16 B aligned, n % 4 == 0)
+            if (full) {
+                const float4 b4 = __ldcg(reinterpret_cast<const float4 *>(e.bias + n));
+                aux[0][0] = b4.x; aux[0][1] = b4.y; aux[0][2] = b4.z; aux[0][3] = b4.w;
+            } else {
 #pragma unroll
-            for (int j = 0; j < 4; j++) aux[i][j] = (n + j < e.N) ? ldcg(e.bias + n + j) : 0.f;
+                for (int j = 0; j < 4; j++) aux[0][j] = (n + j < e.N) ? ldcg(e.bias + n + j) : 0.f;
+            }
         }
     }
+    if (EPI != EPI_MASK) {
+#pragma unroll
+        for (int i = 1; i < R; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) aux[i][j] = aux[0][j];
+    }
+    if (tr && aux[0][0] != 12345.678f) trace_stamp(tr, 14);      // the auxiliary loads have landed
 #pragma unroll
     for (int i = 0; i < R; i++) {
         if (m[i] >= e.M) continue;
@@ -488,10 +579,11 @@ __device__ __forceinline__ void epilogue_rows4(const EpiR &e, const int (&m)[R],
 }
 
 template <int EPI>
-__device__ __forceinline__ void tc_epilogue(const EpiR &epi, int m0, int n0, TcState &st, int *error_flag) {
+__device__ __forceinline__ void tc_epilogue(const EpiR &epi, int m0, int n0, TcState &st, int *error_flag, bool traced) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     mbar_wait(st.accum_bar, st.accum_uses & 1, error_flag);
     st.accum_uses++;
+    if (traced && tid == 64) trace_stamp(st.trace, 6);
     tc_fence_after();
     float *Cs = reinterpret_cast<float *>(st.tiles);      // staging tile [kTM][kCsLd] over operand stage 0 (all MMAs have retired)
     {   // phase 1: warp w owns TMEM lanes 32*(w%4).., column group w/4
@@ -504,43 +596,42 @@ __device__ __forceinline__ void tc_epilogue(const EpiR &epi, int m0, int n0, TcS
     }
     tc_fence_before();
     __syncthreads();     // staging tile complete; all TMEM reads retired (the next tile's first MMA may overwrite the accumulator)
-    {   // phase 2
+    if (traced && tid == 64) trace_stamp(st.trace, 7);
+    if (EPI == EPI_ADAM) {
+        adam_epilogue_tile(epi, Cs, m0, n0);
+    } else {   // phase 2: all four rows of a thread at once, so every global load is in flight before the first store
         const int c4 = (tid & 15) * 4, r0 = tid >> 4;
+        const int m[4] = {m0 + r0, m0 + 32 + r0, m0 + 64 + r0, m0 + 96 + r0};
+        float4 acc[4];
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
-            const int rows[2] = {half * 64 + r0, half * 64 + 32 + r0};
-            const float4 acc[2] = {*reinterpret_cast<const float4 *>(Cs + rows[0] * kCsLd + c4),
-                                   *reinterpret_cast<const float4 *>(Cs + rows[1] * kCsLd + c4)};
-            const int m[2] = {m0 + rows[0], m0 + rows[1]};
-            epilogue_rows4<EPI, 2>(epi, m, n0 + c4, acc);
-        }
+        for (int i = 0; i < 4; i++) acc[i] = *reinterpret_cast<const float4 *>(Cs + (32 * i + r0) * kCsLd + c4);
+        if (traced && tid == 64 && acc[0].x != 12345.678f) trace_stamp(st.trace, 13);
+        epilogue_rows4<EPI, 4>(epi, m, n0 + c4, acc, (traced && tid == 64) ? st.trace : nullptr);
     }
-    fence_proxy_async();   // generic-proxy accesses of the staging tile are ordered before the next TMA write into it
+    if (traced && tid == 64) trace_stamp(st.trace, 8);
+    fence_proxy_async_smem();   // generic-proxy accesses of the staging tile are ordered before the next TMA write into it
     __syncthreads();
 }
 
 }  // namespace tc
 
-__device__ __forceinline__ void gemm_tile_tc(const Task &t, int tile, const AgentBases &bases, int agent,
+// t = shared-memory copy of the task (fields), tg = the task in global memory (TMA descriptors)
+__device__ __forceinline__ void gemm_tile_tc(const Task &t, const Task *tg, int tile, const AgentBases &bases, int agent,
                                              const float *scalars, tc::TcState &st, int *error_flag) {
     using namespace tc;
+    st.tmA = &tg->tmA; st.tmB = &tg->tmB;
     const int tm = tile / t.tiles_n, tn = tile % t.tiles_n;
     const int m0 = tm * kTM, n0 = tn * kTN;
-    tc_mainloop(t, m0, n0, agent, st, error_flag);
-    auto stamp = [&](int slot) {
-        if (st.trace && threadIdx.x == 0 && tile == (int)blockIdx.x - t.tile_begin) {
-            unsigned long long ts;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
-            st.trace[(size_t)blockIdx.x * 8 + slot] = ts;
-        }
-    };
+    const bool traced = st.trace && tile == (int)blockIdx.x - t.tile_begin;      // the CTA's first tile of the stage
+    tc_mainloop(t, m0, n0, agent, st, error_flag, traced);
+    auto stamp = [&](int slot) { if (traced && threadIdx.x == 0) trace_stamp(st.trace, slot); };
     stamp(2);
     const EpiR epi = resolve_epilogue(t, bases, agent, scalars);
     switch (t.epi) {
-        case EPI_F32: tc_epilogue<EPI_F32>(epi, m0, n0, st, error_flag); break;
-        case EPI_BIAS_RELU: tc_epilogue<EPI_BIAS_RELU>(epi, m0, n0, st, error_flag); break;
-        case EPI_MASK: tc_epilogue<EPI_MASK>(epi, m0, n0, st, error_flag); break;
-        default: tc_epilogue<EPI_ADAM>(epi, m0, n0, st, error_flag); break;
+        case EPI_F32: tc_epilogue<EPI_F32>(epi, m0, n0, st, error_flag, traced); break;
+        case EPI_BIAS_RELU: tc_epilogue<EPI_BIAS_RELU>(epi, m0, n0, st, error_flag, traced); break;
+        case EPI_MASK: tc_epilogue<EPI_MASK>(epi, m0, n0, st, error_flag, traced); break;
+        default: tc_epilogue<EPI_ADAM>(epi, m0, n0, st, error_flag, traced); break;
     }
     stamp(3);
 }

@@ -158,17 +158,20 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
 
 template <int kMath>
 __global__ void __launch_bounds__(kThreads, 1)
-sac_update_kernel(const Program P, const int stage_begin, const int stage_end, const int tc_setup, const uint64_t seed) {
+sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Stage single, const int stage_begin, const int stage_end, const int tc_setup, const uint64_t seed) {
+    // `single` = the stage table entry when the launch covers exactly one stage (staged mode): no global load before the first task
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint64_t s_bars[2 * kTStages + 1];
     __shared__ uint32_t s_tmem;
     __shared__ float s_red[kThreads];
+    __shared__ Stage s_stage;
+    __shared__ Task s_task;            // fields of the current task (the TMA descriptors are used from global memory)
 
     auto stamp = [&](int slot) {
         if (P.trace && threadIdx.x == 0) {
             unsigned long long t;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-            P.trace[(size_t)blockIdx.x * 8 + slot] = t;
+            P.trace[(size_t)blockIdx.x * kTraceSlots + slot] = t;
         }
     };
     stamp(0);
@@ -192,18 +195,36 @@ sac_update_kernel(const Program P, const int stage_begin, const int stage_end, c
     stamp(1);
     unsigned int bar_target = 0;
     for (int s = stage_begin; s < stage_end; s++) {
-        const Stage sg = P.stages[s];
-        const int total = sg.n_tiles * P.n_agents;
+        if (threadIdx.x < sizeof(Stage) / 4) {
+            const int32_t *src = (stage_end - stage_begin == 1) ? reinterpret_cast<const int32_t *>(&single) : reinterpret_cast<const int32_t *>(&P.stages[s]);
+            reinterpret_cast<int32_t *>(&s_stage)[threadIdx.x] = src[threadIdx.x];
+        }
+        __syncthreads();
+        stamp(9);
+        const int n_stage_tiles = s_stage.n_tiles, n_stage_tasks = s_stage.task_end - s_stage.task_begin;
+        const int total = n_stage_tiles * P.n_agents;
         for (int wi = blockIdx.x; wi < total; wi += gridDim.x) {
-            const int agent = wi / sg.n_tiles, tile_in_stage = wi % sg.n_tiles;
-            int ti = sg.task_begin;
-            while (ti + 1 < sg.task_end && tile_in_stage >= P.tasks[ti + 1].tile_begin) ti++;
-            const Task &t = P.tasks[ti];
-            const int tile = tile_in_stage - t.tile_begin;
+            const int agent = wi / n_stage_tiles, tile_in_stage = wi % n_stage_tiles;
+            int k = 0;
+            while (k + 1 < n_stage_tasks && tile_in_stage >= s_stage.tile_begin[k + 1]) k++;
+            const Task *tg = &P.tasks[s_stage.task_begin + k];
+            const int tile = tile_in_stage - s_stage.tile_begin[k];
+            {   // one parallel fetch of the task's fields instead of a chain of dependent global loads
+                constexpr int kSkip = 2 * sizeof(CUtensorMap) / 4, kWords = sizeof(Task) / 4 - kSkip;
+                static_assert(kWords <= kThreads, "task copy");
+                if (kTc && threadIdx.x == kThreads - 1) { tc::tma_prefetch_desc(&tg->tmA); tc::tma_prefetch_desc(&tg->tmB); }
+                __syncthreads();     // the previous tile's readers of s_task are done
+                if (wi == (int)blockIdx.x) stamp(10);
+                if ((int)threadIdx.x < kWords)
+                    reinterpret_cast<int32_t *>(&s_task)[kSkip + threadIdx.x] = __ldcg(reinterpret_cast<const int32_t *>(tg) + kSkip + threadIdx.x);
+                __syncthreads();
+                if (wi == (int)blockIdx.x) stamp(11);
+            }
+            const Task &t = s_task;
             float *scalars = resolve(P.scalars, P.bases, agent);
             switch (t.type) {
                 case T_GEMM:
-                    if (kTc) gemm_tile_tc(t, tile, P.bases, agent, scalars, st, P.error_flag);
+                    if (kTc) gemm_tile_tc(t, tg, tile, P.bases, agent, scalars, st, P.error_flag);
                     else gemm_tile_ffma(t, tile, P.bases, agent, scalars, reinterpret_cast<float *>(smem_raw));
                     break;
                 case T_SHADOW: task_shadow(t, tile, P, agent); break;
@@ -214,7 +235,7 @@ sac_update_kernel(const Program P, const int stage_begin, const int stage_end, c
                 case T_SAMPLE_BWD: task_sample_bwd(t, tile, P, agent, scalars); break;
                 case T_OUT_ADAM: task_out_adam(t, tile, P, agent, scalars, s_red); break;
                 case T_BIAS_ADAM: task_bias_adam(t, tile, P, agent, scalars, s_red); break;
-                case T_FINISH: task_finish(t, P, agent, scalars, s_red); break;
+                case T_FINISH: task_finish(t, P, agent, scalars, s_red); __syncthreads(); task_finish_steps(t, scalars); break;
             }
             if (wi == (int)blockIdx.x) stamp(4);
         }
@@ -299,6 +320,8 @@ struct Builder {
     }
     void add(Task t, int n_tiles) {
         Stage &s = stages.back();
+        if (s.task_end - s.task_begin >= kMaxStageTasks) { rc = fail(SACB_ERR_ARG, "too many tasks in one stage"); return; }
+        s.tile_begin[s.task_end - s.task_begin] = s.n_tiles;
         t.tile_begin = s.n_tiles; t.n_tiles = n_tiles;
         s.n_tiles += n_tiles; s.task_end++;
         if (t.type == T_GEMM) has_gemm.back() = 1;
@@ -362,7 +385,7 @@ struct Builder {
         AdamArgs a = adam_args(net, b_off);
         t.p[0] = a.w; t.p[1] = a.m; t.p[2] = a.v; t.p[3] = a.wt; t.p[4] = a.gexp;
         t.i[0] = Bn; t.i[1] = N; t.i[2] = a.step_slot; t.i[3] = a.apply; t.f[0] = a.lr; t.f[1] = a.tau;
-        add(t, cdiv(N, 32));
+        add(t, cdiv(N, kColsumCols));
     }
     // shadow of columns [col0, col0+dst.cols) of the fp32 matrix at w_off (row stride src_ld)
     void shadow_task(int net, int64_t w_off, const PmView &dst, int src_ld, int col0 = 0) {
@@ -464,7 +487,7 @@ struct Builder {
                         t.p[2] = aw.w; t.p[3] = aw.m; t.p[4] = aw.v; t.p[5] = aw.wt; t.p[6] = aw.gexp;
                         t.p[7] = ab.w; t.p[8] = ab.m; t.p[9] = ab.v; t.p[10] = ab.wt; t.p[11] = ab.gexp;
                         t.i[0] = B; t.i[1] = H; t.i[2] = aw.step_slot; t.i[3] = aw.apply; t.f[0] = aw.lr; t.f[1] = aw.tau;
-                        add(t, cdiv(H, 32));
+                        add(t, cdiv(H, kColsumCols));
                     }
                 }
             }
@@ -581,7 +604,8 @@ static int launch_range(sacb_handle h, ProgramInst &p, int s0, int s1, bool coop
     const size_t smem = math_smem(h->cfg.math_mode);
     uint64_t seed = h->cfg.seed;
     int tc_setup = tf32 ? needs_tc : 0;
-    void *args[] = {(void *)&p.prog, (void *)&s0, (void *)&s1, (void *)&tc_setup, (void *)&seed};
+    Stage single = p.stages[s0];
+    void *args[] = {(void *)&p.prog, (void *)&single, (void *)&s0, (void *)&s1, (void *)&tc_setup, (void *)&seed};
     const void *fn = update_kernel_for(h->cfg.math_mode);
     if (cooperative) {
         const int grid = std::min(max_tiles, h->sm_count * h->coop_blocks_per_sm);
@@ -672,7 +696,8 @@ extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap
     const bool trace = getenv("SACB_TRACE") != nullptr;
     unsigned long long *d_trace = nullptr;
     std::vector<unsigned long long> h_trace;
-    if (trace) { SACB_CUDA(cudaMalloc(&d_trace, sizeof(unsigned long long) * 8 * 4096)); p->prog.trace = d_trace; h_trace.resize(8 * 4096); }
+    if (trace) { SACB_CUDA(cudaMalloc(&d_trace, sizeof(unsigned long long) * kTraceSlots * 4096)); SACB_CUDA(cudaMemset(d_trace, 0, sizeof(unsigned long long) * kTraceSlots * 4096));
+                 p->prog.trace = d_trace; h_trace.resize(kTraceSlots * 4096); }
     const int n = std::min<int>(cap, (int)p->stages.size());
     std::vector<cudaEvent_t> ev(p->stages.size() + 1);
     for (auto &e : ev) cudaEventCreate(&e);
@@ -685,18 +710,19 @@ extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap
             const bool tf32 = math_is_tc(h->cfg.math_mode);
             int s0 = s, s1 = s + 1, tc_setup = tf32 ? p->stage_has_gemm[s] : 0;
             uint64_t seed = h->cfg.seed;
-            void *args[] = {(void *)&p->prog, (void *)&s0, (void *)&s1, (void *)&tc_setup, (void *)&seed};
+            Stage single = p->stages[s];
+            void *args[] = {(void *)&p->prog, (void *)&single, (void *)&s0, (void *)&s1, (void *)&tc_setup, (void *)&seed};
             SACB_CUDA(cudaLaunchKernel(update_kernel_for(h->cfg.math_mode), dim3(std::max(1, p->stages[s].n_tiles * h->cfg.n_agents)), dim3(kThreads), args,
                                        math_smem(h->cfg.math_mode), h->stream));
             cudaEventRecord(ev[s + 1], h->stream);
             if (trace && r == reps + 2) {
                 SACB_CUDA(cudaStreamSynchronize(h->stream));
                 const int grid = std::max(1, p->stages[s].n_tiles * h->cfg.n_agents);
-                SACB_CUDA(cudaMemcpy(h_trace.data(), d_trace, sizeof(unsigned long long) * 8 * std::min(grid, 4096), cudaMemcpyDeviceToHost));
+                SACB_CUDA(cudaMemcpy(h_trace.data(), d_trace, sizeof(unsigned long long) * kTraceSlots * std::min(grid, 4096), cudaMemcpyDeviceToHost));
                 double a[8] = {0}, mx_tile = 0, mx_main = 0; unsigned long long t0 = ~0ull, t0max = 0, t5 = 0;
                 const int g = std::min(grid, 4096);
                 for (int b = 0; b < g; b++) {
-                    const unsigned long long *q = &h_trace[b * 8];
+                    const unsigned long long *q = &h_trace[b * kTraceSlots];
                     t0 = std::min(t0, q[0]); t0max = std::max(t0max, q[0]); t5 = std::max(t5, q[5]);
                     a[1] += (double)(q[1] - q[0]); a[4] += (double)(q[4] - q[1]); a[5] += (double)(q[5] - q[4]);
                     mx_tile = std::max(mx_tile, (double)(q[4] - q[1]));
@@ -705,6 +731,26 @@ extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap
                 fprintf(stderr, "[trace] stage %2d grid %4d gemm %d span %6.2f us start-skew %5.2f | per-CTA avg: setup %.2f mainloop %.2f (max %.2f) epilogue %.2f tile %.2f (max %.2f) teardown %.2f\n",
                         s, grid, p->stage_has_gemm[s], (t5 - t0) * 1e-3, (t0max - t0) * 1e-3, a[1] / g * 1e-3, a[2] / g * 1e-3, mx_main * 1e-3, a[3] / g * 1e-3,
                         a[4] / g * 1e-3, mx_tile * 1e-3, a[5] / g * 1e-3);
+                {   // slowest tile of every task of the stage (which task sets the span)
+                    const Stage &sg = p->stages[s];
+                    fprintf(stderr, "[trace]   per-task max tile us:");
+                    for (int k = 0; k < sg.task_end - sg.task_begin; k++) {
+                        const Task &tk = p->tasks[sg.task_begin + k];
+                        double mx = 0;
+                        for (int b = tk.tile_begin; b < tk.tile_begin + tk.n_tiles && b < g; b++) mx = std::max(mx, (double)(h_trace[b * kTraceSlots + 4] - h_trace[b * kTraceSlots + 1]));
+                        fprintf(stderr, " [type %d epi %d %dx%dx%d n=%d] %.1f", tk.type, tk.epi, tk.M, tk.N, tk.K, tk.n_tiles, mx * 1e-3);
+                    }
+                    fprintf(stderr, "\n");
+                }
+                if (p->stage_has_gemm[s]) {      // k-block timeline of CTA 0: TMA issue / arrival times relative to the end of setup
+                    const unsigned long long *q = &h_trace[0];
+                    fprintf(stderr, "[trace]   cta0 issue:");
+                    for (int kb = 0; kb < 16 && q[16 + kb] >= q[1]; kb++) fprintf(stderr, " %.2f", (q[16 + kb] - q[1]) * 1e-3);
+                    fprintf(stderr, " | arrive:");
+                    for (int kb = 0; kb < 16 && q[32 + kb] >= q[1]; kb++) fprintf(stderr, " %.2f", (q[32 + kb] - q[1]) * 1e-3);
+                    fprintf(stderr, " | accum %.2f staged %.2f stored %.2f epi-end %.2f\n", (q[6] - q[1]) * 1e-3, (q[7] - q[1]) * 1e-3, (q[8] - q[1]) * 1e-3, (q[3] - q[1]) * 1e-3);
+                    SACB_CUDA(cudaMemset(d_trace, 0, sizeof(unsigned long long) * kTraceSlots * 4096));
+                }
             }
         }
         SACB_CUDA(cudaStreamSynchronize(h->stream));
@@ -712,6 +758,32 @@ extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap
             for (int s = 0; s < (int)p->stages.size(); s++) { float ms; cudaEventElapsedTime(&ms, ev[s], ev[s + 1]); acc[s] += ms * 1000.f / reps; }
     }
     for (int s = 0; s < n; s++) us_out[s] = acc[s];
+    if (trace && getenv("SACB_TRACE_RANGE")) {
+        // warm-code experiment: stages [a, b) in ONE cooperative launch; the surviving stamps belong to stage b-1 and are
+        // printed relative to its own start (slot 9, right after the grid barrier)
+        int a = 1, b = 4;
+        sscanf(getenv("SACB_TRACE_RANGE"), "%d,%d", &a, &b);
+        int tc_setup = 1; uint64_t seed = h->cfg.seed; Stage single = p->stages[a];
+        void *args[] = {(void *)&p->prog, (void *)&single, (void *)&a, (void *)&b, (void *)&tc_setup, (void *)&seed};
+        int grid = 1;
+        for (int s = a; s < b; s++) grid = std::max(grid, p->stages[s].n_tiles);
+        grid = std::min(grid, h->sm_count);
+        for (int r = 0; r < 3; r++) {
+            SACB_CUDA(cudaMemsetAsync(h->barrier, 0, sizeof(unsigned int), h->stream));
+            SACB_CUDA(cudaLaunchCooperativeKernel(update_kernel_for(h->cfg.math_mode), dim3(grid), dim3(kThreads), args, math_smem(h->cfg.math_mode), h->stream));
+        }
+        SACB_CUDA(cudaStreamSynchronize(h->stream));
+        SACB_CUDA(cudaMemcpy(h_trace.data(), d_trace, sizeof(unsigned long long) * kTraceSlots * grid, cudaMemcpyDeviceToHost));
+        for (int c = 0; c < std::min(grid, 3); c++) {
+            const unsigned long long *q = &h_trace[c * kTraceSlots];
+            fprintf(stderr, "[warm] stages [%d,%d) cta%d: kernel %.2f us | last stage from its start: issue", a, b, c, (q[5] - q[0]) * 1e-3);
+            for (int kb = 0; kb < 16 && q[16 + kb] >= q[9]; kb++) fprintf(stderr, " %.2f", (q[16 + kb] - q[9]) * 1e-3);
+            fprintf(stderr, " | arrive");
+            for (int kb = 0; kb < 16 && q[32 + kb] >= q[9]; kb++) fprintf(stderr, " %.2f", (q[32 + kb] - q[9]) * 1e-3);
+            fprintf(stderr, " | accum %.2f staged %.2f stored %.2f epi-end %.2f || presync %.2f taskcopy %.2f mainloop-entry %.2f | acc-lds %.2f aux-ldg %.2f\n", (q[6] - q[9]) * 1e-3, (q[7] - q[9]) * 1e-3, (q[8] - q[9]) * 1e-3, (q[3] - q[9]) * 1e-3,
+                    (q[10] - q[9]) * 1e-3, (q[11] - q[9]) * 1e-3, (q[12] - q[9]) * 1e-3, (q[13] - q[9]) * 1e-3, (q[14] - q[9]) * 1e-3);
+        }
+    }
     if (trace) { p->prog.trace = nullptr; cudaFree(d_trace); }
     for (auto &e : ev) cudaEventDestroy(e);
     h->kernel_launches += (int64_t)(reps + 3) * p->stages.size();

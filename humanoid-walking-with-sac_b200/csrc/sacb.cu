@@ -43,6 +43,7 @@ extern "C" int sacb_device_count(void) {
 static int scalars_init(sacb_handle h) {
     std::vector<float> sc(32, 0.f);
     sc[SC_ALPHA0] = sc[SC_ALPHA1] = h->cfg.alpha0;     // python float 0.2 until the first update (quirk Q1)
+    for (int slot = SC_STEP_POLICY; slot <= SC_STEP_ALPHA; slot++) adam_factors_store(sc.data(), slot, 0, h->cfg.lr);
     for (int a = 0; a < h->cfg.n_agents; a++)
         SACB_CUDA(cudaMemcpyAsync(h->arena + a * h->L.arena_size + h->L.scalars, sc.data(), 32 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     return cudaStreamSynchronize(h->stream) == cudaSuccess ? SACB_OK : SACB_ERR_DEVICE;
@@ -208,6 +209,8 @@ extern "C" int sacb_set_scalars(sacb_handle h, int agent, const sacb_scalars *in
     sc[SC_ALPHA0] = sc[SC_ALPHA1] = in->alpha;
     sc[SC_STEP_POLICY] = i2f(in->step_policy); sc[SC_STEP_Q1] = i2f(in->step_q1); sc[SC_STEP_Q2] = i2f(in->step_q2);
     sc[SC_STEP_ALPHA] = i2f(in->step_alpha); sc[SC_N_UPDATES] = i2f(in->n_updates);
+    adam_factors_store(sc, SC_STEP_POLICY, (int)in->step_policy, h->cfg.lr); adam_factors_store(sc, SC_STEP_Q1, (int)in->step_q1, h->cfg.lr);
+    adam_factors_store(sc, SC_STEP_Q2, (int)in->step_q2, h->cfg.lr); adam_factors_store(sc, SC_STEP_ALPHA, (int)in->step_alpha, h->cfg.lr);
     SACB_CUDA(cudaMemcpyAsync(dev, sc, sizeof(sc), cudaMemcpyHostToDevice, h->stream));
     SACB_CUDA(cudaStreamSynchronize(h->stream));
     return SACB_OK;

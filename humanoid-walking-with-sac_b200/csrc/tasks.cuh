@@ -61,65 +61,76 @@ __device__ __forceinline__ void task_shadow(const Task &t, int tile, const Progr
     const Pm dst = resolve_pm(t.pm[0], P.bases, agent);
     const float *src0 = resolve(t.p[0], P.bases, agent) + t.i[2];
     const bool even = ((t.i[3] | t.i[2]) & 1) == 0;     // every row starts 8 B aligned in src and 4 B aligned in dst
-#pragma unroll 1
-    for (int i = 0; i < kShadowRows / (kThreads / 32); i++) {
-        const int r = tile * kShadowRows + i * (kThreads / 32) + warp;
-        if (r >= rows) return;
-        const float *src = src0 + (int64_t)r * t.i[3];
-        __nv_bfloat16 *q = dst.hi + (int64_t)r * dst.ld;
-        if (even) {
-            for (int c = 2 * lane; c < cols; c += 64) {
-                float2 x = __ldcg(reinterpret_cast<const float2 *>(src + c));
-                if (c + 1 >= cols) x.y = 0.f;
-                uint32_t hi, lo;
-                split_pack2(x.x, x.y, hi, lo);
-                *reinterpret_cast<uint32_t *>(q + c) = hi;
-                *reinterpret_cast<uint32_t *>(q + c + dst.plane) = lo;
+    constexpr int kR = kShadowRows / (kThreads / 32);    // rows per warp, handled together: kR independent loads in flight per trip
+    const int r0 = tile * kShadowRows + warp;
+    for (int c = 2 * lane; c < cols; c += 64) {
+        float2 x[kR];
+#pragma unroll
+        for (int i = 0; i < kR; i++) {
+            const int r = r0 + i * (kThreads / 32);
+            x[i] = make_float2(0.f, 0.f);
+            if (r < rows) {
+                const float *src = src0 + (int64_t)r * t.i[3] + c;
+                if (even) x[i] = __ldcg(reinterpret_cast<const float2 *>(src));
+                else { x[i].x = ldcg(src); if (c + 1 < cols) x[i].y = ldcg(src + 1); }
             }
-        } else {
-            for (int c = lane; c < cols; c += 32) {
-                __nv_bfloat16 h, l;
-                split_bf16(ldcg(src + c), h, l);
-                q[c] = h; q[c + dst.plane] = l;
-            }
+        }
+#pragma unroll
+        for (int i = 0; i < kR; i++) {
+            const int r = r0 + i * (kThreads / 32);
+            if (r >= rows) continue;
+            if (c + 1 >= cols) x[i].y = 0.f;
+            uint32_t hi, lo;
+            split_pack2(x[i].x, x[i].y, hi, lo);
+            __nv_bfloat16 *q = dst.hi + (int64_t)r * dst.ld + c;
+            *reinterpret_cast<uint32_t *>(q) = hi;
+            *reinterpret_cast<uint32_t *>(q + dst.plane) = lo;
         }
     }
 }
 
 // T_GATHER: pm0 = X PM [3B, ldx] ; p0=r ; p1=d ; i0=B i1=obs i2=act ; ring row = [s | s2 | a | r | d] (16 B aligned)
-//   rows [0,B) <- (s2, .)   rows [B,2B) <- (s, a)   rows [2B,3B) <- (s, .)
-// four warps per sampled row, four rows per tile: 128-bit streaming loads issued back to back, bf16 pair stores
+//   X rows [0,B) <- (s2, .)   rows [B,2B) <- (s, a)   rows [2B,3B) <- (s, .)
+// four rows per tile, four warps per sampled row: one warp per destination row (the fourth moves r and d).  A lane forms
+// pairs of neighbouring destination columns (one 4-byte store per bf16 plane); ring reads are coalesced streaming loads,
+// 8 in flight per lane.
 __device__ __forceinline__ void task_gather(const Task &t, int tile, const Program &P, int agent) {
     const int B = t.i[0], obs = t.i[1], act = t.i[2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = tile * 4 + (warp >> 2), part = warp & 3;
     if (b >= B) return;
-    const Pm X = resolve_pm(t.pm[0], P.bases, agent);
     const int slot = P.slots[(int64_t)agent * P.slots_stride + b];
-    const float4 *row = reinterpret_cast<const float4 *>(P.ring + agent * P.ring_agent_stride + (int64_t)slot * P.ring_row);
-    float *rr = resolve(t.p[0], P.bases, agent), *dd = resolve(t.p[1], P.bases, agent);
-    const int nvec = P.ring_row >> 2;
-    for (int v0 = 0; v0 < nvec; v0 += 128 * 4) {
-        float4 buf[4];
+    const float *row = P.ring + agent * P.ring_agent_stride + (int64_t)slot * P.ring_row;
+    if (part == 3) {
+        if (lane == 0) resolve(t.p[0], P.bases, agent)[b] = __ldcs(row + 2 * obs + act);
+        if (lane == 1) resolve(t.p[1], P.bases, agent)[b] = __ldcs(row + 2 * obs + act + 1);
+        return;
+    }
+    const Pm X = resolve_pm(t.pm[0], P.bases, agent);
+    const int xrow = part == 0 ? b : (part == 1 ? B + b : 2 * B + b);
+    const int ncols = part == 1 ? obs + act : obs;
+    auto src = [&](int c) -> float {       // destination column -> ring element
+        if (part == 0) return __ldcs(row + obs + c);
+        return __ldcs(row + (c < obs ? c : obs + c));      // c >= obs: action column (c - obs) sits at 2*obs + (c - obs)
+    };
+    __nv_bfloat16 *q = X.hi + (int64_t)xrow * X.ld;
+    constexpr int kU = 4;
+    for (int c0 = 2 * lane; c0 < ncols; c0 += 64 * kU) {
+        float x0[kU], x1[kU];
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int v = v0 + u * 128 + part * 32 + lane;
-            buf[u] = v < nvec ? __ldcs(row + v) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int u = 0; u < kU; u++) {
+            const int c = c0 + 64 * u;
+            x0[u] = c < ncols ? src(c) : 0.f;
+            x1[u] = c + 1 < ncols ? src(c + 1) : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int v = v0 + u * 128 + part * 32 + lane;
-            if (v >= nvec) continue;
-            const float e[4] = {buf[u].x, buf[u].y, buf[u].z, buf[u].w};
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const int j = 4 * v + q;
-                if (j < obs) { pm_store(X, B + b, j, e[q]); pm_store(X, 2 * B + b, j, e[q]); }
-                else if (j < 2 * obs) pm_store(X, b, j - obs, e[q]);
-                else if (j < 2 * obs + act) pm_store(X, B + b, obs + (j - 2 * obs), e[q]);
-                else if (j == 2 * obs + act) rr[b] = e[q];
-                else if (j == 2 * obs + act + 1) dd[b] = e[q];
-            }
+        for (int u = 0; u < kU; u++) {
+            const int c = c0 + 64 * u;
+            if (c >= ncols) continue;
+            uint32_t hi, lo;
+            split_pack2(x0[u], x1[u], hi, lo);
+            *reinterpret_cast<uint32_t *>(q + c) = hi;
+            *reinterpret_cast<uint32_t *>(q + c + X.plane) = lo;
         }
     }
 }
@@ -303,12 +314,13 @@ __device__ __forceinline__ void task_sample_bwd(const Task &t, int tile, const P
     pm_store(g, b, A + a, (g_u * s.std * eps - aB) * s.in_range);
 }
 
-// column sums over the batch for 32 columns per tile: thread (cg = tid & 31, rg = tid >> 5) adds rows rg, rg+G, ...
+// column sums over the batch for kColsumCols columns per tile: thread (cg = tid % C, rg = tid / C) adds rows rg, rg+G, ...
 // (loads unrolled 8 deep), the row groups are then combined in shared memory in a fixed order
+constexpr int kColsumCols = 64;
 template <class F>
-__device__ __forceinline__ float colsum32(int B, float *smem, F value_at) {
-    constexpr int G = kThreads / 32;       // row groups
-    const int cg = threadIdx.x & 31, rg = threadIdx.x >> 5;
+__device__ __forceinline__ float colsum(int B, float *smem, F value_at) {
+    constexpr int G = kThreads / kColsumCols;       // row groups
+    const int cg = threadIdx.x % kColsumCols, rg = threadIdx.x / kColsumCols;
     float acc = 0.f;
     int b = rg;
     for (; b + 7 * G < B; b += 8 * G) {
@@ -319,25 +331,25 @@ __device__ __forceinline__ float colsum32(int B, float *smem, F value_at) {
         for (int u = 0; u < 8; u++) acc += v[u];
     }
     for (; b < B; b += G) acc += value_at(b);
-    smem[rg * 32 + cg] = acc;
+    smem[rg * kColsumCols + cg] = acc;
     __syncthreads();
     float tot = 0.f;
-    if (rg == 0) for (int g = 0; g < G; g++) tot += smem[g * 32 + cg];
+    if (rg == 0) for (int g = 0; g < G; g++) tot += smem[g * kColsumCols + cg];
     __syncthreads();
     return tot;     // valid for rg == 0
 }
 
 // T_OUT_ADAM: Q output layer (Linear(H,1)).  pm0=h_L PM [B,H] p1=dq [B] ; p2..p6 = w,m,v,wt,gexp [H] ; p7..p11 = same for bias
-//   i0=B i1=H i2=step_slot i3=apply ; f0=lr f1=tau.   32 columns per tile; tile 0 also does the bias
+//   i0=B i1=H i2=step_slot i3=apply ; f0=lr f1=tau.   kColsumCols columns per tile; tile 0 also does the bias
 __device__ __forceinline__ void task_out_adam(const Task &t, int tile, const Program &P, int agent, const float *scalars, float *smem) {
     const int B = t.i[0], H = t.i[1];
-    const int n = tile * 32 + (threadIdx.x & 31);
+    const int n = tile * kColsumCols + (threadIdx.x % kColsumCols);
     const Pm h = resolve_pm(t.pm[0], P.bases, agent);
     const float *dq = resolve(t.p[1], P.bases, agent);
     float ss, bs;
-    adam_factors(__float_as_int(ldcg(scalars + t.i[2])), t.f[0], ss, bs);
-    const float g = colsum32(B, smem, [&](int b) { return n < H ? ldcg(dq + b) * pm_load(h, b, n) : 0.f; });
-    if (threadIdx.x < 32 && n < H) {
+    adam_factors_cached(scalars, t.i[2], ss, bs);
+    const float g = colsum(B, smem, [&](int b) { return n < H ? ldcg(dq + b) * pm_load(h, b, n) : 0.f; });
+    if (threadIdx.x < kColsumCols && n < H) {
         float *wt = resolve(t.p[5], P.bases, agent), *ge = resolve(t.p[6], P.bases, agent);
         adam_element(g, resolve(t.p[2], P.bases, agent) + n, resolve(t.p[3], P.bases, agent) + n, resolve(t.p[4], P.bases, agent) + n,
                      wt ? wt + n : nullptr, ge ? ge + n : nullptr, t.i[3], ss, bs, t.f[1]);
@@ -353,15 +365,15 @@ __device__ __forceinline__ void task_out_adam(const Task &t, int tile, const Pro
 }
 
 // T_BIAS_ADAM: db[n] = sum_b dh[b,n].  pm0 = dh PM [B,N] ; p0..p4 = b,m,v,bt,gexp ; i0=B i1=N i2=step_slot i3=apply ;
-//   f0=lr f1=tau.   32 columns per tile
+//   f0=lr f1=tau.   kColsumCols columns per tile
 __device__ __forceinline__ void task_bias_adam(const Task &t, int tile, const Program &P, int agent, const float *scalars, float *smem) {
     const int B = t.i[0], N = t.i[1];
-    const int n = tile * 32 + (threadIdx.x & 31);
+    const int n = tile * kColsumCols + (threadIdx.x % kColsumCols);
     const Pm dh = resolve_pm(t.pm[0], P.bases, agent);
-    const float g = colsum32(B, smem, [&](int b) { return n < N ? pm_load(dh, b, n) : 0.f; });
-    if (threadIdx.x < 32 && n < N) {
+    const float g = colsum(B, smem, [&](int b) { return n < N ? pm_load(dh, b, n) : 0.f; });
+    if (threadIdx.x < kColsumCols && n < N) {
         float ss, bs;
-        adam_factors(__float_as_int(ldcg(scalars + t.i[2])), t.f[0], ss, bs);
+        adam_factors_cached(scalars, t.i[2], ss, bs);
         float *bt = resolve(t.p[3], P.bases, agent), *ge = resolve(t.p[4], P.bases, agent);
         adam_element(g, resolve(t.p[0], P.bases, agent) + n, resolve(t.p[1], P.bases, agent) + n, resolve(t.p[2], P.bases, agent) + n,
                      bt ? bt + n : nullptr, ge ? ge + n : nullptr, t.i[3], ss, bs, t.f[1]);
@@ -407,16 +419,23 @@ __device__ __forceinline__ void task_finish(const Task &t, const Program &P, int
             const float g = -(s2 / Bf);                                      // d(-mean(log_alpha*(logp+H_t)))/dlog_alpha
             scalars[SC_LOSS_ALPHA] = la * g;
             float ss, bs;
-            adam_factors(__float_as_int(scalars[SC_STEP_ALPHA]), t.f[0], ss, bs);
+            adam_factors_cached(scalars, SC_STEP_ALPHA, ss, bs);
             adam_element(g, &scalars[SC_LOG_ALPHA], &scalars[SC_LOG_ALPHA_M], &scalars[SC_LOG_ALPHA_V], nullptr, resolve(t.p[2], P.bases, agent), t.i[7], ss, bs, 0.f);
             alpha_next = expf(scalars[SC_LOG_ALPHA]);                        // self.alpha = self.log_alpha.exp()
         }
         if (t.i[7]) scalars[SC_ALPHA0 + ((n_upd + 1) & 1)] = alpha_next;
     }
-    const int slots[4] = {SC_STEP_POLICY, SC_STEP_Q1, SC_STEP_Q2, SC_STEP_ALPHA};
-    for (int k = 0; k < 4; k++)
-        if (t.i[k]) scalars[slots[k]] = __int_as_float(__float_as_int(scalars[slots[k]]) + 1);
     if (t.i[4]) scalars[SC_N_UPDATES] = __int_as_float(__float_as_int(scalars[SC_N_UPDATES]) + 1);
+}
+
+// second half of T_FINISH, threads 0..3 in parallel: bump one optimizer's step counter and cache its next bias corrections
+__device__ __forceinline__ void task_finish_steps(const Task &t, float *scalars) {
+    const int k = threadIdx.x;
+    if (k >= 4 || !t.i[k]) return;
+    const int slot = SC_STEP_POLICY + k;      // SC_STEP_POLICY, SC_STEP_Q1, SC_STEP_Q2, SC_STEP_ALPHA are consecutive
+    const int step = __float_as_int(scalars[slot]) + 1;
+    scalars[slot] = __int_as_float(step);
+    adam_factors_store(scalars, slot, step, t.f[0]);
 }
 
 }  // namespace sacb
