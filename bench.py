@@ -229,7 +229,14 @@ def run_ours(args):
     peaks, peak_src = measured_peaks()
     achieved_tf = FLOP_PER_UPDATE / (upd_ms.value * 1e-3) / 1e12
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": None,
+    traffic = None      # DRAM bytes of one update program (26 stage kernels, warm caches) from the committed ncu capture
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_update_traffic.json")) as f:
+            traffic = float(json.load(f)["update_dram_bytes"])
+    except Exception:
+        pass
+    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
+                "traffic_source": "profiles/r01_update_stages_ncu.csv: dram__bytes_read.sum + dram__bytes_write.sum summed over the stage kernels of one update (algorithmic bytes if streamed from HBM: 63.7e6; the state stays L2 resident)",
                 "kernel": "sac_update_kernel (one fused update program: %d launches/step in '%s' mode)" % (1 if args.launch == "persistent" else n_st, args.launch),
                 "ms_per_launch_sum": upd_ms.value, "peak_source": peak_src + " bf16 dense, sustained (each product costs 3 bf16 MMAs: algorithmic FLOPs are counted once)",
                 "note": "single-agent B=256 is latency/occupancy bound (SURVEY 8d): ~20 dependent GEMM stages of <=0.3 GFLOP",

@@ -9,11 +9,11 @@ the package does not need a GPU, constructing a SAC / buffer does.  There is no 
 """
 import sys
 
-from . import _native, networks_model1, networks_model2, replay_buffer, sac_imp
+from . import _native, distributed, networks_model1, networks_model2, replay_buffer, sac_imp
 from .replay_buffer import PrioritizedReplayBuffer, ReplayBuffer
 from .sac_imp import SAC
 
-__all__ = ["SAC", "ReplayBuffer", "PrioritizedReplayBuffer", "install", "use_networks", "networks_model1", "networks_model2"]
+__all__ = ["SAC", "ReplayBuffer", "PrioritizedReplayBuffer", "install", "use_networks", "networks_model1", "networks_model2", "distributed"]
 
 
 def use_networks(variant):

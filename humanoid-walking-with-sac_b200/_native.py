@@ -93,7 +93,7 @@ SIGNATURES = {
     "sacb_select_action": (I, [H, I, c_f32p, I, c_f32p, c_f32p]),
     "sacb_q_forward": (I, [H, I, I, c_f32p, c_f32p, I64, c_f32p]),
     "sacb_policy_forward": (I, [H, I, c_f32p, I64, c_f32p, c_f32p]),
-    "sacb_dp_backward": (I, [H, I, I64, I64]),
+    "sacb_dp_backward": (I, [H, I, I64, c_i64p, c_f32p, c_f32p]),
     "sacb_dp_apply": (I, [H, I]),
     "sacb_dp_grad_buffer": (I, [H, I, ctypes.POINTER(ctypes.c_void_p), c_i64p]),
     "sacb_get_stats": (I, [H, ctypes.POINTER(Stats)]),

@@ -55,12 +55,28 @@ extern "C" int sacb_dp_grad_buffer(sacb_handle h, int phase, void **dev_ptr, int
     return SACB_OK;
 }
 
-extern "C" int sacb_dp_backward(sacb_handle h, int phase, int64_t B_local, int64_t B_global) {
+namespace sacb { int replay_stage_slots(sacb_handle h, const int64_t *idx, int64_t B); }
+
+extern "C" int sacb_dp_backward(sacb_handle h, int phase, int64_t B_local, const int64_t *idx, const float *eps_next, const float *eps_cur) {
     if (!h || phase < 0 || phase > 1 || h->cfg.n_agents != 1) return fail(SACB_ERR_ARG, "bad argument");
-    (void)B_global;   // every rank uses B_local rows; means of equal-sized means == global mean after the all-reduce average
-    ProgramKey key{(int)B_local, phase == 0 ? 1 : 0, 1, 1, 0, phase};
+    if (B_local < 1 || B_local > h->L.maxB) return fail(SACB_ERR_ARG, "batch size out of range");
+    if ((eps_next == nullptr) != (eps_cur == nullptr)) return fail(SACB_ERR_ARG, "pass both eps arrays or neither");
+    int rc;
+    // every rank averages over its own B_local rows; with equal B_local the all-reduced mean of the rank means is the global mean
+    if (phase == 0) {
+        if (idx && (rc = replay_stage_slots(h, idx, B_local))) return rc;
+        if (eps_next) {
+            const int64_t n = B_local * h->cfg.act_dim;
+            SACB_CUDA(cudaMemcpyAsync(h->ws + h->L.eps, eps_next, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+            SACB_CUDA(cudaMemcpyAsync(h->ws + h->L.eps + n, eps_cur, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
+            h->dp_device_eps = 0;
+        } else {
+            h->dp_device_eps = 1;
+        }
+    }
+    ProgramKey key{(int)B_local, phase == 0 ? 1 : 0, 1, h->dp_device_eps, 0, phase};
     ProgramInst *p;
-    int rc = get_program(h, key, &p);
+    rc = get_program(h, key, &p);
     if (rc) return rc;
     return launch_program(h, *p);
 }

@@ -1,0 +1,80 @@
+"""Multi-GPU use of the learner, limited to where the path shards (BASELINE.json configs[3], configs[4]).
+
+* single agent, B = 256: replicas only (one agent per rank, nothing to exchange);
+* population of independent agents: `partition_agents` assigns agents to ranks, no communication;
+* large-batch data parallel: `DataParallelSAC` averages the critic gradients, then the actor + temperature gradients,
+  across ranks (two dependent all-reduces per step: the actor phase needs the stepped critics, sac_imp.py:109-118).
+
+One process per GPU; `torch.distributed` is only plumbing (NCCL over NVLink on GPUs, gloo in the CPU tests).
+"""
+import ctypes
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _native as N
+
+
+def partition_agents(n_agents, world_size, rank):
+    """Agents owned by `rank`: contiguous, sizes differ by at most one, every agent owned exactly once."""
+    base, extra = divmod(int(n_agents), int(world_size))
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def allreduce_mean_(tensors, group=None):
+    """In-place mean over the ranks of `group` of every tensor in `tensors` (no-op without an initialised group)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return tensors
+    world = dist.get_world_size(group)
+    if world == 1:
+        return tensors
+    for t in tensors:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        t.div_(world)
+    return tensors
+
+
+class DataParallelSAC:
+    """update_parameters for one replicated agent whose minibatch is split over the ranks.
+
+    Every rank holds the same weights / optimizer state and its own replay shard; a step is
+        backward(critics) on B_local rows -> all-reduce mean of the q1|q2 gradient slab -> Adam + Polyak
+        backward(actor, temperature)      -> all-reduce mean of the policy slab and the log_alpha gradient -> Adam
+    so the result equals the single-GPU update on the concatenated batch (mean of equal-sized means) up to fp32
+    reassociation.  `agent` is a `sac_imp.SAC` on this rank's GPU.
+    """
+
+    def __init__(self, agent, group=None):
+        self.agent, self.group = agent, group
+        self._bufs = {}
+        for phase in (0, 1, 2):
+            ptr, n = ctypes.c_void_p(), ctypes.c_int64()
+            N.check(N.lib().sacb_dp_grad_buffer(agent._h, phase, ctypes.byref(ptr), ctypes.byref(n)))
+            self._bufs[phase] = torch.as_tensor(N.DevArray(ptr.value, (n.value,), agent), device=f"cuda:{agent._cfg.device}")
+
+    def gradient_slabs(self, phase):
+        """Device tensors (aliases of the arena) that are averaged after `phase`: 0 -> [q1|q2], 1 -> [policy, log_alpha block]."""
+        return [self._bufs[0]] if phase == 0 else [self._bufs[1], self._bufs[2]]
+
+    def update_parameters(self, batch_size_local, *, idx=None, eps=None):
+        a, lib = self.agent, N.lib()
+        a.replay_buffer._flush()
+        ix = a.replay_buffer._draw(batch_size_local) if idx is None else np.ascontiguousarray(idx, np.int64)
+        e_next = e_cur = None
+        if eps is not None:
+            e_next, e_cur = N.f32(eps[0]), N.f32(eps[1])
+        losses = np.zeros(3, np.float32)
+        for phase in (0, 1):
+            N.check(lib.sacb_dp_backward(a._h, phase, ix.size, N.ptr(ix, ctypes.c_int64) if phase == 0 else None, N.ptr(e_next), N.ptr(e_cur)))
+            a.synchronize()                                    # the library runs on its own stream; NCCL on torch's
+            allreduce_mean_(self.gradient_slabs(phase), self.group)
+            torch.cuda.synchronize(self._bufs[0].device)
+            N.check(lib.sacb_dp_apply(a._h, phase))
+        N.check(lib.sacb_get_losses(a._h, 0, N.ptr(losses)))
+        t = torch.from_numpy(losses.copy()).to(self._bufs[0].device)
+        allreduce_mean_([t], self.group)
+        q1, q2, pi = t.tolist()
+        a._alpha_is_float = False
+        return {"q1_loss": q1, "q2_loss": q2, "policy_loss": pi}

@@ -162,7 +162,9 @@ int sacb_policy_forward(sacb_handle h, int agent, const float *s, int64_t n, flo
 
 /* ---- data-parallel mode (BASELINE.json configs[3]): gradients are exported, all-reduced by the host over
  * NCCL (torch.distributed), then applied.  phase 0 = critics (sac_imp.py:101-113), 1 = actor+alpha (:116-135). */
-int sacb_dp_backward(sacb_handle h, int phase, int64_t B_local, int64_t B_global);
+/* phase 0 takes this rank's minibatch: idx = B_local logical replay indices (NULL: indices staged earlier), eps_next /
+ * eps_cur = [B_local, act] draws (NULL: Philox on device, give every rank its own sacb_config.seed); phase 1 reuses them. */
+int sacb_dp_backward(sacb_handle h, int phase, int64_t B_local, const int64_t *idx, const float *eps_next, const float *eps_cur);
 int sacb_dp_apply(sacb_handle h, int phase);
 int sacb_dp_grad_buffer(sacb_handle h, int phase, void **dev_ptr, int64_t *n_floats);
 
