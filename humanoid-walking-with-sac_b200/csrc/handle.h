@@ -104,6 +104,7 @@ struct sacb_handle_s {
     int64_t staged_steps = 0, staged_next = 0, staged_B = 0;
     std::map<sacb::ProgramKey, sacb::ProgramInst> programs;
     int64_t kernel_launches = 0;
+    int use_pdl = 1;                     // staged mode: programmatic dependent launch between the stage kernels (SACB_NO_PDL=1 disables)
     int dp_device_eps = 1;               // data-parallel mode: eps of the current step drawn on device (phase 1 follows phase 0)
     int coop_blocks_per_sm = 0;
     // ---- replay (replay.cu) ----

@@ -194,6 +194,7 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
 
     stamp(1);
     unsigned int bar_target = 0;
+    bool dep_synced = false;
     for (int s = stage_begin; s < stage_end; s++) {
         if (threadIdx.x < sizeof(Stage) / 4) {
             const int32_t *src = (stage_end - stage_begin == 1) ? reinterpret_cast<const int32_t *>(&single) : reinterpret_cast<const int32_t *>(&P.stages[s]);
@@ -221,6 +222,11 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
                 if (wi == (int)blockIdx.x) stamp(11);
             }
             const Task &t = s_task;
+            if (!dep_synced) {      // everything above only read launch parameters and the static task tables
+                asm volatile("griddepcontrol.wait;" ::: "memory");
+                asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+                dep_synced = true;
+            }
             float *scalars = resolve(P.scalars, P.bases, agent);
             switch (t.type) {
                 case T_GEMM:
@@ -245,6 +251,10 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
         }
     }
 
+    if (!dep_synced) {           // a CTA without a tile still has to release its dependents
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    }
     if (kTc && tc_setup) {
         tc::tc_fence_before();
         __syncthreads();
@@ -611,7 +621,16 @@ static int launch_range(sacb_handle h, ProgramInst &p, int s0, int s1, bool coop
         const int grid = std::min(max_tiles, h->sm_count * h->coop_blocks_per_sm);
         SACB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, h->stream));
     } else {
-        SACB_CUDA(cudaLaunchKernel(fn, dim3(max_tiles), dim3(kThreads), args, smem, h->stream));
+        // programmatic dependent launch: the next stage's CTAs may become resident (on SMs this stage leaves idle) and run
+        // their prologue -- barrier init, TMEM allocation, stage / task table fetch, TMA descriptor prefetch -- while this
+        // stage still computes; they block in griddepcontrol.wait before touching anything a previous stage wrote
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(max_tiles); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = h->use_pdl ? 1 : 0;
+        SACB_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
     }
     return SACB_OK;
 }

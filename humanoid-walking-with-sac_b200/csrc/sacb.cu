@@ -64,6 +64,7 @@ extern "C" int sacb_create(const sacb_config *cfg, sacb_handle *out) {
     sacb_handle h = new sacb_handle_s();
     h->cfg = *cfg;
     h->sm_count = prop.multiProcessorCount;
+    h->use_pdl = getenv("SACB_NO_PDL") ? 0 : 1;
     h->L.build(cfg->obs_dim, cfg->act_dim, cfg->hidden_dim, cfg->n_hidden, cfg->max_batch);
     const int n = cfg->n_agents;
     auto bail = [&](int rc) { sacb_destroy(h); return rc; };
