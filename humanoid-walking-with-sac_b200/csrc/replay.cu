@@ -19,6 +19,25 @@
 
 namespace sacb {
 
+// Programmatic dependent launch for the chain of small dependent kernels of one sample() call: every kernel first waits for
+// its predecessor's results, then lets its successor become resident, so launch latencies overlap instead of adding up.
+#define SACB_PDL_ENTER()                                                  \
+    do {                                                                  \
+        asm volatile("griddepcontrol.wait;" ::: "memory");                \
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   \
+    } while (0)
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 constexpr int kChunk = 1024;          // elements per scan chunk (one warp, 32 per lane)
 constexpr int kSumLeafMax = 128;      // numpy PW_BLOCKSIZE
 constexpr int kSumBlockMax = 4096;    // elements handled by one CTA of per_sum_blocks
@@ -110,6 +129,7 @@ __device__ float pw_block_sum(const float *a, int64_t start, int n, float *s_hea
 
 // grid = top heap size; CTA id+1 = heap id of the top tree (leaf threshold kSumBlockMax)
 __global__ void __launch_bounds__(256) per_sum_blocks(const float *p_alpha, int64_t n, float *top_vals) {
+    SACB_PDL_ENTER();
     __shared__ float s_heap[kSumHeap];
     __shared__ unsigned char s_state[kSumHeap];
     __shared__ float s_leafbuf[8 * kSumLeafMax];
@@ -121,6 +141,7 @@ __global__ void __launch_bounds__(256) per_sum_blocks(const float *p_alpha, int6
 }
 
 __global__ void __launch_bounds__(1024) per_sum_top(int64_t n, int top_depth, float *top_vals, float *total) {
+    SACB_PDL_ENTER();
     for (int depth = top_depth; depth >= 0; depth--) {
         for (unsigned id = (1u << depth) + threadIdx.x; id < (2u << depth); id += blockDim.x) {
             int64_t s, m; bool leaf = false;
@@ -168,6 +189,7 @@ __device__ __forceinline__ double warp_excl_scan(double v, int lane, double &war
 }
 
 __global__ void __launch_bounds__(256) per_chunk(const float *p_alpha, int64_t n, const float *total, double *chunk_sum, int *chunk_fine) {
+    SACB_PDL_ENTER();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t chunk = (int64_t)blockIdx.x * 8 + warp;
     if (chunk * kChunk >= n) return;
@@ -181,6 +203,7 @@ __global__ void __launch_bounds__(256) per_chunk(const float *p_alpha, int64_t n
 
 // single CTA: exclusive Kogge-Stone scan of the chunk sums (n_chunks <= 1024 per pass, looped with a running carry)
 __global__ void __launch_bounds__(1024) per_carry(const double *chunk_sum, const int *chunk_fine, int n_chunks, double *carry, int *counters) {
+    SACB_PDL_ENTER();
     __shared__ double s[1024];
     __shared__ int s_f[1024];
     __shared__ double s_run;
@@ -212,6 +235,7 @@ __global__ void __launch_bounds__(1024) per_carry(const double *chunk_sum, const
 // one warp per sample
 __global__ void __launch_bounds__(256) per_search(const float *p_alpha, int64_t n, const float *total, const double *carry, int n_chunks,
                                                   const double *u, int B, const int *counters, int64_t *idx_out, int *flagged, int *flag_count) {
+    SACB_PDL_ENTER();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = blockIdx.x * 8 + warp;
     if (j >= B) return;
@@ -264,6 +288,7 @@ __global__ void __launch_bounds__(256) per_search(const float *p_alpha, int64_t 
 // numpy's own algorithm, run only when a sample could not be certified: sequential float64 cumsum, /= last, searchsorted right
 __global__ void __launch_bounds__(32) per_exact(const float *p_alpha, int64_t n, const float *total, double *cdf, const double *u, int B,
                                                  const int *flagged, int64_t *idx_out, int *counters) {
+    SACB_PDL_ENTER();
     if (counters[1] == 0) return;
     const int lane = threadIdx.x;
     const float tot = *total;
@@ -289,7 +314,8 @@ __global__ void __launch_bounds__(32) per_exact(const float *p_alpha, int64_t n,
 
 // single CTA: IS weights (replay_buffer.py:67-68), ring slots for the gather
 __global__ void __launch_bounds__(1024) per_finish(const float *p_alpha, int64_t n, const float *total, const int64_t *idx, int B, float neg_beta,
-                                                    float *weights, int32_t *slots, float *isw_ws) {
+                                                    float *weights, int32_t *slots, float *isw_ws, int64_t *idx_copy) {
+    SACB_PDL_ENTER();
     __shared__ float s_max[32];
     float w = -INFINITY;
     const int j = threadIdx.x;
@@ -297,6 +323,7 @@ __global__ void __launch_bounds__(1024) per_finish(const float *p_alpha, int64_t
         const float prob = __fdiv_rn(p_alpha[idx[j]], *total);
         w = powf((float)n * prob, neg_beta);
         slots[j] = (int32_t)idx[j];
+        idx_copy[j] = idx[j];      // indices of the last sample (update_priorities without an index argument, TD write-back)
     }
     float m = w;
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -316,6 +343,7 @@ __global__ void __launch_bounds__(1024) per_finish(const float *p_alpha, int64_t
 }
 
 __global__ void per_uniform_draw(double *u, int B, uint64_t seed, uint64_t counter) {
+    SACB_PDL_ENTER();
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= B) return;
     uint64_t x = seed ^ (counter * 0x9E3779B97F4A7C15ull + (uint64_t)j * 0xBF58476D1CE4E5B9ull);   // splitmix64
@@ -327,6 +355,7 @@ __global__ void per_uniform_draw(double *u, int B, uint64_t seed, uint64_t count
 // priorities: update (last duplicate wins), push (max over the whole capacity array)
 // ---------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) per_update_kernel(float *prio, float *p_alpha, const int64_t *idx, const float *td, int B, float alpha, int is_final) {
+    SACB_PDL_ENTER();
     extern __shared__ int64_t s_idx[];
     for (int j = threadIdx.x; j < B; j += blockDim.x) s_idx[j] = idx[j];
     __syncthreads();
@@ -622,24 +651,27 @@ extern "C" int sacb_per_sample(sacb_handle h, int agent, const double *u, int64_
     const int64_t k = std::min<int64_t>(B, n);                       // n_samples = min(batch_size, len)  (replay_buffer.py:50)
     if (k > h->cfg.max_batch) return fail(SACB_ERR_ARG, "batch size exceeds max_batch");
     PerWs w = per_ws_of(h, 0);
+    cudaStream_t st = h->stream;
+    const bool pdl = h->use_pdl != 0;
     const int64_t frame = h->per_frame[0];
     const double beta = std::min(1.0, (double)h->cfg.per_beta_start + (double)frame * (1.0 - (double)h->cfg.per_beta_start) / (double)h->cfg.per_beta_frames);
     h->per_frame[0] = frame + 1;
     if (u) SACB_CUDA(cudaMemcpyAsync(w.u, u, sizeof(double) * k, cudaMemcpyHostToDevice, h->stream));
-    else per_uniform_draw<<<(int)((k + 255) / 256), 256, 0, h->stream>>>(w.u, (int)k, h->cfg.seed, (uint64_t)frame);
+    else SACB_CUDA(launch_pdl(per_uniform_draw, dim3((int)((k + 255) / 256)), dim3(256), 0, st, pdl, w.u, (int)k, h->cfg.seed, (uint64_t)frame));
     const int depth = top_depth_of(n);
     if (depth > 11) return fail(SACB_ERR_ARG, "capacity too large for the summation heap");
-    per_sum_blocks<<<(2 << depth) - 1, 256, 0, h->stream>>>(h->p_alpha, n, w.block_vals);
-    per_sum_top<<<1, 1024, 0, h->stream>>>(n, depth, w.block_vals, w.total);
+    const float *pa = h->p_alpha;
+    SACB_CUDA(launch_pdl(per_sum_blocks, dim3((2 << depth) - 1), dim3(256), 0, st, pdl, pa, n, w.block_vals));
+    SACB_CUDA(launch_pdl(per_sum_top, dim3(1), dim3(1024), 0, st, pdl, n, depth, w.block_vals, w.total));
     const int n_chunks = (int)((n + kChunk - 1) / kChunk);
-    per_chunk<<<(n_chunks + 7) / 8, 256, 0, h->stream>>>(h->p_alpha, n, w.total, w.chunk_sum, w.chunk_fine);
-    per_carry<<<1, 1024, 0, h->stream>>>(w.chunk_sum, w.chunk_fine, n_chunks, w.chunk_carry, w.counters);
-    per_search<<<(int)((k + 7) / 8), 256, 0, h->stream>>>(h->p_alpha, n, w.total, w.chunk_carry, n_chunks, w.u, (int)k, w.counters, w.idx, w.flagged, w.counters + 1);
-    per_exact<<<1, 32, 0, h->stream>>>(h->p_alpha, n, w.total, w.cdf_exact, w.u, (int)k, w.flagged, w.idx, w.counters);
-    per_finish<<<1, 1024, 0, h->stream>>>(h->p_alpha, n, w.total, w.idx, (int)k, -(float)beta, w.weights, h->slots, h->ws + h->L.isw);
+    SACB_CUDA(launch_pdl(per_chunk, dim3((n_chunks + 7) / 8), dim3(256), 0, st, pdl, pa, n, (const float *)w.total, w.chunk_sum, w.chunk_fine));
+    SACB_CUDA(launch_pdl(per_carry, dim3(1), dim3(1024), 0, st, pdl, (const double *)w.chunk_sum, (const int *)w.chunk_fine, n_chunks, w.chunk_carry, w.counters));
+    SACB_CUDA(launch_pdl(per_search, dim3((int)((k + 7) / 8)), dim3(256), 0, st, pdl, pa, n, (const float *)w.total, (const double *)w.chunk_carry, n_chunks,
+                         (const double *)w.u, (int)k, (const int *)w.counters, w.idx, w.flagged, w.counters + 1));
+    SACB_CUDA(launch_pdl(per_exact, dim3(1), dim3(32), 0, st, pdl, pa, n, (const float *)w.total, w.cdf_exact, (const double *)w.u, (int)k, (const int *)w.flagged, w.idx, w.counters));
+    SACB_CUDA(launch_pdl(per_finish, dim3(1), dim3(1024), 0, st, pdl, pa, n, (const float *)w.total, (const int64_t *)w.idx, (int)k, -(float)beta, w.weights, h->slots,
+                         h->ws + h->L.isw, h->last_idx_dev));
     h->kernel_launches += u ? 7 : 8;
-    SACB_CUDA(cudaGetLastError());
-    SACB_CUDA(cudaMemcpyAsync(h->last_idx_dev, w.idx, sizeof(int64_t) * k, cudaMemcpyDeviceToDevice, h->stream));
     if (idx_out) SACB_CUDA(cudaMemcpyAsync(idx_out, w.idx, sizeof(int64_t) * k, cudaMemcpyDeviceToHost, h->stream));
     if (weights_out) SACB_CUDA(cudaMemcpyAsync(weights_out, w.weights, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
     if (s || a || r || s2 || done) return gather_to_host(h, 0, nullptr, k, s, a, r, s2, done);
@@ -653,9 +685,9 @@ extern "C" int sacb_per_update_final(sacb_handle h, int agent, const int64_t *id
 extern "C" int sacb_per_update_from_td(sacb_handle h, int agent, int64_t B) {
     if (!h || agent != 0 || h->cfg.replay_kind != SACB_REPLAY_PER) return fail(SACB_ERR_ARG, "bad argument");
     if (B < 1 || B > h->cfg.max_batch) return fail(SACB_ERR_ARG, "batch size out of range");
-    per_update_kernel<<<1, 1024, sizeof(int64_t) * B, h->stream>>>(h->prio, h->p_alpha, h->last_idx_dev, h->ws + h->L.td, (int)B, h->cfg.per_alpha, 0);
+    SACB_CUDA(launch_pdl(per_update_kernel, dim3(1), dim3(1024), sizeof(int64_t) * B, h->stream, h->use_pdl != 0, h->prio, h->p_alpha,
+                         (const int64_t *)h->last_idx_dev, (const float *)(h->ws + h->L.td), (int)B, h->cfg.per_alpha, 0));
     h->kernel_launches++;
-    SACB_CUDA(cudaGetLastError());
     return SACB_OK;
 }
 static int per_update_impl(sacb_handle h, int agent, const int64_t *idx, const float *prio, int64_t B, int is_final) {
