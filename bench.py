@@ -101,6 +101,11 @@ def measured_peaks():
 def cpu_reference(steps, warmup, n_per=CAPACITY, seed=0):
     from oracle import per_oracle as PO
     from oracle import sac_oracle_np as O
+    try:    # give the CPU arm every host core (torchrun exports OMP_NUM_THREADS=1, which would handicap it)
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count())
+    except Exception:
+        pass
     st = O.make_state(OBS, ACT, HID, NH, seed=seed, head_scale=0.25)
     pri = synth_priorities(n_per, seed)
     pa = PO.pow_alpha(pri)

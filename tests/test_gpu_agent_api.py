@@ -154,3 +154,32 @@ def test_seeded_construction_matches_reference_initialisers(hw):
     w = net_params(agent, "policy")["fc2.weight"]
     np.testing.assert_allclose(w @ w.T, np.eye(64), atol=1e-4)                 # orthogonal init (networks_model2.py:80)
     hw.use_networks("model1")
+
+
+def test_trainer_loop_call_sequence(hw):
+    """The exact call sequence of SACTrainer.train (trainer.py:182-205) against the drop-in classes, with a stub
+    environment: select_action -> replay_buffer.push(s, a, r, s2, terminated or truncated) -> `len(buffer) > batch_size`
+    gate -> update_parameters(batch_size) -> dict of three python floats appended to the loss history."""
+    hw.use_networks("model1")
+    obs_dim, act_dim, batch_size = 24, 4, 32
+    torch.manual_seed(0); np.random.seed(0); random.seed(0)
+    agent = hw.SAC(obs_dim, act_dim, hidden_dim=64, device="cuda", capacity=500, max_batch=batch_size)
+    rng = np.random.RandomState(0)
+    state = rng.standard_normal(obs_dim)                      # float64 observation, like MuJoCo envs (walk_env.py:30)
+    loss_history, total_steps = [], 0
+    for total_steps in range(1, 121):
+        action = rng.uniform(-0.4, 0.4, act_dim) if total_steps < 20 else agent.select_action(state)       # trainer.py:184-187
+        assert action.shape == (act_dim,)
+        next_state, reward = rng.standard_normal(obs_dim), float(rng.standard_normal())
+        terminated, truncated = bool(rng.uniform() < 0.02), total_steps % 50 == 0
+        agent.replay_buffer.push(state, action, reward, next_state, terminated or truncated)                # trainer.py:191-194
+        state = next_state
+        if len(agent.replay_buffer) > batch_size:                                                           # trainer.py:202
+            info = agent.update_parameters(batch_size)                                                      # trainer.py:204
+            assert set(info) == {"q1_loss", "q2_loss", "policy_loss"} and all(isinstance(v, float) for v in info.values())
+            loss_history.append(info)
+    assert len(loss_history) == 120 - batch_size
+    assert np.isfinite([v for d in loss_history for v in d.values()]).all()
+    assert len(agent.replay_buffer) == 120 and len(agent.replay_buffer.buffer) == 120                      # sac_imp.py:199 reads .buffer
+    a_eval = agent.select_action(state, evaluate=True)                                                     # trainer.py:130
+    assert np.all(np.abs(a_eval) <= 0.4 + 1e-6)
