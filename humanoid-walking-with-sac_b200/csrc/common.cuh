@@ -140,7 +140,7 @@ constexpr int kMaxStageTasks = 28;
 struct Stage {
     int32_t task_begin, task_end;
     int32_t n_tiles;          // per agent
-    int32_t pad;
+    int32_t ksplit;           // staged tensor-core launches: CTAs per output tile (thread-block cluster along K), 1 / 2 / 4
     int32_t tile_begin[kMaxStageTasks];   // first tile of each task of the stage (copy of Task::tile_begin: one load finds the task)
 };
 

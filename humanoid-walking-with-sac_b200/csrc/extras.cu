@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_selftest_kernel(const Task *
     const Task &t = *tp;
     tc::TcState st;
     st.g = 0; st.accum_uses = 0; st.tmem_base = 0; st.full_bar = s_bars; st.empty_bar = s_bars + kTStages; st.accum_bar = s_bars + 2 * kTStages; st.trace = nullptr;
+    st.krank = 0; st.ksplit = 1; st.reduce_uses = 0; st.reduce_bar = nullptr;
     constexpr bool kTc = kMath != SACB_MATH_FP32;
     st.tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     if (kTc) {
@@ -152,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_selftest_kernel(const Task *
         st.tmem_base = s_tmem;
     }
     for (int tile = blockIdx.x; tile < t.n_tiles; tile += gridDim.x) {
-        if (kTc) gemm_tile_tc(t, tp, tile, bases, 0, nullptr, st, error_flag);
+        if (kTc) gemm_tile_tc(t, tp, tile, bases, 0, nullptr, st, error_flag, false);
         else gemm_tile_ffma(t, tile, bases, 0, nullptr, reinterpret_cast<float *>(smem_raw));
     }
     if (kTc) { tc::tc_fence_before(); __syncthreads(); if (threadIdx.x < 32) tc::tmem_dealloc(st.tmem_base, kTN); }

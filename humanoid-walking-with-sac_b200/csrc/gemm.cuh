@@ -301,7 +301,52 @@ struct TcState {
     uint64_t *accum_bar;   //             tcgen05.commit -> everyone: the accumulator tile is complete
     unsigned long long *trace;   // optional per-CTA timestamps (profiling aid)
     const CUtensorMap *tmA, *tmB; // descriptors of the current task in GLOBAL memory (the task's other fields are read from a smem copy)
+    // split-K over a thread-block cluster: the ksplit CTAs of a cluster own consecutive K ranges of ONE output tile.  Every CTA
+    // PUSHES the rows of its partial accumulator to the CTA that finishes them (st.shared::cluster into that CTA's slot
+    // [source rank]), signals the owner's `reduce_bar` (mbarrier, release/acquire at cluster scope) and CTA r then sums the
+    // slots for rows [r, r+1) * 128 / ksplit and runs the epilogue on them.  The slots occupy operand stage 3, the main loop
+    // of a clustered launch uses stages 0-2 only (its K range is short), so a fast peer never overwrites live operands.
+    uint32_t krank, ksplit;
+    uint64_t *reduce_bar;
+    uint32_t reduce_uses;
 };
+__device__ __forceinline__ int tc_stages(const TcState &st) { return st.ksplit > 1 ? kTStages - 1 : kTStages; }
+
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t cluster_nctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r)); return r; }
+// address of the same shared-memory offset inside CTA `rank` of this cluster (distributed shared memory)
+__device__ __forceinline__ uint32_t dsmem_addr(const void *local_ptr, uint32_t rank) {
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_ptr)), "r"(rank));
+    return remote;
+}
+__device__ __forceinline__ void st_dsmem_v4(uint32_t remote, float4 v) {
+    asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote_release(uint32_t remote_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote_bar) : "memory");
+}
+// bounded wait with acquire semantics at cluster scope (the arrivals come from peer CTAs)
+__device__ __forceinline__ bool mbar_wait_cluster(uint64_t *bar, uint32_t parity, int *error_flag) {
+    const uint32_t addr = smem_u32(bar);
+    long long t0 = 0;
+#pragma unroll 1
+    for (uint32_t it = 0;; ++it) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return true;
+        if (it == 0) t0 = clock64();
+        else if (clock64() - t0 > 2000000000ll) break;
+    }
+    if (error_flag) atomicExch(error_flag, 1);
+    return false;
+}
 
 // ---- main loop of one output tile: warp 0 = TMA producer, warp 1 = MMA issuer ----------------------------------
 // smem stage: A region 32 KB then B region 16 KB.
@@ -314,22 +359,24 @@ __device__ __forceinline__ void trace_stamp(unsigned long long *trace, int slot)
     trace[(size_t)blockIdx.x * kTraceSlots + slot] = ts;
 }
 
-__device__ __forceinline__ void tc_mainloop(const Task &t, int m0, int n0, int agent, TcState &st, int *error_flag, bool traced) {
+// returns the number of K-blocks this CTA accumulated (0: its partial tile is zero)
+__device__ __forceinline__ int tc_mainloop(const Task &t, int m0, int n0, int agent, TcState &st, int *error_flag, bool traced) {
     const int warp = threadIdx.x >> 5;
     if (traced && threadIdx.x == 0) trace_stamp(st.trace, 12);
-    const int nkb = cdiv(t.K, kTK);
+    const int nkb_all = cdiv(t.K, kTK), per = cdiv(nkb_all, (int)st.ksplit);
+    const int kb0 = (int)st.krank * per, nkb = max(0, min(nkb_all, kb0 + per) - kb0);      // this CTA's K range
     const uint32_t tiles = smem_u32(st.tiles);
     const int a_mn = t.A.mn_major, b_mn = t.B.mn_major;
-    const uint32_t g0 = st.g;
+    const uint32_t g0 = st.g, nst = (uint32_t)tc_stages(st);
     if (warp == 0) {
         if (elect_one()) {
             for (int kb = 0; kb < nkb; kb++) {
-                const uint32_t g = g0 + kb, s = g % kTStages;
-                mbar_wait(&st.empty_bar[s], ((g / kTStages) & 1) ^ 1, error_flag);
+                const uint32_t g = g0 + kb, s = g % nst;
+                mbar_wait(&st.empty_bar[s], ((g / nst) & 1) ^ 1, error_flag);
                 if (traced && kb < 16) trace_stamp(st.trace, 16 + kb);
                 mbar_arrive_expect_tx(&st.full_bar[s], kTcStageBytes);
                 const uint32_t sa = tiles + s * kTcStageBytes, sb = sa + kTcABytes;
-                const int k0 = kb * kTK, ma = t.A.r0 + m0, nb = t.B.r0 + n0;
+                const int k0 = (kb0 + kb) * kTK, ma = t.A.r0 + m0, nb = t.B.r0 + n0;
                 if (!a_mn) {
                     tma_load_4d(st.tmA, &st.full_bar[s], sa, k0, ma, 0, agent);
                 } else {
@@ -348,8 +395,8 @@ __device__ __forceinline__ void tc_mainloop(const Task &t, int m0, int n0, int a
         const uint32_t a_lbo = a_mn ? kTcABytes / 2 : 16, b_lbo = 16;
         const uint32_t a_kstep = a_mn ? 2048 : 32, b_kstep = b_mn ? 2048 : 32;
         for (int kb = 0; kb < nkb; kb++) {
-            const uint32_t g = g0 + kb, s = g % kTStages;
-            mbar_wait(&st.full_bar[s], (g / kTStages) & 1, error_flag);
+            const uint32_t g = g0 + kb, s = g % nst;
+            mbar_wait(&st.full_bar[s], (g / nst) & 1, error_flag);
             tc_fence_after();
             if (traced && kb < 16 && (threadIdx.x & 31) == 0) trace_stamp(st.trace, 32 + kb);
             if (elect_one()) {
@@ -370,6 +417,7 @@ __device__ __forceinline__ void tc_mainloop(const Task &t, int m0, int n0, int a
         }
     }
     st.g += nkb;
+    return nkb;
 }
 
 // ---- epilogue ----------------------------------------------------------------------------------------------------
@@ -413,8 +461,8 @@ __device__ __forceinline__ AdamOut adam_math(const EpiR &e, float g, float w, fl
 //   pass B: the columns no aligned group covers (a0 leading ones, <= 3 trailing ones), one element per thread
 //   both passes leave the new weights in the staging tile; pass C writes the bf16 pair shadows from there with the
 //   tile-aligned mapping (the shadow rows are padded to 16 B)
-__device__ __forceinline__ void adam_epilogue_tile(const EpiR &e, float *Cs, int m0, int n0) {
-    const int tid = threadIdx.x;
+__device__ __forceinline__ void adam_epilogue_tile(const EpiR &e, float *Cs, int m0, int n0, int row_lo, int row_hi) {
+    const int tid = threadIdx.x;     // only rows [row_lo, row_hi) of the tile belong to this CTA (split-K cluster)
     const int ncols = min(kTN, e.N - n0);      // valid columns of this tile (> 0)
     {   // ---- pass A
         const int j16 = tid & 15, r0 = tid >> 4;
@@ -426,7 +474,7 @@ __device__ __forceinline__ void adam_epilogue_tile(const EpiR &e, float *Cs, int
             mrow[i] = m0 + 32 * i + r0;
             const int a0 = (4 - (int)(((int64_t)mrow[i] * e.N + n0) & 3)) & 3;
             c[i] = a0 + 4 * j16;
-            vec[i] = mrow[i] < e.M && c[i] + 3 < ncols;
+            vec[i] = mrow[i] < e.M && c[i] + 3 < ncols && 32 * i + r0 >= row_lo && 32 * i + r0 < row_hi;
             w[i] = mm[i] = vv[i] = wt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (vec[i] && e.apply) {
                 const int64_t o = (int64_t)mrow[i] * e.N + n0 + c[i];
@@ -455,7 +503,7 @@ __device__ __forceinline__ void adam_epilogue_tile(const EpiR &e, float *Cs, int
     }
     if (e.N % 4 != 0 || ncols < kTN) {   // ---- pass B (warp-uniform condition): thread (row = tid / 4, q = tid % 4)
         const int row = tid >> 2, q = tid & 3, m = m0 + row;
-        if (m < e.M) {
+        if (m < e.M && row >= row_lo && row < row_hi) {
             const int a0 = (4 - (int)(((int64_t)m * e.N + n0) & 3)) & 3;
             const int nv = ncols > a0 ? (ncols - a0) >> 2 : 0, tail0 = a0 + 4 * nv;
             int col[2];
@@ -495,7 +543,7 @@ __device__ __forceinline__ void adam_epilogue_tile(const EpiR &e, float *Cs, int
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int m = m0 + 32 * i + r0;
-            if (m >= e.M) continue;
+            if (m >= e.M || 32 * i + r0 < row_lo || 32 * i + r0 >= row_hi) continue;
             const float4 v4 = *reinterpret_cast<const float4 *>(Cs + (32 * i + r0) * kCsLd + c4);
             const float w1[4] = {v4.x, v4.y, v4.z, v4.w};
             const int n = n0 + c4;
@@ -523,11 +571,13 @@ __device__ __forceinline__ void epilogue_rows4(const EpiR &e, const int (&m)[R],
     for (int i = 0; i < R; i++) { acc[i][0] = acc4[i].x; acc[i][1] = acc4[i].y; acc[i][2] = acc4[i].z; acc[i][3] = acc4[i].w; }
     float aux[R][4];
 #pragma unroll
-    for (int i = 0; i < R; i++) {
+    for (int i = 0; i < R; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) aux[i][j] = 0.f;
-        if (m[i] >= e.M) continue;
-        if (EPI == EPI_MASK) {       // sign of the stored activation (hi plane)
+    if (EPI == EPI_MASK) {
+#pragma unroll
+        for (int i = 0; i < R; i++) {       // sign of the stored activation (hi plane)
+            if (m[i] >= e.M) continue;
             const __nv_bfloat16 *q = e.mask.hi + (int64_t)m[i] * e.mask.ld + n;
             if (full) {
                 const uint2 a = __ldcg(reinterpret_cast<const uint2 *>(q));
@@ -537,17 +587,15 @@ __device__ __forceinline__ void epilogue_rows4(const EpiR &e, const int (&m)[R],
 #pragma unroll
                 for (int j = 0; j < 4; j++) aux[i][j] = (n + j < e.N) ? __bfloat162float(q[j]) : 0.f;
             }
-        } else if (e.bias && i == 0) {       // the bias depends on the column only (arena vectors are 16 B aligned, n % 4 == 0)
-            if (full) {
-                const float4 b4 = __ldcg(reinterpret_cast<const float4 *>(e.bias + n));
-                aux[0][0] = b4.x; aux[0][1] = b4.y; aux[0][2] = b4.z; aux[0][3] = b4.w;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; j++) aux[0][j] = (n + j < e.N) ? ldcg(e.bias + n + j) : 0.f;
-            }
         }
-    }
-    if (EPI != EPI_MASK) {
+    } else if (e.bias) {                    // the bias depends on the column only (arena vectors are 16 B aligned, n % 4 == 0)
+        if (full) {
+            const float4 b4 = __ldcg(reinterpret_cast<const float4 *>(e.bias + n));
+            aux[0][0] = b4.x; aux[0][1] = b4.y; aux[0][2] = b4.z; aux[0][3] = b4.w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) aux[0][j] = (n + j < e.N) ? ldcg(e.bias + n + j) : 0.f;
+        }
 #pragma unroll
         for (int i = 1; i < R; i++)
 #pragma unroll
@@ -579,32 +627,74 @@ __device__ __forceinline__ void epilogue_rows4(const EpiR &e, const int (&m)[R],
 }
 
 template <int EPI>
-__device__ __forceinline__ void tc_epilogue(const EpiR &epi, int m0, int n0, TcState &st, int *error_flag, bool traced) {
+__device__ __forceinline__ void tc_epilogue(const EpiR &epi, int m0, int n0, TcState &st, int nkb_mine, int *error_flag, bool traced) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    mbar_wait(st.accum_bar, st.accum_uses & 1, error_flag);
-    st.accum_uses++;
-    if (traced && tid == 64) trace_stamp(st.trace, 6);
-    tc_fence_after();
-    float *Cs = reinterpret_cast<float *>(st.tiles);      // staging tile [kTM][kCsLd] over operand stage 0 (all MMAs have retired)
+    const int ks = (int)st.ksplit, rows_per = kTM / ks;
+    // staging: ks == 1 -> one tile [kTM][kCsLd] over operand stage 0 (all MMAs have retired);
+    //          ks  > 1 -> ks slots [rows_per][kCsLd] over operand stage 3 (never used by a clustered main loop), slot = source rank
+    float *Cs = reinterpret_cast<float *>(st.tiles + (ks > 1 ? (kTStages - 1) * kTcStageBytes : 0));
     {   // phase 1: warp w owns TMEM lanes 32*(w%4).., column group w/4
         const int row = (warp & 3) * 32 + lane, colh = (warp >> 2) * 16;
         float v[16];
-        tmem_ld16(st.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)colh, v);
-        float4 *dst = reinterpret_cast<float4 *>(Cs + row * kCsLd + colh);
+        if (nkb_mine > 0) {
+            mbar_wait(st.accum_bar, st.accum_uses & 1, error_flag);
+            st.accum_uses++;
+            if (traced && tid == 64) trace_stamp(st.trace, 6);
+            tc_fence_after();
+            tmem_ld16(st.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)colh, v);
+        } else {      // a cluster rank beyond the last K-block contributes a zero partial tile
 #pragma unroll
-        for (int j = 0; j < 4; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            for (int j = 0; j < 16; j++) v[j] = 0.f;
+        }
+        if (ks == 1) {
+            float4 *dst = reinterpret_cast<float4 *>(Cs + row * kCsLd + colh);
+#pragma unroll
+            for (int j = 0; j < 4; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {      // push the row to the CTA that finishes it (warp-uniform owner), slot = my rank
+            const uint32_t owner = (uint32_t)(row / rows_per);
+            const uint32_t dst = dsmem_addr(Cs + ((int)st.krank * rows_per + row % rows_per) * kCsLd + colh, owner);
+#pragma unroll
+            for (int j = 0; j < 4; j++) st_dsmem_v4(dst + 16 * j, make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+        }
     }
     tc_fence_before();
-    __syncthreads();     // staging tile complete; all TMEM reads retired (the next tile's first MMA may overwrite the accumulator)
+    __syncthreads();     // staging complete; all TMEM reads retired (the next tile's first MMA may overwrite the accumulator)
     if (traced && tid == 64) trace_stamp(st.trace, 7);
+    int row_lo = 0, row_hi = kTM;
+    if (ks > 1) {
+        if (tid < ks && tid != (int)st.krank) {      // one release-arrive per peer: my rows have landed in its slots
+            asm volatile("fence.acq_rel.cluster;" ::: "memory");
+            mbar_arrive_remote_release(dsmem_addr(st.reduce_bar, (uint32_t)tid));
+        }
+        mbar_wait_cluster(st.reduce_bar, st.reduce_uses & 1, error_flag);      // ks - 1 peers have pushed their rows to me
+        st.reduce_uses++;
+        if (traced && tid == 64) trace_stamp(st.trace, 48);
+        row_lo = (int)st.krank * rows_per; row_hi = row_lo + rows_per;
+        const int c4 = (tid & 15) * 4;
+        for (int l = tid >> 4; l < rows_per; l += 32) {      // sum the slots in rank order into slot 0 (deterministic)
+            float4 sum = *reinterpret_cast<const float4 *>(Cs + l * kCsLd + c4);
+            for (int r = 1; r < ks; r++) {
+                const float4 p = *reinterpret_cast<const float4 *>(Cs + (r * rows_per + l) * kCsLd + c4);
+                sum.x += p.x; sum.y += p.y; sum.z += p.z; sum.w += p.w;
+            }
+            *reinterpret_cast<float4 *>(Cs + l * kCsLd + c4) = sum;
+        }
+        __syncthreads();
+        if (traced && tid == 64) trace_stamp(st.trace, 49);
+        Cs -= row_lo * kCsLd;      // from here on Cs[row] addresses tile row `row` for row_lo <= row < row_hi
+    }
     if (EPI == EPI_ADAM) {
-        adam_epilogue_tile(epi, Cs, m0, n0);
+        adam_epilogue_tile(epi, Cs, m0, n0, row_lo, row_hi);
     } else {   // phase 2: all four rows of a thread at once, so every global load is in flight before the first store
         const int c4 = (tid & 15) * 4, r0 = tid >> 4;
-        const int m[4] = {m0 + r0, m0 + 32 + r0, m0 + 64 + r0, m0 + 96 + r0};
+        int m[4];
         float4 acc[4];
 #pragma unroll
-        for (int i = 0; i < 4; i++) acc[i] = *reinterpret_cast<const float4 *>(Cs + (32 * i + r0) * kCsLd + c4);
+        for (int i = 0; i < 4; i++) {
+            const bool mine = 32 * i + r0 >= row_lo && 32 * i + r0 < row_hi;
+            m[i] = mine ? m0 + 32 * i + r0 : 0x7fffffff;      // rows of another cluster rank are skipped like rows beyond M
+            acc[i] = mine ? *reinterpret_cast<const float4 *>(Cs + (32 * i + r0) * kCsLd + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         if (traced && tid == 64 && acc[0].x != 12345.678f) trace_stamp(st.trace, 13);
         epilogue_rows4<EPI, 4>(epi, m, n0 + c4, acc, (traced && tid == 64) ? st.trace : nullptr);
     }
@@ -617,21 +707,22 @@ __device__ __forceinline__ void tc_epilogue(const EpiR &epi, int m0, int n0, TcS
 
 // t = shared-memory copy of the task (fields), tg = the task in global memory (TMA descriptors)
 __device__ __forceinline__ void gemm_tile_tc(const Task &t, const Task *tg, int tile, const AgentBases &bases, int agent,
-                                             const float *scalars, tc::TcState &st, int *error_flag) {
+                                             const float *scalars, tc::TcState &st, int *error_flag, bool first_tile) {
     using namespace tc;
     st.tmA = &tg->tmA; st.tmB = &tg->tmB;
     const int tm = tile / t.tiles_n, tn = tile % t.tiles_n;
     const int m0 = tm * kTM, n0 = tn * kTN;
-    const bool traced = st.trace && tile == (int)blockIdx.x - t.tile_begin;      // the CTA's first tile of the stage
-    tc_mainloop(t, m0, n0, agent, st, error_flag, traced);
+    const bool traced = st.trace && first_tile;      // the CTA's first tile of the stage
+    if (st.ksplit > 1 && !first_tile) { cluster_arrive(); cluster_wait(); }      // peers are done with the previous tile's slots
+    const int nkb_mine = tc_mainloop(t, m0, n0, agent, st, error_flag, traced);
     auto stamp = [&](int slot) { if (traced && threadIdx.x == 0) trace_stamp(st.trace, slot); };
     stamp(2);
     const EpiR epi = resolve_epilogue(t, bases, agent, scalars);
     switch (t.epi) {
-        case EPI_F32: tc_epilogue<EPI_F32>(epi, m0, n0, st, error_flag, traced); break;
-        case EPI_BIAS_RELU: tc_epilogue<EPI_BIAS_RELU>(epi, m0, n0, st, error_flag, traced); break;
-        case EPI_MASK: tc_epilogue<EPI_MASK>(epi, m0, n0, st, error_flag, traced); break;
-        default: tc_epilogue<EPI_ADAM>(epi, m0, n0, st, error_flag, traced); break;
+        case EPI_F32: tc_epilogue<EPI_F32>(epi, m0, n0, st, nkb_mine, error_flag, traced); break;
+        case EPI_BIAS_RELU: tc_epilogue<EPI_BIAS_RELU>(epi, m0, n0, st, nkb_mine, error_flag, traced); break;
+        case EPI_MASK: tc_epilogue<EPI_MASK>(epi, m0, n0, st, nkb_mine, error_flag, traced); break;
+        default: tc_epilogue<EPI_ADAM>(epi, m0, n0, st, nkb_mine, error_flag, traced); break;
     }
     stamp(3);
 }

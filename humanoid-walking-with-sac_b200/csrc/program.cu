@@ -161,7 +161,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Stage single, const int stage_begin, const int stage_end, const int tc_setup, const uint64_t seed) {
     // `single` = the stage table entry when the launch covers exactly one stage (staged mode): no global load before the first task
     extern __shared__ __align__(16) uint8_t smem_raw[];
-    __shared__ uint64_t s_bars[2 * kTStages + 1];
+    __shared__ uint64_t s_bars[2 * kTStages + 2];
     __shared__ uint32_t s_tmem;
     __shared__ float s_red[kThreads];
     __shared__ Stage s_stage;
@@ -177,12 +177,15 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
     stamp(0);
     tc::TcState st;
     st.g = 0; st.accum_uses = 0; st.tmem_base = 0;
+    st.krank = tc::cluster_ctarank(); st.ksplit = tc::cluster_nctarank(); st.reduce_uses = 0;
+    st.reduce_bar = s_bars + 2 * kTStages + 1;
     st.full_bar = s_bars; st.empty_bar = s_bars + kTStages; st.accum_bar = s_bars + 2 * kTStages; st.trace = P.trace;
     constexpr bool kTc = kMath != SACB_MATH_FP32;
     st.tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     if (kTc && tc_setup) {
         if (threadIdx.x == 0) {
             for (int i = 0; i <= 2 * kTStages; i++) tc::mbar_init(&s_bars[i], 1);
+            tc::mbar_init(st.reduce_bar, st.ksplit > 1 ? st.ksplit - 1 : 1);
             tc::fence_barrier_init();
         }
         if (threadIdx.x < 32) tc::tmem_alloc(&s_tmem, kTN);
@@ -190,6 +193,7 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
         __syncthreads();
         tc::tc_fence_after();
         st.tmem_base = s_tmem;
+        if (st.ksplit > 1) { tc::cluster_arrive(); tc::cluster_wait(); }      // every peer's reduce barrier is initialised
     }
 
     stamp(1);
@@ -204,7 +208,9 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
         stamp(9);
         const int n_stage_tiles = s_stage.n_tiles, n_stage_tasks = s_stage.task_end - s_stage.task_begin;
         const int total = n_stage_tiles * P.n_agents;
-        for (int wi = blockIdx.x; wi < total; wi += gridDim.x) {
+        // a cluster of ksplit CTAs shares one work item (split-K GEMM tile); without a cluster launch ksplit == 1
+        const int cl = blockIdx.x / st.ksplit, n_cl = gridDim.x / st.ksplit;
+        for (int wi = cl; wi < total; wi += n_cl) {
             const int agent = wi / n_stage_tiles, tile_in_stage = wi % n_stage_tiles;
             int k = 0;
             while (k + 1 < n_stage_tasks && tile_in_stage >= s_stage.tile_begin[k + 1]) k++;
@@ -215,11 +221,11 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
                 static_assert(kWords <= kThreads, "task copy");
                 if (kTc && threadIdx.x == kThreads - 1) { tc::tma_prefetch_desc(&tg->tmA); tc::tma_prefetch_desc(&tg->tmB); }
                 __syncthreads();     // the previous tile's readers of s_task are done
-                if (wi == (int)blockIdx.x) stamp(10);
+                if (wi == cl) stamp(10);
                 if ((int)threadIdx.x < kWords)
                     reinterpret_cast<int32_t *>(&s_task)[kSkip + threadIdx.x] = __ldcg(reinterpret_cast<const int32_t *>(tg) + kSkip + threadIdx.x);
                 __syncthreads();
-                if (wi == (int)blockIdx.x) stamp(11);
+                if (wi == cl) stamp(11);
             }
             const Task &t = s_task;
             if (!dep_synced) {      // everything above only read launch parameters and the static task tables
@@ -228,9 +234,10 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
                 dep_synced = true;
             }
             float *scalars = resolve(P.scalars, P.bases, agent);
+            if (t.type != T_GEMM && st.krank != 0) continue;      // element-wise tasks of a clustered stage run on rank 0 only
             switch (t.type) {
                 case T_GEMM:
-                    if (kTc) gemm_tile_tc(t, tg, tile, P.bases, agent, scalars, st, P.error_flag);
+                    if (kTc) gemm_tile_tc(t, tg, tile, P.bases, agent, scalars, st, P.error_flag, wi == cl);
                     else gemm_tile_ffma(t, tile, P.bases, agent, scalars, reinterpret_cast<float *>(smem_raw));
                     break;
                 case T_SHADOW: task_shadow(t, tile, P, agent); break;
@@ -243,7 +250,7 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
                 case T_BIAS_ADAM: task_bias_adam(t, tile, P, agent, scalars, s_red); break;
                 case T_FINISH: task_finish(t, P, agent, scalars, s_red); __syncthreads(); task_finish_steps(t, scalars); break;
             }
-            if (wi == (int)blockIdx.x) stamp(4);
+            if (wi == cl) stamp(4);
         }
         if (s + 1 < stage_end) {
             bar_target += gridDim.x;
@@ -607,6 +614,37 @@ int check_error_flag(sacb_handle h) {
     return SACB_OK;
 }
 
+// one stage = one launch (staged mode): grid = tiles x ksplit, thread-block cluster of ksplit CTAs along x, optional PDL
+static int launch_stage(sacb_handle h, ProgramInst &p, int s, bool pdl) {
+    const bool tc = math_is_tc(h->cfg.math_mode);
+    const size_t smem = math_smem(h->cfg.math_mode);
+    uint64_t seed = h->cfg.seed;
+    int s0 = s, s1 = s + 1, tc_setup = tc ? p.stage_has_gemm[s] : 0;
+    Stage single = p.stages[s];
+    const int ks = std::max(1, single.ksplit);
+    void *args[] = {(void *)&p.prog, (void *)&single, (void *)&s0, (void *)&s1, (void *)&tc_setup, (void *)&seed};
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(std::max(1, single.n_tiles * h->cfg.n_agents) * ks); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (pdl) {
+        // programmatic dependent launch: the next stage's CTAs may become resident (on SMs this stage leaves idle) and run
+        // their prologue -- barrier init, TMEM allocation, stage / task table fetch, TMA descriptor prefetch -- while this
+        // stage still computes; they block in griddepcontrol.wait before touching anything a previous stage wrote
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        na++;
+    }
+    if (ks > 1) {
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = ks; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+        na++;
+    }
+    cfg.attrs = attr; cfg.numAttrs = na;
+    SACB_CUDA(cudaLaunchKernelExC(&cfg, update_kernel_for(h->cfg.math_mode), args));
+    return SACB_OK;
+}
+
 static int launch_range(sacb_handle h, ProgramInst &p, int s0, int s1, bool cooperative) {
     const bool tf32 = math_is_tc(h->cfg.math_mode);
     int needs_tc = 0, max_tiles = 1;
@@ -621,16 +659,7 @@ static int launch_range(sacb_handle h, ProgramInst &p, int s0, int s1, bool coop
         const int grid = std::min(max_tiles, h->sm_count * h->coop_blocks_per_sm);
         SACB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, h->stream));
     } else {
-        // programmatic dependent launch: the next stage's CTAs may become resident (on SMs this stage leaves idle) and run
-        // their prologue -- barrier init, TMEM allocation, stage / task table fetch, TMA descriptor prefetch -- while this
-        // stage still computes; they block in griddepcontrol.wait before touching anything a previous stage wrote
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(max_tiles); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = h->use_pdl ? 1 : 0;
-        SACB_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+        return launch_stage(h, p, s0, h->use_pdl != 0);
     }
     return SACB_OK;
 }
@@ -654,6 +683,21 @@ int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out) {
     Builder b(h, key);
     b.build();
     if (b.rc != SACB_OK) return b.rc;
+    // split-K (opt-in, SACB_SPLITK=1): a latency-bound stage with few tiles spreads every tile over a 2- or 4-CTA cluster so
+    // that more SMs pull operands (per-SM L2->SMEM ingest bounds the main loop); staged tensor-core launches only.
+    // Measured on B200 (profiles/r01_summary.md): the accumulator is ready 1.6 us (x2) / 2.8 us (x4) earlier, but pushing the
+    // partial tiles through DSMEM and the cluster-scope release/acquire cost 1.5-2.3 us, so it is a wash and stays off.
+    for (size_t s = 0; s < b.stages.size(); s++) {
+        Stage &sg = b.stages[s];
+        sg.ksplit = 1;
+        if (!math_is_tc(h->cfg.math_mode) || h->cfg.launch_mode != SACB_LAUNCH_STAGED || !b.has_gemm[s] || !getenv("SACB_SPLITK")) continue;
+        int max_kb = 1;
+        for (int k = sg.task_begin; k < sg.task_end; k++)
+            if (b.tasks[k].type == T_GEMM) max_kb = std::max(max_kb, cdiv(b.tasks[k].K, kTK));
+        const int ctas = sg.n_tiles * h->cfg.n_agents;
+        for (int ks = 4; ks >= 2; ks /= 2)
+            if (ctas * ks <= h->sm_count && max_kb >= ks) { sg.ksplit = ks; break; }
+    }
     ProgramInst &p = h->programs[key];
     p.tasks = b.tasks; p.stages = b.stages; p.stage_has_gemm = b.has_gemm;
     for (auto &s : p.stages) { p.n_tiles_total += s.n_tiles; p.max_stage_tiles = std::max(p.max_stage_tiles, s.n_tiles); }
@@ -726,17 +770,12 @@ extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap
         cudaEventRecord(ev[0], h->stream);
         for (int s = 0; s < (int)p->stages.size(); s++) {
             // force the staged form regardless of launch_mode: this is a per-stage profile
-            const bool tf32 = math_is_tc(h->cfg.math_mode);
-            int s0 = s, s1 = s + 1, tc_setup = tf32 ? p->stage_has_gemm[s] : 0;
-            uint64_t seed = h->cfg.seed;
-            Stage single = p->stages[s];
-            void *args[] = {(void *)&p->prog, (void *)&single, (void *)&s0, (void *)&s1, (void *)&tc_setup, (void *)&seed};
-            SACB_CUDA(cudaLaunchKernel(update_kernel_for(h->cfg.math_mode), dim3(std::max(1, p->stages[s].n_tiles * h->cfg.n_agents)), dim3(kThreads), args,
-                                       math_smem(h->cfg.math_mode), h->stream));
+            { int rc2 = launch_stage(h, *p, s, false); if (rc2) return rc2; }
             cudaEventRecord(ev[s + 1], h->stream);
             if (trace && r == reps + 2) {
                 SACB_CUDA(cudaStreamSynchronize(h->stream));
-                const int grid = std::max(1, p->stages[s].n_tiles * h->cfg.n_agents);
+                const int ks = std::max(1, p->stages[s].ksplit);
+                const int grid = std::max(1, p->stages[s].n_tiles * h->cfg.n_agents) * ks;
                 SACB_CUDA(cudaMemcpy(h_trace.data(), d_trace, sizeof(unsigned long long) * kTraceSlots * std::min(grid, 4096), cudaMemcpyDeviceToHost));
                 double a[8] = {0}, mx_tile = 0, mx_main = 0; unsigned long long t0 = ~0ull, t0max = 0, t5 = 0;
                 const int g = std::min(grid, 4096);
@@ -747,8 +786,8 @@ extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap
                     mx_tile = std::max(mx_tile, (double)(q[4] - q[1]));
                     if (p->stage_has_gemm[s]) { a[2] += (double)(q[2] - q[1]); a[3] += (double)(q[3] - q[2]); mx_main = std::max(mx_main, (double)(q[2] - q[1])); }
                 }
-                fprintf(stderr, "[trace] stage %2d grid %4d gemm %d span %6.2f us start-skew %5.2f | per-CTA avg: setup %.2f mainloop %.2f (max %.2f) epilogue %.2f tile %.2f (max %.2f) teardown %.2f\n",
-                        s, grid, p->stage_has_gemm[s], (t5 - t0) * 1e-3, (t0max - t0) * 1e-3, a[1] / g * 1e-3, a[2] / g * 1e-3, mx_main * 1e-3, a[3] / g * 1e-3,
+                fprintf(stderr, "[trace] stage %2d ksplit %d grid %4d gemm %d span %6.2f us start-skew %5.2f | per-CTA avg: setup %.2f mainloop %.2f (max %.2f) epilogue %.2f tile %.2f (max %.2f) teardown %.2f\n",
+                        s, ks, grid, p->stage_has_gemm[s], (t5 - t0) * 1e-3, (t0max - t0) * 1e-3, a[1] / g * 1e-3, a[2] / g * 1e-3, mx_main * 1e-3, a[3] / g * 1e-3,
                         a[4] / g * 1e-3, mx_tile * 1e-3, a[5] / g * 1e-3);
                 {   // slowest tile of every task of the stage (which task sets the span)
                     const Stage &sg = p->stages[s];
@@ -756,18 +795,22 @@ extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap
                     for (int k = 0; k < sg.task_end - sg.task_begin; k++) {
                         const Task &tk = p->tasks[sg.task_begin + k];
                         double mx = 0;
-                        for (int b = tk.tile_begin; b < tk.tile_begin + tk.n_tiles && b < g; b++) mx = std::max(mx, (double)(h_trace[b * kTraceSlots + 4] - h_trace[b * kTraceSlots + 1]));
+                        for (int b = tk.tile_begin * ks; b < (tk.tile_begin + tk.n_tiles) * ks && b < g; b++)
+                            if (h_trace[b * kTraceSlots + 4] > h_trace[b * kTraceSlots + 1]) mx = std::max(mx, (double)(h_trace[b * kTraceSlots + 4] - h_trace[b * kTraceSlots + 1]));
                         fprintf(stderr, " [type %d epi %d %dx%dx%d n=%d] %.1f", tk.type, tk.epi, tk.M, tk.N, tk.K, tk.n_tiles, mx * 1e-3);
                     }
                     fprintf(stderr, "\n");
                 }
                 if (p->stage_has_gemm[s]) {      // k-block timeline of CTA 0: TMA issue / arrival times relative to the end of setup
-                    const unsigned long long *q = &h_trace[0];
-                    fprintf(stderr, "[trace]   cta0 issue:");
+                  for (int cta = 0; cta < std::min(ks, 2); cta++) {
+                    const unsigned long long *q = &h_trace[cta * kTraceSlots];
+                    fprintf(stderr, "[trace]   cta%d issue:", cta);
                     for (int kb = 0; kb < 16 && q[16 + kb] >= q[1]; kb++) fprintf(stderr, " %.2f", (q[16 + kb] - q[1]) * 1e-3);
                     fprintf(stderr, " | arrive:");
                     for (int kb = 0; kb < 16 && q[32 + kb] >= q[1]; kb++) fprintf(stderr, " %.2f", (q[32 + kb] - q[1]) * 1e-3);
-                    fprintf(stderr, " | accum %.2f staged %.2f stored %.2f epi-end %.2f\n", (q[6] - q[1]) * 1e-3, (q[7] - q[1]) * 1e-3, (q[8] - q[1]) * 1e-3, (q[3] - q[1]) * 1e-3);
+                    fprintf(stderr, " | accum %.2f staged %.2f cluster-sync %.2f reduced %.2f stored %.2f epi-end %.2f\n", (q[6] - q[1]) * 1e-3, (q[7] - q[1]) * 1e-3,
+                            q[48] > q[1] ? (q[48] - q[1]) * 1e-3 : 0.0, q[49] > q[1] ? (q[49] - q[1]) * 1e-3 : 0.0, (q[8] - q[1]) * 1e-3, (q[3] - q[1]) * 1e-3);
+                  }
                     SACB_CUDA(cudaMemset(d_trace, 0, sizeof(unsigned long long) * kTraceSlots * 4096));
                 }
             }
