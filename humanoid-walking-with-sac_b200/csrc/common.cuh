@@ -157,11 +157,14 @@ struct Program {
     const int32_t *slots;     // physical ring slots of the minibatch rows [n_agents, B]
     int32_t slots_stride; int32_t pad1;
     int32_t *error_flag;      // set by watchdogs (mbarrier / grid barrier timeouts)
+    const float2 *adam_table;     // [kAdamTable] (step_size, sqrt(bc2)) of Adam step t+1 for t = index, computed on the host in float64
+    unsigned long long *timeline; // optional [n_stages][4]: earliest CTA start, earliest dependency release, latest CTA end (profiling aid)
     unsigned long long *trace; // optional [grid][kTraceSlots] globaltimer stamps of each CTA's first tile (profiling aid), or null
 };
 
 // ---- tile geometry ----------------------------------------------------------------------------------------
 constexpr int kThreads = 512;
+constexpr int kAdamTable = 32768;   // beyond ~17.3 k steps both bias corrections round to exactly 1.0f: the last entry serves every later step
 constexpr int kTraceSlots = 64;   // 0..5 kernel phases, 6 accumulator ready, 16+kb TMA issue of k-block kb, 32+kb its arrival (kb < 16)
 // FFMA path (checker / strict mode)
 constexpr int kSM = 64, kSN = 64, kSK = 16;

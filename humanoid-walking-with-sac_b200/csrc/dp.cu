@@ -14,13 +14,13 @@ __global__ void dp_apply_kernel(float *w, float *m, float *v, float *wt, const f
         adam_element(g[i] * scale, w + i, m + i, v + i, wt ? wt + i : nullptr, nullptr, 1, ss, bs, tau);
 }
 
-__global__ void dp_finish_kernel(float *scalars, const float *g_scalars, int phase, int auto_entropy, float lr) {
+__global__ void dp_finish_kernel(float *scalars, const float *g_scalars, int phase, int auto_entropy, const float2 *adam_table) {
     if (threadIdx.x || blockIdx.x) return;
     if (phase == 0) {
         for (int slot = SC_STEP_Q1; slot <= SC_STEP_Q2; slot++) {
             const int step = __float_as_int(scalars[slot]) + 1;
             scalars[slot] = __int_as_float(step);
-            adam_factors_store(scalars, slot, step, lr);
+            adam_factors_store(scalars, slot, step, adam_table);
         }
     } else {
         const int n_upd = __float_as_int(scalars[SC_N_UPDATES]);
@@ -32,12 +32,12 @@ __global__ void dp_finish_kernel(float *scalars, const float *g_scalars, int pha
             alpha_next = expf(scalars[SC_LOG_ALPHA]);
             const int step = __float_as_int(scalars[SC_STEP_ALPHA]) + 1;
             scalars[SC_STEP_ALPHA] = __int_as_float(step);
-            adam_factors_store(scalars, SC_STEP_ALPHA, step, lr);
+            adam_factors_store(scalars, SC_STEP_ALPHA, step, adam_table);
         }
         scalars[SC_ALPHA0 + ((n_upd + 1) & 1)] = alpha_next;
         const int pstep = __float_as_int(scalars[SC_STEP_POLICY]) + 1;
         scalars[SC_STEP_POLICY] = __int_as_float(pstep);
-        adam_factors_store(scalars, SC_STEP_POLICY, pstep, lr);
+        adam_factors_store(scalars, SC_STEP_POLICY, pstep, adam_table);
         scalars[SC_N_UPDATES] = __int_as_float(n_upd + 1);
     }
 }
@@ -92,7 +92,7 @@ extern "C" int sacb_dp_apply(sacb_handle h, int phase) {
         h->kernel_launches++;
     };
     if (phase == 0) { run(1, L.q.size); run(2, L.q.size); } else run(0, L.pol.size);
-    dp_finish_kernel<<<1, 32, 0, h->stream>>>(sc, ar + L.grad_scalars, phase, h->cfg.auto_entropy, h->cfg.lr);
+    dp_finish_kernel<<<1, 32, 0, h->stream>>>(sc, ar + L.grad_scalars, phase, h->cfg.auto_entropy, h->adam_table);
     h->kernel_launches++;
     SACB_CUDA(cudaGetLastError());
     return SACB_OK;

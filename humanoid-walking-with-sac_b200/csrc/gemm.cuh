@@ -75,8 +75,14 @@ __device__ __forceinline__ void adam_factors_cached(const float *scalars, int st
     const float2 f = __ldcg(reinterpret_cast<const float2 *>(scalars + SC_FAC0 + 2 * (step_slot - SC_STEP_POLICY)));
     step_size = f.x; bc2_sqrt = f.y;
 }
-__host__ __device__ inline void adam_factors_store(float *scalars, int step_slot, int step, float lr) {
+__host__ inline void adam_factors_store(float *scalars, int step_slot, int step, float lr) {
     adam_factors(step, lr, scalars[SC_FAC0 + 2 * (step_slot - SC_STEP_POLICY)], scalars[SC_FAC0 + 2 * (step_slot - SC_STEP_POLICY) + 1]);
+}
+// device side: the factors come from the host-built table (float64 pow is very slow on this part)
+__device__ __forceinline__ void adam_factors_store(float *scalars, int step_slot, int step, const float2 *table) {
+    const float2 f = __ldg(table + min(step, kAdamTable - 1));
+    scalars[SC_FAC0 + 2 * (step_slot - SC_STEP_POLICY)] = f.x;
+    scalars[SC_FAC0 + 2 * (step_slot - SC_STEP_POLICY) + 1] = f.y;
 }
 
 // one Adam element update (+ Polyak, sac_imp.py:146-152); returns the new weight
@@ -406,9 +412,13 @@ __device__ __forceinline__ int tc_mainloop(const Task &t, int m0, int n0, int ag
                     const uint64_t da_hi = make_desc(sa + kk * a_kstep, a_lbo), da_lo = make_desc(sa + a_lo + kk * a_kstep, a_lbo);
                     const uint64_t db_hi = make_desc(sb + kk * b_kstep, b_lbo), db_lo = make_desc(sb + b_lo + kk * b_kstep, b_lbo);
                     // small terms first: a_lo*b_hi + a_hi*b_lo, then a_hi*b_hi
+#ifdef SACB_EXP_ONE_MMA      // timing experiment only (wrong numerics): is the K loop bound by MMA issue or by operand ingest?
+                    umma_bf16(st.tmem_base, da_hi, db_hi, idesc, (kb | kk) ? 1u : 0u);
+#else
                     umma_bf16(st.tmem_base, da_lo, db_hi, idesc, (kb | kk) ? 1u : 0u);
                     umma_bf16(st.tmem_base, da_hi, db_lo, idesc, 1u);
                     umma_bf16(st.tmem_base, da_hi, db_hi, idesc, 1u);
+#endif
                 }
                 umma_commit(&st.empty_bar[s]);                 // implies tcgen05.fence::before_thread_sync
                 if (kb == nkb - 1) umma_commit(st.accum_bar);

@@ -175,6 +175,14 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
         }
     };
     stamp(0);
+    auto timeline = [&](int slot, bool is_max) {
+        if (P.timeline && threadIdx.x == 0 && stage_end - stage_begin == 1) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (is_max) atomicMax(&P.timeline[stage_begin * 4 + slot], t); else atomicMin(&P.timeline[stage_begin * 4 + slot], t);
+        }
+    };
+    timeline(0, false);
     tc::TcState st;
     st.g = 0; st.accum_uses = 0; st.tmem_base = 0;
     st.krank = tc::cluster_ctarank(); st.ksplit = tc::cluster_nctarank(); st.reduce_uses = 0;
@@ -232,6 +240,7 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
                 asm volatile("griddepcontrol.wait;" ::: "memory");
                 asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
                 dep_synced = true;
+                timeline(1, false);
             }
             float *scalars = resolve(P.scalars, P.bases, agent);
             if (t.type != T_GEMM && st.krank != 0) continue;      // element-wise tasks of a clustered stage run on rank 0 only
@@ -248,7 +257,7 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
                 case T_SAMPLE_BWD: task_sample_bwd(t, tile, P, agent, scalars); break;
                 case T_OUT_ADAM: task_out_adam(t, tile, P, agent, scalars, s_red); break;
                 case T_BIAS_ADAM: task_bias_adam(t, tile, P, agent, scalars, s_red); break;
-                case T_FINISH: task_finish(t, P, agent, scalars, s_red); __syncthreads(); task_finish_steps(t, scalars); break;
+                case T_FINISH: task_finish(t, P, agent, scalars, s_red); __syncthreads(); task_finish_steps(t, P, scalars); break;
             }
             if (wi == cl) stamp(4);
         }
@@ -268,6 +277,7 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
         if (threadIdx.x < 32) tc::tmem_dealloc(st.tmem_base, kTN);
     }
     stamp(5);
+    timeline(2, true);
 }
 
 // ================================================================================================================
@@ -718,7 +728,7 @@ int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out) {
     }
     P.ring_row = (int32_t)h->ring_row; P.slots_stride = h->cfg.max_batch;
     P.error_flag = h->error_flag;
-    P.trace = nullptr;
+    P.trace = nullptr; P.timeline = nullptr; P.adam_table = h->adam_table;
     p.kernels_per_step = h->cfg.launch_mode == SACB_LAUNCH_PERSISTENT ? 1 : (int)p.stages.size();
 
     // capture one step into a CUDA graph (stage kernels, or memset + the single cooperative launch)
@@ -820,6 +830,40 @@ extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap
             for (int s = 0; s < (int)p->stages.size(); s++) { float ms; cudaEventElapsedTime(&ms, ev[s], ev[s + 1]); acc[s] += ms * 1000.f / reps; }
     }
     for (int s = 0; s < n; s++) us_out[s] = acc[s];
+    if (getenv("SACB_TIMELINE")) {
+        // stage timeline of ONE graph replay as the update really runs (PDL, graph): per stage the earliest CTA start, the
+        // earliest release from griddepcontrol.wait and the latest CTA end, from %globaltimer
+        const int ns = (int)p->stages.size();
+        unsigned long long *d_tl = nullptr;
+        SACB_CUDA(cudaMalloc(&d_tl, sizeof(unsigned long long) * 4 * ns));
+        std::vector<unsigned long long> init(4 * ns, 0ull), tl(4 * ns);
+        for (int s = 0; s < ns; s++) { init[4 * s] = ~0ull; init[4 * s + 1] = ~0ull; }
+        p->prog.timeline = d_tl;
+        cudaGraph_t g = nullptr; cudaGraphExec_t ge = nullptr;
+        SACB_CUDA(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+        int rc3 = SACB_OK;
+        for (int s = 0; s < ns && rc3 == SACB_OK; s++) rc3 = launch_stage(h, *p, s, h->use_pdl != 0);
+        SACB_CUDA(cudaStreamEndCapture(h->stream, &g));
+        p->prog.timeline = nullptr;
+        if (rc3 == SACB_OK && cudaGraphInstantiate(&ge, g, 0) == cudaSuccess) {
+            for (int r = 0; r < 4; r++) {
+                SACB_CUDA(cudaMemcpyAsync(d_tl, init.data(), sizeof(unsigned long long) * 4 * ns, cudaMemcpyHostToDevice, h->stream));
+                SACB_CUDA(cudaStreamSynchronize(h->stream));
+                SACB_CUDA(cudaGraphLaunch(ge, h->stream));
+                SACB_CUDA(cudaStreamSynchronize(h->stream));
+            }
+            SACB_CUDA(cudaMemcpy(tl.data(), d_tl, sizeof(unsigned long long) * 4 * ns, cudaMemcpyDeviceToHost));
+            const unsigned long long t0 = tl[0];
+            fprintf(stderr, "[timeline] stage: first-CTA-start  dependency-release  last-CTA-end | release-after-prev-end  release-to-end  (us, graph replay with PDL)\n");
+            for (int s = 0; s < ns; s++)
+                fprintf(stderr, "[timeline] %2d  %8.2f %8.2f %8.2f | %6.2f %6.2f\n", s, (tl[4 * s] - t0) * 1e-3, (tl[4 * s + 1] - t0) * 1e-3, (tl[4 * s + 2] - t0) * 1e-3,
+                        s ? ((double)tl[4 * s + 1] - (double)tl[4 * (s - 1) + 2]) * 1e-3 : 0.0, (tl[4 * s + 2] - tl[4 * s + 1]) * 1e-3);
+            fprintf(stderr, "[timeline] update = %.2f us\n", (tl[4 * (ns - 1) + 2] - t0) * 1e-3);
+            cudaGraphExecDestroy(ge);
+        }
+        if (g) cudaGraphDestroy(g);
+        cudaFree(d_tl);
+    }
     if (trace && getenv("SACB_TRACE_RANGE")) {
         // warm-code experiment: stages [a, b) in ONE cooperative launch; the surviving stamps belong to stage b-1 and are
         // printed relative to its own start (slot 9, right after the grid barrier)

@@ -86,6 +86,13 @@ extern "C" int sacb_create(const sacb_config *cfg, sacb_handle *out) {
     cudaMemsetAsync(h->barrier, 0, 64, h->stream);
     cudaMemsetAsync(h->error_flag, 0, 64, h->stream);
     cudaMemsetAsync(h->slots, 0, sizeof(int32_t) * cfg->max_batch * n, h->stream);
+    {   // Adam bias corrections for every step count that still differs from (lr, 1) in float32
+        std::vector<float2> tab(kAdamTable);
+        for (int t = 0; t < kAdamTable; t++) adam_factors(t, cfg->lr, tab[t].x, tab[t].y);
+        if (cudaMalloc(&h->adam_table, sizeof(float2) * kAdamTable) != cudaSuccess) return bail(fail(SACB_ERR_NOMEM, "device allocation failed"));
+        cudaMemcpyAsync(h->adam_table, tab.data(), sizeof(float2) * kAdamTable, cudaMemcpyHostToDevice, h->stream);
+        cudaStreamSynchronize(h->stream);
+    }
     int rc = scalars_init(h);
     if (rc) return bail(fail(rc, "scalar init failed"));
     rc = init_kernel_attributes(h);
@@ -104,7 +111,7 @@ extern "C" int sacb_destroy(sacb_handle h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_programs(h);
     replay_destroy(h);
-    cudaFree(h->arena); cudaFree(h->ws); cudaFree(h->barrier); cudaFree(h->error_flag); cudaFree(h->slots); cudaFree(h->slots_identity); cudaFree(h->slots_staged);
+    cudaFree(h->arena); cudaFree(h->ws); cudaFree(h->barrier); cudaFree(h->error_flag); cudaFree(h->slots); cudaFree(h->slots_identity); cudaFree(h->adam_table); cudaFree(h->slots_staged);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->pin_rows) cudaFreeHost(h->pin_rows);
     if (h->stream) cudaStreamDestroy(h->stream);

@@ -213,6 +213,19 @@ __device__ __forceinline__ void task_target_loss(const Task &t, int tile, const 
     float *sq = smem, *sd = smem + 16, *sl = smem + 24;      // dots [4 rows][4 nets], dq [4][2], loss terms [4][2]
     const Pm h = resolve_pm(t.pm[k], P.bases, agent);
     const float *w = resolve(t.p[4 + k], P.bases, agent);
+    // the row's scalars are fetched by its scalar thread BEFORE the dot products, so their latency hides behind them
+    float pre_bias[4] = {0.f, 0.f, 0.f, 0.f}, pre_alpha = 0.f, pre_logp = 0.f, pre_r = 0.f, pre_d = 0.f, pre_w = 1.f;
+    if (threadIdx.x < kLossRows && tile * kLossRows + (int)threadIdx.x < B) {
+        const int br = tile * kLossRows + threadIdx.x;
+        for (int j = 0; j < 4; j++) pre_bias[j] = ldcg(resolve(t.p[8 + j], P.bases, agent));
+        const int n_upd = __float_as_int(ldcg(scalars + SC_N_UPDATES));
+        pre_alpha = ldcg(scalars + SC_ALPHA0 + (n_upd & 1));
+        const float *isw = resolve(t.p[15], P.bases, agent);
+        pre_logp = ldcg(resolve(t.p[14], P.bases, agent) + br);
+        pre_r = ldcg(resolve(t.p[12], P.bases, agent) + br);
+        pre_d = ldcg(resolve(t.p[13], P.bases, agent) + br);
+        if (isw) pre_w = ldcg(isw + br);
+    }
     const float q = b < B ? row_dot(h, w, b, H, lane) : 0.f;
     if (lane == 0) sq[warp] = q;
     __syncthreads();
@@ -221,14 +234,12 @@ __device__ __forceinline__ void task_target_loss(const Task &t, int tile, const 
         float l1 = 0.f, l2 = 0.f, dq1 = 0.f, dq2 = 0.f;
         if (br < B) {
             float qq[4];
-            for (int j = 0; j < 4; j++) qq[j] = sq[r * 4 + j] + ldcg(resolve(t.p[8 + j], P.bases, agent));
-            const int n_upd = __float_as_int(ldcg(scalars + SC_N_UPDATES));
-            const float alpha = ldcg(scalars + SC_ALPHA0 + (n_upd & 1));
-            const float *isw = resolve(t.p[15], P.bases, agent);
+            for (int j = 0; j < 4; j++) qq[j] = sq[r * 4 + j] + pre_bias[j];
+            const float alpha = pre_alpha;
             const float qn = fminf(qq[0], qq[1]);
-            const float vt = qn - alpha * ldcg(resolve(t.p[14], P.bases, agent) + br);                                   // sac_imp.py:97
-            const float yy = ldcg(resolve(t.p[12], P.bases, agent) + br) + (1.f - ldcg(resolve(t.p[13], P.bases, agent) + br)) * t.f[0] * vt;   // :98
-            const float wgt = isw ? ldcg(isw + br) : 1.f;
+            const float vt = qn - alpha * pre_logp;                                   // sac_imp.py:97
+            const float yy = pre_r + (1.f - pre_d) * t.f[0] * vt;                     // :98
+            const float wgt = pre_w;
             const float e1 = qq[2] - yy, e2 = qq[3] - yy;
             dq1 = 2.f * wgt * e1 / (float)B;                                                                          // d mean((q-y)^2) / dq
             dq2 = 2.f * wgt * e2 / (float)B;
@@ -264,6 +275,13 @@ __device__ __forceinline__ void task_actor_loss(const Task &t, int tile, const P
     float *sq = smem, *sd = smem + 16, *sl = smem + 24;
     const Pm h = resolve_pm(t.pm[k & 1], P.bases, agent);
     const float *w = resolve(t.p[2 + (k & 1)], P.bases, agent);
+    float pre_b1 = 0.f, pre_b2 = 0.f, pre_alpha = 0.f, pre_logp = 0.f;      // fetched before the dot products (latency hidden)
+    if (threadIdx.x < kLossRows && tile * kLossRows + (int)threadIdx.x < B) {
+        pre_b1 = ldcg(resolve(t.p[4], P.bases, agent)); pre_b2 = ldcg(resolve(t.p[5], P.bases, agent));
+        const int n_upd = __float_as_int(ldcg(scalars + SC_N_UPDATES));
+        pre_alpha = ldcg(scalars + SC_ALPHA0 + (n_upd & 1));
+        pre_logp = ldcg(resolve(t.p[6], P.bases, agent) + tile * kLossRows + threadIdx.x);
+    }
     const float q = (b < B && k < 2) ? row_dot(h, w, b, H, lane) : 0.f;
     if (lane == 0) sq[warp] = q;
     __syncthreads();
@@ -271,10 +289,9 @@ __device__ __forceinline__ void task_actor_loss(const Task &t, int tile, const P
         const int r = threadIdx.x, br = tile * kLossRows + r;
         float pl = 0.f, ent = 0.f, d1 = 0.f, d2 = 0.f;
         if (br < B) {
-            const float q1 = sq[r * 4] + ldcg(resolve(t.p[4], P.bases, agent)), q2 = sq[r * 4 + 1] + ldcg(resolve(t.p[5], P.bases, agent));
-            const int n_upd = __float_as_int(ldcg(scalars + SC_N_UPDATES));
-            const float alpha = ldcg(scalars + SC_ALPHA0 + (n_upd & 1));
-            const float l = ldcg(resolve(t.p[6], P.bases, agent) + br);
+            const float q1 = sq[r * 4] + pre_b1, q2 = sq[r * 4 + 1] + pre_b2;
+            const float alpha = pre_alpha;
+            const float l = pre_logp;
             pl = alpha * l - fminf(q1, q2);                                          // sac_imp.py:119-121
             const float sel = q1 < q2 ? 1.f : (q1 == q2 ? 0.5f : 0.f);               // torch.minimum backward
             d1 = -sel / (float)B;
@@ -429,13 +446,13 @@ __device__ __forceinline__ void task_finish(const Task &t, const Program &P, int
 }
 
 // second half of T_FINISH, threads 0..3 in parallel: bump one optimizer's step counter and cache its next bias corrections
-__device__ __forceinline__ void task_finish_steps(const Task &t, float *scalars) {
+__device__ __forceinline__ void task_finish_steps(const Task &t, const Program &P, float *scalars) {
     const int k = threadIdx.x;
     if (k >= 4 || !t.i[k]) return;
     const int slot = SC_STEP_POLICY + k;      // SC_STEP_POLICY, SC_STEP_Q1, SC_STEP_Q2, SC_STEP_ALPHA are consecutive
     const int step = __float_as_int(scalars[slot]) + 1;
     scalars[slot] = __int_as_float(step);
-    adam_factors_store(scalars, slot, step, t.f[0]);
+    adam_factors_store(scalars, slot, step, P.adam_table);
 }
 
 }  // namespace sacb
