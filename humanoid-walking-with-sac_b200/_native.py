@@ -103,6 +103,7 @@ SIGNATURES = {
     "sacb_time_stages": (I, [H, I64, c_f32p, I]),
     "sacb_debug_read_activation": (I, [H, I, I, I, I, I64, c_f32p]),
     "sacb_selftest_gemm": (I, [I, I, I, I, I, I, I, c_f32p]),
+    "sacb_selftest_gemm_tile": (I, [I, I, I, I, I, I, I, I, I, c_f32p]),
 }
 
 _lib = None

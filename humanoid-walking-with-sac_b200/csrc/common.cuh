@@ -120,6 +120,7 @@ struct alignas(64) Task {
     int32_t tile_begin;       // first tile of this task inside its stage
     int32_t n_tiles;
     int32_t tiles_m, tiles_n;
+    int32_t bm, bn;           // output tile of this GEMM task: 128 or 64 rows x 64 or 32 columns (chosen per stage by the builder)
     // --- GEMM
     Operand A, B;
     int32_t M, N, K;
@@ -168,7 +169,8 @@ constexpr int kAdamTable = 32768;   // beyond ~17.3 k steps both bias correction
 constexpr int kTraceSlots = 64;   // 0..5 kernel phases, 6 accumulator ready, 16+kb TMA issue of k-block kb, 32+kb its arrival (kb < 16)
 // FFMA path (checker / strict mode)
 constexpr int kSM = 64, kSN = 64, kSK = 16;
-// tcgen05 path: 128 x 64 output tile, K blocks of 64 bf16 (= 128 B, one SWIZZLE_128B row), both planes per stage
+// tcgen05 path: output tile up to 128 x 64 (a task may use 64 rows and / or 32 columns: Task::bm, bn), K blocks of 64 bf16
+// (= 128 B, one SWIZZLE_128B row), both planes per stage
 constexpr int kTM = 128, kTN = 64, kTK = 64, kTStages = 4;
 constexpr int kTcABytes = kTM * kTK * 2 * 2;                      // hi + lo planes of the A tile: 32 KB
 constexpr int kTcBBytes = kTN * kTK * 2 * 2;                      // 16 KB

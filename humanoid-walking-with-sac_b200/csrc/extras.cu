@@ -168,7 +168,12 @@ static float host_bf16_to_float(uint16_t b) { uint32_t u = (uint32_t)b << 16; fl
 }  // namespace sacb
 
 extern "C" int sacb_selftest_gemm(int device, int M, int N, int K, int a_mn, int b_mn, int b_r0, float *rel_err_out) {
+    return sacb_selftest_gemm_tile(device, M, N, K, a_mn, b_mn, b_r0, kTM, kTN, rel_err_out);
+}
+
+extern "C" int sacb_selftest_gemm_tile(int device, int M, int N, int K, int a_mn, int b_mn, int b_r0, int bm, int bn, float *rel_err_out) {
     if (M < 1 || N < 1 || K < 1 || b_r0 < 0 || (b_mn && b_r0 % 8) || !rel_err_out) return fail(SACB_ERR_ARG, "bad argument (an MN-major operand offset must be a multiple of 8)");
+    if ((bm != 64 && bm != 128) || (bn != 32 && bn != 64) || (bn == 32 && b_mn)) return fail(SACB_ERR_ARG, "tile shape must be 64|128 x 32|64 (32 columns only with a K-major B operand)");
     SACB_CUDA(cudaSetDevice(device));
     // stored shapes: K-major [R, K], MN-major [K, R]; the B matrix has b_r0 leading rows/columns that are not part of the operand
     const int NB = N + b_r0;
@@ -203,7 +208,8 @@ extern "C" int sacb_selftest_gemm(int device, int M, int N, int K, int a_mn, int
     Task tk[2];
     for (int v = 0; v < 2; v++) {
         Task &t = tk[v]; memset(&t, 0, sizeof(t));
-        const int tm = v ? kTM : kSM, tn = v ? kTN : kSN;
+        const int tm = v ? bm : kSM, tn = v ? bn : kSN;
+        t.bm = tm; t.bn = tn;
         t.type = T_GEMM; t.M = M; t.N = N; t.K = K; t.epi = EPI_F32;
         t.A.pm.base = make_ref(0, oa); t.A.pm.ld = lda; t.A.pm.plane = na; t.A.mn_major = a_mn; t.A.r0 = 0;
         t.B.pm.base = make_ref(0, ob); t.B.pm.ld = ldb; t.B.pm.plane = nb; t.B.mn_major = b_mn; t.B.r0 = b_r0;
@@ -211,8 +217,8 @@ extern "C" int sacb_selftest_gemm(int device, int M, int N, int K, int a_mn, int
         t.Cpm = t.mask = null_pm(); t.adam.shadow = t.adam.shadow2 = null_pm();
         t.tiles_m = cdiv(M, tm); t.tiles_n = cdiv(N, tn); t.n_tiles = t.tiles_m * t.tiles_n;
     }
-    int rc = make_pm_tensor_map(&tk[1].tmA, d + oa, a_cols, a_rows, lda, na, 0, 1, a_mn ? 64 : kTM);
-    if (rc == SACB_OK) rc = make_pm_tensor_map(&tk[1].tmB, d + ob, b_cols, b_rows, ldb, nb, 0, 1, 64);
+    int rc = make_pm_tensor_map(&tk[1].tmA, d + oa, a_cols, a_rows, lda, na, 0, 1, a_mn ? 64 : bm);
+    if (rc == SACB_OK) rc = make_pm_tensor_map(&tk[1].tmB, d + ob, b_cols, b_rows, ldb, nb, 0, 1, b_mn ? 64 : bn);
     if (rc) { cudaFree(d); cudaFree(d_tasks); cudaFree(flag); return rc; }
     SACB_CUDA(cudaMemcpy(d_tasks, tk, sizeof(tk), cudaMemcpyHostToDevice));
     gemm_selftest_kernel<SACB_MATH_FP32><<<tk[0].n_tiles, kThreads, kSimtSmemBytes>>>(d_tasks, bases, flag);

@@ -355,10 +355,13 @@ __device__ __forceinline__ bool mbar_wait_cluster(uint64_t *bar, uint32_t parity
 }
 
 // ---- main loop of one output tile: warp 0 = TMA producer, warp 1 = MMA issuer ----------------------------------
-// smem stage: A region 32 KB then B region 16 KB.
-//   K-major  A: one box {64 k, 128 rows, 2 planes}            -> [hi 16 KB][lo 16 KB]
-//   MN-major A: two boxes {64 m, 64 k, 2 planes} (m groups)   -> [hi g0 8K][lo g0 8K][hi g1 8K][lo g1 8K]
-//   B (either major): one box {64, 64, 2}                     -> [hi 8 KB][lo 8 KB]
+// smem stage: A region 32 KB then B region 16 KB (a 64-row / 32-column task fills only the front of its region).
+//   K-major  A: one box {64 k, bm rows, 2 planes}             -> [hi bm*128 B][lo bm*128 B]
+//   MN-major A: bm/64 boxes {64 m, 64 k, 2 planes} (m groups) -> [hi g0 8K][lo g0 8K]([hi g1 8K][lo g1 8K])
+//   K-major  B: one box {64 k, bn rows, 2 planes}             -> [hi bn*128 B][lo bn*128 B]
+//   MN-major B: one box {64 n, 64 k, 2 planes} (bn = 64 only) -> [hi 8 KB][lo 8 KB]
+// TMEM accumulator: bm = 128 -> tile row r in lane r; bm = 64 -> tile row r in lane (r % 16) + 32 * (r / 16)
+// (cute::UMMA::tmem_frg_1sm, M_MMA == 64: the upper half of every 32-lane subpartition stays unused).
 __device__ __forceinline__ void trace_stamp(unsigned long long *trace, int slot) {
     unsigned long long ts;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ts));
@@ -380,14 +383,14 @@ __device__ __forceinline__ int tc_mainloop(const Task &t, int m0, int n0, int ag
                 const uint32_t g = g0 + kb, s = g % nst;
                 mbar_wait(&st.empty_bar[s], ((g / nst) & 1) ^ 1, error_flag);
                 if (traced && kb < 16) trace_stamp(st.trace, 16 + kb);
-                mbar_arrive_expect_tx(&st.full_bar[s], kTcStageBytes);
+                mbar_arrive_expect_tx(&st.full_bar[s], (uint32_t)(t.bm + t.bn) * (kTK * 2 * 2));      // both planes of both operand tiles
                 const uint32_t sa = tiles + s * kTcStageBytes, sb = sa + kTcABytes;
                 const int k0 = (kb0 + kb) * kTK, ma = t.A.r0 + m0, nb = t.B.r0 + n0;
                 if (!a_mn) {
-                    tma_load_4d(st.tmA, &st.full_bar[s], sa, k0, ma, 0, agent);
+                    tma_load_4d(st.tmA, &st.full_bar[s], sa, k0, ma, 0, agent);        // box rows = bm (descriptor)
                 } else {
                     tma_load_4d(st.tmA, &st.full_bar[s], sa, ma, k0, 0, agent);
-                    tma_load_4d(st.tmA, &st.full_bar[s], sa + kTcABytes / 2, ma + 64, k0, 0, agent);
+                    if (t.bm > 64) tma_load_4d(st.tmA, &st.full_bar[s], sa + kTcABytes / 2, ma + 64, k0, 0, agent);
                 }
                 if (!b_mn) tma_load_4d(st.tmB, &st.full_bar[s], sb, k0, nb, 0, agent);
                 else tma_load_4d(st.tmB, &st.full_bar[s], sb, nb, k0, 0, agent);
@@ -395,9 +398,10 @@ __device__ __forceinline__ int tc_mainloop(const Task &t, int m0, int n0, int ag
         }
         __syncwarp();
     } else if (warp == 1) {
-        const uint32_t idesc = make_idesc(kTM, kTN, a_mn, b_mn);
-        // byte offsets inside a stage: lo plane of each operand, and the step of one UMMA_K (16 bf16)
-        const uint32_t a_lo = a_mn ? kTcABytes / 4 : kTcABytes / 2, b_lo = kTcBBytes / 2;
+        const uint32_t idesc = make_idesc(t.bm, t.bn, a_mn, b_mn);
+        // byte offsets inside a stage: lo plane of each operand (K-major: after the `rows` 128 B rows of the hi plane; MN-major:
+        // after the 64 k-rows of a 64-wide group), and the step of one UMMA_K (16 bf16)
+        const uint32_t a_lo = a_mn ? kTcABytes / 4 : (uint32_t)t.bm * 128u, b_lo = b_mn ? kTcBBytes / 2 : (uint32_t)t.bn * 128u;
         const uint32_t a_lbo = a_mn ? kTcABytes / 2 : 16, b_lbo = 16;
         const uint32_t a_kstep = a_mn ? 2048 : 32, b_kstep = b_mn ? 2048 : 32;
         for (int kb = 0; kb < nkb; kb++) {
@@ -637,30 +641,35 @@ __device__ __forceinline__ void epilogue_rows4(const EpiR &e, const int (&m)[R],
 }
 
 template <int EPI>
-__device__ __forceinline__ void tc_epilogue(const EpiR &epi, int m0, int n0, TcState &st, int nkb_mine, int *error_flag, bool traced) {
+__device__ __forceinline__ void tc_epilogue(const EpiR &epi, int m0, int n0, int bm, int bn, TcState &st, int nkb_mine, int *error_flag, bool traced) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ks = (int)st.ksplit, rows_per = kTM / ks;
     // staging: ks == 1 -> one tile [kTM][kCsLd] over operand stage 0 (all MMAs have retired);
     //          ks  > 1 -> ks slots [rows_per][kCsLd] over operand stage 3 (never used by a clustered main loop), slot = source rank
     float *Cs = reinterpret_cast<float *>(st.tiles + (ks > 1 ? (kTStages - 1) * kTcStageBytes : 0));
-    {   // phase 1: warp w owns TMEM lanes 32*(w%4).., column group w/4
-        const int row = (warp & 3) * 32 + lane, colh = (warp >> 2) * 16;
+    {   // phase 1: warp w owns TMEM lanes 32*(w%4).., column group w/4.  A 64-row tile keeps 16 rows in the lower half of each
+        // 32-lane subpartition; a 32-column tile has only two column groups.
+        const bool half_m = bm == 64;
+        const int row = half_m ? (warp & 3) * 16 + lane : (warp & 3) * 32 + lane, colh = (warp >> 2) * 16;
+        const bool cols_live = colh < bn;      // warp-uniform
         float v[16];
         if (nkb_mine > 0) {
             mbar_wait(st.accum_bar, st.accum_uses & 1, error_flag);
             st.accum_uses++;
             if (traced && tid == 64) trace_stamp(st.trace, 6);
             tc_fence_after();
-            tmem_ld16(st.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)colh, v);
+            if (cols_live) tmem_ld16(st.tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)colh, v);
         } else {      // a cluster rank beyond the last K-block contributes a zero partial tile
 #pragma unroll
             for (int j = 0; j < 16; j++) v[j] = 0.f;
         }
         if (ks == 1) {
-            float4 *dst = reinterpret_cast<float4 *>(Cs + row * kCsLd + colh);
+            if (cols_live && (!half_m || lane < 16)) {
+                float4 *dst = reinterpret_cast<float4 *>(Cs + row * kCsLd + colh);
 #pragma unroll
-            for (int j = 0; j < 4; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        } else {      // push the row to the CTA that finishes it (warp-uniform owner), slot = my rank
+                for (int j = 0; j < 4; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            }
+        } else {      // push the row to the CTA that finishes it (warp-uniform owner), slot = my rank (clustered tiles are 128 x 64)
             const uint32_t owner = (uint32_t)(row / rows_per);
             const uint32_t dst = dsmem_addr(Cs + ((int)st.krank * rows_per + row % rows_per) * kCsLd + colh, owner);
 #pragma unroll
@@ -670,7 +679,7 @@ __device__ __forceinline__ void tc_epilogue(const EpiR &epi, int m0, int n0, TcS
     tc_fence_before();
     __syncthreads();     // staging complete; all TMEM reads retired (the next tile's first MMA may overwrite the accumulator)
     if (traced && tid == 64) trace_stamp(st.trace, 7);
-    int row_lo = 0, row_hi = kTM;
+    int row_lo = 0, row_hi = bm;
     if (ks > 1) {
         if (tid < ks && tid != (int)st.krank) {      // one release-arrive per peer: my rows have landed in its slots
             asm volatile("fence.acq_rel.cluster;" ::: "memory");
@@ -695,15 +704,18 @@ __device__ __forceinline__ void tc_epilogue(const EpiR &epi, int m0, int n0, TcS
     }
     if (EPI == EPI_ADAM) {
         adam_epilogue_tile(epi, Cs, m0, n0, row_lo, row_hi);
-    } else {   // phase 2: all four rows of a thread at once, so every global load is in flight before the first store
-        const int c4 = (tid & 15) * 4, r0 = tid >> 4;
+    } else {   // phase 2: all rows of a thread at once, so every global load is in flight before the first store.
+        // bn / 4 threads cover a row (4 columns each); the 512 threads cover 32 (bn = 64) or 64 (bn = 32) rows per pass
+        const int ct = bn >> 2, rs = kThreads / ct;
+        const int c4 = (tid % ct) * 4, r0 = tid / ct;
         int m[4];
         float4 acc[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const bool mine = 32 * i + r0 >= row_lo && 32 * i + r0 < row_hi;
-            m[i] = mine ? m0 + 32 * i + r0 : 0x7fffffff;      // rows of another cluster rank are skipped like rows beyond M
-            acc[i] = mine ? *reinterpret_cast<const float4 *>(Cs + (32 * i + r0) * kCsLd + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int row = rs * i + r0;
+            const bool mine = row >= row_lo && row < row_hi;
+            m[i] = mine ? m0 + row : 0x7fffffff;      // rows of another cluster rank / beyond the tile are skipped like rows beyond M
+            acc[i] = mine ? *reinterpret_cast<const float4 *>(Cs + row * kCsLd + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (traced && tid == 64 && acc[0].x != 12345.678f) trace_stamp(st.trace, 13);
         epilogue_rows4<EPI, 4>(epi, m, n0 + c4, acc, (traced && tid == 64) ? st.trace : nullptr);
@@ -721,7 +733,7 @@ __device__ __forceinline__ void gemm_tile_tc(const Task &t, const Task *tg, int 
     using namespace tc;
     st.tmA = &tg->tmA; st.tmB = &tg->tmB;
     const int tm = tile / t.tiles_n, tn = tile % t.tiles_n;
-    const int m0 = tm * kTM, n0 = tn * kTN;
+    const int m0 = tm * t.bm, n0 = tn * t.bn;
     const bool traced = st.trace && first_tile;      // the CTA's first tile of the stage
     if (st.ksplit > 1 && !first_tile) { cluster_arrive(); cluster_wait(); }      // peers are done with the previous tile's slots
     const int nkb_mine = tc_mainloop(t, m0, n0, agent, st, error_flag, traced);
@@ -729,10 +741,10 @@ __device__ __forceinline__ void gemm_tile_tc(const Task &t, const Task *tg, int 
     stamp(2);
     const EpiR epi = resolve_epilogue(t, bases, agent, scalars);
     switch (t.epi) {
-        case EPI_F32: tc_epilogue<EPI_F32>(epi, m0, n0, st, nkb_mine, error_flag, traced); break;
-        case EPI_BIAS_RELU: tc_epilogue<EPI_BIAS_RELU>(epi, m0, n0, st, nkb_mine, error_flag, traced); break;
-        case EPI_MASK: tc_epilogue<EPI_MASK>(epi, m0, n0, st, nkb_mine, error_flag, traced); break;
-        default: tc_epilogue<EPI_ADAM>(epi, m0, n0, st, nkb_mine, error_flag, traced); break;
+        case EPI_F32: tc_epilogue<EPI_F32>(epi, m0, n0, t.bm, t.bn, st, nkb_mine, error_flag, traced); break;
+        case EPI_BIAS_RELU: tc_epilogue<EPI_BIAS_RELU>(epi, m0, n0, t.bm, t.bn, st, nkb_mine, error_flag, traced); break;
+        case EPI_MASK: tc_epilogue<EPI_MASK>(epi, m0, n0, t.bm, t.bn, st, nkb_mine, error_flag, traced); break;
+        default: tc_epilogue<EPI_ADAM>(epi, m0, n0, t.bm, t.bn, st, nkb_mine, error_flag, traced); break;
     }
     stamp(3);
 }

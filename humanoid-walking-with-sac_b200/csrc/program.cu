@@ -298,8 +298,11 @@ struct Builder {
     std::vector<Task> tasks;
     std::vector<Stage> stages;
     std::vector<int> has_gemm;
-    int tm, tn;   // GEMM tile dims of the math mode
+    int tm, tn;   // default GEMM tile dims of the math mode
     int rc = SACB_OK;
+    // tensor-core tile shape per task index (bm, bn), decided by choose_tile_shapes() from a dry first pass; empty = defaults
+    std::vector<std::pair<int, int>> shapes;
+    bool dry = false;      // first pass: count tiles only, no TMA descriptors
 
     Builder(sacb_handle h_, const ProgramKey &k) : h(h_), L(h_->L), key(k) {
         if (math_is_tc(h->cfg.math_mode)) { tm = kTM; tn = kTN; } else { tm = kSM; tn = kSN; }
@@ -365,15 +368,18 @@ struct Builder {
     void gemm(const PmView &a, int a_mn, const PmView &b, int b_mn, int M, int N, int K, Task t, int b_r0 = 0) {
         t.type = T_GEMM; t.M = M; t.N = N; t.K = K;
         t.A.pm = a.ref; t.A.mn_major = a_mn; t.A.r0 = 0; t.B.pm = b.ref; t.B.mn_major = b_mn; t.B.r0 = b_r0;
-        t.tiles_m = cdiv(M, tm); t.tiles_n = cdiv(N, tn);
-        if (math_is_tc(h->cfg.math_mode) && rc == SACB_OK) {
+        const size_t idx = tasks.size();
+        t.bm = idx < shapes.size() && shapes[idx].first ? shapes[idx].first : tm;
+        t.bn = idx < shapes.size() && shapes[idx].second ? shapes[idx].second : tn;
+        t.tiles_m = cdiv(M, t.bm); t.tiles_n = cdiv(N, t.bn);
+        if (math_is_tc(h->cfg.math_mode) && rc == SACB_OK && !dry) {
             // stored extents: K-major [R, K] -> cols = K ; MN-major [K, R] -> cols = R.  TMA zero-fills beyond them.
             const int a_cols = a_mn ? M : K, a_rows = a_mn ? K : M, b_cols = b_mn ? b_r0 + N : K, b_rows = b_mn ? K : b_r0 + N;
             rc = make_pm_tensor_map(&t.tmA, dev_ptr(a.ref.base), a_cols, a_rows, a.ref.ld, a.ref.plane, agent_stride_bytes(a.ref.base),
-                                    h->cfg.n_agents, a_mn ? 64 : kTM);
+                                    h->cfg.n_agents, a_mn ? 64 : t.bm);
             if (rc == SACB_OK)
                 rc = make_pm_tensor_map(&t.tmB, dev_ptr(b.ref.base), b_cols, b_rows, b.ref.ld, b.ref.plane, agent_stride_bytes(b.ref.base),
-                                        h->cfg.n_agents, 64);
+                                        h->cfg.n_agents, b_mn ? 64 : t.bn);
         }
         add(t, t.tiles_m * t.tiles_n);
     }
@@ -419,6 +425,53 @@ struct Builder {
         Task t = blank(T_SHADOW);
         t.p[0] = A(L.param[net] + w_off); t.pm[0] = dst.ref; t.i[0] = dst.rows; t.i[1] = dst.cols; t.i[2] = col0; t.i[3] = src_ld;
         add(t, cdiv(dst.rows, kShadowRows));
+    }
+
+    // Tile shapes of a latency-bound program (tensor-core math, few agents).  A stage is as slow as its slowest CTA, a CTA's
+    // main loop is bound by the per-SM L2 -> shared-memory ingest (~90 GB/s, profiles/r01_summary.md) and a 128 x 64 stage
+    // keeps only 32-64 of the SMs busy.  So while the stage still fits into one wave, the most expensive task is cut into
+    // smaller tiles: 128 -> 64 rows (tcgen05 M = 64) first, then 64 -> 32 columns where B is K-major and the epilogue is not
+    // the Adam one.  Results do not depend on the shape (the K order of every output element is unchanged).
+    static double tile_cost_us(const Task &t, int bm, int bn) {
+        const double ingest = (double)(bm + bn) * std::min(t.K, 1 << 20) * 4.0 / 90e3;          // both planes, 2 B each
+        const double epi = (t.epi == EPI_ADAM ? 6.0 : 1.4) * (double)(bm * bn) / (kTM * kTN);  // measured per 128 x 64 tile
+        return ingest + epi;
+    }
+    std::vector<std::pair<int, int>> choose_tile_shapes(int wave) const {
+        std::vector<std::pair<int, int>> out(tasks.size(), {0, 0});
+        if (!math_is_tc(h->cfg.math_mode) || getenv("SACB_FIXED_TILES")) return out;
+        for (size_t si = 0; si < stages.size(); si++) {
+            const Stage &sg = stages[si];
+            if (!has_gemm[si]) continue;
+            struct Cand { int task, bm, bn, tiles; bool frozen; };
+            std::vector<Cand> c;
+            int total = 0;
+            for (int k = sg.task_begin; k < sg.task_end; k++) {
+                total += tasks[k].n_tiles * h->cfg.n_agents;
+                if (tasks[k].type == T_GEMM) c.push_back({k, kTM, kTN, tasks[k].n_tiles, false});
+            }
+            while (true) {
+                int best = -1; double best_cost = 0;
+                for (size_t i = 0; i < c.size(); i++) {
+                    if (c[i].frozen) continue;
+                    const double cost = tile_cost_us(tasks[c[i].task], c[i].bm, c[i].bn);
+                    if (cost > best_cost) { best_cost = cost; best = (int)i; }
+                }
+                if (best < 0) break;
+                Cand &b = c[best];
+                const Task &t = tasks[b.task];
+                int nbm = b.bm, nbn = b.bn;
+                if (b.bm == kTM && t.M > 64) nbm = 64;
+                else if (b.bn == kTN && !t.B.mn_major && t.epi != EPI_ADAM && t.N > 32) nbn = 32;
+                else { b.frozen = true; continue; }
+                const int ntiles = cdiv(t.M, nbm) * cdiv(t.N, nbn);
+                if (total + (ntiles - b.tiles) * h->cfg.n_agents > wave) { b.frozen = true; continue; }
+                total += (ntiles - b.tiles) * h->cfg.n_agents;
+                b.bm = nbm; b.bn = nbn; b.tiles = ntiles;
+            }
+            for (const Cand &x : c) out[x.task] = {x.bm, x.bn};
+        }
+        return out;
     }
 
     void build() {
@@ -690,7 +743,16 @@ int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out) {
     auto it = h->programs.find(key);
     if (it != h->programs.end()) { *out = &it->second; return SACB_OK; }
     if (key.B < 1 || key.B > h->cfg.max_batch) return fail(SACB_ERR_ARG, "batch size exceeds max_batch of the handle");
+    std::vector<std::pair<int, int>> shapes;
+    {   // dry pass with the default 128 x 64 tiles: the per-stage tile counts drive the choice of tile shapes
+        Builder d(h, key);
+        d.dry = true;
+        d.build();
+        if (d.rc != SACB_OK) return d.rc;
+        shapes = d.choose_tile_shapes(h->sm_count);
+    }
     Builder b(h, key);
+    b.shapes = shapes;
     b.build();
     if (b.rc != SACB_OK) return b.rc;
     // split-K (opt-in, SACB_SPLITK=1): a latency-bound stage with few tiles spreads every tile over a 2- or 4-CTA cluster so
@@ -700,7 +762,7 @@ int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out) {
     for (size_t s = 0; s < b.stages.size(); s++) {
         Stage &sg = b.stages[s];
         sg.ksplit = 1;
-        if (!math_is_tc(h->cfg.math_mode) || h->cfg.launch_mode != SACB_LAUNCH_STAGED || !b.has_gemm[s] || !getenv("SACB_SPLITK")) continue;
+        if (!math_is_tc(h->cfg.math_mode) || h->cfg.launch_mode != SACB_LAUNCH_STAGED || !b.has_gemm[s] || !getenv("SACB_SPLITK") || !getenv("SACB_FIXED_TILES")) continue;
         int max_kb = 1;
         for (int k = sg.task_begin; k < sg.task_end; k++)
             if (b.tasks[k].type == T_GEMM) max_kb = std::max(max_kb, cdiv(b.tasks[k].K, kTK));

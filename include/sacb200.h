@@ -190,6 +190,8 @@ int sacb_debug_read_activation(sacb_handle h, int agent, int group, int k, int l
 /* standalone GEMM self-test of the TMA + tcgen05 tile against the FFMA tile and a host float64 product of the same
  * bf16-pair operands; returns max |diff| / max |ref|.  b_r0 = row/column offset of the B operand inside its matrix. */
 int sacb_selftest_gemm(int device, int M, int N, int K, int a_mn_major, int b_mn_major, int b_r0, float *rel_err_out);
+/* same with an explicit tensor-core tile shape: bm = 64 | 128 rows, bn = 32 | 64 columns (32 only with a K-major B operand) */
+int sacb_selftest_gemm_tile(int device, int M, int N, int K, int a_mn_major, int b_mn_major, int b_r0, int bm, int bn, float *rel_err_out);
 
 #ifdef __cplusplus
 }

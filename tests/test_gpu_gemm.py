@@ -29,3 +29,17 @@ def test_tc_tile_operand_offset(b_mn, r0):
     err = ctypes.c_float()
     N_.check(N_.lib().sacb_selftest_gemm(0, 256, 17, 512, 0, b_mn, r0, ctypes.byref(err)))
     assert err.value < 2e-5, err.value
+
+
+@pytest.mark.parametrize("bm,bn", [(64, 64), (128, 32), (64, 32)])
+@pytest.mark.parametrize("M,N,K", [(256, 512, 512), (256, 512, 365), (100, 70, 45), (130, 65, 129), (512, 34, 512), (64, 32, 64)])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1)])
+def test_tc_tile_shapes(M, N, K, a_mn, b_mn, bm, bn):
+    """64-row tiles (tcgen05 M = 64: rows live in the lower half of each TMEM subpartition) and 32-column tiles."""
+    if bn == 32 and b_mn:
+        pytest.skip("32-column tiles need a K-major B operand")
+    import humanoid_walking_with_sac_b200 as hw
+    N_ = hw._native
+    err = ctypes.c_float()
+    N_.check(N_.lib().sacb_selftest_gemm_tile(0, M, N, K, a_mn, b_mn, 0, bm, bn, ctypes.byref(err)))
+    assert err.value < 2e-5, err.value
