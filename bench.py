@@ -191,9 +191,12 @@ def run_ours(args):
     h = agent._h
 
     def device_step():
-        N.check(lib.sacb_per_sample(h, 0, None, B, None, None, None, None, None, None, None))
-        N.check(lib.sacb_update(h, B, None, None, None, None, N.USE_LAST_SAMPLE | N.NO_LOSS_READBACK))
-        N.check(lib.sacb_per_update_from_td(h, 0, B))
+        if args.no_pipeline:      # the three calls back to back on one stream
+            N.check(lib.sacb_per_sample(h, 0, None, B, None, None, None, None, None, None, None))
+            N.check(lib.sacb_update(h, B, None, None, None, None, N.USE_LAST_SAMPLE | N.NO_LOSS_READBACK))
+            N.check(lib.sacb_per_update_from_td(h, 0, B))
+        else:                     # same work, the write-back and the next sample run under the tail of the update (second stream)
+            N.check(lib.sacb_per_step(h, B, None, N.NO_LOSS_READBACK))
 
     def barrier():
         agent.synchronize()
@@ -280,6 +283,8 @@ def run_ours(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": {"bf16x3": "f32 (bf16 hi/lo operand pairs, 3 tcgen05 MMAs per product, f32 accumulate in TMEM; f32 master weights / Adam)", "fp32": "f32 (FFMA on the bf16-pair operands)"}[args.math],
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "launch": args.launch, "math": args.math, "replicas": world,
+                           "step": "sample(256) -> update -> priority write-back, " + ("sequential on one stream" if args.no_pipeline else
+                                   "software-pipelined: write-back and the next sample run on a second stream once the TD errors exist (sacb_per_step; bitwise equal to the sequential order)"),
                            "l2_policy": "inputs larger than L2: 1M-row ring (2.9 GB) + 4 MB priority table re-read every step; weights/Adam state (63 MB) stay L2 resident by design"},
                 "e2e": {"value": e2e, "unit": "updates/s", "h2d_bytes_per_step": row_bytes + 8 * B, "d2h_bytes_per_step": 12},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu,
@@ -298,6 +303,7 @@ def main():
     ap.add_argument("--launch", default=os.environ.get("SACB_LAUNCH", "staged"), choices=["staged", "persistent"])
     ap.add_argument("--math", default=os.environ.get("SACB_MATH", "bf16x3"), choices=["bf16x3", "fp32"])
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="value: run sample / update / write-back sequentially on one stream")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -82,6 +82,7 @@ SIGNATURES = {
     "sacb_per_update": (I, [H, I, c_i64p, c_f32p, I64]),
     "sacb_per_update_final": (I, [H, I, c_i64p, c_f32p, I64]),
     "sacb_per_update_from_td": (I, [H, I, I64]),
+    "sacb_per_step": (I, [H, I64, c_f32p, U32]),
     "sacb_per_get_priorities": (I, [H, I, c_f32p, I64]),
     "sacb_per_set_priorities": (I, [H, I, c_f32p, c_f32p, I64]),
     "sacb_per_get_stats": (I, [H, I, ctypes.POINTER(PerStats)]),

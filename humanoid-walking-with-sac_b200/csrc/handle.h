@@ -84,6 +84,10 @@ struct ProgramInst {
     Stage *d_stages = nullptr;
     Program prog{};
     cudaGraphExec_t graph = nullptr;
+    // the same step as two graphs split behind the critic-loss stage (TD errors exist): sacb_per_step runs the priority
+    // write-back and the next prioritized sample on a second stream while the tail of the update computes
+    cudaGraphExec_t graph_part[2] = {nullptr, nullptr};
+    int split = -1;
     int n_tiles_total = 0, max_stage_tiles = 0;
     int kernels_per_step = 0;
 };
@@ -94,6 +98,9 @@ struct sacb_handle_s {
     sacb_config cfg;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;      // prioritized replay work that overlaps the update (sacb_per_step)
+    cudaEvent_t ev_td = nullptr, ev_sampled = nullptr;
+    int64_t sample_k = 0;                // rows of the minibatch the last prioritized sample left on the device (0: none)
     sacb::Layout L;
     float *arena = nullptr, *ws = nullptr;
     unsigned int *barrier = nullptr;
@@ -139,9 +146,12 @@ const void *update_kernel_for(int math_mode);
 // program.cu
 int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out);
 int launch_program(sacb_handle h, ProgramInst &p);
+int launch_program_part(sacb_handle h, ProgramInst &p, int part);   // 0: up to and including the critic-loss stage, 1: the rest
 void free_programs(sacb_handle h);
 int check_error_flag(sacb_handle h);
 // replay.cu
 int replay_create(sacb_handle h);
 void replay_destroy(sacb_handle h);
+int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B, int64_t *k_out);   // kernels of one sample() call
+int per_writeback_launch(sacb_handle h, cudaStream_t st, int64_t B);                                 // priorities <- |td| of the last update
 }  // namespace sacb

@@ -660,6 +660,7 @@ struct Builder {
 void free_programs(sacb_handle h) {
     for (auto &kv : h->programs) {
         if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
+        for (auto g : kv.second.graph_part) if (g) cudaGraphExecDestroy(g);
         cudaFree(kv.second.d_tasks); cudaFree(kv.second.d_stages);
     }
     h->programs.clear();
@@ -813,6 +814,35 @@ int launch_program(sacb_handle h, ProgramInst &p) {
     h->kernel_launches += p.kernels_per_step;
     if (p.graph) { SACB_CUDA(cudaGraphLaunch(p.graph, h->stream)); return SACB_OK; }
     return record_step(h, p);
+}
+
+int launch_program_part(sacb_handle h, ProgramInst &p, int part) {
+    if (h->cfg.launch_mode != SACB_LAUNCH_STAGED) {      // a single cooperative launch cannot be split: part 0 is the whole step
+        return part == 0 ? launch_program(h, p) : SACB_OK;
+    }
+    const int ns = (int)p.stages.size();
+    if (p.split < 0) {
+        for (int s = 0; s < ns && p.split < 0; s++)
+            for (int k = p.stages[s].task_begin; k < p.stages[s].task_end; k++)
+                if (p.tasks[k].type == T_TARGET_LOSS) { p.split = s + 1; break; }
+        if (p.split < 0) return fail(SACB_ERR_STATE, "program has no critic-loss stage");
+        for (int part_i = 0; part_i < 2; part_i++) {
+            const int s0 = part_i ? p.split : 0, s1 = part_i ? ns : p.split;
+            cudaGraph_t graph = nullptr;
+            if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) break;
+            int rc = SACB_OK;
+            for (int s = s0; s < s1 && rc == SACB_OK; s++) rc = launch_stage(h, p, s, h->use_pdl != 0);
+            const cudaError_t e2 = cudaStreamEndCapture(h->stream, &graph);
+            if (rc == SACB_OK && e2 == cudaSuccess && graph && cudaGraphInstantiate(&p.graph_part[part_i], graph, 0) != cudaSuccess) p.graph_part[part_i] = nullptr;
+            if (graph) cudaGraphDestroy(graph);
+        }
+        cudaGetLastError();
+    }
+    const int s0 = part ? p.split : 0, s1 = part ? ns : p.split;
+    h->kernel_launches += s1 - s0;
+    if (p.graph_part[part]) { SACB_CUDA(cudaGraphLaunch(p.graph_part[part], h->stream)); return SACB_OK; }
+    for (int s = s0; s < s1; s++) { int rc = launch_stage(h, p, s, h->use_pdl != 0); if (rc) return rc; }
+    return SACB_OK;
 }
 
 }  // namespace sacb

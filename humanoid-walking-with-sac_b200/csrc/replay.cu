@@ -5,12 +5,12 @@
 // contiguous ~2.9 KB read (Humanoid), gathered by one warp with coalesced loads.
 //
 // PER sampling reproduces np.random.choice(len, B, p=probs) bit-for-bit downstream of the p**alpha table:
-//   per_sum_*    float32 total with numpy's pairwise-summation tree (exact same association)
-//   per_chunk    probs = p_alpha / total (float32), float64 chunk sums, count of "fine" elements
-//   per_carry    exclusive scan of the chunk sums
-//   per_search   per-sample inverse-CDF search + provable ambiguity test (see DESIGN.md "PER exactness")
-//   per_exact    sequential float64 cumsum (numpy's own order) only for samples the test could not certify
-//   per_finish   IS weights (N p)^-beta / max, logical indices, ring slots for the update's gather
+// Three launches per sample() call; the last CTA of each grid to finish runs the serial step behind the parallel pass:
+//   per_sum      float32 total with numpy's pairwise-summation tree (exact same association): CTA subtrees, then the top
+//   per_chunk    probs = p_alpha / total (float32), float64 chunk sums, count of "fine" elements; then the exclusive scan
+//   per_search   per-sample inverse-CDF search + provable ambiguity test (see DESIGN.md "PER exactness"); then the sequential
+//                float64 cumsum (numpy's own order) for samples the test could not certify, IS weights (N p)^-beta / max,
+//                logical indices, ring slots for the update's gather
 #include <cmath>
 #include <cstring>
 #include <algorithm>
@@ -42,6 +42,7 @@ constexpr int kChunk = 1024;          // elements per scan chunk (one warp, 32 p
 constexpr int kSumLeafMax = 128;      // numpy PW_BLOCKSIZE
 constexpr int kSumBlockMax = 4096;    // elements handled by one CTA of per_sum_blocks
 constexpr int kSumHeap = 256;         // heap slots per CTA subtree (depth <= 7)
+constexpr int kCarrySmem = 2048;      // chunk prefixes staged in shared memory by per_search when they fit (capacity <= 2 M)
 
 struct PerWs {            // device workspace of one agent's PER sampler
     float *block_vals;    // heap of the top-level summation tree
@@ -50,6 +51,7 @@ struct PerWs {            // device workspace of one agent's PER sampler
     double *chunk_carry;  // [n_chunks + 1] exclusive, last = cdf_last
     int *chunk_fine;      // [n_chunks]
     int *counters;        // [0] total fine, [1] flagged count, [2] exact fallbacks run
+    int *tickets;         // completion tickets of the three sample() kernels (kTicketInts each)
     double *cdf_exact;    // [capacity] only touched by per_exact
     double *u;            // [maxB]
     int *flagged;         // [maxB]
@@ -77,46 +79,52 @@ __host__ __device__ inline bool pw_node(int64_t root_start, int64_t root_n, int 
     return true;
 }
 
-// one numpy leaf (n <= 128) by one warp: data staged in smem, lanes 0..7 own the 8 accumulators
-__device__ __forceinline__ float pw_leaf(const float *a, int n, float *sbuf, int lane) {
-    for (int i = lane; i < n; i += 32) sbuf[i] = a[i];
-    __syncwarp();
+// one numpy leaf (n <= 128) by 8 lanes (a quarter warp): lane k owns accumulator r[k] = a[k] + a[k+8] + a[k+16] + ... in that
+// order; all of its <= 16 loads are issued before the first add.  Result valid in lane 0 of the group.
+__device__ __forceinline__ float pw_leaf8(const float *a, int n, int k /* lane inside the 8-lane group */) {
+    const unsigned lane = threadIdx.x & 31u, gmask = 0xffu << (lane & 24u);
     float res = 0.f;
     if (n < 8) {
-        if (lane == 0) for (int i = 0; i < n; i++) res = __fadd_rn(res, sbuf[i]);
-    } else {
-        float r = 0.f;
-        const int full = n - (n % 8);
-        if (lane < 8) { r = sbuf[lane]; for (int i = 8 + lane; i < full; i += 8) r = __fadd_rn(r, sbuf[i]); }
-        const float r1 = __shfl_down_sync(0xffffffffu, r, 1);
-        float p = __fadd_rn(r, r1);                       // lanes 0,2,4,6: r0+r1, r2+r3, r4+r5, r6+r7
-        const float p2 = __shfl_down_sync(0xffffffffu, p, 2);
-        float q = __fadd_rn(p, p2);                       // lanes 0,4: (r0+r1)+(r2+r3), (r4+r5)+(r6+r7)
-        const float q4 = __shfl_down_sync(0xffffffffu, q, 4);
-        res = __fadd_rn(q, q4);
-        if (lane == 0) for (int i = full; i < n; i++) res = __fadd_rn(res, sbuf[i]);
+        if (k == 0) for (int i = 0; i < n; i++) res = __fadd_rn(res, a[i]);
+        return res;
     }
-    __syncwarp();
-    return res;   // valid in lane 0
+    const int full = n - (n % 8), cnt = full >> 3;      // cnt <= 16 terms per accumulator
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = i < cnt ? __ldg(a + k + 8 * i) : 0.f;
+    float r = v[0];
+#pragma unroll
+    for (int i = 1; i < 16; i++) if (i < cnt) r = __fadd_rn(r, v[i]);
+    const float r1 = __shfl_down_sync(gmask, r, 1, 8);
+    const float p = __fadd_rn(r, r1);                       // k = 0,2,4,6: r0+r1, r2+r3, r4+r5, r6+r7
+    const float p2 = __shfl_down_sync(gmask, p, 2, 8);
+    const float q = __fadd_rn(p, p2);                       // k = 0,4: (r0+r1)+(r2+r3), (r4+r5)+(r6+r7)
+    const float q4 = __shfl_down_sync(gmask, q, 4, 8);
+    res = __fadd_rn(q, q4);
+    if (k == 0) for (int i = full; i < n; i++) res = __fadd_rn(res, a[i]);
+    return res;
 }
 
-// sum of the subtree (start,n), n <= kSumBlockMax, by one CTA (256 threads): leaves by warps, then bottom-up heap
-__device__ float pw_block_sum(const float *a, int64_t start, int n, float *s_heap, unsigned char *s_state, float *s_leafbuf) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // classify heap nodes: 0 = absent, 1 = leaf, 2 = internal
+// sum of the subtree (start,n), n <= kSumBlockMax, by one CTA (256 threads): leaves by 8-lane groups, then bottom-up heap
+__device__ float pw_block_sum(const float *a, int64_t start, int n, float *s_heap, unsigned char *s_state, int *s_leaf) {
+    const int tid = threadIdx.x;
+    __shared__ int s_nleaf;
+    if (tid == 0) s_nleaf = 0;
+    __syncthreads();
+    // classify heap nodes: 0 = absent, 1 = leaf, 2 = internal; leaves are queued (start offset and length packed)
     for (unsigned id = 1 + tid; id < kSumHeap; id += blockDim.x) {
         int64_t s, m; bool leaf = false;
         const bool ex = pw_node(start, n, kSumLeafMax, id, s, m, leaf);
         s_state[id] = ex ? (leaf ? 1 : 2) : 0;
+        if (ex && leaf) { const int slot = atomicAdd(&s_nleaf, 1); s_leaf[3 * slot] = (int)id; s_leaf[3 * slot + 1] = (int)(s - start); s_leaf[3 * slot + 2] = (int)m; }
     }
     __syncthreads();
-    for (unsigned id = 1 + warp; id < kSumHeap; id += blockDim.x / 32) {
-        if (s_state[id] == 1) {
-            int64_t s, m; bool leaf;
-            pw_node(start, n, kSumLeafMax, id, s, m, leaf);
-            const float v = pw_leaf(a + s, (int)m, s_leafbuf + warp * kSumLeafMax, lane);
-            if (lane == 0) s_heap[id] = v;
-        }
+    const int group = tid >> 3, k = tid & 7, n_groups = blockDim.x >> 3;
+    for (int i0 = 0; i0 < s_nleaf; i0 += n_groups) {      // warp-uniform trip count
+        const int i = i0 + group;
+        const bool on = i < s_nleaf;
+        const float v = pw_leaf8(a + start + (on ? s_leaf[3 * i + 1] : 0), on ? s_leaf[3 * i + 2] : 0, k);
+        if (on && k == 0) s_heap[s_leaf[3 * i]] = v;
     }
     __syncthreads();
     for (int depth = 6; depth >= 0; depth--) {      // heap ids [2^depth, 2^(depth+1))
@@ -127,51 +135,112 @@ __device__ float pw_block_sum(const float *a, int64_t start, int n, float *s_hea
     return s_heap[1];
 }
 
-// grid = top heap size; CTA id+1 = heap id of the top tree (leaf threshold kSumBlockMax)
-__global__ void __launch_bounds__(256) per_sum_blocks(const float *p_alpha, int64_t n, float *top_vals) {
+// The last CTA of a grid to finish (completion ticket: results, __threadfence, atomic) runs the grid's serial tail, so a
+// reduction and its finishing step are ONE launch.  The ticket resets itself for the next launch.
+// Two levels so that same-address atomics (which serialise in L2, ~14 ns each) stay short: CTAs take a ticket of their group
+// (blockIdx % kTicketGroups, counters 128 B apart), the last CTA of a group takes one of the final counter.
+constexpr int kTicketGroups = 8, kTicketStride = 32;      // ints
+constexpr int kTicketInts = (kTicketGroups + 1) * kTicketStride;
+__device__ __forceinline__ bool last_block_done(int *ticket) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const int G = min(kTicketGroups, (int)gridDim.x), g = blockIdx.x % G;
+        const int group_size = ((int)gridDim.x - g + G - 1) / G;
+        int last = 0;
+        if (atomicAdd(ticket + g * kTicketStride, 1) == group_size - 1) {
+            ticket[g * kTicketStride] = 0;
+            __threadfence();
+            if (atomicAdd(ticket + kTicketGroups * kTicketStride, 1) == G - 1) { ticket[kTicketGroups * kTicketStride] = 0; last = 1; }
+        }
+        s_last = last;
+    }
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last != 0;
+}
+
+__device__ __forceinline__ double uniform_of(uint64_t seed, uint64_t counter, int j) {      // splitmix64 -> [0, 1) with 53 bits
+    uint64_t x = seed ^ (counter * 0x9E3779B97F4A7C15ull + (uint64_t)j * 0xBF58476D1CE4E5B9ull);
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
+    return (double)(x >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// grid = top heap size; CTA id+1 = heap id of the top tree (leaf threshold kSumBlockMax).  The last CTA to finish adds the
+// top of the tree (numpy's association) and publishes the float32 total.  draw_B > 0: the B uniforms of this call are drawn here.
+__global__ void __launch_bounds__(256) per_sum(const float *p_alpha, int64_t n, int top_depth, float *top_vals, float *total, int *ticket,
+                                               double *u, int draw_B, uint64_t seed, uint64_t counter) {
     SACB_PDL_ENTER();
     __shared__ float s_heap[kSumHeap];
     __shared__ unsigned char s_state[kSumHeap];
-    __shared__ float s_leafbuf[8 * kSumLeafMax];
+    __shared__ int s_leaf[3 * 128];          // a CTA subtree of <= kSumBlockMax elements has at most 128 leaves
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < draw_B; j += gridDim.x * blockDim.x) u[j] = uniform_of(seed, counter, j);
     const unsigned id = blockIdx.x + 1;
     int64_t s, m; bool leaf = false;
-    if (!pw_node(0, n, kSumBlockMax, id, s, m, leaf) || !leaf) return;
-    const float v = pw_block_sum(p_alpha, s, (int)m, s_heap, s_state, s_leafbuf);
-    if (threadIdx.x == 0) top_vals[id] = v;
-}
-
-__global__ void __launch_bounds__(1024) per_sum_top(int64_t n, int top_depth, float *top_vals, float *total) {
-    SACB_PDL_ENTER();
+    if (pw_node(0, n, kSumBlockMax, id, s, m, leaf) && leaf) {      // CTA-uniform
+        const float v = pw_block_sum(p_alpha, s, (int)m, s_heap, s_state, s_leaf);
+        if (threadIdx.x == 0) top_vals[id] = v;
+    }
+    if (!last_block_done(ticket)) return;
+    // top of the tree (heap ids < 2^(top_depth+1) <= 4096) in shared memory: one read of the CTA results, then level by level
+    __shared__ float s_top[4096];
+    __shared__ unsigned char s_tstate[4096];
+    const unsigned n_ids = 2u << top_depth;
+    for (unsigned k = 1 + threadIdx.x; k < n_ids; k += blockDim.x) {
+        int64_t s2, m2; bool lf = false;
+        const bool ex = pw_node(0, n, kSumBlockMax, k, s2, m2, lf);
+        s_tstate[k] = ex ? (lf ? 1 : 2) : 0;
+        if (ex && lf) s_top[k] = __ldcg(top_vals + k);
+    }
+    __syncthreads();
     for (int depth = top_depth; depth >= 0; depth--) {
-        for (unsigned id = (1u << depth) + threadIdx.x; id < (2u << depth); id += blockDim.x) {
-            int64_t s, m; bool leaf = false;
-            if (pw_node(0, n, kSumBlockMax, id, s, m, leaf) && !leaf) top_vals[id] = __fadd_rn(top_vals[2 * id], top_vals[2 * id + 1]);
-        }
+        for (unsigned k = (1u << depth) + threadIdx.x; k < (2u << depth); k += blockDim.x)
+            if (s_tstate[k] == 2) s_top[k] = __fadd_rn(s_top[2 * k], s_top[2 * k + 1]);
         __syncthreads();
     }
-    if (threadIdx.x == 0) *total = top_vals[1];
+    if (threadIdx.x == 0) *total = s_top[1];
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // chunked float64 scan
 // ---------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool is_fine(double p) {      // not an integer multiple of 2^-52
-    const double x = p * 4503599627370496.0;
-    return x != floor(x);
+// "fine" = the float32 probability, as a float64, is not an integer multiple of 2^-52 (only such elements can make a float64
+// partial sum below 1 inexact).  Integer test on the float32 bits: lowest set bit of (2^23 | M) * 2^(E-150) below 2^-52.
+__device__ __forceinline__ bool is_fine(float q) {
+    const uint32_t b = __float_as_uint(q) & 0x7fffffffu;
+    if (b == 0u) return false;
+    const uint32_t E = b >> 23;
+    const uint32_t m = (b & 0x7fffffu) | (E ? 0x800000u : 0u);
+    return (int)(E ? E : 1u) - 150 + (__ffs((int)m) - 1) < -52;
 }
 
-// lane-local pass over 32 consecutive probs of a chunk; returns the lane sum (sequential order), counts fine elements
-__device__ __forceinline__ double lane_pass(const float *p_alpha, int64_t base, int64_t n, float total, int &fine) {
+// the 32 consecutive probabilities probs = p_alpha / total (float32 divide: `probs /= probs.sum()`) owned by a lane; 0 beyond n
+__device__ __forceinline__ void lane_probs(const float *p_alpha, int64_t base, int64_t n, float total, float (&q)[32]) {
+    if (base + 32 <= n) {
+        const float4 *src = reinterpret_cast<const float4 *>(p_alpha + base);      // base is a multiple of 32 floats
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) v[j] = __ldg(src + j);
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            q[4 * j] = __fdiv_rn(v[j].x, total); q[4 * j + 1] = __fdiv_rn(v[j].y, total);
+            q[4 * j + 2] = __fdiv_rn(v[j].z, total); q[4 * j + 3] = __fdiv_rn(v[j].w, total);
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 32; j++) q[j] = base + j < n ? __fdiv_rn(p_alpha[base + j], total) : 0.f;
+    }
+}
+
+// lane-local pass over its 32 probabilities: the lane sum in sequential order (adding the zeros beyond n is exact), fine count
+__device__ __forceinline__ double lane_pass(const float (&q)[32], int &fine) {
     double acc = 0.0;
     fine = 0;
-#pragma unroll 8
+#pragma unroll
     for (int j = 0; j < 32; j++) {
-        const int64_t i = base + j;
-        if (i < n) {
-            const double p = (double)__fdiv_rn(p_alpha[i], total);     // probs /= probs.sum()  (float32 divide)
-            fine += is_fine(p) ? 1 : 0;
-            acc = __dadd_rn(acc, p);
-        }
+        fine += is_fine(q[j]) ? 1 : 0;
+        acc = __dadd_rn(acc, (double)q[j]);
     }
     return acc;
 }
@@ -188,110 +257,73 @@ __device__ __forceinline__ double warp_excl_scan(double v, int lane, double &war
     return lane == 0 ? 0.0 : ex;
 }
 
-__global__ void __launch_bounds__(256) per_chunk(const float *p_alpha, int64_t n, const float *total, double *chunk_sum, int *chunk_fine) {
+// exclusive scan of the chunk sums by ONE CTA (blockDim.x <= 1024): 4 consecutive entries per thread, shuffle scan inside a
+// warp, warp totals through shared memory, running carry between passes of 4 * blockDim.x entries.  A prefix is at most
+// 32 (lane) + 5 (warp) of the chunk sum + 4 + 5 + 32 + passes additions deep (the certification bound assumes <= 128).
+__device__ void carry_scan(const double *chunk_sum, const int *chunk_fine, int n_chunks, double *carry, int *counters) {
+    __shared__ double s_w[32];
+    __shared__ int s_wf[32];
+    __shared__ double s_run;
+    __shared__ int s_frun;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    if (tid == 0) { s_run = 0.0; s_frun = 0; }
+    __syncthreads();
+    for (int base = 0; base < n_chunks; base += 4 * blockDim.x) {
+        const int i0 = base + 4 * tid;
+        double v[4]; int f[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { v[j] = i0 + j < n_chunks ? __ldcg(chunk_sum + i0 + j) : 0.0; f[j] = i0 + j < n_chunks ? __ldcg(chunk_fine + i0 + j) : 0; }
+        double inc[4];
+        inc[0] = v[0]; inc[1] = __dadd_rn(inc[0], v[1]); inc[2] = __dadd_rn(inc[1], v[2]); inc[3] = __dadd_rn(inc[2], v[3]);
+        int ft = f[0] + f[1] + f[2] + f[3];
+        double wt;
+        const double ex = warp_excl_scan(inc[3], lane, wt);      // exclusive over the lanes' totals, wt = warp total
+        int fex = ft;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, fex, o); if (lane >= o) fex += t; }
+        const int fwt = __shfl_sync(0xffffffffu, fex, 31);
+        fex -= ft;
+        if (lane == 0) { s_w[warp] = wt; s_wf[warp] = fwt; }
+        __syncthreads();
+        double wpre = s_run; int fpre = s_frun;
+        for (int w = 0; w < warp; w++) { wpre = __dadd_rn(wpre, s_w[w]); fpre += s_wf[w]; }
+        const double pre = __dadd_rn(wpre, ex);
+#pragma unroll
+        for (int j = 0; j < 4; j++) if (i0 + j < n_chunks) carry[i0 + j] = j ? __dadd_rn(pre, inc[j - 1]) : pre;
+        __syncthreads();
+        if (tid == 0) {
+            double r = s_run; int fr = s_frun;
+            for (int w = 0; w < nw; w++) { r = __dadd_rn(r, s_w[w]); fr += s_wf[w]; }
+            s_run = r; s_frun = fr;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) { carry[n_chunks] = s_run; counters[0] = s_frun; counters[1] = 0; }
+}
+
+// one warp per chunk of 1024 probabilities: float64 chunk sum + count of "fine" elements; the last CTA scans the chunk sums
+__global__ void __launch_bounds__(256) per_chunk(const float *p_alpha, int64_t n, const float *total, double *chunk_sum, int *chunk_fine,
+                                                 int n_chunks, double *carry, int *counters, int *ticket) {
     SACB_PDL_ENTER();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t chunk = (int64_t)blockIdx.x * 8 + warp;
-    if (chunk * kChunk >= n) return;
-    int fine;
-    const double v = lane_pass(p_alpha, chunk * kChunk + lane * 32, n, *total, fine);
-    double wt;
-    warp_excl_scan(v, lane, wt);
-    for (int o = 16; o > 0; o >>= 1) fine += __shfl_xor_sync(0xffffffffu, fine, o);
-    if (lane == 0) { chunk_sum[chunk] = wt; chunk_fine[chunk] = fine; }
-}
-
-// single CTA: exclusive Kogge-Stone scan of the chunk sums (n_chunks <= 1024 per pass, looped with a running carry)
-__global__ void __launch_bounds__(1024) per_carry(const double *chunk_sum, const int *chunk_fine, int n_chunks, double *carry, int *counters) {
-    SACB_PDL_ENTER();
-    __shared__ double s[1024];
-    __shared__ int s_f[1024];
-    __shared__ double s_run;
-    __shared__ int s_frun;
-    if (threadIdx.x == 0) { s_run = 0.0; s_frun = 0; }
-    __syncthreads();
-    for (int base = 0; base < n_chunks; base += 1024) {
-        const int i = base + threadIdx.x;
-        double v = i < n_chunks ? chunk_sum[i] : 0.0;
-        int f = i < n_chunks ? chunk_fine[i] : 0;
-        s[threadIdx.x] = v; s_f[threadIdx.x] = f;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            double t = 0.0; int tf = 0;
-            if (threadIdx.x >= o) { t = s[threadIdx.x - o]; tf = s_f[threadIdx.x - o]; }
-            __syncthreads();
-            if (threadIdx.x >= o) { s[threadIdx.x] = __dadd_rn(t, s[threadIdx.x]); s_f[threadIdx.x] += tf; }
-            __syncthreads();
-        }
-        const double run = s_run; const int frun = s_frun;
-        if (i < n_chunks) carry[i] = __dadd_rn(run, threadIdx.x ? s[threadIdx.x - 1] : 0.0);   // exclusive prefix
-        __syncthreads();
-        if (threadIdx.x == 1023) { s_run = __dadd_rn(run, s[1023]); s_frun = frun + s_f[1023]; }
-        __syncthreads();
+    if (chunk * kChunk < n) {
+        int fine;
+        float q[32];
+        lane_probs(p_alpha, chunk * kChunk + lane * 32, n, *total, q);
+        const double v = lane_pass(q, fine);
+        double wt;
+        warp_excl_scan(v, lane, wt);
+        for (int o = 16; o > 0; o >>= 1) fine += __shfl_xor_sync(0xffffffffu, fine, o);
+        if (lane == 0) { chunk_sum[chunk] = wt; chunk_fine[chunk] = fine; }
     }
-    if (threadIdx.x == 0) { carry[n_chunks] = s_run; counters[0] = s_frun; counters[1] = 0; }
-}
-
-// one warp per sample
-__global__ void __launch_bounds__(256) per_search(const float *p_alpha, int64_t n, const float *total, const double *carry, int n_chunks,
-                                                  const double *u, int B, const int *counters, int64_t *idx_out, int *flagged, int *flag_count) {
-    SACB_PDL_ENTER();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int j = blockIdx.x * 8 + warp;
-    if (j >= B) return;
-    const double last = carry[n_chunks];
-    const double uu = u[j];
-    // provable bound on |cdf_parallel - cdf_sequential| / last  (DESIGN.md): zero when no element has bits below 2^-52
-    const int F = counters[0];
-    const double window = F == 0 ? 0.0 : ((128.0 * (double)F + 64.0) * 2.220446049250313e-16) / last * 4.0 + 4.440892098500626e-16;
-    // chunk: last c with carry[c]/last <= u
-    int lo = 0, hi = n_chunks - 1;
-    while (lo < hi) {
-        const int mid = (lo + hi + 1) >> 1;
-        if (__ddiv_rn(carry[mid], last) <= uu) lo = mid; else hi = mid - 1;
-    }
-    const int c = lo;
-    int fine;
-    const int64_t base = (int64_t)c * kChunk + lane * 32;
-    const double v = lane_pass(p_alpha, base, n, *total, fine);
-    double wt;
-    const double ex = warp_excl_scan(v, lane, wt);
-    // second pass: running cdf inside the lane, count elements with cdf <= u, track the distance to the nearest boundary
-    double acc = __dadd_rn(carry[c], ex);
-    double mind = fabs(__ddiv_rn(carry[c], last) - uu);   // boundary with the previous chunk
-    if (c == 0) mind = 1.0;
-    int cnt = 0;
-    const float tot = *total;
-    for (int k = 0; k < 32; k++) {
-        const int64_t i = base + k;
-        if (i < n) {
-            acc = __dadd_rn(acc, (double)__fdiv_rn(p_alpha[i], tot));
-            const double cn = __ddiv_rn(acc, last);
-            cnt += (cn <= uu) ? 1 : 0;
-            mind = fmin(mind, fabs(cn - uu));
-        }
-    }
-    for (int o = 16; o > 0; o >>= 1) {
-        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-        mind = fmin(mind, __shfl_xor_sync(0xffffffffu, mind, o));
-    }
-    if (lane == 0) {
-        int64_t idx = (int64_t)c * kChunk + cnt;
-        const bool flag = (F != 0 && mind <= window) || idx >= n;
-        if (idx >= n) idx = n - 1;
-        idx_out[j] = idx;
-        flagged[j] = flag ? 1 : 0;
-        if (flag) atomicAdd(flag_count, 1);
-    }
+    if (!last_block_done(ticket)) return;
+    carry_scan(chunk_sum, chunk_fine, n_chunks, carry, counters);
 }
 
 // numpy's own algorithm, run only when a sample could not be certified: sequential float64 cumsum, /= last, searchsorted right
-__global__ void __launch_bounds__(32) per_exact(const float *p_alpha, int64_t n, const float *total, double *cdf, const double *u, int B,
-                                                 const int *flagged, int64_t *idx_out, int *counters) {
-    SACB_PDL_ENTER();
-    if (counters[1] == 0) return;
-    const int lane = threadIdx.x;
-    const float tot = *total;
+__device__ void exact_pass(const float *p_alpha, int64_t n, float tot, double *cdf, const double *u, int B, const int *flagged, int64_t *idx_out, int *counters) {
+    const int lane = threadIdx.x;      // warp 0 only
     if (lane == 0) {
         double acc = 0.0;
         for (int64_t i = 0; i < n; i++) { acc = __dadd_rn(acc, (double)__fdiv_rn(p_alpha[i], tot)); cdf[i] = acc; }
@@ -301,7 +333,7 @@ __global__ void __launch_bounds__(32) per_exact(const float *p_alpha, int64_t n,
     __threadfence_block();
     const double last = cdf[n - 1];
     for (int j = lane; j < B; j += 32) {
-        if (!flagged[j]) continue;
+        if (!__ldcg(flagged + j)) continue;
         const double uu = u[j];
         int64_t lo = 0, hi = n;
         while (lo < hi) {
@@ -312,43 +344,115 @@ __global__ void __launch_bounds__(32) per_exact(const float *p_alpha, int64_t n,
     }
 }
 
-// single CTA: IS weights (replay_buffer.py:67-68), ring slots for the gather
-__global__ void __launch_bounds__(1024) per_finish(const float *p_alpha, int64_t n, const float *total, const int64_t *idx, int B, float neg_beta,
-                                                    float *weights, int32_t *slots, float *isw_ws, int64_t *idx_copy) {
+// one warp per sample: inverse-CDF search + ambiguity test.  The last CTA to finish runs the serial tail of sample():
+// the exact pass for flagged samples (rare), IS weights (replay_buffer.py:67-68), ring slots for the update's gather.
+__global__ void __launch_bounds__(256) per_search(const float *p_alpha, int64_t n, const float *total, const double *carry, int n_chunks,
+                                                  const double *u, int B, int *counters, int64_t *idx_out, int *flagged, int *ticket,
+                                                  double *cdf_exact, float neg_beta, float *weights, int32_t *slots, float *isw_ws, int64_t *idx_copy) {
     SACB_PDL_ENTER();
-    __shared__ float s_max[32];
-    float w = -INFINITY;
-    const int j = threadIdx.x;
-    if (j < B) {
-        const float prob = __fdiv_rn(p_alpha[idx[j]], *total);
-        w = powf((float)n * prob, neg_beta);
-        slots[j] = (int32_t)idx[j];
-        idx_copy[j] = idx[j];      // indices of the last sample (update_priorities without an index argument, TD write-back)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + warp;
+    const float tot = *total;
+    // the chunk prefixes in shared memory (one coalesced read instead of ten dependent L2 round trips per sample)
+    __shared__ double s_carry[kCarrySmem];
+    const bool staged = n_chunks + 1 <= kCarrySmem;
+    if (staged) for (int i = threadIdx.x; i <= n_chunks; i += blockDim.x) s_carry[i] = carry[i];
+    __syncthreads();
+    const double *cr = staged ? s_carry : carry;
+    if (j < B) {      // warp-uniform
+        const double last = cr[n_chunks];
+        const double uu = u[j];
+        // cdf / last <= u (an IEEE divide per probed element, like numpy's cdf /= cdf[-1]) decided without the divide unless the
+        // element is within 2^-49 relative of u * last: outside that band the rounded quotient cannot land on the other side of u
+        const double t = __dmul_rn(uu, last), t_lo = __dmul_rn(t, 1.0 - 1.7763568394002505e-15), t_hi = __dmul_rn(t, 1.0 + 1.7763568394002505e-15);
+        auto le_u = [&](double c) { return c < t_lo ? true : (c > t_hi ? false : __ddiv_rn(c, last) <= uu); };
+        // provable bound on |cdf_parallel - cdf_sequential| / last  (DESIGN.md): zero when no element has bits below 2^-52
+        const int F = counters[0];
+        const double window = F == 0 ? 0.0 : ((128.0 * (double)F + 64.0) * 2.220446049250313e-16) / last * 4.0 + 4.440892098500626e-16 + 1e-13;
+        // chunk: last c with carry[c]/last <= u
+        int lo = 0, hi = n_chunks - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (le_u(cr[mid])) lo = mid; else hi = mid - 1;
+        }
+        const int c = lo;
+        int fine;
+        const int64_t base = (int64_t)c * kChunk + lane * 32;
+        float q[32];
+        lane_probs(p_alpha, base, n, tot, q);
+        const double v = lane_pass(q, fine);
+        double wt;
+        const double ex = warp_excl_scan(v, lane, wt);
+        // running cdf inside the lane (sequential order), count the elements with cdf <= u
+        const double start = __dadd_rn(cr[c], ex);
+        const int64_t rem = n - base;
+        const int mine = rem >= 32 ? 32 : (rem > 0 ? (int)rem : 0);      // elements of this lane that exist
+        int cnt = 0;
+        {
+            double acc = start;
+#pragma unroll
+            for (int k = 0; k < 32; k++) {
+                acc = __dadd_rn(acc, (double)q[k]);
+                cnt += (k < mine && le_u(acc)) ? 1 : 0;
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        // distance from u to the nearest cdf value.  The cdf is monotone (up to rounding between lanes), so the nearest values
+        // sit at the crossing: chunk elements cnt-2 .. cnt+1, plus the boundary with the previous chunk when the crossing is
+        // at the chunk start.  Only those take the divide.
+        double mind = 1.0;
+        if (c > 0 && cnt <= 1) mind = fabs(__ddiv_rn(cr[c], last) - uu);
+        for (int e = cnt - 2; e <= cnt + 1; e++) {
+            if (e < 0 || (e >> 5) != lane || (e & 31) >= mine) continue;
+            double acc = start;
+            const int ke = e & 31;
+#pragma unroll
+            for (int k = 0; k < 32; k++) if (k <= ke) acc = __dadd_rn(acc, (double)q[k]);
+            mind = fmin(mind, fabs(__ddiv_rn(acc, last) - uu));
+        }
+        for (int o = 16; o > 0; o >>= 1) mind = fmin(mind, __shfl_xor_sync(0xffffffffu, mind, o));
+        if (lane == 0) {
+            int64_t idx = (int64_t)c * kChunk + cnt;
+            const bool flag = (F != 0 && mind <= window) || idx >= n;
+            if (idx >= n) idx = n - 1;
+            idx_out[j] = idx;
+            flagged[j] = flag ? 1 : 0;
+            if (flag) atomicAdd(counters + 1, 1);
+        }
     }
-    float m = w;
+    if (!last_block_done(ticket)) return;
+    // ---- serial tail (one CTA) ----
+    if (__ldcg(counters + 1) != 0) {      // CTA-uniform
+        if (threadIdx.x < 32) exact_pass(p_alpha, n, tot, cdf_exact, u, B, flagged, idx_out, counters);
+        __threadfence_block();
+        __syncthreads();
+    }
+    __shared__ float s_max[32];
+    float m = -INFINITY;
+    for (int q = threadIdx.x; q < B; q += blockDim.x) {
+        const int64_t ix = __ldcg(idx_out + q);
+        const float prob = __fdiv_rn(p_alpha[ix], tot);
+        const float w = powf((float)n * prob, neg_beta);
+        weights[q] = w;                // unnormalised for now (same thread rewrites it below)
+        m = fmaxf(m, w);
+        slots[q] = (int32_t)ix;
+        idx_copy[q] = ix;              // indices of the last sample (update_priorities without an index argument, TD write-back)
+    }
     for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = m;
+    if (lane == 0) s_max[warp] = m;
     __syncthreads();
     if (threadIdx.x < 32) {
-        m = s_max[threadIdx.x];
+        m = threadIdx.x < (blockDim.x >> 5) ? s_max[threadIdx.x] : -INFINITY;
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         if (threadIdx.x == 0) s_max[0] = m;
     }
     __syncthreads();
-    if (j < B) {
-        const float wn = __fdiv_rn(w, s_max[0]);
-        weights[j] = wn;
-        if (isw_ws) isw_ws[j] = wn;
+    const float wmax = s_max[0];
+    for (int q = threadIdx.x; q < B; q += blockDim.x) {
+        const float wn = __fdiv_rn(weights[q], wmax);
+        weights[q] = wn;
+        if (isw_ws) isw_ws[q] = wn;
     }
-}
-
-__global__ void per_uniform_draw(double *u, int B, uint64_t seed, uint64_t counter) {
-    SACB_PDL_ENTER();
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= B) return;
-    uint64_t x = seed ^ (counter * 0x9E3779B97F4A7C15ull + (uint64_t)j * 0xBF58476D1CE4E5B9ull);   // splitmix64
-    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull; x ^= x >> 27; x *= 0x94D049BB133111EBull; x ^= x >> 31;
-    u[j] = (double)(x >> 11) * (1.0 / 9007199254740992.0);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -360,9 +464,11 @@ __global__ void __launch_bounds__(1024) per_update_kernel(float *prio, float *p_
     for (int j = threadIdx.x; j < B; j += blockDim.x) s_idx[j] = idx[j];
     __syncthreads();
     for (int j = threadIdx.x; j < B; j += blockDim.x) {
-        bool last = true;
-        for (int k = j + 1; k < B; k++) if (s_idx[k] == s_idx[j]) { last = false; break; }
-        if (last) {
+        const int64_t me = s_idx[j];
+        int dup = 0;      // no early exit: the loads pipeline instead of one shared-memory round trip per iteration
+#pragma unroll 8
+        for (int k = 0; k < B; k++) dup |= (k > j && s_idx[k] == me) ? 1 : 0;
+        if (!dup) {
             const float p = is_final ? td[j] : (float)((double)td[j] + 1e-6);      // priority.item() + 1e-6, stored as float32
             prio[s_idx[j]] = p;
             p_alpha[s_idx[j]] = powf(p, alpha);
@@ -424,6 +530,7 @@ static PerWs per_ws_of(sacb_handle h, int agent) {
     w.chunk_carry = (double *)take(sizeof(double) * (nch + 1));
     w.chunk_fine = (int *)take(sizeof(int) * nch);
     w.counters = (int *)take(256);
+    w.tickets = (int *)take(sizeof(int) * 3 * kTicketInts);
     w.cdf_exact = (double *)take(sizeof(double) * cap);
     w.u = (double *)take(sizeof(double) * B);
     w.flagged = (int *)take(sizeof(int) * B);
@@ -433,7 +540,7 @@ static PerWs per_ws_of(sacb_handle h, int agent) {
 }
 static int64_t per_ws_bytes(sacb_handle h) {
     const int64_t cap = h->cfg.capacity, nch = cap / kChunk + 2, B = h->cfg.max_batch;
-    return 4096 * 4 + 256 + 8 * nch + 8 * (nch + 1) + 4 * nch + 256 + 8 * cap + 8 * B + 4 * B + 8 * B + 4 * B + 16 * 256;
+    return 4096 * 4 + 256 + 8 * nch + 8 * (nch + 1) + 4 * nch + 256 + 8 * cap + 8 * B + 4 * B + 8 * B + 4 * B + 16 * 256 + 4 * 3 * kTicketInts + 256;
 }
 
 int replay_create(sacb_handle h) {
@@ -515,6 +622,7 @@ extern "C" int64_t sacb_len(sacb_handle h, int agent) {
 extern "C" int sacb_clear_replay(sacb_handle h, int agent) {
     if (!h || agent < 0 || agent >= h->cfg.n_agents) return fail(SACB_ERR_ARG, "bad argument");
     h->r_len[agent] = h->r_pos[agent] = h->r_head[agent] = 0;
+    h->sample_k = 0;
     if (h->prio) { cudaMemsetAsync(h->prio, 0, sizeof(float) * h->cfg.capacity, h->stream); cudaMemsetAsync(h->p_alpha, 0, sizeof(float) * h->cfg.capacity, h->stream); }
     return SACB_OK;
 }
@@ -643,35 +751,53 @@ static int top_depth_of(int64_t n) {
     return d;
 }
 
-extern "C" int sacb_per_sample(sacb_handle h, int agent, const double *u, int64_t B, int64_t *idx_out, float *weights_out,
-                               float *s, float *a, float *r, float *s2, float *done) {
-    if (!h || agent != 0 || h->cfg.replay_kind != SACB_REPLAY_PER) return fail(SACB_ERR_ARG, "handle has no prioritized buffer");
+namespace sacb {
+int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B, int64_t *k_out) {
+    if (!h || h->cfg.replay_kind != SACB_REPLAY_PER) return fail(SACB_ERR_ARG, "handle has no prioritized buffer");
     const int64_t n = h->r_len[0];
     if (n < 1) return fail(SACB_ERR_STATE, "cannot sample from an empty buffer");
     const int64_t k = std::min<int64_t>(B, n);                       // n_samples = min(batch_size, len)  (replay_buffer.py:50)
     if (k > h->cfg.max_batch) return fail(SACB_ERR_ARG, "batch size exceeds max_batch");
     PerWs w = per_ws_of(h, 0);
-    cudaStream_t st = h->stream;
     const bool pdl = h->use_pdl != 0;
     const int64_t frame = h->per_frame[0];
     const double beta = std::min(1.0, (double)h->cfg.per_beta_start + (double)frame * (1.0 - (double)h->cfg.per_beta_start) / (double)h->cfg.per_beta_frames);
     h->per_frame[0] = frame + 1;
-    if (u) SACB_CUDA(cudaMemcpyAsync(w.u, u, sizeof(double) * k, cudaMemcpyHostToDevice, h->stream));
-    else SACB_CUDA(launch_pdl(per_uniform_draw, dim3((int)((k + 255) / 256)), dim3(256), 0, st, pdl, w.u, (int)k, h->cfg.seed, (uint64_t)frame));
+    if (u) SACB_CUDA(cudaMemcpyAsync(w.u, u, sizeof(double) * k, cudaMemcpyHostToDevice, st));
     const int depth = top_depth_of(n);
     if (depth > 11) return fail(SACB_ERR_ARG, "capacity too large for the summation heap");
     const float *pa = h->p_alpha;
-    SACB_CUDA(launch_pdl(per_sum_blocks, dim3((2 << depth) - 1), dim3(256), 0, st, pdl, pa, n, w.block_vals));
-    SACB_CUDA(launch_pdl(per_sum_top, dim3(1), dim3(1024), 0, st, pdl, n, depth, w.block_vals, w.total));
+    int *tickets = w.tickets;
+    // three launches, each a parallel pass whose last CTA runs the serial step that used to be its own kernel
+    SACB_CUDA(launch_pdl(per_sum, dim3((2 << depth) - 1), dim3(256), 0, st, pdl, pa, n, depth, w.block_vals, w.total, tickets + 0,
+                         w.u, u ? 0 : (int)k, h->cfg.seed, (uint64_t)frame));
     const int n_chunks = (int)((n + kChunk - 1) / kChunk);
-    SACB_CUDA(launch_pdl(per_chunk, dim3((n_chunks + 7) / 8), dim3(256), 0, st, pdl, pa, n, (const float *)w.total, w.chunk_sum, w.chunk_fine));
-    SACB_CUDA(launch_pdl(per_carry, dim3(1), dim3(1024), 0, st, pdl, (const double *)w.chunk_sum, (const int *)w.chunk_fine, n_chunks, w.chunk_carry, w.counters));
+    SACB_CUDA(launch_pdl(per_chunk, dim3((n_chunks + 7) / 8), dim3(256), 0, st, pdl, pa, n, (const float *)w.total, w.chunk_sum, w.chunk_fine,
+                         n_chunks, w.chunk_carry, w.counters, tickets + kTicketInts));
     SACB_CUDA(launch_pdl(per_search, dim3((int)((k + 7) / 8)), dim3(256), 0, st, pdl, pa, n, (const float *)w.total, (const double *)w.chunk_carry, n_chunks,
-                         (const double *)w.u, (int)k, (const int *)w.counters, w.idx, w.flagged, w.counters + 1));
-    SACB_CUDA(launch_pdl(per_exact, dim3(1), dim3(32), 0, st, pdl, pa, n, (const float *)w.total, w.cdf_exact, (const double *)w.u, (int)k, (const int *)w.flagged, w.idx, w.counters));
-    SACB_CUDA(launch_pdl(per_finish, dim3(1), dim3(1024), 0, st, pdl, pa, n, (const float *)w.total, (const int64_t *)w.idx, (int)k, -(float)beta, w.weights, h->slots,
-                         h->ws + h->L.isw, h->last_idx_dev));
-    h->kernel_launches += u ? 7 : 8;
+                         (const double *)w.u, (int)k, w.counters, w.idx, w.flagged, tickets + 2 * kTicketInts,
+                         w.cdf_exact, -(float)beta, w.weights, h->slots, h->ws + h->L.isw, h->last_idx_dev));
+    h->kernel_launches += 3;
+    h->sample_k = k;
+    if (k_out) *k_out = k;
+    return SACB_OK;
+}
+
+int per_writeback_launch(sacb_handle h, cudaStream_t st, int64_t B) {
+    SACB_CUDA(launch_pdl(per_update_kernel, dim3(1), dim3(1024), sizeof(int64_t) * B, st, h->use_pdl != 0, h->prio, h->p_alpha,
+                         (const int64_t *)h->last_idx_dev, (const float *)(h->ws + h->L.td), (int)B, h->cfg.per_alpha, 0));
+    h->kernel_launches++;
+    return SACB_OK;
+}
+}  // namespace sacb
+
+extern "C" int sacb_per_sample(sacb_handle h, int agent, const double *u, int64_t B, int64_t *idx_out, float *weights_out,
+                               float *s, float *a, float *r, float *s2, float *done) {
+    if (!h || agent != 0 || h->cfg.replay_kind != SACB_REPLAY_PER) return fail(SACB_ERR_ARG, "handle has no prioritized buffer");
+    int64_t k = 0;
+    int rc = per_sample_launch(h, h->stream, u, B, &k);
+    if (rc) return rc;
+    PerWs w = per_ws_of(h, 0);
     if (idx_out) SACB_CUDA(cudaMemcpyAsync(idx_out, w.idx, sizeof(int64_t) * k, cudaMemcpyDeviceToHost, h->stream));
     if (weights_out) SACB_CUDA(cudaMemcpyAsync(weights_out, w.weights, sizeof(float) * k, cudaMemcpyDeviceToHost, h->stream));
     if (s || a || r || s2 || done) return gather_to_host(h, 0, nullptr, k, s, a, r, s2, done);
@@ -685,10 +811,7 @@ extern "C" int sacb_per_update_final(sacb_handle h, int agent, const int64_t *id
 extern "C" int sacb_per_update_from_td(sacb_handle h, int agent, int64_t B) {
     if (!h || agent != 0 || h->cfg.replay_kind != SACB_REPLAY_PER) return fail(SACB_ERR_ARG, "bad argument");
     if (B < 1 || B > h->cfg.max_batch) return fail(SACB_ERR_ARG, "batch size out of range");
-    SACB_CUDA(launch_pdl(per_update_kernel, dim3(1), dim3(1024), sizeof(int64_t) * B, h->stream, h->use_pdl != 0, h->prio, h->p_alpha,
-                         (const int64_t *)h->last_idx_dev, (const float *)(h->ws + h->L.td), (int)B, h->cfg.per_alpha, 0));
-    h->kernel_launches++;
-    return SACB_OK;
+    return per_writeback_launch(h, h->stream, B);
 }
 static int per_update_impl(sacb_handle h, int agent, const int64_t *idx, const float *prio, int64_t B, int is_final) {
     if (!h || agent != 0 || h->cfg.replay_kind != SACB_REPLAY_PER || !prio) return fail(SACB_ERR_ARG, "bad argument");
@@ -717,6 +840,7 @@ extern "C" int sacb_per_get_priorities(sacb_handle h, int agent, float *prio, in
 
 extern "C" int sacb_per_set_priorities(sacb_handle h, int agent, const float *prio, const float *p_alpha, int64_t n) {
     if (!h || agent != 0 || !h->prio || n > h->cfg.capacity || !prio) return fail(SACB_ERR_ARG, "bad argument");
+    h->sample_k = 0;      // a minibatch drawn from the old table is stale
     SACB_CUDA(cudaMemcpyAsync(h->prio, prio, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
     if (p_alpha) SACB_CUDA(cudaMemcpyAsync(h->p_alpha, p_alpha, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
     else { pow_alpha_kernel<<<256, 256, 0, h->stream>>>(h->prio, h->p_alpha, n, h->cfg.per_alpha); h->kernel_launches++; }

@@ -114,6 +114,9 @@ extern "C" int sacb_destroy(sacb_handle h) {
     cudaFree(h->arena); cudaFree(h->ws); cudaFree(h->barrier); cudaFree(h->error_flag); cudaFree(h->slots); cudaFree(h->slots_identity); cudaFree(h->adam_table); cudaFree(h->slots_staged);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->pin_rows) cudaFreeHost(h->pin_rows);
+    if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
+    if (h->ev_td) cudaEventDestroy(h->ev_td);
+    if (h->ev_sampled) cudaEventDestroy(h->ev_sampled);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return SACB_OK;
@@ -326,6 +329,40 @@ extern "C" int sacb_update(sacb_handle h, int64_t B, const int64_t *idx, const f
 }
 
 // ---- test hook: read back a hidden activation matrix of the last update ----------------------------------------------
+/* One learner step over the prioritized buffer with every input resident in HBM, software-pipelined across two streams:
+ *   stream : update stages up to the critic losses (TD errors exist) ............ rest of the update (critic backward, actor, ...)
+ *   stream2:                                          priority write-back |q1 - y| -> prioritized sample for the NEXT step
+ * Same kernels, same order of the dependent operations and therefore the same values as sacb_per_sample -> sacb_update(USE_LAST_SAMPLE)
+ * -> sacb_per_update_from_td called in sequence (tests/test_gpu_replay.py::test_pipelined_step_equals_sequential). */
+extern "C" int sacb_per_step(sacb_handle h, int64_t B, float *losses_out, uint32_t flags) {
+    if (!h || h->cfg.replay_kind != SACB_REPLAY_PER || h->cfg.n_agents != 1) return fail(SACB_ERR_ARG, "handle has no prioritized buffer");
+    if (B < 1 || B > h->L.maxB) return fail(SACB_ERR_ARG, "batch size out of range");
+    if (!h->stream2) {
+        SACB_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+        SACB_CUDA(cudaEventCreateWithFlags(&h->ev_td, cudaEventDisableTiming));
+        SACB_CUDA(cudaEventCreateWithFlags(&h->ev_sampled, cudaEventDisableTiming));
+    }
+    int rc;
+    const int64_t k = std::min<int64_t>(B, h->r_len[0]);
+    if (h->sample_k != k) {      // first call (or the batch size changed): draw this step's minibatch now
+        rc = per_sample_launch(h, h->stream, nullptr, B, nullptr);
+        if (rc) return rc;
+    }
+    ProgramKey key{(int)k, 1, 0, 1, h->cfg.per_weighted_loss ? 1 : 0, -1};
+    ProgramInst *p;
+    rc = get_program(h, key, &p);
+    if (rc) return rc;
+    if ((rc = launch_program_part(h, *p, 0))) return rc;
+    SACB_CUDA(cudaEventRecord(h->ev_td, h->stream));
+    SACB_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_td, 0));
+    if ((rc = per_writeback_launch(h, h->stream2, k))) return rc;
+    if ((rc = per_sample_launch(h, h->stream2, nullptr, B, nullptr))) return rc;
+    SACB_CUDA(cudaEventRecord(h->ev_sampled, h->stream2));
+    if ((rc = launch_program_part(h, *p, 1))) return rc;
+    SACB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_sampled, 0));      // whatever follows on the main stream sees the new sample
+    return finish_update(h, losses_out, flags);
+}
+
 extern "C" int sacb_debug_read_activation(sacb_handle h, int agent, int group, int k, int layer, int64_t B, float *out) {
     if (!h || !out || agent < 0 || agent >= h->cfg.n_agents || group < 0 || group > 3 || k < 0 || k > 1 || layer < 0 || layer >= h->L.n_hidden ||
         B < 1 || B > h->L.maxB)

@@ -224,6 +224,23 @@ class SAC:
             return None
         return {"q1_loss": float(losses[0]), "q2_loss": float(losses[1]), "policy_loss": float(losses[2])}
 
+    def learner_step(self, batch_size=256, *, sync=False):
+        """Throughput form of `update_parameters` over the prioritized buffer (per_weighted_loss mode), everything resident
+        in HBM: update on the minibatch sampled by the previous call -> priorities <- |q1 - y| -> sample for the next call;
+        the write-back and the sample run on a second stream under the rest of the update (`sacb_per_step`).  Device-drawn
+        uniforms and eps.  Same values as `update_parameters` with device draws; a transition pushed between two calls
+        can first be drawn one call later."""
+        buf = self.replay_buffer
+        if not isinstance(buf, PrioritizedReplayBuffer):
+            raise ValueError("learner_step needs the prioritized replay buffer")
+        buf._flush()
+        losses = np.zeros(3, np.float32)
+        N.check(N.lib().sacb_per_step(self._h, batch_size, N.ptr(losses) if sync else None, 0 if sync else N.NO_LOSS_READBACK))
+        self._alpha_is_float = False
+        if not sync:
+            return None
+        return {"q1_loss": float(losses[0]), "q2_loss": float(losses[1]), "policy_loss": float(losses[2])}
+
     def update_from_batch(self, batch, eps=None, is_weights=None, export_grads=False, want_td=False):
         """Same step on a caller-supplied minibatch dict(s,a,r,s2,d) (parity tests / benchmarks; no replay involved)."""
         s, a, r, s2, d = (N.f32(batch[k]) for k in ("s", "a", "r", "s2", "d"))

@@ -149,3 +149,46 @@ def test_buffer_attribute_round_trip(hw):
     other = hw.ReplayBuffer(50)
     other.buffer = dq
     assert len(other) == 50 and other.buffer[7][2] == dq[7][2]
+
+
+def test_pipelined_step_equals_sequential(hw):
+    """sacb_per_step (write-back + next sample on a second stream under the tail of the update) == the three calls in sequence, bitwise."""
+    import ctypes
+    import torch
+    from tests.util import make_agent
+    N = hw._native
+    lib = N.lib()
+    case = cases.UPDATE_CASES["tiny_m2"]
+    B, n, cap = case["batch"], 3000, 4096
+    rng = np.random.RandomState(5)
+    S, A = rng.standard_normal((n, case["obs"])).astype(np.float32), rng.uniform(-0.4, 0.4, (n, case["act"])).astype(np.float32)
+    R, S2, D = rng.standard_normal(n).astype(np.float32), rng.standard_normal((n, case["obs"])).astype(np.float32), (rng.uniform(size=n) < 0.1)
+    pri = np.zeros(cap, np.float32)
+    pri[:n] = np.abs(rng.standard_normal(n)) + 1e-6
+    agents = []
+    for _ in range(2):
+        agent, _st = make_agent(hw, case, math="bf16x3", capacity=cap, replay="per", per_weighted_loss=True)
+        agent.replay_buffer.push_many(S, A, R, S2, D)
+        agent.replay_buffer.set_priorities(pri)
+        agents.append(agent)
+    seq, pipe = agents
+    steps = 7
+    for _ in range(steps):
+        N.check(lib.sacb_per_sample(seq._h, 0, None, B, None, None, None, None, None, None, None))
+        N.check(lib.sacb_update(seq._h, B, None, None, None, None, N.USE_LAST_SAMPLE | N.NO_LOSS_READBACK))
+        N.check(lib.sacb_per_update_from_td(seq._h, 0, B))
+    for _ in range(steps):
+        pipe.learner_step(B)
+    seq.synchronize(); pipe.synchronize()
+    for net in ("policy", "q1", "q2", "q1_target", "q2_target"):
+        a, b = getattr(seq, net).state_dict(), getattr(pipe, net).state_dict()
+        for k in a:
+            assert torch.equal(a[k], b[k]), (net, k)
+    pa, pb = np.empty(cap, np.float32), np.empty(cap, np.float32)
+    N.check(lib.sacb_per_get_priorities(seq._h, 0, N.ptr(pa), cap))
+    N.check(lib.sacb_per_get_priorities(pipe._h, 0, N.ptr(pb), cap))
+    assert np.array_equal(pa, pb)
+    assert not np.array_equal(pa, pri)      # the write-back happened
+    la, lb = np.zeros(3, np.float32), np.zeros(3, np.float32)
+    N.check(lib.sacb_get_losses(seq._h, 0, N.ptr(la))); N.check(lib.sacb_get_losses(pipe._h, 0, N.ptr(lb)))
+    assert np.array_equal(la, lb) and np.all(np.isfinite(la))
