@@ -575,19 +575,16 @@ __device__ __forceinline__ void adam_epilogue_tile(const EpiR &e, float *Cs, int
     }
 }
 
-// R rows (m[i]) x 4 columns starting at n; acc[i] = the staged accumulators.  All global loads are issued before any store.
+// auxiliary operands of R rows (m[i]) x 4 columns starting at n: the bias (column only) or the sign source of the ReLU mask.
+// They do not depend on the accumulator, so the tensor-core epilogue fetches them BEFORE it waits for the main loop.
 template <int EPI, int R>
-__device__ __forceinline__ void epilogue_rows4(const EpiR &e, const int (&m)[R], int n, const float4 (&acc4)[R], unsigned long long *tr) {
-    if (n >= e.N) return;
-    const bool full = n + 3 < e.N;
-    float acc[R][4];
-#pragma unroll
-    for (int i = 0; i < R; i++) { acc[i][0] = acc4[i].x; acc[i][1] = acc4[i].y; acc[i][2] = acc4[i].z; acc[i][3] = acc4[i].w; }
-    float aux[R][4];
+__device__ __forceinline__ void epilogue_aux4(const EpiR &e, const int (&m)[R], int n, float (&aux)[R][4]) {
 #pragma unroll
     for (int i = 0; i < R; i++)
 #pragma unroll
         for (int j = 0; j < 4; j++) aux[i][j] = 0.f;
+    if (n >= e.N) return;
+    const bool full = n + 3 < e.N;
     if (EPI == EPI_MASK) {
 #pragma unroll
         for (int i = 0; i < R; i++) {       // sign of the stored activation (hi plane)
@@ -615,7 +612,16 @@ __device__ __forceinline__ void epilogue_rows4(const EpiR &e, const int (&m)[R],
 #pragma unroll
             for (int j = 0; j < 4; j++) aux[i][j] = aux[0][j];
     }
-    if (tr && aux[0][0] != 12345.678f) trace_stamp(tr, 14);      // the auxiliary loads have landed
+}
+
+// R rows (m[i]) x 4 columns starting at n; acc[i] = the staged accumulators, aux = epilogue_aux4 of the same rows / columns.
+template <int EPI, int R>
+__device__ __forceinline__ void epilogue_rows4(const EpiR &e, const int (&m)[R], int n, const float4 (&acc4)[R], const float (&aux)[R][4]) {
+    if (n >= e.N) return;
+    const bool full = n + 3 < e.N;
+    float acc[R][4];
+#pragma unroll
+    for (int i = 0; i < R; i++) { acc[i][0] = acc4[i].x; acc[i][1] = acc4[i].y; acc[i][2] = acc4[i].z; acc[i][3] = acc4[i].w; }
 #pragma unroll
     for (int i = 0; i < R; i++) {
         if (m[i] >= e.M) continue;
@@ -647,6 +653,21 @@ __device__ __forceinline__ void tc_epilogue(const EpiR &epi, int m0, int n0, int
     // staging: ks == 1 -> one tile [kTM][kCsLd] over operand stage 0 (all MMAs have retired);
     //          ks  > 1 -> ks slots [rows_per][kCsLd] over operand stage 3 (never used by a clustered main loop), slot = source rank
     float *Cs = reinterpret_cast<float *>(st.tiles + (ks > 1 ? (kTStages - 1) * kTcStageBytes : 0));
+    // phase-2 mapping: bn / 4 threads cover a row (4 columns each); the 512 threads cover 32 (bn = 64) or 64 (bn = 32) rows per
+    // pass, four passes.  The rows' auxiliary operands (bias / activation signs) are fetched now, under the main loop.
+    const int ct = bn >> 2, rs = kThreads / ct;
+    const int c4 = (tid % ct) * 4, r0 = tid / ct;
+    const int row_lo = ks > 1 ? (int)st.krank * rows_per : 0, row_hi = ks > 1 ? row_lo + rows_per : bm;
+    int m[4];
+    float aux[4][4];
+    if (EPI != EPI_ADAM) {
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int row = rs * i + r0;
+            m[i] = (row >= row_lo && row < row_hi) ? m0 + row : 0x7fffffff;      // rows of another cluster rank / beyond the tile are skipped like rows beyond M
+        }
+        epilogue_aux4<EPI, 4>(epi, m, n0 + c4, aux);
+    }
     {   // phase 1: warp w owns TMEM lanes 32*(w%4).., column group w/4.  A 64-row tile keeps 16 rows in the lower half of each
         // 32-lane subpartition; a 32-column tile has only two column groups.
         const bool half_m = bm == 64;
@@ -679,7 +700,6 @@ __device__ __forceinline__ void tc_epilogue(const EpiR &epi, int m0, int n0, int
     tc_fence_before();
     __syncthreads();     // staging complete; all TMEM reads retired (the next tile's first MMA may overwrite the accumulator)
     if (traced && tid == 64) trace_stamp(st.trace, 7);
-    int row_lo = 0, row_hi = bm;
     if (ks > 1) {
         if (tid < ks && tid != (int)st.krank) {      // one release-arrive per peer: my rows have landed in its slots
             asm volatile("fence.acq_rel.cluster;" ::: "memory");
@@ -688,15 +708,14 @@ __device__ __forceinline__ void tc_epilogue(const EpiR &epi, int m0, int n0, int
         mbar_wait_cluster(st.reduce_bar, st.reduce_uses & 1, error_flag);      // ks - 1 peers have pushed their rows to me
         st.reduce_uses++;
         if (traced && tid == 64) trace_stamp(st.trace, 48);
-        row_lo = (int)st.krank * rows_per; row_hi = row_lo + rows_per;
-        const int c4 = (tid & 15) * 4;
+        const int cc = (tid & 15) * 4;
         for (int l = tid >> 4; l < rows_per; l += 32) {      // sum the slots in rank order into slot 0 (deterministic)
-            float4 sum = *reinterpret_cast<const float4 *>(Cs + l * kCsLd + c4);
+            float4 sum = *reinterpret_cast<const float4 *>(Cs + l * kCsLd + cc);
             for (int r = 1; r < ks; r++) {
-                const float4 p = *reinterpret_cast<const float4 *>(Cs + (r * rows_per + l) * kCsLd + c4);
+                const float4 p = *reinterpret_cast<const float4 *>(Cs + (r * rows_per + l) * kCsLd + cc);
                 sum.x += p.x; sum.y += p.y; sum.z += p.z; sum.w += p.w;
             }
-            *reinterpret_cast<float4 *>(Cs + l * kCsLd + c4) = sum;
+            *reinterpret_cast<float4 *>(Cs + l * kCsLd + cc) = sum;
         }
         __syncthreads();
         if (traced && tid == 64) trace_stamp(st.trace, 49);
@@ -704,21 +723,15 @@ __device__ __forceinline__ void tc_epilogue(const EpiR &epi, int m0, int n0, int
     }
     if (EPI == EPI_ADAM) {
         adam_epilogue_tile(epi, Cs, m0, n0, row_lo, row_hi);
-    } else {   // phase 2: all rows of a thread at once, so every global load is in flight before the first store.
-        // bn / 4 threads cover a row (4 columns each); the 512 threads cover 32 (bn = 64) or 64 (bn = 32) rows per pass
-        const int ct = bn >> 2, rs = kThreads / ct;
-        const int c4 = (tid % ct) * 4, r0 = tid / ct;
-        int m[4];
+    } else {   // phase 2: the staged accumulators of the thread's rows meet the prefetched auxiliary operands
         float4 acc[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
             const int row = rs * i + r0;
-            const bool mine = row >= row_lo && row < row_hi;
-            m[i] = mine ? m0 + row : 0x7fffffff;      // rows of another cluster rank / beyond the tile are skipped like rows beyond M
-            acc[i] = mine ? *reinterpret_cast<const float4 *>(Cs + row * kCsLd + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+            acc[i] = m[i] != 0x7fffffff ? *reinterpret_cast<const float4 *>(Cs + row * kCsLd + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (traced && tid == 64 && acc[0].x != 12345.678f) trace_stamp(st.trace, 13);
-        epilogue_rows4<EPI, 4>(epi, m, n0 + c4, acc, (traced && tid == 64) ? st.trace : nullptr);
+        epilogue_rows4<EPI, 4>(epi, m, n0 + c4, acc, aux);
     }
     if (traced && tid == 64) trace_stamp(st.trace, 8);
     fence_proxy_async_smem();   // generic-proxy accesses of the staging tile are ordered before the next TMA write into it

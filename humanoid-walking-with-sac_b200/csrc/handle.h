@@ -132,10 +132,15 @@ struct sacb_handle_s {
     float *pin = nullptr;
     int64_t pin_floats = 0;
     float *pin_rows = nullptr;           // packed minibatch rows of sacb_update_batch
+    float *pin_small = nullptr;          // [16] losses + error flag read back with ONE synchronisation (finish_update)
+    float *pin_push = nullptr;           // staging of small pushes (<= kPinPushRows rows): no synchronisation on the push path
+    cudaEvent_t ev_push = nullptr;       // the H2D copy out of pin_push has completed
+    bool push_in_flight = false;
     int64_t pin_rows_cap = 0;
 };
 
 namespace sacb {
+constexpr int kPinPushRows = 64;
 inline bool math_is_tc(int m) { return m != SACB_MATH_FP32; }
 inline size_t math_smem(int m) { return math_is_tc(m) ? (size_t)kTcSmemBytes : (size_t)kSimtSmemBytes; }
 // TMA descriptor of a pair-matrix view (program.cu): dims {cols, rows, 2 planes, n_agents}, box {64, box_rows, 2, 1},

@@ -567,7 +567,7 @@ struct Builder {
                         t.p[2] = aw.w; t.p[3] = aw.m; t.p[4] = aw.v; t.p[5] = aw.wt; t.p[6] = aw.gexp;
                         t.p[7] = ab.w; t.p[8] = ab.m; t.p[9] = ab.v; t.p[10] = ab.wt; t.p[11] = ab.gexp;
                         t.i[0] = B; t.i[1] = H; t.i[2] = aw.step_slot; t.i[3] = aw.apply; t.f[0] = aw.lr; t.f[1] = aw.tau;
-                        add(t, cdiv(H, kColsumCols));
+                        add(t, cdiv(H, kOutAdamCols) + 1);      // + the bias tile
                     }
                 }
             }

@@ -682,6 +682,13 @@ extern "C" int sacb_push_rows(sacb_handle h, int agent, const float *rows, int64
     const int64_t cap = c.capacity, row = h->ring_row;
     float *ring = h->ring + (int64_t)agent * cap * row;
     const bool per = c.replay_kind == SACB_REPLAY_PER;
+    // the trainer's one-transition push (trainer.py:194): staged through pinned memory, nothing on this path waits for the device
+    const bool staged = n <= kPinPushRows && h->pin_push;
+    if (staged) {
+        if (h->push_in_flight) SACB_CUDA(cudaEventSynchronize(h->ev_push));      // the previous copy out of the staging buffer (long done)
+        memcpy(h->pin_push, rows, sizeof(float) * row * n);
+        rows = h->pin_push;
+    }
     int64_t done_n = 0;
     while (done_n < n) {
         int64_t slot;
@@ -701,7 +708,8 @@ extern "C" int sacb_push_rows(sacb_handle h, int agent, const float *rows, int64
         }
         done_n += run;
     }
-    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    if (staged) { SACB_CUDA(cudaEventRecord(h->ev_push, h->stream)); h->push_in_flight = true; }
+    else SACB_CUDA(cudaStreamSynchronize(h->stream));      // the caller may reuse its buffer
     return SACB_OK;
 }
 

@@ -101,6 +101,9 @@ extern "C" int sacb_create(const sacb_config *cfg, sacb_handle *out) {
     if (rc) return bail(rc);
     h->pin_floats = (int64_t)cfg->max_batch * (2 * cfg->obs_dim + 3 * cfg->act_dim + 8) + 64;
     if (cudaMallocHost(&h->pin, sizeof(float) * h->pin_floats) != cudaSuccess) return bail(fail(SACB_ERR_NOMEM, "pinned allocation failed"));
+    if (cudaMallocHost(&h->pin_small, sizeof(float) * 16) != cudaSuccess || cudaMallocHost(&h->pin_push, sizeof(float) * h->ring_row * kPinPushRows) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_push, cudaEventDisableTiming) != cudaSuccess)
+        return bail(fail(SACB_ERR_NOMEM, "pinned allocation failed"));
     *out = h;
     return SACB_OK;
 }
@@ -113,6 +116,9 @@ extern "C" int sacb_destroy(sacb_handle h) {
     replay_destroy(h);
     cudaFree(h->arena); cudaFree(h->ws); cudaFree(h->barrier); cudaFree(h->error_flag); cudaFree(h->slots); cudaFree(h->slots_identity); cudaFree(h->adam_table); cudaFree(h->slots_staged);
     if (h->pin) cudaFreeHost(h->pin);
+    if (h->pin_small) cudaFreeHost(h->pin_small);
+    if (h->pin_push) cudaFreeHost(h->pin_push);
+    if (h->ev_push) cudaEventDestroy(h->ev_push);
     if (h->pin_rows) cudaFreeHost(h->pin_rows);
     if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
     if (h->ev_td) cudaEventDestroy(h->ev_td);
@@ -245,8 +251,15 @@ static int upload_eps(sacb_handle h, int agent, int64_t B, const float *eps_next
 
 static int finish_update(sacb_handle h, float *losses_out, uint32_t flags) {
     if (flags & SACB_NO_LOSS_READBACK) return SACB_OK;
-    if (losses_out) return sacb_get_losses(h, 0, losses_out);     // 3 floats D2H + sync: the `.item()` calls of sac_imp.py:141-143
-    return sacb_synchronize(h);
+    if (!losses_out) return sacb_synchronize(h);
+    // 3 floats D2H (the `.item()` calls of sac_imp.py:141-143) and the device error flag, into pinned memory, ONE synchronisation
+    SACB_CUDA(cudaMemcpyAsync(h->pin_small, h->arena + h->L.scalars + SC_LOSS_Q1, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    SACB_CUDA(cudaMemcpyAsync(h->pin_small + 4, h->error_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    memcpy(losses_out, h->pin_small, 3 * sizeof(float));
+    int32_t flag;
+    memcpy(&flag, h->pin_small + 4, sizeof(flag));
+    return flag ? check_error_flag(h) : SACB_OK;
 }
 
 extern "C" int sacb_update_batch(sacb_handle h, int64_t B, const float *s, const float *a, const float *r, const float *s2,

@@ -334,10 +334,11 @@ __device__ __forceinline__ void task_sample_bwd(const Task &t, int tile, const P
 // column sums over the batch for kColsumCols columns per tile: thread (cg = tid % C, rg = tid / C) adds rows rg, rg+G, ...
 // (loads unrolled 8 deep), the row groups are then combined in shared memory in a fixed order
 constexpr int kColsumCols = 64;
-template <class F>
+constexpr int kOutAdamCols = 32;     // T_OUT_ADAM: narrower tiles (16 row groups): half the dependent load rounds per thread
+template <int kCols, class F>
 __device__ __forceinline__ float colsum(int B, float *smem, F value_at) {
-    constexpr int G = kThreads / kColsumCols;       // row groups
-    const int cg = threadIdx.x % kColsumCols, rg = threadIdx.x / kColsumCols;
+    constexpr int G = kThreads / kCols;       // row groups
+    const int cg = threadIdx.x % kCols, rg = threadIdx.x / kCols;
     float acc = 0.f;
     int b = rg;
     for (; b + 7 * G < B; b += 8 * G) {
@@ -348,36 +349,51 @@ __device__ __forceinline__ float colsum(int B, float *smem, F value_at) {
         for (int u = 0; u < 8; u++) acc += v[u];
     }
     for (; b < B; b += G) acc += value_at(b);
-    smem[rg * kColsumCols + cg] = acc;
+    smem[rg * kCols + cg] = acc;
     __syncthreads();
     float tot = 0.f;
-    if (rg == 0) for (int g = 0; g < G; g++) tot += smem[g * kColsumCols + cg];
+    if (rg == 0) for (int g = 0; g < G; g++) tot += smem[g * kCols + cg];
     __syncthreads();
     return tot;     // valid for rg == 0
 }
 
 // T_OUT_ADAM: Q output layer (Linear(H,1)).  pm0=h_L PM [B,H] p1=dq [B] ; p2..p6 = w,m,v,wt,gexp [H] ; p7..p11 = same for bias
-//   i0=B i1=H i2=step_slot i3=apply ; f0=lr f1=tau.   kColsumCols columns per tile; tile 0 also does the bias
+//   i0=B i1=H i2=step_slot i3=apply ; f0=lr f1=tau.   kOutAdamCols columns per tile; one extra (last) tile does the bias.
+//   The optimiser state of a column is fetched BEFORE its column sum so that the two latencies overlap.
 __device__ __forceinline__ void task_out_adam(const Task &t, int tile, const Program &P, int agent, const float *scalars, float *smem) {
     const int B = t.i[0], H = t.i[1];
-    const int n = tile * kColsumCols + (threadIdx.x % kColsumCols);
-    const Pm h = resolve_pm(t.pm[0], P.bases, agent);
     const float *dq = resolve(t.p[1], P.bases, agent);
     float ss, bs;
     adam_factors_cached(scalars, t.i[2], ss, bs);
-    const float g = colsum(B, smem, [&](int b) { return n < H ? ldcg(dq + b) * pm_load(h, b, n) : 0.f; });
-    if (threadIdx.x < kColsumCols && n < H) {
-        float *wt = resolve(t.p[5], P.bases, agent), *ge = resolve(t.p[6], P.bases, agent);
-        adam_element(g, resolve(t.p[2], P.bases, agent) + n, resolve(t.p[3], P.bases, agent) + n, resolve(t.p[4], P.bases, agent) + n,
-                     wt ? wt + n : nullptr, ge ? ge + n : nullptr, t.i[3], ss, bs, t.f[1]);
+    if (tile == cdiv(H, kOutAdamCols)) {      // bias tile: db = sum_b dq[b], fixed order (32 lane partials, then the warp tree)
+        if (threadIdx.x < 32) {
+            float gb = 0.f;
+            for (int b = threadIdx.x; b < B; b += 32) gb += ldcg(dq + b);
+            gb = warp_sum(gb);
+            if (threadIdx.x == 0)
+                adam_element(gb, resolve(t.p[7], P.bases, agent), resolve(t.p[8], P.bases, agent), resolve(t.p[9], P.bases, agent),
+                             resolve(t.p[10], P.bases, agent), resolve(t.p[11], P.bases, agent), t.i[3], ss, bs, t.f[1]);
+        }
+        return;
     }
-    if (tile == 0 && threadIdx.x < 32) {
-        float gb = 0.f;
-        for (int b = threadIdx.x; b < B; b += 32) gb += ldcg(dq + b);
-        gb = warp_sum(gb);
-        if (threadIdx.x == 0)
-            adam_element(gb, resolve(t.p[7], P.bases, agent), resolve(t.p[8], P.bases, agent), resolve(t.p[9], P.bases, agent),
-                         resolve(t.p[10], P.bases, agent), resolve(t.p[11], P.bases, agent), t.i[3], ss, bs, t.f[1]);
+    const int n = tile * kOutAdamCols + (threadIdx.x % kOutAdamCols);
+    const Pm h = resolve_pm(t.pm[0], P.bases, agent);
+    const bool owner = threadIdx.x < kOutAdamCols && n < H;
+    float *w = resolve(t.p[2], P.bases, agent) + n, *m = resolve(t.p[3], P.bases, agent) + n, *v = resolve(t.p[4], P.bases, agent) + n;
+    float *wt = resolve(t.p[5], P.bases, agent), *ge = resolve(t.p[6], P.bases, agent);
+    float ww = 0.f, mm = 0.f, vv = 0.f, wtv = 0.f;
+    if (owner && t.i[3]) { ww = __ldcg(w); mm = __ldcg(m); vv = __ldcg(v); if (wt) wtv = __ldcg(wt + n); }
+    const float g = colsum<kOutAdamCols>(B, smem, [&](int b) { return n < H ? ldcg(dq + b) * pm_load(h, b, n) : 0.f; });
+    if (owner) {
+        if (ge) ge[n] = g;
+        if (t.i[3]) {      // adam_element on the prefetched state (same arithmetic, same order)
+            mm = mm + (1.0f - kBeta1) * (g - mm);
+            vv = vv * kBeta2 + (1.0f - kBeta2) * g * g;
+            const float denom = sqrtf(vv) / bs + kAdamEps;
+            ww = ww - ss * (mm / denom);
+            *m = mm; *v = vv; *w = ww;
+            if (wt) wt[n] = wtv * (1.0f - t.f[1]) + ww * t.f[1];
+        }
     }
 }
 
@@ -387,7 +403,7 @@ __device__ __forceinline__ void task_bias_adam(const Task &t, int tile, const Pr
     const int B = t.i[0], N = t.i[1];
     const int n = tile * kColsumCols + (threadIdx.x % kColsumCols);
     const Pm dh = resolve_pm(t.pm[0], P.bases, agent);
-    const float g = colsum(B, smem, [&](int b) { return n < N ? pm_load(dh, b, n) : 0.f; });
+    const float g = colsum<kColsumCols>(B, smem, [&](int b) { return n < N ? pm_load(dh, b, n) : 0.f; });
     if (threadIdx.x < kColsumCols && n < N) {
         float ss, bs;
         adam_factors_cached(scalars, t.i[2], ss, bs);

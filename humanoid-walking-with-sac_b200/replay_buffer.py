@@ -30,6 +30,7 @@ class _DeviceBuffer:
         self._owner = None      # SAC agent owning the handle (None: private handle)
         self._cfg = None
         self._pending = []      # packed rows not yet on the device
+        self._row_floats = None
 
     # ---- handle plumbing -------------------------------------------------------------------------------
     def _bind(self, owner):
@@ -59,7 +60,9 @@ class _DeviceBuffer:
     def push(self, state, action, reward, next_state, done):
         s, a, r, s2, d = _as_row_parts(state, action, reward, next_state, done)
         self._ensure_handle(s.size, a.size)
-        row = np.zeros(int(N.lib().sacb_row_floats(self._h)), np.float32)
+        if self._row_floats is None:
+            self._row_floats = int(N.lib().sacb_row_floats(self._h))
+        row = np.zeros(self._row_floats, np.float32)
         o, k = self._cfg.obs_dim, self._cfg.act_dim
         row[:o], row[o:2 * o], row[2 * o:2 * o + k], row[2 * o + k], row[2 * o + k + 1] = s, s2, a, r, d
         self._pending.append(row)
