@@ -98,7 +98,9 @@ enum Epilogue : int32_t {
     EPI_F32 = 0,         // C[fp32] = acc (+ bias[n])
     EPI_BIAS_RELU,       // PM  = relu(acc + bias[n])
     EPI_MASK,            // PM  = acc * (mask_hi[m,n] > 0)
-    EPI_ADAM             // acc = dW tile: Adam on W (+ Polyak into Wt, + shadow PM refresh, + optional grad export)
+    EPI_ADAM,            // acc = dW tile: Adam on W (+ Polyak into Wt, + shadow PM refresh, + optional grad export)
+    EPI_SAMPLE           // policy heads: C[fp32] = acc + bias (mean | log_std_raw), then the tanh-Gaussian sample + log-prob of
+                         // the tile's rows (the T_SAMPLE task fused into the heads GEMM; its arguments sit in the generic slots)
 };
 
 struct AdamArgs {

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_selftest_kernel(const Task *
         st.tmem_base = s_tmem;
     }
     for (int tile = blockIdx.x; tile < t.n_tiles; tile += gridDim.x) {
-        if (kTc) gemm_tile_tc(t, tp, tile, bases, 0, nullptr, st, error_flag, false);
+        if (kTc) gemm_tile_tc(t, tp, tile, bases, 0, nullptr, st, error_flag, false, 0ull);
         else gemm_tile_ffma(t, tile, bases, 0, nullptr, reinterpret_cast<float *>(smem_raw));
     }
     if (kTc) { tc::tc_fence_before(); __syncthreads(); if (threadIdx.x < 32) tc::tmem_dealloc(st.tmem_base, kTN); }

@@ -246,7 +246,7 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
             if (t.type != T_GEMM && st.krank != 0) continue;      // element-wise tasks of a clustered stage run on rank 0 only
             switch (t.type) {
                 case T_GEMM:
-                    if (kTc) gemm_tile_tc(t, tg, tile, P.bases, agent, scalars, st, P.error_flag, wi == cl);
+                    if (kTc) gemm_tile_tc(t, tg, tile, P.bases, agent, scalars, st, P.error_flag, wi == cl, seed);
                     else gemm_tile_ffma(t, tile, P.bases, agent, scalars, reinterpret_cast<float *>(smem_raw));
                     break;
                 case T_SHADOW: task_shadow(t, tile, P, agent); break;
@@ -257,7 +257,7 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
                 case T_SAMPLE_BWD: task_sample_bwd(t, tile, P, agent, scalars); break;
                 case T_OUT_ADAM: task_out_adam(t, tile, P, agent, scalars, s_red); break;
                 case T_BIAS_ADAM: task_bias_adam(t, tile, P, agent, scalars, s_red); break;
-                case T_FINISH: task_finish(t, P, agent, scalars, s_red); __syncthreads(); task_finish_steps(t, P, scalars); break;
+                case T_FINISH: task_finish(t, P, agent, scalars, s_red); break;
             }
             if (wi == cl) stamp(4);
         }
@@ -462,7 +462,7 @@ struct Builder {
                 const Task &t = tasks[b.task];
                 int nbm = b.bm, nbn = b.bn;
                 if (b.bm == kTM && t.M > 64) nbm = 64;
-                else if (b.bn == kTN && !t.B.mn_major && t.epi != EPI_ADAM && t.N > 32) nbn = 32;
+                else if (b.bn == kTN && !t.B.mn_major && t.epi != EPI_ADAM && t.epi != EPI_SAMPLE && t.N > 32) nbn = 32;
                 else { b.frozen = true; continue; }
                 const int ntiles = cdiv(t.M, nbm) * cdiv(t.N, nbn);
                 if (total + (ntiles - b.tiles) * h->cfg.n_agents > wave) { b.frozen = true; continue; }
@@ -510,11 +510,23 @@ struct Builder {
                          epi_bias_relu(hview(L.hc[k][l], B), A(L.param[1 + k] + Q.b[l])));
             }
             // ---- policy heads -> head_raw [2B, 2A] (fp32) ------------------------------------------------------------
+            // tensor-core math with 2A <= 64: the tanh-Gaussian sample + log-prob of both batches runs in the epilogue of the heads
+            // GEMM (EPI_SAMPLE: one stage less); otherwise it is its own stage behind the heads
+            const bool fuse_sample = math_is_tc(h->cfg.math_mode) && A2 <= kTN && !getenv("SACB_NO_FUSE_SAMPLE");
             begin_stage();
-            gemm(hview(L.hp[nh - 1], 2 * B, 0, 2), 0, wsh_head(), 0, 2 * B, A2, H, epi_f32(W(L.head_raw), A2, A(L.param[0] + P.b_out)));
+            if (fuse_sample) {
+                Task t = epi_f32(W(L.head_raw), A2, A(L.param[0] + P.b_out));
+                t.epi = EPI_SAMPLE;
+                t.p[1] = W(L.eps); t.pm[0] = xrows(0, 3 * B, L.ldx).ref; t.p[3] = W(L.logp);
+                t.i[0] = B; t.i[1] = act; t.i[2] = obs; t.i[4] = key.device_eps;
+                t.f[0] = h->cfg.action_scale; t.f[1] = h->cfg.action_bias;
+                gemm(hview(L.hp[nh - 1], 2 * B, 0, 2), 0, wsh_head(), 0, 2 * B, A2, H, t);
+            } else {
+                gemm(hview(L.hp[nh - 1], 2 * B, 0, 2), 0, wsh_head(), 0, 2 * B, A2, H, epi_f32(W(L.head_raw), A2, A(L.param[0] + P.b_out)));
+            }
             // ---- reparameterised sample + log-prob for both batches -------------------------------------------------
-            begin_stage();
-            {
+            if (!fuse_sample) {
+                begin_stage();
                 Task t = blank(T_SAMPLE);
                 t.p[0] = W(L.head_raw); t.p[1] = W(L.eps); t.pm[0] = xrows(0, 3 * B, L.ldx).ref; t.p[3] = W(L.logp);
                 t.i[0] = B; t.i[1] = act; t.i[2] = obs; t.i[4] = key.device_eps;

@@ -6,49 +6,6 @@
 
 namespace sacb {
 
-// ---- Philox4x32-10 (Salmon et al. 2011) for production-mode eps draws --------------------------------------
-__device__ __forceinline__ void philox4x32(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-        const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-}
-__device__ __forceinline__ float philox_normal(uint64_t seed, uint32_t stream, uint32_t step, uint32_t row, uint32_t col) {
-    uint32_t c[4] = {row, col, step, stream};
-    philox4x32(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-    const float u1 = ((float)(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    const float u2 = ((float)(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
-    return sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
-}
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
-
-// tanh-Gaussian sample of one action component: networks_model1.py:83-96 == networks_model2.py:104-117
-struct SampleElem { float action, logp, y, std, in_range; };
-__device__ __forceinline__ SampleElem sample_elem(float mean, float ls_raw, float eps, float scale, float bias) {
-    SampleElem o;
-    const float ls = fminf(fmaxf(ls_raw, kLogStdMin), kLogStdMax);     // torch.clamp(log_std, -20, 2)
-    o.in_range = (ls_raw >= kLogStdMin && ls_raw <= kLogStdMax) ? 1.f : 0.f;
-    o.std = expf(ls);
-    const float x = mean + eps * o.std;                                  // Normal.rsample
-    o.y = tanhf(x);
-    o.action = o.y * scale + bias;
-    const float var = o.std * o.std;
-    const float d = x - mean;
-    float lp = -(d * d) / (2.f * var) - logf(o.std) - kLogSqrt2Pi;      // Normal.log_prob
-    lp -= logf(scale * (1.f - o.y * o.y) + kSquashEps);
-    o.logp = lp;
-    return o;
-}
-
 constexpr int kShadowRows = 64;      // weight rows per T_SHADOW tile (4 per warp)
 constexpr int kLossRows = 4;         // batch rows per T_TARGET_LOSS / T_ACTOR_LOSS tile (4 warps per row)
 
@@ -63,28 +20,38 @@ __device__ __forceinline__ void task_shadow(const Task &t, int tile, const Progr
     const bool even = ((t.i[3] | t.i[2]) & 1) == 0;     // every row starts 8 B aligned in src and 4 B aligned in dst
     constexpr int kR = kShadowRows / (kThreads / 32);    // rows per warp, handled together: kR independent loads in flight per trip
     const int r0 = tile * kShadowRows + warp;
-    for (int c = 2 * lane; c < cols; c += 64) {
-        float2 x[kR];
+    constexpr int kU = 4;                                // column chunks handled together: kR * kU independent loads in flight per trip
+    for (int c0 = 2 * lane; c0 < cols; c0 += 64 * kU) {
+        float2 x[kR][kU];
 #pragma unroll
         for (int i = 0; i < kR; i++) {
             const int r = r0 + i * (kThreads / 32);
-            x[i] = make_float2(0.f, 0.f);
-            if (r < rows) {
-                const float *src = src0 + (int64_t)r * t.i[3] + c;
-                if (even) x[i] = __ldcg(reinterpret_cast<const float2 *>(src));
-                else { x[i].x = ldcg(src); if (c + 1 < cols) x[i].y = ldcg(src + 1); }
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const int c = c0 + 64 * u;
+                x[i][u] = make_float2(0.f, 0.f);
+                if (r < rows && c < cols) {
+                    const float *src = src0 + (int64_t)r * t.i[3] + c;
+                    if (even) x[i][u] = __ldcg(reinterpret_cast<const float2 *>(src));
+                    else { x[i][u].x = ldcg(src); if (c + 1 < cols) x[i][u].y = ldcg(src + 1); }
+                }
             }
         }
 #pragma unroll
         for (int i = 0; i < kR; i++) {
             const int r = r0 + i * (kThreads / 32);
             if (r >= rows) continue;
-            if (c + 1 >= cols) x[i].y = 0.f;
-            uint32_t hi, lo;
-            split_pack2(x[i].x, x[i].y, hi, lo);
-            __nv_bfloat16 *q = dst.hi + (int64_t)r * dst.ld + c;
-            *reinterpret_cast<uint32_t *>(q) = hi;
-            *reinterpret_cast<uint32_t *>(q + dst.plane) = lo;
+#pragma unroll
+            for (int u = 0; u < kU; u++) {
+                const int c = c0 + 64 * u;
+                if (c >= cols) continue;
+                if (c + 1 >= cols) x[i][u].y = 0.f;
+                uint32_t hi, lo;
+                split_pack2(x[i][u].x, x[i][u].y, hi, lo);
+                __nv_bfloat16 *q = dst.hi + (int64_t)r * dst.ld + c;
+                *reinterpret_cast<uint32_t *>(q) = hi;
+                *reinterpret_cast<uint32_t *>(q + dst.plane) = lo;
+            }
         }
     }
 }
@@ -422,6 +389,10 @@ __device__ __forceinline__ void task_finish(const Task &t, const Program &P, int
     const int nt = t.i[5];
     const float Bf = t.f[1];
     const float *cp = resolve(t.p[0], P.bases, agent), *ap = resolve(t.p[1], P.bases, agent);
+    // the agent's scalar block is read ONCE into shared memory, edited there and written back at the end: the serial part below
+    // would otherwise be a chain of ~8 dependent L2 round trips
+    __shared__ float sc[32];
+    if (threadIdx.x < 32) sc[threadIdx.x] = ldcg(scalars + threadIdx.x);
     // deterministic two-level sum: 128 threads each add a contiguous run of tile partials in tile order (one tile
     // each while nt <= 128), thread 0 then adds the 128 run sums in order
     constexpr int kRuns = kThreads / 4;
@@ -435,40 +406,56 @@ __device__ __forceinline__ void task_finish(const Task &t, const Program &P, int
         smem[threadIdx.x] = a1; smem[kRuns + threadIdx.x] = a2; smem[2 * kRuns + threadIdx.x] = b1; smem[3 * kRuns + threadIdx.x] = b2;
     }
     __syncthreads();
-    if (threadIdx.x != 0) return;
-    if (cp) {
-        float s1 = 0.f, s2 = 0.f;
-        for (int i = 0; i < kRuns; i++) { s1 += smem[i]; s2 += smem[kRuns + i]; }
-        scalars[SC_LOSS_Q1] = s1 / Bf; scalars[SC_LOSS_Q2] = s2 / Bf;
+    // threads 32..35: the step counter of one optimizer each (+1, sac_imp.py:109,113,125,134) and its next bias corrections
+    // from the host-built table, fetched while thread 0 works
+    const int k = (int)threadIdx.x - 32;
+    int new_step = 0;
+    float2 fac = make_float2(0.f, 0.f);
+    const bool bump = k >= 0 && k < 4 && t.i[k];      // SC_STEP_POLICY, SC_STEP_Q1, SC_STEP_Q2, SC_STEP_ALPHA are consecutive
+    if (bump) {
+        new_step = __float_as_int(sc[SC_STEP_POLICY + k]) + 1;
+        fac = __ldg(P.adam_table + min(new_step, kAdamTable - 1));
     }
-    if (ap) {
-        float s1 = 0.f, s2 = 0.f;
-        for (int i = 0; i < kRuns; i++) { s1 += smem[2 * kRuns + i]; s2 += smem[3 * kRuns + i]; }
-        scalars[SC_LOSS_PI] = s1 / Bf;
-        const int n_upd = __float_as_int(scalars[SC_N_UPDATES]);
-        float alpha_next = scalars[SC_ALPHA0 + (n_upd & 1)];
-        if (t.i[6]) {
-            const float la = scalars[SC_LOG_ALPHA];
-            const float g = -(s2 / Bf);                                      // d(-mean(log_alpha*(logp+H_t)))/dlog_alpha
-            scalars[SC_LOSS_ALPHA] = la * g;
-            float ss, bs;
-            adam_factors_cached(scalars, SC_STEP_ALPHA, ss, bs);
-            adam_element(g, &scalars[SC_LOG_ALPHA], &scalars[SC_LOG_ALPHA_M], &scalars[SC_LOG_ALPHA_V], nullptr, resolve(t.p[2], P.bases, agent), t.i[7], ss, bs, 0.f);
-            alpha_next = expf(scalars[SC_LOG_ALPHA]);                        // self.alpha = self.log_alpha.exp()
+    if (threadIdx.x == 0) {
+        if (cp) {
+            float s1 = 0.f, s2 = 0.f;
+            for (int i = 0; i < kRuns; i++) { s1 += smem[i]; s2 += smem[kRuns + i]; }
+            sc[SC_LOSS_Q1] = s1 / Bf; sc[SC_LOSS_Q2] = s2 / Bf;
         }
-        if (t.i[7]) scalars[SC_ALPHA0 + ((n_upd + 1) & 1)] = alpha_next;
+        if (ap) {
+            float s1 = 0.f, s2 = 0.f;
+            for (int i = 0; i < kRuns; i++) { s1 += smem[2 * kRuns + i]; s2 += smem[3 * kRuns + i]; }
+            sc[SC_LOSS_PI] = s1 / Bf;
+            const int n_upd = __float_as_int(sc[SC_N_UPDATES]);
+            float alpha_next = sc[SC_ALPHA0 + (n_upd & 1)];
+            if (t.i[6]) {
+                const float la = sc[SC_LOG_ALPHA];
+                const float g = -(s2 / Bf);                                      // d(-mean(log_alpha*(logp+H_t)))/dlog_alpha
+                sc[SC_LOSS_ALPHA] = la * g;
+                float *gexp = resolve(t.p[2], P.bases, agent);
+                if (gexp) *gexp = g;
+                if (t.i[7]) {      // adam_element on the shared-memory copy (same arithmetic)
+                    const float ss = sc[SC_FAC0 + 2 * (SC_STEP_ALPHA - SC_STEP_POLICY)], bs = sc[SC_FAC0 + 2 * (SC_STEP_ALPHA - SC_STEP_POLICY) + 1];
+                    float mm = sc[SC_LOG_ALPHA_M], vv = sc[SC_LOG_ALPHA_V];
+                    mm = mm + (1.0f - kBeta1) * (g - mm);
+                    vv = vv * kBeta2 + (1.0f - kBeta2) * g * g;
+                    const float denom = sqrtf(vv) / bs + kAdamEps;
+                    sc[SC_LOG_ALPHA] = la - ss * (mm / denom);
+                    sc[SC_LOG_ALPHA_M] = mm; sc[SC_LOG_ALPHA_V] = vv;
+                }
+                alpha_next = expf(sc[SC_LOG_ALPHA]);                            // self.alpha = self.log_alpha.exp()
+            }
+            if (t.i[7]) sc[SC_ALPHA0 + ((n_upd + 1) & 1)] = alpha_next;
+        }
+        if (t.i[4]) sc[SC_N_UPDATES] = __int_as_float(__float_as_int(sc[SC_N_UPDATES]) + 1);
     }
-    if (t.i[4]) scalars[SC_N_UPDATES] = __int_as_float(__float_as_int(scalars[SC_N_UPDATES]) + 1);
-}
-
-// second half of T_FINISH, threads 0..3 in parallel: bump one optimizer's step counter and cache its next bias corrections
-__device__ __forceinline__ void task_finish_steps(const Task &t, const Program &P, float *scalars) {
-    const int k = threadIdx.x;
-    if (k >= 4 || !t.i[k]) return;
-    const int slot = SC_STEP_POLICY + k;      // SC_STEP_POLICY, SC_STEP_Q1, SC_STEP_Q2, SC_STEP_ALPHA are consecutive
-    const int step = __float_as_int(scalars[slot]) + 1;
-    scalars[slot] = __int_as_float(step);
-    adam_factors_store(scalars, slot, step, P.adam_table);
+    __syncthreads();      // thread 0 has read the current bias corrections
+    if (bump) {
+        sc[SC_STEP_POLICY + k] = __int_as_float(new_step);
+        sc[SC_FAC0 + 2 * k] = fac.x; sc[SC_FAC0 + 2 * k + 1] = fac.y;
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) scalars[threadIdx.x] = sc[threadIdx.x];
 }
 
 }  // namespace sacb
