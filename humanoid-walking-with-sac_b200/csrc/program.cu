@@ -510,9 +510,11 @@ struct Builder {
                          epi_bias_relu(hview(L.hc[k][l], B), A(L.param[1 + k] + Q.b[l])));
             }
             // ---- policy heads -> head_raw [2B, 2A] (fp32) ------------------------------------------------------------
-            // tensor-core math with 2A <= 64: the tanh-Gaussian sample + log-prob of both batches runs in the epilogue of the heads
-            // GEMM (EPI_SAMPLE: one stage less); otherwise it is its own stage behind the heads
-            const bool fuse_sample = math_is_tc(h->cfg.math_mode) && A2 <= kTN && !getenv("SACB_NO_FUSE_SAMPLE");
+            // opt-in experiment (SACB_FUSE_SAMPLE=1, tensor-core math, 2A <= 64): the tanh-Gaussian sample + log-prob of both batches
+            // in the epilogue of the heads GEMM (EPI_SAMPLE, one stage less).  Correct (parity tests pass) but slower on B200: the
+            // heads GEMM has only 2B / 64 = 8 tiles, so 8 SMs do the transcendental-heavy sampling of 512 rows (13.8 us) that the
+            // separate stage spreads over 32 CTAs (4 us + 1 us stage boundary); profiles/r01_summary.md
+            const bool fuse_sample = math_is_tc(h->cfg.math_mode) && A2 <= kTN && getenv("SACB_FUSE_SAMPLE");
             begin_stage();
             if (fuse_sample) {
                 Task t = epi_f32(W(L.head_raw), A2, A(L.param[0] + P.b_out));
