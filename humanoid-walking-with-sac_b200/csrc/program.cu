@@ -702,7 +702,13 @@ static int launch_stage(sacb_handle h, ProgramInst &p, int s, bool pdl) {
     const int ks = std::max(1, single.ksplit);
     void *args[] = {(void *)&p.prog, (void *)&single, (void *)&s0, (void *)&s1, (void *)&tc_setup, (void *)&seed};
     cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(std::max(1, single.n_tiles * h->cfg.n_agents) * ks); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
+    // population mode: a stage of many more tiles than SMs runs as one resident CTA per SM looping over tiles (barrier /
+    // TMEM setup and teardown once per SM instead of once per tile); a single agent's stage (<= ~150 tiles) keeps one CTA per tile
+    int ctas = std::max(1, single.n_tiles * h->cfg.n_agents);
+    static const int grid_cap = getenv("SACB_GRID_CAP") ? atoi(getenv("SACB_GRID_CAP")) : -1;     // 0 = never cap
+    const int cap = grid_cap < 0 ? h->sm_count : grid_cap;
+    if (ks == 1 && cap > 0 && ctas > 2 * h->sm_count) ctas = cap;
+    cfg.gridDim = dim3(ctas * ks); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
     cudaLaunchAttribute attr[2];
     int na = 0;
     if (pdl) {
