@@ -128,6 +128,7 @@ struct sacb_handle_s {
     int64_t *last_idx_dev = nullptr;             // [n_agents, maxB] logical indices of the last sample
     float *last_w_dev = nullptr;
     sacb_per_stats per_stats{};
+    bool prio_max_valid = false;                 // per-CTA maxima of the priority table are current (replay.cu: per_refresh_max)
     // pinned host staging
     float *pin = nullptr;
     int64_t pin_floats = 0;

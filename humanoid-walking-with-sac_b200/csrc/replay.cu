@@ -52,6 +52,7 @@ struct PerWs {            // device workspace of one agent's PER sampler
     int *chunk_fine;      // [n_chunks]
     int *counters;        // [0] total fine, [1] flagged count, [2] exact fallbacks run
     int *tickets;         // completion tickets of the three sample() kernels (kTicketInts each)
+    float *block_max;     // [128] per-CTA maxima of the priority table (push reads max(priorities), replay_buffer.py:38)
     double *cdf_exact;    // [capacity] only touched by per_exact
     double *u;            // [maxB]
     int *flagged;         // [maxB]
@@ -531,6 +532,7 @@ static PerWs per_ws_of(sacb_handle h, int agent) {
     w.chunk_fine = (int *)take(sizeof(int) * nch);
     w.counters = (int *)take(256);
     w.tickets = (int *)take(sizeof(int) * 3 * kTicketInts);
+    w.block_max = (float *)take(sizeof(float) * 128);
     w.cdf_exact = (double *)take(sizeof(double) * cap);
     w.u = (double *)take(sizeof(double) * B);
     w.flagged = (int *)take(sizeof(int) * B);
@@ -540,7 +542,7 @@ static PerWs per_ws_of(sacb_handle h, int agent) {
 }
 static int64_t per_ws_bytes(sacb_handle h) {
     const int64_t cap = h->cfg.capacity, nch = cap / kChunk + 2, B = h->cfg.max_batch;
-    return 4096 * 4 + 256 + 8 * nch + 8 * (nch + 1) + 4 * nch + 256 + 8 * cap + 8 * B + 4 * B + 8 * B + 4 * B + 16 * 256 + 4 * 3 * kTicketInts + 256;
+    return 4096 * 4 + 256 + 8 * nch + 8 * (nch + 1) + 4 * nch + 256 + 8 * cap + 8 * B + 4 * B + 8 * B + 4 * B + 16 * 256 + 4 * 3 * kTicketInts + 256 + 4 * 128 + 256;
 }
 
 int replay_create(sacb_handle h) {
@@ -623,17 +625,29 @@ extern "C" int sacb_clear_replay(sacb_handle h, int agent) {
     if (!h || agent < 0 || agent >= h->cfg.n_agents) return fail(SACB_ERR_ARG, "bad argument");
     h->r_len[agent] = h->r_pos[agent] = h->r_head[agent] = 0;
     h->sample_k = 0;
+    h->prio_max_valid = false;
     if (h->prio) { cudaMemsetAsync(h->prio, 0, sizeof(float) * h->cfg.capacity, h->stream); cudaMemsetAsync(h->p_alpha, 0, sizeof(float) * h->cfg.capacity, h->stream); }
     return SACB_OK;
+}
+
+// max(priorities) over the whole capacity array (replay_buffer.py:38) as 128 CTA maxima.  The table only changes through
+// update_priorities / set_priorities / clear (a push writes the maximum itself, which leaves it unchanged), so the reduction runs
+// right behind those -- off the push -> sample -> update critical path -- and push reuses it while `prio_max_valid`.
+static void per_refresh_max(sacb_handle h, cudaStream_t st) {
+    PerWs w = per_ws_of(h, 0);
+    max_reduce_kernel<<<128, 1024, 0, st>>>(h->prio, h->cfg.capacity, w.block_max);
+    h->kernel_launches++;
+    h->prio_max_valid = true;
 }
 
 static int per_push_priorities(sacb_handle h, int64_t pos, int64_t count, bool empty) {
     PerWs w = per_ws_of(h, 0);
     const int nb = 128;
-    if (!empty) max_reduce_kernel<<<nb, 1024, 0, h->stream>>>(h->prio, h->cfg.capacity, w.block_vals);
-    per_push_kernel<<<(int)std::min<int64_t>(64, (count + 255) / 256), 256, 0, h->stream>>>(h->prio, h->p_alpha, w.block_vals, nb, empty ? 1 : 0, pos, count,
+    if (!empty && !h->prio_max_valid) per_refresh_max(h, h->stream);
+    per_push_kernel<<<(int)std::min<int64_t>(64, (count + 255) / 256), 256, 0, h->stream>>>(h->prio, h->p_alpha, w.block_max, nb, empty ? 1 : 0, pos, count,
                                                                                           h->cfg.capacity, h->cfg.per_alpha);
-    h->kernel_launches += empty ? 1 : 2;
+    h->kernel_launches++;
+    if (empty) h->prio_max_valid = false;      // the first push writes 1.0 into an all-zero table: reduce again next time
     SACB_CUDA(cudaGetLastError());
     return SACB_OK;
 }
@@ -795,6 +809,7 @@ int per_writeback_launch(sacb_handle h, cudaStream_t st, int64_t B) {
     SACB_CUDA(launch_pdl(per_update_kernel, dim3(1), dim3(1024), sizeof(int64_t) * B, st, h->use_pdl != 0, h->prio, h->p_alpha,
                          (const int64_t *)h->last_idx_dev, (const float *)(h->ws + h->L.td), (int)B, h->cfg.per_alpha, 0));
     h->kernel_launches++;
+    per_refresh_max(h, st);      // for the next push; same stream, behind the write-back
     return SACB_OK;
 }
 }  // namespace sacb
@@ -834,6 +849,7 @@ static int per_update_impl(sacb_handle h, int agent, const int64_t *idx, const f
     SACB_CUDA(cudaMemcpyAsync(w.weights, prio, sizeof(float) * B, cudaMemcpyHostToDevice, h->stream));
     per_update_kernel<<<1, 1024, sizeof(int64_t) * B, h->stream>>>(h->prio, h->p_alpha, idx_dev, w.weights, (int)B, h->cfg.per_alpha, is_final);
     h->kernel_launches++;
+    h->prio_max_valid = false;
     SACB_CUDA(cudaGetLastError());
     SACB_CUDA(cudaStreamSynchronize(h->stream));
     return SACB_OK;
@@ -849,6 +865,7 @@ extern "C" int sacb_per_get_priorities(sacb_handle h, int agent, float *prio, in
 extern "C" int sacb_per_set_priorities(sacb_handle h, int agent, const float *prio, const float *p_alpha, int64_t n) {
     if (!h || agent != 0 || !h->prio || n > h->cfg.capacity || !prio) return fail(SACB_ERR_ARG, "bad argument");
     h->sample_k = 0;      // a minibatch drawn from the old table is stale
+    h->prio_max_valid = false;
     SACB_CUDA(cudaMemcpyAsync(h->prio, prio, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
     if (p_alpha) SACB_CUDA(cudaMemcpyAsync(h->p_alpha, p_alpha, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
     else { pow_alpha_kernel<<<256, 256, 0, h->stream>>>(h->prio, h->p_alpha, n, h->cfg.per_alpha); h->kernel_launches++; }
