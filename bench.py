@@ -185,8 +185,13 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    backend = os.environ.get("SACB_BENCH_BACKEND", "nccl")      # "gloo": diagnosis only (timing barrier without NCCL)
+    red_dev = f"cuda:{local}" if backend == "nccl" else "cpu"
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        if backend == "nccl":
+            dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+        else:
+            dist.init_process_group(backend)
     agent = build_agent(hw, local, args.launch, args.math, seed=rank)
     h = agent._h
 
@@ -217,7 +222,9 @@ def run_ours(args):
         time.sleep(0.15)
     barrier()
     launches = agent.stats()["kernel_launches"] - st0
-    t = torch.tensor([ms.value], device=f"cuda:{local}")
+    if world > 1:
+        print(f"[rank {rank}] device {local}: {ms.value / args.steps:.4f} ms/step", file=sys.stderr)
+    t = torch.tensor([ms.value], device=red_dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
@@ -266,7 +273,7 @@ def run_ours(args):
         out = agent.update_parameters(B)
     agent.synchronize()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], device=f"cuda:{local}")
+    te = torch.tensor([e2e_s], device=red_dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = world * args.steps / float(te.item())

@@ -97,6 +97,7 @@ SIGNATURES = {
     "sacb_dp_backward": (I, [H, I, I64, c_i64p, c_f32p, c_f32p]),
     "sacb_dp_apply": (I, [H, I]),
     "sacb_dp_grad_buffer": (I, [H, I, ctypes.POINTER(ctypes.c_void_p), c_i64p]),
+    "sacb_get_stream": (I, [H, ctypes.POINTER(ctypes.c_void_p)]),
     "sacb_get_stats": (I, [H, ctypes.POINTER(Stats)]),
     "sacb_timer_start": (I, [H]),
     "sacb_timer_stop": (I, [H, c_f32p]),

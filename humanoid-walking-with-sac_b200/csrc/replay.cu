@@ -53,7 +53,7 @@ struct PerWs {            // device workspace of one agent's PER sampler
     int *counters;        // [0] total fine, [1] flagged count, [2] exact fallbacks run
     int *tickets;         // completion tickets of the three sample() kernels (kTicketInts each)
     float *block_max;     // [128] per-CTA maxima of the priority table (push reads max(priorities), replay_buffer.py:38)
-    double *cdf_exact;    // [capacity] only touched by per_exact
+    double *cdf_exact;    // [n_chunks + 1] exact sequential cdf at the chunk starts, only touched by the exact pass (sized for capacity)
     double *u;            // [maxB]
     int *flagged;         // [maxB]
     int64_t *idx;         // [maxB]
@@ -322,26 +322,59 @@ __global__ void __launch_bounds__(256) per_chunk(const float *p_alpha, int64_t n
     carry_scan(chunk_sum, chunk_fine, n_chunks, carry, counters);
 }
 
-// numpy's own algorithm, run only when a sample could not be certified: sequential float64 cumsum, /= last, searchsorted right
-__device__ void exact_pass(const float *p_alpha, int64_t n, float tot, double *cdf, const double *u, int B, const int *flagged, int64_t *idx_out, int *counters) {
+// numpy's own algorithm -- cdf = cumsum(float64(probs)) strictly left to right, cdf /= cdf[-1], searchsorted(side='right') --
+// evaluated exactly for the samples the test above could not certify, by ONE warp whose lanes all track the same running sum.
+// The sequential sum is not walked element by element: a chunk of 1024 probabilities is JUMPED with one addition when that is
+// provably what the element-wise loop computes:
+//   * the chunk holds no "fine" element (every probability is an integer multiple of 2^-52), so its parallel float64 sum is exact, and
+//   * S and S + chunk_sum lie in the same binade [2^e, 2^(e+1)), e <= 0: every partial sum then is a multiple of ulp = 2^(e-52) inside
+//     that binade, i.e. exactly representable -- the sequential additions never round, and their result is S + chunk_sum.
+// Chunks with a fine element or a binade crossing (a few dozen at most: the running sum only grows) are added element by element
+// from shared memory.  Cost ~0.2 ms instead of ~50 ms for the plain loop over 1 M elements, so the rare fallback is no cliff.
+__device__ __forceinline__ int f64_exponent(double x) { return (int)((__double_as_longlong(x) >> 52) & 0x7ff); }
+__device__ void exact_pass(const float *p_alpha, int64_t n, float tot, double *carry_exact, const double *chunk_sum, const int *chunk_fine, int n_chunks,
+                           const double *u, int B, const int *flagged, int64_t *idx_out, int *counters, float *s_q /* [kChunk] shared */) {
     const int lane = threadIdx.x;      // warp 0 only
-    if (lane == 0) {
-        double acc = 0.0;
-        for (int64_t i = 0; i < n; i++) { acc = __dadd_rn(acc, (double)__fdiv_rn(p_alpha[i], tot)); cdf[i] = acc; }
-        counters[2] += 1;
-    }
-    __syncwarp();
-    __threadfence_block();
-    const double last = cdf[n - 1];
-    for (int j = lane; j < B; j += 32) {
-        if (!__ldcg(flagged + j)) continue;
-        const double uu = u[j];
-        int64_t lo = 0, hi = n;
-        while (lo < hi) {
-            const int64_t mid = lo + ((hi - lo) >> 1);
-            if (uu < __ddiv_rn(cdf[mid], last)) hi = mid; else lo = mid + 1;
+    auto stage_chunk = [&](int c) {    // probabilities of chunk c into shared memory (0 beyond n: adding them is exact)
+        const int64_t base = (int64_t)c * kChunk;
+        __syncwarp();
+        for (int k = lane; k < kChunk; k += 32) s_q[k] = base + k < n ? __fdiv_rn(p_alpha[base + k], tot) : 0.f;
+        __syncwarp();
+    };
+    double S = 0.0;
+    for (int c = 0; c < n_chunks; c++) {
+        if (lane == 0) carry_exact[c] = S;      // exact sequential cdf just before chunk c
+        const double cs = __ldcg(chunk_sum + c);
+        const double T = __dadd_rn(S, cs);
+        if (__ldcg(chunk_fine + c) == 0 && S > 0.0 && f64_exponent(T) == f64_exponent(S) && f64_exponent(S) <= 1023) {
+            S = T;
+        } else {
+            stage_chunk(c);
+            for (int k = 0; k < kChunk; k++) S = __dadd_rn(S, (double)s_q[k]);
         }
-        idx_out[j] = lo < n ? lo : n - 1;
+    }
+    if (lane == 0) { carry_exact[n_chunks] = S; counters[2] += 1; }
+    const double last = S;
+    __threadfence_block();
+    __syncwarp();
+    for (int j = 0; j < B; j++) {
+        if (!__ldcg(flagged + j)) continue;      // warp-uniform
+        const double uu = u[j];
+        int lo = 0, hi = n_chunks - 1;           // last chunk c whose preceding cdf value is <= u (chunk 0 always qualifies)
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (__ddiv_rn(__ldcg(carry_exact + mid), last) <= uu) lo = mid; else hi = mid - 1;
+        }
+        stage_chunk(lo);
+        double acc = __ldcg(carry_exact + lo);
+        const int64_t base = (int64_t)lo * kChunk;
+        int cnt = 0;
+        for (int k = 0; k < kChunk && base + k < n; k++) {
+            acc = __dadd_rn(acc, (double)s_q[k]);
+            if (__ddiv_rn(acc, last) <= uu) cnt++; else break;      // monotone: the first cdf value above u ends the count
+        }
+        const int64_t idx = base + cnt;
+        if (lane == 0) idx_out[j] = idx < n ? idx : n - 1;
     }
 }
 
@@ -349,7 +382,8 @@ __device__ void exact_pass(const float *p_alpha, int64_t n, float tot, double *c
 // the exact pass for flagged samples (rare), IS weights (replay_buffer.py:67-68), ring slots for the update's gather.
 __global__ void __launch_bounds__(256) per_search(const float *p_alpha, int64_t n, const float *total, const double *carry, int n_chunks,
                                                   const double *u, int B, int *counters, int64_t *idx_out, int *flagged, int *ticket,
-                                                  double *cdf_exact, float neg_beta, float *weights, int32_t *slots, float *isw_ws, int64_t *idx_copy) {
+                                                  double *carry_exact, const double *chunk_sum, const int *chunk_fine,
+                                                  float neg_beta, float *weights, int32_t *slots, float *isw_ws, int64_t *idx_copy) {
     SACB_PDL_ENTER();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = blockIdx.x * 8 + warp;
@@ -424,7 +458,8 @@ __global__ void __launch_bounds__(256) per_search(const float *p_alpha, int64_t 
     if (!last_block_done(ticket)) return;
     // ---- serial tail (one CTA) ----
     if (__ldcg(counters + 1) != 0) {      // CTA-uniform
-        if (threadIdx.x < 32) exact_pass(p_alpha, n, tot, cdf_exact, u, B, flagged, idx_out, counters);
+        __shared__ float s_q[kChunk];
+        if (threadIdx.x < 32) exact_pass(p_alpha, n, tot, carry_exact, chunk_sum, chunk_fine, n_chunks, u, B, flagged, idx_out, counters, s_q);
         __threadfence_block();
         __syncthreads();
     }
@@ -798,7 +833,7 @@ int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B
                          n_chunks, w.chunk_carry, w.counters, tickets + kTicketInts));
     SACB_CUDA(launch_pdl(per_search, dim3((int)((k + 7) / 8)), dim3(256), 0, st, pdl, pa, n, (const float *)w.total, (const double *)w.chunk_carry, n_chunks,
                          (const double *)w.u, (int)k, w.counters, w.idx, w.flagged, tickets + 2 * kTicketInts,
-                         w.cdf_exact, -(float)beta, w.weights, h->slots, h->ws + h->L.isw, h->last_idx_dev));
+                         w.cdf_exact, (const double *)w.chunk_sum, (const int *)w.chunk_fine, -(float)beta, w.weights, h->slots, h->ws + h->L.isw, h->last_idx_dev));
     h->kernel_launches += 3;
     h->sample_k = k;
     if (k_out) *k_out = k;

@@ -128,6 +128,12 @@ extern "C" int sacb_destroy(sacb_handle h) {
     return SACB_OK;
 }
 
+extern "C" int sacb_get_stream(sacb_handle h, void **stream_out) {
+    if (!h || !stream_out) return fail(SACB_ERR_ARG, "null argument");
+    *stream_out = (void *)h->stream;
+    return SACB_OK;
+}
+
 extern "C" int sacb_synchronize(sacb_handle h) {
     if (!h) return fail(SACB_ERR_ARG, "null handle");
     SACB_CUDA(cudaStreamSynchronize(h->stream));

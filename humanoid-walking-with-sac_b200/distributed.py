@@ -53,28 +53,42 @@ class DataParallelSAC:
             ptr, n = ctypes.c_void_p(), ctypes.c_int64()
             N.check(N.lib().sacb_dp_grad_buffer(agent._h, phase, ctypes.byref(ptr), ctypes.byref(n)))
             self._bufs[phase] = torch.as_tensor(N.DevArray(ptr.value, (n.value,), agent), device=f"cuda:{agent._cfg.device}")
+        sp = ctypes.c_void_p()
+        N.check(N.lib().sacb_get_stream(agent._h, ctypes.byref(sp)))
+        # the library's own stream as a torch stream: the all-reduces are enqueued on it between backward and apply (NCCL orders
+        # itself against the current stream with events), so a step runs without any host synchronisation
+        self._stream = torch.cuda.ExternalStream(sp.value, device=f"cuda:{agent._cfg.device}")
 
     def gradient_slabs(self, phase):
         """Device tensors (aliases of the arena) that are averaged after `phase`: 0 -> [q1|q2], 1 -> [policy, log_alpha block]."""
         return [self._bufs[0]] if phase == 0 else [self._bufs[1], self._bufs[2]]
 
-    def update_parameters(self, batch_size_local, *, idx=None, eps=None):
+    def update_parameters(self, batch_size_local, *, idx=None, eps=None, staged=False, sync=True):
+        """idx / eps: test hooks as in `SAC.update_parameters`; staged=True: the rank's indices were pre-staged on the device
+        (`sacb_stage_indices`); sync=False returns None without reading the losses (throughput mode)."""
         a, lib = self.agent, N.lib()
         a.replay_buffer._flush()
-        ix = a.replay_buffer._draw(batch_size_local) if idx is None else np.ascontiguousarray(idx, np.int64)
+        if staged:
+            ix, n_local = None, int(batch_size_local)
+        else:
+            ix = a.replay_buffer._draw(batch_size_local) if idx is None else np.ascontiguousarray(idx, np.int64)
+            n_local = ix.size
         e_next = e_cur = None
         if eps is not None:
             e_next, e_cur = N.f32(eps[0]), N.f32(eps[1])
+        with torch.cuda.stream(self._stream):
+            for phase in (0, 1):
+                N.check(lib.sacb_dp_backward(a._h, phase, n_local, N.ptr(ix, ctypes.c_int64) if (phase == 0 and ix is not None) else None, N.ptr(e_next), N.ptr(e_cur)))
+                allreduce_mean_(self.gradient_slabs(phase), self.group)       # same stream: ordered behind the backward, ahead of the apply
+                N.check(lib.sacb_dp_apply(a._h, phase))
+        a._alpha_is_float = False
+        if not sync:
+            return None
         losses = np.zeros(3, np.float32)
-        for phase in (0, 1):
-            N.check(lib.sacb_dp_backward(a._h, phase, ix.size, N.ptr(ix, ctypes.c_int64) if phase == 0 else None, N.ptr(e_next), N.ptr(e_cur)))
-            a.synchronize()                                    # the library runs on its own stream; NCCL on torch's
-            allreduce_mean_(self.gradient_slabs(phase), self.group)
-            torch.cuda.synchronize(self._bufs[0].device)
-            N.check(lib.sacb_dp_apply(a._h, phase))
         N.check(lib.sacb_get_losses(a._h, 0, N.ptr(losses)))
         t = torch.from_numpy(losses.copy()).to(self._bufs[0].device)
-        allreduce_mean_([t], self.group)
+        with torch.cuda.stream(self._stream):
+            allreduce_mean_([t], self.group)
+        self._stream.synchronize()
         q1, q2, pi = t.tolist()
-        a._alpha_is_float = False
         return {"q1_loss": q1, "q2_loss": q2, "policy_loss": pi}

@@ -173,6 +173,9 @@ int sacb_policy_forward(sacb_handle h, int agent, const float *s, int64_t n, flo
 int sacb_dp_backward(sacb_handle h, int phase, int64_t B_local, const int64_t *idx, const float *eps_next, const float *eps_cur);
 int sacb_dp_apply(sacb_handle h, int phase);
 int sacb_dp_grad_buffer(sacb_handle h, int phase, void **dev_ptr, int64_t *n_floats);
+/* the handle's private CUDA stream (a cudaStream_t): lets the host enqueue its collective between sacb_dp_backward and
+ * sacb_dp_apply on the SAME stream (torch.cuda.ExternalStream), so a data-parallel step needs no host synchronisation. */
+int sacb_get_stream(sacb_handle h, void **stream_out);
 
 /* ---- instrumentation ---------------------------------------------------------------------------------- */
 typedef struct {

@@ -96,10 +96,11 @@ def test_per_bit_exact_vs_oracle_large(hw, dist, n):
     assert np.mean(idx2 == ref_idx) > 0.99
 
 
-def test_per_ambiguous_samples_take_the_exact_path(hw):
-    """u placed exactly ON cdf boundaries: the certified fast path must flag them and the sequential pass decides."""
-    n = 50000
-    case = dict(n=n, capacity=n, batch=256, seed=41, dist="lognormal3")     # tiny probabilities: bits below 2^-52 ("fine" elements)
+@pytest.mark.parametrize("dist,n", [("lognormal3", 50000), ("halfnormal", 1000000), ("floor1pct", 300000), ("lognormal3", 1000000)])
+def test_per_ambiguous_samples_take_the_exact_path(hw, dist, n):
+    """u placed exactly ON cdf boundaries: the certified fast path must flag them and the exact sequential evaluation decides
+    (chunks without fine elements and without a binade crossing are jumped, the others are walked element by element)."""
+    case = dict(n=n, capacity=n, batch=256, seed=41, dist=dist)     # tiny probabilities: bits below 2^-52 ("fine" elements)
     pri = cases.per_priorities(case)
     pa = (pri ** np.float32(0.6)).astype(np.float32)
     buf = hw.PrioritizedReplayBuffer(n)
