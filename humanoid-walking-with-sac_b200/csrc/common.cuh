@@ -139,6 +139,16 @@ struct alignas(64) Task {
     float f[6];
 };
 
+// Specialised builds of the stage kernel (staged mode): a launch only carries the code its stage can reach, which keeps the
+// register allocation of the hot GEMM paths free of the other paths' pressure and the instruction footprint of a ~10 us kernel small.
+enum StageKind : int32_t {
+    KIND_ANY = 0,        // everything (persistent single-launch mode, fused-sample experiment)
+    KIND_GEMM_PLAIN,     // GEMM tiles with the bias+ReLU / mask / fp32 epilogues only (forward and input-gradient stages)
+    KIND_GEMM_ADAM,      // GEMM tiles with any epilogue but EPI_SAMPLE + the bias / output-layer optimiser tasks (weight-gradient stages)
+    KIND_ELEMENTWISE,    // no GEMM: shadows, gather, sampling, losses, finish
+    KIND_COUNT
+};
+
 constexpr int kMaxStageTasks = 28;
 struct Stage {
     int32_t task_begin, task_end;
