@@ -139,15 +139,32 @@ struct alignas(64) Task {
     float f[6];
 };
 
-// Specialised builds of the stage kernel (staged mode): a launch only carries the code its stage can reach, which keeps the
-// register allocation of the hot GEMM paths free of the other paths' pressure and the instruction footprint of a ~10 us kernel small.
-enum StageKind : int32_t {
-    KIND_ANY = 0,        // everything (persistent single-launch mode, fused-sample experiment)
-    KIND_GEMM_PLAIN,     // GEMM tiles with the bias+ReLU / mask / fp32 epilogues only (forward and input-gradient stages)
-    KIND_GEMM_ADAM,      // GEMM tiles with any epilogue but EPI_SAMPLE + the bias / output-layer optimiser tasks (weight-gradient stages)
-    KIND_ELEMENTWISE,    // no GEMM: shadows, gather, sampling, losses, finish
-    KIND_COUNT
-};
+// Specialised builds of the stage kernel (staged mode): a launch only carries the code its stage can reach -- the task types and
+// GEMM epilogues in its masks -- which keeps the register allocation of the hot paths free of the other paths' pressure (no
+// spills in the forward / element-wise stages) and the instruction footprint of a 3-10 us kernel small.  X(index, task types, epilogues);
+// the host picks the smallest variant that covers a stage, variant 0 (everything) runs the persistent single-launch mode.
+constexpr uint32_t tb(int t) { return 1u << t; }
+constexpr uint32_t kAllTypes = (1u << (T_FINISH + 1)) - 1, kAllEpis = (1u << (EPI_SAMPLE + 1)) - 1;
+constexpr uint32_t kPlainEpis = tb(EPI_F32) | tb(EPI_BIAS_RELU) | tb(EPI_MASK);
+constexpr uint32_t kElemTypes = tb(T_SHADOW) | tb(T_GATHER) | tb(T_SAMPLE) | tb(T_TARGET_LOSS) | tb(T_ACTOR_LOSS) | tb(T_SAMPLE_BWD) | tb(T_FINISH);
+#define SACB_KERNEL_VARIANTS(X)                                                                     \
+    X(0, kAllTypes, kAllEpis)                                                                       \
+    X(1, tb(T_GEMM), tb(EPI_BIAS_RELU))                                                             \
+    X(2, tb(T_GEMM), tb(EPI_MASK))                                                                  \
+    X(3, tb(T_GEMM), tb(EPI_F32))                                                                   \
+    X(4, tb(T_GEMM), kPlainEpis)                                                                    \
+    X(5, tb(T_GEMM) | tb(T_OUT_ADAM), tb(EPI_MASK))                                                 \
+    X(6, tb(T_GEMM) | tb(T_BIAS_ADAM), tb(EPI_ADAM))                                                \
+    X(7, tb(T_GEMM) | tb(T_BIAS_ADAM), tb(EPI_ADAM) | tb(EPI_MASK))                                 \
+    X(8, tb(T_GEMM) | tb(T_BIAS_ADAM) | tb(T_OUT_ADAM), kPlainEpis | tb(EPI_ADAM))                  \
+    X(9, tb(T_SHADOW) | tb(T_GATHER), 0u)                                                           \
+    X(10, tb(T_SAMPLE), 0u)                                                                         \
+    X(11, tb(T_TARGET_LOSS), 0u)                                                                    \
+    X(12, tb(T_ACTOR_LOSS), 0u)                                                                     \
+    X(13, tb(T_SAMPLE_BWD), 0u)                                                                     \
+    X(14, tb(T_FINISH), 0u)                                                                         \
+    X(15, kElemTypes, 0u)
+constexpr int kNumKernelVariants = 16;
 
 constexpr int kMaxStageTasks = 28;
 struct Stage {

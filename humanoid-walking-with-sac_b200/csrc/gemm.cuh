@@ -789,7 +789,7 @@ __device__ __forceinline__ void tc_epilogue(const EpiR &epi, int m0, int n0, int
 }  // namespace tc
 
 // t = shared-memory copy of the task (fields), tg = the task in global memory (TMA descriptors)
-template <int kKind = KIND_ANY>
+template <uint32_t kEpis = kAllEpis>
 __device__ __forceinline__ void gemm_tile_tc(const Task &t, const Task *tg, int tile, const AgentBases &bases, int agent,
                                              const float *scalars, tc::TcState &st, int *error_flag, bool first_tile, uint64_t seed) {
     using namespace tc;
@@ -803,10 +803,10 @@ __device__ __forceinline__ void gemm_tile_tc(const Task &t, const Task *tg, int 
     stamp(2);
     const EpiR epi = resolve_epilogue(t, bases, agent, scalars);
     switch (t.epi) {
-        case EPI_F32: tc_epilogue<EPI_F32>(epi, m0, n0, t.bm, t.bn, st, nkb_mine, error_flag, traced); break;
-        case EPI_BIAS_RELU: tc_epilogue<EPI_BIAS_RELU>(epi, m0, n0, t.bm, t.bn, st, nkb_mine, error_flag, traced); break;
-        case EPI_MASK: tc_epilogue<EPI_MASK>(epi, m0, n0, t.bm, t.bn, st, nkb_mine, error_flag, traced); break;
-        case EPI_SAMPLE: if constexpr (kKind == KIND_ANY) {
+        case EPI_F32: if constexpr ((kEpis & tb(EPI_F32)) != 0) tc_epilogue<EPI_F32>(epi, m0, n0, t.bm, t.bn, st, nkb_mine, error_flag, traced); break;
+        case EPI_BIAS_RELU: if constexpr ((kEpis & tb(EPI_BIAS_RELU)) != 0) tc_epilogue<EPI_BIAS_RELU>(epi, m0, n0, t.bm, t.bn, st, nkb_mine, error_flag, traced); break;
+        case EPI_MASK: if constexpr ((kEpis & tb(EPI_MASK)) != 0) tc_epilogue<EPI_MASK>(epi, m0, n0, t.bm, t.bn, st, nkb_mine, error_flag, traced); break;
+        case EPI_SAMPLE: if constexpr ((kEpis & tb(EPI_SAMPLE)) != 0) {
             SampleEpi se;
             se.head = epi.C; se.bias = epi.bias; se.eps = resolve(t.p[1], bases, agent); se.logp = resolve(t.p[3], bases, agent);
             se.X = resolve_pm(t.pm[0], bases, agent);
@@ -814,7 +814,7 @@ __device__ __forceinline__ void gemm_tile_tc(const Task &t, const Task *tg, int 
             se.step = (uint32_t)__float_as_int(ldcg(scalars + SC_N_UPDATES)); se.agent = (uint32_t)agent; se.seed = seed;
             tc_epilogue<EPI_SAMPLE>(epi, m0, n0, t.bm, t.bn, st, nkb_mine, error_flag, traced, &se);
         } break;
-        default: if constexpr (kKind != KIND_GEMM_PLAIN) tc_epilogue<EPI_ADAM>(epi, m0, n0, t.bm, t.bn, st, nkb_mine, error_flag, traced); break;
+        default: if constexpr ((kEpis & tb(EPI_ADAM)) != 0) tc_epilogue<EPI_ADAM>(epi, m0, n0, t.bm, t.bn, st, nkb_mine, error_flag, traced); break;
     }
     stamp(3);
 }

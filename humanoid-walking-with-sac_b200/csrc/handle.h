@@ -80,7 +80,7 @@ struct ProgramInst {
     std::vector<Task> tasks;
     std::vector<Stage> stages;
     std::vector<int> stage_has_gemm;
-    std::vector<int> stage_kind;         // StageKind: which specialised build of the stage kernel runs the stage (staged mode)
+    std::vector<int> stage_kind;         // kernel variant (SACB_KERNEL_VARIANTS) that runs the stage in staged mode
     Task *d_tasks = nullptr;
     Stage *d_stages = nullptr;
     Program prog{};
@@ -149,7 +149,9 @@ inline size_t math_smem(int m) { return math_is_tc(m) ? (size_t)kTcSmemBytes : (
 // bf16, SWIZZLE_128B.  base = device pointer of the view's first hi element for agent 0.
 int make_pm_tensor_map(CUtensorMap *out, const void *base, int64_t cols, int64_t rows, int64_t ld, int64_t plane_elems,
                        int64_t agent_stride_bytes, int n_agents, int box_rows);
-const void *update_kernel_for(int math_mode, int stage_kind);
+const void *update_kernel_for(int math_mode, int variant);      // variant: index into SACB_KERNEL_VARIANTS (0 = everything)
+bool variant_has_gemm(int variant);
+int pick_variant(uint32_t task_types, uint32_t epilogues);
 // program.cu
 int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out);
 int launch_program(sacb_handle h, ProgramInst &p);

@@ -156,7 +156,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
     tc::fence_proxy_async();
 }
 
-template <int kMath, int kKind>
+template <int kMath, uint32_t kTypes, uint32_t kEpis>
 __global__ void __launch_bounds__(kThreads, 1)
 sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Stage single, const int stage_begin, const int stage_end, const int tc_setup, const uint64_t seed) {
     // `single` = the stage table entry when the launch covers exactly one stage (staged mode): no global load before the first task
@@ -190,7 +190,7 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
     st.full_bar = s_bars; st.empty_bar = s_bars + kTStages; st.accum_bar = s_bars + 2 * kTStages; st.trace = P.trace;
     constexpr bool kTc = kMath != SACB_MATH_FP32;
     st.tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    if (kTc && kKind != KIND_ELEMENTWISE && tc_setup) {
+    if (kTc && (kTypes & tb(T_GEMM)) != 0 && tc_setup) {
         if (threadIdx.x == 0) {
             for (int i = 0; i <= 2 * kTStages; i++) tc::mbar_init(&s_bars[i], 1);
             tc::mbar_init(st.reduce_bar, st.ksplit > 1 ? st.ksplit - 1 : 1);
@@ -244,24 +244,22 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
             }
             float *scalars = resolve(P.scalars, P.bases, agent);
             if (t.type != T_GEMM && st.krank != 0) continue;      // element-wise tasks of a clustered stage run on rank 0 only
-            constexpr bool kGemm = kKind != KIND_ELEMENTWISE, kOpt = kKind == KIND_ANY || kKind == KIND_GEMM_ADAM;
-            constexpr bool kElem = kKind == KIND_ANY || kKind == KIND_ELEMENTWISE;
-            switch (t.type) {
+            switch (t.type) {      // only the task types of this build's mask are compiled in
                 case T_GEMM:
-                    if constexpr (kGemm) {
-                        if (kTc) gemm_tile_tc<kKind>(t, tg, tile, P.bases, agent, scalars, st, P.error_flag, wi == cl, seed);
+                    if constexpr ((kTypes & tb(T_GEMM)) != 0) {
+                        if (kTc) gemm_tile_tc<kEpis>(t, tg, tile, P.bases, agent, scalars, st, P.error_flag, wi == cl, seed);
                         else gemm_tile_ffma(t, tile, P.bases, agent, scalars, reinterpret_cast<float *>(smem_raw));
                     }
                     break;
-                case T_SHADOW: if constexpr (kElem) task_shadow(t, tile, P, agent); break;
-                case T_GATHER: if constexpr (kElem) task_gather(t, tile, P, agent); break;
-                case T_SAMPLE: if constexpr (kElem) task_sample(t, tile, P, agent, scalars, seed); break;
-                case T_TARGET_LOSS: if constexpr (kElem) task_target_loss(t, tile, P, agent, scalars, s_red); break;
-                case T_ACTOR_LOSS: if constexpr (kElem) task_actor_loss(t, tile, P, agent, scalars, s_red); break;
-                case T_SAMPLE_BWD: if constexpr (kElem) task_sample_bwd(t, tile, P, agent, scalars); break;
-                case T_OUT_ADAM: if constexpr (kOpt) task_out_adam(t, tile, P, agent, scalars, s_red); break;
-                case T_BIAS_ADAM: if constexpr (kOpt) task_bias_adam(t, tile, P, agent, scalars, s_red); break;
-                case T_FINISH: if constexpr (kElem) task_finish(t, P, agent, scalars, s_red); break;
+                case T_SHADOW: if constexpr ((kTypes & tb(T_SHADOW)) != 0) task_shadow(t, tile, P, agent); break;
+                case T_GATHER: if constexpr ((kTypes & tb(T_GATHER)) != 0) task_gather(t, tile, P, agent); break;
+                case T_SAMPLE: if constexpr ((kTypes & tb(T_SAMPLE)) != 0) task_sample(t, tile, P, agent, scalars, seed); break;
+                case T_TARGET_LOSS: if constexpr ((kTypes & tb(T_TARGET_LOSS)) != 0) task_target_loss(t, tile, P, agent, scalars, s_red); break;
+                case T_ACTOR_LOSS: if constexpr ((kTypes & tb(T_ACTOR_LOSS)) != 0) task_actor_loss(t, tile, P, agent, scalars, s_red); break;
+                case T_SAMPLE_BWD: if constexpr ((kTypes & tb(T_SAMPLE_BWD)) != 0) task_sample_bwd(t, tile, P, agent, scalars); break;
+                case T_OUT_ADAM: if constexpr ((kTypes & tb(T_OUT_ADAM)) != 0) task_out_adam(t, tile, P, agent, scalars, s_red); break;
+                case T_BIAS_ADAM: if constexpr ((kTypes & tb(T_BIAS_ADAM)) != 0) task_bias_adam(t, tile, P, agent, scalars, s_red); break;
+                case T_FINISH: if constexpr ((kTypes & tb(T_FINISH)) != 0) task_finish(t, P, agent, scalars, s_red); break;
             }
             if (wi == cl) stamp(4);
         }
@@ -275,7 +273,7 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
         asm volatile("griddepcontrol.wait;" ::: "memory");
         asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     }
-    if (kTc && kKind != KIND_ELEMENTWISE && tc_setup) {
+    if (kTc && (kTypes & tb(T_GEMM)) != 0 && tc_setup) {
         tc::tc_fence_before();
         __syncthreads();
         if (threadIdx.x < 32) tc::tmem_dealloc(st.tmem_base, kTN);
@@ -699,8 +697,8 @@ int check_error_flag(sacb_handle h) {
 // one stage = one launch (staged mode): grid = tiles x ksplit, thread-block cluster of ksplit CTAs along x, optional PDL
 static int launch_stage(sacb_handle h, ProgramInst &p, int s, bool pdl) {
     const bool tc = math_is_tc(h->cfg.math_mode);
-    const int kind = p.stage_kind[s];
-    const size_t smem = kind == KIND_ELEMENTWISE ? 0 : math_smem(h->cfg.math_mode);      // element-wise stages only use static shared memory
+    const int kind = p.stage_kind[s];      // index of the kernel variant
+    const size_t smem = variant_has_gemm(kind) ? math_smem(h->cfg.math_mode) : 0;      // element-wise stages only use static shared memory
     uint64_t seed = h->cfg.seed;
     int s0 = s, s1 = s + 1, tc_setup = tc ? p.stage_has_gemm[s] : 0;
     Stage single = p.stages[s];
@@ -743,7 +741,7 @@ static int launch_range(sacb_handle h, ProgramInst &p, int s0, int s1, bool coop
     int tc_setup = tf32 ? needs_tc : 0;
     Stage single = p.stages[s0];
     void *args[] = {(void *)&p.prog, (void *)&single, (void *)&s0, (void *)&s1, (void *)&tc_setup, (void *)&seed};
-    const void *fn = update_kernel_for(h->cfg.math_mode, KIND_ANY);
+    const void *fn = update_kernel_for(h->cfg.math_mode, 0);
     if (cooperative) {
         const int grid = std::min(max_tiles, h->sm_count * h->coop_blocks_per_sm);
         SACB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, h->stream));
@@ -798,21 +796,13 @@ int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out) {
     }
     ProgramInst &p = h->programs[key];
     p.tasks = b.tasks; p.stages = b.stages; p.stage_has_gemm = b.has_gemm;
-    for (size_t s = 0; s < b.stages.size(); s++) {      // which specialised build of the stage kernel can run the stage
-        bool gemm = false, adam = false, opt = false, elem = false, sample_epi = false;
+    for (size_t s = 0; s < b.stages.size(); s++) {      // the smallest build of the stage kernel that covers the stage
+        uint32_t types = 0, epis = 0;
         for (int k = b.stages[s].task_begin; k < b.stages[s].task_end; k++) {
-            const Task &t = b.tasks[k];
-            if (t.type == T_GEMM) { gemm = true; adam |= t.epi == EPI_ADAM; sample_epi |= t.epi == EPI_SAMPLE; }
-            else if (t.type == T_OUT_ADAM || t.type == T_BIAS_ADAM) opt = true;
-            else elem = true;
+            types |= tb(b.tasks[k].type);
+            if (b.tasks[k].type == T_GEMM) epis |= tb(b.tasks[k].epi);
         }
-        int kind = KIND_ANY;
-        if (!getenv("SACB_ONE_KERNEL") && !sample_epi) {
-            if (!gemm && !opt) kind = KIND_ELEMENTWISE;
-            else if (!elem && !adam && !opt) kind = KIND_GEMM_PLAIN;
-            else if (!elem) kind = KIND_GEMM_ADAM;
-        }
-        p.stage_kind.push_back(kind);
+        p.stage_kind.push_back(getenv("SACB_ONE_KERNEL") ? 0 : pick_variant(types, epis));
     }
     for (auto &s : p.stages) { p.n_tiles_total += s.n_tiles; p.max_stage_tiles = std::max(p.max_stage_tiles, s.n_tiles); }
     SACB_CUDA(cudaMalloc(&p.d_tasks, p.tasks.size() * sizeof(Task)));
@@ -1009,7 +999,7 @@ extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap
         grid = std::min(grid, h->sm_count);
         for (int r = 0; r < 3; r++) {
             SACB_CUDA(cudaMemsetAsync(h->barrier, 0, sizeof(unsigned int), h->stream));
-            SACB_CUDA(cudaLaunchCooperativeKernel(update_kernel_for(h->cfg.math_mode, KIND_ANY), dim3(grid), dim3(kThreads), args, math_smem(h->cfg.math_mode), h->stream));
+            SACB_CUDA(cudaLaunchCooperativeKernel(update_kernel_for(h->cfg.math_mode, 0), dim3(grid), dim3(kThreads), args, math_smem(h->cfg.math_mode), h->stream));
         }
         SACB_CUDA(cudaStreamSynchronize(h->stream));
         SACB_CUDA(cudaMemcpy(h_trace.data(), d_trace, sizeof(unsigned long long) * kTraceSlots * grid, cudaMemcpyDeviceToHost));
@@ -1030,26 +1020,44 @@ extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap
 }
 
 namespace sacb {
+struct KernelVariant { uint32_t types, epis; };
+static const KernelVariant kVariants[kNumKernelVariants] = {
+#define X(i, t, e) {(t), (e)},
+    SACB_KERNEL_VARIANTS(X)
+#undef X
+};
+bool variant_has_gemm(int v) { return (kVariants[v].types & tb(T_GEMM)) != 0; }
+int pick_variant(uint32_t types, uint32_t epis) {
+    int best = 0, best_bits = 1 << 30;
+    for (int v = 0; v < kNumKernelVariants; v++) {
+        if ((kVariants[v].types & types) != types || (kVariants[v].epis & epis) != epis) continue;
+        const int bits = __builtin_popcount(kVariants[v].types) * 8 + __builtin_popcount(kVariants[v].epis);
+        if (bits < best_bits) { best_bits = bits; best = v; }
+    }
+    return best;
+}
 template <int kMath>
-static const void *kernel_of_kind(int kind) {
-    switch (kind) {
-        case KIND_GEMM_PLAIN: return (const void *)sac_update_kernel<kMath, KIND_GEMM_PLAIN>;
-        case KIND_GEMM_ADAM: return (const void *)sac_update_kernel<kMath, KIND_GEMM_ADAM>;
-        case KIND_ELEMENTWISE: return (const void *)sac_update_kernel<kMath, KIND_ELEMENTWISE>;
-        default: return (const void *)sac_update_kernel<kMath, KIND_ANY>;
+static const void *kernel_of_variant(int v) {
+    switch (v) {
+#define X(i, t, e) case i: return (const void *)sac_update_kernel<kMath, (t), (e)>;
+        SACB_KERNEL_VARIANTS(X)
+#undef X
+        default: return nullptr;
     }
 }
-const void *update_kernel_for(int m, int kind) {
-    return m == SACB_MATH_BF16X3 ? kernel_of_kind<SACB_MATH_BF16X3>(kind) : kernel_of_kind<SACB_MATH_FP32>(kind);
+const void *update_kernel_for(int m, int variant) {
+    // the fp32 (FFMA) math mode is the checker: one build with everything (element-wise stages still launch without dynamic smem)
+    if (m != SACB_MATH_BF16X3) return (const void *)sac_update_kernel<SACB_MATH_FP32, kAllTypes, kAllEpis>;
+    return kernel_of_variant<SACB_MATH_BF16X3>(variant);
 }
 int init_kernel_attributes(sacb_handle h) {
     const int m = h->cfg.math_mode;
     if (m != SACB_MATH_FP32 && m != SACB_MATH_BF16X3) return fail(SACB_ERR_ARG, "bad math_mode");
-    for (int kind = 0; kind < KIND_COUNT; kind++)
-        if (kind != KIND_ELEMENTWISE)
-            SACB_CUDA(cudaFuncSetAttribute(update_kernel_for(m, kind), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)math_smem(m)));
+    for (int v = 0; v < kNumKernelVariants; v++)
+        if (variant_has_gemm(v))
+            SACB_CUDA(cudaFuncSetAttribute(update_kernel_for(m, v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)math_smem(m)));
     int nb = 0;
-    SACB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, update_kernel_for(m, KIND_ANY), kThreads, math_smem(m)));
+    SACB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, update_kernel_for(m, 0), kThreads, math_smem(m)));
     h->coop_blocks_per_sm = std::max(1, std::min(nb, math_is_tc(m) ? 2 : 4));
     return SACB_OK;
 }
