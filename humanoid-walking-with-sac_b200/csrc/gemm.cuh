@@ -458,6 +458,7 @@ __device__ __forceinline__ void store_pm4(const Pm &p, int m, int n, int N, cons
     }
 }
 
+constexpr int kAdamRowGroups = 2;      // pass A of the Adam epilogue handles 4 / kAdamRowGroups of a thread's rows at a time
 // Adam (+ Polyak, + shadow refresh) on one weight element; g = gradient
 struct AdamOut { float m, v, w, t; };
 __device__ __forceinline__ AdamOut adam_math(const EpiR &e, float g, float w, float m, float v, float wt) {
@@ -479,36 +480,40 @@ __device__ __forceinline__ AdamOut adam_math(const EpiR &e, float g, float w, fl
 __device__ __forceinline__ void adam_epilogue_tile(const EpiR &e, float *Cs, int m0, int n0, int row_lo, int row_hi) {
     const int tid = threadIdx.x;     // only rows [row_lo, row_hi) of the tile belong to this CTA (split-K cluster)
     const int ncols = min(kTN, e.N - n0);      // valid columns of this tile (> 0)
-    {   // ---- pass A
+#pragma unroll 1
+    for (int half = 0; half < kAdamRowGroups; half++) {   // ---- pass A, kAdamRows rows of a thread at a time (register budget)
         const int j16 = tid & 15, r0 = tid >> 4;
-        int mrow[4], c[4];
-        bool vec[4];
-        float4 w[4], mm[4], vv[4], wt[4];
+        constexpr int R = 4 / kAdamRowGroups;
+        int mrow[R], c[R];
+        bool vec[R];
+        float4 w[R], mm[R], vv[R], wt[R];
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            mrow[i] = m0 + 32 * i + r0;
-            const int a0 = (4 - (int)(((int64_t)mrow[i] * e.N + n0) & 3)) & 3;
-            c[i] = a0 + 4 * j16;
-            vec[i] = mrow[i] < e.M && c[i] + 3 < ncols && 32 * i + r0 >= row_lo && 32 * i + r0 < row_hi;
-            w[i] = mm[i] = vv[i] = wt[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (vec[i] && e.apply) {
-                const int64_t o = (int64_t)mrow[i] * e.N + n0 + c[i];
-                w[i] = __ldcg(reinterpret_cast<const float4 *>(e.w + o));
-                mm[i] = __ldcg(reinterpret_cast<const float4 *>(e.m + o));
-                vv[i] = __ldcg(reinterpret_cast<const float4 *>(e.v + o));
-                if (e.wt) wt[i] = __ldcg(reinterpret_cast<const float4 *>(e.wt + o));
+        for (int ii = 0; ii < R; ii++) {
+            const int i = half * R + ii;
+            mrow[ii] = m0 + 32 * i + r0;
+            const int a0 = (4 - (int)(((int64_t)mrow[ii] * e.N + n0) & 3)) & 3;
+            c[ii] = a0 + 4 * j16;
+            vec[ii] = mrow[ii] < e.M && c[ii] + 3 < ncols && 32 * i + r0 >= row_lo && 32 * i + r0 < row_hi;
+            w[ii] = mm[ii] = vv[ii] = wt[ii] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (vec[ii] && e.apply) {
+                const int64_t o = (int64_t)mrow[ii] * e.N + n0 + c[ii];
+                w[ii] = __ldcg(reinterpret_cast<const float4 *>(e.w + o));
+                mm[ii] = __ldcg(reinterpret_cast<const float4 *>(e.m + o));
+                vv[ii] = __ldcg(reinterpret_cast<const float4 *>(e.v + o));
+                if (e.wt) wt[ii] = __ldcg(reinterpret_cast<const float4 *>(e.wt + o));
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-            if (!vec[i]) continue;
-            float *cs = Cs + (32 * i + r0) * kCsLd + c[i];
-            const int64_t o = (int64_t)mrow[i] * e.N + n0 + c[i];
+        for (int ii = 0; ii < R; ii++) {
+            const int i = half * R + ii;
+            if (!vec[ii]) continue;
+            float *cs = Cs + (32 * i + r0) * kCsLd + c[ii];
+            const int64_t o = (int64_t)mrow[ii] * e.N + n0 + c[ii];
             const float g[4] = {cs[0], cs[1], cs[2], cs[3]};
             if (e.gexp) *reinterpret_cast<float4 *>(e.gexp + o) = make_float4(g[0], g[1], g[2], g[3]);
             if (!e.apply) continue;
-            const AdamOut a = adam_math(e, g[0], w[i].x, mm[i].x, vv[i].x, wt[i].x), b = adam_math(e, g[1], w[i].y, mm[i].y, vv[i].y, wt[i].y);
-            const AdamOut cc = adam_math(e, g[2], w[i].z, mm[i].z, vv[i].z, wt[i].z), d = adam_math(e, g[3], w[i].w, mm[i].w, vv[i].w, wt[i].w);
+            const AdamOut a = adam_math(e, g[0], w[ii].x, mm[ii].x, vv[ii].x, wt[ii].x), b = adam_math(e, g[1], w[ii].y, mm[ii].y, vv[ii].y, wt[ii].y);
+            const AdamOut cc = adam_math(e, g[2], w[ii].z, mm[ii].z, vv[ii].z, wt[ii].z), d = adam_math(e, g[3], w[ii].w, mm[ii].w, vv[ii].w, wt[ii].w);
             *reinterpret_cast<float4 *>(e.m + o) = make_float4(a.m, b.m, cc.m, d.m);
             *reinterpret_cast<float4 *>(e.v + o) = make_float4(a.v, b.v, cc.v, d.v);
             *reinterpret_cast<float4 *>(e.w + o) = make_float4(a.w, b.w, cc.w, d.w);
