@@ -254,7 +254,7 @@ def run_ours(args):
                 "traffic_source": "profiles/r01_update_stages_ncu.csv: dram__bytes_read.sum + dram__bytes_write.sum summed over the stage kernels of one update (algorithmic bytes if streamed from HBM: 63.7e6; the state stays L2 resident)",
                 "kernel": "sac_update_kernel (one fused update program: %d launches/step in '%s' mode)" % (1 if args.launch == "persistent" else n_st, args.launch),
                 "ms_per_launch_sum": upd_ms.value, "peak_source": peak_src + " bf16 dense, sustained (each product costs 3 bf16 MMAs: algorithmic FLOPs are counted once)",
-                "note": "single-agent B=256 is latency/occupancy bound (SURVEY 8d): ~20 dependent GEMM stages of <=0.3 GFLOP",
+                "note": "single-agent B=256 is latency/occupancy bound (SURVEY 8d): 26 dependent stages of <=0.27 GFLOP, ~3 us of fixed cost each (profiles/r01_summary.md)",
                 "stage_us": [round(float(stage_us[i]), 2) for i in range(max(0, min(n_st, 64)))],
                 "per_sample": {"ms_per_call": per_call_ms, "samples_per_s": B / (per_call_ms * 1e-3),
                                "achieved_GBps": (3 * 4.0 * CAPACITY + B * 4 * (2 * OBS + ACT + 2)) / (per_call_ms * 1e-3) / 1e9,
