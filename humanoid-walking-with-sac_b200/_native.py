@@ -92,6 +92,7 @@ SIGNATURES = {
     "sacb_stage_indices": (I, [H, c_i64p, I64, I64]),
     "sacb_get_losses": (I, [H, I, c_f32p]),
     "sacb_select_action": (I, [H, I, c_f32p, I, c_f32p, c_f32p]),
+    "sacb_select_action_batch": (I, [H, c_f32p, I, c_f32p, c_f32p]),
     "sacb_q_forward": (I, [H, I, I, c_f32p, c_f32p, I64, c_f32p]),
     "sacb_policy_forward": (I, [H, I, c_f32p, I64, c_f32p, c_f32p]),
     "sacb_dp_backward": (I, [H, I, I64, c_i64p, c_f32p, c_f32p]),

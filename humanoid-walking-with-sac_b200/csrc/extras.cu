@@ -1,4 +1,5 @@
 // Row-wise network evaluation (select_action, QNetwork / GaussianPolicy callables) and the tensor-core self test.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include <algorithm>
@@ -73,13 +74,111 @@ static size_t mlp_smem(const MlpArgs &a) { return sizeof(float) * 2 * std::max(a
 }  // namespace sacb
 using namespace sacb;
 
-// scratch inside the workspace that the update does not need between steps: head_raw / g_head / eps regions are
-// step-local, but a concurrent select_action must not clobber them -> use the pinned buffer + stage_rows instead.
-extern "C" int sacb_select_action(sacb_handle h, int agent, const float *obs, int evaluate, const float *eps, float *action_out) {
-    if (!h || !obs || !action_out || agent < 0 || agent >= h->cfg.n_agents) return fail(SACB_ERR_ARG, "bad argument");
+namespace sacb {
+// ---- select_action: one launch per layer, the output rows of a layer spread over many CTAs -------------------------------------
+// A single CTA reading the whole policy (2.9 MB fp32 for 3x512 on 348 inputs) is bound by one SM's L2 ingest (~30 us); 16 output
+// rows per CTA put every layer on 32 SMs, and programmatic dependent launch hides the launch latency of the 5-kernel chain.
+struct LayerArgs { const float *w, *b; int in, out, relu; int64_t agent_stride; };
+
+__global__ void __launch_bounds__(512) mlp_layer_kernel(LayerArgs a, const float *x, int ldx, float *y, int ldy, int rows_per_agent) {
+    extern __shared__ float sx[];
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const int row = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t ao = (int64_t)(row / rows_per_agent) * a.agent_stride;
+    for (int j = threadIdx.x; j < a.in; j += blockDim.x) sx[j] = __ldcg(x + (int64_t)row * ldx + j);
+    __syncthreads();
+    const int o = blockIdx.x * 16 + warp;
+    if (o >= a.out) return;
+    const float *wr = a.w + ao + (int64_t)o * a.in;
+    float s = 0.f;
+    if (a.in % 4 == 0 && (reinterpret_cast<uintptr_t>(wr) & 15) == 0) {
+        for (int j = lane * 4; j < a.in; j += 128) {
+            const float4 w4 = __ldcg(reinterpret_cast<const float4 *>(wr + j));
+            s = fmaf(w4.x, sx[j], s); s = fmaf(w4.y, sx[j + 1], s); s = fmaf(w4.z, sx[j + 2], s); s = fmaf(w4.w, sx[j + 3], s);
+        }
+    } else {
+        for (int j = lane; j < a.in; j += 32) s = fmaf(__ldcg(wr + j), sx[j], s);
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+        s += __ldcg(a.b + ao + o);
+        y[(int64_t)row * ldy + o] = a.relu ? fmaxf(s, 0.f) : s;
+    }
+}
+
+__global__ void action_pdl_kernel(const float *head, const float *eps, int n, int A, int evaluate, float scale, float bias, float *act, uint64_t seed, uint32_t counter) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n * A) return;
+    const int r = i / A, c = i % A;
+    const float mean = __ldcg(head + (int64_t)r * 2 * A + c), ls = __ldcg(head + (int64_t)r * 2 * A + A + c);
+    if (evaluate) { act[i] = tanhf(mean) * scale + bias; return; }
+    const float e = eps ? eps[i] : philox_normal(seed, 0x5e1ec7u, counter, (uint32_t)r, (uint32_t)c);
+    act[i] = sample_elem(mean, ls, e, scale, bias).action;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// policy forward + action for `rows` observations (rows_per_agent consecutive rows belong to one agent, first agent = agent0);
+// obs / eps / action travel through pinned memory, one synchronisation
+static int select_action_rows(sacb_handle h, int agent0, int rows, int rows_per_agent, const float *obs, int evaluate, const float *eps, float *action_out) {
+    const int O = h->cfg.obs_dim, A = h->cfg.act_dim, H = h->cfg.hidden_dim, nh = h->cfg.n_hidden;
+    const int64_t per_row = align_up(O, 4) + 2 * (int64_t)H + align_up(2 * A, 4) + 2 * align_up(A, 4);
+    if (h->act_rows < rows) {
+        cudaFree(h->act_ws); if (h->pin_act) cudaFreeHost(h->pin_act);
+        h->act_ws = nullptr; h->pin_act = nullptr; h->act_rows = 0;
+        if (cudaMalloc(&h->act_ws, sizeof(float) * per_row * rows) != cudaSuccess || cudaMallocHost(&h->pin_act, sizeof(float) * (O + 2 * A) * rows) != cudaSuccess)
+            return fail(SACB_ERR_NOMEM, "select_action scratch allocation failed");
+        h->act_rows = rows;
+    }
+    float *d_obs = h->act_ws, *d_h0 = d_obs + (int64_t)align_up(O, 4) * rows, *d_h1 = d_h0 + (int64_t)H * rows;
+    float *d_head = d_h1 + (int64_t)H * rows, *d_eps = d_head + (int64_t)align_up(2 * A, 4) * rows, *d_act = d_eps + (int64_t)align_up(A, 4) * rows;
+    float *p_obs = h->pin_act, *p_eps = p_obs + (int64_t)O * rows, *p_act = p_eps + (int64_t)A * rows;
+    const bool use_eps = eps && !evaluate;
+    memcpy(p_obs, obs, sizeof(float) * O * rows);      // the previous call synchronised: the pinned block is free
+    SACB_CUDA(cudaMemcpyAsync(d_obs, p_obs, sizeof(float) * O * rows, cudaMemcpyHostToDevice, h->stream));
+    if (use_eps) {
+        memcpy(p_eps, eps, sizeof(float) * A * rows);
+        SACB_CUDA(cudaMemcpyAsync(d_eps, p_eps, sizeof(float) * A * rows, cudaMemcpyHostToDevice, h->stream));
+    }
+    const NetLayout &nl = h->L.pol;
+    const float *base = h->arena + (int64_t)agent0 * h->L.arena_size + h->L.param[SACB_NET_POLICY];
+    const float *x = d_obs; int ldx = O;
+    float *bufs[2] = {d_h0, d_h1};
+    for (int l = 0; l <= nh; l++) {
+        LayerArgs a;
+        a.w = base + (l < nh ? nl.w[l] : nl.w_out); a.b = base + (l < nh ? nl.b[l] : nl.b_out);
+        a.in = l == 0 ? O : H; a.out = l < nh ? H : 2 * A; a.relu = l < nh; a.agent_stride = h->L.arena_size;
+        float *y = l < nh ? bufs[l & 1] : d_head;
+        const int ldy = l < nh ? H : 2 * A;
+        SACB_CUDA(launch_chain(mlp_layer_kernel, dim3((a.out + 15) / 16, rows), dim3(512), sizeof(float) * a.in, h->stream, a, x, ldx, y, ldy, rows_per_agent));
+        x = y; ldx = ldy;
+    }
+    static uint32_t counter = 0;
+    SACB_CUDA(launch_chain(action_pdl_kernel, dim3((rows * A + 127) / 128), dim3(128), 0, h->stream, (const float *)d_head, (const float *)(use_eps ? d_eps : nullptr),
+                           rows, A, evaluate, h->cfg.action_scale, h->cfg.action_bias, d_act, h->cfg.seed, counter++));
+    h->kernel_launches += nh + 2;
+    SACB_CUDA(cudaMemcpyAsync(p_act, d_act, sizeof(float) * A * rows, cudaMemcpyDeviceToHost, h->stream));
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    memcpy(action_out, p_act, sizeof(float) * A * rows);
+    return SACB_OK;
+}
+}  // namespace sacb
+
+// the first version (one CTA walks the whole policy, pageable copies), kept behind SACB_ACT_SINGLE_CTA=1 for A/B timing
+static int select_action_single_cta(sacb_handle h, int agent, const float *obs, int evaluate, const float *eps, float *action_out) {
     const int O = h->cfg.obs_dim, A = h->cfg.act_dim;
     float *d_obs = h->stage_rows, *d_head = d_obs + align_up(O, 4), *d_eps = d_head + align_up(2 * A, 4), *d_act = d_eps + align_up(A, 4);
-    static_assert(sizeof(float) == 4, "");
     SACB_CUDA(cudaMemcpyAsync(d_obs, obs, sizeof(float) * O, cudaMemcpyHostToDevice, h->stream));
     if (eps && !evaluate) SACB_CUDA(cudaMemcpyAsync(d_eps, eps, sizeof(float) * A, cudaMemcpyHostToDevice, h->stream));
     MlpArgs a = mlp_args(h, agent, SACB_NET_POLICY);
@@ -92,6 +191,18 @@ extern "C" int sacb_select_action(sacb_handle h, int agent, const float *obs, in
     SACB_CUDA(cudaMemcpyAsync(action_out, d_act, sizeof(float) * A, cudaMemcpyDeviceToHost, h->stream));
     SACB_CUDA(cudaStreamSynchronize(h->stream));
     return SACB_OK;
+}
+
+extern "C" int sacb_select_action(sacb_handle h, int agent, const float *obs, int evaluate, const float *eps, float *action_out) {
+    if (!h || !obs || !action_out || agent < 0 || agent >= h->cfg.n_agents) return fail(SACB_ERR_ARG, "bad argument");
+    static const bool single = getenv("SACB_ACT_SINGLE_CTA") != nullptr;
+    if (single) return select_action_single_cta(h, agent, obs, evaluate, eps, action_out);
+    return select_action_rows(h, agent, 1, 1, obs, evaluate, eps, action_out);
+}
+
+extern "C" int sacb_select_action_batch(sacb_handle h, const float *obs, int evaluate, const float *eps, float *action_out) {
+    if (!h || !obs || !action_out) return fail(SACB_ERR_ARG, "bad argument");
+    return select_action_rows(h, 0, h->cfg.n_agents, 1, obs, evaluate, eps, action_out);
 }
 
 extern "C" int sacb_q_forward(sacb_handle h, int agent, int net, const float *s, const float *a, int64_t n, float *q_out) {

@@ -118,6 +118,8 @@ extern "C" int sacb_destroy(sacb_handle h) {
     if (h->pin) cudaFreeHost(h->pin);
     if (h->pin_small) cudaFreeHost(h->pin_small);
     if (h->pin_push) cudaFreeHost(h->pin_push);
+    cudaFree(h->act_ws);
+    if (h->pin_act) cudaFreeHost(h->pin_act);
     if (h->ev_push) cudaEventDestroy(h->ev_push);
     if (h->pin_rows) cudaFreeHost(h->pin_rows);
     if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }

@@ -161,6 +161,9 @@ int sacb_get_losses(sacb_handle h, int agent, float *losses_out);
 /* ---- SAC.select_action (sac_imp.py:54-72) -------------------------------------------------------------- */
 int sacb_select_action(sacb_handle h, int agent, const float *obs, int evaluate, const float *eps_or_null,
                        float *action_out);
+/* population form: obs [n_agents, obs_dim] -> action_out [n_agents, act_dim], agent i acts on row i with its
+ * own policy; eps_or_null [n_agents, act_dim].  One chain of launches for the whole population. */
+int sacb_select_action_batch(sacb_handle h, const float *obs, int evaluate, const float *eps_or_null, float *action_out);
 
 /* ---- networks as callables (QNetwork.forward, GaussianPolicy.forward / .sample) on n rows -------------- */
 int sacb_q_forward(sacb_handle h, int agent, int net, const float *s, const float *a, int64_t n, float *q_out);

@@ -70,6 +70,16 @@ def test_population_equals_independent_agents(hw):
                     out = np.empty(p.numel(), np.float32)
                     N.check(lib.sacb_export_tensor(h, a, net_id, N.SLOT_PARAM, t, N.ptr(out), out.size))
                     np.testing.assert_array_equal(out.reshape(p.shape), p.detach().cpu().numpy(), err_msg=f"agent {a} {net}.{nm}")
+        # population select_action: row i of the batch acts with agent i's policy, one chain of launches
+        rng = np.random.RandomState(5)
+        obs = rng.standard_normal((n_agents, case["obs"])).astype(np.float32)
+        eps = rng.standard_normal((n_agents, case["act"])).astype(np.float32)
+        for evaluate, e in ((1, None), (0, eps)):
+            act = np.empty((n_agents, case["act"]), np.float32)
+            N.check(lib.sacb_select_action_batch(h, N.ptr(obs), evaluate, N.ptr(e), N.ptr(act)))
+            for a, agent in enumerate(singles):
+                ref = agent.select_action(obs[a], evaluate=bool(evaluate), eps=None if e is None else e[a:a + 1])
+                np.testing.assert_array_equal(act[a], ref, err_msg=f"agent {a} evaluate={evaluate}")
     finally:
         lib.sacb_destroy(h)
 
