@@ -138,6 +138,9 @@ struct sacb_handle_s {
     float *pin_push = nullptr;           // staging of small pushes (<= kPinPushRows rows): no synchronisation on the push path
     cudaEvent_t ev_push = nullptr;       // the H2D copy out of pin_push has completed
     bool push_in_flight = false;
+    double *pin_u = nullptr;             // pinned block for the host-drawn PER uniforms
+    cudaEvent_t ev_u = nullptr;
+    bool u_in_flight = false;
     float *act_ws = nullptr, *pin_act = nullptr;   // select_action scratch (device) and pinned obs / eps / action block
     int act_rows = 0;
     int64_t pin_rows_cap = 0;

@@ -820,7 +820,17 @@ int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B
     const int64_t frame = h->per_frame[0];
     const double beta = std::min(1.0, (double)h->cfg.per_beta_start + (double)frame * (1.0 - (double)h->cfg.per_beta_start) / (double)h->cfg.per_beta_frames);
     h->per_frame[0] = frame + 1;
-    if (u) SACB_CUDA(cudaMemcpyAsync(w.u, u, sizeof(double) * k, cudaMemcpyHostToDevice, st));
+    if (u) {      // host-drawn uniforms (np.random.random_sample inside np.random.choice): through pinned memory, no pageable staging
+        if (!h->pin_u) {
+            if (cudaMallocHost(&h->pin_u, sizeof(double) * h->cfg.max_batch) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_u, cudaEventDisableTiming) != cudaSuccess)
+                return fail(SACB_ERR_NOMEM, "pinned allocation failed");
+        }
+        if (h->u_in_flight) SACB_CUDA(cudaEventSynchronize(h->ev_u));      // the previous copy out of the block (long done)
+        memcpy(h->pin_u, u, sizeof(double) * k);
+        SACB_CUDA(cudaMemcpyAsync(w.u, h->pin_u, sizeof(double) * k, cudaMemcpyHostToDevice, st));
+        SACB_CUDA(cudaEventRecord(h->ev_u, st));
+        h->u_in_flight = true;
+    }
     const int depth = top_depth_of(n);
     if (depth > 11) return fail(SACB_ERR_ARG, "capacity too large for the summation heap");
     const float *pa = h->p_alpha;

@@ -118,6 +118,8 @@ extern "C" int sacb_destroy(sacb_handle h) {
     if (h->pin) cudaFreeHost(h->pin);
     if (h->pin_small) cudaFreeHost(h->pin_small);
     if (h->pin_push) cudaFreeHost(h->pin_push);
+    if (h->pin_u) cudaFreeHost(h->pin_u);
+    if (h->ev_u) cudaEventDestroy(h->ev_u);
     cudaFree(h->act_ws);
     if (h->pin_act) cudaFreeHost(h->pin_act);
     if (h->ev_push) cudaEventDestroy(h->ev_push);
