@@ -191,7 +191,7 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
     constexpr bool kTc = kMath != SACB_MATH_FP32;
     st.tiles = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     if (kTc && (kTypes & tb(T_GEMM)) != 0 && tc_setup) {
-        if (threadIdx.x == 0) {
+        if (threadIdx.x == 32) {      // warp 1 initialises the barriers while warp 0 allocates tensor memory
             for (int i = 0; i <= 2 * kTStages; i++) tc::mbar_init(&s_bars[i], 1);
             tc::mbar_init(st.reduce_bar, st.ksplit > 1 ? st.ksplit - 1 : 1);
             tc::fence_barrier_init();
