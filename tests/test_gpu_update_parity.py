@@ -142,3 +142,28 @@ def test_device_eps_mode_runs_and_learns(hw):
         l1 = agent.update_from_batch(b)
     assert np.isfinite(list(l1.values())).all()
     assert l1["q1_loss"] < l0["q1_loss"]
+
+
+@pytest.mark.parametrize("B", [2048])
+def test_large_batch_update_matches_oracle(hw, B):
+    """BASELINE.json configs[3] in miniature (one rank's share of a large global batch, C2 nets): stages with many more tiles than
+    SMs run one resident CTA per SM looping over tiles -- same arithmetic, checked against the oracle (losses, every gradient, alpha)."""
+    case = dict(cases.UPDATE_CASES["c2_humanoid_m2"], batch=B, steps=1, seed=77)
+    tol = TOL["bf16x3"]
+    agent, st = make_agent(hw, case, math="bf16x3")
+    b = batch_of(case, 0)
+    got = agent.update_from_batch(b, eps=(b["eps_next"], b["eps_cur"]), export_grads=True)
+    hint = relu_hint(agent, case)
+    ref_losses, aux = O.update_parameters(st, b, return_aux=True, relu_hint=hint)
+    assert hint.mismatch == 0, (hint.mismatch, hint.adopted, hint.ambiguous)
+    for k in ("q1_loss", "q2_loss", "policy_loss"):
+        assert abs(got[k] - ref_losses[k]) <= tol["loss"] * abs(ref_losses[k]) + 1e-6, (k, got[k], ref_losses[k])
+    for net in ("q1", "q2", "policy"):
+        gg = agent.exported_grads(net)
+        for nm, ref in aux[f"{net}_grads"].items():
+            ok, overall, bad = grad_close(gg[nm], ref, tol["grad"], max_flips=0)
+            assert ok, (net, nm, overall, bad)
+    a = agent.alpha
+    a = float(a) if not hasattr(a, "item") else float(a.item())
+    assert abs(a - st.alpha) <= 1e-5 * abs(st.alpha), (a, st.alpha)
+    assert agent.stats()["grid"] > 2 * agent.stats()["sm_count"]      # the widest stage really exceeds two waves (tile-loop CTAs)
