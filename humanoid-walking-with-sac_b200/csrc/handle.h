@@ -138,6 +138,8 @@ struct sacb_handle_s {
     float *pin_push = nullptr;           // staging of small pushes (<= kPinPushRows rows): no synchronisation on the push path
     cudaEvent_t ev_push = nullptr;       // the H2D copy out of pin_push has completed
     bool push_in_flight = false;
+    cudaEvent_t ev_slots = nullptr;      // the H2D copy of the minibatch slots out of `pin` has completed
+    bool slots_in_flight = false;
     double *pin_u = nullptr;             // pinned block for the host-drawn PER uniforms
     cudaEvent_t ev_u = nullptr;
     bool u_in_flight = false;

@@ -616,16 +616,18 @@ int replay_stage_slots(sacb_handle h, const int64_t *idx, int64_t B) {
     const int n = h->cfg.n_agents;
     int32_t *pin = reinterpret_cast<int32_t *>(h->pin);
     if ((int64_t)n * B * (int64_t)sizeof(int32_t) > h->pin_floats * (int64_t)sizeof(float)) return fail(SACB_ERR_ARG, "index set too large");
+    if (!h->ev_slots) SACB_CUDA(cudaEventCreateWithFlags(&h->ev_slots, cudaEventDisableTiming));
+    if (h->slots_in_flight) SACB_CUDA(cudaEventSynchronize(h->ev_slots));      // the previous copy out of the pinned block (long done)
     for (int a = 0; a < n; a++)
         for (int64_t j = 0; j < B; j++) {
             const int64_t lj = idx[a * B + j];
             if (lj < 0 || lj >= h->r_len[a]) return fail(SACB_ERR_STATE, "replay index out of range");
             pin[a * B + j] = (int32_t)physical_slot(h, a, lj);
         }
-    SACB_CUDA(cudaStreamSynchronize(h->stream));   // the pinned buffer is reused by every call
     for (int a = 0; a < n; a++)
         SACB_CUDA(cudaMemcpyAsync(h->slots + (int64_t)a * h->cfg.max_batch, pin + a * B, sizeof(int32_t) * B, cudaMemcpyHostToDevice, h->stream));
-    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    SACB_CUDA(cudaEventRecord(h->ev_slots, h->stream));      // no synchronisation on this path: the update is enqueued right behind
+    h->slots_in_flight = true;
     return SACB_OK;
 }
 

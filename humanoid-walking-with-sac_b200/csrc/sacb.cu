@@ -123,6 +123,7 @@ extern "C" int sacb_destroy(sacb_handle h) {
     cudaFree(h->act_ws);
     if (h->pin_act) cudaFreeHost(h->pin_act);
     if (h->ev_push) cudaEventDestroy(h->ev_push);
+    if (h->ev_slots) cudaEventDestroy(h->ev_slots);
     if (h->pin_rows) cudaFreeHost(h->pin_rows);
     if (h->stream2) { cudaStreamSynchronize(h->stream2); cudaStreamDestroy(h->stream2); }
     if (h->ev_td) cudaEventDestroy(h->ev_td);

@@ -103,3 +103,21 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("the oracle", ""), f
+
+
+def test_range_sample_is_random_sample(hw):
+    """The uniform buffer's index draw: same picks and same consumption of the global `random` stream as
+    `random.sample(range(n), k)` (== `random.sample(deque, k)`, replay_buffer.py:15), on the pool path, the set path, with
+    rejections (n just above a power of two) and with repeated picks (k close to n)."""
+    import random
+    from humanoid_walking_with_sac_b200.replay_buffer import _range_sample
+    for n, k in [(1_000_000, 256), (5000, 256), (1100, 256), (2 ** 20, 256), (2 ** 20 + 1, 64), (300000, 1024), (1046, 256), (100, 7), (123457, 1), (2000, 1500), (7, 0)]:
+        for seed in range(4):
+            random.seed(seed)
+            ref = random.sample(range(n), k)
+            after_ref = random.random()
+            random.seed(seed)
+            got = _range_sample(n, k)
+            assert list(got) == ref and random.random() == after_ref, (n, k, seed)
+    with pytest.raises(ValueError):
+        _range_sample(10, 11)
