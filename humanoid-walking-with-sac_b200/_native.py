@@ -149,7 +149,12 @@ def f32(a):
 
 
 def ptr(a, ctype=ctypes.c_float):
-    return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctype))
+    # ctypes.cast on the raw address: about 3x cheaper than ndarray.ctypes.data_as, and this sits on the per-step path
+    if a is None:
+        return None
+    p = ctypes.cast(a.__array_interface__["data"][0], ctypes.POINTER(ctype))
+    p._owner = a      # keeps a temporary array alive for as long as the pointer object lives (what data_as does)
+    return p
 
 
 def default_config():

@@ -114,7 +114,7 @@ class _DeviceBuffer:
 
     def _flush(self):
         if self._pending:
-            rows = np.ascontiguousarray(np.stack(self._pending))
+            rows = self._pending[0][None, :] if len(self._pending) == 1 else np.ascontiguousarray(np.stack(self._pending))
             self._pending = []
             N.check(N.lib().sacb_push_rows(self._h, 0, N.ptr(rows), rows.shape[0]))
 
