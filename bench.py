@@ -50,12 +50,43 @@ def synth_priorities(n, seed):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe): NVML polled every ~4 ms from a
+    thread (the timed region of a default run is ~70 ms, too short for `nvidia-smi -lms`), `nvidia-smi` as the fallback."""
+
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, gpu):
-        self.rows, self.gpu, self.proc = [], gpu, None
+        self.gpu, self.sm, self.mx, self.reasons, self.proc, self.stop, self.thread, self.rows = gpu, [], [], set(), None, False, None, []
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop:
+            try:
+                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
+                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                for bit, name in self.REASONS:
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def __enter__(self):
+        if self.nvml:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return self
         q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
@@ -68,22 +99,23 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            r = [x.strip() for x in line.split(",")]
+            if len(r) >= 7 and r[0].replace(".", "").isdigit():
+                self.sm.append(float(r[0])); self.mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(name)
 
     def __exit__(self, *a):
+        self.stop = True
+        if self.thread:
+            self.thread.join(timeout=1.0)
         if self.proc:
             self.proc.terminate()
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
-        reasons = set()
-        for r in self.rows:
-            if len(r) >= 7:
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(self.sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def measured_peaks():
@@ -219,7 +251,8 @@ def run_ours(args):
         for _ in range(args.steps):
             device_step()
         N.check(lib.sacb_timer_stop(h, ctypes.byref(ms)))
-        time.sleep(0.15)
+        if not clk.nvml:
+            time.sleep(0.15)
     barrier()
     launches = agent.stats()["kernel_launches"] - st0
     if world > 1:

@@ -152,8 +152,10 @@ def test_buffer_attribute_round_trip(hw):
     assert len(other) == 50 and other.buffer[7][2] == dq[7][2]
 
 
-def test_pipelined_step_equals_sequential(hw):
-    """sacb_per_step (write-back + next sample on a second stream under the tail of the update) == the three calls in sequence, bitwise."""
+@pytest.mark.parametrize("launch", ["staged", "persistent"])
+def test_pipelined_step_equals_sequential(hw, launch):
+    """sacb_per_step (write-back + next sample on a second stream under the tail of the update) == the three calls in sequence, bitwise.
+    (persistent launch mode: the single cooperative launch cannot be split, the PER work simply follows it on the second stream)"""
     import ctypes
     import torch
     from tests.util import make_agent
@@ -168,7 +170,7 @@ def test_pipelined_step_equals_sequential(hw):
     pri[:n] = np.abs(rng.standard_normal(n)) + 1e-6
     agents = []
     for _ in range(2):
-        agent, _st = make_agent(hw, case, math="bf16x3", capacity=cap, replay="per", per_weighted_loss=True)
+        agent, _st = make_agent(hw, case, math="bf16x3", launch=launch, capacity=cap, replay="per", per_weighted_loss=True)
         agent.replay_buffer.push_many(S, A, R, S2, D)
         agent.replay_buffer.set_priorities(pri)
         agents.append(agent)
