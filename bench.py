@@ -324,7 +324,7 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "launch": args.launch, "math": args.math, "replicas": world,
                            "step": "sample(256) -> update -> priority write-back, " + ("sequential on one stream" if args.no_pipeline else
-                                   "software-pipelined: write-back and the next sample run on a second stream once the TD errors exist (sacb_per_step; bitwise equal to the sequential order)"),
+                                   "software-pipelined: write-back and the next sample run on a second stream under the tail of the update (sacb_per_step; bitwise equal to the sequential order)"),
                            "l2_policy": "inputs larger than L2: 1M-row ring (2.9 GB) + 4 MB priority table re-read every step; weights/Adam state (63 MB) stay L2 resident by design"},
                 "e2e": {"value": e2e, "unit": "updates/s", "h2d_bytes_per_step": row_bytes + 8 * B, "d2h_bytes_per_step": 12},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu,

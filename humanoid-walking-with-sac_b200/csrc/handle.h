@@ -85,8 +85,8 @@ struct ProgramInst {
     Stage *d_stages = nullptr;
     Program prog{};
     cudaGraphExec_t graph = nullptr;
-    // the same step as two graphs split behind the critic-loss stage (TD errors exist): sacb_per_step runs the priority
-    // write-back and the next prioritized sample on a second stream while the tail of the update computes
+    // the same step as two graphs split in front of the actor-loss stage (the TD errors exist since the critic-loss stage):
+    // sacb_per_step runs the priority write-back and the next prioritized sample on a second stream under the tail of the update
     cudaGraphExec_t graph_part[2] = {nullptr, nullptr};
     int split = -1;
     int n_tiles_total = 0, max_stage_tiles = 0;

@@ -853,10 +853,18 @@ int launch_program_part(sacb_handle h, ProgramInst &p, int part) {
     }
     const int ns = (int)p.stages.size();
     if (p.split < 0) {
-        for (int s = 0; s < ns && p.split < 0; s++)
-            for (int k = p.stages[s].task_begin; k < p.stages[s].task_end; k++)
-                if (p.tasks[k].type == T_TARGET_LOSS) { p.split = s + 1; break; }
-        if (p.split < 0) return fail(SACB_ERR_STATE, "program has no critic-loss stage");
+        // The replay work may start anywhere behind the critic-loss stage (the TD errors exist from there on).  It is started in front
+        // of the actor-loss stage: the stages from there on (losses, dL/da chain, sample backward, policy backward) leave 20-140 SMs
+        // idle, so the sampler's kernels do not queue behind the wide critic-backward stages (step 0.2215 -> 0.2075 ms at C2).
+        int td_stage = -1, actor_stage = -1;
+        for (int s = 0; s < ns; s++)
+            for (int k = p.stages[s].task_begin; k < p.stages[s].task_end; k++) {
+                if (p.tasks[k].type == T_TARGET_LOSS && td_stage < 0) td_stage = s;
+                if (p.tasks[k].type == T_ACTOR_LOSS && actor_stage < 0) actor_stage = s;
+            }
+        if (td_stage < 0) return fail(SACB_ERR_STATE, "program has no critic-loss stage");
+        p.split = actor_stage > td_stage ? actor_stage : td_stage + 1;
+        if (getenv("SACB_PER_SPLIT")) p.split = std::min(ns - 1, std::max(td_stage + 1, atoi(getenv("SACB_PER_SPLIT"))));      // experiment switch
         for (int part_i = 0; part_i < 2; part_i++) {
             const int s0 = part_i ? p.split : 0, s1 = part_i ? ns : p.split;
             cudaGraph_t graph = nullptr;

@@ -354,7 +354,7 @@ extern "C" int sacb_update(sacb_handle h, int64_t B, const int64_t *idx, const f
 
 // ---- test hook: read back a hidden activation matrix of the last update ----------------------------------------------
 /* One learner step over the prioritized buffer with every input resident in HBM, software-pipelined across two streams:
- *   stream : update stages up to the critic losses (TD errors exist) ............ rest of the update (critic backward, actor, ...)
+ *   stream : update stages up to the updated-critic forward (TD errors exist) ... rest of the update (actor loss, dL/da, policy backward)
  *   stream2:                                          priority write-back |q1 - y| -> prioritized sample for the NEXT step
  * Same kernels, same order of the dependent operations and therefore the same values as sacb_per_sample -> sacb_update(USE_LAST_SAMPLE)
  * -> sacb_per_update_from_td called in sequence (tests/test_gpu_replay.py::test_pipelined_step_equals_sequential). */

@@ -128,7 +128,7 @@ int sacb_per_update_final(sacb_handle h, int agent, const int64_t *idx, const fl
 int sacb_per_update_from_td(sacb_handle h, int agent, int64_t B);
 /* throughput form of the trainer's learner step over the prioritized buffer (trainer.py:202-205 with PER), everything resident
  * in HBM: update on the minibatch the previous call sampled -> priorities <- |q1 - y| -> sample (device uniforms) for the next
- * call.  The write-back and the next sample run on a second stream as soon as the TD errors exist, overlapping the rest of
+ * call.  The write-back and the next sample run on a second stream under the tail of the update (from the actor-loss stage on), overlapping the rest of
  * the update; values are identical to sacb_per_sample / sacb_update(SACB_USE_LAST_SAMPLE) / sacb_per_update_from_td in sequence.
  * A transition pushed between two calls can first be drawn by the call after the next one. */
 int sacb_per_step(sacb_handle h, int64_t B, float *losses_out_or_null, uint32_t flags);
