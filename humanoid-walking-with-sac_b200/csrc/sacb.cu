@@ -264,8 +264,8 @@ static int finish_update(sacb_handle h, float *losses_out, uint32_t flags) {
     if (flags & SACB_NO_LOSS_READBACK) return SACB_OK;
     if (!losses_out) return sacb_synchronize(h);
     // 3 floats D2H (the `.item()` calls of sac_imp.py:141-143) and the device error flag, into pinned memory, ONE synchronisation
-    SACB_CUDA(cudaMemcpyAsync(h->pin_small, h->arena + h->L.scalars + SC_LOSS_Q1, 3 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    SACB_CUDA(cudaMemcpyAsync(h->pin_small + 4, h->error_flag, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    static_assert(SC_ERROR_FLAG == SC_LOSS_Q1 + 4, "losses and the flag copy are contiguous");
+    SACB_CUDA(cudaMemcpyAsync(h->pin_small, h->arena + h->L.scalars + SC_LOSS_Q1, 5 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     SACB_CUDA(cudaStreamSynchronize(h->stream));
     memcpy(losses_out, h->pin_small, 3 * sizeof(float));
     int32_t flag;

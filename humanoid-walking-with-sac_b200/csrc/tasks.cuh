@@ -448,6 +448,7 @@ __device__ __forceinline__ void task_finish(const Task &t, const Program &P, int
             if (t.i[7]) sc[SC_ALPHA0 + ((n_upd + 1) & 1)] = alpha_next;
         }
         if (t.i[4]) sc[SC_N_UPDATES] = __int_as_float(__float_as_int(sc[SC_N_UPDATES]) + 1);
+        sc[SC_ERROR_FLAG] = __int_as_float(*reinterpret_cast<volatile int *>(P.error_flag));      // watchdog flags of the earlier stages
     }
     __syncthreads();      // thread 0 has read the current bias corrections
     if (bump) {

@@ -202,22 +202,25 @@ class SAC:
         Test hooks: `eps=(eps_next, eps_cur)` [B,act] arrays, `idx` positions, `u` uniforms.  sync=False skips the
         blocking read of the three losses (returns None)."""
         buf = self.replay_buffer
-        buf._flush()
         lib = N.lib()
         e_next = e_cur = None
         if eps is not None:
             e_next, e_cur = N.f32(eps[0]), N.f32(eps[1])
         losses = np.zeros(3, np.float32)
         flags = 0 if sync else N.NO_LOSS_READBACK
-        if isinstance(buf, PrioritizedReplayBuffer):
+        per = isinstance(buf, PrioritizedReplayBuffer)
+        if per:      # host-side draws first: everything behind the flush is then enqueued back to back
             n = min(batch_size, len(buf))
             uu = np.ascontiguousarray(np.random.random_sample(n) if u is None else u, np.float64)
+        else:
+            ix = buf._draw(batch_size) if idx is None else np.ascontiguousarray(idx, np.int64)
+        buf._flush()
+        if per:
             N.check(lib.sacb_per_sample(self._h, 0, N.ptr(uu, ctypes.c_double), batch_size, None, None, None, None, None, None, None))
             N.check(lib.sacb_update(self._h, n, None, N.ptr(e_next), N.ptr(e_cur), N.ptr(losses) if sync else None, flags | N.USE_LAST_SAMPLE))
             if self._cfg.per_weighted_loss:
                 N.check(lib.sacb_per_update_from_td(self._h, 0, n))
         else:
-            ix = buf._draw(batch_size) if idx is None else np.ascontiguousarray(idx, np.int64)
             N.check(lib.sacb_update(self._h, ix.size, N.ptr(ix, ctypes.c_int64), N.ptr(e_next), N.ptr(e_cur), N.ptr(losses) if sync else None, flags))
         self._alpha_is_float = False
         if not sync:
