@@ -65,21 +65,27 @@ class ClockSampler:
             vis = os.environ.get("CUDA_VISIBLE_DEVICES")
             phys = int(vis.split(",")[gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu
             self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx.append(float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)))
         except Exception:
             self.nvml = None
 
-    def _poll(self):
+    def sample_now(self):
+        """One sample from the calling thread (the bench calls it while the queued steps are still running on the GPU)."""
         n = self.nvml
+        if not n:
+            return
+        try:
+            self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
+            mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            for bit, name in self.REASONS:
+                if mask & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
+    def _poll(self):
         while not self.stop:
-            try:
-                self.sm.append(float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)))
-                self.mx.append(float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)))
-                mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
-                for bit, name in self.REASONS:
-                    if mask & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
+            self.sample_now()
             time.sleep(0.004)
 
     def __enter__(self):
@@ -250,6 +256,7 @@ def run_ours(args):
         N.check(lib.sacb_timer_start(h))
         for _ in range(args.steps):
             device_step()
+        clk.sample_now()      # the host runs far ahead of the device: the queued steps are executing right now
         N.check(lib.sacb_timer_stop(h, ctypes.byref(ms)))
         if not clk.nvml:
             time.sleep(0.15)
