@@ -145,7 +145,7 @@ enum {
     SACB_NO_LOSS_READBACK = 2, /* do not sync / copy the three loss scalars (throughput mode)                 */
     SACB_EXPORT_GRADS = 4      /* keep the critic/policy gradients in the SACB_SLOT_GRAD arena (tests)        */
 };
-/* idx: B logical indices (NULL => SACB_USE_LAST_SAMPLE or, for the uniform buffer, an on-device draw);
+/* idx: B logical indices (NULL => SACB_USE_LAST_SAMPLE, or the next index set pre-staged with sacb_stage_indices; otherwise SACB_ERR_ARG);
  * eps_next / eps_cur: [B, act] N(0,1) draws of the two policy.sample calls (sac_imp.py:89, :116), NULL => Philox;
  * losses_out[3] = q1_loss, q2_loss, policy_loss (sac_imp.py:140-144). */
 int sacb_update(sacb_handle h, int64_t B, const int64_t *idx, const float *eps_next, const float *eps_cur,
