@@ -90,6 +90,8 @@ class ClockSampler:
 
     def __enter__(self):
         if self.nvml:
+            self.sample_now()                       # absorbs NVML's slow first queries before the timed region starts ...
+            self.sm.clear(); self.reasons.clear()   # ... and is not a sample of it
             self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
             return self
@@ -256,8 +258,11 @@ def run_ours(args):
         N.check(lib.sacb_timer_start(h))
         for _ in range(args.steps):
             device_step()
-        clk.sample_now()      # the host runs far ahead of the device: the queued steps are executing right now
+        # (NVML is only queried from the sampler's own thread: a query from THIS thread between the last launch and the stop event
+        #  stalled the submission of the queued steps by 30-100 ms in one run out of four)
         N.check(lib.sacb_timer_stop(h, ctypes.byref(ms)))
+        if clk.nvml and not clk.sm:
+            clk.sample_now()      # region shorter than one NVML query: one sample right behind it
         if not clk.nvml:
             time.sleep(0.15)
     barrier()

@@ -68,7 +68,12 @@ extern "C" int sacb_create(const sacb_config *cfg, sacb_handle *out) {
     h->L.build(cfg->obs_dim, cfg->act_dim, cfg->hidden_dim, cfg->n_hidden, cfg->max_batch);
     const int n = cfg->n_agents;
     auto bail = [&](int rc) { sacb_destroy(h); return rc; };
-    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(SACB_ERR_DEVICE, "stream create failed"));
+    {   // the update runs on the highest-priority stream: when sacb_per_step overlaps replay work (second, lowest-priority stream) with the
+        // tail of the update, a freed SM goes to a waiting stage CTA first
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        if (cudaStreamCreateWithPriority(&h->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess) return bail(fail(SACB_ERR_DEVICE, "stream create failed"));
+    }
     if (cudaMalloc(&h->arena, sizeof(float) * h->L.arena_size * n) != cudaSuccess ||
         cudaMalloc(&h->ws, sizeof(float) * h->L.ws_size * n) != cudaSuccess ||
         cudaMalloc(&h->barrier, 64) != cudaSuccess || cudaMalloc(&h->error_flag, 64) != cudaSuccess ||
@@ -362,7 +367,9 @@ extern "C" int sacb_per_step(sacb_handle h, int64_t B, float *losses_out, uint32
     if (!h || h->cfg.replay_kind != SACB_REPLAY_PER || h->cfg.n_agents != 1) return fail(SACB_ERR_ARG, "handle has no prioritized buffer");
     if (B < 1 || B > h->L.maxB) return fail(SACB_ERR_ARG, "batch size out of range");
     if (!h->stream2) {
-        SACB_CUDA(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+        int prio_lo = 0, prio_hi = 0;
+        cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+        SACB_CUDA(cudaStreamCreateWithPriority(&h->stream2, cudaStreamNonBlocking, prio_lo));
         SACB_CUDA(cudaEventCreateWithFlags(&h->ev_td, cudaEventDisableTiming));
         SACB_CUDA(cudaEventCreateWithFlags(&h->ev_sampled, cudaEventDisableTiming));
     }
