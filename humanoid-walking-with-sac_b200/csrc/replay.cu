@@ -40,7 +40,7 @@ static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 
 constexpr int kChunk = 1024;          // elements per scan chunk (one warp, 32 per lane)
 constexpr int kSumLeafMax = 128;      // numpy PW_BLOCKSIZE
-constexpr int kSumBlockMax = 4096;    // elements handled by one CTA of per_sum_blocks
+constexpr int kSumBlockMax = 4096;    // elements of one CTA subtree in per_sum
 constexpr int kSumHeap = 256;         // heap slots per CTA subtree (depth <= 7)
 constexpr int kCarrySmem = 2048;      // chunk prefixes staged in shared memory by per_search when they fit (capacity <= 2 M)
 

@@ -167,3 +167,37 @@ def test_large_batch_update_matches_oracle(hw, B):
     a = float(a) if not hasattr(a, "item") else float(a.item())
     assert abs(a - st.alpha) <= 1e-5 * abs(st.alpha), (a, st.alpha)
     assert agent.stats()["grid"] > 2 * agent.stats()["sm_count"]      # the widest stage really exceeds two waves (tile-loop CTAs)
+
+
+ODD_SHAPES = {
+    "wide_action_m1": dict(obs=20, act=40, hidden=64, n_hidden=2, batch=37, steps=2, seed=91, bias_scale=0.05, head_scale=0.25),     # 2A = 80 > one 64-column tile
+    "one_action_m2": dict(obs=7, act=1, hidden=8, n_hidden=3, batch=5, steps=2, seed=92, bias_scale=0.05),                           # everything smaller than a tile
+    "odd_everything_m2": dict(obs=131, act=9, hidden=72, n_hidden=3, batch=129, steps=1, seed=93, bias_scale=0.05, head_scale=0.5),  # no dimension a multiple of 64
+}
+
+
+@pytest.mark.parametrize("math", ["fp32", "bf16x3"])
+@pytest.mark.parametrize("name", list(ODD_SHAPES))
+def test_odd_shapes_match_oracle(hw, name, math):
+    """Ragged tiles everywhere (TMA zero fill, partial Adam tiles, heads wider than one tile, B below / just above a tile)."""
+    case = ODD_SHAPES[name]
+    tol = TOL[math]
+    agent, st = make_agent(hw, case, math=math)
+    for step in range(case["steps"]):
+        b = batch_of(case, step)
+        got = agent.update_from_batch(b, eps=(b["eps_next"], b["eps_cur"]), export_grads=True)
+        hint = relu_hint(agent, case)
+        ref_losses, aux = O.update_parameters(st, b, return_aux=True, relu_hint=hint)
+        assert hint.mismatch == 0, (step, hint.mismatch, hint.adopted, hint.ambiguous)
+        for k in ("q1_loss", "q2_loss", "policy_loss"):
+            assert abs(got[k] - ref_losses[k]) <= tol["loss"] * abs(ref_losses[k]) + 1e-6, (step, k, got[k], ref_losses[k])
+        for net in ("q1", "q2", "policy"):
+            gg = agent.exported_grads(net)
+            for nm, ref in aux[f"{net}_grads"].items():
+                ok, overall, bad = grad_close(gg[nm], ref, tol["grad"], max_flips=0)
+                assert ok, (step, net, nm, overall, bad)
+    budget = tol["budget"] * st.lr * case["steps"] + 1e-7
+    for net in ("policy", "q1", "q2", "q1_target", "q2_target"):
+        mine = net_params(agent, net)
+        for nm, ref in getattr(st, net).items():
+            assert np.mean(np.abs(mine[nm] - ref) > budget) < tol["frac"], (net, nm)
