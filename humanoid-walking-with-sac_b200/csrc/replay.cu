@@ -341,16 +341,35 @@ __device__ void exact_pass(const float *p_alpha, int64_t n, float tot, double *c
         for (int k = lane; k < kChunk; k += 32) s_q[k] = base + k < n ? __fdiv_rn(p_alpha[base + k], tot) : 0.f;
         __syncwarp();
     };
+    // the same argument one level down: inside a chunk that has to be walked, a lane's 32 consecutive probabilities are jumped when
+    // they hold no fine element and do not leave the binade; only the other groups are added element by element
+    auto walk_chunk = [&](int c, double S) {
+        stage_chunk(c);
+        double gs = 0.0;
+        int gf = 0;
+#pragma unroll 8
+        for (int j = 0; j < 32; j++) { const float q = s_q[lane * 32 + j]; gf |= is_fine(q) ? 1 : 0; gs = __dadd_rn(gs, (double)q); }
+        for (int g = 0; g < 32; g++) {
+            const double gsg = __shfl_sync(0xffffffffu, gs, g);
+            const int gfg = __shfl_sync(0xffffffffu, gf, g);
+            const double T = __dadd_rn(S, gsg);
+            if (!gfg && S > 0.0 && f64_exponent(T) == f64_exponent(S) && f64_exponent(S) <= 1023) S = T;
+            else for (int j = 0; j < 32; j++) S = __dadd_rn(S, (double)s_q[g * 32 + j]);
+        }
+        return S;
+    };
     double S = 0.0;
-    for (int c = 0; c < n_chunks; c++) {
-        if (lane == 0) carry_exact[c] = S;      // exact sequential cdf just before chunk c
-        const double cs = __ldcg(chunk_sum + c);
-        const double T = __dadd_rn(S, cs);
-        if (__ldcg(chunk_fine + c) == 0 && S > 0.0 && f64_exponent(T) == f64_exponent(S) && f64_exponent(S) <= 1023) {
-            S = T;
-        } else {
-            stage_chunk(c);
-            for (int k = 0; k < kChunk; k++) S = __dadd_rn(S, (double)s_q[k]);
+    for (int c0 = 0; c0 < n_chunks; c0 += 32) {      // chunk sums fetched 32 at a time (one coalesced read, then shuffles)
+        const double cs_l = c0 + lane < n_chunks ? __ldcg(chunk_sum + c0 + lane) : 0.0;
+        const int cf_l = c0 + lane < n_chunks ? __ldcg(chunk_fine + c0 + lane) : 0;
+        for (int j = 0; j < 32 && c0 + j < n_chunks; j++) {
+            const int c = c0 + j;
+            if (lane == 0) carry_exact[c] = S;      // exact sequential cdf just before chunk c
+            const double cs = __shfl_sync(0xffffffffu, cs_l, j);
+            const int cf = __shfl_sync(0xffffffffu, cf_l, j);
+            const double T = __dadd_rn(S, cs);
+            if (cf == 0 && S > 0.0 && f64_exponent(T) == f64_exponent(S) && f64_exponent(S) <= 1023) S = T;
+            else S = walk_chunk(c, S);
         }
     }
     if (lane == 0) { carry_exact[n_chunks] = S; counters[2] += 1; }
