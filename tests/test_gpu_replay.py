@@ -195,3 +195,26 @@ def test_pipelined_step_equals_sequential(hw, launch):
     la, lb = np.zeros(3, np.float32), np.zeros(3, np.float32)
     N.check(lib.sacb_get_losses(seq._h, 0, N.ptr(la))); N.check(lib.sacb_get_losses(pipe._h, 0, N.ptr(lb)))
     assert np.array_equal(la, lb) and np.all(np.isfinite(la))
+
+
+@pytest.mark.parametrize("dist,n", [("floor1pct", 1000000), ("lognormal3", 1000000)])
+def test_per_many_calls_on_adversarial_priorities(hw, dist, n):
+    """120 sample() calls (30 720 draws) on the priority sets with thousands of fine probabilities: every index equals numpy's, whether the
+    sample was certified on the fast path (window = (12 F + 8) eps / last, replay.cu) or went through the exact pass."""
+    case = dict(n=n, capacity=n, batch=256, seed=51, dist=dist)
+    pri = cases.per_priorities(case)
+    pa = (pri ** np.float32(0.6)).astype(np.float32)
+    buf = hw.PrioritizedReplayBuffer(n)
+    lib, N = hw._native.lib(), hw._native
+    buf.push_many(np.zeros((1, 2)), np.zeros((1, 1)), np.zeros(1), np.zeros((1, 2)), np.zeros(1))
+    rows = np.zeros((n - 1, int(lib.sacb_row_floats(buf._h))), np.float32)
+    N.check(lib.sacb_push_rows(buf._h, 0, N.ptr(rows), n - 1))
+    buf.set_priorities(pri, pa)
+    rng = np.random.RandomState(7)
+    for call in range(120):
+        u = rng.random_sample(256)
+        *_, idx, _ = buf.sample(256, u=u)
+        ref_idx, _ = PO.sample(pa, u, PO.beta(1 + call))
+        np.testing.assert_array_equal(idx, ref_idx, err_msg=f"call {call}")
+    st = buf._stats()
+    assert st.n_fine > 500, st.n_fine      # the case really is adversarial (floor probabilities below 2^-28 only appear at N = 1 M)
