@@ -39,7 +39,7 @@ class Config(ctypes.Structure):
 class Scalars(ctypes.Structure):
     _fields_ = [("log_alpha", ctypes.c_float), ("alpha", ctypes.c_float), ("log_alpha_m", ctypes.c_float), ("log_alpha_v", ctypes.c_float),
                 ("step_policy", ctypes.c_int64), ("step_q1", ctypes.c_int64), ("step_q2", ctypes.c_int64), ("step_alpha", ctypes.c_int64),
-                ("n_updates", ctypes.c_int64)]
+                ("n_updates", ctypes.c_int64), ("act_counter", ctypes.c_int64)]
 
 
 class PerStats(ctypes.Structure):
@@ -71,6 +71,8 @@ SIGNATURES = {
     "sacb_export_tensor": (I, [H, I, I, I, I, c_f32p, I64]),
     "sacb_get_scalars": (I, [H, I, ctypes.POINTER(Scalars)]),
     "sacb_set_scalars": (I, [H, I, ctypes.POINTER(Scalars)]),
+    "sacb_set_lr": (I, [H, ctypes.c_float]),
+    "sacb_invalidate_shadows": (I, [H]),
     "sacb_push": (I, [H, I, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, I64]),
     "sacb_push_rows": (I, [H, I, c_f32p, I64]),
     "sacb_row_floats": (I64, [H]),
@@ -95,6 +97,7 @@ SIGNATURES = {
     "sacb_select_action_batch": (I, [H, c_f32p, I, c_f32p, c_f32p]),
     "sacb_q_forward": (I, [H, I, I, c_f32p, c_f32p, I64, c_f32p]),
     "sacb_policy_forward": (I, [H, I, c_f32p, I64, c_f32p, c_f32p]),
+    "sacb_policy_sample": (I, [H, I, c_f32p, I64, c_f32p, c_f32p, c_f32p]),
     "sacb_dp_backward": (I, [H, I, I64, c_i64p, c_f32p, c_f32p]),
     "sacb_dp_apply": (I, [H, I]),
     "sacb_dp_grad_buffer": (I, [H, I, ctypes.POINTER(ctypes.c_void_p), c_i64p]),

@@ -91,6 +91,7 @@ extern "C" int sacb_dp_apply(sacb_handle h, int phase) {
                                                     1.0f, sc, net == 0 ? SC_STEP_POLICY : (net == 1 ? SC_STEP_Q1 : SC_STEP_Q2), h->cfg.lr, h->cfg.tau);
         h->kernel_launches++;
     };
+    h->shadows_valid = false;      // the element-wise apply writes fp32 weights only: the next program re-derives the shadows
     if (phase == 0) { run(1, L.q.size); run(2, L.q.size); } else run(0, L.pol.size);
     dp_finish_kernel<<<1, 32, 0, h->stream>>>(sc, ar + L.grad_scalars, phase, h->cfg.auto_entropy, h->adam_table);
     h->kernel_launches++;

@@ -164,9 +164,8 @@ static int select_action_rows(sacb_handle h, int agent0, int rows, int rows_per_
         SACB_CUDA(launch_chain(mlp_layer_kernel, dim3((a.out + 15) / 16, rows), dim3(512), sizeof(float) * a.in, h->stream, a, x, ldx, y, ldy, rows_per_agent));
         x = y; ldx = ldy;
     }
-    static uint32_t counter = 0;
     SACB_CUDA(launch_chain(action_pdl_kernel, dim3((rows * A + 127) / 128), dim3(128), 0, h->stream, (const float *)d_head, (const float *)(use_eps ? d_eps : nullptr),
-                           rows, A, evaluate, h->cfg.action_scale, h->cfg.action_bias, d_act, h->cfg.seed, counter++));
+                           rows, A, evaluate, h->cfg.action_scale, h->cfg.action_bias, d_act, h->cfg.seed, h->act_counter++));
     h->kernel_launches += nh + 2;
     SACB_CUDA(cudaMemcpyAsync(p_act, d_act, sizeof(float) * A * rows, cudaMemcpyDeviceToHost, h->stream));
     SACB_CUDA(cudaStreamSynchronize(h->stream));
@@ -183,9 +182,8 @@ static int select_action_single_cta(sacb_handle h, int agent, const float *obs, 
     if (eps && !evaluate) SACB_CUDA(cudaMemcpyAsync(d_eps, eps, sizeof(float) * A, cudaMemcpyHostToDevice, h->stream));
     MlpArgs a = mlp_args(h, agent, SACB_NET_POLICY);
     mlp_rows_kernel<<<1, 512, mlp_smem(a), h->stream>>>(a, d_obs, O, nullptr, 0, d_head, 2 * A);
-    static uint32_t counter = 0;
     action_kernel<<<1, std::max(32, (A + 31) / 32 * 32), 0, h->stream>>>(d_head, (eps && !evaluate) ? d_eps : nullptr, 1, A, evaluate, h->cfg.action_scale,
-                                                                        h->cfg.action_bias, d_act, h->cfg.seed, counter++);
+                                                                        h->cfg.action_bias, d_act, h->cfg.seed, h->act_counter++);
     h->kernel_launches += 2;
     SACB_CUDA(cudaGetLastError());
     SACB_CUDA(cudaMemcpyAsync(action_out, d_act, sizeof(float) * A, cudaMemcpyDeviceToHost, h->stream));
@@ -239,6 +237,49 @@ extern "C" int sacb_policy_forward(sacb_handle h, int agent, const float *s, int
             log_std_out[r * A + c] = std::min(std::max(head[r * 2 * A + A + c], kLogStdMin), kLogStdMax);   // torch.clamp(log_std, -20, 2)
         }
     cudaFree(d_s); cudaFree(d_h);
+    return SACB_OK;
+}
+
+namespace sacb {
+// head_raw [n, 2A] (+ eps [n, A], or Philox draws) -> action [n, A], log_prob [n]: one warp per row, the arithmetic of the update's
+// T_SAMPLE task (sample_elem), log-prob summed over the action components in lane order + warp tree (networks_model1.py:78-99)
+__global__ void policy_sample_kernel(const float *head, const float *eps, int n, int A, float scale, float bias, float *act, float *logp,
+                                     uint64_t seed, uint32_t counter) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= n) return;
+    float lp = 0.f;
+    for (int c = lane; c < A; c += 32) {
+        const float mean = head[(int64_t)row * 2 * A + c], ls = head[(int64_t)row * 2 * A + A + c];
+        const float e = eps ? eps[(int64_t)row * A + c] : philox_normal(seed, 0x5a3b1eu, counter, (uint32_t)row, (uint32_t)c);
+        const SampleElem s = sample_elem(mean, ls, e, scale, bias);
+        act[(int64_t)row * A + c] = s.action;
+        lp += s.logp;
+    }
+    lp = warp_sum(lp);
+    if (lane == 0) logp[row] = lp;
+}
+}  // namespace sacb
+
+extern "C" int sacb_policy_sample(sacb_handle h, int agent, const float *s, int64_t n, const float *eps, float *action_out, float *log_prob_out) {
+    if (!h || !s || !action_out || !log_prob_out || n < 1 || agent < 0 || agent >= h->cfg.n_agents) return fail(SACB_ERR_ARG, "bad argument");
+    const int O = h->cfg.obs_dim, A = h->cfg.act_dim;
+    float *d_s, *d_h, *d_e = nullptr, *d_a, *d_l;
+    SACB_CUDA(cudaMalloc(&d_s, sizeof(float) * n * O)); SACB_CUDA(cudaMalloc(&d_h, sizeof(float) * n * 2 * A));
+    SACB_CUDA(cudaMalloc(&d_a, sizeof(float) * n * A)); SACB_CUDA(cudaMalloc(&d_l, sizeof(float) * n));
+    SACB_CUDA(cudaMemcpyAsync(d_s, s, sizeof(float) * n * O, cudaMemcpyHostToDevice, h->stream));
+    if (eps) {
+        SACB_CUDA(cudaMalloc(&d_e, sizeof(float) * n * A));
+        SACB_CUDA(cudaMemcpyAsync(d_e, eps, sizeof(float) * n * A, cudaMemcpyHostToDevice, h->stream));
+    }
+    MlpArgs m = mlp_args(h, agent, SACB_NET_POLICY);
+    mlp_rows_kernel<<<(int)n, 512, mlp_smem(m), h->stream>>>(m, d_s, O, nullptr, 0, d_h, 2 * A);
+    policy_sample_kernel<<<(int)((n + 7) / 8), 256, 0, h->stream>>>(d_h, d_e, (int)n, A, h->cfg.action_scale, h->cfg.action_bias, d_a, d_l, h->cfg.seed, h->act_counter++);
+    h->kernel_launches += 2;
+    SACB_CUDA(cudaGetLastError());
+    SACB_CUDA(cudaMemcpyAsync(action_out, d_a, sizeof(float) * n * A, cudaMemcpyDeviceToHost, h->stream));
+    SACB_CUDA(cudaMemcpyAsync(log_prob_out, d_l, sizeof(float) * n, cudaMemcpyDeviceToHost, h->stream));
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    cudaFree(d_s); cudaFree(d_h); cudaFree(d_e); cudaFree(d_a); cudaFree(d_l);
     return SACB_OK;
 }
 

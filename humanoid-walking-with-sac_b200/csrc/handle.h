@@ -70,9 +70,12 @@ struct Layout {
 
 struct ProgramKey {
     int B, with_gather, export_grads, device_eps, use_isw, dp_phase;
+    // 1: the bf16 pair shadows of all five nets are current (the Adam / Polyak epilogues of the previous update refreshed them in
+    // place and nobody wrote the fp32 weights since): the program has no shadow tasks.  0: stage 0 re-derives every shadow.
+    int resident = 0;
     bool operator<(const ProgramKey &o) const {
-        return std::tie(B, with_gather, export_grads, device_eps, use_isw, dp_phase) <
-               std::tie(o.B, o.with_gather, o.export_grads, o.device_eps, o.use_isw, o.dp_phase);
+        return std::tie(B, with_gather, export_grads, device_eps, use_isw, dp_phase, resident) <
+               std::tie(o.B, o.with_gather, o.export_grads, o.device_eps, o.use_isw, o.dp_phase, o.resident);
     }
 };
 
@@ -113,6 +116,7 @@ struct sacb_handle_s {
     int64_t staged_steps = 0, staged_next = 0, staged_B = 0;
     std::map<sacb::ProgramKey, sacb::ProgramInst> programs;
     int64_t kernel_launches = 0;
+    bool shadows_valid = false;          // see ProgramKey::resident; cleared by every write of fp32 weights from outside the update program
     int use_pdl = 1;                     // staged mode: programmatic dependent launch between the stage kernels (SACB_NO_PDL=1 disables)
     int dp_device_eps = 1;               // data-parallel mode: eps of the current step drawn on device (phase 1 follows phase 0)
     int coop_blocks_per_sm = 0;
@@ -122,6 +126,7 @@ struct sacb_handle_s {
     std::vector<int64_t> r_len, r_pos, r_head;   // per agent: count, next write slot, slot of the oldest entry
     float *stage_rows = nullptr;         // device staging for pushes
     int64_t stage_rows_cap = 0;
+    int32_t *gather_slots = nullptr;     // [stage_rows_cap] slots of a host-facing gather (sacb_read_transitions)
     // PER
     float *prio = nullptr, *p_alpha = nullptr;   // [n_agents, capacity]
     std::vector<int64_t> per_frame;
@@ -145,6 +150,7 @@ struct sacb_handle_s {
     bool u_in_flight = false;
     float *act_ws = nullptr, *pin_act = nullptr;   // select_action scratch (device) and pinned obs / eps / action block
     int act_rows = 0;
+    uint32_t act_counter = 0;            // Philox counter of select_action's exploration draws (checkpointed through sacb_scalars)
     int64_t pin_rows_cap = 0;
 };
 
@@ -165,6 +171,9 @@ int launch_program(sacb_handle h, ProgramInst &p);
 int launch_program_part(sacb_handle h, ProgramInst &p, int part);   // 0: up to and including the critic-loss stage, 1: the rest
 void free_programs(sacb_handle h);
 int check_error_flag(sacb_handle h);
+// the key of the program that serves the next update of this handle (fills ProgramKey::resident), and the bookkeeping behind its launch
+ProgramKey update_key(sacb_handle h, int B, int with_gather, int export_grads, int device_eps, int use_isw);
+void after_update_launch(sacb_handle h, const ProgramKey &key);
 // replay.cu
 int replay_create(sacb_handle h);
 void replay_destroy(sacb_handle h);

@@ -345,7 +345,7 @@ struct Builder {
         t.C = t.bias = null_ref();
         t.Cpm = t.mask = t.A.pm = t.B.pm = null_pm();
         t.adam.w = t.adam.m = t.adam.v = t.adam.wt = t.adam.gexp = null_ref();
-        t.adam.shadow = t.adam.shadow2 = null_pm();
+        t.adam.shadow = t.adam.shadow2 = t.adam.shadow_t = null_pm();
         for (auto &p : t.p) p = null_ref();
         for (auto &p : t.pm) p = null_pm();
         return t;
@@ -392,6 +392,9 @@ struct Builder {
     // which optimizer a trainable net (0 policy, 1 q1, 2 q2) uses
     static int step_slot(int net) { return net == 0 ? SC_STEP_POLICY : (net == 1 ? SC_STEP_Q1 : SC_STEP_Q2); }
     bool apply() const { return key.dp_phase < 0; }
+    // every epilogue that changes a weight also refreshes its shadow (policy and targets included), so that the next step can run
+    // without the shadow stage; not in a split-K build (its staging leaves no room for the target tile)
+    bool keep_resident() const { return apply() && math_is_tc(h->cfg.math_mode) ? !getenv("SACB_SPLITK") : apply(); }
     bool exporting() const { return key.export_grads || key.dp_phase >= 0; }
 
     AdamArgs adam_args(int net, int64_t off_in_net) {
@@ -399,7 +402,7 @@ struct Builder {
         a.w = A(L.param[net] + off_in_net); a.m = A(L.adam_m[net] + off_in_net); a.v = A(L.adam_v[net] + off_in_net);
         a.wt = net == 0 ? null_ref() : A(L.param[net + 2] + off_in_net);     // q1 -> q1_target, q2 -> q2_target
         a.gexp = exporting() ? A(L.grad[net] + off_in_net) : null_ref();
-        a.shadow = a.shadow2 = null_pm(); a.shadow2_col0 = 0; a.pad0 = 0;
+        a.shadow = a.shadow2 = a.shadow_t = null_pm(); a.shadow2_col0 = 0; a.pad0 = 0;
         a.step_slot = step_slot(net); a.apply = apply() ? 1 : 0;
         a.lr = h->cfg.lr; a.tau = h->cfg.tau;
         return a;
@@ -409,8 +412,9 @@ struct Builder {
     Task epi_adam(int net, int layer) {
         const NetLayout &n = net == 0 ? L.pol : L.q;
         Task t = blank(T_GEMM); t.epi = EPI_ADAM; t.adam = adam_args(net, n.w[layer]);
-        if (net != 0) t.adam.shadow = wsh(net, layer).ref;
+        if (net != 0 || keep_resident()) t.adam.shadow = wsh(net, layer).ref;
         if (net != 0 && layer == 0) { t.adam.shadow2 = wsh_act(net).ref; t.adam.shadow2_col0 = L.obs; }
+        if (net != 0 && keep_resident()) t.adam.shadow_t = wsh(net + 2, layer).ref;      // Polyak target's shadow
         return t;
     }
 
@@ -486,8 +490,9 @@ struct Builder {
         auto X3 = [&](int cols) { return xrows(2 * B, B, cols); };
 
         // ---- stage: weight shadows (+ minibatch gather) --------------------------------------------------------
-        begin_stage();
-        for (int net = 0; net < 5; net++) {
+        const bool shadow_stage = !key.resident;
+        if (shadow_stage || (key.with_gather && critics)) begin_stage();
+        for (int net = 0; net < 5 && shadow_stage; net++) {
             if (!critics && (net == 3 || net == 4)) continue;      // the actor phase does not read the targets
             const NetLayout &n = net == 0 ? P : Q;
             for (int l = 0; l < nh; l++) shadow_task(net, n.w[l], wsh(net, l), n.in_of(l));
@@ -641,6 +646,7 @@ struct Builder {
                         gemm(hview(L.dhp[l], B), 0, wsh(0, l), 1, B, H, H, epi_mask(hview(L.dhp[l - 1], B), hp_cur(l - 1)));
                     if (s == 1) {              // heads: dW = g^T h_{nh-1}
                         Task t = blank(T_GEMM); t.epi = EPI_ADAM; t.adam = adam_args(0, P.w_out);
+                        if (keep_resident()) t.adam.shadow = wsh_head().ref;
                         gemm(ghead(B), 1, hp_cur(nh - 1), 1, A2, H, B, t);
                         bias_adam(0, P.b_out, ghead(B), B, A2);
                     } else {
@@ -841,6 +847,17 @@ int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out) {
     return SACB_OK;
 }
 
+ProgramKey update_key(sacb_handle h, int B, int with_gather, int export_grads, int device_eps, int use_isw) {
+    ProgramKey k{B, with_gather, export_grads, device_eps, use_isw, -1};
+    static const bool always = getenv("SACB_ALWAYS_SHADOW") != nullptr;      // A/B switch: re-derive every shadow every step (round-1 behaviour)
+    k.resident = (h->shadows_valid && !always) ? 1 : 0;
+    return k;
+}
+void after_update_launch(sacb_handle h, const ProgramKey &key) {
+    // a full update (Adam applied) leaves every shadow current: its epilogues refreshed what they changed
+    if (key.dp_phase < 0) h->shadows_valid = !(math_is_tc(h->cfg.math_mode) && getenv("SACB_SPLITK"));
+}
+
 int launch_program(sacb_handle h, ProgramInst &p) {
     h->kernel_launches += p.kernels_per_step;
     if (p.graph) { SACB_CUDA(cudaGraphLaunch(p.graph, h->stream)); return SACB_OK; }
@@ -893,9 +910,15 @@ using namespace sacb;
 
 extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap) {
     if (!h) return fail(SACB_ERR_ARG, "null handle");
-    ProgramKey key{(int)B, 0, 0, 1, 0, -1};
     ProgramInst *p;
-    int rc = get_program(h, key, &p);
+    int rc;
+    if (!h->shadows_valid) {      // one step that (re)derives the shadows, then the steady-state program is profiled
+        ProgramKey k0 = update_key(h, (int)B, 0, 0, 1, 0);
+        if ((rc = get_program(h, k0, &p)) || (rc = launch_program(h, *p))) return rc;
+        after_update_launch(h, k0);
+    }
+    ProgramKey key = update_key(h, (int)B, 0, 0, 1, 0);
+    rc = get_program(h, key, &p);
     if (rc) return rc;
     const bool trace = getenv("SACB_TRACE") != nullptr;
     unsigned long long *d_trace = nullptr;

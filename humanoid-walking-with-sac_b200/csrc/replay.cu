@@ -633,7 +633,7 @@ int replay_create(sacb_handle h) {
 }
 
 void replay_destroy(sacb_handle h) {
-    cudaFree(h->ring); cudaFree(h->stage_rows); cudaFree(h->prio); cudaFree(h->p_alpha); cudaFree(h->per_ws); cudaFree(h->last_idx_dev);
+    cudaFree(h->ring); cudaFree(h->stage_rows); cudaFree(h->prio); cudaFree(h->p_alpha); cudaFree(h->per_ws); cudaFree(h->last_idx_dev); cudaFree(h->gather_slots);
 }
 
 // logical index -> physical ring slot.  uniform: deque order (j-th oldest); PER: list position
@@ -798,9 +798,12 @@ static int gather_to_host(sacb_handle h, int agent, const int32_t *slots_host, i
     const sacb_config &c = h->cfg;
     const int64_t row = h->ring_row;
     const float *ring = h->ring + (int64_t)agent * c.capacity * row;
-    int32_t *slots_dev = h->slots + (int64_t)agent * c.max_batch;
-    for (int64_t off = 0; off < n; off += c.max_batch) {
-        const int64_t m = std::min<int64_t>(c.max_batch, n - off);
+    // host-facing reads (`.buffer`, checkpoints, ReplayBuffer.sample of any size) move stage_rows_cap rows per round trip
+    if (!h->gather_slots && cudaMalloc(&h->gather_slots, sizeof(int32_t) * h->stage_rows_cap) != cudaSuccess) return fail(SACB_ERR_NOMEM, "device allocation failed");
+    int32_t *slots_dev = h->gather_slots;
+    const int64_t chunk = h->stage_rows_cap;
+    for (int64_t off = 0; off < n; off += chunk) {
+        const int64_t m = std::min<int64_t>(chunk, n - off);
         if (slots_host) SACB_CUDA(cudaMemcpyAsync(slots_dev, slots_host + off, sizeof(int32_t) * m, cudaMemcpyHostToDevice, h->stream));
         gather_rows_kernel<<<(int)((m + 7) / 8), 256, 0, h->stream>>>(ring, row, slots_dev, (int)m, h->stage_rows);
         h->kernel_launches++;
@@ -911,6 +914,7 @@ extern "C" int sacb_per_update_final(sacb_handle h, int agent, const int64_t *id
 extern "C" int sacb_per_update_from_td(sacb_handle h, int agent, int64_t B) {
     if (!h || agent != 0 || h->cfg.replay_kind != SACB_REPLAY_PER) return fail(SACB_ERR_ARG, "bad argument");
     if (B < 1 || B > h->cfg.max_batch) return fail(SACB_ERR_ARG, "batch size out of range");
+    if (h->sample_k != B) return fail(SACB_ERR_STATE, "sacb_per_update_from_td: the last prioritized sample does not hold B rows");
     return per_writeback_launch(h, h->stream, B);
 }
 static int per_update_impl(sacb_handle h, int agent, const int64_t *idx, const float *prio, int64_t B, int is_final) {

@@ -138,6 +138,12 @@ extern "C" int sacb_destroy(sacb_handle h) {
     return SACB_OK;
 }
 
+extern "C" int sacb_invalidate_shadows(sacb_handle h) {
+    if (!h) return fail(SACB_ERR_ARG, "null handle");
+    h->shadows_valid = false;
+    return SACB_OK;
+}
+
 extern "C" int sacb_get_stream(sacb_handle h, void **stream_out) {
     if (!h || !stream_out) return fail(SACB_ERR_ARG, "null argument");
     *stream_out = (void *)h->stream;
@@ -201,6 +207,7 @@ extern "C" int sacb_import_tensor(sacb_handle h, int agent, int net, int slot, i
     int rc = tensor_offset(h, agent, net, slot, tensor, &off, &cnt);
     if (rc) return rc;
     if (n != cnt) return fail(SACB_ERR_ARG, "tensor size mismatch");
+    if (slot == SACB_SLOT_PARAM) h->shadows_valid = false;
     SACB_CUDA(cudaMemcpyAsync(h->arena + off, src, sizeof(float) * n, cudaMemcpyHostToDevice, h->stream));
     SACB_CUDA(cudaStreamSynchronize(h->stream));
     return SACB_OK;
@@ -229,6 +236,7 @@ extern "C" int sacb_get_scalars(sacb_handle h, int agent, sacb_scalars *out) {
     out->alpha = sc[SC_ALPHA0 + (out->n_updates & 1)];
     out->step_policy = f2i(sc[SC_STEP_POLICY]); out->step_q1 = f2i(sc[SC_STEP_Q1]); out->step_q2 = f2i(sc[SC_STEP_Q2]);
     out->step_alpha = f2i(sc[SC_STEP_ALPHA]);
+    out->act_counter = h->act_counter;
     return SACB_OK;
 }
 
@@ -245,6 +253,27 @@ extern "C" int sacb_set_scalars(sacb_handle h, int agent, const sacb_scalars *in
     adam_factors_store(sc, SC_STEP_POLICY, (int)in->step_policy, h->cfg.lr); adam_factors_store(sc, SC_STEP_Q1, (int)in->step_q1, h->cfg.lr);
     adam_factors_store(sc, SC_STEP_Q2, (int)in->step_q2, h->cfg.lr); adam_factors_store(sc, SC_STEP_ALPHA, (int)in->step_alpha, h->cfg.lr);
     SACB_CUDA(cudaMemcpyAsync(dev, sc, sizeof(sc), cudaMemcpyHostToDevice, h->stream));
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    h->act_counter = (uint32_t)in->act_counter;
+    return SACB_OK;
+}
+
+extern "C" int sacb_set_lr(sacb_handle h, float lr) {
+    if (!h || !(lr > 0.f)) return fail(SACB_ERR_ARG, "bad learning rate");
+    if (lr == h->cfg.lr) return SACB_OK;
+    h->cfg.lr = lr;
+    std::vector<float2> tab(kAdamTable);
+    for (int t = 0; t < kAdamTable; t++) adam_factors(t, lr, tab[t].x, tab[t].y);
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    SACB_CUDA(cudaMemcpyAsync(h->adam_table, tab.data(), sizeof(float2) * kAdamTable, cudaMemcpyHostToDevice, h->stream));
+    for (int a = 0; a < h->cfg.n_agents; a++) {      // cached factors of the NEXT step of every optimizer
+        float sc[32];
+        float *dev = h->arena + a * h->L.arena_size + h->L.scalars;
+        SACB_CUDA(cudaMemcpyAsync(sc, dev, sizeof(sc), cudaMemcpyDeviceToHost, h->stream));
+        SACB_CUDA(cudaStreamSynchronize(h->stream));
+        for (int slot = SC_STEP_POLICY; slot <= SC_STEP_ALPHA; slot++) adam_factors_store(sc, slot, (int)f2i(sc[slot]), lr);
+        SACB_CUDA(cudaMemcpyAsync(dev, sc, sizeof(sc), cudaMemcpyHostToDevice, h->stream));
+    }
     SACB_CUDA(cudaStreamSynchronize(h->stream));
     return SACB_OK;
 }
@@ -310,12 +339,13 @@ extern "C" int sacb_update_batch(sacb_handle h, int64_t B, const float *s, const
     if (isw) SACB_CUDA(cudaMemcpyAsync(ws + L.isw, isw, sizeof(float) * B, cudaMemcpyHostToDevice, h->stream));
     int rc = upload_eps(h, 0, B, eps_next, eps_cur);
     if (rc) return rc;
-    ProgramKey key{(int)B, 2, (flags & SACB_EXPORT_GRADS) ? 1 : 0, eps_next ? 0 : 1, isw ? 1 : 0, -1};
+    ProgramKey key = update_key(h, (int)B, 2, (flags & SACB_EXPORT_GRADS) ? 1 : 0, eps_next ? 0 : 1, isw ? 1 : 0);
     ProgramInst *p;
     rc = get_program(h, key, &p);
     if (rc) return rc;
     rc = launch_program(h, *p);
     if (rc) return rc;
+    after_update_launch(h, key);
     if (td_abs_out) {
         SACB_CUDA(cudaMemcpyAsync(td_abs_out, ws + L.td, sizeof(float) * B, cudaMemcpyDeviceToHost, h->stream));
         SACB_CUDA(cudaStreamSynchronize(h->stream));
@@ -341,6 +371,9 @@ extern "C" int sacb_update(sacb_handle h, int64_t B, const int64_t *idx, const f
                                   cudaMemcpyDeviceToDevice, h->stream));
     } else if (!(flags & SACB_USE_LAST_SAMPLE)) {
         return fail(SACB_ERR_ARG, "no indices: pass idx, stage them, or set SACB_USE_LAST_SAMPLE");
+    } else if (h->cfg.replay_kind == SACB_REPLAY_PER && h->sample_k != B) {
+        // set_priorities / clear / a sample of another size leave no (or a stale) minibatch behind
+        return fail(SACB_ERR_STATE, "SACB_USE_LAST_SAMPLE: the last prioritized sample does not hold B rows (sample again)");
     }
     if (eps_next) for (int a = 0; a < h->cfg.n_agents; a++) {
         const int64_t n = B * h->cfg.act_dim;
@@ -348,12 +381,13 @@ extern "C" int sacb_update(sacb_handle h, int64_t B, const int64_t *idx, const f
         if (rc) return rc;
     }
     const int use_isw = (h->cfg.per_weighted_loss && h->cfg.replay_kind == SACB_REPLAY_PER) ? 1 : 0;
-    ProgramKey key{(int)B, 1, (flags & SACB_EXPORT_GRADS) ? 1 : 0, eps_next ? 0 : 1, use_isw, -1};
+    ProgramKey key = update_key(h, (int)B, 1, (flags & SACB_EXPORT_GRADS) ? 1 : 0, eps_next ? 0 : 1, use_isw);
     ProgramInst *p;
     rc = get_program(h, key, &p);
     if (rc) return rc;
     rc = launch_program(h, *p);
     if (rc) return rc;
+    after_update_launch(h, key);
     return finish_update(h, losses_out, flags);
 }
 
@@ -379,11 +413,12 @@ extern "C" int sacb_per_step(sacb_handle h, int64_t B, float *losses_out, uint32
         rc = per_sample_launch(h, h->stream, nullptr, B, nullptr);
         if (rc) return rc;
     }
-    ProgramKey key{(int)k, 1, 0, 1, h->cfg.per_weighted_loss ? 1 : 0, -1};
+    ProgramKey key = update_key(h, (int)k, 1, 0, 1, h->cfg.per_weighted_loss ? 1 : 0);
     ProgramInst *p;
     rc = get_program(h, key, &p);
     if (rc) return rc;
     if ((rc = launch_program_part(h, *p, 0))) return rc;
+    after_update_launch(h, key);
     SACB_CUDA(cudaEventRecord(h->ev_td, h->stream));
     SACB_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_td, 0));
     if ((rc = per_writeback_launch(h, h->stream2, k))) return rc;
@@ -433,9 +468,15 @@ extern "C" int sacb_get_stats(sacb_handle h, sacb_stats *out) {
 
 extern "C" int sacb_time_update(sacb_handle h, int64_t B, int iters, float *ms_per_step) {
     if (!h || !ms_per_step || iters < 1) return fail(SACB_ERR_ARG, "bad argument");
-    ProgramKey key{(int)B, 0, 0, 1, 0, -1};
     ProgramInst *p;
-    int rc = get_program(h, key, &p);
+    int rc;
+    if (!h->shadows_valid) {      // one step that (re)derives the shadows, then the steady-state program is timed
+        ProgramKey k0 = update_key(h, (int)B, 0, 0, 1, 0);
+        if ((rc = get_program(h, k0, &p)) || (rc = launch_program(h, *p))) return rc;
+        after_update_launch(h, k0);
+    }
+    ProgramKey key = update_key(h, (int)B, 0, 0, 1, 0);
+    rc = get_program(h, key, &p);
     if (rc) return rc;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);

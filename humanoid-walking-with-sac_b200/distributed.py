@@ -68,6 +68,7 @@ class DataParallelSAC:
         (`sacb_stage_indices`); sync=False returns None without reading the losses (throughput mode)."""
         a, lib = self.agent, N.lib()
         a.replay_buffer._flush()
+        a._publish_alias_writes()
         if staged:
             ix, n_local = None, int(batch_size_local)
         else:

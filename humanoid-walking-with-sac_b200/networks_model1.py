@@ -6,8 +6,6 @@ aliases a slice of the device arena that the fused update kernels read and write
 `load_state_dict()` and `torch.save` keep the reference layout while no autograd graph is ever
 built.  `forward` / `sample` evaluate rows through the library (sacb_q_forward / sacb_policy_forward).
 """
-import math
-
 import numpy as np
 import torch
 import torch.nn as nn
@@ -97,13 +95,14 @@ class GaussianPolicy(_ArenaModule):
         return torch.from_numpy(mean), torch.from_numpy(log_std)
 
     def sample(self, state, eps=None):
-        """networks_model1.py:78-99 on host tensors, from the library's (mean, log_std); eps defaults to torch.randn."""
-        mean, log_std = self.forward(state)
-        std = log_std.exp()
-        eps = torch.randn_like(mean) if eps is None else torch.as_tensor(eps, dtype=mean.dtype).reshape(mean.shape)
-        x_t = mean + eps * std
-        y_t = torch.tanh(x_t)
-        action = y_t * self.action_scale + self.action_bias
-        log_prob = -((x_t - mean) ** 2) / (2 * std * std) - log_std - math.log(math.sqrt(2 * math.pi))
-        log_prob = log_prob - torch.log(self.action_scale * (1 - y_t.pow(2)) + 1e-6)
-        return action, log_prob.sum(dim=-1, keepdim=True)
+        """networks_model1.py:78-99 evaluated by the library (sacb_policy_sample: the same device arithmetic as the update's
+        sampling stage).  eps [n, act] replaces the N(0,1) draw of Normal.rsample; None draws on the device (Philox)."""
+        if not self._bound():
+            raise RuntimeError("GaussianPolicy is evaluated by the CUDA library: construct it through SAC (no PyTorch fallback)")
+        s = N.f32(torch.as_tensor(state).detach().cpu().numpy())
+        s = s.reshape(-1, s.shape[-1])
+        act = self.mean.out_features
+        e = None if eps is None else N.f32(torch.as_tensor(eps).detach().cpu().numpy()).reshape(s.shape[0], act)
+        action, logp = np.empty((s.shape[0], act), np.float32), np.empty(s.shape[0], np.float32)
+        N.check(N.lib().sacb_policy_sample(self._owner._h, 0, N.ptr(s), s.shape[0], N.ptr(e), N.ptr(action), N.ptr(logp)))
+        return torch.from_numpy(action), torch.from_numpy(logp).unsqueeze(-1)

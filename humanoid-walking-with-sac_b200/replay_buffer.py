@@ -170,7 +170,12 @@ class ReplayBuffer(_DeviceBuffer):
 
     def sample(self, batch_size):
         idx = self._draw(batch_size)        # ValueError("Sample larger than population...") like the reference
-        return self._read(idx)
+        self._flush()
+        n, o, k = idx.size, self._cfg.obs_dim, self._cfg.act_dim
+        s, a, r = np.empty((n, o), np.float32), np.empty((n, k), np.float32), np.empty(n, np.float32)
+        s2, d = np.empty((n, o), np.float32), np.empty(n, np.float32)
+        N.check(N.lib().sacb_sample_uniform(self._h, 0, N.ptr(idx, ctypes.c_int64), n, N.ptr(s), N.ptr(a), N.ptr(r), N.ptr(s2), N.ptr(d)))
+        return s, a, r, s2, d
 
 
 class PrioritizedReplayBuffer(_DeviceBuffer):

@@ -65,6 +65,7 @@ class ArenaAdam:
         state = sd["state"]
         if not state:
             self._set_step(0)
+            self._restore_lr(sd)
             return
         first = state[min(state)]
         self._set_step(int(float(first["step"])))
@@ -73,13 +74,20 @@ class ArenaAdam:
             sc.log_alpha_m = float(torch.as_tensor(first["exp_avg"]).reshape(-1)[0])
             sc.log_alpha_v = float(torch.as_tensor(first["exp_avg_sq"]).reshape(-1)[0])
             self._owner._set_scalars(sc)
+            self._restore_lr(sd)
             return
         for i, st in state.items():
             for slot, key in ((N.SLOT_ADAM_M, "exp_avg"), (N.SLOT_ADAM_V, "exp_avg_sq")):
                 host = N.f32(torch.as_tensor(st[key]).detach().cpu().numpy())
                 N.check(N.lib().sacb_import_tensor(self._owner._h, 0, self._net_id, slot, int(i), N.ptr(host), host.size))
-        if sd.get("param_groups"):
-            self.param_groups[0]["lr"] = sd["param_groups"][0].get("lr", self.param_groups[0]["lr"])
+        self._restore_lr(sd)
+
+    def _restore_lr(self, sd):
+        # torch.optim.Adam.load_state_dict restores the learning rate of the checkpoint (sac_imp.py:215-218); the device
+        # Adam of all four optimizers shares ONE rate (sac_imp.py:39-49), so a differing value re-derives its step-size table
+        if sd.get("param_groups") and "lr" in sd["param_groups"][0]:
+            lr = float(sd["param_groups"][0]["lr"])
+            self._owner._set_lr(lr)
 
 
 class SAC:
@@ -137,6 +145,21 @@ class SAC:
                               if replay == "per" else ReplayBuffer(capacity))
         self.replay_buffer._bind(self)
         self._alpha_is_float = True        # python float until the first update (quirk Q1)
+        self._aliases = [p for n in _NETS for p in getattr(self, n).parameters()]
+        self._alias_versions = None
+
+    def _publish_alias_writes(self):
+        """The GEMMs read bf16 hi/lo shadows that the update's own epilogues keep current.  A write through the torch aliases
+        (load_state_dict, `with torch.no_grad(): p.mul_(...)`, ...) bumps the tensors' version counters: the library is then told to
+        re-derive every shadow before the next update.  (`p.data` views have their own counter: call invalidate_shadows() after
+        writing through one.)"""
+        v = [p._version for p in self._aliases]
+        if v != self._alias_versions:
+            self._alias_versions = v
+            N.check(N.lib().sacb_invalidate_shadows(self._h))
+
+    def invalidate_shadows(self):
+        N.check(N.lib().sacb_invalidate_shadows(self._h))
 
     def __del__(self):
         h = getattr(self, "_h", None)
@@ -155,6 +178,22 @@ class SAC:
 
     def _set_scalars(self, sc):
         N.check(N.lib().sacb_set_scalars(self._h, 0, ctypes.byref(sc)))
+
+    def _set_lr(self, lr):
+        N.check(N.lib().sacb_set_lr(self._h, lr))
+        self._lr = lr
+        for opt in ("policy_optimizer", "q1_optimizer", "q2_optimizer", "alpha_optimizer"):
+            if hasattr(self, opt):
+                getattr(self, opt).param_groups[0]["lr"] = lr
+
+    def _library_stream(self):
+        """The handle's private CUDA stream as a torch stream: torch-side reads / writes of the aliased arena (state_dict,
+        load_state_dict, torch.save) are enqueued on it, i.e. ordered against the kernels of the library."""
+        if getattr(self, "_ext_stream", None) is None:
+            sp = ctypes.c_void_p()
+            N.check(N.lib().sacb_get_stream(self._h, ctypes.byref(sp)))
+            self._ext_stream = torch.cuda.ExternalStream(sp.value, device=f"cuda:{self._cfg.device}")
+        return torch.cuda.stream(self._ext_stream)
 
     def _tensor(self, net_id, slot, t, shape):
         dev = ctypes.c_void_p()
@@ -203,6 +242,7 @@ class SAC:
         blocking read of the three losses (returns None)."""
         buf = self.replay_buffer
         lib = N.lib()
+        self._publish_alias_writes()
         e_next = e_cur = None
         if eps is not None:
             e_next, e_cur = N.f32(eps[0]), N.f32(eps[1])
@@ -237,6 +277,7 @@ class SAC:
         if not isinstance(buf, PrioritizedReplayBuffer):
             raise ValueError("learner_step needs the prioritized replay buffer")
         buf._flush()
+        self._publish_alias_writes()
         losses = np.zeros(3, np.float32)
         N.check(N.lib().sacb_per_step(self._h, batch_size, N.ptr(losses) if sync else None, 0 if sync else N.NO_LOSS_READBACK))
         self._alpha_is_float = False
@@ -248,6 +289,7 @@ class SAC:
         """Same step on a caller-supplied minibatch dict(s,a,r,s2,d) (parity tests / benchmarks; no replay involved)."""
         s, a, r, s2, d = (N.f32(batch[k]) for k in ("s", "a", "r", "s2", "d"))
         B = s.shape[0]
+        self._publish_alias_writes()
         e_next = e_cur = None
         if eps is not None:
             e_next, e_cur = N.f32(eps[0]), N.f32(eps[1])
@@ -271,30 +313,42 @@ class SAC:
 
     # ---- persistence (same dictionary keys as the reference) ----------------------------------------------------
     def save(self, path):
-        torch.save({f"{n}_state_dict": getattr(self, n).state_dict() for n in _NETS} | {"alpha": self.alpha}, path)
+        self.synchronize()                  # an update enqueued with sync=False / learner_step may still be running
+        with self._library_stream():
+            torch.save({f"{n}_state_dict": getattr(self, n).state_dict() for n in _NETS} | {"alpha": self.alpha}, path)
 
     def _load_nets(self, checkpoint):
-        for n in _NETS:
-            getattr(self, n).load_state_dict(checkpoint[f"{n}_state_dict"])
+        # the copies into the aliased arena run on the library's own stream (torch's current stream is not ordered against it)
+        with self._library_stream():
+            for n in _NETS:
+                getattr(self, n).load_state_dict(checkpoint[f"{n}_state_dict"])
+        self.synchronize()
 
     def load(self, path):
         checkpoint = torch.load(path, map_location=self.device, weights_only=False)
         self._load_nets(checkpoint)
         self.alpha = checkpoint["alpha"]
 
-    def save_checkpoint(self, path, episode, total_steps, replay_buffer=True):
+    def save_checkpoint(self, path, episode, total_steps, replay_buffer=True, *, rng_state=False):
+        """sac_imp.py:177-201, same keys.  rng_state=True adds one extra key ('sacb_rng_state': the Philox counters of the
+        on-device eps / exploration draws) so that a seeded run resumes its own random stream; the reference ignores it."""
+        self.synchronize()
         checkpoint = {"episode": episode, "total_steps": total_steps}
-        checkpoint.update({f"{n}_state_dict": getattr(self, n).state_dict() for n in _NETS})
-        for n in ("policy", "q1", "q2"):
-            checkpoint[f"{n}_optimizer_state_dict"] = getattr(self, f"{n}_optimizer").state_dict()
-        checkpoint["alpha"] = self.alpha
-        if self.automatic_entropy_tuning:
-            checkpoint["log_alpha"] = self.log_alpha
-            checkpoint["alpha_optimizer_state_dict"] = self.alpha_optimizer.state_dict()
-        if replay_buffer:
-            checkpoint["replay_buffer"] = self.replay_buffer.buffer
-        # the reference only writes the file inside `if replay_buffer:` (sac_imp.py:198-201); always writing is the fix
-        torch.save(checkpoint, path)
+        with self._library_stream():
+            checkpoint.update({f"{n}_state_dict": getattr(self, n).state_dict() for n in _NETS})
+            for n in ("policy", "q1", "q2"):
+                checkpoint[f"{n}_optimizer_state_dict"] = getattr(self, f"{n}_optimizer").state_dict()
+            checkpoint["alpha"] = self.alpha
+            if self.automatic_entropy_tuning:
+                checkpoint["log_alpha"] = self.log_alpha
+                checkpoint["alpha_optimizer_state_dict"] = self.alpha_optimizer.state_dict()
+            if replay_buffer:
+                checkpoint["replay_buffer"] = self.replay_buffer.buffer
+            if rng_state:
+                sc = self._scalars()
+                checkpoint["sacb_rng_state"] = {"seed": int(self._cfg.seed), "n_updates": int(sc.n_updates), "act_counter": int(sc.act_counter)}
+            # the reference only writes the file inside `if replay_buffer:` (sac_imp.py:198-201); always writing is the fix
+            torch.save(checkpoint, path)
 
     def load_checkpoint(self, path, load_replay_buffer=True):
         checkpoint = torch.load(path, map_location=self.device, weights_only=False)   # pickled deque / numpy inside
@@ -309,6 +363,11 @@ class SAC:
             self.alpha_optimizer.load_state_dict(checkpoint["alpha_optimizer_state_dict"])
         if load_replay_buffer and "replay_buffer" in checkpoint:
             self.replay_buffer.buffer = checkpoint["replay_buffer"]
+        rs = checkpoint.get("sacb_rng_state")
+        if rs is not None and int(rs.get("seed", -1)) == int(self._cfg.seed):      # resume this seed's Philox streams where they stopped
+            sc = self._scalars()
+            sc.n_updates, sc.act_counter = int(rs["n_updates"]), int(rs["act_counter"])
+            self._set_scalars(sc)
         return checkpoint.get("episode", 0), checkpoint.get("total_steps", 0)
 
     # ---- instrumentation ------------------------------------------------------------------------------------------

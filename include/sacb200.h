@@ -89,13 +89,21 @@ int sacb_tensor_info(sacb_handle h, int net, int tensor, int64_t *rows, int64_t 
 int sacb_tensor_dev(sacb_handle h, int agent, int net, int slot, int tensor, void **dev_ptr);
 int sacb_import_tensor(sacb_handle h, int agent, int net, int slot, int tensor, const float *src, int64_t n);
 int sacb_export_tensor(sacb_handle h, int agent, int net, int slot, int tensor, float *dst, int64_t n);
+/* The GEMMs read bf16 hi/lo shadows of the weights that the update's own Adam / Polyak epilogues keep current.  A write of fp32
+ * weights from OUTSIDE the library (through the torch aliases of sacb_tensor_dev: load_state_dict, in-place edits) must be followed
+ * by this call; the next update then re-derives every shadow first.  sacb_import_tensor does it implicitly. */
+int sacb_invalidate_shadows(sacb_handle h);
 /* scalars: log_alpha + its Adam state (sac_imp.py:48-49), alpha (:23,:135), per-optimizer step counts. */
 typedef struct {
     float log_alpha, alpha, log_alpha_m, log_alpha_v;
     int64_t step_policy, step_q1, step_q2, step_alpha, n_updates;
+    int64_t act_counter;   /* Philox counter of select_action's exploration draws (per handle; saved by save_checkpoint) */
 } sacb_scalars;
 int sacb_get_scalars(sacb_handle h, int agent, sacb_scalars *out);
 int sacb_set_scalars(sacb_handle h, int agent, const sacb_scalars *in);
+/* torch.optim.Adam.load_state_dict restores param_groups[0]['lr'] (sac_imp.py:215-218): rebuilds the Adam step-size table and the
+ * cached bias-correction factors of every agent for the new learning rate (all four optimizers share it, sac_imp.py:39-49). */
+int sacb_set_lr(sacb_handle h, float lr);
 
 /* ---- replay: ReplayBuffer.push / PrioritizedReplayBuffer.push (replay_buffer.py:10-11, :36-46) ----------
  * n transitions, row-major float32 (the cast of sac_imp.py:81-85 happens in the shim); done as 0/1 floats. */
@@ -168,6 +176,10 @@ int sacb_select_action_batch(sacb_handle h, const float *obs, int evaluate, cons
 /* ---- networks as callables (QNetwork.forward, GaussianPolicy.forward / .sample) on n rows -------------- */
 int sacb_q_forward(sacb_handle h, int agent, int net, const float *s, const float *a, int64_t n, float *q_out);
 int sacb_policy_forward(sacb_handle h, int agent, const float *s, int64_t n, float *mean_out, float *log_std_out);
+/* GaussianPolicy.sample (networks_model1.py:78-99 == networks_model2.py:99-120) on n rows: reparameterised draw, tanh squash, scale /
+ * bias, log-prob summed over the action components.  eps_or_null [n, act] = the N(0,1) draws of Normal.rsample; NULL => Philox. */
+int sacb_policy_sample(sacb_handle h, int agent, const float *s, int64_t n, const float *eps_or_null, float *action_out,
+                       float *log_prob_out);
 
 /* ---- data-parallel mode (BASELINE.json configs[3]): gradients are exported, all-reduced by the host over
  * NCCL (torch.distributed), then applied.  phase 0 = critics (sac_imp.py:101-113), 1 = actor+alpha (:116-135). */

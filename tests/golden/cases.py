@@ -73,3 +73,21 @@ def per_priorities(case):
 def per_td(case):
     rng = np.random.RandomState(700 + case["seed"])
     return np.abs(rng.standard_normal(case["batch"])).astype(np.float32)
+
+
+# networks as callables (QNetwork.forward, GaussianPolicy.forward / .sample) on the initial weights of these update cases
+NETS_CASES = ("tiny_m1", "tiny_m2", "c2_humanoid_m2")
+
+
+def nets_inputs(case, n):
+    rng = np.random.RandomState(900 + case["seed"])
+    return dict(s=rng.standard_normal((n, case["obs"])).astype(np.float32),
+                a=rng.uniform(-0.4, 0.4, (n, case["act"])).astype(np.float32),
+                eps=rng.standard_normal((n, case["act"])).astype(np.float32))
+
+
+def ckpt_transitions(case, n=20):
+    """Transitions pushed into the buffer before a checkpoint is written (float64 observations like MuJoCo, python scalars)."""
+    rng = np.random.RandomState(950 + case["seed"])
+    return [(rng.standard_normal(case["obs"]), rng.uniform(-0.4, 0.4, case["act"]).astype(np.float32), float(rng.standard_normal()),
+             rng.standard_normal(case["obs"]), bool(i % 6 == 5)) for i in range(n)]

@@ -200,7 +200,104 @@ def run_uniform_case(case):
     return out
 
 
+def run_nets_case(case, n=32):
+    """The networks as callables on the INITIAL weights: QNetwork.forward (networks_model1.py:27-33 / networks_model2.py:37-46),
+    GaussianPolicy.forward (:65-76 / :85-97) and GaussianPolicy.sample (:78-99 / :99-120) with the rsample draw injected."""
+    st = O.make_state(case["obs"], case["act"], case["hidden"], case["n_hidden"], seed=case["seed"],
+                      bias_scale=case.get("bias_scale", 0.0), head_scale=case.get("head_scale", 1.0))
+    agent = build_reference_agent(case, st)
+    inp = cases.nets_inputs(case, n)
+    s, a = torch.from_numpy(inp["s"]), torch.from_numpy(inp["a"])
+    out = {}
+    with torch.no_grad():
+        out["q1"] = agent.q1(s, a).numpy()
+        out["q2_target"] = agent.q2_target(s, a).numpy()
+        mean, log_std = agent.policy(s)
+        out["mean"], out["log_std"] = mean.numpy(), log_std.numpy()
+        with EpsInjector() as inj:
+            inj.queue.append(inp["eps"])
+            action, logp = agent.policy.sample(s)
+        out["action"], out["log_prob"] = action.numpy(), logp.numpy()
+    return out
+
+
+def _seeded_updates(agent, case, steps, first=0):
+    losses = []
+    with EpsInjector() as inj:
+        for step in range(first, first + steps):
+            b = O.make_batch(case["obs"], case["act"], case["batch"], seed=case["seed"] * 100 + step)
+            agent.replay_buffer.sample = lambda n, b=b: (b["s"], b["a"], b["r"], b["s2"], b["d"])
+            inj.queue += [b["eps_next"], b["eps_cur"]]
+            info = agent.update_parameters(case["batch"])
+            losses.append([info["q1_loss"], info["q2_loss"], info["policy_loss"]])
+    return np.array(losses, np.float64)
+
+
+def run_ckpt_written_by_reference():
+    """Files written by the reference's own save() (sac_imp.py:154-162) and save_checkpoint() (:177-201) after two seeded updates
+    of tiny_m1 with 20 transitions in the deque, plus what the reference itself does NEXT (third update, select_action)."""
+    case = cases.UPDATE_CASES["tiny_m1"]
+    st = O.make_state(case["obs"], case["act"], case["hidden"], case["n_hidden"], seed=case["seed"], bias_scale=case.get("bias_scale", 0.0))
+    agent = build_reference_agent(case, st)
+    sample_fn = agent.replay_buffer.sample
+    _seeded_updates(agent, case, 2)
+    for t in cases.ckpt_transitions(case):
+        agent.replay_buffer.push(*t)
+    agent.replay_buffer.sample = sample_fn
+    agent.save(os.path.join(HERE, "ckpt_ref_save.pt"))
+    agent.save_checkpoint(os.path.join(HERE, "ckpt_ref_checkpoint.pt"), episode=7, total_steps=123)
+    out = {"next_losses": _seeded_updates(agent, case, 1, first=2), "next_alpha": np.array(float(agent.alpha))}
+    obs_vec = np.random.RandomState(77 + case["seed"]).standard_normal(case["obs"]).astype(np.float32)
+    out["select_eval_after"] = agent.select_action(obs_vec, evaluate=True)
+    return out
+
+
+SHIPPED = {"bipedal": ("sac_BipedalWalker-v3_1737453113", dict(obs=24, act=4, hidden=256, n_hidden=2, batch=256, seed=31)),
+           "humanoid376": ("sac_Humanoid-v5_1734629000", dict(obs=376, act=17, hidden=256, n_hidden=2, batch=256, seed=32))}
+
+
+def run_shipped_checkpoint(tag):
+    """The reference loads its own shipped results/*/best_model.pt (sac_imp.py:164-173), acts, and takes one seeded update."""
+    import shutil
+    dirname, case = SHIPPED[tag]
+    src = os.path.join("/root/reference/results", dirname, "best_model.pt")
+    shutil.copyfile(src, os.path.join(HERE, f"shipped_{tag}_best_model.pt"))      # reference-held fixture (binary artefact, not source)
+    sac_imp.QNetwork, sac_imp.GaussianPolicy = networks_model1.QNetwork, networks_model1.GaussianPolicy
+    agent = sac_imp.SAC(case["obs"], case["act"], hidden_dim=case["hidden"], device="cpu")
+    # sac_imp.py:164-173 verbatim, except map_location: the shipped files hold CUDA tensors and this container has no GPU
+    ck = torch.load(src, map_location="cpu", weights_only=False)
+    for net in ("policy", "q1", "q2", "q1_target", "q2_target"):
+        getattr(agent, net).load_state_dict(ck[f"{net}_state_dict"])
+    agent.alpha = ck["alpha"]
+    out = {"alpha_loaded": np.array(float(agent.alpha))}
+    obs_mat = np.random.RandomState(77 + case["seed"]).standard_normal((8, case["obs"])).astype(np.float32)
+    out["select_eval"] = np.stack([agent.select_action(o, evaluate=True) for o in obs_mat])
+    inp = cases.nets_inputs(case, 16)
+    with torch.no_grad():
+        out["q1"] = agent.q1(torch.from_numpy(inp["s"]), torch.from_numpy(inp["a"])).numpy()
+    out["losses"] = _seeded_updates(agent, case, 1)
+    out["alpha_after"] = np.array(float(agent.alpha))
+    out["select_eval_after"] = np.stack([agent.select_action(o, evaluate=True) for o in obs_mat])
+    return out
+
+
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else None
+    if only in (None, "nets"):
+        for name in cases.NETS_CASES:
+            out = run_nets_case(cases.UPDATE_CASES[name])
+            np.savez_compressed(os.path.join(HERE, f"nets_{name}.npz"), **out)
+            print("nets", name, out["q1"][:2].ravel(), out["log_prob"][:2].ravel())
+    if only in (None, "ckpt"):
+        out = run_ckpt_written_by_reference()
+        np.savez_compressed(os.path.join(HERE, "ckpt_ref_expected.npz"), **out)
+        print("ckpt written by the reference; next losses", out["next_losses"])
+        for tag in SHIPPED:
+            out = run_shipped_checkpoint(tag)
+            np.savez_compressed(os.path.join(HERE, f"shipped_{tag}_expected.npz"), **out)
+            print("shipped", tag, "alpha", out["alpha_loaded"], "losses", out["losses"])
+    if only is not None:
+        return
     for name, case in cases.UPDATE_CASES.items():
         out = run_update_case(case)
         np.savez_compressed(os.path.join(HERE, f"update_{name}.npz"), **out)

@@ -121,3 +121,57 @@ def test_range_sample_is_random_sample(hw):
             assert list(got) == ref and random.random() == after_ref, (n, k, seed)
     with pytest.raises(ValueError):
         _range_sample(10, 11)
+
+
+def test_reference_loads_product_checkpoints():
+    """Interop in the other direction: files written by the PRODUCT on a B200 (tests/test_gpu_networks_ckpt.py::
+    test_write_product_checkpoints_for_the_reference, committed under tests/golden/) go through the reference's own
+    SAC.load / SAC.load_checkpoint (sac_imp.py:164-173, :203-233); the reference then takes the same next step the product took.
+    Needs the live reference: skipped where /root/reference does not exist (the GPU box)."""
+    import functools
+    import sys
+    gold = os.path.join(ROOT, "tests", "golden")
+    files = [os.path.join(gold, f) for f in ("product_save.pt", "product_checkpoint.pt", "product_expected.npz")]
+    if not os.path.isdir("/root/reference") or not all(os.path.exists(f) for f in files):
+        pytest.skip("needs /root/reference and the product-written fixtures")
+    import numpy as np
+    import torch
+    from oracle import sac_oracle_np as O
+    from tests.golden import cases
+    sys.dont_write_bytecode = True
+    saved = {k: sys.modules.get(k) for k in ("sac_imp", "networks_model1", "networks_model2", "replay_buffer")}
+    sys.path.insert(0, "/root/reference")
+    try:
+        for k in saved:
+            sys.modules.pop(k, None)
+        import sac_imp as ref_sac
+        case = cases.UPDATE_CASES["tiny_m1"]
+        real_load = torch.load
+        # the files hold CUDA tensors and a pickled list; the reference calls torch.load(path) bare (sac_imp.py:166, :205)
+        torch.load = functools.partial(real_load, map_location="cpu", weights_only=False)
+        try:
+            agent = ref_sac.SAC(case["obs"], case["act"], hidden_dim=case["hidden"], device="cpu")
+            agent.load(files[0])
+            ep, steps = agent.load_checkpoint(files[1])
+        finally:
+            torch.load = real_load
+        assert (ep, steps) == (3, 45) and len(agent.replay_buffer.buffer) == 20
+        assert agent.q1_optimizer.state_dict()["state"][0]["step"] == 2
+        b = O.make_batch(case["obs"], case["act"], case["batch"], seed=case["seed"] * 100 + 2)
+        agent.replay_buffer.sample = lambda n: (b["s"], b["a"], b["r"], b["s2"], b["d"])
+        queue = [b["eps_next"], b["eps_cur"]]
+        orig = torch.distributions.normal._standard_normal
+        torch.distributions.normal._standard_normal = lambda shape, dtype, device: torch.from_numpy(queue.pop(0)).to(dtype)
+        try:
+            info = agent.update_parameters(case["batch"])
+        finally:
+            torch.distributions.normal._standard_normal = orig
+        exp = np.load(files[2])
+        np.testing.assert_allclose([info["q1_loss"], info["q2_loss"], info["policy_loss"]], exp["next_losses"], rtol=3e-4)
+        np.testing.assert_allclose(float(agent.alpha), exp["next_alpha"], rtol=1e-5)
+    finally:
+        sys.path.remove("/root/reference")
+        for k, v in saved.items():
+            sys.modules.pop(k, None)
+            if v is not None:
+                sys.modules[k] = v

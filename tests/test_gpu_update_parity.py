@@ -66,7 +66,12 @@ def run_case(hw, name, math, launch):
         for nm, ref in getattr(st, net).items():
             frac_bad = np.mean(np.abs(mine[nm] - ref) > budget)
             assert frac_bad < tol["frac"], (net, nm, frac_bad, np.abs(mine[nm] - ref).max())
-            assert np.abs(mine[nm].ravel()[:64] - g[f"paramhead/{net}/{nm}"]).max() < 2.1 * st.lr * case["steps"]
+            # directly against the live reference's weights (no oracle, no ReLU hint in between): the oracle<->golden budget
+            # (0.02 lr per step) plus the device<->oracle budget; a ReLU tie that falls the other way moves single entries by up to
+            # 2 lr, so at most 2 of the 64 kept values may exceed it -- a wrong-sign or missing step fails on every entry
+            dg = np.abs(mine[nm].ravel()[:64] - g[f"paramhead/{net}/{nm}"])
+            assert dg.max() < 2.1 * st.lr * case["steps"], (net, nm, dg.max())
+            assert int(np.sum(dg > 2 * budget)) <= 2, (net, nm, np.sort(dg)[-4:], budget)
     for net, opt in (("policy", st.policy_opt), ("q1", st.q1_opt), ("q2", st.q2_opt)):
         sd = getattr(agent, f"{net}_optimizer").state_dict()
         names = list(getattr(st, net).keys())

@@ -68,3 +68,31 @@ def grad_close(got, ref, tol, max_flips=2):
     overall = relerr(got, ref)
     ok = overall < tol or (bad <= max_flips and overall < 5e-2)
     return ok, overall, bad
+
+
+def state_from_checkpoint(path, case, alpha_from_file=True):
+    """Oracle SACState holding the networks of a reference-format `save()` / `save_checkpoint()` file (sac_imp.py:154-233)."""
+    ck = torch.load(path, map_location="cpu", weights_only=False)
+    st = O.make_state(case["obs"], case["act"], case["hidden"], case["n_hidden"], seed=0)
+    for net in ("policy", "q1", "q2", "q1_target", "q2_target"):
+        setattr(st, net, {k: v.detach().cpu().numpy().astype(np.float32).copy() for k, v in ck[f"{net}_state_dict"].items()})
+    if alpha_from_file:
+        a = ck["alpha"]
+        st.alpha = float(a.detach().reshape(-1)[0]) if torch.is_tensor(a) else float(a)
+    for net, opt in (("policy", "policy_opt"), ("q1", "q1_opt"), ("q2", "q2_opt")):
+        sd = ck.get(f"{net}_optimizer_state_dict")
+        if sd and sd["state"]:
+            names = list(getattr(st, net).keys())
+            o = getattr(st, opt)
+            for i, nm in enumerate(names):
+                o.m[nm] = sd["state"][i]["exp_avg"].cpu().numpy().copy()
+                o.v[nm] = sd["state"][i]["exp_avg_sq"].cpu().numpy().copy()
+            o.step = int(float(sd["state"][0]["step"]))
+    if "log_alpha" in ck:
+        st.log_alpha = ck["log_alpha"].detach().cpu().numpy().astype(np.float32).reshape(1).copy()
+        sd = ck.get("alpha_optimizer_state_dict")
+        if sd and sd["state"]:
+            st.alpha_opt.m["log_alpha"] = sd["state"][0]["exp_avg"].cpu().numpy().reshape(1).copy()
+            st.alpha_opt.v["log_alpha"] = sd["state"][0]["exp_avg_sq"].cpu().numpy().reshape(1).copy()
+            st.alpha_opt.step = int(float(sd["state"][0]["step"]))
+    return st, ck
