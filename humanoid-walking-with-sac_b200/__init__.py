@@ -11,9 +11,9 @@ import sys
 
 from . import _native, distributed, networks_model1, networks_model2, replay_buffer, sac_imp
 from .replay_buffer import PrioritizedReplayBuffer, ReplayBuffer
-from .sac_imp import SAC
+from .sac_imp import SAC, PopulationSAC
 
-__all__ = ["SAC", "ReplayBuffer", "PrioritizedReplayBuffer", "install", "use_networks", "networks_model1", "networks_model2", "distributed"]
+__all__ = ["SAC", "PopulationSAC", "ReplayBuffer", "PrioritizedReplayBuffer", "install", "use_networks", "networks_model1", "networks_model2", "distributed"]
 
 
 def use_networks(variant):

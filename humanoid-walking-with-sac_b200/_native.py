@@ -21,7 +21,7 @@ LAUNCH_STAGED, LAUNCH_PERSISTENT = 0, 1
 NET_POLICY, NET_Q1, NET_Q2, NET_Q1_TARGET, NET_Q2_TARGET = range(5)
 SLOT_PARAM, SLOT_ADAM_M, SLOT_ADAM_V, SLOT_GRAD = range(4)
 REPLAY_UNIFORM, REPLAY_PER = 0, 1
-USE_LAST_SAMPLE, NO_LOSS_READBACK, EXPORT_GRADS = 1, 2, 4
+USE_LAST_SAMPLE, NO_LOSS_READBACK, EXPORT_GRADS, DEVICE_INDICES = 1, 2, 4, 8
 
 
 class Config(ctypes.Structure):
@@ -90,9 +90,11 @@ SIGNATURES = {
     "sacb_per_get_stats": (I, [H, I, ctypes.POINTER(PerStats)]),
     "sacb_per_set_frame": (I, [H, I, I64]),
     "sacb_update": (I, [H, I64, c_i64p, c_f32p, c_f32p, c_f32p, U32]),
+    "sacb_update_steps": (I, [H, I64, I, c_f32p, U32]),
     "sacb_update_batch": (I, [H, I64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, U32]),
     "sacb_stage_indices": (I, [H, c_i64p, I64, I64]),
     "sacb_get_losses": (I, [H, I, c_f32p]),
+    "sacb_get_losses_all": (I, [H, c_f32p]),
     "sacb_select_action": (I, [H, I, c_f32p, I, c_f32p, c_f32p]),
     "sacb_select_action_batch": (I, [H, c_f32p, I, c_f32p, c_f32p]),
     "sacb_q_forward": (I, [H, I, I, c_f32p, c_f32p, I64, c_f32p]),
@@ -107,6 +109,7 @@ SIGNATURES = {
     "sacb_timer_stop": (I, [H, c_f32p]),
     "sacb_time_update": (I, [H, I64, I, c_f32p]),
     "sacb_time_stages": (I, [H, I64, c_f32p, I]),
+    "sacb_debug_read_slots": (I, [H, I, ctypes.POINTER(ctypes.c_int32), I64]),
     "sacb_debug_read_activation": (I, [H, I, I, I, I, I64, c_f32p]),
     "sacb_selftest_gemm": (I, [I, I, I, I, I, I, I, c_f32p]),
     "sacb_selftest_gemm_tile": (I, [I, I, I, I, I, I, I, I, I, c_f32p]),

@@ -67,6 +67,7 @@ enum ScalarSlot {
     SC_LOSS_Q1, SC_LOSS_Q2, SC_LOSS_PI, SC_LOSS_ALPHA,
     SC_ERROR_FLAG,                   // copy of the device error flag made by T_FINISH: losses + flag come back in ONE D2H copy
     SC_COUNT = 16,
+    SC_HIST_POS = 24,                // int32 bit pattern: completed updates since create, never reset: loss_hist[(pos % kLossHist)] = losses of that update
     // Adam bias-correction factors of the NEXT step of each optimizer, refreshed whenever a step counter changes
     // (T_FINISH, sacb_set_scalars, the data-parallel apply): [SC_FAC0 + 2*(step_slot - SC_STEP_POLICY)] = step_size, +1 = sqrt(bc2)
     SC_FAC0 = 16
@@ -186,6 +187,7 @@ struct Program {
     unsigned int *barrier;    // grid barrier counter (persistent mode)
     // replay ring (T_GATHER)
     const float *ring; int64_t ring_agent_stride; int32_t ring_row; int32_t pad0;
+    const int64_t *ring_meta; // [n_agents][2] = (stored transitions, slot of the oldest one): the uniform ring as the device sees it (device index draws)
     const int32_t *slots;     // physical ring slots of the minibatch rows [n_agents, B]
     int32_t slots_stride; int32_t pad1;
     int32_t *error_flag;      // set by watchdogs (mbarrier / grid barrier timeouts)
@@ -197,6 +199,7 @@ struct Program {
 // ---- tile geometry ----------------------------------------------------------------------------------------
 constexpr int kThreads = 512;
 constexpr int kAdamTable = 32768;   // beyond ~17.3 k steps both bias corrections round to exactly 1.0f: the last entry serves every later step
+constexpr int kLossHist = 64;     // per-agent ring of the last updates' (q1, q2, policy, alpha) losses: K updates per call, ONE read-back
 constexpr int kTraceSlots = 64;   // 0..5 kernel phases, 6 accumulator ready, 16+kb TMA issue of k-block kb, 32+kb its arrival (kb < 16)
 // FFMA path (checker / strict mode)
 constexpr int kSM = 64, kSN = 64, kSK = 16;

@@ -51,6 +51,7 @@ struct Layout {
     NetLayout pol, q;
     // arena (per agent): scalars | params pol,q1,q2,q1t,q2t | m pol,q1,q2 | v pol,q1,q2 | grad pol,q1,q2 | shadows x5
     int64_t scalars = 0;
+    int64_t loss_hist = 0;          // [kLossHist][4] losses of the last updates (T_FINISH), see sacb_update_steps
     int64_t param[5] = {0, 0, 0, 0, 0};
     int64_t shadow[5] = {0, 0, 0, 0, 0};
     int64_t adam_m[3] = {0, 0, 0}, adam_v[3] = {0, 0, 0}, grad[3] = {0, 0, 0};
@@ -124,6 +125,8 @@ struct sacb_handle_s {
     float *ring = nullptr;
     int64_t ring_row = 0;                // floats per transition: [s | s2 | a | r | d] padded to 4
     std::vector<int64_t> r_len, r_pos, r_head;   // per agent: count, next write slot, slot of the oldest entry
+    int64_t *ring_meta = nullptr;        // device [n_agents][2] = (r_len, r_head) for on-device index draws; re-uploaded when a push changed it
+    bool ring_meta_dirty = true;
     float *stage_rows = nullptr;         // device staging for pushes
     int64_t stage_rows_cap = 0;
     int32_t *gather_slots = nullptr;     // [stage_rows_cap] slots of a host-facing gather (sacb_read_transitions)
@@ -139,6 +142,7 @@ struct sacb_handle_s {
     float *pin = nullptr;
     int64_t pin_floats = 0;
     float *pin_rows = nullptr;           // packed minibatch rows of sacb_update_batch
+    float *pin_hist = nullptr;           // [32 + 4 * kLossHist] scalar block + loss history of agent 0 (sacb_update_steps: ONE read-back for K updates)
     float *pin_small = nullptr;          // [16] losses + error flag read back with ONE synchronisation (finish_update)
     float *pin_push = nullptr;           // staging of small pushes (<= kPinPushRows rows): no synchronisation on the push path
     cudaEvent_t ev_push = nullptr;       // the H2D copy out of pin_push has completed
@@ -178,5 +182,6 @@ void after_update_launch(sacb_handle h, const ProgramKey &key);
 int replay_create(sacb_handle h);
 void replay_destroy(sacb_handle h);
 int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B, int64_t *k_out);   // kernels of one sample() call
+int upload_ring_meta(sacb_handle h);                                                                   // (len, head) of every agent's ring -> device, if a push changed them
 int per_writeback_launch(sacb_handle h, cudaStream_t st, int64_t B);                                 // priorities <- |td| of the last update
 }  // namespace sacb

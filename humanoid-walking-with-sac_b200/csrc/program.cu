@@ -69,6 +69,7 @@ void Layout::build(int obs_, int act_, int hidden_, int n_hidden_, int maxB_) {
     build_net(q, false, obs + act, hidden, n_hidden, 1, act);
     int64_t o = 0;
     scalars = o; o += 32;
+    loss_hist = o; o += 4 * kLossHist;
     param[0] = o; o += pol.size;
     for (int k = 1; k < 5; k++) { param[k] = o; o += q.size; }
     const int64_t sz[3] = {pol.size, q.size, q.size};
@@ -252,7 +253,7 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
                     }
                     break;
                 case T_SHADOW: if constexpr ((kTypes & tb(T_SHADOW)) != 0) task_shadow(t, tile, P, agent); break;
-                case T_GATHER: if constexpr ((kTypes & tb(T_GATHER)) != 0) task_gather(t, tile, P, agent); break;
+                case T_GATHER: if constexpr ((kTypes & tb(T_GATHER)) != 0) task_gather(t, tile, P, agent, scalars, seed); break;
                 case T_SAMPLE: if constexpr ((kTypes & tb(T_SAMPLE)) != 0) task_sample(t, tile, P, agent, scalars, seed); break;
                 case T_TARGET_LOSS: if constexpr ((kTypes & tb(T_TARGET_LOSS)) != 0) task_target_loss(t, tile, P, agent, scalars, s_red); break;
                 case T_ACTOR_LOSS: if constexpr ((kTypes & tb(T_ACTOR_LOSS)) != 0) task_actor_loss(t, tile, P, agent, scalars, s_red); break;
@@ -503,6 +504,8 @@ struct Builder {
             Task t = blank(T_GATHER);
             t.pm[0] = xrows(0, 3 * B, L.ldx).ref; t.p[0] = W(L.r); t.p[1] = W(L.d);
             t.i[0] = B; t.i[1] = obs; t.i[2] = act;
+            t.i[3] = key.with_gather == 3 ? 1 : 0;      // 3: positions drawn on the device (uniform ring), see draw_position
+            t.i[4] = (int32_t)h->cfg.capacity;
             add(t, cdiv(B, 4));
         }
         if (critics) {
@@ -668,6 +671,7 @@ struct Builder {
             t.p[0] = critics ? W(L.loss_part) : null_ref();
             t.p[1] = actor ? W(L.aloss_part) : null_ref();
             t.p[2] = exporting() ? A(L.grad_scalars) : null_ref();
+            t.p[3] = A(L.loss_hist);
             t.i[0] = ap; t.i[1] = ap; t.i[2] = ap; t.i[3] = ap && h->cfg.auto_entropy; t.i[4] = ap;
             t.i[5] = cdiv(B, kLossRows); t.i[6] = h->cfg.auto_entropy; t.i[7] = ap;
             t.f[0] = h->cfg.lr; t.f[1] = (float)B;
@@ -827,6 +831,7 @@ int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out) {
         P.ring = h->ring; P.ring_agent_stride = h->cfg.capacity * h->ring_row; P.slots = h->slots;
     }
     P.ring_row = (int32_t)h->ring_row; P.slots_stride = h->cfg.max_batch;
+    P.ring_meta = h->ring_meta;
     P.error_flag = h->error_flag;
     P.trace = nullptr; P.timeline = nullptr; P.adam_table = h->adam_table;
     p.kernels_per_step = h->cfg.launch_mode == SACB_LAUNCH_PERSISTENT ? 1 : (int)p.stages.size();

@@ -633,13 +633,35 @@ int replay_create(sacb_handle h) {
 }
 
 void replay_destroy(sacb_handle h) {
-    cudaFree(h->ring); cudaFree(h->stage_rows); cudaFree(h->prio); cudaFree(h->p_alpha); cudaFree(h->per_ws); cudaFree(h->last_idx_dev); cudaFree(h->gather_slots);
+    cudaFree(h->ring); cudaFree(h->stage_rows); cudaFree(h->prio); cudaFree(h->p_alpha); cudaFree(h->per_ws); cudaFree(h->last_idx_dev); cudaFree(h->gather_slots); cudaFree(h->ring_meta);
 }
 
 // logical index -> physical ring slot.  uniform: deque order (j-th oldest); PER: list position
 static inline int64_t physical_slot(sacb_handle h, int agent, int64_t j) {
     if (h->cfg.replay_kind == SACB_REPLAY_PER) return j;
     return (h->r_head[agent] + j) % h->cfg.capacity;
+}
+
+// ring geometry for the device index draws: values travel as kernel parameters (no staging buffer to keep alive), <= 128 agents per launch
+struct MetaChunk { int64_t v[256]; };
+__global__ void set_ring_meta_kernel(int64_t *meta, MetaChunk c, int first, int count) {
+    const int i = threadIdx.x;
+    if (i < 2 * count) meta[2 * first + i] = c.v[i];
+}
+int upload_ring_meta(sacb_handle h) {
+    if (!h->ring_meta_dirty) return SACB_OK;
+    const int n = h->cfg.n_agents;
+    if (!h->ring_meta && cudaMalloc(&h->ring_meta, sizeof(int64_t) * 2 * n) != cudaSuccess) return fail(SACB_ERR_NOMEM, "device allocation failed");
+    for (int first = 0; first < n; first += 128) {
+        MetaChunk c;
+        const int count = std::min(128, n - first);
+        for (int a = 0; a < count; a++) { c.v[2 * a] = h->r_len[first + a]; c.v[2 * a + 1] = h->r_head[first + a]; }
+        set_ring_meta_kernel<<<1, 256, 0, h->stream>>>(h->ring_meta, c, first, count);
+        h->kernel_launches++;
+    }
+    SACB_CUDA(cudaGetLastError());
+    h->ring_meta_dirty = false;
+    return SACB_OK;
 }
 
 int replay_stage_slots(sacb_handle h, const int64_t *idx, int64_t B) {
@@ -691,6 +713,7 @@ extern "C" int64_t sacb_len(sacb_handle h, int agent) {
 extern "C" int sacb_clear_replay(sacb_handle h, int agent) {
     if (!h || agent < 0 || agent >= h->cfg.n_agents) return fail(SACB_ERR_ARG, "bad argument");
     h->r_len[agent] = h->r_pos[agent] = h->r_head[agent] = 0;
+    h->ring_meta_dirty = true;
     h->sample_k = 0;
     h->prio_max_valid = false;
     if (h->prio) { cudaMemsetAsync(h->prio, 0, sizeof(float) * h->cfg.capacity, h->stream); cudaMemsetAsync(h->p_alpha, 0, sizeof(float) * h->cfg.capacity, h->stream); }
@@ -726,6 +749,7 @@ extern "C" int sacb_push(sacb_handle h, int agent, const float *s, const float *
     float *ring = h->ring + (int64_t)agent * cap * row;
     const bool per = c.replay_kind == SACB_REPLAY_PER;
     int64_t done_n = 0;
+    h->ring_meta_dirty = true;
     while (done_n < n) {
         // next write slot; a contiguous run never crosses the end of the ring
         int64_t slot;
@@ -771,6 +795,7 @@ extern "C" int sacb_push_rows(sacb_handle h, int agent, const float *rows, int64
         rows = h->pin_push;
     }
     int64_t done_n = 0;
+    h->ring_meta_dirty = true;
     while (done_n < n) {
         int64_t slot;
         if (per) slot = h->r_pos[agent];

@@ -122,6 +122,7 @@ extern "C" int sacb_destroy(sacb_handle h) {
     cudaFree(h->arena); cudaFree(h->ws); cudaFree(h->barrier); cudaFree(h->error_flag); cudaFree(h->slots); cudaFree(h->slots_identity); cudaFree(h->adam_table); cudaFree(h->slots_staged);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->pin_small) cudaFreeHost(h->pin_small);
+    if (h->pin_hist) cudaFreeHost(h->pin_hist);
     if (h->pin_push) cudaFreeHost(h->pin_push);
     if (h->pin_u) cudaFreeHost(h->pin_u);
     if (h->ev_u) cudaEventDestroy(h->ev_u);
@@ -285,6 +286,15 @@ extern "C" int sacb_get_losses(sacb_handle h, int agent, float *losses_out) {
     return check_error_flag(h);
 }
 
+extern "C" int sacb_get_losses_all(sacb_handle h, float *losses_out) {
+    if (!h || !losses_out) return fail(SACB_ERR_ARG, "bad argument");
+    // one strided copy: the loss scalars sit at the same offset of every agent's arena
+    SACB_CUDA(cudaMemcpy2DAsync(losses_out, 3 * sizeof(float), h->arena + h->L.scalars + SC_LOSS_Q1, sizeof(float) * h->L.arena_size, 3 * sizeof(float),
+                                h->cfg.n_agents, cudaMemcpyDeviceToHost, h->stream));
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    return check_error_flag(h);
+}
+
 // ---- update_parameters ---------------------------------------------------------------------------------------------
 static int upload_eps(sacb_handle h, int agent, int64_t B, const float *eps_next, const float *eps_cur) {
     float *ws = h->ws + agent * h->L.ws_size;
@@ -360,17 +370,23 @@ extern "C" int sacb_update(sacb_handle h, int64_t B, const int64_t *idx, const f
     if (!h) return fail(SACB_ERR_ARG, "null handle");
     if (B < 1 || B > h->L.maxB) return fail(SACB_ERR_ARG, "batch size out of range");
     if ((eps_next == nullptr) != (eps_cur == nullptr)) return fail(SACB_ERR_ARG, "pass both eps arrays or neither");
-    int rc;
+    int rc, gather_mode = 1;
     if (idx) {
         rc = replay_stage_slots(h, idx, B);
         if (rc) return rc;
-    } else if (h->staged_steps > 0 && !(flags & SACB_USE_LAST_SAMPLE)) {
+    } else if (h->staged_steps > 0 && !(flags & SACB_DEVICE_INDICES) && !(flags & SACB_USE_LAST_SAMPLE)) {
         const int64_t k = h->staged_next % h->staged_steps;
         h->staged_next++;
         SACB_CUDA(cudaMemcpyAsync(h->slots, h->slots_staged + k * h->cfg.n_agents * h->staged_B, sizeof(int32_t) * h->staged_B * h->cfg.n_agents,
                                   cudaMemcpyDeviceToDevice, h->stream));
+    } else if (flags & SACB_DEVICE_INDICES) {      // positions drawn inside the gather stage (uniform ring, without replacement)
+        if (h->cfg.replay_kind != SACB_REPLAY_UNIFORM) return fail(SACB_ERR_ARG, "SACB_DEVICE_INDICES needs the uniform replay ring (the prioritized one has sacb_per_step)");
+        for (int a = 0; a < h->cfg.n_agents; a++)
+            if (B > h->r_len[a]) return fail(SACB_ERR_STATE, "Sample larger than population or is negative");
+        if ((rc = upload_ring_meta(h))) return rc;
+        gather_mode = 3;
     } else if (!(flags & SACB_USE_LAST_SAMPLE)) {
-        return fail(SACB_ERR_ARG, "no indices: pass idx, stage them, or set SACB_USE_LAST_SAMPLE");
+        return fail(SACB_ERR_ARG, "no indices: pass idx, stage them, set SACB_DEVICE_INDICES or SACB_USE_LAST_SAMPLE");
     } else if (h->cfg.replay_kind == SACB_REPLAY_PER && h->sample_k != B) {
         // set_priorities / clear / a sample of another size leave no (or a stale) minibatch behind
         return fail(SACB_ERR_STATE, "SACB_USE_LAST_SAMPLE: the last prioritized sample does not hold B rows (sample again)");
@@ -381,7 +397,7 @@ extern "C" int sacb_update(sacb_handle h, int64_t B, const int64_t *idx, const f
         if (rc) return rc;
     }
     const int use_isw = (h->cfg.per_weighted_loss && h->cfg.replay_kind == SACB_REPLAY_PER) ? 1 : 0;
-    ProgramKey key = update_key(h, (int)B, 1, (flags & SACB_EXPORT_GRADS) ? 1 : 0, eps_next ? 0 : 1, use_isw);
+    ProgramKey key = update_key(h, (int)B, gather_mode, (flags & SACB_EXPORT_GRADS) ? 1 : 0, eps_next ? 0 : 1, use_isw);
     ProgramInst *p;
     rc = get_program(h, key, &p);
     if (rc) return rc;
@@ -397,7 +413,7 @@ extern "C" int sacb_update(sacb_handle h, int64_t B, const int64_t *idx, const f
  *   stream2:                                          priority write-back |q1 - y| -> prioritized sample for the NEXT step
  * Same kernels, same order of the dependent operations and therefore the same values as sacb_per_sample -> sacb_update(USE_LAST_SAMPLE)
  * -> sacb_per_update_from_td called in sequence (tests/test_gpu_replay.py::test_pipelined_step_equals_sequential). */
-extern "C" int sacb_per_step(sacb_handle h, int64_t B, float *losses_out, uint32_t flags) {
+static int per_step_enqueue(sacb_handle h, int64_t B) {
     if (!h || h->cfg.replay_kind != SACB_REPLAY_PER || h->cfg.n_agents != 1) return fail(SACB_ERR_ARG, "handle has no prioritized buffer");
     if (B < 1 || B > h->L.maxB) return fail(SACB_ERR_ARG, "batch size out of range");
     if (!h->stream2) {
@@ -426,7 +442,42 @@ extern "C" int sacb_per_step(sacb_handle h, int64_t B, float *losses_out, uint32
     SACB_CUDA(cudaEventRecord(h->ev_sampled, h->stream2));
     if ((rc = launch_program_part(h, *p, 1))) return rc;
     SACB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_sampled, 0));      // whatever follows on the main stream sees the new sample
+    return SACB_OK;
+}
+
+extern "C" int sacb_per_step(sacb_handle h, int64_t B, float *losses_out, uint32_t flags) {
+    int rc = per_step_enqueue(h, B);
+    if (rc) return rc;
     return finish_update(h, losses_out, flags);
+}
+
+/* K learner steps per call, nothing of a step touches the host ("multi-step fused launches with on-device index
+ * draw"): K replays of the step graph(s) back to back -- prioritized ring: the sacb_per_step pipeline; uniform ring: positions drawn
+ * inside the gather stage (SACB_DEVICE_INDICES) -- then ONE device->host copy of the scalar block and the loss history ring.
+ * Bitwise equal to K single calls. */
+extern "C" int sacb_update_steps(sacb_handle h, int64_t B, int K, float *losses_out, uint32_t flags) {
+    if (!h || K < 1 || K > kLossHist) return fail(SACB_ERR_ARG, "K must be 1..64");
+    if (h->cfg.n_agents != 1 && losses_out) return fail(SACB_ERR_ARG, "loss read-back of sacb_update_steps serves a single agent (use sacb_get_losses per agent)");
+    int rc;
+    for (int i = 0; i < K; i++) {
+        if (h->cfg.replay_kind == SACB_REPLAY_PER) rc = per_step_enqueue(h, B);
+        else rc = sacb_update(h, B, nullptr, nullptr, nullptr, nullptr, (flags & ~SACB_USE_LAST_SAMPLE) | SACB_DEVICE_INDICES | SACB_NO_LOSS_READBACK);
+        if (rc) return rc;
+    }
+    if ((flags & SACB_NO_LOSS_READBACK) || !losses_out) return (flags & SACB_NO_LOSS_READBACK) ? SACB_OK : sacb_synchronize(h);
+    constexpr int kN = 32 + 4 * kLossHist;
+    if (!h->pin_hist && cudaMallocHost(&h->pin_hist, sizeof(float) * kN) != cudaSuccess) return fail(SACB_ERR_NOMEM, "pinned allocation failed");
+    SACB_CUDA(cudaMemcpyAsync(h->pin_hist, h->arena + h->L.scalars, sizeof(float) * 32, cudaMemcpyDeviceToHost, h->stream));
+    SACB_CUDA(cudaMemcpyAsync(h->pin_hist + 32, h->arena + h->L.loss_hist, sizeof(float) * 4 * kLossHist, cudaMemcpyDeviceToHost, h->stream));
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    int32_t pos, flag;
+    memcpy(&pos, h->pin_hist + SC_HIST_POS, 4);
+    memcpy(&flag, h->pin_hist + SC_ERROR_FLAG, 4);
+    for (int i = 0; i < K; i++) {
+        const int slot = ((pos - K + i) % kLossHist + kLossHist) % kLossHist;
+        memcpy(losses_out + 3 * i, h->pin_hist + 32 + 4 * slot, 3 * sizeof(float));
+    }
+    return flag ? check_error_flag(h) : SACB_OK;
 }
 
 extern "C" int sacb_debug_read_activation(sacb_handle h, int agent, int group, int k, int layer, int64_t B, float *out) {
@@ -449,6 +500,13 @@ extern "C" int sacb_debug_read_activation(sacb_handle h, int agent, int group, i
         memcpy(&fa, &a, 4); memcpy(&fb, &b, 4);
         out[i] = fa + fb;
     }
+    return SACB_OK;
+}
+
+extern "C" int sacb_debug_read_slots(sacb_handle h, int agent, int32_t *slots_out, int64_t B) {
+    if (!h || !slots_out || agent < 0 || agent >= h->cfg.n_agents || B < 1 || B > h->L.maxB) return fail(SACB_ERR_ARG, "bad argument");
+    SACB_CUDA(cudaMemcpyAsync(slots_out, h->slots + (int64_t)agent * h->cfg.max_batch, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, h->stream));
+    SACB_CUDA(cudaStreamSynchronize(h->stream));
     return SACB_OK;
 }
 

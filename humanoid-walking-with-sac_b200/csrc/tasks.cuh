@@ -61,12 +61,43 @@ __device__ __forceinline__ void task_shadow(const Task &t, int tile, const Progr
 // four rows per tile, four warps per sampled row: one warp per destination row (the fourth moves r and d).  A lane forms
 // pairs of neighbouring destination columns (one 4-byte store per bf16 plane); ring reads are coalesced streaming loads,
 // 8 in flight per lane.
-__device__ __forceinline__ void task_gather(const Task &t, int tile, const Program &P, int agent) {
+// Device index draw of the uniform ring (production mode, no host in the loop): minibatch row b of update `step` reads the
+// transition at logical position perm(b), perm = a keyed bijection of [0, n) -- B DISTINCT positions, i.e. sampling without
+// replacement like random.sample (replay_buffer.py:15).  The bijection works on the next power of two (rounds of odd multiply /
+// add / xor-shift, each a bijection of k-bit integers, keyed by Philox(seed; step, agent)) and cycle-walks back into [0, n).
+__device__ __forceinline__ uint32_t draw_position(uint32_t b, uint32_t n, uint64_t seed, uint32_t agent, uint32_t step) {
+    uint32_t key[4] = {step, agent, 0x1d5a7b1eu, 0u};
+    philox4x32(key, (uint32_t)seed, (uint32_t)(seed >> 32));
+    uint32_t k2[4] = {step, agent, 0x1d5a7b1fu, 1u};
+    philox4x32(k2, (uint32_t)seed, (uint32_t)(seed >> 32));
+    const int bits = n <= 2 ? 1 : 32 - __clz(n - 1);
+    const uint32_t mask = bits >= 32 ? 0xFFFFFFFFu : ((1u << bits) - 1u);
+    const int sh = max(1, bits / 2);
+    uint32_t x = b;
+    do {
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            x = (x * (key[r] | 1u) + k2[r]) & mask;
+            x ^= x >> sh;
+        }
+    } while (x >= n);
+    return x;
+}
+
+__device__ __forceinline__ void task_gather(const Task &t, int tile, const Program &P, int agent, const float *scalars, uint64_t seed) {
     const int B = t.i[0], obs = t.i[1], act = t.i[2];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int b = tile * 4 + (warp >> 2), part = warp & 3;
     if (b >= B) return;
-    const int slot = P.slots[(int64_t)agent * P.slots_stride + b];
+    int slot;
+    if (t.i[3]) {      // indices drawn here (the four warps of a row compute the same slot); recorded for the host / tests
+        const int64_t n = P.ring_meta[2 * agent], head = P.ring_meta[2 * agent + 1];
+        const uint32_t step = (uint32_t)__float_as_int(ldcg(scalars + SC_N_UPDATES));
+        slot = (int)((head + draw_position((uint32_t)b, (uint32_t)n, seed, (uint32_t)agent, step)) % t.i[4]);
+        if (part == 3 && lane == 2) const_cast<int32_t *>(P.slots)[(int64_t)agent * P.slots_stride + b] = slot;
+    } else {
+        slot = P.slots[(int64_t)agent * P.slots_stride + b];
+    }
     const float *row = P.ring + agent * P.ring_agent_stride + (int64_t)slot * P.ring_row;
     if (part == 3) {
         if (lane == 0) resolve(t.p[0], P.bases, agent)[b] = __ldcs(row + 2 * obs + act);
@@ -447,7 +478,13 @@ __device__ __forceinline__ void task_finish(const Task &t, const Program &P, int
             }
             if (t.i[7]) sc[SC_ALPHA0 + ((n_upd + 1) & 1)] = alpha_next;
         }
-        if (t.i[4]) sc[SC_N_UPDATES] = __int_as_float(__float_as_int(sc[SC_N_UPDATES]) + 1);
+        if (t.i[4]) {
+            sc[SC_N_UPDATES] = __int_as_float(__float_as_int(sc[SC_N_UPDATES]) + 1);
+            const int pos = __float_as_int(sc[SC_HIST_POS]);
+            float *hist = resolve(t.p[3], P.bases, agent) + 4 * (pos % kLossHist);
+            hist[0] = sc[SC_LOSS_Q1]; hist[1] = sc[SC_LOSS_Q2]; hist[2] = sc[SC_LOSS_PI]; hist[3] = sc[SC_LOSS_ALPHA];
+            sc[SC_HIST_POS] = __int_as_float(pos + 1);
+        }
         sc[SC_ERROR_FLAG] = __int_as_float(*reinterpret_cast<volatile int *>(P.error_flag));      // watchdog flags of the earlier stages
     }
     __syncthreads();      // thread 0 has read the current bias corrections

@@ -48,6 +48,8 @@ class DataParallelSAC:
 
     def __init__(self, agent, group=None):
         self.agent, self.group = agent, group
+        self.exchange = True           # False: skip the all-reduces (measurement of their share only; the replicas then diverge)
+        self.exchange_kind = "ncclAllReduce (torch.distributed) on the library's stream + element-wise Adam apply"
         self._bufs = {}
         for phase in (0, 1, 2):
             ptr, n = ctypes.c_void_p(), ctypes.c_int64()
@@ -80,7 +82,8 @@ class DataParallelSAC:
         with torch.cuda.stream(self._stream):
             for phase in (0, 1):
                 N.check(lib.sacb_dp_backward(a._h, phase, n_local, N.ptr(ix, ctypes.c_int64) if (phase == 0 and ix is not None) else None, N.ptr(e_next), N.ptr(e_cur)))
-                allreduce_mean_(self.gradient_slabs(phase), self.group)       # same stream: ordered behind the backward, ahead of the apply
+                if self.exchange:
+                    allreduce_mean_(self.gradient_slabs(phase), self.group)   # same stream: ordered behind the backward, ahead of the apply
                 N.check(lib.sacb_dp_apply(a._h, phase))
         a._alpha_is_float = False
         if not sync:

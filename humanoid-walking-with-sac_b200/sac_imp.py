@@ -267,6 +267,20 @@ class SAC:
             return None
         return {"q1_loss": float(losses[0]), "q2_loss": float(losses[1]), "policy_loss": float(losses[2])}
 
+    def learner_steps(self, batch_size=256, k=8, *, sync=True):
+        """K learner steps per call, nothing of a step on the host (trainer.py:190-205 with the updates of K
+        environment steps batched): prioritized ring = K x the `learner_step` pipeline, uniform ring = K updates whose positions are
+        drawn inside the gather stage (a keyed bijection of range(len): distinct positions, like random.sample); eps on the device;
+        ONE read-back of the K loss triples.  Bitwise equal to K single calls.  Returns a list of K dicts (sync=False: None)."""
+        self.replay_buffer._flush()
+        self._publish_alias_writes()
+        losses = np.zeros((k, 3), np.float32)
+        N.check(N.lib().sacb_update_steps(self._h, batch_size, k, N.ptr(losses) if sync else None, 0 if sync else N.NO_LOSS_READBACK))
+        self._alpha_is_float = False
+        if not sync:
+            return None
+        return [{"q1_loss": float(l[0]), "q2_loss": float(l[1]), "policy_loss": float(l[2])} for l in losses]
+
     def learner_step(self, batch_size=256, *, sync=False):
         """Throughput form of `update_parameters` over the prioritized buffer (per_weighted_loss mode), everything resident
         in HBM: update on the minibatch sampled by the previous call -> priorities <- |q1 - y| -> sample for the next call;
@@ -378,3 +392,130 @@ class SAC:
 
     def synchronize(self):
         N.check(N.lib().sacb_synchronize(self._h))
+
+
+class PopulationSAC:
+    """`n_agents` independent SAC agents (distinct seeds) trained by ONE batched update program per step on one GPU
+    (BASELINE.json configs[4]; the per-agent step is sac_imp.py:74-144).  Agent i = exactly what `torch.manual_seed(seeds[i]);
+    SAC(state_dim, action_dim, ...)` builds: same initialiser calls in the same order, its own Adam state, temperature, Philox stream
+    (stream id = agent index) and its own uniform replay ring of `capacity` transitions in HBM -- the agent index is a grid
+    dimension of every stage kernel and the 4th coordinate of the TMA descriptors.  No inter-agent (or inter-GPU) traffic:
+    `distributed.partition_agents` assigns global agent ids to ranks.  Minibatch positions are drawn on the device."""
+
+    def __init__(self, n_agents, state_dim, action_dim, hidden_dim=256, gamma=0.99, tau=0.005, lr=3e-4, alpha=0.2,
+                 automatic_entropy_tuning=True, device="cuda", *, seeds=None, capacity=100000, max_batch=256, math="bf16x3",
+                 launch="staged", seed=None, action_bounds=None):
+        if not str(device).startswith("cuda"):
+            raise RuntimeError("PopulationSAC runs on a B200 only (device='cuda[:i]'); there is no CPU path")
+        self.n_agents, self.device = int(n_agents), device
+        self.seeds = list(range(self.n_agents)) if seeds is None else [int(x) for x in seeds]
+        if len(self.seeds) != self.n_agents:
+            raise ValueError("one seed per agent")
+        kw = {} if action_bounds is None else {"action_bounds": action_bounds}
+        probe = GaussianPolicy(state_dim, action_dim, hidden_dim, **kw)
+        cfg = N.default_config()
+        cfg.obs_dim, cfg.act_dim, cfg.hidden_dim, cfg.n_hidden = state_dim, action_dim, hidden_dim, getattr(probe, "N_HIDDEN", 2)
+        cfg.gamma, cfg.tau, cfg.lr, cfg.alpha0, cfg.auto_entropy = gamma, tau, lr, alpha, int(bool(automatic_entropy_tuning))
+        cfg.action_scale, cfg.action_bias = probe.action_scale, probe.action_bias
+        cfg.replay_kind, cfg.capacity, cfg.max_batch, cfg.n_agents = N.REPLAY_UNIFORM, capacity, max_batch, self.n_agents
+        cfg.device = torch.device(device).index or 0
+        cfg.math_mode = {"fp32": N.MATH_FP32, "bf16x3": N.MATH_BF16X3}[math]
+        cfg.launch_mode = {"staged": N.LAUNCH_STAGED, "persistent": N.LAUNCH_PERSISTENT}[launch]
+        cfg.seed = random.getrandbits(63) if seed is None else int(seed)
+        self._cfg = cfg
+        self._h = N.create(cfg)
+        self._names = {}
+        lib = N.lib()
+        for i, sd in enumerate(self.seeds):
+            torch.manual_seed(sd)                      # the construction order of sac_imp.py:28-36 under this agent's seed
+            pol = GaussianPolicy(state_dim, action_dim, hidden_dim, **kw)
+            q1, q2 = QNetwork(state_dim, action_dim, hidden_dim), QNetwork(state_dim, action_dim, hidden_dim)
+            QNetwork(state_dim, action_dim, hidden_dim); QNetwork(state_dim, action_dim, hidden_dim)     # the targets' own (discarded) init draws
+            for net_id, mod in ((N.NET_POLICY, pol), (N.NET_Q1, q1), (N.NET_Q2, q2), (N.NET_Q1_TARGET, q1), (N.NET_Q2_TARGET, q2)):
+                self._names[net_id] = [(n, tuple(p.shape)) for n, p in mod.named_parameters()]
+                for t, (_, p) in enumerate(mod.named_parameters()):
+                    host = N.f32(p.detach().numpy())
+                    N.check(lib.sacb_import_tensor(self._h, i, net_id, N.SLOT_PARAM, t, N.ptr(host), host.size))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None:
+            try:
+                N.lib().sacb_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    def __len__(self):
+        return self.n_agents
+
+    # ---- replay (per-agent uniform ring, replay_buffer.py:5-22) -------------------------------------------------------
+    def push(self, agent, state, action, reward, next_state, done):
+        self.push_many(agent, N.f32(state)[None], N.f32(action)[None], [reward], N.f32(next_state)[None], [done])
+
+    def push_many(self, agent, states, actions, rewards, next_states, dones):
+        s, a, s2 = N.f32(states), N.f32(actions), N.f32(next_states)
+        r, d = N.f32(rewards).ravel(), N.f32(dones).ravel()
+        N.check(N.lib().sacb_push(self._h, int(agent), N.ptr(s), N.ptr(a), N.ptr(r), N.ptr(s2), N.ptr(d), s.shape[0]))
+
+    def buffer_len(self, agent):
+        return int(N.lib().sacb_len(self._h, int(agent)))
+
+    # ---- acting / learning ------------------------------------------------------------------------------------------------
+    def select_action(self, states, evaluate=False, *, eps=None):
+        """states [n_agents, obs] -> actions [n_agents, act]: agent i acts on row i with its own policy (sac_imp.py:54-72 each)."""
+        obs = N.f32(states).reshape(self.n_agents, self._cfg.obs_dim)
+        out = np.empty((self.n_agents, self._cfg.act_dim), np.float32)
+        e = None if eps is None else N.f32(eps).reshape(self.n_agents, self._cfg.act_dim)
+        N.check(N.lib().sacb_select_action_batch(self._h, N.ptr(obs), int(bool(evaluate)), N.ptr(e), N.ptr(out)))
+        return out
+
+    def update_parameters(self, batch_size=256, *, idx=None, eps=None, sync=True):
+        """One update of EVERY agent (sac_imp.py:74-144 each) in one program.  idx [n_agents, B] positions / eps = (eps_next,
+        eps_cur) [n_agents, B, act] are test hooks; by default both are drawn on the device.  Returns a list of loss dicts."""
+        lib = N.lib()
+        e_next = e_cur = None
+        if eps is not None:
+            e_next, e_cur = N.f32(eps[0]), N.f32(eps[1])
+        if idx is not None:
+            ix = np.ascontiguousarray(idx, np.int64).reshape(self.n_agents, batch_size)
+            N.check(lib.sacb_update(self._h, batch_size, N.ptr(ix, ctypes.c_int64), N.ptr(e_next), N.ptr(e_cur), None, N.NO_LOSS_READBACK))
+        else:
+            N.check(lib.sacb_update(self._h, batch_size, None, N.ptr(e_next), N.ptr(e_cur), None, N.NO_LOSS_READBACK | N.DEVICE_INDICES))
+        if not sync:
+            return None
+        losses = np.zeros((self.n_agents, 3), np.float32)
+        N.check(lib.sacb_get_losses_all(self._h, N.ptr(losses)))
+        return [{"q1_loss": float(l[0]), "q2_loss": float(l[1]), "policy_loss": float(l[2])} for l in losses]
+
+    def synchronize(self):
+        N.check(N.lib().sacb_synchronize(self._h))
+
+    # ---- per-agent state in the reference's save() layout (sac_imp.py:154-162) ---------------------------------------
+    def agent_state(self, agent):
+        lib, out = N.lib(), {}
+        for net_id, name in enumerate(_NETS):
+            sd = {}
+            for t, (pname, shape) in enumerate(self._names[net_id]):
+                host = np.empty(shape, np.float32)
+                N.check(lib.sacb_export_tensor(self._h, int(agent), net_id, N.SLOT_PARAM, t, N.ptr(host), host.size))
+                sd[pname] = torch.from_numpy(host)
+            out[f"{name}_state_dict"] = sd
+        sc = N.Scalars()
+        N.check(lib.sacb_get_scalars(self._h, int(agent), ctypes.byref(sc)))
+        out["alpha"] = float(sc.alpha) if sc.n_updates == 0 or not self._cfg.auto_entropy else torch.tensor([sc.alpha])
+        return out
+
+    def load_agent(self, agent, checkpoint):
+        """Inverse of `agent_state` (accepts a file written by the reference's or the product's `SAC.save`)."""
+        lib = N.lib()
+        for net_id, name in enumerate(_NETS):
+            sd = checkpoint[f"{name}_state_dict"]
+            for t, (pname, _) in enumerate(self._names[net_id]):
+                host = N.f32(torch.as_tensor(sd[pname]).detach().cpu().numpy())
+                N.check(lib.sacb_import_tensor(self._h, int(agent), net_id, N.SLOT_PARAM, t, N.ptr(host), host.size))
+        sc = N.Scalars()
+        N.check(lib.sacb_get_scalars(self._h, int(agent), ctypes.byref(sc)))
+        a = checkpoint["alpha"]
+        sc.alpha = float(a.detach().reshape(-1)[0]) if torch.is_tensor(a) else float(a)
+        N.check(lib.sacb_set_scalars(self._h, int(agent), ctypes.byref(sc)))

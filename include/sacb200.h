@@ -151,13 +151,20 @@ int sacb_per_set_frame(sacb_handle h, int agent, int64_t frame);
 enum {
     SACB_USE_LAST_SAMPLE = 1,  /* minibatch = rows chosen by the last sacb_per_sample / sacb_stage_indices */
     SACB_NO_LOSS_READBACK = 2, /* do not sync / copy the three loss scalars (throughput mode)                 */
-    SACB_EXPORT_GRADS = 4      /* keep the critic/policy gradients in the SACB_SLOT_GRAD arena (tests)        */
+    SACB_EXPORT_GRADS = 4,     /* keep the critic/policy gradients in the SACB_SLOT_GRAD arena (tests)        */
+    SACB_DEVICE_INDICES = 8    /* uniform ring: the B positions are drawn on the device inside the gather stage (keyed bijection of
+                                  [0, len): B distinct positions = sampling without replacement, replay_buffer.py:15); idx = NULL.
+                                  Nothing of the step touches the host: population mode, K updates per call (sacb_update_steps) */
 };
 /* idx: B logical indices (NULL => SACB_USE_LAST_SAMPLE, or the next index set pre-staged with sacb_stage_indices; otherwise SACB_ERR_ARG);
  * eps_next / eps_cur: [B, act] N(0,1) draws of the two policy.sample calls (sac_imp.py:89, :116), NULL => Philox;
  * losses_out[3] = q1_loss, q2_loss, policy_loss (sac_imp.py:140-144). */
 int sacb_update(sacb_handle h, int64_t B, const int64_t *idx, const float *eps_next, const float *eps_cur,
                 float *losses_out, uint32_t flags);
+/* K learner steps per call with nothing of a step on the host (trainer.py:190-205 batched): prioritized ring =
+ * K x the sacb_per_step pipeline, uniform ring = K updates with SACB_DEVICE_INDICES; eps drawn on the device; then ONE read-back:
+ * losses_out[K][3] (NULL or SACB_NO_LOSS_READBACK: none).  K <= 64.  Bitwise equal to K single calls. */
+int sacb_update_steps(sacb_handle h, int64_t B, int K, float *losses_out, uint32_t flags);
 /* update on a caller-supplied minibatch (no replay involved): test / bench entry. */
 int sacb_update_batch(sacb_handle h, int64_t B, const float *s, const float *a, const float *r, const float *s2,
                       const float *done, const float *is_weights_or_null, const float *eps_next,
@@ -165,6 +172,8 @@ int sacb_update_batch(sacb_handle h, int64_t B, const float *s, const float *a, 
 /* pre-stage indices for the next n_steps updates on the device (bench "inputs resident in HBM"). */
 int sacb_stage_indices(sacb_handle h, const int64_t *idx, int64_t B, int64_t n_steps);
 int sacb_get_losses(sacb_handle h, int agent, float *losses_out);
+/* population: losses_out[n_agents][3] of the last update of every agent, one strided device->host copy */
+int sacb_get_losses_all(sacb_handle h, float *losses_out);
 
 /* ---- SAC.select_action (sac_imp.py:54-72) -------------------------------------------------------------- */
 int sacb_select_action(sacb_handle h, int agent, const float *obs, int evaluate, const float *eps_or_null,
@@ -211,6 +220,8 @@ int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap);
  * 2: updated critic k on (s, a_new) (:117-118) ; 3: target critic k on (s2, a2) (:92-93).  The parity tests use the signs
  * (ReLU masks) to make the comparison with the oracle independent of pre-activations that round to either side of zero. */
 int sacb_debug_read_activation(sacb_handle h, int agent, int group, int k, int layer, int64_t B, float *out);
+/* test hook: physical ring slots of the minibatch rows of the LAST update (host-staged, pre-staged or device-drawn) */
+int sacb_debug_read_slots(sacb_handle h, int agent, int32_t *slots_out, int64_t B);
 /* standalone GEMM self-test of the TMA + tcgen05 tile against the FFMA tile and a host float64 product of the same
  * bf16-pair operands; returns max |diff| / max |ref|.  b_r0 = row/column offset of the B operand inside its matrix. */
 int sacb_selftest_gemm(int device, int M, int N, int K, int a_mn_major, int b_mn_major, int b_r0, float *rel_err_out);

@@ -151,3 +151,102 @@ def test_data_parallel_wrapper_world1_matches_plain_update(hw):
         for nm in w:
             assert np.mean(np.abs(w[nm] - m[nm]) > 0.02 * 3e-4) < 5e-3, (net, nm)
     assert dp_agent.policy_optimizer.state_dict()["state"][0]["step"] == 1
+
+
+def test_population_class_equals_seeded_single_agents(hw):
+    """PopulationSAC(seeds=[..]) agent i == `torch.manual_seed(seeds[i]); SAC(...)`: same initial weights (reference initialiser
+    calls in the order of sac_imp.py:28-36), and after two updates on the same rows / eps the same weights and losses, bitwise."""
+    hw.use_networks("model2")
+    obs, act, hid, B, seeds = 13, 5, 48, 24, [7, 3, 11]
+    pop = hw.PopulationSAC(len(seeds), obs, act, hidden_dim=hid, device="cuda", seeds=seeds, capacity=64, max_batch=B, seed=99)
+    singles = []
+    rng = np.random.RandomState(0)
+    data = []
+    for i, sd in enumerate(seeds):
+        torch.manual_seed(sd)
+        ag = hw.SAC(obs, act, hidden_dim=hid, device="cuda", capacity=64, max_batch=B, seed=99)
+        b = O.make_batch(obs, act, 40, seed=500 + i)
+        ag.replay_buffer.push_many(b["s"], b["a"], b["r"], b["s2"], b["d"])
+        pop.push_many(i, b["s"], b["a"], b["r"], b["s2"], b["d"])
+        singles.append(ag)
+        st = pop.agent_state(i)
+        for net in ("policy", "q1", "q2", "q1_target", "q2_target"):
+            for k, v in net_params(ag, net).items():
+                np.testing.assert_array_equal(st[f"{net}_state_dict"][k].numpy(), v, err_msg=f"initial weights agent {i} {net}.{k}")
+    assert pop.buffer_len(1) == 40
+    for step in range(2):
+        idx = np.stack([rng.permutation(40)[:B] for _ in seeds]).astype(np.int64)
+        e_next = rng.standard_normal((len(seeds), B, act)).astype(np.float32)
+        e_cur = rng.standard_normal((len(seeds), B, act)).astype(np.float32)
+        got = pop.update_parameters(B, idx=idx, eps=(e_next, e_cur))
+        for i, ag in enumerate(singles):
+            ref = ag.update_parameters(B, idx=idx[i], eps=(e_next[i], e_cur[i]))
+            assert got[i] == ref, (step, i, got[i], ref)
+    for i, ag in enumerate(singles):
+        st = pop.agent_state(i)
+        for net in ("policy", "q1", "q2", "q1_target", "q2_target"):
+            for k, v in net_params(ag, net).items():
+                np.testing.assert_array_equal(st[f"{net}_state_dict"][k].numpy(), v, err_msg=f"agent {i} {net}.{k}")
+        assert abs(float(st["alpha"]) - float(ag.alpha)) == 0.0
+    # production mode: positions and eps drawn on the device, every agent its own stream
+    out = pop.update_parameters(B)
+    assert len(out) == len(seeds) and all(np.isfinite(list(o.values())).all() for o in out)
+    assert out[0] != out[1]
+    acts = pop.select_action(rng.standard_normal((len(seeds), obs)), evaluate=True)
+    assert acts.shape == (len(seeds), act) and np.all(np.abs(acts) <= 0.4 + 1e-6)
+    hw.use_networks("model1")
+
+
+def test_device_index_draw_is_a_sample_without_replacement(hw):
+    """SACB_DEVICE_INDICES: the gather stage draws B DISTINCT ring positions per update (random.sample semantics,
+    replay_buffer.py:15), different every step, covering the ring uniformly; wrapped ring (head != 0) included."""
+    N = hw._native
+    lib = N.lib()
+    hw.use_networks("model1")
+    obs, act, B, cap = 6, 2, 64, 300
+    agent = hw.SAC(obs, act, hidden_dim=16, device="cuda", capacity=cap, max_batch=B, seed=5)
+    n = 420                                   # > capacity: the ring has wrapped
+    ids = np.arange(n, dtype=np.float32)
+    agent.replay_buffer.push_many(np.tile(ids[:, None], (1, obs)), np.zeros((n, act), np.float32), ids, np.tile(ids[:, None], (1, obs)), np.zeros(n))
+    counts = np.zeros(n)
+    seen = []
+    slots = np.empty(B, np.int32)
+    for step in range(200):
+        N.check(lib.sacb_update(agent._h, B, None, None, None, None, N.NO_LOSS_READBACK | N.DEVICE_INDICES))
+        N.check(lib.sacb_debug_read_slots(agent._h, 0, N.ptr(slots, ctypes.c_int32), B))
+        assert len(set(slots.tolist())) == B and slots.min() >= 0 and slots.max() < cap
+        seen.append(slots.copy())
+        counts[slots] += 1
+    assert not np.array_equal(seen[0], seen[1])
+    hit = counts[:cap]
+    assert hit.min() > 0 and abs(hit.mean() - 200 * B / cap) < 1e-9 and hit.std() < 3.5 * np.sqrt(200 * B / cap)      # ~Binomial spread
+    with pytest.raises(ValueError):
+        small = hw.SAC(obs, act, hidden_dim=16, device="cuda", capacity=cap, max_batch=B, seed=5)
+        small.replay_buffer.push_many(np.zeros((10, obs)), np.zeros((10, act)), np.zeros(10), np.zeros((10, obs)), np.zeros(10))
+        N.check(lib.sacb_update(small._h, B, None, None, None, None, N.NO_LOSS_READBACK | N.DEVICE_INDICES))
+
+
+@pytest.mark.parametrize("replay", ["uniform", "per"])
+def test_k_steps_per_call_equal_single_calls(hw, replay):
+    """learner_steps(k=K) (sacb_update_steps: K steps enqueued back to back, ONE loss read-back) == K single calls, bitwise."""
+    hw.use_networks("model1")
+    obs, act, B, K = 11, 3, 32, 6
+    agents = []
+    rng = np.random.RandomState(1)
+    b = O.make_batch(obs, act, 500, seed=77)
+    pri = (np.abs(rng.standard_normal(512)) + 1e-6).astype(np.float32)
+    for _ in range(2):
+        torch.manual_seed(3)
+        ag = hw.SAC(obs, act, hidden_dim=32, device="cuda", capacity=512, max_batch=B, seed=42, replay=replay, per_weighted_loss=(replay == "per"))
+        ag.replay_buffer.push_many(b["s"], b["a"], b["r"], b["s2"], b["d"])
+        if replay == "per":
+            ag.replay_buffer.set_priorities(pri)
+        agents.append(ag)
+    many = agents[0].learner_steps(B, k=K)
+    single = [agents[1].learner_steps(B, k=1)[0] for _ in range(K)]
+    assert many == single
+    for net in ("policy", "q1", "q2_target"):
+        for k, v in net_params(agents[0], net).items():
+            np.testing.assert_array_equal(v, net_params(agents[1], net)[k])
+    if replay == "per":
+        np.testing.assert_array_equal(agents[0].replay_buffer.priorities, agents[1].replay_buffer.priorities)
