@@ -112,6 +112,7 @@ SIGNATURES = {
     "sacb_debug_read_slots": (I, [H, I, ctypes.POINTER(ctypes.c_int32), I64]),
     "sacb_debug_read_activation": (I, [H, I, I, I, I, I64, c_f32p]),
     "sacb_selftest_gemm": (I, [I, I, I, I, I, I, I, c_f32p]),
+    "sacb_selftest_gemm_stream": (I, [I, I, I, I, I, I, I, I, I, c_f32p]),
     "sacb_selftest_gemm_tile": (I, [I, I, I, I, I, I, I, I, I, c_f32p]),
 }
 

@@ -111,7 +111,6 @@ struct AdamArgs {
     Ref gexp;           // gradient export (null unless SACB_EXPORT_GRADS / data-parallel mode)
     PmRef shadow;       // bf16 pair shadow of w refreshed in place (null: not needed before the next step)
     PmRef shadow2;      // second shadow holding only columns >= shadow2_col0 of w (the action block of a critic's fc1)
-    PmRef shadow_t;     // bf16 pair shadow of the Polyak target wt, refreshed in place (null: the shadow stage of the next step does it)
     int32_t shadow2_col0, pad0;
     int32_t step_slot;  // ScalarSlot of the optimizer step counter (value BEFORE this step's increment)
     int32_t apply;      // 0 = only export the gradient (data-parallel backward), 1 = apply Adam
@@ -152,20 +151,20 @@ constexpr uint32_t kPlainEpis = tb(EPI_F32) | tb(EPI_BIAS_RELU) | tb(EPI_MASK);
 constexpr uint32_t kElemTypes = tb(T_SHADOW) | tb(T_GATHER) | tb(T_SAMPLE) | tb(T_TARGET_LOSS) | tb(T_ACTOR_LOSS) | tb(T_SAMPLE_BWD) | tb(T_FINISH);
 #define SACB_KERNEL_VARIANTS(X)                                                                     \
     X(0, kAllTypes, kAllEpis)                                                                       \
-    X(1, tb(T_GEMM), tb(EPI_BIAS_RELU))                                                             \
+    X(1, tb(T_GEMM) | tb(T_SHADOW), tb(EPI_BIAS_RELU))                                                         \
     X(2, tb(T_GEMM), tb(EPI_MASK))                                                                  \
     X(3, tb(T_GEMM), tb(EPI_F32))                                                                   \
     X(4, tb(T_GEMM), kPlainEpis)                                                                    \
     X(5, tb(T_GEMM) | tb(T_OUT_ADAM), tb(EPI_MASK))                                                 \
-    X(6, tb(T_GEMM) | tb(T_BIAS_ADAM), tb(EPI_ADAM))                                                \
-    X(7, tb(T_GEMM) | tb(T_BIAS_ADAM), tb(EPI_ADAM) | tb(EPI_MASK))                                 \
+    X(6, tb(T_GEMM) | tb(T_BIAS_ADAM) | tb(T_SHADOW), tb(EPI_ADAM))                                 \
+    X(7, tb(T_GEMM) | tb(T_BIAS_ADAM) | tb(T_SHADOW), tb(EPI_ADAM) | tb(EPI_MASK))                               \
     X(8, tb(T_GEMM) | tb(T_BIAS_ADAM) | tb(T_OUT_ADAM), kPlainEpis | tb(EPI_ADAM))                  \
     X(9, tb(T_SHADOW) | tb(T_GATHER), 0u)                                                           \
     X(10, tb(T_SAMPLE), 0u)                                                                         \
     X(11, tb(T_TARGET_LOSS), 0u)                                                                    \
     X(12, tb(T_ACTOR_LOSS), 0u)                                                                     \
     X(13, tb(T_SAMPLE_BWD), 0u)                                                                     \
-    X(14, tb(T_FINISH), 0u)                                                                         \
+    X(14, tb(T_FINISH) | tb(T_SHADOW), 0u)                                                                    \
     X(15, kElemTypes, 0u)
 constexpr int kNumKernelVariants = 16;
 

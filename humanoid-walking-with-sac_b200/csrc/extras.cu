@@ -6,6 +6,7 @@
 
 #include "handle.h"
 #include "tasks.cuh"
+#include "stream.cuh"
 
 namespace sacb {
 
@@ -318,6 +319,81 @@ static uint16_t host_bf16_rn(float x) {
 }
 static float host_bf16_to_float(uint16_t b) { uint32_t u = (uint32_t)b << 16; float f; memcpy(&f, &u, 4); return f; }
 }  // namespace sacb
+
+namespace sacb {
+__global__ void __launch_bounds__(stream::kThreads, 1) stream_selftest_kernel(const __grid_constant__ Program P, const __grid_constant__ Stage stage) {
+    extern __shared__ __align__(1024) uint8_t smem_stream[];
+    if ((tc::smem_u32(smem_stream) & 1023u) != 0) { if (threadIdx.x == 0) atomicExch(P.error_flag, 3); return; }
+    stream::gemm_stage(P, stage, smem_stream, 0ull);
+}
+}  // namespace sacb
+
+/* the stream kernel's tile (128 rows x bn = 64 | 128 columns, decoupled producer / MMA / epilogue over a round-robin tile list, `ctas`
+ * resident CTAs) against the FFMA tile on the same bf16-pair operands */
+extern "C" int sacb_selftest_gemm_stream(int device, int M, int N, int K, int a_mn, int b_mn, int b_r0, int bn, int ctas, float *rel_err_out) {
+    if (M < 1 || N < 1 || K < 1 || b_r0 < 0 || (b_mn && b_r0 % 8) || !rel_err_out || (bn != 64 && bn != 128) || ctas < 1) return fail(SACB_ERR_ARG, "bad argument");
+    SACB_CUDA(cudaSetDevice(device));
+    const int NB = N + b_r0;
+    const int a_rows = a_mn ? K : M, a_cols = a_mn ? M : K, b_rows = b_mn ? K : NB, b_cols = b_mn ? NB : K;
+    const int lda = (int)align_up(a_cols, 8) + 8, ldb = (int)align_up(b_cols, 8) + 8;
+    const int64_t na = (int64_t)a_rows * lda, nb = (int64_t)b_rows * ldb, nc = (int64_t)M * N;
+    std::vector<uint16_t> pa(2 * na, 0), pb(2 * nb, 0);
+    std::vector<float> c0(nc), c1(nc);
+    uint32_t sd = 777u;
+    auto rnd = [&]() { sd = sd * 1664525u + 1013904223u; return ((sd >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
+    auto fill = [&](std::vector<uint16_t> &p, int rows, int ld, int64_t n) {
+        for (int r = 0; r < rows; r++)
+            for (int c = 0; c < ld; c++) {
+                const float x = rnd();
+                const uint16_t hi = host_bf16_rn(x), lo = host_bf16_rn(x - host_bf16_to_float(hi));
+                p[(int64_t)r * ld + c] = hi; p[n + (int64_t)r * ld + c] = lo;
+            }
+    };
+    fill(pa, a_rows, lda, na);
+    fill(pb, b_rows, ldb, nb);
+    const int64_t oa = 0, ob = align_up(na, 32), oc0 = ob + align_up(nb, 32), oc1 = oc0 + align_up(nc, 32), total = oc1 + align_up(nc, 32);
+    float *d; Task *d_tasks; int *flag;
+    SACB_CUDA(cudaMalloc(&d, sizeof(float) * total));
+    SACB_CUDA(cudaMemset(d, 0, sizeof(float) * total));
+    SACB_CUDA(cudaMalloc(&d_tasks, 2 * sizeof(Task)));
+    SACB_CUDA(cudaMalloc(&flag, 64)); SACB_CUDA(cudaMemset(flag, 0, 64));
+    SACB_CUDA(cudaMemcpy(d + oa, pa.data(), 2 * na * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    SACB_CUDA(cudaMemcpy(d + ob, pb.data(), 2 * nb * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    AgentBases bases{d, d, 0, 0};
+    Task tk[2];
+    for (int v = 0; v < 2; v++) {
+        Task &t = tk[v]; memset(&t, 0, sizeof(t));
+        t.bm = v ? stream::kBM : kSM; t.bn = v ? bn : kSN;
+        t.type = T_GEMM; t.M = M; t.N = N; t.K = K; t.epi = EPI_F32;
+        t.A.pm.base = make_ref(0, oa); t.A.pm.ld = lda; t.A.pm.plane = na; t.A.mn_major = a_mn; t.A.r0 = 0;
+        t.B.pm.base = make_ref(0, ob); t.B.pm.ld = ldb; t.B.pm.plane = nb; t.B.mn_major = b_mn; t.B.r0 = b_r0;
+        t.C = make_ref(0, v ? oc1 : oc0); t.ldc = N; t.bias = null_ref();
+        t.Cpm = t.mask = null_pm(); t.adam.shadow = t.adam.shadow2 = null_pm();
+        t.tiles_m = cdiv(M, t.bm); t.tiles_n = cdiv(N, t.bn); t.n_tiles = t.tiles_m * t.tiles_n;
+    }
+    int rc = make_pm_tensor_map(&tk[1].tmA, d + oa, a_cols, a_rows, lda, na, 0, 1, a_mn ? 64 : stream::kBM);
+    if (rc == SACB_OK) rc = make_pm_tensor_map(&tk[1].tmB, d + ob, b_cols, b_rows, ldb, nb, 0, 1, b_mn ? 64 : bn);
+    if (rc) { cudaFree(d); cudaFree(d_tasks); cudaFree(flag); return rc; }
+    SACB_CUDA(cudaMemcpy(d_tasks, tk, sizeof(tk), cudaMemcpyHostToDevice));
+    gemm_selftest_kernel<SACB_MATH_FP32><<<tk[0].n_tiles, kThreads, kSimtSmemBytes>>>(d_tasks, bases, flag);
+    Program P; memset(&P, 0, sizeof(P));
+    P.tasks = d_tasks; P.n_agents = 1; P.bases = bases; P.scalars = null_ref(); P.error_flag = flag;
+    Stage sg; memset(&sg, 0, sizeof(sg));
+    sg.task_begin = 1; sg.task_end = 2; sg.n_tiles = tk[1].n_tiles; sg.ksplit = 1;
+    SACB_CUDA(cudaFuncSetAttribute(stream_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stream::kSmemBytes));
+    stream_selftest_kernel<<<std::min(tk[1].n_tiles, ctas), stream::kThreads, stream::kSmemBytes>>>(P, sg);
+    SACB_CUDA(cudaDeviceSynchronize());
+    int hf = 0;
+    SACB_CUDA(cudaMemcpy(&hf, flag, sizeof(int), cudaMemcpyDeviceToHost));
+    SACB_CUDA(cudaMemcpy(c0.data(), d + oc0, sizeof(float) * nc, cudaMemcpyDeviceToHost));
+    SACB_CUDA(cudaMemcpy(c1.data(), d + oc1, sizeof(float) * nc, cudaMemcpyDeviceToHost));
+    cudaFree(d); cudaFree(d_tasks); cudaFree(flag);
+    if (hf) return fail(SACB_ERR_DEVICE, hf == 3 ? "stream kernel: dynamic shared memory is not 1024-byte aligned" : "tcgen05 / TMA pipeline watchdog fired in the stream self test");
+    double maxref = 0, maxdiff = 0;
+    for (int64_t i = 0; i < nc; i++) { maxref = std::max(maxref, (double)fabsf(c0[i])); maxdiff = std::max(maxdiff, (double)fabsf(c0[i] - c1[i])); }
+    *rel_err_out = (float)(maxdiff / std::max(maxref, 1e-30));
+    return SACB_OK;
+}
 
 extern "C" int sacb_selftest_gemm(int device, int M, int N, int K, int a_mn, int b_mn, int b_r0, float *rel_err_out) {
     return sacb_selftest_gemm_tile(device, M, N, K, a_mn, b_mn, b_r0, kTM, kTN, rel_err_out);

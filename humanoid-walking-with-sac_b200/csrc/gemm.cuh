@@ -57,7 +57,7 @@ struct EpiR {
     const float *bias;
     Pm mask;
     float *w, *m, *v, *wt, *gexp;
-    Pm shadow, shadow2, shadow_t;
+    Pm shadow, shadow2;
     int shadow2_col0;
     int apply;
     float step_size, bc2_sqrt, inv_bc2_sqrt, tau;
@@ -113,7 +113,6 @@ __device__ __forceinline__ void epilogue_element(const EpiR &e, int m, int n, fl
                                           e.apply, e.step_size, e.bc2_sqrt, e.tau);
             if (e.shadow.hi && e.apply) pm_store(e.shadow, m, n, w1);
             if (e.shadow2.hi && e.apply && n >= e.shadow2_col0) pm_store(e.shadow2, m, n - e.shadow2_col0, w1);
-            if (e.shadow_t.hi && e.apply && e.wt) pm_store(e.shadow_t, m, n, e.wt[o]);
         } break;
     }
 }
@@ -127,13 +126,12 @@ __device__ __forceinline__ EpiR resolve_epilogue(const Task &t, const AgentBases
     e.mask = resolve_pm(t.mask, b, agent);
     e.w = e.m = e.v = e.wt = e.gexp = nullptr; e.apply = 0; e.step_size = e.bc2_sqrt = e.inv_bc2_sqrt = 0.f; e.tau = 0.f;
     e.shadow.hi = nullptr; e.shadow.ld = 0; e.shadow.plane = 0;
-    e.shadow2 = e.shadow; e.shadow_t = e.shadow; e.shadow2_col0 = 0;
+    e.shadow2 = e.shadow; e.shadow2_col0 = 0;
     if (t.epi == EPI_ADAM) {
         e.w = resolve(t.adam.w, b, agent); e.m = resolve(t.adam.m, b, agent); e.v = resolve(t.adam.v, b, agent);
         e.wt = resolve(t.adam.wt, b, agent); e.gexp = resolve(t.adam.gexp, b, agent);
         e.shadow = resolve_pm(t.adam.shadow, b, agent);
         e.shadow2 = resolve_pm(t.adam.shadow2, b, agent); e.shadow2_col0 = t.adam.shadow2_col0;
-        e.shadow_t = resolve_pm(t.adam.shadow_t, b, agent);
         e.apply = t.adam.apply; e.tau = t.adam.tau;
         adam_factors_cached(scalars, t.adam.step_slot, e.step_size, e.bc2_sqrt);
         e.inv_bc2_sqrt = 1.0f / e.bc2_sqrt;
@@ -479,10 +477,8 @@ __device__ __forceinline__ AdamOut adam_math(const EpiR &e, float g, float w, fl
 //   pass B: the columns no aligned group covers (a0 leading ones, <= 3 trailing ones), one element per thread
 //   both passes leave the new weights in the staging tile; pass C writes the bf16 pair shadows from there with the
 //   tile-aligned mapping (the shadow rows are padded to 16 B)
-//   Ct (or null): second staging tile for the new TARGET weights (Polyak), whose shadow pass C refreshes as well
-__device__ __forceinline__ void adam_epilogue_tile(const EpiR &e, float *Cs, float *Ct, int m0, int n0, int row_lo, int row_hi) {
+__device__ __forceinline__ void adam_epilogue_tile(const EpiR &e, float *Cs, int m0, int n0, int row_lo, int row_hi) {
     const int tid = threadIdx.x;     // only rows [row_lo, row_hi) of the tile belong to this CTA (split-K cluster)
-    const bool stage_t = Ct != nullptr && e.shadow_t.hi != nullptr && e.wt != nullptr;
     const int ncols = min(kTN, e.N - n0);      // valid columns of this tile (> 0)
 #pragma unroll 1
     for (int half = 0; half < kAdamRowGroups; half++) {   // ---- pass A, kAdamRows rows of a thread at a time (register budget)
@@ -523,7 +519,6 @@ __device__ __forceinline__ void adam_epilogue_tile(const EpiR &e, float *Cs, flo
             *reinterpret_cast<float4 *>(e.w + o) = make_float4(a.w, b.w, cc.w, d.w);
             if (e.wt) *reinterpret_cast<float4 *>(e.wt + o) = make_float4(a.t, b.t, cc.t, d.t);
             cs[0] = a.w; cs[1] = b.w; cs[2] = cc.w; cs[3] = d.w;
-            if (stage_t) { float *ct = Ct + (32 * i + r0) * kCsLd + c[ii]; ct[0] = a.t; ct[1] = b.t; ct[2] = cc.t; ct[3] = d.t; }
         }
     }
     if (e.N % 4 != 0 || ncols < kTN) {   // ---- pass B (warp-uniform condition): thread (row = tid / 4, q = tid % 4)
@@ -557,12 +552,11 @@ __device__ __forceinline__ void adam_epilogue_tile(const EpiR &e, float *Cs, flo
                 e.m[o] = r.m; e.v[o] = r.v; e.w[o] = r.w;
                 if (e.wt) e.wt[o] = r.t;
                 *cs = r.w;
-                if (stage_t) Ct[row * kCsLd + col[u]] = r.t;
             }
         }
     }
-    if (!e.apply || (!e.shadow.hi && !e.shadow2.hi && !stage_t)) return;
-    __syncthreads();                     // ---- pass C: the staging tile(s) now hold the new weights (and new target weights)
+    if (!e.apply || (!e.shadow.hi && !e.shadow2.hi)) return;
+    __syncthreads();                     // ---- pass C: the staging tile now holds the new weights
     {
         const int c4 = (tid & 15) * 4, r0 = tid >> 4;
         if (c4 >= ncols) return;
@@ -574,11 +568,6 @@ __device__ __forceinline__ void adam_epilogue_tile(const EpiR &e, float *Cs, flo
             const float w1[4] = {v4.x, v4.y, v4.z, v4.w};
             const int n = n0 + c4;
             if (e.shadow.hi) store_pm4(e.shadow, m, n, e.N, w1);
-            if (stage_t) {
-                const float4 t4 = *reinterpret_cast<const float4 *>(Ct + (32 * i + r0) * kCsLd + c4);
-                const float t1[4] = {t4.x, t4.y, t4.z, t4.w};
-                store_pm4(e.shadow_t, m, n, e.N, t1);
-            }
             if (e.shadow2.hi && n + 3 >= e.shadow2_col0) {
                 if (n >= e.shadow2_col0 && ((n - e.shadow2_col0) & 3) == 0) {
                     store_pm4(e.shadow2, m, n - e.shadow2_col0, e.N - e.shadow2_col0, w1);
@@ -784,9 +773,7 @@ __device__ __forceinline__ void tc_epilogue(const EpiR &epi, int m0, int n0, int
         Cs -= row_lo * kCsLd;      // from here on Cs[row] addresses tile row `row` for row_lo <= row < row_hi
     }
     if (EPI == EPI_ADAM) {
-        // second staging tile (new target weights) = operand stage 1: every MMA of the tile has retired; not available to a
-        // split-K cluster, whose slots occupy the last stage (the builder gives such programs no target shadow)
-        adam_epilogue_tile(epi, Cs, ks == 1 ? reinterpret_cast<float *>(st.tiles + kTcStageBytes) : nullptr, m0, n0, row_lo, row_hi);
+        adam_epilogue_tile(epi, Cs, m0, n0, row_lo, row_hi);
     } else if (EPI == EPI_SAMPLE) {
         sample_epilogue_tile(*se, Cs, m0, bm, pre_eps, pre_b0, pre_b1);
     } else {   // phase 2: the staged accumulators of the thread's rows meet the prefetched auxiliary operands

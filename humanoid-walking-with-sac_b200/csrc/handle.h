@@ -84,6 +84,7 @@ struct ProgramInst {
     std::vector<Task> tasks;
     std::vector<Stage> stages;
     std::vector<int> stage_has_gemm;
+    std::vector<int> stage_stream;       // 1: the stage holds only GEMM tasks and runs on the stream kernel (throughput programs, stream.cuh)
     std::vector<int> stage_kind;         // kernel variant (SACB_KERNEL_VARIANTS) that runs the stage in staged mode
     Task *d_tasks = nullptr;
     Stage *d_stages = nullptr;

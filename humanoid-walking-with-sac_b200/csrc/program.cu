@@ -12,6 +12,7 @@
 
 #include "handle.h"
 #include "tasks.cuh"
+#include "stream.cuh"
 
 namespace sacb {
 
@@ -283,6 +284,17 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
     timeline(2, true);
 }
 
+// throughput form of a stage that holds only GEMM tasks (stream.cuh): one resident CTA per SM, roles decoupled across tiles
+__global__ void __launch_bounds__(stream::kThreads, 1)
+sac_stream_kernel(const __grid_constant__ Program P, const __grid_constant__ Stage stage, const uint64_t seed) {
+    extern __shared__ __align__(1024) uint8_t smem_stream[];
+    if ((tc::smem_u32(smem_stream) & 1023u) != 0) {      // SWIZZLE_128B operand tiles need 1024-byte alignment; the kernel owns all 227 KB
+        if (threadIdx.x == 0) atomicExch(P.error_flag, 3);
+        return;
+    }
+    stream::gemm_stage(P, stage, smem_stream, seed);
+}
+
 // ================================================================================================================
 // program builder
 // ================================================================================================================
@@ -346,7 +358,7 @@ struct Builder {
         t.C = t.bias = null_ref();
         t.Cpm = t.mask = t.A.pm = t.B.pm = null_pm();
         t.adam.w = t.adam.m = t.adam.v = t.adam.wt = t.adam.gexp = null_ref();
-        t.adam.shadow = t.adam.shadow2 = t.adam.shadow_t = null_pm();
+        t.adam.shadow = t.adam.shadow2 = null_pm();
         for (auto &p : t.p) p = null_ref();
         for (auto &p : t.pm) p = null_pm();
         return t;
@@ -393,9 +405,11 @@ struct Builder {
     // which optimizer a trainable net (0 policy, 1 q1, 2 q2) uses
     static int step_slot(int net) { return net == 0 ? SC_STEP_POLICY : (net == 1 ? SC_STEP_Q1 : SC_STEP_Q2); }
     bool apply() const { return key.dp_phase < 0; }
-    // every epilogue that changes a weight also refreshes its shadow (policy and targets included), so that the next step can run
-    // without the shadow stage; not in a split-K build (its staging leaves no room for the target tile)
-    bool keep_resident() const { return apply() && math_is_tc(h->cfg.math_mode) ? !getenv("SACB_SPLITK") : apply(); }
+    // A step that applies Adam leaves every shadow current, so that the next step runs without the shadow stage: the critics'
+    // shadows are refreshed by their Adam epilogues (the actor phase of the SAME step reads them), the Polyak targets' and the
+    // policy's by T_SHADOW tasks riding in later stages of the step that leave most SMs idle (actor-phase critic forward, policy
+    // backward, finish) -- in the epilogue the two extra planes cost 1.2-1.8 us per Adam stage, there they cost nothing.
+    bool keep_resident() const { return apply(); }
     bool exporting() const { return key.export_grads || key.dp_phase >= 0; }
 
     AdamArgs adam_args(int net, int64_t off_in_net) {
@@ -403,7 +417,7 @@ struct Builder {
         a.w = A(L.param[net] + off_in_net); a.m = A(L.adam_m[net] + off_in_net); a.v = A(L.adam_v[net] + off_in_net);
         a.wt = net == 0 ? null_ref() : A(L.param[net + 2] + off_in_net);     // q1 -> q1_target, q2 -> q2_target
         a.gexp = exporting() ? A(L.grad[net] + off_in_net) : null_ref();
-        a.shadow = a.shadow2 = a.shadow_t = null_pm(); a.shadow2_col0 = 0; a.pad0 = 0;
+        a.shadow = a.shadow2 = null_pm(); a.shadow2_col0 = 0; a.pad0 = 0;
         a.step_slot = step_slot(net); a.apply = apply() ? 1 : 0;
         a.lr = h->cfg.lr; a.tau = h->cfg.tau;
         return a;
@@ -413,9 +427,8 @@ struct Builder {
     Task epi_adam(int net, int layer) {
         const NetLayout &n = net == 0 ? L.pol : L.q;
         Task t = blank(T_GEMM); t.epi = EPI_ADAM; t.adam = adam_args(net, n.w[layer]);
-        if (net != 0 || keep_resident()) t.adam.shadow = wsh(net, layer).ref;
+        if (net != 0) t.adam.shadow = wsh(net, layer).ref;
         if (net != 0 && layer == 0) { t.adam.shadow2 = wsh_act(net).ref; t.adam.shadow2_col0 = L.obs; }
-        if (net != 0 && keep_resident()) t.adam.shadow_t = wsh(net + 2, layer).ref;      // Polyak target's shadow
         return t;
     }
 
@@ -479,6 +492,41 @@ struct Builder {
             for (const Cand &x : c) out[x.task] = {x.bm, x.bn};
         }
         return out;
+    }
+
+    // Throughput programs (stages with many more tiles than SMs): every GEMM task takes the stream kernel's tile, 128 rows x 128
+    // columns (64 where the output is narrower than 96 columns: policy heads, dL/da).
+    std::vector<std::pair<int, int>> stream_tile_shapes() const {
+        std::vector<std::pair<int, int>> out(tasks.size(), {0, 0});
+        for (size_t k = 0; k < tasks.size(); k++)
+            if (tasks[k].type == T_GEMM) out[k] = {stream::kBM, tasks[k].N >= 96 ? stream::kBN : 64};
+        return out;
+    }
+    // ... and a stage that mixes GEMM tasks with column-sum / element-wise tasks is cut in two (the tasks of a stage are independent
+    // of each other): first the non-GEMM tasks on the generic stage kernel, then the GEMM tasks on the stream kernel.
+    void split_mixed_stages(std::vector<int> &stage_stream) {
+        std::vector<Task> nt;
+        std::vector<Stage> ns;
+        std::vector<int> ng;
+        stage_stream.clear();
+        auto emit = [&](const std::vector<Task> &ts, bool gemm) {
+            Stage sg{};
+            sg.task_begin = (int)nt.size(); sg.n_tiles = 0; sg.ksplit = 1;
+            for (size_t i = 0; i < ts.size(); i++) {
+                Task t = ts[i];
+                sg.tile_begin[i] = sg.n_tiles; t.tile_begin = sg.n_tiles; sg.n_tiles += t.n_tiles;
+                nt.push_back(t);
+            }
+            sg.task_end = (int)nt.size();
+            ns.push_back(sg); ng.push_back(gemm ? 1 : 0); stage_stream.push_back(gemm ? 1 : 0);
+        };
+        for (size_t si = 0; si < stages.size(); si++) {
+            std::vector<Task> g, o;
+            for (int k = stages[si].task_begin; k < stages[si].task_end; k++) (tasks[k].type == T_GEMM ? g : o).push_back(tasks[k]);
+            if (!o.empty()) emit(o, false);
+            if (!g.empty()) emit(g, true);
+        }
+        tasks.swap(nt); stages.swap(ns); has_gemm.swap(ng);
     }
 
     void build() {
@@ -604,6 +652,8 @@ struct Builder {
                 for (int k = 0; k < 2; k++)
                     gemm(l == 0 ? X3(obs + act) : hview(L.ha[k][l - 1], B), 0, wsh(1 + k, l), 0, B, H, in_q,
                          epi_bias_relu(hview(L.ha[k][l], B), A(L.param[1 + k] + Q.b[l])));
+                if (critics && keep_resident())      // the Polyak targets moved in the critic backward: one layer's shadows per stage
+                    for (int k = 0; k < 2; k++) shadow_task(3 + k, Q.w[nh - 1 - l], wsh(3 + k, nh - 1 - l), Q.in_of(nh - 1 - l));
             }
             begin_stage();
             {
@@ -649,7 +699,6 @@ struct Builder {
                         gemm(hview(L.dhp[l], B), 0, wsh(0, l), 1, B, H, H, epi_mask(hview(L.dhp[l - 1], B), hp_cur(l - 1)));
                     if (s == 1) {              // heads: dW = g^T h_{nh-1}
                         Task t = blank(T_GEMM); t.epi = EPI_ADAM; t.adam = adam_args(0, P.w_out);
-                        if (keep_resident()) t.adam.shadow = wsh_head().ref;
                         gemm(ghead(B), 1, hp_cur(nh - 1), 1, A2, H, B, t);
                         bias_adam(0, P.b_out, ghead(B), B, A2);
                     } else {
@@ -660,6 +709,10 @@ struct Builder {
                     if (s == nh) {
                         gemm(hview(L.dhp[0], B), 1, X1(obs), 1, H, obs, B, epi_adam(0, 0));
                         bias_adam(0, P.b[0], hview(L.dhp[0], B), B, H);
+                    }
+                    if (keep_resident()) {      // shadow of what the PREVIOUS stage stepped: heads (s-1 = 1) or hidden layer nh-s+2
+                        if (s == 2) shadow_task(0, P.w_out, wsh_head(), H);
+                        else if (s > 2) shadow_task(0, P.w[nh - s + 2], wsh(0, nh - s + 2), P.in_of(nh - s + 2));
                     }
                 }
             }
@@ -676,6 +729,10 @@ struct Builder {
             t.i[5] = cdiv(B, kLossRows); t.i[6] = h->cfg.auto_entropy; t.i[7] = ap;
             t.f[0] = h->cfg.lr; t.f[1] = (float)B;
             add(t, 1);
+            if (actor && keep_resident()) {      // the last policy-backward stage stepped layers 1 and 0
+                shadow_task(0, P.w[1], wsh(0, 1), P.in_of(1));
+                shadow_task(0, P.w[0], wsh(0, 0), P.in_of(0));
+            }
         }
     }
 
@@ -705,7 +762,23 @@ int check_error_flag(sacb_handle h) {
 }
 
 // one stage = one launch (staged mode): grid = tiles x ksplit, thread-block cluster of ksplit CTAs along x, optional PDL
+static int launch_stream_stage(sacb_handle h, ProgramInst &p, int s, bool pdl) {
+    uint64_t seed = h->cfg.seed;
+    Stage single = p.stages[s];
+    void *args[] = {(void *)&p.prog, (void *)&single, (void *)&seed};
+    cudaLaunchConfig_t cfg{};
+    const int tiles = std::max(1, single.n_tiles * h->cfg.n_agents);
+    cfg.gridDim = dim3(std::min(tiles, h->sm_count)); cfg.blockDim = dim3(stream::kThreads); cfg.dynamicSmemBytes = stream::kSmemBytes; cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    SACB_CUDA(cudaLaunchKernelExC(&cfg, (const void *)sac_stream_kernel, args));
+    return SACB_OK;
+}
+
 static int launch_stage(sacb_handle h, ProgramInst &p, int s, bool pdl) {
+    if (p.stage_stream[s]) return launch_stream_stage(h, p, s, pdl);
     const bool tc = math_is_tc(h->cfg.math_mode);
     const int kind = p.stage_kind[s];      // index of the kernel variant
     const size_t smem = variant_has_gemm(kind) ? math_smem(h->cfg.math_mode) : 0;      // element-wise stages only use static shared memory
@@ -778,17 +851,25 @@ int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out) {
     if (it != h->programs.end()) { *out = &it->second; return SACB_OK; }
     if (key.B < 1 || key.B > h->cfg.max_batch) return fail(SACB_ERR_ARG, "batch size exceeds max_batch of the handle");
     std::vector<std::pair<int, int>> shapes;
+    bool stream_mode = false;
     {   // dry pass with the default 128 x 64 tiles: the per-stage tile counts drive the choice of tile shapes
         Builder d(h, key);
         d.dry = true;
         d.build();
         if (d.rc != SACB_OK) return d.rc;
-        shapes = d.choose_tile_shapes(h->sm_count);
+        int widest = 0;
+        for (size_t s = 0; s < d.stages.size(); s++) if (d.has_gemm[s]) widest = std::max(widest, d.stages[s].n_tiles * h->cfg.n_agents);
+        // throughput form: the widest GEMM stage has more than two waves of tiles (population of agents, large batches)
+        stream_mode = math_is_tc(h->cfg.math_mode) && h->cfg.launch_mode == SACB_LAUNCH_STAGED && widest > 2 * h->sm_count &&
+                      !getenv("SACB_NO_STREAM") && !getenv("SACB_FUSE_SAMPLE") && !getenv("SACB_SPLITK");
+        shapes = stream_mode ? d.stream_tile_shapes() : d.choose_tile_shapes(h->sm_count);
     }
     Builder b(h, key);
     b.shapes = shapes;
     b.build();
     if (b.rc != SACB_OK) return b.rc;
+    std::vector<int> stage_stream;
+    if (stream_mode) b.split_mixed_stages(stage_stream);
     // split-K (opt-in, SACB_SPLITK=1): a latency-bound stage with few tiles spreads every tile over a 2- or 4-CTA cluster so
     // that more SMs pull operands (per-SM L2->SMEM ingest bounds the main loop); staged tensor-core launches only.
     // Measured on B200 (profiles/r01_summary.md): the accumulator is ready 1.6 us (x2) / 2.8 us (x4) earlier, but pushing the
@@ -806,6 +887,7 @@ int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out) {
     }
     ProgramInst &p = h->programs[key];
     p.tasks = b.tasks; p.stages = b.stages; p.stage_has_gemm = b.has_gemm;
+    p.stage_stream = stage_stream.empty() ? std::vector<int>(b.stages.size(), 0) : stage_stream;
     for (size_t s = 0; s < b.stages.size(); s++) {      // the smallest build of the stage kernel that covers the stage
         uint32_t types = 0, epis = 0;
         for (int k = b.stages[s].task_begin; k < b.stages[s].task_end; k++) {
@@ -860,7 +942,7 @@ ProgramKey update_key(sacb_handle h, int B, int with_gather, int export_grads, i
 }
 void after_update_launch(sacb_handle h, const ProgramKey &key) {
     // a full update (Adam applied) leaves every shadow current: its epilogues refreshed what they changed
-    if (key.dp_phase < 0) h->shadows_valid = !(math_is_tc(h->cfg.math_mode) && getenv("SACB_SPLITK"));
+    if (key.dp_phase < 0) h->shadows_valid = true;
 }
 
 int launch_program(sacb_handle h, ProgramInst &p) {
@@ -1092,6 +1174,7 @@ int init_kernel_attributes(sacb_handle h) {
     for (int v = 0; v < kNumKernelVariants; v++)
         if (variant_has_gemm(v))
             SACB_CUDA(cudaFuncSetAttribute(update_kernel_for(m, v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)math_smem(m)));
+    SACB_CUDA(cudaFuncSetAttribute((const void *)sac_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stream::kSmemBytes));
     int nb = 0;
     SACB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, update_kernel_for(m, 0), kThreads, math_smem(m)));
     h->coop_blocks_per_sm = std::max(1, std::min(nb, math_is_tc(m) ? 2 : 4));

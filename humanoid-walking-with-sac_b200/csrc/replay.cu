@@ -825,8 +825,9 @@ static int gather_to_host(sacb_handle h, int agent, const int32_t *slots_host, i
     const float *ring = h->ring + (int64_t)agent * c.capacity * row;
     // host-facing reads (`.buffer`, checkpoints, ReplayBuffer.sample of any size) move stage_rows_cap rows per round trip
     if (!h->gather_slots && cudaMalloc(&h->gather_slots, sizeof(int32_t) * h->stage_rows_cap) != cudaSuccess) return fail(SACB_ERR_NOMEM, "device allocation failed");
-    int32_t *slots_dev = h->gather_slots;
-    const int64_t chunk = h->stage_rows_cap;
+    // slots_host == null: the slots of the last prioritized sample, already on the device (at most max_batch of them)
+    int32_t *slots_dev = slots_host ? h->gather_slots : h->slots + (int64_t)agent * c.max_batch;
+    const int64_t chunk = slots_host ? h->stage_rows_cap : std::max<int64_t>(n, 1);
     for (int64_t off = 0; off < n; off += chunk) {
         const int64_t m = std::min<int64_t>(chunk, n - off);
         if (slots_host) SACB_CUDA(cudaMemcpyAsync(slots_dev, slots_host + off, sizeof(int32_t) * m, cudaMemcpyHostToDevice, h->stream));

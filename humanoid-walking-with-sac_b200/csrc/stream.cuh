@@ -1,0 +1,367 @@
+// Throughput form of a GEMM stage (population of agents, large-batch data parallel): stages whose tiles outnumber the SMs.
+//
+// One resident CTA per SM walks its share of the stage's output tiles with the three roles decoupled, so that operand ingest,
+// tensor-core issue and the epilogue of consecutive tiles overlap (in the latency form -- gemm.cuh, one tile per CTA -- they run
+// one after the other, which is right when a stage has at most one tile per SM):
+//   warp 0        TMA producer : runs ahead across tile boundaries, bounded only by the 3 x 64 KB operand ring
+//   warp 1        MMA issuer   : tcgen05.mma (bf16x3) into one of TWO 128-column TMEM accumulators
+//   warp 2        TMEM allocation / release
+//   warps 4..11   epilogue     : tcgen05.ld -> staging tile -> coalesced fused epilogue of tile i while tile i+1 is accumulated
+// Output tile 128 x 128 (128 x 64 where N < 96): per 64-deep K block a CTA pulls 64 KB for 2.1 MFLOP of products -- 1.5x the
+// operand reuse of the 128 x 64 latency tile (32.8 instead of 21.8 FLOP per operand byte) against the chip-wide L2 -> SMEM limit.
+// Tiles are assigned round-robin (tile = blockIdx.x + i * gridDim.x): every role derives the same sequence on its own.
+// Same arithmetic per output element as the latency form (same K order, same three products), so results are bit-identical.
+#pragma once
+#include "gemm.cuh"
+
+namespace sacb {
+namespace stream {
+
+constexpr int kThreads = 384;                 // 12 warps
+constexpr int kEpiWarp0 = 4, kEpiThreads = 256;
+constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 3;
+constexpr int kABytes = kBM * kBK * 2 * 2;    // hi + lo planes: 32 KB
+constexpr int kBBytes = kBN * kBK * 2 * 2;    // 32 KB
+constexpr int kStageBytes = kABytes + kBBytes;
+constexpr int kRingBytes = kStages * kStageBytes;                 // 192 KB
+constexpr int kStagingBytes = kBM * tc::kCsLd * 4;                // 128 x 68 floats = 34 KB: 64 columns of the tile at a time
+constexpr int kMiscBytes = 1024;                                  // barriers, TMEM base, stage table
+constexpr int kSmemBytes = kRingBytes + kStagingBytes + kMiscBytes;   // 232448 = the 227 KB a CTA can have: no static shared memory
+constexpr int kAccCols = 128, kTmemCols = 2 * kAccCols;
+
+struct Misc {                 // lives behind the staging tile
+    uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+    int32_t n_tiles, n_tasks, task_begin;
+    int32_t tile_begin[kMaxStageTasks];
+};
+static_assert(sizeof(Misc) <= kMiscBytes, "misc block");
+
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory"); }
+
+__device__ __forceinline__ void tmem_alloc_cols(uint32_t *dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(bar)) : "memory");
+}
+
+// the tile a work item denotes; every role calls this with the same arguments
+struct TileRef { const Task *tg; int agent, m0, n0, bm, bn; };
+__device__ __forceinline__ TileRef locate(const Program &P, const Misc &mi, int wi) {
+    TileRef r;
+    r.agent = wi / mi.n_tiles;
+    const int tis = wi % mi.n_tiles;
+    int k = 0;
+    while (k + 1 < mi.n_tasks && tis >= mi.tile_begin[k + 1]) k++;
+    r.tg = &P.tasks[mi.task_begin + k];
+    const int tile = tis - mi.tile_begin[k];
+    r.bm = r.tg->bm; r.bn = r.tg->bn;
+    const int tn = r.tg->tiles_n;
+    r.m0 = (tile / tn) * r.bm; r.n0 = (tile % tn) * r.bn;
+    return r;
+}
+
+// ---- Adam (+ Polyak, + critic shadow refresh) on 64 columns of the tile held in the staging tile, 256 epilogue threads.
+// Same passes as tc::adam_epilogue_tile (aligned 128-bit groups per row, stragglers, shadows from the staged new weights).
+__device__ __forceinline__ void adam_epilogue(const EpiR &e, float *Cs, int m0, int n0, int et) {
+    const int ncols = min(64, e.N - n0);
+    if (ncols <= 0) return;      // uniform over the epilogue threads
+    const int j16 = et & 15, r0 = et >> 4;      // 16 threads per row, rows r0 + 16 i
+#pragma unroll 1
+    for (int grp = 0; grp < 4; grp++) {         // pass A, two rows of a thread at a time
+        int mrow[2], c[2];
+        bool vec[2];
+        float4 w[2], mm[2], vv[2], wt[2];
+#pragma unroll
+        for (int ii = 0; ii < 2; ii++) {
+            const int row = r0 + 16 * (2 * grp + ii);
+            mrow[ii] = m0 + row;
+            const int a0 = (4 - (int)(((int64_t)mrow[ii] * e.N + n0) & 3)) & 3;
+            c[ii] = a0 + 4 * j16;
+            vec[ii] = mrow[ii] < e.M && c[ii] + 3 < ncols;
+            w[ii] = mm[ii] = vv[ii] = wt[ii] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (vec[ii] && e.apply) {
+                const int64_t o = (int64_t)mrow[ii] * e.N + n0 + c[ii];
+                w[ii] = __ldcg(reinterpret_cast<const float4 *>(e.w + o));
+                mm[ii] = __ldcg(reinterpret_cast<const float4 *>(e.m + o));
+                vv[ii] = __ldcg(reinterpret_cast<const float4 *>(e.v + o));
+                if (e.wt) wt[ii] = __ldcg(reinterpret_cast<const float4 *>(e.wt + o));
+            }
+        }
+#pragma unroll
+        for (int ii = 0; ii < 2; ii++) {
+            if (!vec[ii]) continue;
+            const int row = r0 + 16 * (2 * grp + ii);
+            float *cs = Cs + row * tc::kCsLd + c[ii];
+            const int64_t o = (int64_t)mrow[ii] * e.N + n0 + c[ii];
+            const float g[4] = {cs[0], cs[1], cs[2], cs[3]};
+            if (e.gexp) *reinterpret_cast<float4 *>(e.gexp + o) = make_float4(g[0], g[1], g[2], g[3]);
+            if (!e.apply) continue;
+            const tc::AdamOut a = tc::adam_math(e, g[0], w[ii].x, mm[ii].x, vv[ii].x, wt[ii].x), b = tc::adam_math(e, g[1], w[ii].y, mm[ii].y, vv[ii].y, wt[ii].y);
+            const tc::AdamOut cc = tc::adam_math(e, g[2], w[ii].z, mm[ii].z, vv[ii].z, wt[ii].z), d = tc::adam_math(e, g[3], w[ii].w, mm[ii].w, vv[ii].w, wt[ii].w);
+            *reinterpret_cast<float4 *>(e.m + o) = make_float4(a.m, b.m, cc.m, d.m);
+            *reinterpret_cast<float4 *>(e.v + o) = make_float4(a.v, b.v, cc.v, d.v);
+            *reinterpret_cast<float4 *>(e.w + o) = make_float4(a.w, b.w, cc.w, d.w);
+            if (e.wt) *reinterpret_cast<float4 *>(e.wt + o) = make_float4(a.t, b.t, cc.t, d.t);
+            cs[0] = a.w; cs[1] = b.w; cs[2] = cc.w; cs[3] = d.w;
+        }
+    }
+    if (e.N % 4 != 0 || ncols < 64) {           // pass B: the columns no aligned group covers; thread (row = et / 4 (+ 64), q = et % 4)
+#pragma unroll 1
+        for (int hb = 0; hb < 2; hb++) {
+            const int row = (et >> 2) + 64 * hb, q = et & 3, m = m0 + row;
+            if (m >= e.M) continue;
+            const int a0 = (4 - (int)(((int64_t)m * e.N + n0) & 3)) & 3;
+            const int nv = ncols > a0 ? (ncols - a0) >> 2 : 0, tail0 = a0 + 4 * nv;
+            int col[2];
+            int cnt = 0;
+            if (q < min(a0, ncols)) col[cnt++] = q;
+            if (tail0 + q < ncols) col[cnt++] = tail0 + q;
+            for (int u = 0; u < cnt; u++) {
+                const int64_t o = (int64_t)m * e.N + n0 + col[u];
+                float *cs = Cs + row * tc::kCsLd + col[u];
+                const float g = *cs;
+                if (e.gexp) e.gexp[o] = g;
+                if (!e.apply) continue;
+                const tc::AdamOut r = tc::adam_math(e, g, __ldcg(e.w + o), __ldcg(e.m + o), __ldcg(e.v + o), e.wt ? __ldcg(e.wt + o) : 0.f);
+                e.m[o] = r.m; e.v[o] = r.v; e.w[o] = r.w;
+                if (e.wt) e.wt[o] = r.t;
+                *cs = r.w;
+            }
+        }
+    }
+    if (!e.apply || (!e.shadow.hi && !e.shadow2.hi)) return;
+    epi_bar();                                  // pass C: the staging tile holds the new weights
+    const int c4 = j16 * 4;
+    if (c4 >= ncols) return;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const int row = r0 + 16 * i, m = m0 + row;
+        if (m >= e.M) continue;
+        const float4 v4 = *reinterpret_cast<const float4 *>(Cs + row * tc::kCsLd + c4);
+        const float w1[4] = {v4.x, v4.y, v4.z, v4.w};
+        const int n = n0 + c4;
+        if (e.shadow.hi) tc::store_pm4(e.shadow, m, n, e.N, w1);
+        if (e.shadow2.hi && n + 3 >= e.shadow2_col0) {
+            if (n >= e.shadow2_col0 && ((n - e.shadow2_col0) & 3) == 0) {
+                tc::store_pm4(e.shadow2, m, n - e.shadow2_col0, e.N - e.shadow2_col0, w1);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    if (n + j >= e.shadow2_col0 && n + j < e.N) pm_store(e.shadow2, m, n + j - e.shadow2_col0, w1[j]);
+            }
+        }
+    }
+}
+
+// L2 prefetch of the optimizer state an Adam tile will stream (w, m, v, target: 4 x bm x bn floats), issued by the epilogue
+// warps while the tile is still being accumulated: the epilogue then finds its operands in L2 instead of paying DRAM latency
+// in every one of its load phases
+__device__ __forceinline__ void adam_prefetch(const EpiR &e, int m0, int n0, int bn, int et) {
+    if (!e.apply) return;
+    const int lines_per_row = (bn * 4 + 127) / 128 + 1;      // rows start at any 4-byte phase
+    for (int i = et; i < kBM * lines_per_row; i += kEpiThreads) {
+        const int row = i / lines_per_row, l = i % lines_per_row, m = m0 + row;
+        if (m >= e.M) continue;
+        const int64_t o = (int64_t)m * e.N + n0 + l * 32;
+        if (n0 + l * 32 >= e.N + 32) continue;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(e.w + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(e.m + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(e.v + o));
+        if (e.wt) asm volatile("prefetch.global.L2 [%0];" ::"l"(e.wt + o));
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void plain_epilogue(const EpiR &epi, const float *Cs, int m0, int n0c, int et, const float (&aux)[8][4]) {
+    const int c4 = (et & 15) * 4, r0 = et >> 4;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        int m[4];
+        float4 acc[4];
+        float ax[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int row = r0 + 16 * (4 * half + i);
+            m[i] = m0 + row;
+            acc[i] = *reinterpret_cast<const float4 *>(Cs + row * tc::kCsLd + c4);
+#pragma unroll
+            for (int j = 0; j < 4; j++) ax[i][j] = aux[4 * half + i][j];
+        }
+        tc::epilogue_rows4<EPI, 4>(epi, m, n0c + c4, acc, ax);
+    }
+}
+
+template <int EPI>
+__device__ __forceinline__ void plain_aux(const EpiR &epi, int m0, int n0c, int et, float (&aux)[8][4]) {
+    const int c4 = (et & 15) * 4, r0 = et >> 4;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        int m[4];
+        float ax[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) m[i] = m0 + r0 + 16 * (4 * half + i);
+        tc::epilogue_aux4<EPI, 4>(epi, m, n0c + c4, ax);
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) aux[4 * half + i][j] = ax[i][j];
+    }
+}
+
+// epilogue of one tile: per 64-column pass TMEM -> staging tile (phase 1), fused epilogue from the staging tile (phase 2).
+// The first pass's bias / mask operands and the L2 prefetch of the Adam state are issued BEFORE the wait on the accumulator.
+template <int EPI>
+__device__ __forceinline__ void epilogue_tile(const EpiR &epi, float *Cs, uint32_t acc_addr, const TileRef &r, int et, uint64_t *acc_full, uint32_t parity,
+                                              uint64_t *acc_empty, int *err) {
+    const int ew = et >> 5, lane = et & 31, q = ew & 3, hcol = (ew >> 2) * 32;
+    const int passes = r.bn > 64 ? 2 : 1;
+    float aux[8][4];
+    if (EPI == EPI_ADAM) adam_prefetch(epi, r.m0, r.n0, r.bn, et);
+    else plain_aux<EPI>(epi, r.m0, r.n0, et, aux);
+    tc::mbar_wait(acc_full, parity, err);
+    tc::tc_fence_after();
+    for (int pass = 0; pass < passes; pass++) {
+        const bool last = pass == passes - 1;
+        const int n0c = r.n0 + 64 * pass;
+        if (n0c >= epi.N) {      // ragged N: nothing to store from this pass, but the accumulator still has to be released
+            if (last) { tc::tc_fence_before(); if (lane == 0) mbar_arrive(acc_empty); }
+            continue;
+        }
+        if (EPI != EPI_ADAM && pass > 0) plain_aux<EPI>(epi, r.m0, n0c, et, aux);
+        {
+            float v[16];
+            float4 *dst = reinterpret_cast<float4 *>(Cs + (q * 32 + lane) * tc::kCsLd + hcol);
+            const uint32_t taddr = acc_addr + ((uint32_t)(q * 32) << 16) + (uint32_t)(64 * pass + hcol);
+            tc::tmem_ld16(taddr, v);
+#pragma unroll
+            for (int j = 0; j < 4; j++) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            tc::tmem_ld16(taddr + 16, v);
+#pragma unroll
+            for (int j = 0; j < 4; j++) dst[4 + j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        if (last) {      // every TMEM read of this warp has retired (tcgen05.wait::ld inside tmem_ld16): the accumulator may be reused
+            tc::tc_fence_before();
+            if (lane == 0) mbar_arrive(acc_empty);
+        }
+        epi_bar();
+        if (EPI == EPI_ADAM) adam_epilogue(epi, Cs, r.m0, n0c, et);
+        else plain_epilogue<EPI>(epi, Cs, r.m0, n0c, et, aux);
+        epi_bar();        // the staging tile is free for the next pass / tile
+    }
+}
+
+// the kernel body; P.tasks of the stage are all T_GEMM with bm = 128 and bn in {64, 128}
+__device__ __forceinline__ void gemm_stage(const Program &P, const Stage &stage, uint8_t *smem, uint64_t seed) {
+    uint8_t *ring = smem;                                              // 1024-aligned (checked by the caller)
+    float *Cs = reinterpret_cast<float *>(smem + kRingBytes);
+    Misc &mi = *reinterpret_cast<Misc *>(smem + kRingBytes + kStagingBytes);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 32) {
+        for (int i = 0; i < kStages; i++) { tc::mbar_init(&mi.full[i], 1); tc::mbar_init(&mi.empty[i], 1); }
+        for (int i = 0; i < 2; i++) { tc::mbar_init(&mi.acc_full[i], 1); tc::mbar_init(&mi.acc_empty[i], kEpiThreads / 32); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc_cols(&mi.tmem_base, kTmemCols);
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + kMaxStageTasks) mi.tile_begin[threadIdx.x - 64] = stage.tile_begin[threadIdx.x - 64];
+    if (threadIdx.x == 96) { mi.n_tiles = stage.n_tiles; mi.n_tasks = stage.task_end - stage.task_begin; mi.task_begin = stage.task_begin; }
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    const uint32_t tmem = mi.tmem_base;
+    const int total = mi.n_tiles * P.n_agents;
+    int *err = P.error_flag;
+
+    if (warp == 0) {                       // ---------------------------------------------------------------- TMA producer
+        if (tc::elect_one()) {
+            uint32_t g = 0;
+            for (int wi = blockIdx.x; wi < total; wi += gridDim.x) {
+                const TileRef r = locate(P, mi, wi);
+                const Task &t = *r.tg;
+                const int a_mn = t.A.mn_major, b_mn = t.B.mn_major, nkb = cdiv(t.K, kBK);
+                const int ma = t.A.r0 + r.m0, nb = t.B.r0 + r.n0;
+                const uint32_t bytes = (uint32_t)(r.bm + r.bn) * (kBK * 2 * 2);
+                for (int kb = 0; kb < nkb; kb++, g++) {
+                    const uint32_t s = g % kStages;
+                    tc::mbar_wait(&mi.empty[s], ((g / kStages) & 1) ^ 1, err);
+                    tc::mbar_arrive_expect_tx(&mi.full[s], bytes);
+                    const uint32_t sa = tc::smem_u32(ring) + s * kStageBytes, sb = sa + kABytes;
+                    const int k0 = kb * kBK;
+                    if (!a_mn) {
+                        tc::tma_load_4d(&t.tmA, &mi.full[s], sa, k0, ma, 0, r.agent);
+                    } else {
+                        tc::tma_load_4d(&t.tmA, &mi.full[s], sa, ma, k0, 0, r.agent);
+                        tc::tma_load_4d(&t.tmA, &mi.full[s], sa + kABytes / 2, ma + 64, k0, 0, r.agent);
+                    }
+                    if (!b_mn) {
+                        tc::tma_load_4d(&t.tmB, &mi.full[s], sb, k0, nb, 0, r.agent);
+                    } else {
+                        tc::tma_load_4d(&t.tmB, &mi.full[s], sb, nb, k0, 0, r.agent);
+                        if (r.bn > 64) tc::tma_load_4d(&t.tmB, &mi.full[s], sb + kBBytes / 2, nb + 64, k0, 0, r.agent);
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {                // ---------------------------------------------------------------- MMA issuer
+        uint32_t g = 0, it = 0;
+        for (int wi = blockIdx.x; wi < total; wi += gridDim.x, it++) {
+            const TileRef r = locate(P, mi, wi);
+            const Task &t = *r.tg;
+            const int a_mn = t.A.mn_major, b_mn = t.B.mn_major, nkb = cdiv(t.K, kBK);
+            const uint32_t buf = it & 1, use = it >> 1;
+            tc::mbar_wait(&mi.acc_empty[buf], (use & 1) ^ 1, err);      // the epilogue has drained this accumulator
+            tc::tc_fence_after();
+            const uint32_t idesc = tc::make_idesc(r.bm, r.bn, a_mn, b_mn), d = tmem + buf * kAccCols;
+            const uint32_t a_lo = a_mn ? kABytes / 4 : (uint32_t)r.bm * 128u, b_lo = b_mn ? kBBytes / 4 : (uint32_t)r.bn * 128u;
+            const uint32_t a_lbo = a_mn ? kABytes / 2 : 16, b_lbo = b_mn ? kBBytes / 2 : 16;
+            const uint32_t a_kstep = a_mn ? 2048 : 32, b_kstep = b_mn ? 2048 : 32;
+            for (int kb = 0; kb < nkb; kb++, g++) {
+                const uint32_t s = g % kStages;
+                tc::mbar_wait(&mi.full[s], (g / kStages) & 1, err);
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                    const uint32_t sa = tc::smem_u32(ring) + s * kStageBytes, sb = sa + kABytes;
+#pragma unroll
+                    for (int kk = 0; kk < kBK / 16; kk++) {
+                        const uint64_t da_hi = tc::make_desc(sa + kk * a_kstep, a_lbo), da_lo = tc::make_desc(sa + a_lo + kk * a_kstep, a_lbo);
+                        const uint64_t db_hi = tc::make_desc(sb + kk * b_kstep, b_lbo), db_lo = tc::make_desc(sb + b_lo + kk * b_kstep, b_lbo);
+                        tc::umma_bf16(d, da_lo, db_hi, idesc, (kb | kk) ? 1u : 0u);      // same order of the three products as the latency tile
+                        tc::umma_bf16(d, da_hi, db_lo, idesc, 1u);
+                        tc::umma_bf16(d, da_hi, db_hi, idesc, 1u);
+                    }
+                    tc::umma_commit(&mi.empty[s]);
+                    if (kb == nkb - 1) tc::umma_commit(&mi.acc_full[buf]);
+                }
+                __syncwarp();
+            }
+        }
+    } else if (warp >= kEpiWarp0) {        // ---------------------------------------------------------------- epilogue
+        const int et = threadIdx.x - kEpiWarp0 * 32;
+        uint32_t it = 0;
+        for (int wi = blockIdx.x; wi < total; wi += gridDim.x, it++) {
+            const TileRef r = locate(P, mi, wi);
+            const Task &t = *r.tg;
+            const float *scalars = resolve(P.scalars, P.bases, r.agent);
+            const EpiR epi = resolve_epilogue(t, P.bases, r.agent, scalars);
+            const uint32_t buf = it & 1, use = it >> 1;
+            const uint32_t acc = tmem + buf * kAccCols;
+            switch (epi.epi) {
+                case EPI_F32: epilogue_tile<EPI_F32>(epi, Cs, acc, r, et, &mi.acc_full[buf], use & 1, &mi.acc_empty[buf], err); break;
+                case EPI_BIAS_RELU: epilogue_tile<EPI_BIAS_RELU>(epi, Cs, acc, r, et, &mi.acc_full[buf], use & 1, &mi.acc_empty[buf], err); break;
+                case EPI_MASK: epilogue_tile<EPI_MASK>(epi, Cs, acc, r, et, &mi.acc_full[buf], use & 1, &mi.acc_empty[buf], err); break;
+                default: epilogue_tile<EPI_ADAM>(epi, Cs, acc, r, et, &mi.acc_full[buf], use & 1, &mi.acc_empty[buf], err); break;
+            }
+        }
+    }
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tc::tmem_dealloc(tmem, kTmemCols);
+}
+
+}  // namespace stream
+}  // namespace sacb

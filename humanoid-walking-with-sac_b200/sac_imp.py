@@ -217,7 +217,9 @@ class SAC:
 
     @property
     def log_alpha(self):
-        return torch.tensor([self._scalars().log_alpha], device=self.device)
+        # a leaf that requires grad, like the reference's (sac_imp.py:48): a checkpoint written here stays trainable when the
+        # reference's load_checkpoint (sac_imp.py:222-223) rebinds `self.log_alpha` to the loaded tensor
+        return torch.tensor([self._scalars().log_alpha], device=self.device, requires_grad=True)
 
     @log_alpha.setter
     def log_alpha(self, value):

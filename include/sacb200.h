@@ -228,6 +228,10 @@ int sacb_selftest_gemm(int device, int M, int N, int K, int a_mn_major, int b_mn
 /* same with an explicit tensor-core tile shape: bm = 64 | 128 rows, bn = 32 | 64 columns (32 only with a K-major B operand) */
 int sacb_selftest_gemm_tile(int device, int M, int N, int K, int a_mn_major, int b_mn_major, int b_r0, int bm, int bn, float *rel_err_out);
 
+/* same for the throughput ("stream") form of a GEMM stage: 128 x bn (64 | 128) tiles walked by `ctas` resident CTAs with decoupled
+ * TMA / tcgen05 / epilogue roles and two TMEM accumulators (csrc/stream.cuh) */
+int sacb_selftest_gemm_stream(int device, int M, int N, int K, int a_mn_major, int b_mn_major, int b_r0, int bn, int ctas, float *rel_err_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -43,3 +43,27 @@ def test_tc_tile_shapes(M, N, K, a_mn, b_mn, bm, bn):
     err = ctypes.c_float()
     N_.check(N_.lib().sacb_selftest_gemm_tile(0, M, N, K, a_mn, b_mn, 0, bm, bn, ctypes.byref(err)))
     assert err.value < 2e-5, err.value
+
+
+@pytest.mark.parametrize("bn", [64, 128])
+@pytest.mark.parametrize("M,N,K,ctas", [(256, 512, 512, 148), (1024, 512, 365, 3), (512, 365, 256, 5), (100, 70, 45, 1), (130, 129, 129, 2),
+                                        (34, 512, 256, 148), (512, 684, 1024, 7), (2048, 256, 64, 4)])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1)])
+def test_stream_tile_matches_ffma(M, N, K, ctas, a_mn, b_mn, bn):
+    """Throughput ("stream") form of a GEMM stage: 128 x 64 / 128 x 128 tiles, a few resident CTAs walking MANY tiles each
+    (the producer / MMA / epilogue roles run ahead of each other across tiles, two TMEM accumulators), all operand majors,
+    ragged M / N / K."""
+    import humanoid_walking_with_sac_b200 as hw
+    N_ = hw._native
+    err = ctypes.c_float()
+    N_.check(N_.lib().sacb_selftest_gemm_stream(0, M, N, K, a_mn, b_mn, 0, bn, ctas, ctypes.byref(err)))
+    assert err.value < 2e-5, err.value
+
+
+@pytest.mark.parametrize("b_mn,r0", [(0, 344), (1, 8)])
+def test_stream_tile_operand_offset(b_mn, r0):
+    import humanoid_walking_with_sac_b200 as hw
+    N_ = hw._native
+    err = ctypes.c_float()
+    N_.check(N_.lib().sacb_selftest_gemm_stream(0, 512, 17, 512, 0, b_mn, r0, 64, 2, ctypes.byref(err)))
+    assert err.value < 2e-5, err.value

