@@ -102,6 +102,10 @@ SIGNATURES = {
     "sacb_policy_sample": (I, [H, I, c_f32p, I64, c_f32p, c_f32p, c_f32p]),
     "sacb_dp_backward": (I, [H, I, I64, c_i64p, c_f32p, c_f32p]),
     "sacb_dp_apply": (I, [H, I]),
+    "sacb_dp_ipc_handle": (I, [H, ctypes.c_void_p]),
+    "sacb_dp_connect": (I, [H, I, I, ctypes.c_void_p]),
+    "sacb_dp_exchange_apply": (I, [H, I]),
+    "sacb_dp_get_losses": (I, [H, c_f32p]),
     "sacb_dp_grad_buffer": (I, [H, I, ctypes.POINTER(ctypes.c_void_p), c_i64p]),
     "sacb_get_stream": (I, [H, ctypes.POINTER(ctypes.c_void_p)]),
     "sacb_get_stats": (I, [H, ctypes.POINTER(Stats)]),

@@ -111,6 +111,7 @@ struct AdamArgs {
     Ref gexp;           // gradient export (null unless SACB_EXPORT_GRADS / data-parallel mode)
     PmRef shadow;       // bf16 pair shadow of w refreshed in place (null: not needed before the next step)
     PmRef shadow2;      // second shadow holding only columns >= shadow2_col0 of w (the action block of a critic's fc1)
+    PmRef shadow_t;     // throughput programs only (stream.cuh): bf16 pair shadow of the Polyak target wt, refreshed in the epilogue too
     int32_t shadow2_col0, pad0;
     int32_t step_slot;  // ScalarSlot of the optimizer step counter (value BEFORE this step's increment)
     int32_t apply;      // 0 = only export the gradient (data-parallel backward), 1 = apply Adam

@@ -57,7 +57,7 @@ struct EpiR {
     const float *bias;
     Pm mask;
     float *w, *m, *v, *wt, *gexp;
-    Pm shadow, shadow2;
+    Pm shadow, shadow2, shadow_t;
     int shadow2_col0;
     int apply;
     float step_size, bc2_sqrt, inv_bc2_sqrt, tau;
@@ -126,12 +126,13 @@ __device__ __forceinline__ EpiR resolve_epilogue(const Task &t, const AgentBases
     e.mask = resolve_pm(t.mask, b, agent);
     e.w = e.m = e.v = e.wt = e.gexp = nullptr; e.apply = 0; e.step_size = e.bc2_sqrt = e.inv_bc2_sqrt = 0.f; e.tau = 0.f;
     e.shadow.hi = nullptr; e.shadow.ld = 0; e.shadow.plane = 0;
-    e.shadow2 = e.shadow; e.shadow2_col0 = 0;
+    e.shadow2 = e.shadow; e.shadow_t = e.shadow; e.shadow2_col0 = 0;
     if (t.epi == EPI_ADAM) {
         e.w = resolve(t.adam.w, b, agent); e.m = resolve(t.adam.m, b, agent); e.v = resolve(t.adam.v, b, agent);
         e.wt = resolve(t.adam.wt, b, agent); e.gexp = resolve(t.adam.gexp, b, agent);
         e.shadow = resolve_pm(t.adam.shadow, b, agent);
         e.shadow2 = resolve_pm(t.adam.shadow2, b, agent); e.shadow2_col0 = t.adam.shadow2_col0;
+        e.shadow_t = resolve_pm(t.adam.shadow_t, b, agent);
         e.apply = t.adam.apply; e.tau = t.adam.tau;
         adam_factors_cached(scalars, t.adam.step_slot, e.step_size, e.bc2_sqrt);
         e.inv_bc2_sqrt = 1.0f / e.bc2_sqrt;

@@ -56,6 +56,7 @@ struct Layout {
     int64_t shadow[5] = {0, 0, 0, 0, 0};
     int64_t adam_m[3] = {0, 0, 0}, adam_v[3] = {0, 0, 0}, grad[3] = {0, 0, 0};
     int64_t grad_scalars = 0;       // exported log_alpha gradient
+    int64_t dp_flags = 0;           // [kDpMaxWorld] uint32 epoch flags written by the data-parallel peers (dp.cu)
     int64_t arena_size = 0;
     // workspace (per agent)
     // fp32 vectors / small matrices
@@ -120,6 +121,10 @@ struct sacb_handle_s {
     int64_t kernel_launches = 0;
     bool shadows_valid = false;          // see ProgramKey::resident; cleared by every write of fp32 weights from outside the update program
     int use_pdl = 1;                     // staged mode: programmatic dependent launch between the stage kernels (SACB_NO_PDL=1 disables)
+    // data-parallel exchange over peer memory (dp.cu): rank / world of this replica, the peers' arenas (cudaIpcOpenMemHandle; own = arena)
+    int dp_rank = 0, dp_world = 1;
+    float *dp_peer_arena[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint32_t dp_epoch = 0;
     int dp_device_eps = 1;               // data-parallel mode: eps of the current step drawn on device (phase 1 follows phase 0)
     int coop_blocks_per_sm = 0;
     // ---- replay (replay.cu) ----

@@ -78,6 +78,7 @@ void Layout::build(int obs_, int act_, int hidden_, int n_hidden_, int maxB_) {
     for (int k = 0; k < 3; k++) { adam_v[k] = o; o += sz[k]; }
     for (int k = 0; k < 3; k++) { grad[k] = o; o += sz[k]; }
     grad_scalars = o; o += 32;
+    dp_flags = o; o += 32;
     shadow[0] = o; o += pol.sh_size;
     for (int k = 1; k < 5; k++) { shadow[k] = o; o += q.sh_size; }
     arena_size = align_up(o, 64);
@@ -165,7 +166,7 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
     extern __shared__ __align__(16) uint8_t smem_raw[];
     __shared__ uint64_t s_bars[2 * kTStages + 2];
     __shared__ uint32_t s_tmem;
-    __shared__ float s_red[kThreads];
+    __shared__ float s_red[kColsumSmem];      // >= kThreads floats
     __shared__ Stage s_stage;
     __shared__ Task s_task;            // fields of the current task (the TMA descriptors are used from global memory)
 
@@ -209,6 +210,7 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
     stamp(1);
     unsigned int bar_target = 0;
     bool dep_synced = false;
+    const Task *cached_task = nullptr;
     for (int s = stage_begin; s < stage_end; s++) {
         if (threadIdx.x < sizeof(Stage) / 4) {
             const int32_t *src = (stage_end - stage_begin == 1) ? reinterpret_cast<const int32_t *>(&single) : reinterpret_cast<const int32_t *>(&P.stages[s]);
@@ -226,7 +228,9 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
             while (k + 1 < n_stage_tasks && tile_in_stage >= s_stage.tile_begin[k + 1]) k++;
             const Task *tg = &P.tasks[s_stage.task_begin + k];
             const int tile = tile_in_stage - s_stage.tile_begin[k];
-            {   // one parallel fetch of the task's fields instead of a chain of dependent global loads
+            if (tg != cached_task) {   // one parallel fetch of the task's fields instead of a chain of dependent global loads; a CTA that walks
+                                       // many tiles of the same task (population / large batch) keeps its copy
+                cached_task = tg;
                 constexpr int kSkip = 2 * sizeof(CUtensorMap) / 4, kWords = sizeof(Task) / 4 - kSkip;
                 static_assert(kWords <= kThreads, "task copy");
                 if (kTc && threadIdx.x == kThreads - 1) { tc::tma_prefetch_desc(&tg->tmA); tc::tma_prefetch_desc(&tg->tmB); }
@@ -318,6 +322,7 @@ struct Builder {
     // tensor-core tile shape per task index (bm, bn), decided by choose_tile_shapes() from a dry first pass; empty = defaults
     std::vector<std::pair<int, int>> shapes;
     bool dry = false;      // first pass: count tiles only, no TMA descriptors
+    bool stream = false;   // throughput program: GEMM stages run on the stream kernel (it alone understands split-K tasks)
 
     Builder(sacb_handle h_, const ProgramKey &k) : h(h_), L(h_->L), key(k) {
         if (math_is_tc(h->cfg.math_mode)) { tm = kTM; tn = kTN; } else { tm = kSM; tn = kSN; }
@@ -358,7 +363,7 @@ struct Builder {
         t.C = t.bias = null_ref();
         t.Cpm = t.mask = t.A.pm = t.B.pm = null_pm();
         t.adam.w = t.adam.m = t.adam.v = t.adam.wt = t.adam.gexp = null_ref();
-        t.adam.shadow = t.adam.shadow2 = null_pm();
+        t.adam.shadow = t.adam.shadow2 = t.adam.shadow_t = null_pm();
         for (auto &p : t.p) p = null_ref();
         for (auto &p : t.pm) p = null_pm();
         return t;
@@ -396,12 +401,22 @@ struct Builder {
                 rc = make_pm_tensor_map(&t.tmB, dev_ptr(b.ref.base), b_cols, b_rows, b.ref.ld, b.ref.plane, agent_stride_bytes(b.ref.base),
                                         h->cfg.n_agents, b_mn ? 64 : t.bn);
         }
-        add(t, t.tiles_m * t.tiles_n);
+        int n_chunks = 1;
+        if (stream && t.epi == EPI_ADAM && !apply()) {      // gradient export over a long batch dimension: split K, accumulate with atomics
+            const int nkb = cdiv(K, stream::kBK);
+            n_chunks = std::max(1, std::min(16, nkb / 16));
+            if (n_chunks > 1) t.i[7] = cdiv(nkb, n_chunks);
+        }
+        add(t, t.tiles_m * t.tiles_n * n_chunks);
     }
     Task epi_bias_relu(const PmView &C, Ref bias) { Task t = blank(T_GEMM); t.epi = EPI_BIAS_RELU; t.Cpm = C.ref; t.bias = bias; return t; }
     Task epi_mask(const PmView &C, const PmView &mask) { Task t = blank(T_GEMM); t.epi = EPI_MASK; t.Cpm = C.ref; t.mask = mask.ref; return t; }
     Task epi_f32(Ref C, int ldc, Ref bias) { Task t = blank(T_GEMM); t.epi = EPI_F32; t.C = C; t.ldc = ldc; t.bias = bias; return t; }
 
+    // rows per tile of a column-sum task (bias / output-layer gradients).  A program that only EXPORTS gradients (data-parallel
+    // backward: the slab is zeroed at the start of the step) cuts large batches into chunks of 1024 rows accumulated with atomics,
+    // so that the reduction over the batch spreads over the SMs; a program that applies Adam keeps one (deterministic) chunk
+    int colsum_rows(int Bn) const { return (!apply() && Bn > 2048) ? 1024 : std::max(Bn, 1); }
     // which optimizer a trainable net (0 policy, 1 q1, 2 q2) uses
     static int step_slot(int net) { return net == 0 ? SC_STEP_POLICY : (net == 1 ? SC_STEP_Q1 : SC_STEP_Q2); }
     bool apply() const { return key.dp_phase < 0; }
@@ -410,6 +425,10 @@ struct Builder {
     // policy's by T_SHADOW tasks riding in later stages of the step that leave most SMs idle (actor-phase critic forward, policy
     // backward, finish) -- in the epilogue the two extra planes cost 1.2-1.8 us per Adam stage, there they cost nothing.
     bool keep_resident() const { return apply(); }
+    // Throughput programs are bound by HBM traffic, not by stage latency: there every Adam epilogue writes the shadows of what it
+    // steps (policy and Polyak targets included) straight from its registers -- no extra pass over the fp32 weights, no extra stages.
+    bool epilogue_shadows() const { return stream && keep_resident(); }
+    bool task_shadows() const { return !stream && keep_resident(); }
     bool exporting() const { return key.export_grads || key.dp_phase >= 0; }
 
     AdamArgs adam_args(int net, int64_t off_in_net) {
@@ -417,7 +436,7 @@ struct Builder {
         a.w = A(L.param[net] + off_in_net); a.m = A(L.adam_m[net] + off_in_net); a.v = A(L.adam_v[net] + off_in_net);
         a.wt = net == 0 ? null_ref() : A(L.param[net + 2] + off_in_net);     // q1 -> q1_target, q2 -> q2_target
         a.gexp = exporting() ? A(L.grad[net] + off_in_net) : null_ref();
-        a.shadow = a.shadow2 = null_pm(); a.shadow2_col0 = 0; a.pad0 = 0;
+        a.shadow = a.shadow2 = a.shadow_t = null_pm(); a.shadow2_col0 = 0; a.pad0 = 0;
         a.step_slot = step_slot(net); a.apply = apply() ? 1 : 0;
         a.lr = h->cfg.lr; a.tau = h->cfg.tau;
         return a;
@@ -427,8 +446,9 @@ struct Builder {
     Task epi_adam(int net, int layer) {
         const NetLayout &n = net == 0 ? L.pol : L.q;
         Task t = blank(T_GEMM); t.epi = EPI_ADAM; t.adam = adam_args(net, n.w[layer]);
-        if (net != 0) t.adam.shadow = wsh(net, layer).ref;
+        if (net != 0 || epilogue_shadows()) t.adam.shadow = wsh(net, layer).ref;
         if (net != 0 && layer == 0) { t.adam.shadow2 = wsh_act(net).ref; t.adam.shadow2_col0 = L.obs; }
+        if (net != 0 && epilogue_shadows()) t.adam.shadow_t = wsh(net + 2, layer).ref;
         return t;
     }
 
@@ -438,7 +458,8 @@ struct Builder {
         AdamArgs a = adam_args(net, b_off);
         t.p[0] = a.w; t.p[1] = a.m; t.p[2] = a.v; t.p[3] = a.wt; t.p[4] = a.gexp;
         t.i[0] = Bn; t.i[1] = N; t.i[2] = a.step_slot; t.i[3] = a.apply; t.f[0] = a.lr; t.f[1] = a.tau;
-        add(t, cdiv(N, kColsumCols));
+        t.i[5] = colsum_rows(Bn);
+        add(t, cdiv(N, kColsumCols) * cdiv(Bn, t.i[5]));
     }
     // shadow of columns [col0, col0+dst.cols) of the fp32 matrix at w_off (row stride src_ld)
     void shadow_task(int net, int64_t w_off, const PmView &dst, int src_ld, int col0 = 0) {
@@ -639,7 +660,8 @@ struct Builder {
                         t.p[2] = aw.w; t.p[3] = aw.m; t.p[4] = aw.v; t.p[5] = aw.wt; t.p[6] = aw.gexp;
                         t.p[7] = ab.w; t.p[8] = ab.m; t.p[9] = ab.v; t.p[10] = ab.wt; t.p[11] = ab.gexp;
                         t.i[0] = B; t.i[1] = H; t.i[2] = aw.step_slot; t.i[3] = aw.apply; t.f[0] = aw.lr; t.f[1] = aw.tau;
-                        add(t, cdiv(H, kOutAdamCols) + 1);      // + the bias tile
+                        t.i[5] = colsum_rows(B);
+                        add(t, (cdiv(H, kColsumCols) + 1) * cdiv(B, t.i[5]));      // + the bias tile, per row chunk
                     }
                 }
             }
@@ -652,7 +674,7 @@ struct Builder {
                 for (int k = 0; k < 2; k++)
                     gemm(l == 0 ? X3(obs + act) : hview(L.ha[k][l - 1], B), 0, wsh(1 + k, l), 0, B, H, in_q,
                          epi_bias_relu(hview(L.ha[k][l], B), A(L.param[1 + k] + Q.b[l])));
-                if (critics && keep_resident())      // the Polyak targets moved in the critic backward: one layer's shadows per stage
+                if (critics && task_shadows())      // the Polyak targets moved in the critic backward: one layer's shadows per stage
                     for (int k = 0; k < 2; k++) shadow_task(3 + k, Q.w[nh - 1 - l], wsh(3 + k, nh - 1 - l), Q.in_of(nh - 1 - l));
             }
             begin_stage();
@@ -699,6 +721,7 @@ struct Builder {
                         gemm(hview(L.dhp[l], B), 0, wsh(0, l), 1, B, H, H, epi_mask(hview(L.dhp[l - 1], B), hp_cur(l - 1)));
                     if (s == 1) {              // heads: dW = g^T h_{nh-1}
                         Task t = blank(T_GEMM); t.epi = EPI_ADAM; t.adam = adam_args(0, P.w_out);
+                        if (epilogue_shadows()) t.adam.shadow = wsh_head().ref;
                         gemm(ghead(B), 1, hp_cur(nh - 1), 1, A2, H, B, t);
                         bias_adam(0, P.b_out, ghead(B), B, A2);
                     } else {
@@ -710,7 +733,7 @@ struct Builder {
                         gemm(hview(L.dhp[0], B), 1, X1(obs), 1, H, obs, B, epi_adam(0, 0));
                         bias_adam(0, P.b[0], hview(L.dhp[0], B), B, H);
                     }
-                    if (keep_resident()) {      // shadow of what the PREVIOUS stage stepped: heads (s-1 = 1) or hidden layer nh-s+2
+                    if (task_shadows()) {      // shadow of what the PREVIOUS stage stepped: heads (s-1 = 1) or hidden layer nh-s+2
                         if (s == 2) shadow_task(0, P.w_out, wsh_head(), H);
                         else if (s > 2) shadow_task(0, P.w[nh - s + 2], wsh(0, nh - s + 2), P.in_of(nh - s + 2));
                     }
@@ -729,7 +752,7 @@ struct Builder {
             t.i[5] = cdiv(B, kLossRows); t.i[6] = h->cfg.auto_entropy; t.i[7] = ap;
             t.f[0] = h->cfg.lr; t.f[1] = (float)B;
             add(t, 1);
-            if (actor && keep_resident()) {      // the last policy-backward stage stepped layers 1 and 0
+            if (actor && task_shadows()) {      // the last policy-backward stage stepped layers 1 and 0
                 shadow_task(0, P.w[1], wsh(0, 1), P.in_of(1));
                 shadow_task(0, P.w[0], wsh(0, 0), P.in_of(0));
             }
@@ -866,6 +889,7 @@ int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out) {
     }
     Builder b(h, key);
     b.shapes = shapes;
+    b.stream = stream_mode;
     b.build();
     if (b.rc != SACB_OK) return b.rc;
     std::vector<int> stage_stream;

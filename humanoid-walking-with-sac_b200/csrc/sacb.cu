@@ -119,6 +119,8 @@ extern "C" int sacb_destroy(sacb_handle h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     free_programs(h);
     replay_destroy(h);
+    for (int p = 0; p < h->dp_world; p++)      // peers' arenas mapped for the data-parallel exchange
+        if (p != h->dp_rank && h->dp_peer_arena[p]) cudaIpcCloseMemHandle(h->dp_peer_arena[p]);
     cudaFree(h->arena); cudaFree(h->ws); cudaFree(h->barrier); cudaFree(h->error_flag); cudaFree(h->slots); cudaFree(h->slots_identity); cudaFree(h->adam_table); cudaFree(h->slots_staged);
     if (h->pin) cudaFreeHost(h->pin);
     if (h->pin_small) cudaFreeHost(h->pin_small);

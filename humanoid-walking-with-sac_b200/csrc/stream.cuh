@@ -48,7 +48,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 }
 
 // the tile a work item denotes; every role calls this with the same arguments
-struct TileRef { const Task *tg; int agent, m0, n0, bm, bn; };
+struct TileRef { const Task *tg; int agent, m0, n0, bm, bn, kb0, nkb; };
 __device__ __forceinline__ TileRef locate(const Program &P, const Misc &mi, int wi) {
     TileRef r;
     r.agent = wi / mi.n_tiles;
@@ -56,16 +56,37 @@ __device__ __forceinline__ TileRef locate(const Program &P, const Misc &mi, int 
     int k = 0;
     while (k + 1 < mi.n_tasks && tis >= mi.tile_begin[k + 1]) k++;
     r.tg = &P.tasks[mi.task_begin + k];
-    const int tile = tis - mi.tile_begin[k];
+    int tile = tis - mi.tile_begin[k];
     r.bm = r.tg->bm; r.bn = r.tg->bn;
-    const int tn = r.tg->tiles_n;
+    const int tn = r.tg->tiles_n, per = r.tg->tiles_m * tn;
+    // split K (gradient-export GEMMs of large batches, Task::i[7] = K blocks per chunk): tile = [chunk][tm][tn], the chunks of an
+    // output tile are accumulated into the zeroed gradient slab with atomics by their epilogues
+    const int chunk = r.tg->i[7], nkb_all = cdiv(r.tg->K, kBK);
+    r.kb0 = 0; r.nkb = nkb_all;
+    if (chunk > 0) { r.kb0 = (tile / per) * chunk; r.nkb = max(0, min(nkb_all - r.kb0, chunk)); tile %= per; }
     r.m0 = (tile / tn) * r.bm; r.n0 = (tile % tn) * r.bn;
     return r;
 }
 
-// ---- Adam (+ Polyak, + critic shadow refresh) on 64 columns of the tile held in the staging tile, 256 epilogue threads.
-// Same passes as tc::adam_epilogue_tile (aligned 128-bit groups per row, stragglers, shadows from the staged new weights).
-__device__ __forceinline__ void adam_epilogue(const EpiR &e, float *Cs, int m0, int n0, int et) {
+// ---- Adam (+ Polyak, + shadow refresh) on 64 columns of the tile held in the staging tile, 256 epilogue threads.
+// pass A: per row the 16 threads take the 4-column groups that start at the first 16-byte aligned column of THAT row (the fp32
+//         matrices are contiguous [M, N]: a row starts at any 4-byte phase when N % 4 != 0), all loads of two rows before any store
+// pass B: the columns no aligned group covers, one element per thread
+// Shadows (of the stepped weights, of the action block of a critic's fc1, of the Polyak target) are written straight from the
+// registers that hold the new values: 8-byte stores per plane where the group is 4-column aligned in the shadow, else per element.
+__device__ __forceinline__ void shadow_store4(const Pm &p, int m, int n, int N, const float (&x)[4]) {
+    if (!p.hi) return;
+    if ((n & 3) == 0) { tc::store_pm4(p, m, n, N, x); return; }
+#pragma unroll
+    for (int j = 0; j < 4; j++) if (n + j < N) pm_store(p, m, n + j, x[j]);
+}
+__device__ __forceinline__ void shadow2_store4(const EpiR &e, int m, int n, const float (&x)[4]) {      // columns >= shadow2_col0 only
+    if (!e.shadow2.hi || n + 3 < e.shadow2_col0) return;
+    if (n >= e.shadow2_col0 && ((n - e.shadow2_col0) & 3) == 0) { tc::store_pm4(e.shadow2, m, n - e.shadow2_col0, e.N - e.shadow2_col0, x); return; }
+#pragma unroll
+    for (int j = 0; j < 4; j++) if (n + j >= e.shadow2_col0 && n + j < e.N) pm_store(e.shadow2, m, n + j - e.shadow2_col0, x[j]);
+}
+__device__ __forceinline__ void adam_epilogue(const EpiR &e, const float *Cs, int m0, int n0, int et, bool accumulate) {
     const int ncols = min(64, e.N - n0);
     if (ncols <= 0) return;      // uniform over the epilogue threads
     const int j16 = et & 15, r0 = et >> 4;      // 16 threads per row, rows r0 + 16 i
@@ -94,10 +115,13 @@ __device__ __forceinline__ void adam_epilogue(const EpiR &e, float *Cs, int m0, 
         for (int ii = 0; ii < 2; ii++) {
             if (!vec[ii]) continue;
             const int row = r0 + 16 * (2 * grp + ii);
-            float *cs = Cs + row * tc::kCsLd + c[ii];
+            const float *cs = Cs + row * tc::kCsLd + c[ii];
             const int64_t o = (int64_t)mrow[ii] * e.N + n0 + c[ii];
             const float g[4] = {cs[0], cs[1], cs[2], cs[3]};
-            if (e.gexp) *reinterpret_cast<float4 *>(e.gexp + o) = make_float4(g[0], g[1], g[2], g[3]);
+            if (e.gexp) {
+                if (accumulate) atomicAdd(reinterpret_cast<float4 *>(e.gexp + o), make_float4(g[0], g[1], g[2], g[3]));      // one 16-byte reduction at L2
+                else *reinterpret_cast<float4 *>(e.gexp + o) = make_float4(g[0], g[1], g[2], g[3]);
+            }
             if (!e.apply) continue;
             const tc::AdamOut a = tc::adam_math(e, g[0], w[ii].x, mm[ii].x, vv[ii].x, wt[ii].x), b = tc::adam_math(e, g[1], w[ii].y, mm[ii].y, vv[ii].y, wt[ii].y);
             const tc::AdamOut cc = tc::adam_math(e, g[2], w[ii].z, mm[ii].z, vv[ii].z, wt[ii].z), d = tc::adam_math(e, g[3], w[ii].w, mm[ii].w, vv[ii].w, wt[ii].w);
@@ -105,7 +129,11 @@ __device__ __forceinline__ void adam_epilogue(const EpiR &e, float *Cs, int m0, 
             *reinterpret_cast<float4 *>(e.v + o) = make_float4(a.v, b.v, cc.v, d.v);
             *reinterpret_cast<float4 *>(e.w + o) = make_float4(a.w, b.w, cc.w, d.w);
             if (e.wt) *reinterpret_cast<float4 *>(e.wt + o) = make_float4(a.t, b.t, cc.t, d.t);
-            cs[0] = a.w; cs[1] = b.w; cs[2] = cc.w; cs[3] = d.w;
+            const float w1[4] = {a.w, b.w, cc.w, d.w};
+            const int n = n0 + c[ii];
+            shadow_store4(e.shadow, mrow[ii], n, e.N, w1);
+            shadow2_store4(e, mrow[ii], n, w1);
+            if (e.wt && e.shadow_t.hi) { const float t1[4] = {a.t, b.t, cc.t, d.t}; shadow_store4(e.shadow_t, mrow[ii], n, e.N, t1); }
         }
     }
     if (e.N % 4 != 0 || ncols < 64) {           // pass B: the columns no aligned group covers; thread (row = et / 4 (+ 64), q = et % 4)
@@ -121,52 +149,32 @@ __device__ __forceinline__ void adam_epilogue(const EpiR &e, float *Cs, int m0, 
             if (tail0 + q < ncols) col[cnt++] = tail0 + q;
             for (int u = 0; u < cnt; u++) {
                 const int64_t o = (int64_t)m * e.N + n0 + col[u];
-                float *cs = Cs + row * tc::kCsLd + col[u];
-                const float g = *cs;
-                if (e.gexp) e.gexp[o] = g;
+                const float g = Cs[row * tc::kCsLd + col[u]];
+                if (e.gexp) { if (accumulate) atomicAdd(e.gexp + o, g); else e.gexp[o] = g; }
                 if (!e.apply) continue;
                 const tc::AdamOut r = tc::adam_math(e, g, __ldcg(e.w + o), __ldcg(e.m + o), __ldcg(e.v + o), e.wt ? __ldcg(e.wt + o) : 0.f);
                 e.m[o] = r.m; e.v[o] = r.v; e.w[o] = r.w;
                 if (e.wt) e.wt[o] = r.t;
-                *cs = r.w;
-            }
-        }
-    }
-    if (!e.apply || (!e.shadow.hi && !e.shadow2.hi)) return;
-    epi_bar();                                  // pass C: the staging tile holds the new weights
-    const int c4 = j16 * 4;
-    if (c4 >= ncols) return;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const int row = r0 + 16 * i, m = m0 + row;
-        if (m >= e.M) continue;
-        const float4 v4 = *reinterpret_cast<const float4 *>(Cs + row * tc::kCsLd + c4);
-        const float w1[4] = {v4.x, v4.y, v4.z, v4.w};
-        const int n = n0 + c4;
-        if (e.shadow.hi) tc::store_pm4(e.shadow, m, n, e.N, w1);
-        if (e.shadow2.hi && n + 3 >= e.shadow2_col0) {
-            if (n >= e.shadow2_col0 && ((n - e.shadow2_col0) & 3) == 0) {
-                tc::store_pm4(e.shadow2, m, n - e.shadow2_col0, e.N - e.shadow2_col0, w1);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 4; j++)
-                    if (n + j >= e.shadow2_col0 && n + j < e.N) pm_store(e.shadow2, m, n + j - e.shadow2_col0, w1[j]);
+                const int n = n0 + col[u];
+                if (e.shadow.hi) pm_store(e.shadow, m, n, r.w);
+                if (e.shadow2.hi && n >= e.shadow2_col0) pm_store(e.shadow2, m, n - e.shadow2_col0, r.w);
+                if (e.wt && e.shadow_t.hi) pm_store(e.shadow_t, m, n, r.t);
             }
         }
     }
 }
 
-// L2 prefetch of the optimizer state an Adam tile will stream (w, m, v, target: 4 x bm x bn floats), issued by the epilogue
-// warps while the tile is still being accumulated: the epilogue then finds its operands in L2 instead of paying DRAM latency
-// in every one of its load phases
-__device__ __forceinline__ void adam_prefetch(const EpiR &e, int m0, int n0, int bn, int et) {
-    if (!e.apply) return;
-    const int lines_per_row = (bn * 4 + 127) / 128 + 1;      // rows start at any 4-byte phase
-    for (int i = et; i < kBM * lines_per_row; i += kEpiThreads) {
-        const int row = i / lines_per_row, l = i % lines_per_row, m = m0 + row;
-        if (m >= e.M) continue;
-        const int64_t o = (int64_t)m * e.N + n0 + l * 32;
-        if (n0 + l * 32 >= e.N + 32) continue;
+// L2 prefetch of the optimizer state one 64-column pass of an Adam tile will stream (w, m, v, target: 4 x 128 x 64 floats), issued
+// by the epilogue warps at the start of the tile, so that the load phases of its passes find their operands in L2 instead of paying
+// DRAM latency four times per pass.  (Prefetching a whole pass AHEAD was measured slower -- 1.36 -> 1.63 ms on the heaviest Adam
+// stage of a 128-agent population: the stage is DRAM-throughput bound, earlier prefetches only get evicted.)
+__device__ __forceinline__ void adam_prefetch(const EpiR &e, int m0, int n0c, int et) {
+    if (!e.apply || n0c >= e.N) return;
+    constexpr int kLines = 3;      // 64 floats = 2 lines, + 1: rows start at any 4-byte phase
+    for (int i = et; i < kBM * kLines; i += kEpiThreads) {
+        const int row = i / kLines, l = i % kLines, m = m0 + row;
+        if (m >= e.M || n0c + l * 32 >= e.N + 32) continue;
+        const int64_t o = (int64_t)m * e.N + n0c + l * 32;
         asm volatile("prefetch.global.L2 [%0];" ::"l"(e.w + o));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(e.m + o));
         asm volatile("prefetch.global.L2 [%0];" ::"l"(e.v + o));
@@ -219,7 +227,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiR &epi, float *Cs, uint32
     const int ew = et >> 5, lane = et & 31, q = ew & 3, hcol = (ew >> 2) * 32;
     const int passes = r.bn > 64 ? 2 : 1;
     float aux[8][4];
-    if (EPI == EPI_ADAM) adam_prefetch(epi, r.m0, r.n0, r.bn, et);
+    if (EPI == EPI_ADAM) { for (int p = 0; p < passes; p++) adam_prefetch(epi, r.m0, r.n0 + 64 * p, et); }
     else plain_aux<EPI>(epi, r.m0, r.n0, et, aux);
     tc::mbar_wait(acc_full, parity, err);
     tc::tc_fence_after();
@@ -247,7 +255,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiR &epi, float *Cs, uint32
             if (lane == 0) mbar_arrive(acc_empty);
         }
         epi_bar();
-        if (EPI == EPI_ADAM) adam_epilogue(epi, Cs, r.m0, n0c, et);
+        if (EPI == EPI_ADAM) adam_epilogue(epi, Cs, r.m0, n0c, et, r.tg->i[7] > 0);
         else plain_epilogue<EPI>(epi, Cs, r.m0, n0c, et, aux);
         epi_bar();        // the staging tile is free for the next pass / tile
     }
@@ -282,7 +290,7 @@ __device__ __forceinline__ void gemm_stage(const Program &P, const Stage &stage,
             for (int wi = blockIdx.x; wi < total; wi += gridDim.x) {
                 const TileRef r = locate(P, mi, wi);
                 const Task &t = *r.tg;
-                const int a_mn = t.A.mn_major, b_mn = t.B.mn_major, nkb = cdiv(t.K, kBK);
+                const int a_mn = t.A.mn_major, b_mn = t.B.mn_major, nkb = r.nkb;
                 const int ma = t.A.r0 + r.m0, nb = t.B.r0 + r.n0;
                 const uint32_t bytes = (uint32_t)(r.bm + r.bn) * (kBK * 2 * 2);
                 for (int kb = 0; kb < nkb; kb++, g++) {
@@ -290,7 +298,7 @@ __device__ __forceinline__ void gemm_stage(const Program &P, const Stage &stage,
                     tc::mbar_wait(&mi.empty[s], ((g / kStages) & 1) ^ 1, err);
                     tc::mbar_arrive_expect_tx(&mi.full[s], bytes);
                     const uint32_t sa = tc::smem_u32(ring) + s * kStageBytes, sb = sa + kABytes;
-                    const int k0 = kb * kBK;
+                    const int k0 = (r.kb0 + kb) * kBK;
                     if (!a_mn) {
                         tc::tma_load_4d(&t.tmA, &mi.full[s], sa, k0, ma, 0, r.agent);
                     } else {
@@ -312,7 +320,7 @@ __device__ __forceinline__ void gemm_stage(const Program &P, const Stage &stage,
         for (int wi = blockIdx.x; wi < total; wi += gridDim.x, it++) {
             const TileRef r = locate(P, mi, wi);
             const Task &t = *r.tg;
-            const int a_mn = t.A.mn_major, b_mn = t.B.mn_major, nkb = cdiv(t.K, kBK);
+            const int a_mn = t.A.mn_major, b_mn = t.B.mn_major, nkb = r.nkb;
             const uint32_t buf = it & 1, use = it >> 1;
             tc::mbar_wait(&mi.acc_empty[buf], (use & 1) ^ 1, err);      // the epilogue has drained this accumulator
             tc::tc_fence_after();

@@ -329,85 +329,140 @@ __device__ __forceinline__ void task_sample_bwd(const Task &t, int tile, const P
     pm_store(g, b, A + a, (g_u * s.std * eps - aB) * s.in_range);
 }
 
-// column sums over the batch for kColsumCols columns per tile: thread (cg = tid % C, rg = tid / C) adds rows rg, rg+G, ...
-// (loads unrolled 8 deep), the row groups are then combined in shared memory in a fixed order
+// Column sums over batch rows for a tile of kColsumCols = 64 columns: a thread owns 8 consecutive columns (one 16-byte load per
+// bf16 plane and row) of row lane tid / 8, rows lane, lane + 64, ... (4 rows in flight); the four row lanes of a warp are combined
+// with shuffles, the 16 warps through shared memory in warp order: a fixed summation order.  Result valid for threadIdx.x < 64.
 constexpr int kColsumCols = 64;
-constexpr int kOutAdamCols = 32;     // T_OUT_ADAM: narrower tiles (16 row groups): half the dependent load rounds per thread
-template <int kCols, class F>
-__device__ __forceinline__ float colsum(int B, float *smem, F value_at) {
-    constexpr int G = kThreads / kCols;       // row groups
-    const int cg = threadIdx.x % kCols, rg = threadIdx.x / kCols;
-    float acc = 0.f;
-    int b = rg;
-    for (; b + 7 * G < B; b += 8 * G) {
-        float v[8];
+constexpr int kColsumSmem = (kThreads / 32) * kColsumCols;      // floats of shared memory
+template <class F>
+__device__ __forceinline__ float colsum64(int r0, int r1, float *smem, F load8) {
+    const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float acc[8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) v[u] = value_at(b + G * u);
+    for (int j = 0; j < 8; j++) acc[j] = 0.f;
+    int b = r0 + rl;
+    for (; b + 3 * 64 < r1; b += 4 * 64) {
+        float v[4][8];
 #pragma unroll
-        for (int u = 0; u < 8; u++) acc += v[u];
+        for (int u = 0; u < 4; u++) load8(b + 64 * u, cg * 8, v[u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] += v[u][j];
     }
-    for (; b < B; b += G) acc += value_at(b);
-    smem[rg * kCols + cg] = acc;
+    for (; b < r1; b += 64) {
+        float v[8];
+        load8(b, cg * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] += v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 8);
+        acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 16);
+    }
+    if (lane < 8) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) smem[warp * kColsumCols + cg * 8 + j] = acc[j];
+    }
     __syncthreads();
     float tot = 0.f;
-    if (rg == 0) for (int g = 0; g < G; g++) tot += smem[g * kCols + cg];
+    if (threadIdx.x < kColsumCols)
+        for (int w = 0; w < kThreads / 32; w++) tot += smem[w * kColsumCols + threadIdx.x];
     __syncthreads();
-    return tot;     // valid for rg == 0
+    return tot;
+}
+
+// Adam on one element whose optimizer state was fetched before the column sum (the two latencies overlap); same arithmetic as adam_element
+struct PreState { float w, m, v, wt; };
+__device__ __forceinline__ PreState prefetch_state(bool on, const float *w, const float *m, const float *v, const float *wt) {
+    PreState s{0.f, 0.f, 0.f, 0.f};
+    if (on) { s.w = __ldcg(w); s.m = __ldcg(m); s.v = __ldcg(v); if (wt) s.wt = __ldcg(wt); }
+    return s;
+}
+__device__ __forceinline__ void adam_prefetched(float g, PreState s, float *w, float *m, float *v, float *wt, float ss, float bs, float tau) {
+    const float mm = s.m + (1.0f - kBeta1) * (g - s.m);
+    const float vv = s.v * kBeta2 + (1.0f - kBeta2) * g * g;
+    const float denom = sqrtf(vv) / bs + kAdamEps;
+    const float ww = s.w - ss * (mm / denom);
+    *m = mm; *v = vv; *w = ww;
+    if (wt) *wt = s.wt * (1.0f - tau) + ww * tau;
+}
+// gradient of a column-sum task: exported (optionally accumulated over row chunks with atomics: data-parallel programs, whose
+// gradient slab is zeroed at the start of the step) and / or applied
+__device__ __forceinline__ void colsum_finish(float g, bool chunked, float *ge, int apply, PreState st, float *w, float *m, float *v, float *wt,
+                                              float ss, float bs, float tau) {
+    if (ge) { if (chunked) atomicAdd(ge, g); else *ge = g; }
+    if (apply) adam_prefetched(g, st, w, m, v, wt, ss, bs, tau);
 }
 
 // T_OUT_ADAM: Q output layer (Linear(H,1)).  pm0=h_L PM [B,H] p1=dq [B] ; p2..p6 = w,m,v,wt,gexp [H] ; p7..p11 = same for bias
-//   i0=B i1=H i2=step_slot i3=apply ; f0=lr f1=tau.   kOutAdamCols columns per tile; one extra (last) tile does the bias.
-//   The optimiser state of a column is fetched BEFORE its column sum so that the two latencies overlap.
+//   i0=B i1=H i2=step_slot i3=apply i5=rows per chunk (>= B: one chunk) ; f0=lr f1=tau.
+//   tiles: [row chunk][64-column tile] for the weight gradient, then one bias tile per row chunk
 __device__ __forceinline__ void task_out_adam(const Task &t, int tile, const Program &P, int agent, const float *scalars, float *smem) {
-    const int B = t.i[0], H = t.i[1];
+    const int B = t.i[0], H = t.i[1], R = t.i[5], n_ct = cdiv(H, kColsumCols), n_rc = cdiv(B, R);
     const float *dq = resolve(t.p[1], P.bases, agent);
     float ss, bs;
     adam_factors_cached(scalars, t.i[2], ss, bs);
-    if (tile == cdiv(H, kOutAdamCols)) {      // bias tile: db = sum_b dq[b], fixed order (32 lane partials, then the warp tree)
+    if (tile >= n_ct * n_rc) {      // bias tile of row chunk tile - n_ct * n_rc: db = sum_b dq[b] (32 lane partials, then the warp tree)
+        const int rc = tile - n_ct * n_rc, r0 = rc * R, r1 = min(B, r0 + R);
         if (threadIdx.x < 32) {
             float gb = 0.f;
-            for (int b = threadIdx.x; b < B; b += 32) gb += ldcg(dq + b);
+            for (int b = r0 + threadIdx.x; b < r1; b += 32) gb += ldcg(dq + b);
             gb = warp_sum(gb);
-            if (threadIdx.x == 0)
-                adam_element(gb, resolve(t.p[7], P.bases, agent), resolve(t.p[8], P.bases, agent), resolve(t.p[9], P.bases, agent),
-                             resolve(t.p[10], P.bases, agent), resolve(t.p[11], P.bases, agent), t.i[3], ss, bs, t.f[1]);
+            if (threadIdx.x == 0) {
+                float *w = resolve(t.p[7], P.bases, agent), *m = resolve(t.p[8], P.bases, agent), *v = resolve(t.p[9], P.bases, agent);
+                float *wt = resolve(t.p[10], P.bases, agent), *ge = resolve(t.p[11], P.bases, agent);
+                colsum_finish(gb, n_rc > 1, ge, t.i[3], prefetch_state(t.i[3] != 0, w, m, v, wt), w, m, v, wt, ss, bs, t.f[1]);
+            }
         }
         return;
     }
-    const int n = tile * kOutAdamCols + (threadIdx.x % kOutAdamCols);
+    const int ct = tile % n_ct, rc = tile / n_ct, r0 = rc * R, r1 = min(B, r0 + R);
+    const int n = ct * kColsumCols + threadIdx.x;
     const Pm h = resolve_pm(t.pm[0], P.bases, agent);
-    const bool owner = threadIdx.x < kOutAdamCols && n < H;
+    const bool owner = threadIdx.x < kColsumCols && n < H;
     float *w = resolve(t.p[2], P.bases, agent) + n, *m = resolve(t.p[3], P.bases, agent) + n, *v = resolve(t.p[4], P.bases, agent) + n;
     float *wt = resolve(t.p[5], P.bases, agent), *ge = resolve(t.p[6], P.bases, agent);
-    float ww = 0.f, mm = 0.f, vv = 0.f, wtv = 0.f;
-    if (owner && t.i[3]) { ww = __ldcg(w); mm = __ldcg(m); vv = __ldcg(v); if (wt) wtv = __ldcg(wt + n); }
-    const float g = colsum<kOutAdamCols>(B, smem, [&](int b) { return n < H ? ldcg(dq + b) * pm_load(h, b, n) : 0.f; });
-    if (owner) {
-        if (ge) ge[n] = g;
-        if (t.i[3]) {      // adam_element on the prefetched state (same arithmetic, same order)
-            mm = mm + (1.0f - kBeta1) * (g - mm);
-            vv = vv * kBeta2 + (1.0f - kBeta2) * g * g;
-            const float denom = sqrtf(vv) / bs + kAdamEps;
-            ww = ww - ss * (mm / denom);
-            *m = mm; *v = vv; *w = ww;
-            if (wt) wt[n] = wtv * (1.0f - t.f[1]) + ww * t.f[1];
+    const PreState st = prefetch_state(owner && t.i[3], w, m, v, wt ? wt + n : nullptr);
+    const int c0 = ct * kColsumCols;
+    const float g = colsum64(r0, r1, smem, [&](int b, int c, float (&out)[8]) {
+        if (c0 + c < h.ld) {
+            pm_load8(h, b, c0 + c, out);
+            const float d = ldcg(dq + b);
+#pragma unroll
+            for (int j = 0; j < 8; j++) out[j] *= d;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) out[j] = 0.f;
         }
-    }
+    });
+    if (owner) colsum_finish(g, n_rc > 1, ge ? ge + n : nullptr, t.i[3], st, w, m, v, wt ? wt + n : nullptr, ss, bs, t.f[1]);
 }
 
-// T_BIAS_ADAM: db[n] = sum_b dh[b,n].  pm0 = dh PM [B,N] ; p0..p4 = b,m,v,bt,gexp ; i0=B i1=N i2=step_slot i3=apply ;
-//   f0=lr f1=tau.   kColsumCols columns per tile
+// T_BIAS_ADAM: db[n] = sum_b dh[b,n].  pm0 = dh PM [B,N] ; p0..p4 = b,m,v,bt,gexp ; i0=B i1=N i2=step_slot i3=apply
+//   i5=rows per chunk ; f0=lr f1=tau.   tiles: [row chunk][64-column tile]
 __device__ __forceinline__ void task_bias_adam(const Task &t, int tile, const Program &P, int agent, const float *scalars, float *smem) {
-    const int B = t.i[0], N = t.i[1];
-    const int n = tile * kColsumCols + (threadIdx.x % kColsumCols);
+    const int B = t.i[0], N = t.i[1], R = t.i[5], n_ct = cdiv(N, kColsumCols), n_rc = cdiv(B, R);
+    const int ct = tile % n_ct, rc = tile / n_ct, r0 = rc * R, r1 = min(B, r0 + R);
+    const int n = ct * kColsumCols + threadIdx.x;
     const Pm dh = resolve_pm(t.pm[0], P.bases, agent);
-    const float g = colsum<kColsumCols>(B, smem, [&](int b) { return n < N ? pm_load(dh, b, n) : 0.f; });
-    if (threadIdx.x < kColsumCols && n < N) {
+    const bool owner = threadIdx.x < kColsumCols && n < N;
+    float *w = resolve(t.p[0], P.bases, agent) + n, *m = resolve(t.p[1], P.bases, agent) + n, *v = resolve(t.p[2], P.bases, agent) + n;
+    float *bt = resolve(t.p[3], P.bases, agent), *ge = resolve(t.p[4], P.bases, agent);
+    const PreState st = prefetch_state(owner && t.i[3], w, m, v, bt ? bt + n : nullptr);
+    const int c0 = ct * kColsumCols;
+    const float g = colsum64(r0, r1, smem, [&](int b, int c, float (&out)[8]) {
+        if (c0 + c < dh.ld) pm_load8(dh, b, c0 + c, out);
+        else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) out[j] = 0.f;
+        }
+    });
+    if (owner) {
         float ss, bs;
         adam_factors_cached(scalars, t.i[2], ss, bs);
-        float *bt = resolve(t.p[3], P.bases, agent), *ge = resolve(t.p[4], P.bases, agent);
-        adam_element(g, resolve(t.p[0], P.bases, agent) + n, resolve(t.p[1], P.bases, agent) + n, resolve(t.p[2], P.bases, agent) + n,
-                     bt ? bt + n : nullptr, ge ? ge + n : nullptr, t.i[3], ss, bs, t.f[1]);
+        colsum_finish(g, n_rc > 1, ge ? ge + n : nullptr, t.i[3], st, w, m, v, bt ? bt + n : nullptr, ss, bs, t.f[1]);
     }
 }
 

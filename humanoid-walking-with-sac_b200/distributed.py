@@ -46,10 +46,32 @@ class DataParallelSAC:
     reassociation.  `agent` is a `sac_imp.SAC` on this rank's GPU.
     """
 
-    def __init__(self, agent, group=None):
+    def __init__(self, agent, group=None, exchange="peer"):
+        """exchange: 'peer' = the library's own fused exchange (flag barrier + ONE kernel that sums the replicas' gradient slabs over
+        NVLink peer memory in rank order and applies Adam; needs all ranks on one node) -- 'nccl' = torch.distributed all-reduce of
+        the slabs followed by the element-wise apply kernel (the round-1 path, kept for A/B timing and multi-node use)."""
         self.agent, self.group = agent, group
-        self.exchange = True           # False: skip the all-reduces (measurement of their share only; the replicas then diverge)
-        self.exchange_kind = "ncclAllReduce (torch.distributed) on the library's stream + element-wise Adam apply"
+        self.exchange = True           # False: skip the exchange (measurement of its share only; the replicas then diverge)
+        world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+        self.world, self.rank = world, rank
+        self.mode = exchange
+        if exchange == "peer":
+            lib = N.lib()
+            mine = ctypes.create_string_buffer(64)
+            N.check(lib.sacb_dp_ipc_handle(agent._h, mine))
+            handles = [None] * world
+            if world > 1:
+                dist.all_gather_object(handles, bytes(mine.raw), group=group)      # plumbing only: 64 bytes per rank
+            else:
+                handles[0] = bytes(mine.raw)
+            blob = ctypes.create_string_buffer(b"".join(handles), 64 * world)
+            N.check(lib.sacb_dp_connect(agent._h, rank, world, blob))
+            if world > 1:
+                dist.barrier(group=group)      # every rank has mapped its peers before the first flag is written
+            self.exchange_kind = "fused: flag barrier in NVLink peer memory + one kernel summing the replicas' gradient slabs (peer loads) with Adam + Polyak applied in the same pass"
+        else:
+            self.exchange_kind = "ncclAllReduce (torch.distributed) on the library's stream + element-wise Adam apply"
         self._bufs = {}
         for phase in (0, 1, 2):
             ptr, n = ctypes.c_void_p(), ctypes.c_int64()
@@ -82,13 +104,19 @@ class DataParallelSAC:
         with torch.cuda.stream(self._stream):
             for phase in (0, 1):
                 N.check(lib.sacb_dp_backward(a._h, phase, n_local, N.ptr(ix, ctypes.c_int64) if (phase == 0 and ix is not None) else None, N.ptr(e_next), N.ptr(e_cur)))
-                if self.exchange:
-                    allreduce_mean_(self.gradient_slabs(phase), self.group)   # same stream: ordered behind the backward, ahead of the apply
-                N.check(lib.sacb_dp_apply(a._h, phase))
+                if self.mode == "peer" and self.exchange:
+                    N.check(lib.sacb_dp_exchange_apply(a._h, phase))          # barrier + peer-memory reduction + Adam in one kernel
+                else:
+                    if self.exchange:
+                        allreduce_mean_(self.gradient_slabs(phase), self.group)   # same stream: ordered behind the backward, ahead of the apply
+                    N.check(lib.sacb_dp_apply(a._h, phase))
         a._alpha_is_float = False
         if not sync:
             return None
         losses = np.zeros(3, np.float32)
+        if self.mode == "peer" and self.exchange:      # the finish kernels averaged the replicas' loss scalars through peer memory
+            N.check(lib.sacb_dp_get_losses(a._h, N.ptr(losses)))
+            return {"q1_loss": float(losses[0]), "q2_loss": float(losses[1]), "policy_loss": float(losses[2])}
         N.check(lib.sacb_get_losses(a._h, 0, N.ptr(losses)))
         t = torch.from_numpy(losses.copy()).to(self._bufs[0].device)
         with torch.cuda.stream(self._stream):

@@ -197,6 +197,16 @@ int sacb_policy_sample(sacb_handle h, int agent, const float *s, int64_t n, cons
 int sacb_dp_backward(sacb_handle h, int phase, int64_t B_local, const int64_t *idx, const float *eps_next, const float *eps_cur);
 int sacb_dp_apply(sacb_handle h, int phase);
 int sacb_dp_grad_buffer(sacb_handle h, int phase, void **dev_ptr, int64_t *n_floats);
+/* Fused exchange over NVLink peer memory (one node, 1..8 replicas, one process per GPU): sacb_dp_ipc_handle gives the 64-byte CUDA IPC
+ * handle of this replica's arena; after the host has gathered all of them (any transport: torch.distributed.all_gather_object),
+ * sacb_dp_connect maps the peers' arenas.  sacb_dp_exchange_apply(phase) then replaces "all-reduce + sacb_dp_apply": a flag barrier
+ * in peer memory, and ONE kernel that reads the W gradient slabs (own HBM + peers over NVLink), sums them in rank order and applies
+ * Adam + Polyak -- the reduced gradient never touches memory; the log_alpha gradient and the loss scalars are averaged the same way
+ * (sacb_dp_get_losses).  Without sacb_dp_connect (or world = 1) it is the plain vectorised apply. */
+int sacb_dp_ipc_handle(sacb_handle h, void *handle_out_64_bytes);
+int sacb_dp_connect(sacb_handle h, int rank, int world, const void *handles_world_x_64_bytes);
+int sacb_dp_exchange_apply(sacb_handle h, int phase);
+int sacb_dp_get_losses(sacb_handle h, float *losses_out);
 /* the handle's private CUDA stream (a cudaStream_t): lets the host enqueue its collective between sacb_dp_backward and
  * sacb_dp_apply on the SAME stream (torch.cuda.ExternalStream), so a data-parallel step needs no host synchronisation. */
 int sacb_get_stream(sacb_handle h, void **stream_out);
