@@ -14,6 +14,10 @@
 #include "tasks.cuh"
 #include "stream.cuh"
 
+#ifndef SACB_NO_OUTLINE
+#define SACB_NO_OUTLINE 1   // outlining measured SLOWER on B200 (persistent 0.265 -> 0.278 ms, one-kernel staged 0.242 -> 0.250): kept as an experiment switch
+#endif
+
 namespace sacb {
 
 // ================================================================================================================
@@ -159,6 +163,24 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
     tc::fence_proxy_async();
 }
 
+// The build that carries every code path (variant 0: the single persistent launch) calls its task bodies through NON-inlined
+// functions, one per task type / GEMM epilogue: each body then gets its own register allocation and schedule (as in the per-stage
+// builds) instead of sharing the union of everybody's live ranges, which put spills into the MMA issue loop and the Adam epilogue.
+template <uint32_t kEpi>
+__device__ __noinline__ void gemm_tile_tc_outlined(const Task &t, const Task *tg, int tile, const AgentBases &bases, int agent, const float *scalars,
+                                                   tc::TcState &st, int *error_flag, bool first_tile, uint64_t seed) {
+    gemm_tile_tc<kEpi>(t, tg, tile, bases, agent, scalars, st, error_flag, first_tile, seed);
+}
+__device__ __noinline__ void task_shadow_outlined(const Task &t, int tile, const Program &P, int agent) { task_shadow(t, tile, P, agent); }
+__device__ __noinline__ void task_gather_outlined(const Task &t, int tile, const Program &P, int agent, const float *scalars, uint64_t seed) { task_gather(t, tile, P, agent, scalars, seed); }
+__device__ __noinline__ void task_sample_outlined(const Task &t, int tile, const Program &P, int agent, const float *scalars, uint64_t seed) { task_sample(t, tile, P, agent, scalars, seed); }
+__device__ __noinline__ void task_target_loss_outlined(const Task &t, int tile, const Program &P, int agent, const float *scalars, float *smem) { task_target_loss(t, tile, P, agent, scalars, smem); }
+__device__ __noinline__ void task_actor_loss_outlined(const Task &t, int tile, const Program &P, int agent, const float *scalars, float *smem) { task_actor_loss(t, tile, P, agent, scalars, smem); }
+__device__ __noinline__ void task_sample_bwd_outlined(const Task &t, int tile, const Program &P, int agent, const float *scalars) { task_sample_bwd(t, tile, P, agent, scalars); }
+__device__ __noinline__ void task_out_adam_outlined(const Task &t, int tile, const Program &P, int agent, const float *scalars, float *smem) { task_out_adam(t, tile, P, agent, scalars, smem); }
+__device__ __noinline__ void task_bias_adam_outlined(const Task &t, int tile, const Program &P, int agent, const float *scalars, float *smem) { task_bias_adam(t, tile, P, agent, scalars, smem); }
+__device__ __noinline__ void task_finish_outlined(const Task &t, const Program &P, int agent, float *scalars, float *smem) { task_finish(t, P, agent, scalars, smem); }
+
 template <int kMath, uint32_t kTypes, uint32_t kEpis>
 __global__ void __launch_bounds__(kThreads, 1)
 sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Stage single, const int stage_begin, const int stage_end, const int tc_setup, const uint64_t seed) {
@@ -250,6 +272,29 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
             }
             float *scalars = resolve(P.scalars, P.bases, agent);
             if (t.type != T_GEMM && st.krank != 0) continue;      // element-wise tasks of a clustered stage run on rank 0 only
+            constexpr bool kOutlined = kTc && kTypes == kAllTypes && kEpis == kAllEpis && !SACB_NO_OUTLINE;
+            if constexpr (kOutlined) {
+                switch (t.type) {
+                    case T_GEMM:
+                        switch (t.epi) {
+                            case EPI_F32: gemm_tile_tc_outlined<tb(EPI_F32)>(t, tg, tile, P.bases, agent, scalars, st, P.error_flag, wi == cl, seed); break;
+                            case EPI_BIAS_RELU: gemm_tile_tc_outlined<tb(EPI_BIAS_RELU)>(t, tg, tile, P.bases, agent, scalars, st, P.error_flag, wi == cl, seed); break;
+                            case EPI_MASK: gemm_tile_tc_outlined<tb(EPI_MASK)>(t, tg, tile, P.bases, agent, scalars, st, P.error_flag, wi == cl, seed); break;
+                            case EPI_SAMPLE: gemm_tile_tc_outlined<tb(EPI_SAMPLE)>(t, tg, tile, P.bases, agent, scalars, st, P.error_flag, wi == cl, seed); break;
+                            default: gemm_tile_tc_outlined<tb(EPI_ADAM)>(t, tg, tile, P.bases, agent, scalars, st, P.error_flag, wi == cl, seed); break;
+                        }
+                        break;
+                    case T_SHADOW: task_shadow_outlined(t, tile, P, agent); break;
+                    case T_GATHER: task_gather_outlined(t, tile, P, agent, scalars, seed); break;
+                    case T_SAMPLE: task_sample_outlined(t, tile, P, agent, scalars, seed); break;
+                    case T_TARGET_LOSS: task_target_loss_outlined(t, tile, P, agent, scalars, s_red); break;
+                    case T_ACTOR_LOSS: task_actor_loss_outlined(t, tile, P, agent, scalars, s_red); break;
+                    case T_SAMPLE_BWD: task_sample_bwd_outlined(t, tile, P, agent, scalars); break;
+                    case T_OUT_ADAM: task_out_adam_outlined(t, tile, P, agent, scalars, s_red); break;
+                    case T_BIAS_ADAM: task_bias_adam_outlined(t, tile, P, agent, scalars, s_red); break;
+                    case T_FINISH: task_finish_outlined(t, P, agent, scalars, s_red); break;
+                }
+            } else
             switch (t.type) {      // only the task types of this build's mask are compiled in
                 case T_GEMM:
                     if constexpr ((kTypes & tb(T_GEMM)) != 0) {

@@ -25,7 +25,7 @@ rng = np.random.RandomState(rank)
 agent.replay_buffer.push_many(rng.standard_normal((CAP, OBS)).astype(np.float32), rng.uniform(-0.4, 0.4, (CAP, ACT)).astype(np.float32),
                               rng.standard_normal(CAP).astype(np.float32), rng.standard_normal((CAP, OBS)).astype(np.float32),
                               (rng.uniform(size=CAP) < 0.01).astype(np.float32))
-dp = hw.distributed.DataParallelSAC(agent)
+dp = hw.distributed.DataParallelSAC(agent, exchange=os.environ.get('SACB_DP_EXCHANGE', 'peer'))
 idx = rng.randint(0, CAP, BL).astype(np.int64)
 out = dp.update_parameters(BL, idx=idx)                 # stages this rank's rows on the device; device-drawn eps
 for _ in range(3):
@@ -45,7 +45,7 @@ if world > 1:
 per = float(t.item()) / steps
 last = dp.update_parameters(BL, staged=True)
 if rank == 0:
-    print(f"DP_BENCH world={world} global_batch={GB} local_batch={BL} ms_per_step={per:.3f} updates_per_s={1e3 / per:.1f} "
+    print(f"DP_BENCH exchange={dp.mode} world={world} global_batch={GB} local_batch={BL} ms_per_step={per:.3f} updates_per_s={1e3 / per:.1f} "
           f"transitions_per_s={GB / per * 1e3:.3e} algorithmic_TFLOPs={5.382e9 * GB / 256 / (per * 1e-3) / 1e12:.1f} losses={last}")
 if world > 1:
     dist.barrier(); dist.destroy_process_group()
