@@ -152,7 +152,7 @@ constexpr uint32_t kPlainEpis = tb(EPI_F32) | tb(EPI_BIAS_RELU) | tb(EPI_MASK);
 constexpr uint32_t kElemTypes = tb(T_SHADOW) | tb(T_GATHER) | tb(T_SAMPLE) | tb(T_TARGET_LOSS) | tb(T_ACTOR_LOSS) | tb(T_SAMPLE_BWD) | tb(T_FINISH);
 #define SACB_KERNEL_VARIANTS(X)                                                                     \
     X(0, kAllTypes, kAllEpis)                                                                       \
-    X(1, tb(T_GEMM) | tb(T_SHADOW), tb(EPI_BIAS_RELU))                                                         \
+    X(1, tb(T_GEMM), tb(EPI_BIAS_RELU))                                                         \
     X(2, tb(T_GEMM), tb(EPI_MASK))                                                                  \
     X(3, tb(T_GEMM), tb(EPI_F32))                                                                   \
     X(4, tb(T_GEMM), kPlainEpis)                                                                    \
@@ -165,9 +165,10 @@ constexpr uint32_t kElemTypes = tb(T_SHADOW) | tb(T_GATHER) | tb(T_SAMPLE) | tb(
     X(11, tb(T_TARGET_LOSS), 0u)                                                                    \
     X(12, tb(T_ACTOR_LOSS), 0u)                                                                     \
     X(13, tb(T_SAMPLE_BWD), 0u)                                                                     \
-    X(14, tb(T_FINISH) | tb(T_SHADOW), 0u)                                                                    \
-    X(15, kElemTypes, 0u)
-constexpr int kNumKernelVariants = 16;
+    X(14, tb(T_FINISH), 0u)                                                                                    \
+    X(15, kElemTypes, 0u)                                                                           \
+    X(16, tb(T_GEMM) | tb(T_SHADOW), tb(EPI_BIAS_RELU))
+constexpr int kNumKernelVariants = 17;
 
 constexpr int kMaxStageTasks = 28;
 struct Stage {

@@ -2,6 +2,7 @@
 // B_local rows with gradients exported (not applied), the host all-reduces the gradient arena over NCCL
 // (torch.distributed), then sacb_dp_apply runs Adam (+ Polyak) on the averaged gradients.
 //   phase 0 = critics (sac_imp.py:101-113), phase 1 = actor + temperature (sac_imp.py:116-135)
+#include <cstdlib>
 #include <cstring>
 
 #include "handle.h"
@@ -61,32 +62,61 @@ __global__ void dp_signal_kernel(PeerSlabs ps, int rank, int world, uint32_t epo
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(ps.flags[p] + rank), "r"(epoch) : "memory");
 }
 
-__global__ void __launch_bounds__(256) dp_reduce_apply_kernel(PeerSlabs ps, int rank, int world, uint32_t epoch, float *w, float *m, float *v, float *wt, int64_t n,
-                                                              int64_t n_first, const float *scalars, int slot_first, int slot_second, float tau, int *error_flag) {
-    if (world > 1) {      // all peers' slabs of this epoch are complete (flags live in MY arena: local polls)
-        if (threadIdx.x < world) {
-            const uint32_t *f = ps.flags[rank] + threadIdx.x;
-            long long t0 = clock64();
-            while (true) {
-                uint32_t x;
-                asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(x) : "l"(f) : "memory");
-                if ((int32_t)(x - epoch) >= 0) break;
-                if (clock64() - t0 > 4000000000ll) { atomicExch(error_flag, 4); break; }      // a peer never arrived: flag it, never hang the box
-            }
+// all peers have announced `epoch` (flags live in MY arena: local polls by the first `world` threads of every CTA)
+__device__ __forceinline__ void dp_wait_peers(const PeerSlabs &ps, int rank, int world, uint32_t epoch, int *error_flag) {
+    if (world <= 1) return;
+    if (threadIdx.x < world) {
+        const uint32_t *f = ps.flags[rank] + threadIdx.x;
+        long long t0 = clock64();
+        while (true) {
+            uint32_t x;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(x) : "l"(f) : "memory");
+            if ((int32_t)(x - epoch) >= 0) break;
+            if (clock64() - t0 > 4000000000ll) { atomicExch(error_flag, 4); break; }      // a peer never arrived: flag it, never hang the box
         }
-        __syncthreads();
     }
+    __syncthreads();
+}
+
+// two-shot exchange, first half (world >= 4): replica r sums slice r of the W slabs in rank order and leaves the MEAN in its own slab
+// (only r itself reads slice r of its own slab in this half, so the reduction is in place).  One-shot reads (W - 1) n bytes per
+// replica over NVLink, two-shot 2 (W - 1) / W n: 7x -> 1.75x the slab at 8 replicas.
+__global__ void __launch_bounds__(256) dp_reduce_scatter_kernel(PeerSlabs ps, int rank, int world, uint32_t epoch, float *mine, int64_t n4, int *error_flag) {
+    dp_wait_peers(ps, rank, world, epoch, error_flag);
+    const int64_t per = (n4 + world - 1) / world, i0 = rank * per, i1 = min(n4, i0 + per);
+    const float inv_w = 1.0f / (float)world;
+    for (int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < i1; i += (int64_t)gridDim.x * blockDim.x) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int p = 0; p < world; p++) {
+            const float4 x = __ldcg(reinterpret_cast<const float4 *>(ps.g[p]) + i);
+            g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+        }
+        g.x *= inv_w; g.y *= inv_w; g.z *= inv_w; g.w *= inv_w;
+        reinterpret_cast<float4 *>(mine)[i] = g;
+    }
+}
+
+// gathered != 0: second half of the two-shot exchange -- element i is already the replica mean, held by replica i / ceil(n4 / W)
+__global__ void __launch_bounds__(256) dp_reduce_apply_kernel(PeerSlabs ps, int rank, int world, uint32_t epoch, float *w, float *m, float *v, float *wt, int64_t n,
+                                                              int64_t n_first, const float *scalars, int slot_first, int slot_second, float tau, int *error_flag,
+                                                              int gathered) {
+    dp_wait_peers(ps, rank, world, epoch, error_flag);
+    const int64_t per = (n / 4 + world - 1) / world;
     float ss[2], ibs[2];
     { float a, b; adam_factors_cached(scalars, slot_first, a, b); ss[0] = a; ibs[0] = 1.0f / b; adam_factors_cached(scalars, slot_second, a, b); ss[1] = a; ibs[1] = 1.0f / b; }
     const float inv_w = 1.0f / (float)world;
     const int64_t n4 = n / 4;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
         float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int p = 0; p < world; p++) {      // rank order on every replica
-            const float4 x = __ldcg(reinterpret_cast<const float4 *>(ps.g[p]) + i);
-            g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+        if (gathered) {
+            g = __ldcg(reinterpret_cast<const float4 *>(ps.g[i / per]) + i);
+        } else {
+            for (int p = 0; p < world; p++) {      // rank order on every replica
+                const float4 x = __ldcg(reinterpret_cast<const float4 *>(ps.g[p]) + i);
+                g.x += x.x; g.y += x.y; g.z += x.z; g.w += x.w;
+            }
+            g.x *= inv_w; g.y *= inv_w; g.z *= inv_w; g.w *= inv_w;
         }
-        g.x *= inv_w; g.y *= inv_w; g.z *= inv_w; g.w *= inv_w;
         const int h = (i * 4 >= n_first) ? 1 : 0;
         float4 W4 = reinterpret_cast<float4 *>(w)[i], M4 = reinterpret_cast<float4 *>(m)[i], V4 = reinterpret_cast<float4 *>(v)[i];
         float4 T4 = wt ? reinterpret_cast<float4 *>(wt)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -188,16 +218,25 @@ extern "C" int sacb_dp_exchange_apply(sacb_handle h, int phase) {
         gsc.g[p] = base ? base + L.grad_scalars : nullptr; gsc.flags[p] = nullptr;
         lss.g[p] = base ? base + L.scalars + SC_LOSS_Q1 : nullptr; lss.flags[p] = nullptr;
     }
-    const uint32_t epoch = ++h->dp_epoch;
+    uint32_t epoch = ++h->dp_epoch;
     if (W > 1) { dp_signal_kernel<<<1, 32, 0, h->stream>>>(ps, r, W, epoch); h->kernel_launches++; }
     h->shadows_valid = false;      // fp32 weights only: the next program re-derives the shadows
     const int grid = 2 * h->sm_count;
+    const int64_t n = phase == 0 ? 2 * L.q.size : L.pol.size;
+    static const int two_shot_min = getenv("SACB_DP_TWO_SHOT_MIN") ? atoi(getenv("SACB_DP_TWO_SHOT_MIN")) : 4;
+    const int gathered = W >= two_shot_min ? 1 : 0;
+    if (gathered) {      // reduce-scatter in place, second barrier, then the gather rides in the apply kernel
+        dp_reduce_scatter_kernel<<<h->sm_count, 256, 0, h->stream>>>(ps, r, W, epoch, ar + goff, n / 4, h->error_flag);
+        epoch = ++h->dp_epoch;
+        dp_signal_kernel<<<1, 32, 0, h->stream>>>(ps, r, W, epoch);
+        h->kernel_launches += 2;
+    }
     if (phase == 0)
-        dp_reduce_apply_kernel<<<grid, 256, 0, h->stream>>>(ps, r, W, epoch, ar + L.param[1], ar + L.adam_m[1], ar + L.adam_v[1], ar + L.param[3], 2 * L.q.size, L.q.size, sc,
-                                                            SC_STEP_Q1, SC_STEP_Q2, h->cfg.tau, h->error_flag);
+        dp_reduce_apply_kernel<<<grid, 256, 0, h->stream>>>(ps, r, W, epoch, ar + L.param[1], ar + L.adam_m[1], ar + L.adam_v[1], ar + L.param[3], n, L.q.size, sc,
+                                                            SC_STEP_Q1, SC_STEP_Q2, h->cfg.tau, h->error_flag, gathered);
     else
-        dp_reduce_apply_kernel<<<grid, 256, 0, h->stream>>>(ps, r, W, epoch, ar + L.param[0], ar + L.adam_m[0], ar + L.adam_v[0], nullptr, L.pol.size, L.pol.size, sc,
-                                                            SC_STEP_POLICY, SC_STEP_POLICY, h->cfg.tau, h->error_flag);
+        dp_reduce_apply_kernel<<<grid, 256, 0, h->stream>>>(ps, r, W, epoch, ar + L.param[0], ar + L.adam_m[0], ar + L.adam_v[0], nullptr, n, L.pol.size, sc,
+                                                            SC_STEP_POLICY, SC_STEP_POLICY, h->cfg.tau, h->error_flag, gathered);
     dp_finish_peers_kernel<<<1, 32, 0, h->stream>>>(sc, gsc, lss, W, phase, h->cfg.auto_entropy, h->adam_table);
     h->kernel_launches += 2;
     SACB_CUDA(cudaGetLastError());

@@ -473,6 +473,7 @@ struct Builder {
     // Throughput programs are bound by HBM traffic, not by stage latency: there every Adam epilogue writes the shadows of what it
     // steps (policy and Polyak targets included) straight from its registers -- no extra pass over the fp32 weights, no extra stages.
     bool epilogue_shadows() const { return stream && keep_resident(); }
+    int loss_rows() const { return stream ? kLossRowsMax : kLossRows; }      // batch rows per tile of the two loss tasks (tasks.cuh)
     bool task_shadows() const { return !stream && keep_resident(); }
     bool exporting() const { return key.export_grads || key.dp_phase >= 0; }
 
@@ -491,7 +492,9 @@ struct Builder {
     Task epi_adam(int net, int layer) {
         const NetLayout &n = net == 0 ? L.pol : L.q;
         Task t = blank(T_GEMM); t.epi = EPI_ADAM; t.adam = adam_args(net, n.w[layer]);
-        if (net != 0 || epilogue_shadows()) t.adam.shadow = wsh(net, layer).ref;
+        // (latency programs: the two policy layers stepped by the LAST backward stage refresh their shadows in the epilogue as well:
+        //  +1.2 us on that stage, against +3 us for shadow tasks next to the single-CTA finish stage)
+        if (net != 0 || epilogue_shadows() || (task_shadows() && layer <= 1)) t.adam.shadow = wsh(net, layer).ref;
         if (net != 0 && layer == 0) { t.adam.shadow2 = wsh_act(net).ref; t.adam.shadow2_col0 = L.obs; }
         if (net != 0 && epilogue_shadows()) t.adam.shadow_t = wsh(net + 2, layer).ref;
         return t;
@@ -562,10 +565,19 @@ struct Builder {
 
     // Throughput programs (stages with many more tiles than SMs): every GEMM task takes the stream kernel's tile, 128 rows x 128
     // columns (64 where the output is narrower than 96 columns: policy heads, dL/da).
+    // A stage that would hold fewer than kStreamWideMin x SMs tiles of 128 x 128 keeps 64-column tiles: twice the tiles for the
+    // round-robin over the resident CTAs (mid-size batches: better wave quantisation and more tiles to overlap per CTA).
     std::vector<std::pair<int, int>> stream_tile_shapes() const {
+        static const int wide_min = getenv("SACB_STREAM_WIDE_MIN") ? atoi(getenv("SACB_STREAM_WIDE_MIN")) : 3;
         std::vector<std::pair<int, int>> out(tasks.size(), {0, 0});
-        for (size_t k = 0; k < tasks.size(); k++)
-            if (tasks[k].type == T_GEMM) out[k] = {stream::kBM, tasks[k].N >= 96 ? stream::kBN : 64};
+        for (size_t si = 0; si < stages.size(); si++) {
+            int wide_tiles = 0;
+            for (int k = stages[si].task_begin; k < stages[si].task_end; k++)
+                if (tasks[k].type == T_GEMM) wide_tiles += cdiv(tasks[k].M, stream::kBM) * cdiv(tasks[k].N, tasks[k].N >= 96 ? stream::kBN : 64) * h->cfg.n_agents;
+            const bool wide = wide_tiles >= wide_min * h->sm_count;
+            for (int k = stages[si].task_begin; k < stages[si].task_end; k++)
+                if (tasks[k].type == T_GEMM) out[k] = {stream::kBM, (wide && tasks[k].N >= 96) ? stream::kBN : 64};
+        }
         return out;
     }
     // ... and a stage that mixes GEMM tasks with column-sum / element-wise tasks is cut in two (the tasks of a stage are independent
@@ -679,8 +691,8 @@ struct Builder {
                 t.p[12] = W(L.r); t.p[13] = W(L.d); t.p[14] = W(L.logp); t.p[15] = key.use_isw ? W(L.isw) : null_ref();
                 t.p[16] = W(L.y); t.p[17] = W(L.dq[0]); t.p[18] = W(L.dq[1]); t.p[19] = W(L.td);
                 t.p[22] = W(L.loss_part);
-                t.i[0] = B; t.i[1] = H; t.f[0] = h->cfg.gamma;
-                add(t, cdiv(B, kLossRows));
+                t.i[0] = B; t.i[1] = H; t.i[2] = loss_rows(); t.f[0] = h->cfg.gamma;
+                add(t, cdiv(B, loss_rows()));
             }
             // ---- critic backward --------------------------------------------------------------------------------------
             //   stage s (1..nh): dX of layer l = nh-s (0-based, only while l >= 1) ; dW/db of layer l+1 ; last stage: dW/db of layer 0
@@ -730,8 +742,8 @@ struct Builder {
                 t.p[2] = A(L.param[1] + Q.w_out); t.p[3] = A(L.param[2] + Q.w_out);
                 t.p[4] = A(L.param[1] + Q.b_out); t.p[5] = A(L.param[2] + Q.b_out);
                 t.p[6] = W(L.logp + B); t.p[9] = W(L.aloss_part);
-                t.i[0] = B; t.i[1] = H; t.f[0] = -(float)act;
-                add(t, cdiv(B, kLossRows));
+                t.i[0] = B; t.i[1] = H; t.i[2] = loss_rows(); t.f[0] = -(float)act;
+                add(t, cdiv(B, loss_rows()));
             }
             // ---- dL/da through both critics (input gradients only: the Q weights are constants here, quirk Q2) -------
             for (int s = 1; s <= nh; s++) {
@@ -794,13 +806,10 @@ struct Builder {
             t.p[2] = exporting() ? A(L.grad_scalars) : null_ref();
             t.p[3] = A(L.loss_hist);
             t.i[0] = ap; t.i[1] = ap; t.i[2] = ap; t.i[3] = ap && h->cfg.auto_entropy; t.i[4] = ap;
-            t.i[5] = cdiv(B, kLossRows); t.i[6] = h->cfg.auto_entropy; t.i[7] = ap;
+            t.i[5] = cdiv(B, loss_rows()) * (loss_rows() / kLossRows); t.i[6] = h->cfg.auto_entropy; t.i[7] = ap;
             t.f[0] = h->cfg.lr; t.f[1] = (float)B;
             add(t, 1);
-            if (actor && task_shadows()) {      // the last policy-backward stage stepped layers 1 and 0
-                shadow_task(0, P.w[1], wsh(0, 1), P.in_of(1));
-                shadow_task(0, P.w[0], wsh(0, 0), P.in_of(0));
-            }
+
         }
     }
 

@@ -7,7 +7,6 @@
 namespace sacb {
 
 constexpr int kShadowRows = 64;      // weight rows per T_SHADOW tile (4 per warp)
-constexpr int kLossRows = 4;         // batch rows per T_TARGET_LOSS / T_ACTOR_LOSS tile (4 warps per row)
 
 // T_SHADOW: p0 = fp32 weight matrix (row stride i3) ; pm0 = shadow PM of its columns [i2, i2+i1) ; i0=rows i1=cols.  One warp per row.
 // Runs at the start of every step, so weights written from outside the update (load_state_dict through the
@@ -195,26 +194,31 @@ __device__ __forceinline__ void write_dh_last(const Pm &dh, const Pm &h, const f
     }
 }
 
-// T_TARGET_LOSS: Bellman target + critic MSE terms + dL/dq   (sac_imp.py:92-105).  kLossRows rows per tile, 4 warps per row:
-// warp k of a row forms the output-layer dot product of net k, one thread per row then does the scalar arithmetic,
-// warps 2,3 finally write dL/dh of the last hidden layer of q1,q2.
+// The two loss tasks work on R = Task::i[2] batch rows per tile: R = 4 (latency programs: 4 warps per row, one per network, 64
+// tiles at B = 256) or R = 16 (throughput programs: a warp takes one network for 4 rows, all of their loads in flight together;
+// four times fewer dependent round trips per row).  Warp w handles the pairs (row, net) = (w / 4 + 4 j, w % 4), j < R / 4.
+constexpr int kLossRows = 4, kLossRowsMax = 16;
+
+// T_TARGET_LOSS: Bellman target + critic MSE terms + dL/dq   (sac_imp.py:92-105).
+// Warp (row, k) forms the output-layer dot product of net k for its rows, one thread per row then does the scalar arithmetic,
+// the warps of nets 2, 3 (q1, q2) finally write dL/dh of the last hidden layer.
 //   pm0,pm1 = last hidden activations of q1_target,q2_target on (s2,a2) [B,H] ; pm2,pm3 = of q1,q2 on (s,a)
 //   p4..p7 = output-layer weights [H] of q1t,q2t,q1,q2 ; p8..p11 = their biases [1]
 //   p12=r p13=d p14=logp_next p15=is_weights(null -> 1) ; outputs p16=y p17=dq1 p18=dq2 p19=td (|q1-y|)
 //   pm4,pm5 = dL/dh of the last hidden layer of q1,q2 [B,H] (consumed by the critic backward GEMMs)
 //   p[22] = per-tile partial sums of w*(q-y)^2 [n_tiles, 2] (summed in tile order by T_FINISH: deterministic)
-//   i0=B i1=H ; f0=gamma
+//   i0=B i1=H i2=R ; f0=gamma
 __device__ __forceinline__ void task_target_loss(const Task &t, int tile, const Program &P, int agent, const float *scalars, float *smem) {
-    const int B = t.i[0], H = t.i[1];
+    const int B = t.i[0], H = t.i[1], R = t.i[2], nj = R >> 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rt = warp >> 2, k = warp & 3, b = tile * kLossRows + rt;
-    float *sq = smem, *sd = smem + 16, *sl = smem + 24;      // dots [4 rows][4 nets], dq [4][2], loss terms [4][2]
+    const int k = warp & 3, r_w = warp >> 2;
+    float *sq = smem, *sd = smem + 4 * kLossRowsMax, *sl = sd + 2 * kLossRowsMax;      // dots [R][4 nets], dq [R][2], loss terms [R][2]
     const Pm h = resolve_pm(t.pm[k], P.bases, agent);
     const float *w = resolve(t.p[4 + k], P.bases, agent);
     // the row's scalars are fetched by its scalar thread BEFORE the dot products, so their latency hides behind them
     float pre_bias[4] = {0.f, 0.f, 0.f, 0.f}, pre_alpha = 0.f, pre_logp = 0.f, pre_r = 0.f, pre_d = 0.f, pre_w = 1.f;
-    if (threadIdx.x < kLossRows && tile * kLossRows + (int)threadIdx.x < B) {
-        const int br = tile * kLossRows + threadIdx.x;
+    if ((int)threadIdx.x < R && tile * R + (int)threadIdx.x < B) {
+        const int br = tile * R + threadIdx.x;
         for (int j = 0; j < 4; j++) pre_bias[j] = ldcg(resolve(t.p[8 + j], P.bases, agent));
         const int n_upd = __float_as_int(ldcg(scalars + SC_N_UPDATES));
         pre_alpha = ldcg(scalars + SC_ALPHA0 + (n_upd & 1));
@@ -224,11 +228,15 @@ __device__ __forceinline__ void task_target_loss(const Task &t, int tile, const 
         pre_d = ldcg(resolve(t.p[13], P.bases, agent) + br);
         if (isw) pre_w = ldcg(isw + br);
     }
-    const float q = b < B ? row_dot(h, w, b, H, lane) : 0.f;
-    if (lane == 0) sq[warp] = q;
+#pragma unroll 4
+    for (int j = 0; j < nj; j++) {
+        const int r = r_w + 4 * j, b = tile * R + r;
+        const float q = b < B ? row_dot(h, w, b, H, lane) : 0.f;
+        if (lane == 0) sq[r * 4 + k] = q;
+    }
     __syncthreads();
-    if (threadIdx.x < kLossRows) {
-        const int r = threadIdx.x, br = tile * kLossRows + r;
+    if ((int)threadIdx.x < R) {
+        const int r = threadIdx.x, br = tile * R + r;
         float l1 = 0.f, l2 = 0.f, dq1 = 0.f, dq2 = 0.f;
         if (br < B) {
             float qq[4];
@@ -250,41 +258,55 @@ __device__ __forceinline__ void task_target_loss(const Task &t, int tile, const 
         sd[2 * r] = dq1; sd[2 * r + 1] = dq2; sl[2 * r] = l1; sl[2 * r + 1] = l2;
     }
     __syncthreads();
-    if (b < B && k >= 2) write_dh_last(resolve_pm(t.pm[2 + k], P.bases, agent), h, w, b, H, lane, sd[2 * rt + (k - 2)]);
-    if (threadIdx.x == 0) {
+    if (k >= 2) {
+        const Pm dh = resolve_pm(t.pm[2 + k], P.bases, agent);
+#pragma unroll 4
+        for (int j = 0; j < nj; j++) {
+            const int r = r_w + 4 * j, b = tile * R + r;
+            if (b < B) write_dh_last(dh, h, w, b, H, lane, sd[2 * r + (k - 2)]);
+        }
+    }
+    if ((int)threadIdx.x < nj) {      // partials per group of kLossRows rows, whatever R is: T_FINISH adds the same sequence of numbers
+        const int sub = threadIdx.x;
         float s1 = 0.f, s2 = 0.f;
-        for (int i = 0; i < kLossRows; i++) { s1 += sl[2 * i]; s2 += sl[2 * i + 1]; }
+        for (int i = kLossRows * sub; i < kLossRows * (sub + 1); i++) { s1 += sl[2 * i]; s2 += sl[2 * i + 1]; }
         float *part = resolve(t.p[22], P.bases, agent);
-        part[2 * tile] = s1; part[2 * tile + 1] = s2;
+        part[2 * (tile * nj + sub)] = s1; part[2 * (tile * nj + sub) + 1] = s2;
     }
     __syncthreads();
 }
 
-// T_ACTOR_LOSS: policy-loss terms and min-Q routing (sac_imp.py:117-121).  Same tiling: warps 0,1 of a row form the two
-// dot products, warps 2,3 write dL/dh of the last hidden layer of q1,q2.
+// T_ACTOR_LOSS: policy-loss terms and min-Q routing (sac_imp.py:117-121).  Same tiling: the warps of "nets" 0, 1 form the two dot
+// products, those of 2, 3 write dL/dh of the last hidden layer of q1, q2.
 //   pm0,pm1 = last hidden activations of q1,q2 on (s, a_new) ; p2,p3 = output weights ; p4,p5 = output biases
 //   p6=logp_cur ; pm2,pm3 = dL/dh of the last hidden layer of q1,q2 (the Q weights are constants here, quirk Q2)
 //   p9 = per-tile partials [n_tiles,2]: sum(alpha*logp - minq), sum(logp + target_entropy)
-//   i0=B i1=H ; f0=target_entropy
+//   i0=B i1=H i2=R ; f0=target_entropy
 __device__ __forceinline__ void task_actor_loss(const Task &t, int tile, const Program &P, int agent, const float *scalars, float *smem) {
-    const int B = t.i[0], H = t.i[1];
+    const int B = t.i[0], H = t.i[1], R = t.i[2], nj = R >> 2;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int rt = warp >> 2, k = warp & 3, b = tile * kLossRows + rt;
-    float *sq = smem, *sd = smem + 16, *sl = smem + 24;
+    const int k = warp & 3, r_w = warp >> 2;
+    float *sq = smem, *sd = smem + 4 * kLossRowsMax, *sl = sd + 2 * kLossRowsMax;
     const Pm h = resolve_pm(t.pm[k & 1], P.bases, agent);
     const float *w = resolve(t.p[2 + (k & 1)], P.bases, agent);
     float pre_b1 = 0.f, pre_b2 = 0.f, pre_alpha = 0.f, pre_logp = 0.f;      // fetched before the dot products (latency hidden)
-    if (threadIdx.x < kLossRows && tile * kLossRows + (int)threadIdx.x < B) {
+    if ((int)threadIdx.x < R && tile * R + (int)threadIdx.x < B) {
         pre_b1 = ldcg(resolve(t.p[4], P.bases, agent)); pre_b2 = ldcg(resolve(t.p[5], P.bases, agent));
         const int n_upd = __float_as_int(ldcg(scalars + SC_N_UPDATES));
         pre_alpha = ldcg(scalars + SC_ALPHA0 + (n_upd & 1));
-        pre_logp = ldcg(resolve(t.p[6], P.bases, agent) + tile * kLossRows + threadIdx.x);
+        pre_logp = ldcg(resolve(t.p[6], P.bases, agent) + tile * R + threadIdx.x);
     }
-    const float q = (b < B && k < 2) ? row_dot(h, w, b, H, lane) : 0.f;
-    if (lane == 0) sq[warp] = q;
+    if (k < 2) {
+#pragma unroll 4
+        for (int j = 0; j < nj; j++) {
+            const int r = r_w + 4 * j, b = tile * R + r;
+            const float q = b < B ? row_dot(h, w, b, H, lane) : 0.f;
+            if (lane == 0) sq[r * 4 + k] = q;
+        }
+    }
     __syncthreads();
-    if (threadIdx.x < kLossRows) {
-        const int r = threadIdx.x, br = tile * kLossRows + r;
+    if ((int)threadIdx.x < R) {
+        const int r = threadIdx.x, br = tile * R + r;
         float pl = 0.f, ent = 0.f, d1 = 0.f, d2 = 0.f;
         if (br < B) {
             const float q1 = sq[r * 4] + pre_b1, q2 = sq[r * 4 + 1] + pre_b2;
@@ -299,12 +321,20 @@ __device__ __forceinline__ void task_actor_loss(const Task &t, int tile, const P
         sd[2 * r] = d1; sd[2 * r + 1] = d2; sl[2 * r] = pl; sl[2 * r + 1] = ent;
     }
     __syncthreads();
-    if (b < B && k >= 2) write_dh_last(resolve_pm(t.pm[k], P.bases, agent), h, w, b, H, lane, sd[2 * rt + (k - 2)]);
-    if (threadIdx.x == 0) {
+    if (k >= 2) {
+        const Pm dh = resolve_pm(t.pm[k], P.bases, agent);
+#pragma unroll 4
+        for (int j = 0; j < nj; j++) {
+            const int r = r_w + 4 * j, b = tile * R + r;
+            if (b < B) write_dh_last(dh, h, w, b, H, lane, sd[2 * r + (k - 2)]);
+        }
+    }
+    if ((int)threadIdx.x < nj) {
+        const int sub = threadIdx.x;
         float s1 = 0.f, s2 = 0.f;
-        for (int i = 0; i < kLossRows; i++) { s1 += sl[2 * i]; s2 += sl[2 * i + 1]; }
+        for (int i = kLossRows * sub; i < kLossRows * (sub + 1); i++) { s1 += sl[2 * i]; s2 += sl[2 * i + 1]; }
         float *part = resolve(t.p[9], P.bases, agent);
-        part[2 * tile] = s1; part[2 * tile + 1] = s2;
+        part[2 * (tile * nj + sub)] = s1; part[2 * (tile * nj + sub) + 1] = s2;
     }
     __syncthreads();
 }
