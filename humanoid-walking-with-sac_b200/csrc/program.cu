@@ -1083,6 +1083,9 @@ extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap
         after_update_launch(h, k0);
     }
     ProgramKey key = update_key(h, (int)B, 0, 0, 1, 0);
+    if (getenv("SACB_TIME_DP_PHASE")) {      // profile the backward half of a data-parallel phase instead (gradients exported, nothing applied)
+        key = ProgramKey{(int)B, 0, 1, 1, 0, atoi(getenv("SACB_TIME_DP_PHASE"))};
+    }
     rc = get_program(h, key, &p);
     if (rc) return rc;
     const bool trace = getenv("SACB_TRACE") != nullptr;

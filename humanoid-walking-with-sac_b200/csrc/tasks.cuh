@@ -194,6 +194,62 @@ __device__ __forceinline__ void write_dh_last(const Pm &dh, const Pm &h, const f
     }
 }
 
+// four rows at once (throughput programs): the loads of all four rows of a trip are in flight together, the weights are read once
+__device__ __forceinline__ void row_dot4(const Pm &h, const float *w, const int64_t (&row)[4], const bool (&on)[4], int n, int lane, float (&out)[4]) {
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int j = lane * 8; j < n; j += 256) {
+        uint4 hh[4], ll[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            hh[i] = ll[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (on[i]) {
+                const __nv_bfloat16 *q = h.hi + row[i] * h.ld + j;
+                hh[i] = __ldcg(reinterpret_cast<const uint4 *>(q));
+                ll[i] = __ldcg(reinterpret_cast<const uint4 *>(q + h.plane));
+            }
+        }
+        const float4 w0 = __ldcg(reinterpret_cast<const float4 *>(w + j)), w1 = __ldcg(reinterpret_cast<const float4 *>(w + j + 4));
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t hw[4] = {hh[i].x, hh[i].y, hh[i].z, hh[i].w}, lw[4] = {ll[i].x, ll[i].y, ll[i].z, ll[i].w};
+            float hv[8];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {      // same value reconstruction and the same order of the 8 products as row_dot / pm_load8
+                hv[2 * c] = bf16_bits_to_float(hw[c] & 0xFFFFu) + bf16_bits_to_float(lw[c] & 0xFFFFu);
+                hv[2 * c + 1] = bf16_bits_to_float(hw[c] >> 16) + bf16_bits_to_float(lw[c] >> 16);
+            }
+            s[i] += hv[0] * wv[0] + hv[1] * wv[1] + hv[2] * wv[2] + hv[3] * wv[3] + hv[4] * wv[4] + hv[5] * wv[5] + hv[6] * wv[6] + hv[7] * wv[7];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) out[i] = warp_sum(s[i]);
+}
+__device__ __forceinline__ void write_dh_last4(const Pm &dh, const Pm &h, const float *w_out, const int64_t (&row)[4], const bool (&on)[4], int n, int lane, const float (&dq)[4]) {
+    for (int j = lane * 8; j < n; j += 256) {
+        uint4 hh[4];
+#pragma unroll
+        for (int i = 0; i < 4; i++) hh[i] = on[i] ? __ldcg(reinterpret_cast<const uint4 *>(h.hi + row[i] * h.ld + j)) : make_uint4(0u, 0u, 0u, 0u);
+        const float4 w0 = __ldcg(reinterpret_cast<const float4 *>(w_out + j)), w1 = __ldcg(reinterpret_cast<const float4 *>(w_out + j + 4));
+        const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            if (!on[i]) continue;
+            const uint32_t hw[4] = {hh[i].x, hh[i].y, hh[i].z, hh[i].w};
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const float g0 = bf16_bits_to_float(hw[c] & 0xFFFFu) > 0.f ? dq[i] * wv[2 * c] : 0.f;
+                const float g1 = bf16_bits_to_float(hw[c] >> 16) > 0.f ? dq[i] * wv[2 * c + 1] : 0.f;
+                split_pack2(g0, g1, hi[c], lo[c]);
+            }
+            __nv_bfloat16 *q = dh.hi + row[i] * dh.ld + j;
+            *reinterpret_cast<uint4 *>(q) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4 *>(q + dh.plane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    }
+}
+
 // The two loss tasks work on R = Task::i[2] batch rows per tile: R = 4 (latency programs: 4 warps per row, one per network, 64
 // tiles at B = 256) or R = 16 (throughput programs: a warp takes one network for 4 rows, all of their loads in flight together;
 // four times fewer dependent round trips per row).  Warp w handles the pairs (row, net) = (w / 4 + 4 j, w % 4), j < R / 4.
@@ -228,11 +284,18 @@ __device__ __forceinline__ void task_target_loss(const Task &t, int tile, const 
         pre_d = ldcg(resolve(t.p[13], P.bases, agent) + br);
         if (isw) pre_w = ldcg(isw + br);
     }
-#pragma unroll 4
-    for (int j = 0; j < nj; j++) {
-        const int r = r_w + 4 * j, b = tile * R + r;
+    int64_t rows4[4];
+    bool on4[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { rows4[j] = tile * R + r_w + 4 * j; on4[j] = j < nj && rows4[j] < B; }
+    if (nj == 4) {
+        float q4[4];
+        row_dot4(h, w, rows4, on4, H, lane, q4);
+        if (lane == 0) for (int j = 0; j < 4; j++) sq[(r_w + 4 * j) * 4 + k] = on4[j] ? q4[j] : 0.f;
+    } else {
+        const int b = tile * R + r_w;
         const float q = b < B ? row_dot(h, w, b, H, lane) : 0.f;
-        if (lane == 0) sq[r * 4 + k] = q;
+        if (lane == 0) sq[r_w * 4 + k] = q;
     }
     __syncthreads();
     if ((int)threadIdx.x < R) {
@@ -260,10 +323,12 @@ __device__ __forceinline__ void task_target_loss(const Task &t, int tile, const 
     __syncthreads();
     if (k >= 2) {
         const Pm dh = resolve_pm(t.pm[2 + k], P.bases, agent);
-#pragma unroll 4
-        for (int j = 0; j < nj; j++) {
-            const int r = r_w + 4 * j, b = tile * R + r;
-            if (b < B) write_dh_last(dh, h, w, b, H, lane, sd[2 * r + (k - 2)]);
+        if (nj == 4) {
+            float dq4[4];
+            for (int j = 0; j < 4; j++) dq4[j] = sd[2 * (r_w + 4 * j) + (k - 2)];
+            write_dh_last4(dh, h, w, rows4, on4, H, lane, dq4);
+        } else if (on4[0]) {
+            write_dh_last(dh, h, w, rows4[0], H, lane, sd[2 * r_w + (k - 2)]);
         }
     }
     if ((int)threadIdx.x < nj) {      // partials per group of kLossRows rows, whatever R is: T_FINISH adds the same sequence of numbers
@@ -296,12 +361,19 @@ __device__ __forceinline__ void task_actor_loss(const Task &t, int tile, const P
         pre_alpha = ldcg(scalars + SC_ALPHA0 + (n_upd & 1));
         pre_logp = ldcg(resolve(t.p[6], P.bases, agent) + tile * R + threadIdx.x);
     }
+    int64_t rows4[4];
+    bool on4[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) { rows4[j] = tile * R + r_w + 4 * j; on4[j] = j < nj && rows4[j] < B; }
     if (k < 2) {
-#pragma unroll 4
-        for (int j = 0; j < nj; j++) {
-            const int r = r_w + 4 * j, b = tile * R + r;
+        if (nj == 4) {
+            float q4[4];
+            row_dot4(h, w, rows4, on4, H, lane, q4);
+            if (lane == 0) for (int j = 0; j < 4; j++) sq[(r_w + 4 * j) * 4 + k] = on4[j] ? q4[j] : 0.f;
+        } else {
+            const int b = tile * R + r_w;
             const float q = b < B ? row_dot(h, w, b, H, lane) : 0.f;
-            if (lane == 0) sq[r * 4 + k] = q;
+            if (lane == 0) sq[r_w * 4 + k] = q;
         }
     }
     __syncthreads();
@@ -323,10 +395,12 @@ __device__ __forceinline__ void task_actor_loss(const Task &t, int tile, const P
     __syncthreads();
     if (k >= 2) {
         const Pm dh = resolve_pm(t.pm[k], P.bases, agent);
-#pragma unroll 4
-        for (int j = 0; j < nj; j++) {
-            const int r = r_w + 4 * j, b = tile * R + r;
-            if (b < B) write_dh_last(dh, h, w, b, H, lane, sd[2 * r + (k - 2)]);
+        if (nj == 4) {
+            float dq4[4];
+            for (int j = 0; j < 4; j++) dq4[j] = sd[2 * (r_w + 4 * j) + (k - 2)];
+            write_dh_last4(dh, h, w, rows4, on4, H, lane, dq4);
+        } else if (on4[0]) {
+            write_dh_last(dh, h, w, rows4[0], H, lane, sd[2 * r_w + (k - 2)]);
         }
     }
     if ((int)threadIdx.x < nj) {
@@ -371,6 +445,15 @@ __device__ __forceinline__ float colsum64(int r0, int r1, float *smem, F load8) 
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[j] = 0.f;
     int b = r0 + rl;
+    for (; b + 7 * 64 < r1; b += 8 * 64) {      // long batches: 8 rows (16 loads of 16 bytes) in flight per thread
+        float v[8][8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) load8(b + 64 * u, cg * 8, v[u]);
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] += v[u][j];
+    }
     for (; b + 3 * 64 < r1; b += 4 * 64) {
         float v[4][8];
 #pragma unroll
@@ -515,7 +598,18 @@ __device__ __forceinline__ void task_finish(const Task &t, const Program &P, int
     if ((int)threadIdx.x < kRuns) {
         const int c = cdiv(nt, kRuns), i0 = threadIdx.x * c, i1 = min(nt, i0 + c);
         float a1 = 0.f, a2 = 0.f, b1 = 0.f, b2 = 0.f;
-        for (int i = i0; i < i1; i++) {
+        int i = i0;
+        for (; i + 7 < i1; i += 8) {      // large batches: eight partial pairs in flight (same order of the additions)
+            float2 c8[8], d8[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                c8[u] = cp ? __ldcg(reinterpret_cast<const float2 *>(cp) + i + u) : make_float2(0.f, 0.f);
+                d8[u] = ap ? __ldcg(reinterpret_cast<const float2 *>(ap) + i + u) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < 8; u++) { if (cp) { a1 += c8[u].x; a2 += c8[u].y; } if (ap) { b1 += d8[u].x; b2 += d8[u].y; } }
+        }
+        for (; i < i1; i++) {
             if (cp) { a1 += ldcg(cp + 2 * i); a2 += ldcg(cp + 2 * i + 1); }
             if (ap) { b1 += ldcg(ap + 2 * i); b2 += ldcg(ap + 2 * i + 1); }
         }
