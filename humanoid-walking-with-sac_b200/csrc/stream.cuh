@@ -227,8 +227,40 @@ __device__ __forceinline__ void epilogue_tile(const EpiR &epi, float *Cs, uint32
     const int ew = et >> 5, lane = et & 31, q = ew & 3, hcol = (ew >> 2) * 32;
     const int passes = r.bn > 64 ? 2 : 1;
     float aux[8][4];
-    if (EPI == EPI_ADAM) { for (int p = 0; p < passes; p++) adam_prefetch(epi, r.m0, r.n0 + 64 * p, et); }
-    else plain_aux<EPI>(epi, r.m0, r.n0, et, aux);
+    uint32_t mask_bits[2] = {0u, 0u};
+    if (EPI == EPI_ADAM) {
+        for (int p = 0; p < passes; p++) adam_prefetch(epi, r.m0, r.n0 + 64 * p, et);
+    } else if (EPI == EPI_MASK) {
+        // the ReLU-mask operand (sign of the stored activation) of BOTH passes is fetched now and kept as one bit per element:
+        // no global load sits between the accumulator and the stores any more (the mask loads paced the dX stages: an epilogue
+        // whose second pass started with an exposed L2 / DRAM round trip)
+        // (all 16 loads of a thread are issued back to back from clamped addresses and only then unpacked: written with the
+        //  row / column guards around each load the compiler serialised them, eight L2 round trips per pass -- ncu source view)
+        const int c4 = (et & 15) * 4, r0 = et >> 4;
+        uint2 raw[2][8];
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int row = min(r.m0 + r0 + 16 * i, epi.M - 1), col = min(r.n0 + 64 * p + c4, epi.N - 4);      // EPI_MASK outputs are hidden-width: N % 8 == 0
+                raw[p][i] = (p < passes) ? __ldcg(reinterpret_cast<const uint2 *>(epi.mask.hi + (int64_t)row * epi.mask.ld + col)) : make_uint2(0u, 0u);
+            }
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const bool ok = p < passes && r.m0 + r0 + 16 * i < epi.M && r.n0 + 64 * p + c4 < epi.N;
+                const uint32_t w[2] = {raw[p][i].x, raw[p][i].y};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t h = (w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;      // bf16 bits of the stored activation: > 0 <=> sign clear, not zero
+                    const bool pos = ok && (h & 0x8000u) == 0u && (h & 0x7FFFu) != 0u && (h & 0x7FFFu) <= 0x7F80u;
+                    mask_bits[p] |= (pos ? 1u : 0u) << (4 * i + j);
+                }
+            }
+    } else {
+        plain_aux<EPI>(epi, r.m0, r.n0, et, aux);
+    }
     tc::mbar_wait(acc_full, parity, err);
     tc::tc_fence_after();
     for (int pass = 0; pass < passes; pass++) {
@@ -238,7 +270,14 @@ __device__ __forceinline__ void epilogue_tile(const EpiR &epi, float *Cs, uint32
             if (last) { tc::tc_fence_before(); if (lane == 0) mbar_arrive(acc_empty); }
             continue;
         }
-        if (EPI != EPI_ADAM && pass > 0) plain_aux<EPI>(epi, r.m0, n0c, et, aux);
+        if (EPI == EPI_MASK) {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) aux[i][j] = ((mask_bits[pass] >> (4 * i + j)) & 1u) ? 1.f : 0.f;
+        } else if (EPI != EPI_ADAM && pass > 0) {
+            plain_aux<EPI>(epi, r.m0, n0c, et, aux);
+        }
         {
             float v[16];
             float4 *dst = reinterpret_cast<float4 *>(Cs + (q * 32 + lane) * tc::kCsLd + hcol);
@@ -358,6 +397,17 @@ __device__ __forceinline__ void gemm_stage(const Program &P, const Stage &stage,
             const EpiR epi = resolve_epilogue(t, P.bases, r.agent, scalars);
             const uint32_t buf = it & 1, use = it >> 1;
             const uint32_t acc = tmem + buf * kAccCols;
+            if (wi + (int)gridDim.x < total) {      // the NEXT tile's ReLU-mask rows -> L2 while this tile is finished (one line per thread)
+                const TileRef nr = locate(P, mi, wi + gridDim.x);
+                if (nr.tg->epi == EPI_MASK) {
+                    const Pm mk = resolve_pm(nr.tg->mask, P.bases, nr.agent);
+                    const int lines = (nr.bn * 2 + 127) / 128;
+                    for (int i = et; i < kBM * lines; i += kEpiThreads) {
+                        const int row = nr.m0 + i / lines, col = nr.n0 + (i % lines) * 64;
+                        if (row < nr.tg->M && col < nr.tg->N) asm volatile("prefetch.global.L2 [%0];" ::"l"(mk.hi + (int64_t)row * mk.ld + col));
+                    }
+                }
+            }
             switch (epi.epi) {
                 case EPI_F32: epilogue_tile<EPI_F32>(epi, Cs, acc, r, et, &mi.acc_full[buf], use & 1, &mi.acc_empty[buf], err); break;
                 case EPI_BIAS_RELU: epilogue_tile<EPI_BIAS_RELU>(epi, Cs, acc, r, et, &mi.acc_full[buf], use & 1, &mi.acc_empty[buf], err); break;
