@@ -466,7 +466,9 @@ __device__ __forceinline__ AdamOut adam_math(const EpiR &e, float g, float w, fl
     AdamOut o;
     o.m = m + (1.0f - kBeta1) * (g - m);                                  // exp_avg.lerp_(grad, 1 - beta1)
     o.v = v * kBeta2 + (1.0f - kBeta2) * g * g;                           // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, 1 - beta2)
-    o.w = w - e.step_size * __fdividef(o.m, __fsqrt_rn(o.v) * e.inv_bc2_sqrt + kAdamEps);     // <= 2 ulp from the IEEE form
+    float sq;      // sqrt.approx (MUFU, <= 1 ulp) instead of the IEEE subroutine call: 7 % of an Adam stage's issue slots went into its call / return
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(sq) : "f"(o.v));
+    o.w = w - e.step_size * __fdividef(o.m, sq * e.inv_bc2_sqrt + kAdamEps);     // <= 3 ulp from the IEEE form
     o.t = wt * (1.0f - e.tau) + o.w * e.tau;                              // target <- target*(1-tau) + param*tau  (sac_imp.py:146-152)
     return o;
 }
