@@ -317,6 +317,9 @@ struct TcState {
     uint32_t krank, ksplit;
     uint64_t *reduce_bar;
     uint32_t reduce_uses;
+    // K blocks of the CTA's first tile whose B operand (a weight shadow no earlier stage of this step is still writing) was requested
+    // BEFORE the grid-dependency wait (tc_prefetch_b): their `full` barriers are armed with the whole stage's bytes already
+    uint32_t b_pre;
 };
 __device__ __forceinline__ int tc_stages(const TcState &st) { return st.ksplit > 1 ? kTStages - 1 : kTStages; }
 
@@ -370,6 +373,29 @@ __device__ __forceinline__ void trace_stamp(unsigned long long *trace, int slot)
     trace[(size_t)blockIdx.x * kTraceSlots + slot] = ts;
 }
 
+// Staged launches: a stage's CTAs become resident and run their prologue while the previous stage still computes (programmatic
+// dependent launch).  The A operand of a GEMM (activations, gradients) is what the previous stage produces, but the B operand of a
+// forward / dX GEMM is a weight shadow that, for most stages, nothing has written since two stages ago or longer (Task::i[6], set by
+// the host builder): its first K blocks are requested here, before griddepcontrol.wait, so that after the release only the A
+// halves still have to cross the SM's L2 port -- the stage is bound by exactly that ingest.
+__device__ __forceinline__ void tc_prefetch_b(const Task &t, const Task *tg, int tile, int agent, TcState &st) {
+    st.b_pre = 0;
+    if (st.ksplit != 1 || st.g != 0 || (threadIdx.x >> 5) != 0) return;
+    const int nkb = cdiv(t.K, kTK), n_pre = min(nkb, kTStages);
+    if (elect_one()) {
+        const int n0 = (tile % t.tiles_n) * t.bn, nb = t.B.r0 + n0;
+        const uint32_t tiles = smem_u32(st.tiles);
+        for (int kb = 0; kb < n_pre; kb++) {
+            mbar_arrive_expect_tx(&st.full_bar[kb], (uint32_t)(t.bm + t.bn) * (kTK * 2 * 2));      // A + B bytes: the A loads follow in tc_mainloop
+            const uint32_t sb = tiles + kb * kTcStageBytes + kTcABytes;
+            if (!t.B.mn_major) tma_load_4d(&tg->tmB, &st.full_bar[kb], sb, kb * kTK, nb, 0, agent);
+            else tma_load_4d(&tg->tmB, &st.full_bar[kb], sb, nb, kb * kTK, 0, agent);
+        }
+    }
+    __syncwarp();
+    st.b_pre = (uint32_t)n_pre;      // uniform over warp 0 (the only warp that reads it)
+}
+
 // returns the number of K-blocks this CTA accumulated (0: its partial tile is zero)
 __device__ __forceinline__ int tc_mainloop(const Task &t, int m0, int n0, int agent, TcState &st, int *error_flag, bool traced) {
     const int warp = threadIdx.x >> 5;
@@ -383,9 +409,10 @@ __device__ __forceinline__ int tc_mainloop(const Task &t, int m0, int n0, int ag
         if (elect_one()) {
             for (int kb = 0; kb < nkb; kb++) {
                 const uint32_t g = g0 + kb, s = g % nst;
-                mbar_wait(&st.empty_bar[s], ((g / nst) & 1) ^ 1, error_flag);
+                const bool pre = (uint32_t)kb < st.b_pre;      // B requested and the barrier armed before the dependency wait (first tile, g0 == 0)
+                if (!pre) mbar_wait(&st.empty_bar[s], ((g / nst) & 1) ^ 1, error_flag);
                 if (traced && kb < 16) trace_stamp(st.trace, 16 + kb);
-                mbar_arrive_expect_tx(&st.full_bar[s], (uint32_t)(t.bm + t.bn) * (kTK * 2 * 2));      // both planes of both operand tiles
+                if (!pre) mbar_arrive_expect_tx(&st.full_bar[s], (uint32_t)(t.bm + t.bn) * (kTK * 2 * 2));      // both planes of both operand tiles
                 const uint32_t sa = tiles + s * kTcStageBytes, sb = sa + kTcABytes;
                 const int k0 = (kb0 + kb) * kTK, ma = t.A.r0 + m0, nb = t.B.r0 + n0;
                 if (!a_mn) {
@@ -394,11 +421,13 @@ __device__ __forceinline__ int tc_mainloop(const Task &t, int m0, int n0, int ag
                     tma_load_4d(st.tmA, &st.full_bar[s], sa, ma, k0, 0, agent);
                     if (t.bm > 64) tma_load_4d(st.tmA, &st.full_bar[s], sa + kTcABytes / 2, ma + 64, k0, 0, agent);
                 }
+                if (pre) continue;
                 if (!b_mn) tma_load_4d(st.tmB, &st.full_bar[s], sb, k0, nb, 0, agent);
                 else tma_load_4d(st.tmB, &st.full_bar[s], sb, nb, k0, 0, agent);
             }
         }
         __syncwarp();
+        st.b_pre = 0;
     } else if (warp == 1) {
         const uint32_t idesc = make_idesc(t.bm, t.bn, a_mn, b_mn);
         // byte offsets inside a stage: lo plane of each operand (K-major: after the `rows` 128 B rows of the hi plane; MN-major:

@@ -5,6 +5,7 @@
 // critics + Adam -> temperature + Adam -> Polyak.
 #include <algorithm>
 #include <string>
+#include <map>
 #include <tuple>
 #include <cstring>
 #include <cstdio>
@@ -209,7 +210,7 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
     };
     timeline(0, false);
     tc::TcState st;
-    st.g = 0; st.accum_uses = 0; st.tmem_base = 0;
+    st.g = 0; st.accum_uses = 0; st.tmem_base = 0; st.b_pre = 0;
     st.krank = tc::cluster_ctarank(); st.ksplit = tc::cluster_nctarank(); st.reduce_uses = 0;
     st.reduce_bar = s_bars + 2 * kTStages + 1;
     st.full_bar = s_bars; st.empty_bar = s_bars + kTStages; st.accum_bar = s_bars + 2 * kTStages; st.trace = P.trace;
@@ -265,6 +266,9 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
             }
             const Task &t = s_task;
             if (!dep_synced) {      // everything above only read launch parameters and the static task tables
+                if constexpr (kTc && (kTypes & tb(T_GEMM)) != 0) {
+                    if (t.type == T_GEMM && t.i[6] && tc_setup && stage_end - stage_begin == 1) tc::tc_prefetch_b(t, tg, tile, agent, st);
+                }
                 asm volatile("griddepcontrol.wait;" ::: "memory");
                 asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
                 dep_synced = true;
@@ -366,6 +370,7 @@ struct Builder {
     int rc = SACB_OK;
     // tensor-core tile shape per task index (bm, bn), decided by choose_tile_shapes() from a dry first pass; empty = defaults
     std::vector<std::pair<int, int>> shapes;
+    std::map<int64_t, int> shadow_writer;      // arena offset of a weight shadow PM -> last stage of THIS program that writes it
     bool dry = false;      // first pass: count tiles only, no TMA descriptors
     bool stream = false;   // throughput program: GEMM stages run on the stream kernel (it alone understands split-K tasks)
 
@@ -434,6 +439,16 @@ struct Builder {
         t.type = T_GEMM; t.M = M; t.N = N; t.K = K;
         t.A.pm = a.ref; t.A.mn_major = a_mn; t.A.r0 = 0; t.B.pm = b.ref; t.B.mn_major = b_mn; t.B.r0 = b_r0;
         const size_t idx = tasks.size();
+        {   // B = a weight shadow (arena PM) that no stage later than two back has written: may be requested before the grid-dependency
+            // wait (gemm.cuh: tc_prefetch_b).  Writers: T_SHADOW tasks and Adam epilogues; the stage right before may still be running
+            const int cur = (int)stages.size() - 1;
+            const bool in_arena = ((b.ref.base.v >> 62) & 1) == 0;
+            const auto w = shadow_writer.find(b.ref.base.v);
+            // (opt-in, SACB_EARLY_B=1: measured no gain on B200 -- 0.1990 vs 0.1984 ms -- because with one 193 KB CTA per SM only the
+            //  ~20 CTAs of a stage that land on SMs the previous stage left idle are resident before the release at all)
+            t.i[6] = (in_arena && !stream && (w == shadow_writer.end() || w->second <= cur - 2) && getenv("SACB_EARLY_B")) ? 1 : 0;
+            for (const PmRef *r : {&t.adam.shadow, &t.adam.shadow2}) if (!is_null(r->base)) shadow_writer[r->base.v] = cur;
+        }
         t.bm = idx < shapes.size() && shapes[idx].first ? shapes[idx].first : tm;
         t.bn = idx < shapes.size() && shapes[idx].second ? shapes[idx].second : tn;
         t.tiles_m = cdiv(M, t.bm); t.tiles_n = cdiv(N, t.bn);
@@ -513,6 +528,7 @@ struct Builder {
     void shadow_task(int net, int64_t w_off, const PmView &dst, int src_ld, int col0 = 0) {
         Task t = blank(T_SHADOW);
         t.p[0] = A(L.param[net] + w_off); t.pm[0] = dst.ref; t.i[0] = dst.rows; t.i[1] = dst.cols; t.i[2] = col0; t.i[3] = src_ld;
+        shadow_writer[dst.ref.base.v] = (int)stages.size() - 1;
         add(t, cdiv(dst.rows, kShadowRows));
     }
 
