@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsacb200.so")
+LIB_PATH = os.environ.get("SACB_LIB") or os.path.join(_HERE, "libsacb200.so")      # SACB_LIB: an experiment build of the same sources (A/B timing)
 
 c_f32p = ctypes.POINTER(ctypes.c_float)
 c_f64p = ctypes.POINTER(ctypes.c_double)

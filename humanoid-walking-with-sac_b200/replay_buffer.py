@@ -174,7 +174,11 @@ class ReplayBuffer(_DeviceBuffer):
         n, o, k = idx.size, self._cfg.obs_dim, self._cfg.act_dim
         s, a, r = np.empty((n, o), np.float32), np.empty((n, k), np.float32), np.empty(n, np.float32)
         s2, d = np.empty((n, o), np.float32), np.empty(n, np.float32)
-        N.check(N.lib().sacb_sample_uniform(self._h, 0, N.ptr(idx, ctypes.c_int64), n, N.ptr(s), N.ptr(a), N.ptr(r), N.ptr(s2), N.ptr(d)))
+        step = int(self._cfg.max_batch)     # the device staging area holds max_batch rows: a larger request (the reference takes any size) is gathered in pieces
+        for b in range(0, n, step):
+            e = min(n, b + step)
+            N.check(N.lib().sacb_sample_uniform(self._h, 0, N.ptr(idx[b:e], ctypes.c_int64), e - b, N.ptr(s[b:e]), N.ptr(a[b:e]), N.ptr(r[b:e]),
+                                                N.ptr(s2[b:e]), N.ptr(d[b:e])))
         return s, a, r, s2, d
 
 
@@ -236,6 +240,9 @@ class PrioritizedReplayBuffer(_DeviceBuffer):
     def sample(self, batch_size, u=None):
         self._flush()
         n = min(batch_size, len(self))                                           # replay_buffer.py:50
+        if n > int(self._cfg.max_batch):     # one call normalises the IS weights by the batch maximum on the device: no piecewise form
+            raise ValueError(f"prioritized sample of {n} rows exceeds this buffer's max_batch={int(self._cfg.max_batch)} "
+                             "(standalone buffers: 1024; a SAC-owned buffer: the agent's max_batch)")
         if u is None:
             u = np.random.random_sample(n)       # the draw np.random.choice(len, n, p=probs) makes (mtrand.pyx::choice)
         u = np.ascontiguousarray(u, np.float64)

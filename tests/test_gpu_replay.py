@@ -152,6 +152,26 @@ def test_buffer_attribute_round_trip(hw):
     assert len(other) == 50 and other.buffer[7][2] == dq[7][2]
 
 
+def test_uniform_sample_larger_than_the_device_staging_area(hw):
+    """replay_buffer.py:12-17 takes any batch size up to len(buffer); a standalone buffer stages 1024 rows per gather."""
+    n, obs, act = 3000, 5, 2
+    rng = np.random.RandomState(4)
+    s, a, s2 = rng.randn(n, obs).astype(np.float32), rng.randn(n, act).astype(np.float32), rng.randn(n, obs).astype(np.float32)
+    r, d = rng.randn(n).astype(np.float32), (rng.rand(n) < 0.1).astype(np.float32)
+    buf = hw.ReplayBuffer(4096)
+    buf.push_many(s, a, r, s2, d)
+    random.seed(11)
+    expect = np.asarray(random.sample(range(n), 2500))
+    random.seed(11)
+    gs, ga, gr, gs2, gd = buf.sample(2500)
+    np.testing.assert_array_equal(gs, s[expect]); np.testing.assert_array_equal(ga, a[expect]); np.testing.assert_array_equal(gr, r[expect])
+    np.testing.assert_array_equal(gs2, s2[expect]); np.testing.assert_array_equal(gd, d[expect])
+    per = hw.PrioritizedReplayBuffer(4096)
+    per.push_many(s, a, r, s2, d)
+    with pytest.raises(ValueError):
+        per.sample(2500)
+
+
 @pytest.mark.parametrize("launch", ["staged", "persistent"])
 def test_pipelined_step_equals_sequential(hw, launch):
     """sacb_per_step (write-back + next sample on a second stream under the tail of the update) == the three calls in sequence, bitwise.

@@ -1,6 +1,7 @@
 import sys, os, ctypes
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ["SACB_TRACE"] = "1"
+if not os.environ.get("SACB_NOTRACE"):
+    os.environ["SACB_TRACE"] = "1"
 import humanoid_walking_with_sac_b200 as hw
 from tests.golden import cases
 from tests.util import batch_of, make_agent
