@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(64, 1) rate_kernel(const __grid_constant__ CUt
         for (int kb = 0; kb < p.nkb && !p.mma_only; kb++) {
             const int s = kb % p.nst;
             mbar_wait(&empty[s], ((kb / p.nst) & 1) ^ 1);
-            if (kb < kMaxKb) o[4 + kb] = gtime();
+            if (kb == 0) o[4 + kb] = gtime();
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&full[s])), "r"(bytes) : "memory");
             const uint32_t sa = smem_u32(tiles + s * p.stage_bytes), sb = sa + p.rows_a * 256, bar = smem_u32(&full[s]);
             const int k0 = (kb % 8) * 64;
@@ -119,8 +119,8 @@ __global__ void __launch_bounds__(64, 1) rate_kernel(const __grid_constant__ CUt
             for (int kb = 0; kb < p.nkb; kb++) {
                 const int s = kb % p.nst;
                 if (!p.mma_only) mbar_wait(&full[s], (kb / p.nst) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                if (kb < kMaxKb) o[4 + kMaxKb + kb] = gtime();
+                if (p.mma_per_kk) asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                if (kb == 0 || kb == p.nkb - 1) o[4 + kMaxKb + kb] = gtime();      // first and last arrival only: a stamp (timer read + global store) costs ~0.1 us
                 c0[kb & 7] = clock64();
                 if (p.mma_per_kk) {
                     const uint32_t sa = smem_u32(tiles + s * p.stage_bytes), sb = sa + p.rows_a * 256;
@@ -242,17 +242,20 @@ int main(int argc, char **argv) {
     CK(cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * kStageBytes + 1024));
     const int nkb = 8;
     printf("== operand ingest: TMA K blocks into a 192 KB ring, consumer = plain mbarrier arrive (no MMA)\n");
-    printf("rowsA rowsB slots ctas | per-K-block arrival interval us | KB per K block -> B/clk at 1.965 GHz\n");
+    printf("rowsA rowsB slots ctas | per-K-block arrival interval us | KB per K block -> B/clk at 1.965 GHz   (8 K blocks; slots = K blocks requested before the first one is consumed)\n");
     struct V { int ra, rb; };
     const V vs[] = {{64, 32}, {64, 64}, {128, 64}, {128, 128}};
     for (const V &v : vs)
+    for (int deep = 0; deep < 2; deep++)
     for (int ctas : {1, 8, 128, 148}) {
         const CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
         CUtensorMap tA = make(v.ra, 2, promo), tB = make(v.rb, 2, promo), tA1 = make(v.ra, 1, promo), tB1 = make(v.rb, 1, promo), tAB = make(64, 2, promo);
         std::vector<unsigned long long> h(148 * (4 + 2 * kMaxKb));
         double iv = 0;
         const int reps = 5;
-        const int sbytes = (v.ra + v.rb) * 256, nst = std::min(8, 4 * kStageBytes / sbytes);
+        const int kb_bytes = (v.ra + v.rb) * 256;
+        const int sbytes = deep ? kb_bytes : std::max(kb_bytes, kStageBytes), nst = deep ? std::min(8, 4 * kStageBytes / sbytes) : std::min(4, 4 * kStageBytes / sbytes);
+        if (deep && nst <= 4 && sbytes == std::max(kb_bytes, kStageBytes)) continue;      // same configuration as the shallow run
         Params p{0, 0, 0, 0, nst, sbytes, 0, 0, nkb, v.ra, v.rb, 1, flat, gmaps, d_out};
         for (int r = 0; r < reps + 2; r++) {
             rate_kernel<<<ctas, 64, 4 * kStageBytes + 1024>>>(tA, tB, tA1, tB1, tAB, p);
@@ -265,7 +268,7 @@ int main(int argc, char **argv) {
             }
         }
         iv = iv / ((double)reps * ctas) * 1e-3;
-        printf("%4d %4d %4d %4d | %.3f | %.0f KB -> %.1f B/clk\n", v.ra, v.rb, nst, ctas, iv, sbytes / 1024.0, sbytes / (iv * 1965.0));
+        printf("%4d %4d %4d %4d | %.3f | %.0f KB -> %.1f B/clk\n", v.ra, v.rb, nst, ctas, iv, kb_bytes / 1024.0, kb_bytes / (iv * 1965.0));
     }
     printf("== tcgen05.mma kind::f16, cta_group::1, both operands in shared memory (K-major, SWIZZLE_128B), 128 K steps back to back\n");
     long long *d_mma = nullptr; CK(cudaMalloc(&d_mma, 16));
@@ -277,8 +280,5 @@ int main(int argc, char **argv) {
     run_mma_rate<128, 128, 1>("M128 N128", d_mma);
     run_mma_rate<128, 128, 3>("M128 N128 x3 (stream tile)", d_mma);
     run_mma_rate<128, 256, 1>("M128 N256", d_mma);
-    run_mma_rate<128, 256, 2>("M128 N256 x2", d_mma);
-    run_mma_rate<64, 128, 1>("M64 N128", d_mma);
-    run_mma_rate<64, 256, 1>("M64 N256", d_mma);
     return 0;
 }
