@@ -328,10 +328,10 @@ __global__ void __launch_bounds__(stream::kThreads, 1) stream_selftest_kernel(co
 }
 }  // namespace sacb
 
-/* the stream kernel's tile (128 rows x bn = 64 | 128 columns, decoupled producer / MMA / epilogue over a round-robin tile list, `ctas`
+/* the stream kernel's tile (128 rows x bn = 64 | 128 | 256 columns, decoupled producer / MMA / epilogue over a round-robin tile list, `ctas`
  * resident CTAs) against the FFMA tile on the same bf16-pair operands */
 extern "C" int sacb_selftest_gemm_stream(int device, int M, int N, int K, int a_mn, int b_mn, int b_r0, int bn, int ctas, float *rel_err_out) {
-    if (M < 1 || N < 1 || K < 1 || b_r0 < 0 || (b_mn && b_r0 % 8) || !rel_err_out || (bn != 64 && bn != 128) || ctas < 1) return fail(SACB_ERR_ARG, "bad argument");
+    if (M < 1 || N < 1 || K < 1 || b_r0 < 0 || (b_mn && b_r0 % 8) || !rel_err_out || (bn != 64 && bn != 128 && bn != 256) || ctas < 1) return fail(SACB_ERR_ARG, "bad argument");
     SACB_CUDA(cudaSetDevice(device));
     const int NB = N + b_r0;
     const int a_rows = a_mn ? K : M, a_cols = a_mn ? M : K, b_rows = b_mn ? K : NB, b_cols = b_mn ? NB : K;

@@ -585,14 +585,30 @@ struct Builder {
     // round-robin over the resident CTAs (mid-size batches: better wave quantisation and more tiles to overlap per CTA).
     std::vector<std::pair<int, int>> stream_tile_shapes() const {
         static const int wide_min = getenv("SACB_STREAM_WIDE_MIN") ? atoi(getenv("SACB_STREAM_WIDE_MIN")) : 3;
+        // 128 x 256 tiles (two 96 KB ring slots, both 256-column accumulators) where the stage still holds kStreamN256Min x SMs of them:
+        // 0.75x the L2 -> SM operand traffic per flop of the 128 x 128 tile, which is what bounds a large-batch GEMM stage
+        // (SACB_STREAM_N256_MIN: waves of 256-wide tiles a stage needs, 0 = never).  Not where a task of the stage has only a handful
+        // of tiles (the K = batch dW GEMMs of a fused-Adam program, 8-16 tiles of a thousand K blocks each, sharing a stage with the
+        // dX GEMMs): those tiles are the stage's long pole, halving their number or their ring slots costs more than the wide tiles save
+        static const int n256_min = getenv("SACB_STREAM_N256_MIN") ? atoi(getenv("SACB_STREAM_N256_MIN")) : 1;
+        auto takes_256 = [](const Task &t) { return t.N >= 192 && cdiv(t.N, 256) * 256 <= cdiv(t.N, 128) * 128; };      // no extra padding against 128-wide tiles
         std::vector<std::pair<int, int>> out(tasks.size(), {0, 0});
         for (size_t si = 0; si < stages.size(); si++) {
-            int wide_tiles = 0;
+            int wide_tiles = 0, tiles_256 = 0;
+            bool all_many = true;
             for (int k = stages[si].task_begin; k < stages[si].task_end; k++)
-                if (tasks[k].type == T_GEMM) wide_tiles += cdiv(tasks[k].M, stream::kBM) * cdiv(tasks[k].N, tasks[k].N >= 96 ? stream::kBN : 64) * h->cfg.n_agents;
+                if (tasks[k].type == T_GEMM) {
+                    // split-K chunks a gradient-export dW GEMM will be cut into (gemm(): the dry pass itself does not split)
+                    const int chunks = (tasks[k].epi == EPI_ADAM && !apply()) ? std::max(1, std::min(16, cdiv(tasks[k].K, stream::kBK) / 16)) : 1;
+                    wide_tiles += cdiv(tasks[k].M, stream::kBM) * cdiv(tasks[k].N, tasks[k].N >= 96 ? stream::kBN : 64) * h->cfg.n_agents;
+                    const int t256 = cdiv(tasks[k].M, stream::kBM) * cdiv(tasks[k].N, takes_256(tasks[k]) ? 256 : (tasks[k].N >= 96 ? stream::kBN : 64)) * chunks * h->cfg.n_agents;
+                    tiles_256 += t256;
+                    all_many = all_many && 2 * t256 >= h->sm_count;
+                }
             const bool wide = wide_tiles >= wide_min * h->sm_count;
+            const bool very_wide = n256_min > 0 && all_many && tiles_256 >= n256_min * h->sm_count;
             for (int k = stages[si].task_begin; k < stages[si].task_end; k++)
-                if (tasks[k].type == T_GEMM) out[k] = {stream::kBM, (wide && tasks[k].N >= 96) ? stream::kBN : 64};
+                if (tasks[k].type == T_GEMM) out[k] = {stream::kBM, (very_wide && takes_256(tasks[k])) ? 256 : ((wide && tasks[k].N >= 96) ? stream::kBN : 64)};
         }
         return out;
     }

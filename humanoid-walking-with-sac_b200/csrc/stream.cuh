@@ -7,8 +7,11 @@
 //   warp 1        MMA issuer   : tcgen05.mma (bf16x3) into one of TWO 128-column TMEM accumulators
 //   warp 2        TMEM allocation / release
 //   warps 4..11   epilogue     : tcgen05.ld -> staging tile -> coalesced fused epilogue of tile i while tile i+1 is accumulated
-// Output tile 128 x 128 (128 x 64 where N < 96): per 64-deep K block a CTA pulls 64 KB for 2.1 MFLOP of products -- 1.5x the
-// operand reuse of the 128 x 64 latency tile (32.8 instead of 21.8 FLOP per operand byte) against the chip-wide L2 -> SMEM limit.
+// Output tile 128 x 256 / 128 x 128 / 128 x 64 (chosen per stage by the builder): per 64-deep K block a CTA pulls 96 / 64 / 48 KB for
+// 4.2 / 2.1 / 1.05 MFLOP of products -- 43.7 / 32.8 / 21.8 FLOP per operand byte against the chip-wide L2 -> SMEM limit (the 128 x 128
+// tile already issues its MMAs at the tensor peak, profiles/r02_tcgen05_rate_by_shape.txt; what holds a large-batch stage at 46-52 %
+// tensor-pipe activity is operand delivery: 7.6 TB/s of L2 -> SM traffic, profiles/r02_summary.md).  The 192 KB operand ring is cut
+// into as many slots as the stage's widest tile allows: 2 x 96 KB, 3 x 64 KB or 4 x 48 KB.
 // Tiles are assigned round-robin (tile = blockIdx.x + i * gridDim.x): every role derives the same sequence on its own.
 // Same arithmetic per output element as the latency form (same K order, same three products), so results are bit-identical.
 #pragma once
@@ -19,20 +22,20 @@ namespace stream {
 
 constexpr int kThreads = 384;                 // 12 warps
 constexpr int kEpiWarp0 = 4, kEpiThreads = 256;
-constexpr int kBM = 128, kBN = 128, kBK = 64, kStages = 3;
+constexpr int kBM = 128, kBN = 128, kBNMax = 256, kBK = 64, kMaxStages = 4;
 constexpr int kABytes = kBM * kBK * 2 * 2;    // hi + lo planes: 32 KB
-constexpr int kBBytes = kBN * kBK * 2 * 2;    // 32 KB
-constexpr int kStageBytes = kABytes + kBBytes;
-constexpr int kRingBytes = kStages * kStageBytes;                 // 192 KB
+constexpr int kGroupBytes = 64 * kBK * 2 * 2; // one 64-wide group of an MN-major operand, hi + lo: 16 KB ([hi 8 KB][lo 8 KB])
+constexpr int kRingBytes = 192 * 1024;
 constexpr int kStagingBytes = kBM * tc::kCsLd * 4;                // 128 x 68 floats = 34 KB: 64 columns of the tile at a time
 constexpr int kMiscBytes = 1024;                                  // barriers, TMEM base, stage table
 constexpr int kSmemBytes = kRingBytes + kStagingBytes + kMiscBytes;   // 232448 = the 227 KB a CTA can have: no static shared memory
-constexpr int kAccCols = 128, kTmemCols = 2 * kAccCols;
+constexpr int kAccCols = kBNMax, kTmemCols = 2 * kAccCols;      // two accumulators of up to 256 columns: all 512 TMEM columns
 
 struct Misc {                 // lives behind the staging tile
-    uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
+    uint64_t full[kMaxStages], empty[kMaxStages], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
     int32_t n_tiles, n_tasks, task_begin;
+    int32_t slot_bytes, n_slots;      // ring geometry of this stage: slots of (128 + widest bn) x 256 B
     int32_t tile_begin[kMaxStageTasks];
 };
 static_assert(sizeof(Misc) <= kMiscBytes, "misc block");
@@ -225,39 +228,47 @@ template <int EPI>
 __device__ __forceinline__ void epilogue_tile(const EpiR &epi, float *Cs, uint32_t acc_addr, const TileRef &r, int et, uint64_t *acc_full, uint32_t parity,
                                               uint64_t *acc_empty, int *err) {
     const int ew = et >> 5, lane = et & 31, q = ew & 3, hcol = (ew >> 2) * 32;
-    const int passes = r.bn > 64 ? 2 : 1;
+    const int passes = r.bn >> 6;      // 64 columns of the tile at a time: 1, 2 or 4 passes
     float aux[8][4];
-    uint32_t mask_bits[2] = {0u, 0u};
+    uint32_t mask_bits[4] = {0u, 0u, 0u, 0u};
     if (EPI == EPI_ADAM) {
         for (int p = 0; p < passes; p++) adam_prefetch(epi, r.m0, r.n0 + 64 * p, et);
     } else if (EPI == EPI_MASK) {
-        // the ReLU-mask operand (sign of the stored activation) of BOTH passes is fetched now and kept as one bit per element:
+        // the ReLU-mask operand (sign of the stored activation) of ALL passes is fetched now and kept as one bit per element:
         // no global load sits between the accumulator and the stores any more (the mask loads paced the dX stages: an epilogue
         // whose second pass started with an exposed L2 / DRAM round trip)
-        // (all 16 loads of a thread are issued back to back from clamped addresses and only then unpacked: written with the
-        //  row / column guards around each load the compiler serialised them, eight L2 round trips per pass -- ncu source view)
+        // (the 16 loads of two passes are issued back to back from clamped addresses and only then unpacked: written with the
+        //  row / column guards around each load the compiler serialised them, eight L2 round trips per pass -- ncu source view;
+        //  a 256-column tile fetches its second pair of passes the same way right behind the first)
         const int c4 = (et & 15) * 4, r0 = et >> 4;
-        uint2 raw[2][8];
+        auto fetch2 = [&](int pb, uint32_t &bits_a, uint32_t &bits_b) {
+            uint2 raw[2][8];
 #pragma unroll
-        for (int p = 0; p < 2; p++)
+            for (int p = 0; p < 2; p++)
 #pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const int row = min(r.m0 + r0 + 16 * i, epi.M - 1), col = min(r.n0 + 64 * p + c4, epi.N - 4);      // EPI_MASK outputs are hidden-width: N % 8 == 0
-                raw[p][i] = (p < passes) ? __ldcg(reinterpret_cast<const uint2 *>(epi.mask.hi + (int64_t)row * epi.mask.ld + col)) : make_uint2(0u, 0u);
-            }
-#pragma unroll
-        for (int p = 0; p < 2; p++)
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const bool ok = p < passes && r.m0 + r0 + 16 * i < epi.M && r.n0 + 64 * p + c4 < epi.N;
-                const uint32_t w[2] = {raw[p][i].x, raw[p][i].y};
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t h = (w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;      // bf16 bits of the stored activation: > 0 <=> sign clear, not zero
-                    const bool pos = ok && (h & 0x8000u) == 0u && (h & 0x7FFFu) != 0u && (h & 0x7FFFu) <= 0x7F80u;
-                    mask_bits[p] |= (pos ? 1u : 0u) << (4 * i + j);
+                for (int i = 0; i < 8; i++) {
+                    const int row = min(r.m0 + r0 + 16 * i, epi.M - 1), col = min(r.n0 + 64 * (pb + p) + c4, epi.N - 4);      // EPI_MASK outputs are hidden-width: N % 8 == 0
+                    raw[p][i] = (pb + p < passes) ? __ldcg(reinterpret_cast<const uint2 *>(epi.mask.hi + (int64_t)row * epi.mask.ld + col)) : make_uint2(0u, 0u);
                 }
+#pragma unroll
+            for (int p = 0; p < 2; p++) {
+                uint32_t bits = 0u;
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    const bool ok = pb + p < passes && r.m0 + r0 + 16 * i < epi.M && r.n0 + 64 * (pb + p) + c4 < epi.N;
+                    const uint32_t w[2] = {raw[p][i].x, raw[p][i].y};
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t h = (w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;      // bf16 bits of the stored activation: > 0 <=> sign clear, not zero
+                        const bool pos = ok && (h & 0x8000u) == 0u && (h & 0x7FFFu) != 0u && (h & 0x7FFFu) <= 0x7F80u;
+                        bits |= (pos ? 1u : 0u) << (4 * i + j);
+                    }
+                }
+                if (p == 0) bits_a = bits; else bits_b = bits;
             }
+        };
+        fetch2(0, mask_bits[0], mask_bits[1]);
+        if (passes > 2) fetch2(2, mask_bits[2], mask_bits[3]);      // CTA-uniform
     } else {
         plain_aux<EPI>(epi, r.m0, r.n0, et, aux);
     }
@@ -271,10 +282,11 @@ __device__ __forceinline__ void epilogue_tile(const EpiR &epi, float *Cs, uint32
             continue;
         }
         if (EPI == EPI_MASK) {
+            const uint32_t mb = pass == 0 ? mask_bits[0] : (pass == 1 ? mask_bits[1] : (pass == 2 ? mask_bits[2] : mask_bits[3]));
 #pragma unroll
             for (int i = 0; i < 8; i++)
 #pragma unroll
-                for (int j = 0; j < 4; j++) aux[i][j] = ((mask_bits[pass] >> (4 * i + j)) & 1u) ? 1.f : 0.f;
+                for (int j = 0; j < 4; j++) aux[i][j] = ((mb >> (4 * i + j)) & 1u) ? 1.f : 0.f;
         } else if (EPI != EPI_ADAM && pass > 0) {
             plain_aux<EPI>(epi, r.m0, n0c, et, aux);
         }
@@ -300,26 +312,32 @@ __device__ __forceinline__ void epilogue_tile(const EpiR &epi, float *Cs, uint32
     }
 }
 
-// the kernel body; P.tasks of the stage are all T_GEMM with bm = 128 and bn in {64, 128}
+// the kernel body; P.tasks of the stage are all T_GEMM with bm = 128 and bn in {64, 128, 256}
 __device__ __forceinline__ void gemm_stage(const Program &P, const Stage &stage, uint8_t *smem, uint64_t seed) {
     uint8_t *ring = smem;                                              // 1024-aligned (checked by the caller)
     float *Cs = reinterpret_cast<float *>(smem + kRingBytes);
     Misc &mi = *reinterpret_cast<Misc *>(smem + kRingBytes + kStagingBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 32) {
-        for (int i = 0; i < kStages; i++) { tc::mbar_init(&mi.full[i], 1); tc::mbar_init(&mi.empty[i], 1); }
+        for (int i = 0; i < kMaxStages; i++) { tc::mbar_init(&mi.full[i], 1); tc::mbar_init(&mi.empty[i], 1); }
         for (int i = 0; i < 2; i++) { tc::mbar_init(&mi.acc_full[i], 1); tc::mbar_init(&mi.acc_empty[i], kEpiThreads / 32); }
         tc::fence_barrier_init();
     }
     if (warp == 2) tmem_alloc_cols(&mi.tmem_base, kTmemCols);
     if (threadIdx.x >= 64 && threadIdx.x < 64 + kMaxStageTasks) mi.tile_begin[threadIdx.x - 64] = stage.tile_begin[threadIdx.x - 64];
-    if (threadIdx.x == 96) { mi.n_tiles = stage.n_tiles; mi.n_tasks = stage.task_end - stage.task_begin; mi.task_begin = stage.task_begin; }
+    if (threadIdx.x == 96) {
+        mi.n_tiles = stage.n_tiles; mi.n_tasks = stage.task_end - stage.task_begin; mi.task_begin = stage.task_begin;
+        int bn_max = 64;      // the producer runs ahead across tile boundaries: one slot size per stage, that of its widest tile
+        for (int k = stage.task_begin; k < stage.task_end; k++) bn_max = max(bn_max, __ldg(&P.tasks[k].bn));
+        mi.slot_bytes = kABytes + bn_max * (kBK * 2 * 2);
+        mi.n_slots = min(kMaxStages, kRingBytes / mi.slot_bytes);
+    }
     tc::tc_fence_before();
     __syncthreads();
     tc::tc_fence_after();
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    const uint32_t tmem = mi.tmem_base;
+    const uint32_t tmem = mi.tmem_base, n_slots = (uint32_t)mi.n_slots, slot_bytes = (uint32_t)mi.slot_bytes;
     const int total = mi.n_tiles * P.n_agents;
     int *err = P.error_flag;
 
@@ -333,10 +351,10 @@ __device__ __forceinline__ void gemm_stage(const Program &P, const Stage &stage,
                 const int ma = t.A.r0 + r.m0, nb = t.B.r0 + r.n0;
                 const uint32_t bytes = (uint32_t)(r.bm + r.bn) * (kBK * 2 * 2);
                 for (int kb = 0; kb < nkb; kb++, g++) {
-                    const uint32_t s = g % kStages;
-                    tc::mbar_wait(&mi.empty[s], ((g / kStages) & 1) ^ 1, err);
+                    const uint32_t s = g % n_slots;
+                    tc::mbar_wait(&mi.empty[s], ((g / n_slots) & 1) ^ 1, err);
                     tc::mbar_arrive_expect_tx(&mi.full[s], bytes);
-                    const uint32_t sa = tc::smem_u32(ring) + s * kStageBytes, sb = sa + kABytes;
+                    const uint32_t sa = tc::smem_u32(ring) + s * slot_bytes, sb = sa + kABytes;
                     const int k0 = (r.kb0 + kb) * kBK;
                     if (!a_mn) {
                         tc::tma_load_4d(&t.tmA, &mi.full[s], sa, k0, ma, 0, r.agent);
@@ -346,9 +364,8 @@ __device__ __forceinline__ void gemm_stage(const Program &P, const Stage &stage,
                     }
                     if (!b_mn) {
                         tc::tma_load_4d(&t.tmB, &mi.full[s], sb, k0, nb, 0, r.agent);
-                    } else {
-                        tc::tma_load_4d(&t.tmB, &mi.full[s], sb, nb, k0, 0, r.agent);
-                        if (r.bn > 64) tc::tma_load_4d(&t.tmB, &mi.full[s], sb + kBBytes / 2, nb + 64, k0, 0, r.agent);
+                    } else {      // one box per 64-wide group of columns
+                        for (int j = 0; j < r.bn; j += 64) tc::tma_load_4d(&t.tmB, &mi.full[s], sb + (j >> 6) * kGroupBytes, nb + j, k0, 0, r.agent);
                     }
                 }
             }
@@ -364,15 +381,15 @@ __device__ __forceinline__ void gemm_stage(const Program &P, const Stage &stage,
             tc::mbar_wait(&mi.acc_empty[buf], (use & 1) ^ 1, err);      // the epilogue has drained this accumulator
             tc::tc_fence_after();
             const uint32_t idesc = tc::make_idesc(r.bm, r.bn, a_mn, b_mn), d = tmem + buf * kAccCols;
-            const uint32_t a_lo = a_mn ? kABytes / 4 : (uint32_t)r.bm * 128u, b_lo = b_mn ? kBBytes / 4 : (uint32_t)r.bn * 128u;
-            const uint32_t a_lbo = a_mn ? kABytes / 2 : 16, b_lbo = b_mn ? kBBytes / 2 : 16;
+            const uint32_t a_lo = a_mn ? kGroupBytes / 2 : (uint32_t)r.bm * 128u, b_lo = b_mn ? kGroupBytes / 2 : (uint32_t)r.bn * 128u;
+            const uint32_t a_lbo = a_mn ? kGroupBytes : 16, b_lbo = b_mn ? kGroupBytes : 16;
             const uint32_t a_kstep = a_mn ? 2048 : 32, b_kstep = b_mn ? 2048 : 32;
             for (int kb = 0; kb < nkb; kb++, g++) {
-                const uint32_t s = g % kStages;
-                tc::mbar_wait(&mi.full[s], (g / kStages) & 1, err);
+                const uint32_t s = g % n_slots;
+                tc::mbar_wait(&mi.full[s], (g / n_slots) & 1, err);
                 tc::tc_fence_after();
                 if (tc::elect_one()) {
-                    const uint32_t sa = tc::smem_u32(ring) + s * kStageBytes, sb = sa + kABytes;
+                    const uint32_t sa = tc::smem_u32(ring) + s * slot_bytes, sb = sa + kABytes;
 #pragma unroll
                     for (int kk = 0; kk < kBK / 16; kk++) {
                         const uint64_t da_hi = tc::make_desc(sa + kk * a_kstep, a_lbo), da_lo = tc::make_desc(sa + a_lo + kk * a_kstep, a_lbo);

@@ -45,12 +45,12 @@ def test_tc_tile_shapes(M, N, K, a_mn, b_mn, bm, bn):
     assert err.value < 2e-5, err.value
 
 
-@pytest.mark.parametrize("bn", [64, 128])
+@pytest.mark.parametrize("bn", [64, 128, 256])
 @pytest.mark.parametrize("M,N,K,ctas", [(256, 512, 512, 148), (1024, 512, 365, 3), (512, 365, 256, 5), (100, 70, 45, 1), (130, 129, 129, 2),
                                         (34, 512, 256, 148), (512, 684, 1024, 7), (2048, 256, 64, 4)])
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1)])
 def test_stream_tile_matches_ffma(M, N, K, ctas, a_mn, b_mn, bn):
-    """Throughput ("stream") form of a GEMM stage: 128 x 64 / 128 x 128 tiles, a few resident CTAs walking MANY tiles each
+    """Throughput ("stream") form of a GEMM stage: 128 x 64 / 128 x 128 / 128 x 256 tiles (4 / 3 / 2 ring slots), a few resident CTAs walking MANY tiles each
     (the producer / MMA / epilogue roles run ahead of each other across tiles, two TMEM accumulators), all operand majors,
     ragged M / N / K."""
     import humanoid_walking_with_sac_b200 as hw
