@@ -590,7 +590,7 @@ struct Builder {
         // (SACB_STREAM_N256_MIN: waves of 256-wide tiles a stage needs, 0 = never).  Not where a task of the stage has only a handful
         // of tiles (the K = batch dW GEMMs of a fused-Adam program, 8-16 tiles of a thousand K blocks each, sharing a stage with the
         // dX GEMMs): those tiles are the stage's long pole, halving their number or their ring slots costs more than the wide tiles save
-        static const int n256_min = getenv("SACB_STREAM_N256_MIN") ? atoi(getenv("SACB_STREAM_N256_MIN")) : 1;
+        const int n256_min = getenv("SACB_STREAM_N256_MIN") ? atoi(getenv("SACB_STREAM_N256_MIN")) : 1;      // read per program build (tests A/B both forms in one process)
         auto takes_256 = [](const Task &t) { return t.N >= 192 && cdiv(t.N, 256) * 256 <= cdiv(t.N, 128) * 128; };      // no extra padding against 128-wide tiles
         std::vector<std::pair<int, int>> out(tasks.size(), {0, 0});
         for (size_t si = 0; si < stages.size(); si++) {

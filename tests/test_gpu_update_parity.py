@@ -176,6 +176,29 @@ def test_large_batch_update_matches_oracle(hw, B):
     assert agent.stats()["grid"] > 2 * agent.stats()["sm_count"]      # the widest stage really exceeds two waves (tile-loop CTAs)
 
 
+def test_wide_stream_tiles_equal_128_wide_tiles_bitwise(hw, monkeypatch):
+    """Throughput form at B = 8192 (C2 nets): the program built with 128 x 256 stream tiles (two ring slots, four epilogue passes)
+    must equal the one built with 128 x 128 tiles bit for bit -- same K order and the same three products per output element."""
+    case = dict(cases.UPDATE_CASES["c2_humanoid_m2"], batch=8192, steps=2, seed=78)
+    agents = []
+    for n256 in ("0", "1"):
+        monkeypatch.setenv("SACB_STREAM_N256_MIN", n256)      # read when the update program is built (first update of the handle)
+        agent, _ = make_agent(hw, case, math="bf16x3")
+        losses = []
+        for step in range(case["steps"]):
+            b = batch_of(case, step)
+            losses.append(agent.update_from_batch(b, eps=(b["eps_next"], b["eps_cur"])))
+        agents.append((agent, losses))
+    (a0, l0), (a1, l1) = agents
+    assert a1.stats()["n_tiles"] < a0.stats()["n_tiles"]      # the second program really is cut into wider (fewer) tiles
+    assert l0 == l1, (l0, l1)
+    for net in ("policy", "q1", "q2", "q1_target", "q2_target"):
+        p0, p1 = net_params(a0, net), net_params(a1, net)
+        for nm in p0:
+            np.testing.assert_array_equal(p0[nm], p1[nm], err_msg=f"{net}.{nm}")
+    assert np.isfinite(list(l1[-1].values())).all()
+
+
 ODD_SHAPES = {
     "wide_action_m1": dict(obs=20, act=40, hidden=64, n_hidden=2, batch=37, steps=2, seed=91, bias_scale=0.05, head_scale=0.25),     # 2A = 80 > one 64-column tile
     "one_action_m2": dict(obs=7, act=1, hidden=8, n_hidden=3, batch=5, steps=2, seed=92, bias_scale=0.05),                           # everything smaller than a tile
