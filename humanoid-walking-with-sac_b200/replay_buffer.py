@@ -174,11 +174,8 @@ class ReplayBuffer(_DeviceBuffer):
         n, o, k = idx.size, self._cfg.obs_dim, self._cfg.act_dim
         s, a, r = np.empty((n, o), np.float32), np.empty((n, k), np.float32), np.empty(n, np.float32)
         s2, d = np.empty((n, o), np.float32), np.empty(n, np.float32)
-        step = int(self._cfg.max_batch)     # the device staging area holds max_batch rows: a larger request (the reference takes any size) is gathered in pieces
-        for b in range(0, n, step):
-            e = min(n, b + step)
-            N.check(N.lib().sacb_sample_uniform(self._h, 0, N.ptr(idx[b:e], ctypes.c_int64), e - b, N.ptr(s[b:e]), N.ptr(a[b:e]), N.ptr(r[b:e]),
-                                                N.ptr(s2[b:e]), N.ptr(d[b:e])))
+        # any size up to len(buffer), like the reference: the library gathers through its staging area in pieces (replay.cu: gather_to_host)
+        N.check(N.lib().sacb_sample_uniform(self._h, 0, N.ptr(idx, ctypes.c_int64), n, N.ptr(s), N.ptr(a), N.ptr(r), N.ptr(s2), N.ptr(d)))
         return s, a, r, s2, d
 
 

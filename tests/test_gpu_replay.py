@@ -153,23 +153,23 @@ def test_buffer_attribute_round_trip(hw):
 
 
 def test_uniform_sample_larger_than_the_device_staging_area(hw):
-    """replay_buffer.py:12-17 takes any batch size up to len(buffer); a standalone buffer stages 1024 rows per gather."""
-    n, obs, act = 3000, 5, 2
+    """replay_buffer.py:12-17 takes any batch size up to len(buffer); the library gathers through a staging area of 4096 rows."""
+    n, obs, act = 6000, 5, 2
     rng = np.random.RandomState(4)
     s, a, s2 = rng.randn(n, obs).astype(np.float32), rng.randn(n, act).astype(np.float32), rng.randn(n, obs).astype(np.float32)
     r, d = rng.randn(n).astype(np.float32), (rng.rand(n) < 0.1).astype(np.float32)
-    buf = hw.ReplayBuffer(4096)
+    buf = hw.ReplayBuffer(8192)
     buf.push_many(s, a, r, s2, d)
     random.seed(11)
-    expect = np.asarray(random.sample(range(n), 2500))
+    expect = np.asarray(random.sample(range(n), 5000))
     random.seed(11)
-    gs, ga, gr, gs2, gd = buf.sample(2500)
+    gs, ga, gr, gs2, gd = buf.sample(5000)
     np.testing.assert_array_equal(gs, s[expect]); np.testing.assert_array_equal(ga, a[expect]); np.testing.assert_array_equal(gr, r[expect])
     np.testing.assert_array_equal(gs2, s2[expect]); np.testing.assert_array_equal(gd, d[expect])
-    per = hw.PrioritizedReplayBuffer(4096)
+    per = hw.PrioritizedReplayBuffer(8192)
     per.push_many(s, a, r, s2, d)
     with pytest.raises(ValueError):
-        per.sample(2500)
+        per.sample(5000)
 
 
 @pytest.mark.parametrize("launch", ["staged", "persistent"])
