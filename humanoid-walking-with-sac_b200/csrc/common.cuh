@@ -167,8 +167,14 @@ constexpr uint32_t kElemTypes = tb(T_SHADOW) | tb(T_GATHER) | tb(T_SAMPLE) | tb(
     X(13, tb(T_SAMPLE_BWD), 0u)                                                                     \
     X(14, tb(T_FINISH), 0u)                                                                                    \
     X(15, kElemTypes, 0u)                                                                           \
-    X(16, tb(T_GEMM) | tb(T_SHADOW), tb(EPI_BIAS_RELU))
-constexpr int kNumKernelVariants = 17;
+    X(16, tb(T_GEMM) | tb(T_SHADOW), tb(EPI_BIAS_RELU))                                             \
+    X(17, tb(T_OUT_ADAM) | tb(T_BIAS_ADAM), 0u)
+constexpr int kNumKernelVariants = 18;
+// "Light" builds: column-sum / sample-backward stages only.  A tile of theirs is one batch of loads, two barriers and a 64-element
+// Adam step: a throughput program walks thousands of them (population: 2304 per stage) and one 512-thread CTA per SM leaves the
+// memory system idle between its two dependent round trips.  They are compiled for TWO resident CTAs per SM (<= 64 registers).
+constexpr uint32_t kLightTypes = tb(T_OUT_ADAM) | tb(T_BIAS_ADAM) | tb(T_SAMPLE_BWD);
+constexpr int variant_min_blocks(uint32_t types, uint32_t epis) { return (types != 0 && (types & ~kLightTypes) == 0 && epis == 0) ? 2 : 1; }
 
 constexpr int kMaxStageTasks = 28;
 struct Stage {

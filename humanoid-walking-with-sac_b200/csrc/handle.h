@@ -174,6 +174,7 @@ int make_pm_tensor_map(CUtensorMap *out, const void *base, int64_t cols, int64_t
                        int64_t agent_stride_bytes, int n_agents, int box_rows);
 const void *update_kernel_for(int math_mode, int variant);      // variant: index into SACB_KERNEL_VARIANTS (0 = everything)
 bool variant_has_gemm(int variant);
+int variant_blocks_per_sm(int variant);      // resident CTAs per SM a build is compiled for (light column-sum builds: 2)
 int pick_variant(uint32_t task_types, uint32_t epilogues);
 // program.cu
 int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out);

@@ -183,7 +183,7 @@ __device__ __noinline__ void task_bias_adam_outlined(const Task &t, int tile, co
 __device__ __noinline__ void task_finish_outlined(const Task &t, const Program &P, int agent, float *scalars, float *smem) { task_finish(t, P, agent, scalars, smem); }
 
 template <int kMath, uint32_t kTypes, uint32_t kEpis>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, variant_min_blocks(kTypes, kEpis))
 sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Stage single, const int stage_begin, const int stage_end, const int tc_setup, const uint64_t seed) {
     // `single` = the stage table entry when the launch covers exactly one stage (staged mode): no global load before the first task
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -312,8 +312,8 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
                 case T_TARGET_LOSS: if constexpr ((kTypes & tb(T_TARGET_LOSS)) != 0) task_target_loss(t, tile, P, agent, scalars, s_red); break;
                 case T_ACTOR_LOSS: if constexpr ((kTypes & tb(T_ACTOR_LOSS)) != 0) task_actor_loss(t, tile, P, agent, scalars, s_red); break;
                 case T_SAMPLE_BWD: if constexpr ((kTypes & tb(T_SAMPLE_BWD)) != 0) task_sample_bwd(t, tile, P, agent, scalars); break;
-                case T_OUT_ADAM: if constexpr ((kTypes & tb(T_OUT_ADAM)) != 0) task_out_adam(t, tile, P, agent, scalars, s_red); break;
-                case T_BIAS_ADAM: if constexpr ((kTypes & tb(T_BIAS_ADAM)) != 0) task_bias_adam(t, tile, P, agent, scalars, s_red); break;
+                case T_OUT_ADAM: if constexpr ((kTypes & tb(T_OUT_ADAM)) != 0) task_out_adam<variant_min_blocks(kTypes, kEpis) == 1>(t, tile, P, agent, scalars, s_red); break;
+                case T_BIAS_ADAM: if constexpr ((kTypes & tb(T_BIAS_ADAM)) != 0) task_bias_adam<variant_min_blocks(kTypes, kEpis) == 1>(t, tile, P, agent, scalars, s_red); break;
                 case T_FINISH: if constexpr ((kTypes & tb(T_FINISH)) != 0) task_finish(t, P, agent, scalars, s_red); break;
             }
             if (wi == cl) stamp(4);
@@ -902,7 +902,12 @@ static int launch_stage(sacb_handle h, ProgramInst &p, int s, bool pdl) {
     int ctas = std::max(1, single.n_tiles * h->cfg.n_agents);
     static const int grid_cap = getenv("SACB_GRID_CAP") ? atoi(getenv("SACB_GRID_CAP")) : -1;     // 0 = never cap
     const int cap = grid_cap < 0 ? h->sm_count : grid_cap;
-    if (ks == 1 && cap > 0 && ctas > 2 * h->sm_count) ctas = cap;
+    if (ks == 1 && cap > 0 && ctas > 2 * h->sm_count) {      // resident CTAs looping over tiles wi = blockIdx.x + i * gridDim.x
+        ctas = std::min(ctas, cap * (tc ? variant_blocks_per_sm(kind) : 1));
+        // a grid that is a multiple of the stage's per-agent tile count keeps every CTA on ONE tile of ONE task across the agents it
+        // walks: the task record is fetched once instead of once per tile (population mode: a column-sum stage holds 2-6 tasks)
+        if (single.task_end - single.task_begin > 1 && single.n_tiles <= ctas / 2) ctas = (ctas / single.n_tiles) * single.n_tiles;
+    }
     cfg.gridDim = dim3(ctas * ks); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = h->stream;
     cudaLaunchAttribute attr[2];
     int na = 0;
@@ -1258,6 +1263,7 @@ static const KernelVariant kVariants[kNumKernelVariants] = {
 #undef X
 };
 bool variant_has_gemm(int v) { return (kVariants[v].types & tb(T_GEMM)) != 0; }
+int variant_blocks_per_sm(int v) { return variant_min_blocks(kVariants[v].types, kVariants[v].epis); }
 int pick_variant(uint32_t types, uint32_t epis) {
     int best = 0, best_bits = 1 << 30;
     for (int v = 0; v < kNumKernelVariants; v++) {

@@ -438,14 +438,15 @@ __device__ __forceinline__ void task_sample_bwd(const Task &t, int tile, const P
 // with shuffles, the 16 warps through shared memory in warp order: a fixed summation order.  Result valid for threadIdx.x < 64.
 constexpr int kColsumCols = 64;
 constexpr int kColsumSmem = (kThreads / 32) * kColsumCols;      // floats of shared memory
-template <class F>
+// kDeep = false (the two-CTAs-per-SM builds, 64 registers): at most 4 rows in flight per thread, the second resident CTA supplies the rest
+template <bool kDeep, class F>
 __device__ __forceinline__ float colsum64(int r0, int r1, float *smem, F load8) {
     const int cg = threadIdx.x & 7, rl = threadIdx.x >> 3, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) acc[j] = 0.f;
     int b = r0 + rl;
-    for (; b + 7 * 64 < r1; b += 8 * 64) {      // long batches: 8 rows (16 loads of 16 bytes) in flight per thread
+    for (; kDeep && b + 7 * 64 < r1; b += 8 * 64) {      // long batches: 8 rows (16 loads of 16 bytes) in flight per thread
         float v[8][8];
 #pragma unroll
         for (int u = 0; u < 8; u++) load8(b + 64 * u, cg * 8, v[u]);
@@ -512,6 +513,7 @@ __device__ __forceinline__ void colsum_finish(float g, bool chunked, float *ge, 
 // T_OUT_ADAM: Q output layer (Linear(H,1)).  pm0=h_L PM [B,H] p1=dq [B] ; p2..p6 = w,m,v,wt,gexp [H] ; p7..p11 = same for bias
 //   i0=B i1=H i2=step_slot i3=apply i5=rows per chunk (>= B: one chunk) ; f0=lr f1=tau.
 //   tiles: [row chunk][64-column tile] for the weight gradient, then one bias tile per row chunk
+template <bool kDeep = true>
 __device__ __forceinline__ void task_out_adam(const Task &t, int tile, const Program &P, int agent, const float *scalars, float *smem) {
     const int B = t.i[0], H = t.i[1], R = t.i[5], n_ct = cdiv(H, kColsumCols), n_rc = cdiv(B, R);
     const float *dq = resolve(t.p[1], P.bases, agent);
@@ -539,7 +541,7 @@ __device__ __forceinline__ void task_out_adam(const Task &t, int tile, const Pro
     float *wt = resolve(t.p[5], P.bases, agent), *ge = resolve(t.p[6], P.bases, agent);
     const PreState st = prefetch_state(owner && t.i[3], w, m, v, wt ? wt + n : nullptr);
     const int c0 = ct * kColsumCols;
-    const float g = colsum64(r0, r1, smem, [&](int b, int c, float (&out)[8]) {
+    const float g = colsum64<kDeep>(r0, r1, smem, [&](int b, int c, float (&out)[8]) {
         if (c0 + c < h.ld) {
             pm_load8(h, b, c0 + c, out);
             const float d = ldcg(dq + b);
@@ -555,6 +557,7 @@ __device__ __forceinline__ void task_out_adam(const Task &t, int tile, const Pro
 
 // T_BIAS_ADAM: db[n] = sum_b dh[b,n].  pm0 = dh PM [B,N] ; p0..p4 = b,m,v,bt,gexp ; i0=B i1=N i2=step_slot i3=apply
 //   i5=rows per chunk ; f0=lr f1=tau.   tiles: [row chunk][64-column tile]
+template <bool kDeep = true>
 __device__ __forceinline__ void task_bias_adam(const Task &t, int tile, const Program &P, int agent, const float *scalars, float *smem) {
     const int B = t.i[0], N = t.i[1], R = t.i[5], n_ct = cdiv(N, kColsumCols), n_rc = cdiv(B, R);
     const int ct = tile % n_ct, rc = tile / n_ct, r0 = rc * R, r1 = min(B, r0 + R);
@@ -565,7 +568,7 @@ __device__ __forceinline__ void task_bias_adam(const Task &t, int tile, const Pr
     float *bt = resolve(t.p[3], P.bases, agent), *ge = resolve(t.p[4], P.bases, agent);
     const PreState st = prefetch_state(owner && t.i[3], w, m, v, bt ? bt + n : nullptr);
     const int c0 = ct * kColsumCols;
-    const float g = colsum64(r0, r1, smem, [&](int b, int c, float (&out)[8]) {
+    const float g = colsum64<kDeep>(r0, r1, smem, [&](int b, int c, float (&out)[8]) {
         if (c0 + c < dh.ld) pm_load8(dh, b, c0 + c, out);
         else {
 #pragma unroll
