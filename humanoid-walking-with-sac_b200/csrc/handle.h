@@ -175,7 +175,7 @@ int make_pm_tensor_map(CUtensorMap *out, const void *base, int64_t cols, int64_t
 const void *update_kernel_for(int math_mode, int variant);      // variant: index into SACB_KERNEL_VARIANTS (0 = everything)
 bool variant_has_gemm(int variant);
 int variant_blocks_per_sm(int variant);      // resident CTAs per SM a build is compiled for (light column-sum builds: 2)
-int pick_variant(uint32_t task_types, uint32_t epilogues);
+int pick_variant(uint32_t task_types, uint32_t epilogues, bool allow_light_colsum = true);
 // program.cu
 int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out);
 int launch_program(sacb_handle h, ProgramInst &p);

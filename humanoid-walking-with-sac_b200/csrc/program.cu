@@ -591,7 +591,10 @@ struct Builder {
         // of tiles (the K = batch dW GEMMs of a fused-Adam program, 8-16 tiles of a thousand K blocks each, sharing a stage with the
         // dX GEMMs): those tiles are the stage's long pole, halving their number or their ring slots costs more than the wide tiles save
         const int n256_min = getenv("SACB_STREAM_N256_MIN") ? atoi(getenv("SACB_STREAM_N256_MIN")) : 1;      // read per program build (tests A/B both forms in one process)
-        auto takes_256 = [](const Task &t) { return t.N >= 192 && cdiv(t.N, 256) * 256 <= cdiv(t.N, 128) * 128; };      // no extra padding against 128-wide tiles
+        // no extra padding against 128-wide tiles; a tile that steps weights keeps 128 columns (its stage gives 64 KB of the ring to the
+        // optimizer-state landing zone of the Adam epilogue: two 64 KB slots are left)
+        const bool applies = apply();
+        auto takes_256 = [applies](const Task &t) { return t.N >= 192 && cdiv(t.N, 256) * 256 <= cdiv(t.N, 128) * 128 && !(t.epi == EPI_ADAM && applies); };
         std::vector<std::pair<int, int>> out(tasks.size(), {0, 0});
         for (size_t si = 0; si < stages.size(); si++) {
             int wide_tiles = 0, tiles_256 = 0;
@@ -1009,7 +1012,10 @@ int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out) {
             types |= tb(b.tasks[k].type);
             if (b.tasks[k].type == T_GEMM) epis |= tb(b.tasks[k].epi);
         }
-        p.stage_kind.push_back(getenv("SACB_ONE_KERNEL") ? 0 : pick_variant(types, epis));
+        // the two-CTAs-per-SM column-sum build (4 rows in flight per thread) pays where resident CTAs walk thousands of small tiles (a
+        // population); a stage of a few long tiles (one agent, large batch) keeps the one-CTA build with 8 rows in flight
+        const bool many = b.stages[s].n_tiles * h->cfg.n_agents > 2 * h->sm_count;
+        p.stage_kind.push_back(getenv("SACB_ONE_KERNEL") ? 0 : pick_variant(types, epis, many));
     }
     for (auto &s : p.stages) { p.n_tiles_total += s.n_tiles; p.max_stage_tiles = std::max(p.max_stage_tiles, s.n_tiles); }
     SACB_CUDA(cudaMalloc(&p.d_tasks, p.tasks.size() * sizeof(Task)));
@@ -1264,10 +1270,11 @@ static const KernelVariant kVariants[kNumKernelVariants] = {
 };
 bool variant_has_gemm(int v) { return (kVariants[v].types & tb(T_GEMM)) != 0; }
 int variant_blocks_per_sm(int v) { return variant_min_blocks(kVariants[v].types, kVariants[v].epis); }
-int pick_variant(uint32_t types, uint32_t epis) {
+int pick_variant(uint32_t types, uint32_t epis, bool allow_light_colsum) {
     int best = 0, best_bits = 1 << 30;
     for (int v = 0; v < kNumKernelVariants; v++) {
         if ((kVariants[v].types & types) != types || (kVariants[v].epis & epis) != epis) continue;
+        if (!allow_light_colsum && variant_blocks_per_sm(v) > 1 && (kVariants[v].types & (tb(T_OUT_ADAM) | tb(T_BIAS_ADAM)))) continue;
         const int bits = __builtin_popcount(kVariants[v].types) * 8 + __builtin_popcount(kVariants[v].epis);
         if (bits < best_bits) { best_bits = bits; best = v; }
     }

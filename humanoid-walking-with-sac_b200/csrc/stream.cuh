@@ -30,12 +30,19 @@ constexpr int kStagingBytes = kBM * tc::kCsLd * 4;                // 128 x 68 fl
 constexpr int kMiscBytes = 1024;                                  // barriers, TMEM base, stage table
 constexpr int kSmemBytes = kRingBytes + kStagingBytes + kMiscBytes;   // 232448 = the 227 KB a CTA can have: no static shared memory
 constexpr int kAccCols = kBNMax, kTmemCols = 2 * kAccCols;      // two accumulators of up to 256 columns: all 512 TMEM columns
+// Optimizer-state landing zone of the Adam epilogue (stages that step weights): the last 64 KB of the ring, two buffers of
+// [w | m | v | target][2 rows][256 threads] float4 filled with cp.async -- the state of the NEXT two-row group of a thread is in flight
+// (no registers held) while the current group is stepped.  Such a stage runs on a 128 KB operand ring.
+constexpr int kStateBufBytes = 4 * 2 * kEpiThreads * 16;         // 32 KB
+constexpr int kStateBytes = 2 * kStateBufBytes;                   // 64 KB
+constexpr int kRingBytesAdam = kRingBytes - kStateBytes;          // 128 KB
 
 struct Misc {                 // lives behind the staging tile
     uint64_t full[kMaxStages], empty[kMaxStages], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
     int32_t n_tiles, n_tasks, task_begin;
     int32_t slot_bytes, n_slots;      // ring geometry of this stage: slots of (128 + widest bn) x 256 B
+    int32_t adam_state;               // the stage steps weights: the tail of the ring is the optimizer-state landing zone
     int32_t tile_begin[kMaxStageTasks];
 };
 static_assert(sizeof(Misc) <= kMiscBytes, "misc block");
@@ -89,54 +96,101 @@ __device__ __forceinline__ void shadow2_store4(const EpiR &e, int m, int n, cons
 #pragma unroll
     for (int j = 0; j < 4; j++) if (n + j >= e.shadow2_col0 && n + j < e.N) pm_store(e.shadow2, m, n + j - e.shadow2_col0, x[j]);
 }
-__device__ __forceinline__ void adam_epilogue(const EpiR &e, const float *Cs, int m0, int n0, int et, bool accumulate) {
+// one two-row group of a thread: rows r0 + 16 (2 grp + ii), the aligned 4-column group c[ii] of each
+struct AdamGroup { int mrow[2], c[2]; bool vec[2]; };
+__device__ __forceinline__ AdamGroup adam_group(const EpiR &e, int m0, int n0, int ncols, int et, int grp) {
+    AdamGroup g;
+    const int j16 = et & 15, r0 = et >> 4;
+#pragma unroll
+    for (int ii = 0; ii < 2; ii++) {
+        g.mrow[ii] = m0 + r0 + 16 * (2 * grp + ii);
+        const int a0 = (4 - (int)(((int64_t)g.mrow[ii] * e.N + n0) & 3)) & 3;
+        g.c[ii] = a0 + 4 * j16;
+        g.vec[ii] = g.mrow[ii] < e.M && g.c[ii] + 3 < ncols;
+    }
+    return g;
+}
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+// request the optimizer state of group `grp` of the pass at columns n0 into landing buffer `buf` (one commit group, always)
+__device__ __forceinline__ void adam_issue(const EpiR &e, float4 *state, int m0, int n0, int et, int grp, int buf) {
     const int ncols = min(64, e.N - n0);
-    if (ncols <= 0) return;      // uniform over the epilogue threads
-    const int j16 = et & 15, r0 = et >> 4;      // 16 threads per row, rows r0 + 16 i
-#pragma unroll 1
-    for (int grp = 0; grp < 4; grp++) {         // pass A, two rows of a thread at a time
-        int mrow[2], c[2];
-        bool vec[2];
-        float4 w[2], mm[2], vv[2], wt[2];
+    if (e.apply && ncols > 0) {
+        const AdamGroup g = adam_group(e, m0, n0, ncols, et, grp);
+        float4 *dst = state + (size_t)buf * (kStateBufBytes / 16) + et;
 #pragma unroll
         for (int ii = 0; ii < 2; ii++) {
-            const int row = r0 + 16 * (2 * grp + ii);
-            mrow[ii] = m0 + row;
-            const int a0 = (4 - (int)(((int64_t)mrow[ii] * e.N + n0) & 3)) & 3;
-            c[ii] = a0 + 4 * j16;
-            vec[ii] = mrow[ii] < e.M && c[ii] + 3 < ncols;
-            w[ii] = mm[ii] = vv[ii] = wt[ii] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (vec[ii] && e.apply) {
-                const int64_t o = (int64_t)mrow[ii] * e.N + n0 + c[ii];
-                w[ii] = __ldcg(reinterpret_cast<const float4 *>(e.w + o));
-                mm[ii] = __ldcg(reinterpret_cast<const float4 *>(e.m + o));
-                vv[ii] = __ldcg(reinterpret_cast<const float4 *>(e.v + o));
-                if (e.wt) wt[ii] = __ldcg(reinterpret_cast<const float4 *>(e.wt + o));
+            if (!g.vec[ii]) continue;
+            const int64_t o = (int64_t)g.mrow[ii] * e.N + n0 + g.c[ii];
+            cp_async16(dst + (0 * 2 + ii) * kEpiThreads, e.w + o);
+            cp_async16(dst + (1 * 2 + ii) * kEpiThreads, e.m + o);
+            cp_async16(dst + (2 * 2 + ii) * kEpiThreads, e.v + o);
+            if (e.wt) cp_async16(dst + (3 * 2 + ii) * kEpiThreads, e.wt + o);
+        }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+// `state` = the landing zone when the stage has one (then groups 0 and 1 of this pass were requested by the caller), else null:
+// plain loads, two rows of a thread at a time
+__device__ __forceinline__ void adam_epilogue(const EpiR &e, const float *Cs, float4 *state, int m0, int n0, int et, bool accumulate) {
+    const int ncols = min(64, e.N - n0);
+    if (ncols <= 0) {      // uniform over the epilogue threads; the caller's two requests still have to retire
+        if (state) asm volatile("cp.async.wait_group 0;" ::: "memory");
+        return;
+    }
+#pragma unroll 1
+    for (int grp = 0; grp < 4; grp++) {         // pass A, two rows of a thread at a time
+        const AdamGroup g = adam_group(e, m0, n0, ncols, et, grp);
+        float4 w[2], mm[2], vv[2], wt[2];
+        if (state) {      // groups grp and grp + 1 are in flight: wait for the older one, then put group grp + 2 behind them
+            if (grp < 3) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const float4 *src = state + (size_t)(grp & 1) * (kStateBufBytes / 16) + et;
+#pragma unroll
+            for (int ii = 0; ii < 2; ii++) {
+                w[ii] = mm[ii] = vv[ii] = wt[ii] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g.vec[ii] && e.apply) {      // a thread reads back exactly what it requested: no barrier
+                    w[ii] = src[(0 * 2 + ii) * kEpiThreads]; mm[ii] = src[(1 * 2 + ii) * kEpiThreads]; vv[ii] = src[(2 * 2 + ii) * kEpiThreads];
+                    if (e.wt) wt[ii] = src[(3 * 2 + ii) * kEpiThreads];
+                }
+            }
+            if (grp + 2 < 4) adam_issue(e, state, m0, n0, et, grp + 2, grp & 1);      // the buffer just read
+        } else {
+#pragma unroll
+            for (int ii = 0; ii < 2; ii++) {
+                w[ii] = mm[ii] = vv[ii] = wt[ii] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (g.vec[ii] && e.apply) {
+                    const int64_t o = (int64_t)g.mrow[ii] * e.N + n0 + g.c[ii];
+                    w[ii] = __ldcg(reinterpret_cast<const float4 *>(e.w + o));
+                    mm[ii] = __ldcg(reinterpret_cast<const float4 *>(e.m + o));
+                    vv[ii] = __ldcg(reinterpret_cast<const float4 *>(e.v + o));
+                    if (e.wt) wt[ii] = __ldcg(reinterpret_cast<const float4 *>(e.wt + o));
+                }
             }
         }
 #pragma unroll
         for (int ii = 0; ii < 2; ii++) {
-            if (!vec[ii]) continue;
-            const int row = r0 + 16 * (2 * grp + ii);
-            const float *cs = Cs + row * tc::kCsLd + c[ii];
-            const int64_t o = (int64_t)mrow[ii] * e.N + n0 + c[ii];
-            const float g[4] = {cs[0], cs[1], cs[2], cs[3]};
+            if (!g.vec[ii]) continue;
+            const int row = (et >> 4) + 16 * (2 * grp + ii);
+            const float *cs = Cs + row * tc::kCsLd + g.c[ii];
+            const int64_t o = (int64_t)g.mrow[ii] * e.N + n0 + g.c[ii];
+            const float gr[4] = {cs[0], cs[1], cs[2], cs[3]};
             if (e.gexp) {
-                if (accumulate) atomicAdd(reinterpret_cast<float4 *>(e.gexp + o), make_float4(g[0], g[1], g[2], g[3]));      // one 16-byte reduction at L2
-                else *reinterpret_cast<float4 *>(e.gexp + o) = make_float4(g[0], g[1], g[2], g[3]);
+                if (accumulate) atomicAdd(reinterpret_cast<float4 *>(e.gexp + o), make_float4(gr[0], gr[1], gr[2], gr[3]));      // one 16-byte reduction at L2
+                else *reinterpret_cast<float4 *>(e.gexp + o) = make_float4(gr[0], gr[1], gr[2], gr[3]);
             }
             if (!e.apply) continue;
-            const tc::AdamOut a = tc::adam_math(e, g[0], w[ii].x, mm[ii].x, vv[ii].x, wt[ii].x), b = tc::adam_math(e, g[1], w[ii].y, mm[ii].y, vv[ii].y, wt[ii].y);
-            const tc::AdamOut cc = tc::adam_math(e, g[2], w[ii].z, mm[ii].z, vv[ii].z, wt[ii].z), d = tc::adam_math(e, g[3], w[ii].w, mm[ii].w, vv[ii].w, wt[ii].w);
+            const tc::AdamOut a = tc::adam_math(e, gr[0], w[ii].x, mm[ii].x, vv[ii].x, wt[ii].x), b = tc::adam_math(e, gr[1], w[ii].y, mm[ii].y, vv[ii].y, wt[ii].y);
+            const tc::AdamOut cc = tc::adam_math(e, gr[2], w[ii].z, mm[ii].z, vv[ii].z, wt[ii].z), d = tc::adam_math(e, gr[3], w[ii].w, mm[ii].w, vv[ii].w, wt[ii].w);
             *reinterpret_cast<float4 *>(e.m + o) = make_float4(a.m, b.m, cc.m, d.m);
             *reinterpret_cast<float4 *>(e.v + o) = make_float4(a.v, b.v, cc.v, d.v);
             *reinterpret_cast<float4 *>(e.w + o) = make_float4(a.w, b.w, cc.w, d.w);
             if (e.wt) *reinterpret_cast<float4 *>(e.wt + o) = make_float4(a.t, b.t, cc.t, d.t);
             const float w1[4] = {a.w, b.w, cc.w, d.w};
-            const int n = n0 + c[ii];
-            shadow_store4(e.shadow, mrow[ii], n, e.N, w1);
-            shadow2_store4(e, mrow[ii], n, w1);
-            if (e.wt && e.shadow_t.hi) { const float t1[4] = {a.t, b.t, cc.t, d.t}; shadow_store4(e.shadow_t, mrow[ii], n, e.N, t1); }
+            const int n = n0 + g.c[ii];
+            shadow_store4(e.shadow, g.mrow[ii], n, e.N, w1);
+            shadow2_store4(e, g.mrow[ii], n, w1);
+            if (e.wt && e.shadow_t.hi) { const float t1[4] = {a.t, b.t, cc.t, d.t}; shadow_store4(e.shadow_t, g.mrow[ii], n, e.N, t1); }
         }
     }
     if (e.N % 4 != 0 || ncols < 64) {           // pass B: the columns no aligned group covers; thread (row = et / 4 (+ 64), q = et % 4)
@@ -225,14 +279,15 @@ __device__ __forceinline__ void plain_aux(const EpiR &epi, int m0, int n0c, int 
 // epilogue of one tile: per 64-column pass TMEM -> staging tile (phase 1), fused epilogue from the staging tile (phase 2).
 // The first pass's bias / mask operands and the L2 prefetch of the Adam state are issued BEFORE the wait on the accumulator.
 template <int EPI>
-__device__ __forceinline__ void epilogue_tile(const EpiR &epi, float *Cs, uint32_t acc_addr, const TileRef &r, int et, uint64_t *acc_full, uint32_t parity,
+__device__ __forceinline__ void epilogue_tile(const EpiR &epi, float *Cs, float4 *state, uint32_t acc_addr, const TileRef &r, int et, uint64_t *acc_full, uint32_t parity,
                                               uint64_t *acc_empty, int *err) {
     const int ew = et >> 5, lane = et & 31, q = ew & 3, hcol = (ew >> 2) * 32;
     const int passes = r.bn >> 6;      // 64 columns of the tile at a time: 1, 2 or 4 passes
     float aux[8][4];
     uint32_t mask_bits[4] = {0u, 0u, 0u, 0u};
     if (EPI == EPI_ADAM) {
-        for (int p = 0; p < passes; p++) adam_prefetch(epi, r.m0, r.n0 + 64 * p, et);
+        for (int p = state ? 1 : 0; p < passes; p++) adam_prefetch(epi, r.m0, r.n0 + 64 * p, et);
+        if (state) { adam_issue(epi, state, r.m0, r.n0, et, 0, 0); adam_issue(epi, state, r.m0, r.n0, et, 1, 1); }      // first pass: under the main loop
     } else if (EPI == EPI_MASK) {
         // the ReLU-mask operand (sign of the stored activation) of ALL passes is fetched now and kept as one bit per element:
         // no global load sits between the accumulator and the stores any more (the mask loads paced the dX stages: an epilogue
@@ -279,6 +334,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiR &epi, float *Cs, uint32
         const int n0c = r.n0 + 64 * pass;
         if (n0c >= epi.N) {      // ragged N: nothing to store from this pass, but the accumulator still has to be released
             if (last) { tc::tc_fence_before(); if (lane == 0) mbar_arrive(acc_empty); }
+            if (EPI == EPI_ADAM && state) {      // keep the request pipeline in step: retire this pass's (empty) groups, request the next pass's
+                asm volatile("cp.async.wait_group 0;" ::: "memory");
+                if (!last) { adam_issue(epi, state, r.m0, n0c + 64, et, 0, 0); adam_issue(epi, state, r.m0, n0c + 64, et, 1, 1); }
+            }
             continue;
         }
         if (EPI == EPI_MASK) {
@@ -306,8 +365,11 @@ __device__ __forceinline__ void epilogue_tile(const EpiR &epi, float *Cs, uint32
             if (lane == 0) mbar_arrive(acc_empty);
         }
         epi_bar();
-        if (EPI == EPI_ADAM) adam_epilogue(epi, Cs, r.m0, n0c, et, r.tg->i[7] > 0);
-        else plain_epilogue<EPI>(epi, Cs, r.m0, n0c, et, aux);
+        if (EPI == EPI_ADAM) {
+            adam_epilogue(epi, Cs, state, r.m0, n0c, et, r.tg->i[7] > 0);
+            // the next pass's first two groups: in flight across the barrier and the next TMEM -> staging copy
+            if (state && !last) { adam_issue(epi, state, r.m0, n0c + 64, et, 0, 0); adam_issue(epi, state, r.m0, n0c + 64, et, 1, 1); }
+        } else plain_epilogue<EPI>(epi, Cs, r.m0, n0c, et, aux);
         epi_bar();        // the staging tile is free for the next pass / tile
     }
 }
@@ -327,10 +389,16 @@ __device__ __forceinline__ void gemm_stage(const Program &P, const Stage &stage,
     if (threadIdx.x >= 64 && threadIdx.x < 64 + kMaxStageTasks) mi.tile_begin[threadIdx.x - 64] = stage.tile_begin[threadIdx.x - 64];
     if (threadIdx.x == 96) {
         mi.n_tiles = stage.n_tiles; mi.n_tasks = stage.task_end - stage.task_begin; mi.task_begin = stage.task_begin;
-        int bn_max = 64;      // the producer runs ahead across tile boundaries: one slot size per stage, that of its widest tile
-        for (int k = stage.task_begin; k < stage.task_end; k++) bn_max = max(bn_max, __ldg(&P.tasks[k].bn));
+        int bn_max = 64, steps = 0;      // the producer runs ahead across tile boundaries: one slot size per stage, that of its widest tile
+        for (int k = stage.task_begin; k < stage.task_end; k++) {
+            bn_max = max(bn_max, __ldg(&P.tasks[k].bn));
+            // a short K loop (K = batch of a population's agents): the tile is bound by its Adam epilogue; a long one (large batch) by its
+            // main loop, which keeps the whole ring
+            if (__ldg(&P.tasks[k].epi) == EPI_ADAM && __ldg(&P.tasks[k].adam.apply)) steps |= __ldg(&P.tasks[k].K) <= 16 * kBK ? 1 : 2;
+        }
         mi.slot_bytes = kABytes + bn_max * (kBK * 2 * 2);
-        mi.n_slots = min(kMaxStages, kRingBytes / mi.slot_bytes);
+        mi.adam_state = (steps == 1 && 2 * mi.slot_bytes <= kRingBytesAdam) ? 1 : 0;      // (the builder keeps weight-stepping tiles at 128 columns)
+        mi.n_slots = min(kMaxStages, (mi.adam_state ? kRingBytesAdam : kRingBytes) / mi.slot_bytes);
     }
     tc::tc_fence_before();
     __syncthreads();
@@ -406,6 +474,7 @@ __device__ __forceinline__ void gemm_stage(const Program &P, const Stage &stage,
         }
     } else if (warp >= kEpiWarp0) {        // ---------------------------------------------------------------- epilogue
         const int et = threadIdx.x - kEpiWarp0 * 32;
+        float4 *state = mi.adam_state ? reinterpret_cast<float4 *>(ring + kRingBytesAdam) : nullptr;
         uint32_t it = 0;
         for (int wi = blockIdx.x; wi < total; wi += gridDim.x, it++) {
             const TileRef r = locate(P, mi, wi);
@@ -426,10 +495,10 @@ __device__ __forceinline__ void gemm_stage(const Program &P, const Stage &stage,
                 }
             }
             switch (epi.epi) {
-                case EPI_F32: epilogue_tile<EPI_F32>(epi, Cs, acc, r, et, &mi.acc_full[buf], use & 1, &mi.acc_empty[buf], err); break;
-                case EPI_BIAS_RELU: epilogue_tile<EPI_BIAS_RELU>(epi, Cs, acc, r, et, &mi.acc_full[buf], use & 1, &mi.acc_empty[buf], err); break;
-                case EPI_MASK: epilogue_tile<EPI_MASK>(epi, Cs, acc, r, et, &mi.acc_full[buf], use & 1, &mi.acc_empty[buf], err); break;
-                default: epilogue_tile<EPI_ADAM>(epi, Cs, acc, r, et, &mi.acc_full[buf], use & 1, &mi.acc_empty[buf], err); break;
+                case EPI_F32: epilogue_tile<EPI_F32>(epi, Cs, nullptr, acc, r, et, &mi.acc_full[buf], use & 1, &mi.acc_empty[buf], err); break;
+                case EPI_BIAS_RELU: epilogue_tile<EPI_BIAS_RELU>(epi, Cs, nullptr, acc, r, et, &mi.acc_full[buf], use & 1, &mi.acc_empty[buf], err); break;
+                case EPI_MASK: epilogue_tile<EPI_MASK>(epi, Cs, nullptr, acc, r, et, &mi.acc_full[buf], use & 1, &mi.acc_empty[buf], err); break;
+                default: epilogue_tile<EPI_ADAM>(epi, Cs, (state && epi.apply) ? state : nullptr, acc, r, et, &mi.acc_full[buf], use & 1, &mi.acc_empty[buf], err); break;
             }
         }
     }
