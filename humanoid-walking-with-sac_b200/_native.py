@@ -32,7 +32,7 @@ class Config(ctypes.Structure):
         ("replay_kind", ctypes.c_int32), ("capacity", ctypes.c_int64),
         ("per_alpha", ctypes.c_float), ("per_beta_start", ctypes.c_float), ("per_beta_frames", ctypes.c_int64),
         ("max_batch", ctypes.c_int32), ("n_agents", ctypes.c_int32), ("math_mode", ctypes.c_int32), ("launch_mode", ctypes.c_int32),
-        ("device", ctypes.c_int32), ("seed", ctypes.c_uint64), ("per_weighted_loss", ctypes.c_int32), ("reserved", ctypes.c_int32 * 7),
+        ("device", ctypes.c_int32), ("seed", ctypes.c_uint64), ("per_weighted_loss", ctypes.c_int32), ("layer_norm", ctypes.c_int32), ("reserved", ctypes.c_int32 * 6),
     ]
 
 

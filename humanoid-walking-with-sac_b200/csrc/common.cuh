@@ -93,7 +93,9 @@ enum TaskType : int32_t {
     T_SAMPLE_BWD,    // dL/da -> dL/dmean, dL/dlog_std                             
     T_OUT_ADAM,      // Q output layer: dW=dq^T h, db=sum dq, Adam, Polyak
     T_BIAS_ADAM,     // hidden-layer bias: db = colsum(dh), Adam, Polyak
-    T_FINISH         // loss scalars, temperature step (sac_imp.py:128-135), step counters
+    T_FINISH,        // loss scalars, temperature step (sac_imp.py:128-135), step counters
+    T_LN_FWD,        // opt-in LayerNorm variant: z (fp32) -> relu(LN(z) * gamma + beta) as a PM, row statistics kept
+    T_LN_BWD         // gradient of that: dpre (PM, ReLU mask applied) -> dz (PM) and the per-row terms of dgamma
 };
 
 enum Epilogue : int32_t {
@@ -147,9 +149,9 @@ struct alignas(64) Task {
 // spills in the forward / element-wise stages) and the instruction footprint of a 3-10 us kernel small.  X(index, task types, epilogues);
 // the host picks the smallest variant that covers a stage, variant 0 (everything) runs the persistent single-launch mode.
 constexpr uint32_t tb(int t) { return 1u << t; }
-constexpr uint32_t kAllTypes = (1u << (T_FINISH + 1)) - 1, kAllEpis = (1u << (EPI_SAMPLE + 1)) - 1;
+constexpr uint32_t kAllTypes = (1u << (T_LN_BWD + 1)) - 1, kAllEpis = (1u << (EPI_SAMPLE + 1)) - 1;
 constexpr uint32_t kPlainEpis = tb(EPI_F32) | tb(EPI_BIAS_RELU) | tb(EPI_MASK);
-constexpr uint32_t kElemTypes = tb(T_SHADOW) | tb(T_GATHER) | tb(T_SAMPLE) | tb(T_TARGET_LOSS) | tb(T_ACTOR_LOSS) | tb(T_SAMPLE_BWD) | tb(T_FINISH);
+constexpr uint32_t kElemTypes = tb(T_SHADOW) | tb(T_GATHER) | tb(T_SAMPLE) | tb(T_TARGET_LOSS) | tb(T_ACTOR_LOSS) | tb(T_SAMPLE_BWD) | tb(T_FINISH) | tb(T_LN_FWD) | tb(T_LN_BWD);
 #define SACB_KERNEL_VARIANTS(X)                                                                     \
     X(0, kAllTypes, kAllEpis)                                                                       \
     X(1, tb(T_GEMM), tb(EPI_BIAS_RELU))                                                         \
@@ -168,8 +170,10 @@ constexpr uint32_t kElemTypes = tb(T_SHADOW) | tb(T_GATHER) | tb(T_SAMPLE) | tb(
     X(14, tb(T_FINISH), 0u)                                                                                    \
     X(15, kElemTypes, 0u)                                                                           \
     X(16, tb(T_GEMM) | tb(T_SHADOW), tb(EPI_BIAS_RELU))                                             \
-    X(17, tb(T_OUT_ADAM) | tb(T_BIAS_ADAM), 0u)
-constexpr int kNumKernelVariants = 18;
+    X(17, tb(T_OUT_ADAM) | tb(T_BIAS_ADAM), 0u)                                                     \
+    X(18, tb(T_LN_FWD), 0u)                                                                         \
+    X(19, tb(T_LN_BWD), 0u)
+constexpr int kNumKernelVariants = 20;
 // "Light" builds: column-sum / sample-backward stages only.  A tile of theirs is one batch of loads, two barriers and a 64-element
 // Adam step: a throughput program walks thousands of them (population: 2304 per stage) and one 512-thread CTA per SM leaves the
 // memory system idle between its two dependent round trips.  They are compiled for TWO resident CTAs per SM (<= 64 registers).

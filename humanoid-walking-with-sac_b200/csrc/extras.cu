@@ -12,9 +12,22 @@ namespace sacb {
 
 struct MlpArgs {
     const float *w[4], *b[4];
+    const float *g[4], *be[4];      // LayerNorm weight / bias of hidden layer l (opt-in variant, else null)
     const float *w_out, *b_out;
     int n_hidden, in_dim, hidden, out_dim;
 };
+
+// sum of v over the CTA (all threads get it); `red` = 32 floats of shared memory
+__device__ __forceinline__ float block_sum(float v, float *red) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    float t = 0.f;
+    for (int w = 0; w < nw; w++) t += red[w];
+    return t;
+}
 
 // one CTA per input row: y = W_out . relu(... relu(W_0 x + b_0) ...) + b_out ; warp-per-output-row dot products,
 // activations in shared memory (2 x hidden floats + in_dim).  B = 1 is the select_action latency path (sac_imp.py:54-72).
@@ -32,9 +45,21 @@ __global__ void __launch_bounds__(512) mlp_rows_kernel(MlpArgs a, const float *x
             float s = 0.f;
             for (int j = lane; j < in; j += 32) s = fmaf(__ldg(wr + j), cur[j], s);
             s = warp_sum(s);
-            if (lane == 0) nxt[o] = fmaxf(s + __ldg(a.b[l] + o), 0.f);
+            if (lane == 0) nxt[o] = a.g[l] ? s + __ldg(a.b[l] + o) : fmaxf(s + __ldg(a.b[l] + o), 0.f);
         }
         __syncthreads();
+        if (a.g[l]) {      // LayerNorm (biased variance, eps 1e-5) + affine + ReLU over the row
+            __shared__ float red[32];
+            float ps = 0.f;
+            for (int o = threadIdx.x; o < a.hidden; o += blockDim.x) ps += nxt[o];
+            const float mean = block_sum(ps, red) / (float)a.hidden;
+            float pq = 0.f;
+            for (int o = threadIdx.x; o < a.hidden; o += blockDim.x) { const float d = nxt[o] - mean; pq += d * d; }
+            const float rstd = 1.0f / sqrtf(block_sum(pq, red) / (float)a.hidden + 1e-5f);
+            for (int o = threadIdx.x; o < a.hidden; o += blockDim.x)
+                nxt[o] = fmaxf((nxt[o] - mean) * rstd * __ldg(a.g[l] + o) + __ldg(a.be[l] + o), 0.f);
+            __syncthreads();
+        }
         float *t = cur; cur = nxt; nxt = t;
         in = a.hidden;
     }
@@ -64,7 +89,10 @@ static MlpArgs mlp_args(sacb_handle h, int agent, int net) {
     const float *base = h->arena + (int64_t)agent * h->L.arena_size + h->L.param[net];
     MlpArgs a;
     memset(&a, 0, sizeof(a));
-    for (int l = 0; l < nl.n_hidden; l++) { a.w[l] = base + nl.w[l]; a.b[l] = base + nl.b[l]; }
+    for (int l = 0; l < nl.n_hidden; l++) {
+        a.w[l] = base + nl.w[l]; a.b[l] = base + nl.b[l];
+        if (nl.layer_norm) { a.g[l] = base + nl.g[l]; a.be[l] = base + nl.be[l]; }
+    }
     a.w_out = base + nl.w_out; a.b_out = base + nl.b_out;
     a.n_hidden = nl.n_hidden; a.in_dim = nl.in_dim; a.hidden = nl.hidden; a.out_dim = nl.out_dim;
     return a;
@@ -195,12 +223,20 @@ static int select_action_single_cta(sacb_handle h, int agent, const float *obs, 
 extern "C" int sacb_select_action(sacb_handle h, int agent, const float *obs, int evaluate, const float *eps, float *action_out) {
     if (!h || !obs || !action_out || agent < 0 || agent >= h->cfg.n_agents) return fail(SACB_ERR_ARG, "bad argument");
     static const bool single = getenv("SACB_ACT_SINGLE_CTA") != nullptr;
-    if (single) return select_action_single_cta(h, agent, obs, evaluate, eps, action_out);
+    // LayerNorm variant: a layer's output row has to be complete before it is normalised -- the one-CTA-per-row kernel does that
+    if (single || h->cfg.layer_norm) return select_action_single_cta(h, agent, obs, evaluate, eps, action_out);
     return select_action_rows(h, agent, 1, 1, obs, evaluate, eps, action_out);
 }
 
 extern "C" int sacb_select_action_batch(sacb_handle h, const float *obs, int evaluate, const float *eps, float *action_out) {
     if (!h || !obs || !action_out) return fail(SACB_ERR_ARG, "bad argument");
+    if (h->cfg.layer_norm) {
+        for (int a = 0; a < h->cfg.n_agents; a++) {
+            const int rc = select_action_single_cta(h, a, obs + (int64_t)a * h->cfg.obs_dim, evaluate, eps ? eps + (int64_t)a * h->cfg.act_dim : nullptr, action_out + (int64_t)a * h->cfg.act_dim);
+            if (rc) return rc;
+        }
+        return SACB_OK;
+    }
     return select_action_rows(h, 0, h->cfg.n_agents, 1, obs, evaluate, eps, action_out);
 }
 

@@ -32,6 +32,8 @@ struct NetLayout {
     bool is_policy = false;
     int64_t w[4] = {0, 0, 0, 0}, b[4] = {0, 0, 0, 0};         // hidden layer l (0-based) weight [H,in_l] / bias [H]
     int64_t w_out = 0, b_out = 0;                             // output layer / fused heads
+    bool layer_norm = false;                                  // opt-in: LayerNorm (affine) between hidden Linear l and its ReLU
+    int64_t g[4] = {0, 0, 0, 0}, be[4] = {0, 0, 0, 0};         // its weight (gamma) / bias (beta) [H]
     int64_t size = 0;                                         // floats, multiple of 32
     // bf16 hi/lo shadow PMs of the GEMM weights (offsets in floats inside the net's shadow block):
     // hidden layer l: [hidden, sh_ld[l]] ; policy heads: [2A, hidden] (Q output layers are read as fp32 vectors)
@@ -40,7 +42,8 @@ struct NetLayout {
     int64_t sh_w[4] = {0, 0, 0, 0}, sh_out = 0, sh_act = 0, sh_size = 0;
     int sh_ld[4] = {0, 0, 0, 0}, sh_act_ld = 0;
     int in_of(int l) const { return l == 0 ? in_dim : hidden; }
-    int n_tensors() const { return is_policy ? 2 * n_hidden + 4 : 2 * n_hidden + 2; }
+    int per_layer() const { return layer_norm ? 4 : 2; }      // API tensors per hidden layer: weight, bias (, ln.weight, ln.bias)
+    int n_tensors() const { return per_layer() * n_hidden + (is_policy ? 4 : 2); }
     // API tensor -> (offset in net, rows, cols)
     void tensor(int t, int64_t &off, int64_t &rows, int64_t &cols) const;
 };
@@ -66,8 +69,14 @@ struct Layout {
     int64_t X = 0, g_head = 0;                                           // [3*maxB, ldx], [maxB, ldg]
     int64_t hp[4] = {0, 0, 0, 0}, dhp[4] = {0, 0, 0, 0};                 // policy activations [2*maxB,H] / grads [maxB,H]
     int64_t ht[2][4], hc[2][4], ha[2][4], dhc[2][4], dha[2][4];          // [maxB,H]
+    // LayerNorm variant only (else unused): pre-normalisation outputs z (fp32), row statistics (mean, rstd), dz PMs (the dh PMs then
+    // hold dpre = gradient at the LayerNorm output), PMs of dpre * xhat (column sums = dgamma)
+    bool layer_norm = false;
+    int64_t zp[4], zt[2][4], zc[2][4], za[2][4];                         // [2*maxB,H] / [maxB,H] fp32
+    int64_t sp[4], st[2][4], sc[2][4], sa[2][4];                         // [rows][2] fp32
+    int64_t dzp[4], dzc[2][4], dza[2][4], ggp[4], ggc[2][4];             // PMs [maxB,H]
     int64_t ws_size = 0;
-    void build(int obs, int act, int hidden, int n_hidden, int maxB);
+    void build(int obs, int act, int hidden, int n_hidden, int maxB, bool layer_norm = false);
 };
 
 struct ProgramKey {

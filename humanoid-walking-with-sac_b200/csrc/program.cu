@@ -25,11 +25,11 @@ namespace sacb {
 // layout
 // ================================================================================================================
 void NetLayout::tensor(int t, int64_t &off, int64_t &rows, int64_t &cols) const {
-    const int nh2 = 2 * n_hidden;
+    const int pl = per_layer(), nh2 = pl * n_hidden;
     if (t < nh2) {
-        const int l = t / 2;
-        if (t % 2 == 0) { off = w[l]; rows = hidden; cols = in_of(l); }
-        else { off = b[l]; rows = hidden; cols = 1; }
+        const int l = t / pl, j = t % pl;
+        if (j == 0) { off = w[l]; rows = hidden; cols = in_of(l); }
+        else { off = j == 1 ? b[l] : (j == 2 ? g[l] : be[l]); rows = hidden; cols = 1; }
         return;
     }
     const int k = t - nh2;
@@ -44,12 +44,13 @@ void NetLayout::tensor(int t, int64_t &off, int64_t &rows, int64_t &cols) const 
     }
 }
 
-static void build_net(NetLayout &n, bool is_policy, int in_dim, int hidden, int n_hidden, int out_dim, int act_cols) {
-    n.is_policy = is_policy; n.in_dim = in_dim; n.hidden = hidden; n.n_hidden = n_hidden; n.out_dim = out_dim;
+static void build_net(NetLayout &n, bool is_policy, int in_dim, int hidden, int n_hidden, int out_dim, int act_cols, bool layer_norm) {
+    n.is_policy = is_policy; n.in_dim = in_dim; n.hidden = hidden; n.n_hidden = n_hidden; n.out_dim = out_dim; n.layer_norm = layer_norm;
     int64_t o = 0;
     for (int l = 0; l < n_hidden; l++) {
         n.w[l] = o; o = align_up(o + (int64_t)hidden * n.in_of(l), 4);
         n.b[l] = o; o = align_up(o + hidden, 4);
+        if (layer_norm) { n.g[l] = o; o = align_up(o + hidden, 4); n.be[l] = o; o = align_up(o + hidden, 4); }
     }
     n.w_out = o; o = align_up(o + (int64_t)out_dim * hidden, 4);
     n.b_out = o; o = align_up(o + out_dim, 4);
@@ -67,12 +68,12 @@ static void build_net(NetLayout &n, bool is_policy, int in_dim, int hidden, int 
     n.sh_size = align_up(o, 32);
 }
 
-void Layout::build(int obs_, int act_, int hidden_, int n_hidden_, int maxB_) {
-    obs = obs_; act = act_; hidden = hidden_; n_hidden = n_hidden_; maxB = maxB_;
+void Layout::build(int obs_, int act_, int hidden_, int n_hidden_, int maxB_, bool layer_norm_) {
+    obs = obs_; act = act_; hidden = hidden_; n_hidden = n_hidden_; maxB = maxB_; layer_norm = layer_norm_;
     ldx = (int)align_up(obs + act, 8);
     ldg = (int)align_up(2 * act, 8);
-    build_net(pol, true, obs, hidden, n_hidden, 2 * act, 0);
-    build_net(q, false, obs + act, hidden, n_hidden, 1, act);
+    build_net(pol, true, obs, hidden, n_hidden, 2 * act, 0, layer_norm);
+    build_net(q, false, obs + act, hidden, n_hidden, 1, act, layer_norm);
     int64_t o = 0;
     scalars = o; o += 32;
     loss_hist = o; o += 4 * kLossHist;
@@ -104,6 +105,15 @@ void Layout::build(int obs_, int act_, int hidden_, int n_hidden_, int maxB_) {
             ht[k][l] = take(B * H); hc[k][l] = take(B * H); ha[k][l] = take(B * H);
             dhc[k][l] = take(B * H); dha[k][l] = take(B * H);
         }
+    if (layer_norm) {
+        for (int l = 0; l < n_hidden; l++) { zp[l] = take(2 * B * H); sp[l] = take(4 * B); dzp[l] = take(B * H); ggp[l] = take(B * H); }
+        for (int k = 0; k < 2; k++)
+            for (int l = 0; l < n_hidden; l++) {
+                zt[k][l] = take(B * H); zc[k][l] = take(B * H); za[k][l] = take(B * H);
+                st[k][l] = take(2 * B); sc[k][l] = take(2 * B); sa[k][l] = take(2 * B);
+                dzc[k][l] = take(B * H); dza[k][l] = take(B * H); ggc[k][l] = take(B * H);
+            }
+    }
     ws_size = align_up(o, 64);
 }
 
@@ -297,6 +307,8 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
                     case T_OUT_ADAM: task_out_adam_outlined(t, tile, P, agent, scalars, s_red); break;
                     case T_BIAS_ADAM: task_bias_adam_outlined(t, tile, P, agent, scalars, s_red); break;
                     case T_FINISH: task_finish_outlined(t, P, agent, scalars, s_red); break;
+                    case T_LN_FWD: task_ln_fwd(t, tile, P, agent); break;
+                    case T_LN_BWD: task_ln_bwd(t, tile, P, agent); break;
                 }
             } else
             switch (t.type) {      // only the task types of this build's mask are compiled in
@@ -315,6 +327,8 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
                 case T_OUT_ADAM: if constexpr ((kTypes & tb(T_OUT_ADAM)) != 0) task_out_adam<variant_min_blocks(kTypes, kEpis) == 1>(t, tile, P, agent, scalars, s_red); break;
                 case T_BIAS_ADAM: if constexpr ((kTypes & tb(T_BIAS_ADAM)) != 0) task_bias_adam<variant_min_blocks(kTypes, kEpis) == 1>(t, tile, P, agent, scalars, s_red); break;
                 case T_FINISH: if constexpr ((kTypes & tb(T_FINISH)) != 0) task_finish(t, P, agent, scalars, s_red); break;
+                case T_LN_FWD: if constexpr ((kTypes & tb(T_LN_FWD)) != 0) task_ln_fwd(t, tile, P, agent); break;
+                case T_LN_BWD: if constexpr ((kTypes & tb(T_LN_BWD)) != 0) task_ln_bwd(t, tile, P, agent); break;
             }
             if (wi == cl) stamp(4);
         }
@@ -524,6 +538,34 @@ struct Builder {
         t.i[5] = colsum_rows(Bn);
         add(t, cdiv(N, kColsumCols) * cdiv(Bn, t.i[5]));
     }
+    // ---- opt-in LayerNorm variant (cfg.layer_norm): hidden layer = Linear -> LayerNorm (affine) -> ReLU.  The forward GEMM then writes the
+    // Linear output z as fp32 (EPI_F32 with the bias) and a T_LN_FWD stage behind it normalises the rows into the activation PM; a
+    // backward GEMM / loss task still writes the gradient at the ReLU input (mask applied) into the dh PM -- which is now the gradient at
+    // the LayerNorm OUTPUT -- and a T_LN_BWD stage turns it into dz, the gradient at the Linear output, in its own PM; dgamma / dbeta
+    // are column sums over the batch (T_BIAS_ADAM) of dpre * xhat and dpre.
+    bool ln() const { return L.layer_norm; }
+    Task fwd_epi(const PmView &hout, Ref bias, int64_t z_off) { return ln() ? epi_f32(W(z_off), L.hidden, bias) : epi_bias_relu(hout, bias); }
+    void ln_fwd(int net, int l, int64_t z_off, int64_t st_off, const PmView &hout, int rows) {
+        const NetLayout &n = net == 0 ? L.pol : L.q;
+        Task t = blank(T_LN_FWD);
+        t.p[0] = W(z_off); t.p[1] = A(L.param[net] + n.g[l]); t.p[2] = A(L.param[net] + n.be[l]); t.p[3] = W(st_off);
+        t.pm[0] = hout.ref; t.i[0] = rows; t.i[1] = L.hidden; t.f[0] = 1e-5f;      // torch.nn.LayerNorm default eps
+        add(t, cdiv(rows, kLnRows));
+    }
+    void ln_bwd(int net, int l, const PmView &dpre, int64_t z_off, int64_t st_off, const PmView &dz, const PmView *gg, int rows) {
+        const NetLayout &n = net == 0 ? L.pol : L.q;
+        Task t = blank(T_LN_BWD);
+        t.pm[0] = dpre.ref; t.p[0] = W(z_off); t.p[1] = A(L.param[net] + n.g[l]); t.p[3] = W(st_off);
+        t.pm[1] = dz.ref; t.pm[2] = gg ? gg->ref : null_pm(); t.i[0] = rows; t.i[1] = L.hidden;
+        add(t, cdiv(rows, kLnRows));
+    }
+    // Adam on gamma / beta of hidden layer l of a trainable net: column sums of dpre * xhat (gg) and of dpre
+    void ln_param_adam(int net, int l, const PmView &gg, const PmView &dpre, int Bn) {
+        const NetLayout &n = net == 0 ? L.pol : L.q;
+        bias_adam(net, n.g[l], gg, Bn, L.hidden);
+        bias_adam(net, n.be[l], dpre, Bn, L.hidden);
+    }
+
     // shadow of columns [col0, col0+dst.cols) of the fp32 matrix at w_off (row stride src_ld)
     void shadow_task(int net, int64_t w_off, const PmView &dst, int src_ld, int col0 = 0) {
         Task t = blank(T_SHADOW);
@@ -675,10 +717,15 @@ struct Builder {
                 begin_stage();
                 const int in_p = P.in_of(l), in_q = Q.in_of(l);
                 gemm(l == 0 ? xrows(0, 2 * B, obs) : hview(L.hp[l - 1], 2 * B, 0, 2), 0, wsh(0, l), 0, 2 * B, H, in_p,
-                     epi_bias_relu(hview(L.hp[l], 2 * B, 0, 2), A(L.param[0] + P.b[l])));
+                     fwd_epi(hview(L.hp[l], 2 * B, 0, 2), A(L.param[0] + P.b[l]), L.zp[l]));
                 for (int k = 0; k < 2; k++)
                     gemm(l == 0 ? X1(obs + act) : hview(L.hc[k][l - 1], B), 0, wsh(1 + k, l), 0, B, H, in_q,
-                         epi_bias_relu(hview(L.hc[k][l], B), A(L.param[1 + k] + Q.b[l])));
+                         fwd_epi(hview(L.hc[k][l], B), A(L.param[1 + k] + Q.b[l]), L.zc[k][l]));
+                if (ln()) {
+                    begin_stage();
+                    ln_fwd(0, l, L.zp[l], L.sp[l], hview(L.hp[l], 2 * B, 0, 2), 2 * B);
+                    for (int k = 0; k < 2; k++) ln_fwd(1 + k, l, L.zc[k][l], L.sc[k][l], hview(L.hc[k][l], B), B);
+                }
             }
             // ---- policy heads -> head_raw [2B, 2A] (fp32) ------------------------------------------------------------
             // opt-in experiment (SACB_FUSE_SAMPLE=1, tensor-core math, 2A <= 64): the tanh-Gaussian sample + log-prob of both batches
@@ -712,7 +759,11 @@ struct Builder {
                 const int in_q = Q.in_of(l);
                 for (int k = 0; k < 2; k++)
                     gemm(l == 0 ? X2(obs + act) : hview(L.ht[k][l - 1], B), 0, wsh(3 + k, l), 0, B, H, in_q,
-                         epi_bias_relu(hview(L.ht[k][l], B), A(L.param[3 + k] + Q.b[l])));
+                         fwd_epi(hview(L.ht[k][l], B), A(L.param[3 + k] + Q.b[l]), L.zt[k][l]));
+                if (ln()) {
+                    begin_stage();
+                    for (int k = 0; k < 2; k++) ln_fwd(3 + k, l, L.zt[k][l], L.st[k][l], hview(L.ht[k][l], B), B);
+                }
             }
             // ---- Bellman target, critic losses, dL/dq, dL/dh of the last hidden layer --------------------------------
             begin_stage();
@@ -729,6 +780,17 @@ struct Builder {
                 t.i[0] = B; t.i[1] = H; t.i[2] = loss_rows(); t.f[0] = h->cfg.gamma;
                 add(t, cdiv(B, loss_rows()));
             }
+            // gradient at the Linear output of critic k's hidden layer x: the dh PM itself, or (LayerNorm variant) the dz PM behind it
+            auto DZC = [&](int k, int x) { return ln() ? hview(L.dzc[k][x], B) : hview(L.dhc[k][x], B); };
+            auto ln_bwd_c = [&](int x) {      // own stage: dpre -> dz of layer x of both critics
+                if (!ln()) return;
+                begin_stage();
+                for (int k = 0; k < 2; k++) {
+                    const PmView gg = hview(L.ggc[k][x], B);
+                    ln_bwd(1 + k, x, hview(L.dhc[k][x], B), L.zc[k][x], L.sc[k][x], hview(L.dzc[k][x], B), &gg, B);
+                }
+            };
+            ln_bwd_c(nh - 1);
             // ---- critic backward --------------------------------------------------------------------------------------
             //   stage s (1..nh): dX of layer l = nh-s (0-based, only while l >= 1) ; dW/db of layer l+1 ; last stage: dW/db of layer 0
             for (int s = 1; s <= nh; s++) {
@@ -737,11 +799,12 @@ struct Builder {
                 for (int k = 0; k < 2; k++) {
                     const int net = 1 + k;
                     if (l >= 1)   // dh_{l-1} = (dh_l . W_l) * relu'(h_{l-1})
-                        gemm(hview(L.dhc[k][l], B), 0, wsh(net, l), 1, B, Q.in_of(l), H, epi_mask(hview(L.dhc[k][l - 1], B), hview(L.hc[k][l - 1], B)));
+                        gemm(DZC(k, l), 0, wsh(net, l), 1, B, Q.in_of(l), H, epi_mask(hview(L.dhc[k][l - 1], B), hview(L.hc[k][l - 1], B)));
                     auto dW = [&](int layer) {   // dW_layer = dh_layer^T . x_layer ; fused Adam + Polyak + shadow refresh
                         const int in = Q.in_of(layer);
-                        gemm(hview(L.dhc[k][layer], B), 1, layer == 0 ? X1(in) : hview(L.hc[k][layer - 1], B), 1, H, in, B, epi_adam(net, layer));
-                        bias_adam(net, Q.b[layer], hview(L.dhc[k][layer], B), B, H);
+                        gemm(DZC(k, layer), 1, layer == 0 ? X1(in) : hview(L.hc[k][layer - 1], B), 1, H, in, B, epi_adam(net, layer));
+                        bias_adam(net, Q.b[layer], DZC(k, layer), B, H);
+                        if (ln()) ln_param_adam(net, layer, hview(L.ggc[k][layer], B), hview(L.dhc[k][layer], B), B);
                     };
                     if (l + 1 <= nh - 1) dW(l + 1);
                     if (s == nh) dW(0);
@@ -756,6 +819,7 @@ struct Builder {
                         add(t, (cdiv(H, kColsumCols) + 1) * cdiv(B, t.i[5]));      // + the bias tile, per row chunk
                     }
                 }
+                if (l >= 1) ln_bwd_c(l - 1);
             }
         }
         if (actor) {
@@ -765,9 +829,13 @@ struct Builder {
                 const int in_q = Q.in_of(l);
                 for (int k = 0; k < 2; k++)
                     gemm(l == 0 ? X3(obs + act) : hview(L.ha[k][l - 1], B), 0, wsh(1 + k, l), 0, B, H, in_q,
-                         epi_bias_relu(hview(L.ha[k][l], B), A(L.param[1 + k] + Q.b[l])));
+                         fwd_epi(hview(L.ha[k][l], B), A(L.param[1 + k] + Q.b[l]), L.za[k][l]));
                 if (critics && task_shadows())      // the Polyak targets moved in the critic backward: one layer's shadows per stage
                     for (int k = 0; k < 2; k++) shadow_task(3 + k, Q.w[nh - 1 - l], wsh(3 + k, nh - 1 - l), Q.in_of(nh - 1 - l));
+                if (ln()) {
+                    begin_stage();
+                    for (int k = 0; k < 2; k++) ln_fwd(1 + k, l, L.za[k][l], L.sa[k][l], hview(L.ha[k][l], B), B);
+                }
             }
             begin_stage();
             {
@@ -781,16 +849,24 @@ struct Builder {
                 add(t, cdiv(B, loss_rows()));
             }
             // ---- dL/da through both critics (input gradients only: the Q weights are constants here, quirk Q2) -------
+            auto DZA = [&](int k, int x) { return ln() ? hview(L.dza[k][x], B) : hview(L.dha[k][x], B); };
+            auto ln_bwd_a = [&](int x) {
+                if (!ln()) return;
+                begin_stage();
+                for (int k = 0; k < 2; k++) ln_bwd(1 + k, x, hview(L.dha[k][x], B), L.za[k][x], L.sa[k][x], hview(L.dza[k][x], B), nullptr, B);
+            };
+            ln_bwd_a(nh - 1);
             for (int s = 1; s <= nh; s++) {
                 begin_stage();
                 const int l = nh - s;
                 for (int k = 0; k < 2; k++) {
                     const int net = 1 + k;
                     if (l >= 1)
-                        gemm(hview(L.dha[k][l], B), 0, wsh(net, l), 1, B, H, H, epi_mask(hview(L.dha[k][l - 1], B), hview(L.ha[k][l - 1], B)));
+                        gemm(DZA(k, l), 0, wsh(net, l), 1, B, H, H, epi_mask(hview(L.dha[k][l - 1], B), hview(L.ha[k][l - 1], B)));
                     else   // layer 0: only the action columns [obs, obs+act) of W_0 [H, obs+act] (their own shadow PM)
-                        gemm(hview(L.dha[k][0], B), 0, wsh_act(net), 1, B, act, H, epi_f32(W(L.da[k]), act, null_ref()));
+                        gemm(DZA(k, 0), 0, wsh_act(net), 1, B, act, H, epi_f32(W(L.da[k]), act, null_ref()));
                 }
+                if (l >= 1) ln_bwd_a(l - 1);
             }
             begin_stage();
             {
@@ -803,14 +879,22 @@ struct Builder {
             // ---- policy backward (current-state rows B..2B of the policy activations) --------------------------------
             //   stage 0: dh_{nh-1} from the heads ; stage s: dh_{nh-1-s}, dW of the layer above ; last: dW_0
             auto hp_cur = [&](int l) { return hview(L.hp[l], B, B, 2); };
+            auto DZP = [&](int x) { return ln() ? hview(L.dzp[x], B) : hview(L.dhp[x], B); };
+            auto ln_bwd_p = [&](int x) {      // the policy's current-state rows are rows B..2B of its z / statistics
+                if (!ln()) return;
+                begin_stage();
+                const PmView gg = hview(L.ggp[x], B);
+                ln_bwd(0, x, hview(L.dhp[x], B), L.zp[x] + (int64_t)B * H, L.sp[x] + 2 * (int64_t)B, hview(L.dzp[x], B), &gg, B);
+            };
             for (int s = 0; s <= nh; s++) {
                 begin_stage();
                 if (s == 0) {
                     gemm(ghead(B), 0, wsh_head(), 1, B, H, A2, epi_mask(hview(L.dhp[nh - 1], B), hp_cur(nh - 1)));
+                    ln_bwd_p(nh - 1);
                 } else {
                     const int l = nh - s;      // dh_l available; produce dh_{l-1} (if l >= 1)
                     if (l >= 1)
-                        gemm(hview(L.dhp[l], B), 0, wsh(0, l), 1, B, H, H, epi_mask(hview(L.dhp[l - 1], B), hp_cur(l - 1)));
+                        gemm(DZP(l), 0, wsh(0, l), 1, B, H, H, epi_mask(hview(L.dhp[l - 1], B), hp_cur(l - 1)));
                     if (s == 1) {              // heads: dW = g^T h_{nh-1}
                         Task t = blank(T_GEMM); t.epi = EPI_ADAM; t.adam = adam_args(0, P.w_out);
                         if (epilogue_shadows()) t.adam.shadow = wsh_head().ref;
@@ -818,17 +902,20 @@ struct Builder {
                         bias_adam(0, P.b_out, ghead(B), B, A2);
                     } else {
                         const int lw = l + 1;  // dW of the layer whose dX ran in the previous stage
-                        gemm(hview(L.dhp[lw], B), 1, hp_cur(lw - 1), 1, H, H, B, epi_adam(0, lw));
-                        bias_adam(0, P.b[lw], hview(L.dhp[lw], B), B, H);
+                        gemm(DZP(lw), 1, hp_cur(lw - 1), 1, H, H, B, epi_adam(0, lw));
+                        bias_adam(0, P.b[lw], DZP(lw), B, H);
+                        if (ln()) ln_param_adam(0, lw, hview(L.ggp[lw], B), hview(L.dhp[lw], B), B);
                     }
                     if (s == nh) {
-                        gemm(hview(L.dhp[0], B), 1, X1(obs), 1, H, obs, B, epi_adam(0, 0));
-                        bias_adam(0, P.b[0], hview(L.dhp[0], B), B, H);
+                        gemm(DZP(0), 1, X1(obs), 1, H, obs, B, epi_adam(0, 0));
+                        bias_adam(0, P.b[0], DZP(0), B, H);
+                        if (ln()) ln_param_adam(0, 0, hview(L.ggp[0], B), hview(L.dhp[0], B), B);
                     }
                     if (task_shadows()) {      // shadow of what the PREVIOUS stage stepped: heads (s-1 = 1) or hidden layer nh-s+2
                         if (s == 2) shadow_task(0, P.w_out, wsh_head(), H);
                         else if (s > 2) shadow_task(0, P.w[nh - s + 2], wsh(0, nh - s + 2), P.in_of(nh - s + 2));
                     }
+                    if (l >= 1) ln_bwd_p(l - 1);
                 }
             }
         }

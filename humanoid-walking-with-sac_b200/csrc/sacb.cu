@@ -55,6 +55,7 @@ extern "C" int sacb_create(const sacb_config *cfg, sacb_handle *out) {
     if (cfg->n_hidden != 2 && cfg->n_hidden != 3) return fail(SACB_ERR_ARG, "n_hidden must be 2 (networks_model1) or 3 (networks_model2)");
     if (cfg->max_batch < 1 || cfg->n_agents < 1 || cfg->capacity < 1) return fail(SACB_ERR_ARG, "bad max_batch / n_agents / capacity");
     if (2 * cfg->act_dim > 256) return fail(SACB_ERR_ARG, "act_dim > 128 unsupported");
+    if (cfg->layer_norm && cfg->hidden_dim > 1024) return fail(SACB_ERR_ARG, "layer_norm: hidden_dim > 1024 unsupported (a row is normalised in registers)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device >= ndev) { cudaGetLastError(); return fail(SACB_ERR_DEVICE, "no CUDA device: this library has no CPU fallback"); }
     cudaDeviceProp prop;
@@ -65,7 +66,7 @@ extern "C" int sacb_create(const sacb_config *cfg, sacb_handle *out) {
     h->cfg = *cfg;
     h->sm_count = prop.multiProcessorCount;
     h->use_pdl = getenv("SACB_NO_PDL") ? 0 : 1;
-    h->L.build(cfg->obs_dim, cfg->act_dim, cfg->hidden_dim, cfg->n_hidden, cfg->max_batch);
+    h->L.build(cfg->obs_dim, cfg->act_dim, cfg->hidden_dim, cfg->n_hidden, cfg->max_batch, cfg->layer_norm != 0);
     const int n = cfg->n_agents;
     auto bail = [&](int rc) { sacb_destroy(h); return rc; };
     {   // the update runs on the highest-priority stream: when sacb_per_step overlaps replay work (second, lowest-priority stream) with the
@@ -96,6 +97,16 @@ extern "C" int sacb_create(const sacb_config *cfg, sacb_handle *out) {
         for (int t = 0; t < kAdamTable; t++) adam_factors(t, cfg->lr, tab[t].x, tab[t].y);
         if (cudaMalloc(&h->adam_table, sizeof(float2) * kAdamTable) != cudaSuccess) return bail(fail(SACB_ERR_NOMEM, "device allocation failed"));
         cudaMemcpyAsync(h->adam_table, tab.data(), sizeof(float2) * kAdamTable, cudaMemcpyHostToDevice, h->stream);
+        cudaStreamSynchronize(h->stream);
+    }
+    if (cfg->layer_norm) {      // LayerNorm weights start at 1 (torch.nn.LayerNorm), biases at 0 (the memset above)
+        std::vector<float> ones(cfg->hidden_dim, 1.0f);
+        for (int a = 0; a < n; a++)
+            for (int net = 0; net < 5; net++) {
+                const NetLayout &nl = net == 0 ? h->L.pol : h->L.q;
+                for (int l = 0; l < nl.n_hidden; l++)
+                    cudaMemcpyAsync(h->arena + (int64_t)a * h->L.arena_size + h->L.param[net] + nl.g[l], ones.data(), sizeof(float) * cfg->hidden_dim, cudaMemcpyHostToDevice, h->stream);
+            }
         cudaStreamSynchronize(h->stream);
     }
     int rc = scalars_init(h);

@@ -582,6 +582,108 @@ __device__ __forceinline__ void task_bias_adam(const Task &t, int tile, const Pr
     }
 }
 
+// ---- opt-in LayerNorm variant (no counterpart in the reference: DESIGN.md) --------------------------------------------------------
+// One warp per row, the row (H <= 1024 values, H % 8 == 0) held in registers: 8 consecutive elements per lane and trip.
+constexpr int kLnRows = kThreads / 32, kLnMaxH = 1024, kLnTrips = kLnMaxH / 256;
+__device__ __forceinline__ void pm_store8(const Pm &p, int64_t row, int col, const float (&x)[8]) {
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) split_pack2(x[2 * i], x[2 * i + 1], hi[i], lo[i]);
+    __nv_bfloat16 *q = p.hi + row * p.ld + col;
+    *reinterpret_cast<uint4 *>(q) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4 *>(q + p.plane) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+__device__ __forceinline__ void load8f(const float *p, float (&out)[8]) {
+    const float4 a = __ldcg(reinterpret_cast<const float4 *>(p)), b = __ldcg(reinterpret_cast<const float4 *>(p + 4));
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+}
+// T_LN_FWD: h = relu((z - mean) * rstd * gamma + beta), mean / biased variance over the H columns of the row (torch.nn.LayerNorm, eps f0).
+//   p0 = z fp32 [rows, H] (Linear output incl. bias, written by the GEMM of the stage before) ; p1 = gamma [H] ; p2 = beta [H] ;
+//   p3 = statistics out [rows][2] = (mean, rstd) ; pm0 = h PM [rows, H] ; i0 = rows ; i1 = H ; f0 = eps
+__device__ __forceinline__ void task_ln_fwd(const Task &t, int tile, const Program &P, int agent) {
+    const int rows = t.i[0], H = t.i[1], warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = tile * kLnRows + warp;
+    if (row >= rows) return;      // warp-uniform
+    const float *z = resolve(t.p[0], P.bases, agent) + (int64_t)row * H, *gam = resolve(t.p[1], P.bases, agent), *bet = resolve(t.p[2], P.bases, agent);
+    float v[kLnTrips][8];
+    float s = 0.f;
+#pragma unroll
+    for (int u = 0; u < kLnTrips; u++) {
+        const int j = u * 256 + lane * 8;
+        if (j < H) {
+            load8f(z + j, v[u]);
+#pragma unroll
+            for (int i = 0; i < 8; i++) s += v[u][i];
+        }
+    }
+    const float mean = warp_sum(s) / (float)H;
+    float q = 0.f;
+#pragma unroll
+    for (int u = 0; u < kLnTrips; u++)
+        if (u * 256 + lane * 8 < H) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) { const float d = v[u][i] - mean; q += d * d; }
+        }
+    const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)H + t.f[0]);
+    const Pm h = resolve_pm(t.pm[0], P.bases, agent);
+#pragma unroll
+    for (int u = 0; u < kLnTrips; u++) {
+        const int j = u * 256 + lane * 8;
+        if (j < H) {
+            float g[8], b[8], y[8];
+            load8f(gam + j, g); load8f(bet + j, b);
+#pragma unroll
+            for (int i = 0; i < 8; i++) y[i] = fmaxf((v[u][i] - mean) * rstd * g[i] + b[i], 0.f);
+            pm_store8(h, row, j, y);
+        }
+    }
+    if (lane == 0) { float *st = resolve(t.p[3], P.bases, agent) + 2 * (int64_t)row; st[0] = mean; st[1] = rstd; }
+}
+// T_LN_BWD: dpre = gradient at the LayerNorm output (ReLU mask already applied by the producer) -> dz = gradient at the Linear output:
+//   g = dpre * gamma ; xhat = (z - mean) * rstd ; dz = rstd * (g - mean_j(g) - xhat * mean_j(g * xhat)) ; gg = dpre * xhat (its column
+//   sums over the batch are dgamma, those of dpre are dbeta: T_BIAS_ADAM tasks)
+//   pm0 = dpre PM [B, H] ; p0 = z fp32 (first of the B rows) ; p1 = gamma ; p3 = statistics (first of the B rows) ;
+//   pm1 = dz PM out ; pm2 = gg PM out (null base: not wanted) ; i0 = B ; i1 = H
+__device__ __forceinline__ void task_ln_bwd(const Task &t, int tile, const Program &P, int agent) {
+    const int rows = t.i[0], H = t.i[1], warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = tile * kLnRows + warp;
+    if (row >= rows) return;
+    const float *z = resolve(t.p[0], P.bases, agent) + (int64_t)row * H, *gam = resolve(t.p[1], P.bases, agent);
+    const float *st = resolve(t.p[3], P.bases, agent) + 2 * (int64_t)row;
+    const float mean = ldcg(st), rstd = ldcg(st + 1);
+    const Pm dpre = resolve_pm(t.pm[0], P.bases, agent), dz = resolve_pm(t.pm[1], P.bases, agent);
+    const bool want_gg = !is_null(t.pm[2].base);
+    float g[kLnTrips][8], xh[kLnTrips][8];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int u = 0; u < kLnTrips; u++) {
+        const int j = u * 256 + lane * 8;
+        if (j < H) {
+            float d[8], zz[8], gm[8];
+            pm_load8(dpre, row, j, d); load8f(z + j, zz); load8f(gam + j, gm);
+#pragma unroll
+            for (int i = 0; i < 8; i++) { xh[u][i] = (zz[i] - mean) * rstd; g[u][i] = d[i] * gm[i]; s1 += g[u][i]; s2 += g[u][i] * xh[u][i]; }
+            if (want_gg) {
+                float gg[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) gg[i] = d[i] * xh[u][i];
+                pm_store8(resolve_pm(t.pm[2], P.bases, agent), row, j, gg);
+            }
+        }
+    }
+    const float m1 = warp_sum(s1) / (float)H, m2 = warp_sum(s2) / (float)H;
+#pragma unroll
+    for (int u = 0; u < kLnTrips; u++) {
+        const int j = u * 256 + lane * 8;
+        if (j < H) {
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) o[i] = rstd * (g[u][i] - m1 - xh[u][i] * m2);
+            pm_store8(dz, row, j, o);
+        }
+    }
+}
+
 // T_FINISH (one thread): finalise the loss scalars from the per-tile partials (fixed order), the temperature step
 // (sac_imp.py:128-135) and the optimizer step counters (+1 each, sac_imp.py:109,113,125,134).
 //   p0 = critic partials [nt,2] (null: skip) ; p1 = actor partials [nt,2] (null: skip) ; p2 = exported log_alpha gradient (or null)

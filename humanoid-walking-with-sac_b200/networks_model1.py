@@ -49,11 +49,15 @@ class _ArenaModule(nn.Module):
 
 
 class QNetwork(_ArenaModule):
-    def __init__(self, state_dim, action_dim, hidden_dim=DEFAULT_HIDDEN):
+    def __init__(self, state_dim, action_dim, hidden_dim=DEFAULT_HIDDEN, *, layer_norm=False):
+        """layer_norm=True (extension, default off: the reference has no LayerNorm -- networks_model2.py:86 is only a comment) puts
+        `ln{i}` = nn.LayerNorm(hidden_dim) between `fc{i}` and its ReLU; parameters then come as fc1.*, ln1.*, fc2.*, ln2.*, ..."""
         super().__init__()
         widths = [state_dim + action_dim] + [hidden_dim] * self.N_HIDDEN
         for i in range(self.N_HIDDEN):
             setattr(self, f"fc{i + 1}", nn.Linear(widths[i], widths[i + 1]))
+            if layer_norm:
+                setattr(self, f"ln{i + 1}", nn.LayerNorm(hidden_dim))
         setattr(self, f"fc{self.N_HIDDEN + 1}", nn.Linear(hidden_dim, 1))
         self.apply(self._init_weights)
 
@@ -70,11 +74,13 @@ class QNetwork(_ArenaModule):
 
 
 class GaussianPolicy(_ArenaModule):
-    def __init__(self, state_dim, action_dim, hidden_dim=DEFAULT_HIDDEN, action_bounds=None):
+    def __init__(self, state_dim, action_dim, hidden_dim=DEFAULT_HIDDEN, action_bounds=None, *, layer_norm=False):
         super().__init__()
         widths = [state_dim] + [hidden_dim] * self.N_HIDDEN
         for i in range(self.N_HIDDEN):
             setattr(self, f"fc{i + 1}", nn.Linear(widths[i], widths[i + 1]))
+            if layer_norm:
+                setattr(self, f"ln{i + 1}", nn.LayerNorm(hidden_dim))
         self.mean = nn.Linear(hidden_dim, action_dim)
         self.log_std = nn.Linear(hidden_dim, action_dim)
         lo, hi = (-0.4, 0.4) if action_bounds is None else action_bounds      # networks_model1.py:52-55

@@ -20,14 +20,14 @@ def _init_orthogonal(module):
 class QNetwork(_m1.QNetwork):
     N_HIDDEN = N_HIDDEN
 
-    def __init__(self, state_dim, action_dim, hidden_dim=DEFAULT_HIDDEN):
-        super().__init__(state_dim, action_dim, hidden_dim)
+    def __init__(self, state_dim, action_dim, hidden_dim=DEFAULT_HIDDEN, *, layer_norm=False):
+        super().__init__(state_dim, action_dim, hidden_dim, layer_norm=layer_norm)
 
 
 class GaussianPolicy(_m1.GaussianPolicy):
     N_HIDDEN = N_HIDDEN
     _init_weights = staticmethod(_init_orthogonal)
 
-    def __init__(self, state_dim, action_dim, hidden_dim=DEFAULT_HIDDEN, device="cuda", action_bounds=None):
-        super().__init__(state_dim, action_dim, hidden_dim, action_bounds)
+    def __init__(self, state_dim, action_dim, hidden_dim=DEFAULT_HIDDEN, device="cuda", action_bounds=None, *, layer_norm=False):
+        super().__init__(state_dim, action_dim, hidden_dim, action_bounds, layer_norm=layer_norm)
         self.device = device     # kept for signature compatibility; placement is decided by the owning SAC

@@ -96,7 +96,7 @@ class SAC:
     def __init__(self, state_dim, action_dim, hidden_dim=256, gamma=0.99, tau=0.005, lr=3e-4, alpha=0.2,
                  automatic_entropy_tuning=True, device="cuda" if torch.cuda.is_available() else "cpu", *,
                  replay="uniform", capacity=1000000, max_batch=256, math="bf16x3", launch="staged", seed=None,
-                 per_alpha=0.6, per_beta_start=0.4, per_beta_frames=100000, per_weighted_loss=False, action_bounds=None):
+                 per_alpha=0.6, per_beta_start=0.4, per_beta_frames=100000, per_weighted_loss=False, action_bounds=None, layer_norm=False):
         if not str(device).startswith("cuda"):
             raise RuntimeError("this SAC runs on a B200 only (device='cuda[:i]'); there is no CPU path")
         self.gamma, self.tau, self.device = gamma, tau, device
@@ -107,11 +107,13 @@ class SAC:
         # networks: built on the host with the reference's initialisers (same global-RNG consumption order as
         # sac_imp.py:28-36), then uploaded; afterwards every parameter aliases the device arena
         kw = {} if action_bounds is None else {"action_bounds": action_bounds}
-        self.policy = GaussianPolicy(state_dim, action_dim, hidden_dim, **kw)
-        self.q1 = QNetwork(state_dim, action_dim, hidden_dim)
-        self.q2 = QNetwork(state_dim, action_dim, hidden_dim)
-        self.q1_target = QNetwork(state_dim, action_dim, hidden_dim)
-        self.q2_target = QNetwork(state_dim, action_dim, hidden_dim)
+        ln = {"layer_norm": True} if layer_norm else {}      # extension, default off (no LayerNorm in the reference): DESIGN.md
+        self.layer_norm = bool(layer_norm)
+        self.policy = GaussianPolicy(state_dim, action_dim, hidden_dim, **kw, **ln)
+        self.q1 = QNetwork(state_dim, action_dim, hidden_dim, **ln)
+        self.q2 = QNetwork(state_dim, action_dim, hidden_dim, **ln)
+        self.q1_target = QNetwork(state_dim, action_dim, hidden_dim, **ln)
+        self.q2_target = QNetwork(state_dim, action_dim, hidden_dim, **ln)
         self.q1_target.load_state_dict(self.q1.state_dict())
         self.q2_target.load_state_dict(self.q2.state_dict())
         n_hidden = getattr(self.q1, "N_HIDDEN", 2)
@@ -126,6 +128,7 @@ class SAC:
         cfg.capacity, cfg.max_batch, cfg.n_agents, cfg.device = capacity, max_batch, 1, dev_index
         cfg.per_alpha, cfg.per_beta_start, cfg.per_beta_frames = per_alpha, per_beta_start, per_beta_frames
         cfg.per_weighted_loss = int(bool(per_weighted_loss))
+        cfg.layer_norm = int(bool(layer_norm))
         cfg.math_mode = {"fp32": N.MATH_FP32, "bf16x3": N.MATH_BF16X3}[math]
         cfg.launch_mode = {"staged": N.LAUNCH_STAGED, "persistent": N.LAUNCH_PERSISTENT}[launch]
         cfg.seed = random.getrandbits(63) if seed is None else int(seed)

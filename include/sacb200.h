@@ -66,7 +66,10 @@ typedef struct {
     int32_t device;                /* CUDA ordinal */
     uint64_t seed;                 /* Philox key for on-device eps / index draws (production mode) */
     int32_t per_weighted_loss;     /* extension: IS-weighted critic loss + |td| priority write-back */
-    int32_t reserved[7];
+    int32_t layer_norm;            /* extension, default 0 (the reference has none: networks_model2.py:86 is a comment): LayerNorm with
+                                      affine parameters between every hidden Linear and its ReLU of all five networks; parameter
+                                      tensors per hidden layer then are weight, bias, ln.weight, ln.bias.  No reference parity. */
+    int32_t reserved[6];
 } sacb_config;
 
 void sacb_default_config(sacb_config *cfg);

@@ -43,7 +43,10 @@ class TorchSAC:
     # ---- networks -------------------------------------------------------------------------------------------------
     def _trunk(self, P, x):
         for i in range(1, self.n_hidden + 1):
-            x = F.relu(F.linear(x, P[f"fc{i}.weight"], P[f"fc{i}.bias"]))
+            x = F.linear(x, P[f"fc{i}.weight"], P[f"fc{i}.bias"])
+            if f"ln{i}.weight" in P:      # the product's opt-in LayerNorm variant (NOT in the reference): torch.nn.LayerNorm semantics, eps 1e-5
+                x = F.layer_norm(x, (x.shape[-1],), P[f"ln{i}.weight"], P[f"ln{i}.bias"], 1e-5)
+            x = F.relu(x)
         return x
 
     def q(self, P, s, a):                                    # networks_model1.py:27-33
