@@ -17,6 +17,7 @@ CASES = {
     "tiny_m2": dict(obs=11, act=3, hidden=64, n_hidden=3, batch=32, steps=3, seed=5),
     "ragged_m1": dict(obs=24, act=4, hidden=72, n_hidden=2, batch=37, steps=2, seed=6),
     "c2_like_m2": dict(obs=348, act=17, hidden=512, n_hidden=3, batch=256, steps=2, seed=7),
+    "large_batch_m2": dict(obs=348, act=17, hidden=512, n_hidden=3, batch=2048, steps=1, seed=8),      # throughput form (stream kernel + split stages)
 }
 
 
