@@ -136,6 +136,23 @@ __global__ void __launch_bounds__(512) mlp_layer_kernel(LayerArgs a, const float
     }
 }
 
+// LayerNorm variant: y[row, :] <- relu(LN(y[row, :]) * gamma + beta) in place, one CTA per row, behind the layer kernel in the PDL chain
+__global__ void __launch_bounds__(256) ln_relu_rows_kernel(float *y, int ldy, int H, const float *g, const float *be, int64_t agent_stride, int rows_per_agent) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    __shared__ float red[32];
+    const int row = blockIdx.x;
+    const int64_t ao = (int64_t)(row / rows_per_agent) * agent_stride;
+    float *yr = y + (int64_t)row * ldy;
+    float ps = 0.f;
+    for (int o = threadIdx.x; o < H; o += blockDim.x) ps += __ldcg(yr + o);
+    const float mean = block_sum(ps, red) / (float)H;
+    float pq = 0.f;
+    for (int o = threadIdx.x; o < H; o += blockDim.x) { const float d = __ldcg(yr + o) - mean; pq += d * d; }
+    const float rstd = 1.0f / sqrtf(block_sum(pq, red) / (float)H + 1e-5f);
+    for (int o = threadIdx.x; o < H; o += blockDim.x) yr[o] = fmaxf((__ldcg(yr + o) - mean) * rstd * __ldcg(g + ao + o) + __ldcg(be + ao + o), 0.f);
+}
+
 __global__ void action_pdl_kernel(const float *head, const float *eps, int n, int A, int evaluate, float scale, float bias, float *act, uint64_t seed, uint32_t counter) {
     asm volatile("griddepcontrol.wait;" ::: "memory");
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -187,10 +204,14 @@ static int select_action_rows(sacb_handle h, int agent0, int rows, int rows_per_
     for (int l = 0; l <= nh; l++) {
         LayerArgs a;
         a.w = base + (l < nh ? nl.w[l] : nl.w_out); a.b = base + (l < nh ? nl.b[l] : nl.b_out);
-        a.in = l == 0 ? O : H; a.out = l < nh ? H : 2 * A; a.relu = l < nh; a.agent_stride = h->L.arena_size;
+        a.in = l == 0 ? O : H; a.out = l < nh ? H : 2 * A; a.relu = l < nh && !nl.layer_norm; a.agent_stride = h->L.arena_size;
         float *y = l < nh ? bufs[l & 1] : d_head;
         const int ldy = l < nh ? H : 2 * A;
         SACB_CUDA(launch_chain(mlp_layer_kernel, dim3((a.out + 15) / 16, rows), dim3(512), sizeof(float) * a.in, h->stream, a, x, ldx, y, ldy, rows_per_agent));
+        if (l < nh && nl.layer_norm) {
+            SACB_CUDA(launch_chain(ln_relu_rows_kernel, dim3(rows), dim3(256), 0, h->stream, y, ldy, H, base + nl.g[l], base + nl.be[l], (int64_t)h->L.arena_size, rows_per_agent));
+            h->kernel_launches++;
+        }
         x = y; ldx = ldy;
     }
     SACB_CUDA(launch_chain(action_pdl_kernel, dim3((rows * A + 127) / 128), dim3(128), 0, h->stream, (const float *)d_head, (const float *)(use_eps ? d_eps : nullptr),
@@ -223,20 +244,12 @@ static int select_action_single_cta(sacb_handle h, int agent, const float *obs, 
 extern "C" int sacb_select_action(sacb_handle h, int agent, const float *obs, int evaluate, const float *eps, float *action_out) {
     if (!h || !obs || !action_out || agent < 0 || agent >= h->cfg.n_agents) return fail(SACB_ERR_ARG, "bad argument");
     static const bool single = getenv("SACB_ACT_SINGLE_CTA") != nullptr;
-    // LayerNorm variant: a layer's output row has to be complete before it is normalised -- the one-CTA-per-row kernel does that
-    if (single || h->cfg.layer_norm) return select_action_single_cta(h, agent, obs, evaluate, eps, action_out);
+    if (single) return select_action_single_cta(h, agent, obs, evaluate, eps, action_out);
     return select_action_rows(h, agent, 1, 1, obs, evaluate, eps, action_out);
 }
 
 extern "C" int sacb_select_action_batch(sacb_handle h, const float *obs, int evaluate, const float *eps, float *action_out) {
     if (!h || !obs || !action_out) return fail(SACB_ERR_ARG, "bad argument");
-    if (h->cfg.layer_norm) {
-        for (int a = 0; a < h->cfg.n_agents; a++) {
-            const int rc = select_action_single_cta(h, a, obs + (int64_t)a * h->cfg.obs_dim, evaluate, eps ? eps + (int64_t)a * h->cfg.act_dim : nullptr, action_out + (int64_t)a * h->cfg.act_dim);
-            if (rc) return rc;
-        }
-        return SACB_OK;
-    }
     return select_action_rows(h, 0, h->cfg.n_agents, 1, obs, evaluate, eps, action_out);
 }
 
