@@ -114,6 +114,7 @@ struct sacb_handle_s {
     sacb_config cfg;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    bool per_fused = false;              // the last prioritized sample ran chunk pass + search as one launch (where its flagged count is kept)
     cudaStream_t stream2 = nullptr;      // prioritized replay work that overlaps the update (sacb_per_step)
     cudaEvent_t ev_td = nullptr, ev_sampled = nullptr;
     int64_t sample_k = 0;                // rows of the minibatch the last prioritized sample left on the device (0: none)

@@ -5,12 +5,12 @@
 // contiguous ~2.9 KB read (Humanoid), gathered by one warp with coalesced loads.
 //
 // PER sampling reproduces np.random.choice(len, B, p=probs) bit-for-bit downstream of the p**alpha table:
-// Three launches per sample() call; the last CTA of each grid to finish runs the serial step behind the parallel pass:
-//   per_sum      float32 total with numpy's pairwise-summation tree (exact same association): CTA subtrees, then the top
-//   per_chunk    probs = p_alpha / total (float32), float64 chunk sums, count of "fine" elements; then the exclusive scan
-//   per_search   per-sample inverse-CDF search + provable ambiguity test (see DESIGN.md "PER exactness"); then the sequential
-//                float64 cumsum (numpy's own order) for samples the test could not certify, IS weights (N p)^-beta / max,
-//                logical indices, ring slots for the update's gather
+// Two launches per sample() call (per_sum, per_chunk_search = the two passes below claimed as work items of ONE grid):
+//   per_sum      float32 total with numpy's pairwise-summation tree (exact same association): CTA subtrees, then the top (last CTA)
+//   chunk groups probs = p_alpha / total (float32), float64 chunk sums, count of "fine" elements
+//   search groups exclusive scan of the chunk sums (per group, shared memory), per-sample inverse-CDF search + provable ambiguity test
+//                (see DESIGN.md "PER exactness"); the last group then runs the sequential float64 cumsum (numpy's own order) for
+//                samples the test could not certify, IS weights (N p)^-beta / max, logical indices, ring slots for the update's gather
 #include <cmath>
 #include <cstring>
 #include <algorithm>
@@ -142,13 +142,14 @@ __device__ float pw_block_sum(const float *a, int64_t start, int n, float *s_hea
 // (blockIdx % kTicketGroups, counters 128 B apart), the last CTA of a group takes one of the final counter.
 constexpr int kTicketGroups = 8, kTicketStride = 32;      // ints
 constexpr int kTicketInts = (kTicketGroups + 1) * kTicketStride;
-__device__ __forceinline__ bool last_block_done(int *ticket) {
+__device__ __forceinline__ bool last_block_done(int *ticket, int n_blocks = -1, int block = -1) {      // default: the whole grid
     __shared__ int s_last;
+    if (n_blocks < 0) { n_blocks = (int)gridDim.x; block = (int)blockIdx.x; }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const int G = min(kTicketGroups, (int)gridDim.x), g = blockIdx.x % G;
-        const int group_size = ((int)gridDim.x - g + G - 1) / G;
+        const int G = min(kTicketGroups, n_blocks), g = block % G;
+        const int group_size = (n_blocks - g + G - 1) / G;
         int last = 0;
         if (atomicAdd(ticket + g * kTicketStride, 1) == group_size - 1) {
             ticket[g * kTicketStride] = 0;
@@ -303,21 +304,24 @@ __device__ void carry_scan(const double *chunk_sum, const int *chunk_fine, int n
 }
 
 // one warp per chunk of 1024 probabilities: float64 chunk sum + count of "fine" elements; the last CTA scans the chunk sums
-__global__ void __launch_bounds__(256) per_chunk(const float *p_alpha, int64_t n, const float *total, double *chunk_sum, int *chunk_fine,
-                                                 int n_chunks, double *carry, int *counters, int *ticket) {
-    SACB_PDL_ENTER();
+__device__ __forceinline__ void chunk_group(const float *p_alpha, int64_t n, float total, int group, double *chunk_sum, int *chunk_fine) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int64_t chunk = (int64_t)blockIdx.x * 8 + warp;
+    const int64_t chunk = (int64_t)group * 8 + warp;
     if (chunk * kChunk < n) {
         int fine;
         float q[32];
-        lane_probs(p_alpha, chunk * kChunk + lane * 32, n, *total, q);
+        lane_probs(p_alpha, chunk * kChunk + lane * 32, n, total, q);
         const double v = lane_pass(q, fine);
         double wt;
         warp_excl_scan(v, lane, wt);
         for (int o = 16; o > 0; o >>= 1) fine += __shfl_xor_sync(0xffffffffu, fine, o);
         if (lane == 0) { chunk_sum[chunk] = wt; chunk_fine[chunk] = fine; }
     }
+}
+__global__ void __launch_bounds__(256) per_chunk(const float *p_alpha, int64_t n, const float *total, double *chunk_sum, int *chunk_fine,
+                                                 int n_chunks, double *carry, int *counters, int *ticket) {
+    SACB_PDL_ENTER();
+    chunk_group(p_alpha, n, *total, (int)blockIdx.x, chunk_sum, chunk_fine);
     if (!last_block_done(ticket)) return;
     carry_scan(chunk_sum, chunk_fine, n_chunks, carry, counters);
 }
@@ -399,20 +403,20 @@ __device__ void exact_pass(const float *p_alpha, int64_t n, float tot, double *c
 
 // one warp per sample: inverse-CDF search + ambiguity test.  The last CTA to finish runs the serial tail of sample():
 // the exact pass for flagged samples (rare), IS weights (replay_buffer.py:67-68), ring slots for the update's gather.
-__global__ void __launch_bounds__(256) per_search(const float *p_alpha, int64_t n, const float *total, const double *carry, int n_chunks,
-                                                  const double *u, int B, int *counters, int64_t *idx_out, int *flagged, int *ticket,
-                                                  double *carry_exact, const double *chunk_sum, const int *chunk_fine,
-                                                  float neg_beta, float *weights, int32_t *slots, float *isw_ws, int64_t *idx_copy) {
-    SACB_PDL_ENTER();
+struct SearchArgs {
+    const float *p_alpha; int64_t n; const double *u; int B; int *counters; int64_t *idx_out; int *flagged; int *ticket;
+    double *carry_exact; const double *chunk_sum; const int *chunk_fine; int n_chunks;
+    float neg_beta; float *weights; int32_t *slots; float *isw_ws; int64_t *idx_copy;
+};
+// group sg of n_sg: 8 samples, one per warp; cr = chunk prefixes (shared or global), F = number of fine elements.  The last group to
+// finish runs the serial tail.  Returns true in that group only (after the tail).
+__device__ __forceinline__ bool search_group(const SearchArgs &a, const double *cr, int F, float tot, int sg, int n_sg) {
+    const float *p_alpha = a.p_alpha; const int64_t n = a.n; const double *u = a.u; const int B = a.B, n_chunks = a.n_chunks;
+    int *counters = a.counters; int64_t *idx_out = a.idx_out; int *flagged = a.flagged;
+    double *carry_exact = a.carry_exact; const double *chunk_sum = a.chunk_sum; const int *chunk_fine = a.chunk_fine;
+    const float neg_beta = a.neg_beta; float *weights = a.weights; int32_t *slots = a.slots; float *isw_ws = a.isw_ws; int64_t *idx_copy = a.idx_copy;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int j = blockIdx.x * 8 + warp;
-    const float tot = *total;
-    // the chunk prefixes in shared memory (one coalesced read instead of ten dependent L2 round trips per sample)
-    __shared__ double s_carry[kCarrySmem];
-    const bool staged = n_chunks + 1 <= kCarrySmem;
-    if (staged) for (int i = threadIdx.x; i <= n_chunks; i += blockDim.x) s_carry[i] = carry[i];
-    __syncthreads();
-    const double *cr = staged ? s_carry : carry;
+    const int j = sg * 8 + warp;
     if (j < B) {      // warp-uniform
         const double last = cr[n_chunks];
         const double uu = u[j];
@@ -432,7 +436,6 @@ __global__ void __launch_bounds__(256) per_search(const float *p_alpha, int64_t 
         //    rounding (<= eps / 2) per divide.
         // The window is twice that, plus 1e-13 for the crossing-only evaluation of the nearest cdf value below.  Measured on the
         // adversarial sets (1 M elements, F = 10 126): |parallel - sequential| = 0.12 F eps.  Zero when no element is fine.
-        const int F = counters[0];
         const double window = F == 0 ? 0.0 : ((12.0 * (double)F + 8.0) * 2.220446049250313e-16) / last + 4.440892098500626e-16 + 1e-13;
         // chunk: last c with carry[c]/last <= u
         int lo = 0, hi = n_chunks - 1;
@@ -485,7 +488,7 @@ __global__ void __launch_bounds__(256) per_search(const float *p_alpha, int64_t 
             if (flag) atomicAdd(counters + 1, 1);
         }
     }
-    if (!last_block_done(ticket)) return;
+    if (!last_block_done(a.ticket, n_sg, sg)) return false;
     // ---- serial tail (one CTA) ----
     if (__ldcg(counters + 1) != 0) {      // CTA-uniform
         __shared__ float s_q[kChunk];
@@ -519,6 +522,57 @@ __global__ void __launch_bounds__(256) per_search(const float *p_alpha, int64_t 
         weights[q] = wn;
         if (isw_ws) isw_ws[q] = wn;
     }
+    return true;
+}
+
+__global__ void __launch_bounds__(256) per_search(const float *total, const double *carry, SearchArgs a) {
+    SACB_PDL_ENTER();
+    const float tot = *total;
+    // the chunk prefixes in shared memory (one coalesced read instead of ten dependent L2 round trips per sample)
+    __shared__ double s_carry[kCarrySmem];
+    const bool staged = a.n_chunks + 1 <= kCarrySmem;
+    if (staged) for (int i = threadIdx.x; i <= a.n_chunks; i += blockDim.x) s_carry[i] = carry[i];
+    __syncthreads();
+    search_group(a, staged ? s_carry : carry, a.counters[0], tot, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// per_chunk and per_search as ONE launch (capacity <= 2 M: the chunk prefixes fit into shared memory).  CTAs claim work items in order
+// from a queue: first the chunk groups, then the search groups.  A search group waits until every chunk group has signalled -- those
+// were all claimed by CTAs that are running, so the wait cannot deadlock whatever the residency -- then scans the chunk sums ITSELF
+// into shared memory (1 K additions, redundantly per group: no second grid-wide rendezvous, no serial tail CTA) and searches its 8
+// samples.  queue[0] = next item, queue[32] = finished chunk groups; the tail of the last search group resets both.
+__global__ void __launch_bounds__(256) per_chunk_search(const float *total, double *chunk_sum, int *chunk_fine, double *carry, int *queue, SearchArgs a) {
+    SACB_PDL_ENTER();
+    __shared__ int s_item;
+    __shared__ double s_carry[kCarrySmem];
+    __shared__ int s_cnt[2];
+    if (threadIdx.x == 0) s_item = atomicAdd(queue, 1);
+    __syncthreads();
+    const int item = s_item, n_cg = (a.n_chunks + 7) / 8, n_sg = (a.B + 7) / 8;
+    const float tot = *total;
+    if (item < n_cg) {
+        chunk_group(a.p_alpha, a.n, tot, item, chunk_sum, chunk_fine);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(queue + 32, 1);
+        return;
+    }
+    const int sg = item - n_cg;
+    if (sg >= n_sg) return;
+    if (threadIdx.x == 0) {
+        unsigned int it = 0;
+        int v;
+        do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(queue + 32) : "memory"); } while (v < n_cg && ++it < (1u << 26));
+    }
+    __syncthreads();
+    carry_scan(chunk_sum, chunk_fine, a.n_chunks, s_carry, s_cnt);      // chunk sums are read with ld.cg (L2): written by other CTAs of this launch
+    __syncthreads();
+    if (sg == 0) {      // the global copies (exact pass, statistics)
+        for (int i = threadIdx.x; i <= a.n_chunks; i += blockDim.x) carry[i] = s_carry[i];
+        if (threadIdx.x == 0) a.counters[0] = s_cnt[0];
+    }
+    if (!search_group(a, s_carry, s_cnt[0], tot, sg, n_sg)) return;
+    if (threadIdx.x == 0) { queue[0] = 0; queue[32] = 0; a.counters[3] = a.counters[1]; a.counters[1] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -900,12 +954,24 @@ int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B
     SACB_CUDA(launch_pdl(per_sum, dim3((2 << depth) - 1), dim3(256), 0, st, pdl, pa, n, depth, w.block_vals, w.total, tickets + 0,
                          w.u, u ? 0 : (int)k, h->cfg.seed, (uint64_t)frame));
     const int n_chunks = (int)((n + kChunk - 1) / kChunk);
-    SACB_CUDA(launch_pdl(per_chunk, dim3((n_chunks + 7) / 8), dim3(256), 0, st, pdl, pa, n, (const float *)w.total, w.chunk_sum, w.chunk_fine,
-                         n_chunks, w.chunk_carry, w.counters, tickets + kTicketInts));
-    SACB_CUDA(launch_pdl(per_search, dim3((int)((k + 7) / 8)), dim3(256), 0, st, pdl, pa, n, (const float *)w.total, (const double *)w.chunk_carry, n_chunks,
-                         (const double *)w.u, (int)k, w.counters, w.idx, w.flagged, tickets + 2 * kTicketInts,
-                         w.cdf_exact, (const double *)w.chunk_sum, (const int *)w.chunk_fine, -(float)beta, w.weights, h->slots, h->ws + h->L.isw, h->last_idx_dev));
-    h->kernel_launches += 3;
+    SearchArgs sa;
+    sa.p_alpha = pa; sa.n = n; sa.u = w.u; sa.B = (int)k; sa.counters = w.counters; sa.idx_out = w.idx; sa.flagged = w.flagged;
+    sa.ticket = tickets + 2 * kTicketInts; sa.carry_exact = w.cdf_exact; sa.chunk_sum = w.chunk_sum; sa.chunk_fine = w.chunk_fine; sa.n_chunks = n_chunks;
+    sa.neg_beta = -(float)beta; sa.weights = w.weights; sa.slots = h->slots; sa.isw_ws = h->ws + h->L.isw; sa.idx_copy = h->last_idx_dev;
+    static const bool split_launch = getenv("SACB_PER_THREE_LAUNCHES") != nullptr;      // A/B: the round-1 form (separate chunk and search launches)
+    if (n_chunks + 1 <= kCarrySmem && !split_launch) {
+        // chunk pass and search as ONE launch: CTAs claim chunk groups, then search groups, in order from a work queue
+        SACB_CUDA(launch_pdl(per_chunk_search, dim3((n_chunks + 7) / 8 + (int)((k + 7) / 8)), dim3(256), 0, st, pdl, (const float *)w.total, w.chunk_sum, w.chunk_fine,
+                             w.chunk_carry, tickets + kTicketInts, sa));
+        h->kernel_launches += 2;
+        h->per_fused = true;
+    } else {
+        SACB_CUDA(launch_pdl(per_chunk, dim3((n_chunks + 7) / 8), dim3(256), 0, st, pdl, pa, n, (const float *)w.total, w.chunk_sum, w.chunk_fine,
+                             n_chunks, w.chunk_carry, w.counters, tickets + kTicketInts));
+        SACB_CUDA(launch_pdl(per_search, dim3((int)((k + 7) / 8)), dim3(256), 0, st, pdl, (const float *)w.total, (const double *)w.chunk_carry, sa));
+        h->kernel_launches += 3;
+        h->per_fused = false;
+    }
     h->sample_k = k;
     if (k_out) *k_out = k;
     return SACB_OK;
@@ -987,12 +1053,12 @@ extern "C" int sacb_per_get_stats(sacb_handle h, int agent, sacb_per_stats *out)
     float tot = 0.f; double last = 0.0;
     const int64_t n = std::max<int64_t>(1, h->r_len[0]);
     const int n_chunks = (int)((n + kChunk - 1) / kChunk);
-    SACB_CUDA(cudaMemcpyAsync(counters, w.counters, sizeof(int) * 3, cudaMemcpyDeviceToHost, h->stream));
+    SACB_CUDA(cudaMemcpyAsync(counters, w.counters, sizeof(int) * 4, cudaMemcpyDeviceToHost, h->stream));
     SACB_CUDA(cudaMemcpyAsync(&tot, w.total, sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     SACB_CUDA(cudaMemcpyAsync(&last, w.chunk_carry + n_chunks, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     SACB_CUDA(cudaStreamSynchronize(h->stream));
     out->frame = h->per_frame[0]; out->pos = h->r_pos[0]; out->len = h->r_len[0];
-    out->n_fine = counters[0]; out->n_flagged = counters[1]; out->n_exact_fallbacks = counters[2];
+    out->n_fine = counters[0]; out->n_flagged = h->per_fused ? counters[3] : counters[1]; out->n_exact_fallbacks = counters[2];
     out->total_f32 = tot; out->cdf_last = last;
     return SACB_OK;
 }
