@@ -169,6 +169,27 @@ __device__ __forceinline__ double uniform_of(uint64_t seed, uint64_t counter, in
     return (double)(x >> 11) * (1.0 / 9007199254740992.0);
 }
 
+// top of the summation tree (heap ids < 2^(top_depth+1) <= 4096) in shared memory: one read of the CTA results, then level by level
+// in numpy's association.  Every thread of the CTA returns the float32 total.
+__device__ float top_tree_sum(int64_t n, int top_depth, const float *top_vals) {
+    __shared__ float s_top[4096];
+    __shared__ unsigned char s_tstate[4096];
+    const unsigned n_ids = 2u << top_depth;
+    for (unsigned k = 1 + threadIdx.x; k < n_ids; k += blockDim.x) {
+        int64_t s2, m2; bool lf = false;
+        const bool ex = pw_node(0, n, kSumBlockMax, k, s2, m2, lf);
+        s_tstate[k] = ex ? (lf ? 1 : 2) : 0;
+        if (ex && lf) s_top[k] = __ldcg(top_vals + k);
+    }
+    __syncthreads();
+    for (int depth = top_depth; depth >= 0; depth--) {
+        for (unsigned k = (1u << depth) + threadIdx.x; k < (2u << depth); k += blockDim.x)
+            if (s_tstate[k] == 2) s_top[k] = __fadd_rn(s_top[2 * k], s_top[2 * k + 1]);
+        __syncthreads();
+    }
+    return s_top[1];
+}
+
 // grid = top heap size; CTA id+1 = heap id of the top tree (leaf threshold kSumBlockMax).  The last CTA to finish adds the
 // top of the tree (numpy's association) and publishes the float32 total.  draw_B > 0: the B uniforms of this call are drawn here.
 __global__ void __launch_bounds__(256) per_sum(const float *p_alpha, int64_t n, int top_depth, float *top_vals, float *total, int *ticket,
@@ -185,23 +206,8 @@ __global__ void __launch_bounds__(256) per_sum(const float *p_alpha, int64_t n, 
         if (threadIdx.x == 0) top_vals[id] = v;
     }
     if (!last_block_done(ticket)) return;
-    // top of the tree (heap ids < 2^(top_depth+1) <= 4096) in shared memory: one read of the CTA results, then level by level
-    __shared__ float s_top[4096];
-    __shared__ unsigned char s_tstate[4096];
-    const unsigned n_ids = 2u << top_depth;
-    for (unsigned k = 1 + threadIdx.x; k < n_ids; k += blockDim.x) {
-        int64_t s2, m2; bool lf = false;
-        const bool ex = pw_node(0, n, kSumBlockMax, k, s2, m2, lf);
-        s_tstate[k] = ex ? (lf ? 1 : 2) : 0;
-        if (ex && lf) s_top[k] = __ldcg(top_vals + k);
-    }
-    __syncthreads();
-    for (int depth = top_depth; depth >= 0; depth--) {
-        for (unsigned k = (1u << depth) + threadIdx.x; k < (2u << depth); k += blockDim.x)
-            if (s_tstate[k] == 2) s_top[k] = __fadd_rn(s_top[2 * k], s_top[2 * k + 1]);
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *total = s_top[1];
+    const float tot = top_tree_sum(n, top_depth, top_vals);
+    if (threadIdx.x == 0) *total = tot;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -573,6 +579,68 @@ __global__ void __launch_bounds__(256) per_chunk_search(const float *total, doub
     }
     if (!search_group(a, s_carry, s_cnt[0], tot, sg, n_sg)) return;
     if (threadIdx.x == 0) { queue[0] = 0; queue[32] = 0; a.counters[3] = a.counters[1]; a.counters[1] = 0; }
+}
+
+// The whole sample() as ONE launch: the queue hands out the sum groups (CTA subtrees of the pairwise tree), then the chunk groups, then
+// the search groups.  A chunk group waits for every sum group, adds the top of the tree ITSELF (<= 4 K values in shared memory, the same
+// association in every CTA, so every CTA holds the same float32 total) and runs its chunk pass; a search group waits for every chunk
+// group as above.  Waits only ever point at lower-numbered items, which were claimed by running CTAs: no deadlock whatever the residency.
+// queue[0] = next item, queue[32] = finished chunk groups, queue[64] = finished sum groups.
+struct SumArgs { int top_depth; float *top_vals; float *total; double *u; int draw_B; uint64_t seed, counter; };
+__global__ void __launch_bounds__(256) per_sample_fused(SumArgs sm, double *chunk_sum, int *chunk_fine, double *carry, int *queue, SearchArgs a) {
+    SACB_PDL_ENTER();
+    __shared__ int s_item;
+    __shared__ double s_carry[kCarrySmem];
+    __shared__ int s_cnt[2];
+    if (threadIdx.x == 0) s_item = atomicAdd(queue, 1);
+    __syncthreads();
+    const int item = s_item, n_sum = (2 << sm.top_depth) - 1, n_cg = (a.n_chunks + 7) / 8, n_sg = (a.B + 7) / 8;
+    auto wait_for = [&](int *counter, int target) {
+        if (threadIdx.x == 0) {
+            unsigned int it = 0;
+            int v;
+            do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory"); } while (v < target && ++it < (1u << 26));
+        }
+        __syncthreads();
+    };
+    if (item < n_sum) {
+        __shared__ float s_heap[kSumHeap];
+        __shared__ unsigned char s_state[kSumHeap];
+        __shared__ int s_leaf[3 * 128];
+        for (int j = item * blockDim.x + threadIdx.x; j < sm.draw_B; j += n_sum * blockDim.x) sm.u[j] = uniform_of(sm.seed, sm.counter, j);
+        const unsigned id = (unsigned)item + 1;
+        int64_t s, m; bool leaf = false;
+        if (pw_node(0, a.n, kSumBlockMax, id, s, m, leaf) && leaf) {      // CTA-uniform
+            const float v = pw_block_sum(a.p_alpha, s, (int)m, s_heap, s_state, s_leaf);
+            if (threadIdx.x == 0) sm.top_vals[id] = v;
+        }
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(queue + 64, 1);
+        return;
+    }
+    if (item < n_sum + n_cg) {
+        wait_for(queue + 64, n_sum);
+        const float tot = top_tree_sum(a.n, sm.top_depth, sm.top_vals);
+        if (item == n_sum && threadIdx.x == 0) *sm.total = tot;      // the global copy (search groups, statistics, the exact pass)
+        chunk_group(a.p_alpha, a.n, tot, item - n_sum, chunk_sum, chunk_fine);
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) atomicAdd(queue + 32, 1);
+        return;
+    }
+    const int sg = item - n_sum - n_cg;
+    if (sg >= n_sg) return;
+    wait_for(queue + 32, n_cg);
+    const float tot = __ldcg(sm.total);
+    carry_scan(chunk_sum, chunk_fine, a.n_chunks, s_carry, s_cnt);
+    __syncthreads();
+    if (sg == 0) {
+        for (int i = threadIdx.x; i <= a.n_chunks; i += blockDim.x) carry[i] = s_carry[i];
+        if (threadIdx.x == 0) a.counters[0] = s_cnt[0];
+    }
+    if (!search_group(a, s_carry, s_cnt[0], tot, sg, n_sg)) return;
+    if (threadIdx.x == 0) { queue[0] = 0; queue[32] = 0; queue[64] = 0; a.counters[3] = a.counters[1]; a.counters[1] = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -950,26 +1018,41 @@ int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B
     if (depth > 11) return fail(SACB_ERR_ARG, "capacity too large for the summation heap");
     const float *pa = h->p_alpha;
     int *tickets = w.tickets;
-    // three launches, each a parallel pass whose last CTA runs the serial step that used to be its own kernel
-    SACB_CUDA(launch_pdl(per_sum, dim3((2 << depth) - 1), dim3(256), 0, st, pdl, pa, n, depth, w.block_vals, w.total, tickets + 0,
-                         w.u, u ? 0 : (int)k, h->cfg.seed, (uint64_t)frame));
+    static const bool split_launch = getenv("SACB_PER_THREE_LAUNCHES") != nullptr;      // A/B: the round-1 form (separate sum, chunk and search launches)
+    // per_sum + per_chunk_search is the default; everything as ONE launch (SACB_PER_ONE_LAUNCH=1: per_sample_fused) measured the same
+    // 30.7 against 30.2 us per sample(256) at N = 1 M: the top of the tree added redundantly by every chunk group costs what the launch boundary saved
+    static const bool two_launches = getenv("SACB_PER_ONE_LAUNCH") == nullptr;
     const int n_chunks = (int)((n + kChunk - 1) / kChunk);
     SearchArgs sa;
     sa.p_alpha = pa; sa.n = n; sa.u = w.u; sa.B = (int)k; sa.counters = w.counters; sa.idx_out = w.idx; sa.flagged = w.flagged;
     sa.ticket = tickets + 2 * kTicketInts; sa.carry_exact = w.cdf_exact; sa.chunk_sum = w.chunk_sum; sa.chunk_fine = w.chunk_fine; sa.n_chunks = n_chunks;
     sa.neg_beta = -(float)beta; sa.weights = w.weights; sa.slots = h->slots; sa.isw_ws = h->ws + h->L.isw; sa.idx_copy = h->last_idx_dev;
-    static const bool split_launch = getenv("SACB_PER_THREE_LAUNCHES") != nullptr;      // A/B: the round-1 form (separate chunk and search launches)
+    if (n_chunks + 1 <= kCarrySmem && !split_launch && !two_launches) {
+        // the whole call as ONE launch: CTAs claim sum groups, chunk groups, search groups, in that order, from a work queue
+        SumArgs sm;
+        sm.top_depth = depth; sm.top_vals = w.block_vals; sm.total = w.total; sm.u = w.u; sm.draw_B = u ? 0 : (int)k; sm.seed = h->cfg.seed; sm.counter = (uint64_t)frame;
+        SACB_CUDA(launch_pdl(per_sample_fused, dim3((2 << depth) - 1 + (n_chunks + 7) / 8 + (int)((k + 7) / 8)), dim3(256), 0, st, pdl, sm, w.chunk_sum, w.chunk_fine,
+                             w.chunk_carry, tickets + kTicketInts, sa));
+        h->kernel_launches += 1;
+        h->per_fused = true;
+        h->sample_k = k;
+        if (k_out) *k_out = k;
+        return SACB_OK;
+    }
+    SACB_CUDA(launch_pdl(per_sum, dim3((2 << depth) - 1), dim3(256), 0, st, pdl, pa, n, depth, w.block_vals, w.total, tickets + 0,
+                         w.u, u ? 0 : (int)k, h->cfg.seed, (uint64_t)frame));
+    h->kernel_launches += 1;
     if (n_chunks + 1 <= kCarrySmem && !split_launch) {
         // chunk pass and search as ONE launch: CTAs claim chunk groups, then search groups, in order from a work queue
         SACB_CUDA(launch_pdl(per_chunk_search, dim3((n_chunks + 7) / 8 + (int)((k + 7) / 8)), dim3(256), 0, st, pdl, (const float *)w.total, w.chunk_sum, w.chunk_fine,
                              w.chunk_carry, tickets + kTicketInts, sa));
-        h->kernel_launches += 2;
+        h->kernel_launches += 1;
         h->per_fused = true;
     } else {
         SACB_CUDA(launch_pdl(per_chunk, dim3((n_chunks + 7) / 8), dim3(256), 0, st, pdl, pa, n, (const float *)w.total, w.chunk_sum, w.chunk_fine,
                              n_chunks, w.chunk_carry, w.counters, tickets + kTicketInts));
         SACB_CUDA(launch_pdl(per_search, dim3((int)((k + 7) / 8)), dim3(256), 0, st, pdl, (const float *)w.total, (const double *)w.chunk_carry, sa));
-        h->kernel_launches += 3;
+        h->kernel_launches += 2;
         h->per_fused = false;
     }
     h->sample_k = k;
