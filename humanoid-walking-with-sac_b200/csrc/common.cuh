@@ -150,10 +150,13 @@ struct alignas(64) Task {
 // the host picks the smallest variant that covers a stage, variant 0 (everything) runs the persistent single-launch mode.
 constexpr uint32_t tb(int t) { return 1u << t; }
 constexpr uint32_t kAllTypes = (1u << (T_LN_BWD + 1)) - 1, kAllEpis = (1u << (EPI_SAMPLE + 1)) - 1;
+// everything the reference architecture needs: the single persistent launch of a handle without LayerNorm does not carry the
+// LayerNorm tasks (their code alone cost the everything-build 0.265 -> 0.302 ms per update)
+constexpr uint32_t kBaseTypes = kAllTypes & ~((1u << T_LN_FWD) | (1u << T_LN_BWD));
 constexpr uint32_t kPlainEpis = tb(EPI_F32) | tb(EPI_BIAS_RELU) | tb(EPI_MASK);
 constexpr uint32_t kElemTypes = tb(T_SHADOW) | tb(T_GATHER) | tb(T_SAMPLE) | tb(T_TARGET_LOSS) | tb(T_ACTOR_LOSS) | tb(T_SAMPLE_BWD) | tb(T_FINISH) | tb(T_LN_FWD) | tb(T_LN_BWD);
 #define SACB_KERNEL_VARIANTS(X)                                                                     \
-    X(0, kAllTypes, kAllEpis)                                                                       \
+    X(0, kBaseTypes, kAllEpis)                                                                      \
     X(1, tb(T_GEMM), tb(EPI_BIAS_RELU))                                                         \
     X(2, tb(T_GEMM), tb(EPI_MASK))                                                                  \
     X(3, tb(T_GEMM), tb(EPI_F32))                                                                   \
@@ -172,8 +175,10 @@ constexpr uint32_t kElemTypes = tb(T_SHADOW) | tb(T_GATHER) | tb(T_SAMPLE) | tb(
     X(16, tb(T_GEMM) | tb(T_SHADOW), tb(EPI_BIAS_RELU))                                             \
     X(17, tb(T_OUT_ADAM) | tb(T_BIAS_ADAM), 0u)                                                     \
     X(18, tb(T_LN_FWD), 0u)                                                                         \
-    X(19, tb(T_LN_BWD), 0u)
-constexpr int kNumKernelVariants = 20;
+    X(19, tb(T_LN_BWD), 0u)                                                                         \
+    X(20, kAllTypes, kAllEpis)
+constexpr int kNumKernelVariants = 21;
+constexpr int kVariantEverything = 0, kVariantEverythingLn = 20;      // the build a persistent launch runs (without / with LayerNorm)
 // "Light" builds: column-sum / sample-backward stages only.  A tile of theirs is one batch of loads, two barriers and a 64-element
 // Adam step: a throughput program walks thousands of them (population: 2304 per stage) and one 512-thread CTA per SM leaves the
 // memory system idle between its two dependent round trips.  They are compiled for TWO resident CTAs per SM (<= 64 registers).

@@ -286,7 +286,7 @@ sac_update_kernel(const __grid_constant__ Program P, const __grid_constant__ Sta
             }
             float *scalars = resolve(P.scalars, P.bases, agent);
             if (t.type != T_GEMM && st.krank != 0) continue;      // element-wise tasks of a clustered stage run on rank 0 only
-            constexpr bool kOutlined = kTc && kTypes == kAllTypes && kEpis == kAllEpis && !SACB_NO_OUTLINE;
+            constexpr bool kOutlined = kTc && (kTypes & kBaseTypes) == kBaseTypes && kEpis == kAllEpis && !SACB_NO_OUTLINE;
             if constexpr (kOutlined) {
                 switch (t.type) {
                     case T_GEMM:
@@ -1028,7 +1028,7 @@ static int launch_range(sacb_handle h, ProgramInst &p, int s0, int s1, bool coop
     int tc_setup = tf32 ? needs_tc : 0;
     Stage single = p.stages[s0];
     void *args[] = {(void *)&p.prog, (void *)&single, (void *)&s0, (void *)&s1, (void *)&tc_setup, (void *)&seed};
-    const void *fn = update_kernel_for(h->cfg.math_mode, 0);
+    const void *fn = update_kernel_for(h->cfg.math_mode, h->cfg.layer_norm ? kVariantEverythingLn : kVariantEverything);
     if (cooperative) {
         const int grid = std::min(max_tiles, h->sm_count * h->coop_blocks_per_sm);
         SACB_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kThreads), args, smem, h->stream));
@@ -1102,7 +1102,7 @@ int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out) {
         // the two-CTAs-per-SM column-sum build (4 rows in flight per thread) pays where resident CTAs walk thousands of small tiles (a
         // population); a stage of a few long tiles (one agent, large batch) keeps the one-CTA build with 8 rows in flight
         const bool many = b.stages[s].n_tiles * h->cfg.n_agents > 2 * h->sm_count;
-        p.stage_kind.push_back(getenv("SACB_ONE_KERNEL") ? 0 : pick_variant(types, epis, many));
+        p.stage_kind.push_back(getenv("SACB_ONE_KERNEL") ? (h->cfg.layer_norm ? kVariantEverythingLn : kVariantEverything) : pick_variant(types, epis, many));
     }
     for (auto &s : p.stages) { p.n_tiles_total += s.n_tiles; p.max_stage_tiles = std::max(p.max_stage_tiles, s.n_tiles); }
     SACB_CUDA(cudaMalloc(&p.d_tasks, p.tasks.size() * sizeof(Task)));
@@ -1328,7 +1328,7 @@ extern "C" int sacb_time_stages(sacb_handle h, int64_t B, float *us_out, int cap
         grid = std::min(grid, h->sm_count);
         for (int r = 0; r < 3; r++) {
             SACB_CUDA(cudaMemsetAsync(h->barrier, 0, sizeof(unsigned int), h->stream));
-            SACB_CUDA(cudaLaunchCooperativeKernel(update_kernel_for(h->cfg.math_mode, 0), dim3(grid), dim3(kThreads), args, math_smem(h->cfg.math_mode), h->stream));
+            SACB_CUDA(cudaLaunchCooperativeKernel(update_kernel_for(h->cfg.math_mode, h->cfg.layer_norm ? kVariantEverythingLn : kVariantEverything), dim3(grid), dim3(kThreads), args, math_smem(h->cfg.math_mode), h->stream));
         }
         SACB_CUDA(cudaStreamSynchronize(h->stream));
         SACB_CUDA(cudaMemcpy(h_trace.data(), d_trace, sizeof(unsigned long long) * kTraceSlots * grid, cudaMemcpyDeviceToHost));
@@ -1389,7 +1389,7 @@ int init_kernel_attributes(sacb_handle h) {
             SACB_CUDA(cudaFuncSetAttribute(update_kernel_for(m, v), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)math_smem(m)));
     SACB_CUDA(cudaFuncSetAttribute((const void *)sac_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stream::kSmemBytes));
     int nb = 0;
-    SACB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, update_kernel_for(m, 0), kThreads, math_smem(m)));
+    SACB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, update_kernel_for(m, h->cfg.layer_norm ? kVariantEverythingLn : kVariantEverything), kThreads, math_smem(m)));
     h->coop_blocks_per_sm = std::max(1, std::min(nb, math_is_tc(m) ? 2 : 4));
     return SACB_OK;
 }
