@@ -635,7 +635,7 @@ struct Builder {
         const int n256_min = getenv("SACB_STREAM_N256_MIN") ? atoi(getenv("SACB_STREAM_N256_MIN")) : 1;      // read per program build (tests A/B both forms in one process)
         // no extra padding against 128-wide tiles; a tile that steps weights keeps 128 columns (its stage gives 64 KB of the ring to the
         // optimizer-state landing zone of the Adam epilogue: two 64 KB slots are left)
-        const bool applies = apply();
+        const bool applies = apply();      // (256-column weight-stepping tiles on a one-slot ring were measured: no gain, 691 -> 786 us on a mixed stage)
         auto takes_256 = [applies](const Task &t) { return t.N >= 192 && cdiv(t.N, 256) * 256 <= cdiv(t.N, 128) * 128 && !(t.epi == EPI_ADAM && applies); };
         std::vector<std::pair<int, int>> out(tasks.size(), {0, 0});
         for (size_t si = 0; si < stages.size(); si++) {

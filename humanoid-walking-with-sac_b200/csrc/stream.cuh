@@ -17,6 +17,9 @@
 #pragma once
 #include "gemm.cuh"
 
+#ifndef SACB_STATE_DEPTH
+#define SACB_STATE_DEPTH 2
+#endif
 namespace sacb {
 namespace stream {
 
@@ -34,7 +37,8 @@ constexpr int kAccCols = kBNMax, kTmemCols = 2 * kAccCols;      // two accumulat
 // [w | m | v | target][2 rows][256 threads] float4 filled with cp.async -- the state of the NEXT two-row group of a thread is in flight
 // (no registers held) while the current group is stepped.  Such a stage runs on a 128 KB operand ring.
 constexpr int kStateBufBytes = 4 * 2 * kEpiThreads * 16;         // 32 KB
-constexpr int kStateBytes = 2 * kStateBufBytes;                   // 64 KB
+constexpr int kStateDepth = SACB_STATE_DEPTH;                      // two-row groups of a thread in flight
+constexpr int kStateBytes = kStateDepth * kStateBufBytes;
 constexpr int kRingBytesAdam = kRingBytes - kStateBytes;          // 128 KB
 
 struct Misc {                 // lives behind the staging tile
@@ -144,8 +148,12 @@ __device__ __forceinline__ void adam_epilogue(const EpiR &e, const float *Cs, fl
         const AdamGroup g = adam_group(e, m0, n0, ncols, et, grp);
         float4 w[2], mm[2], vv[2], wt[2];
         if (state) {      // groups grp and grp + 1 are in flight: wait for the older one, then put group grp + 2 behind them
-            if (grp < 3) asm volatile("cp.async.wait_group 1;" ::: "memory"); else asm volatile("cp.async.wait_group 0;" ::: "memory");
-            const float4 *src = state + (size_t)(grp & 1) * (kStateBufBytes / 16) + et;
+            // groups grp .. min(grp + kStateDepth - 1, 3) are in flight: wait for the oldest
+            const int younger = min(kStateDepth - 1, 3 - grp);
+            if (younger >= 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+            else if (younger == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+            else asm volatile("cp.async.wait_group 0;" ::: "memory");
+            const float4 *src = state + (size_t)(grp % kStateDepth) * (kStateBufBytes / 16) + et;
 #pragma unroll
             for (int ii = 0; ii < 2; ii++) {
                 w[ii] = mm[ii] = vv[ii] = wt[ii] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -154,7 +162,7 @@ __device__ __forceinline__ void adam_epilogue(const EpiR &e, const float *Cs, fl
                     if (e.wt) wt[ii] = src[(3 * 2 + ii) * kEpiThreads];
                 }
             }
-            if (grp + 2 < 4) adam_issue(e, state, m0, n0, et, grp + 2, grp & 1);      // the buffer just read
+            if (grp + kStateDepth < 4) adam_issue(e, state, m0, n0, et, grp + kStateDepth, grp % kStateDepth);      // the buffer just read
         } else {
 #pragma unroll
             for (int ii = 0; ii < 2; ii++) {
@@ -287,7 +295,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiR &epi, float *Cs, float4
     uint32_t mask_bits[4] = {0u, 0u, 0u, 0u};
     if (EPI == EPI_ADAM) {
         for (int p = state ? 1 : 0; p < passes; p++) adam_prefetch(epi, r.m0, r.n0 + 64 * p, et);
-        if (state) { adam_issue(epi, state, r.m0, r.n0, et, 0, 0); adam_issue(epi, state, r.m0, r.n0, et, 1, 1); }      // first pass: under the main loop
+        if (state) for (int g0 = 0; g0 < kStateDepth; g0++) adam_issue(epi, state, r.m0, r.n0, et, g0, g0);      // first pass: under the main loop
     } else if (EPI == EPI_MASK) {
         // the ReLU-mask operand (sign of the stored activation) of ALL passes is fetched now and kept as one bit per element:
         // no global load sits between the accumulator and the stores any more (the mask loads paced the dX stages: an epilogue
@@ -336,7 +344,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiR &epi, float *Cs, float4
             if (last) { tc::tc_fence_before(); if (lane == 0) mbar_arrive(acc_empty); }
             if (EPI == EPI_ADAM && state) {      // keep the request pipeline in step: retire this pass's (empty) groups, request the next pass's
                 asm volatile("cp.async.wait_group 0;" ::: "memory");
-                if (!last) { adam_issue(epi, state, r.m0, n0c + 64, et, 0, 0); adam_issue(epi, state, r.m0, n0c + 64, et, 1, 1); }
+                if (!last) for (int g0 = 0; g0 < kStateDepth; g0++) adam_issue(epi, state, r.m0, n0c + 64, et, g0, g0);
             }
             continue;
         }
@@ -368,7 +376,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiR &epi, float *Cs, float4
         if (EPI == EPI_ADAM) {
             adam_epilogue(epi, Cs, state, r.m0, n0c, et, r.tg->i[7] > 0);
             // the next pass's first two groups: in flight across the barrier and the next TMEM -> staging copy
-            if (state && !last) { adam_issue(epi, state, r.m0, n0c + 64, et, 0, 0); adam_issue(epi, state, r.m0, n0c + 64, et, 1, 1); }
+            if (state && !last) for (int g0 = 0; g0 < kStateDepth; g0++) adam_issue(epi, state, r.m0, n0c + 64, et, g0, g0);
         } else plain_epilogue<EPI>(epi, Cs, r.m0, n0c, et, aux);
         epi_bar();        // the staging tile is free for the next pass / tile
     }
@@ -397,7 +405,7 @@ __device__ __forceinline__ void gemm_stage(const Program &P, const Stage &stage,
             if (__ldg(&P.tasks[k].epi) == EPI_ADAM && __ldg(&P.tasks[k].adam.apply)) steps |= __ldg(&P.tasks[k].K) <= 16 * kBK ? 1 : 2;
         }
         mi.slot_bytes = kABytes + bn_max * (kBK * 2 * 2);
-        mi.adam_state = (steps == 1 && 2 * mi.slot_bytes <= kRingBytesAdam) ? 1 : 0;      // (the builder keeps weight-stepping tiles at 128 columns)
+        mi.adam_state = (steps == 1 && mi.slot_bytes <= kRingBytesAdam) ? 1 : 0;      // (the builder keeps weight-stepping tiles at 128 columns)
         mi.n_slots = min(kMaxStages, (mi.adam_state ? kRingBytesAdam : kRingBytes) / mi.slot_bytes);
     }
     tc::tc_fence_before();
