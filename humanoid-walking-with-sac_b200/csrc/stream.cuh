@@ -202,25 +202,44 @@ __device__ __forceinline__ void adam_epilogue(const EpiR &e, const float *Cs, fl
         }
     }
     if (e.N % 4 != 0 || ncols < 64) {           // pass B: the columns no aligned group covers; thread (row = et / 4 (+ 64), q = et % 4)
-#pragma unroll 1
+        // at most two such columns per row half and thread: all (<= 16) scalar loads of the thread are issued before the first step, one
+        // exposed round trip instead of four (a critic's fc1 has 365 columns: every row of every pass comes through here)
+        int64_t off[4];
+        int rowc[4], coln[4];
+        float sw[4], sm[4], sv[4], st[4];
+        int cnt = 0;
+#pragma unroll
         for (int hb = 0; hb < 2; hb++) {
             const int row = (et >> 2) + 64 * hb, q = et & 3, m = m0 + row;
-            if (m >= e.M) continue;
+            const bool live = m < e.M;
             const int a0 = (4 - (int)(((int64_t)m * e.N + n0) & 3)) & 3;
             const int nv = ncols > a0 ? (ncols - a0) >> 2 : 0, tail0 = a0 + 4 * nv;
-            int col[2];
-            int cnt = 0;
-            if (q < min(a0, ncols)) col[cnt++] = q;
-            if (tail0 + q < ncols) col[cnt++] = tail0 + q;
-            for (int u = 0; u < cnt; u++) {
-                const int64_t o = (int64_t)m * e.N + n0 + col[u];
-                const float g = Cs[row * tc::kCsLd + col[u]];
+            const int cand[2] = {q, tail0 + q};
+            const bool on[2] = {live && q < min(a0, ncols), live && tail0 + q < ncols};
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int k = 2 * hb + u;
+                off[k] = -1; rowc[k] = row; coln[k] = cand[u];
+                sw[k] = sm[k] = sv[k] = st[k] = 0.f;
+                if (on[u]) {
+                    off[k] = (int64_t)m * e.N + n0 + cand[u];
+                    if (e.apply) { sw[k] = __ldcg(e.w + off[k]); sm[k] = __ldcg(e.m + off[k]); sv[k] = __ldcg(e.v + off[k]); if (e.wt) st[k] = __ldcg(e.wt + off[k]); }
+                    cnt++;
+                }
+            }
+        }
+        if (cnt) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (off[k] < 0) continue;
+                const int64_t o = off[k];
+                const float g = Cs[rowc[k] * tc::kCsLd + coln[k]];
                 if (e.gexp) { if (accumulate) atomicAdd(e.gexp + o, g); else e.gexp[o] = g; }
                 if (!e.apply) continue;
-                const tc::AdamOut r = tc::adam_math(e, g, __ldcg(e.w + o), __ldcg(e.m + o), __ldcg(e.v + o), e.wt ? __ldcg(e.wt + o) : 0.f);
+                const tc::AdamOut r = tc::adam_math(e, g, sw[k], sm[k], sv[k], st[k]);
                 e.m[o] = r.m; e.v[o] = r.v; e.w[o] = r.w;
                 if (e.wt) e.wt[o] = r.t;
-                const int n = n0 + col[u];
+                const int m = m0 + rowc[k], n = n0 + coln[k];
                 if (e.shadow.hi) pm_store(e.shadow, m, n, r.w);
                 if (e.shadow2.hi && n >= e.shadow2_col0) pm_store(e.shadow2, m, n - e.shadow2_col0, r.w);
                 if (e.wt && e.shadow_t.hi) pm_store(e.shadow_t, m, n, r.t);
