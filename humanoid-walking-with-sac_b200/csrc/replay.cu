@@ -5,7 +5,8 @@
 // contiguous ~2.9 KB read (Humanoid), gathered by one warp with coalesced loads.
 //
 // PER sampling reproduces np.random.choice(len, B, p=probs) bit-for-bit downstream of the p**alpha table:
-// Two launches per sample() call (per_sum, per_chunk_search = the two passes below claimed as work items of ONE grid):
+// One launch per sample() call (per_sample_fused: the three kinds of work below claimed in order as work items of ONE grid;
+// SACB_PER_TWO_LAUNCHES / SACB_PER_THREE_LAUNCHES keep the earlier forms: per_sum + per_chunk_search, per_sum + per_chunk + per_search):
 //   per_sum      float32 total with numpy's pairwise-summation tree (exact same association): CTA subtrees, then the top (last CTA)
 //   chunk groups probs = p_alpha / total (float32), float64 chunk sums, count of "fine" elements
 //   search groups exclusive scan of the chunk sums (per group, shared memory), per-sample inverse-CDF search + provable ambiguity test
@@ -1019,9 +1020,10 @@ int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B
     const float *pa = h->p_alpha;
     int *tickets = w.tickets;
     static const bool split_launch = getenv("SACB_PER_THREE_LAUNCHES") != nullptr;      // A/B: the round-1 form (separate sum, chunk and search launches)
-    // per_sum + per_chunk_search is the default; everything as ONE launch (SACB_PER_ONE_LAUNCH=1: per_sample_fused) measured the same
-    // 30.7 against 30.2 us per sample(256) at N = 1 M: the top of the tree added redundantly by every chunk group costs what the launch boundary saved
-    static const bool two_launches = getenv("SACB_PER_ONE_LAUNCH") == nullptr;
+    // default: the whole call as ONE launch (per_sample_fused).  sample(256) at N = 1 M on its own: 30.7 us, against 30.2 us for per_sum +
+    // per_chunk_search (SACB_PER_TWO_LAUNCHES=1) and 34.7 us for three launches; under the update (sacb_per_step, 4000 pipelined steps):
+    // 211.3 / 213.2 / 211.5 us per step
+    static const bool two_launches = getenv("SACB_PER_TWO_LAUNCHES") != nullptr;
     const int n_chunks = (int)((n + kChunk - 1) / kChunk);
     SearchArgs sa;
     sa.p_alpha = pa; sa.n = n; sa.u = w.u; sa.B = (int)k; sa.counters = w.counters; sa.idx_out = w.idx; sa.flagged = w.flagged;
