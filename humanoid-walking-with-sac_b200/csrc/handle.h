@@ -149,6 +149,7 @@ struct sacb_handle_s {
     // PER
     float *prio = nullptr, *p_alpha = nullptr;   // [n_agents, capacity]
     std::vector<int64_t> per_frame;
+    bool per_frame_dirty = true;         // the device copy of per_frame[0] (read and advanced by the sample kernels) has to be uploaded
     void *per_ws = nullptr;                      // scan workspace (see replay.cu)
     int64_t *last_idx_dev = nullptr;             // [n_agents, maxB] logical indices of the last sample
     float *last_w_dev = nullptr;

@@ -194,11 +194,12 @@ __device__ float top_tree_sum(int64_t n, int top_depth, const float *top_vals) {
 // grid = top heap size; CTA id+1 = heap id of the top tree (leaf threshold kSumBlockMax).  The last CTA to finish adds the
 // top of the tree (numpy's association) and publishes the float32 total.  draw_B > 0: the B uniforms of this call are drawn here.
 __global__ void __launch_bounds__(256) per_sum(const float *p_alpha, int64_t n, int top_depth, float *top_vals, float *total, int *ticket,
-                                               double *u, int draw_B, uint64_t seed, uint64_t counter) {
+                                               double *u, int draw_B, uint64_t seed, const int64_t *frame) {
     SACB_PDL_ENTER();
     __shared__ float s_heap[kSumHeap];
     __shared__ unsigned char s_state[kSumHeap];
     __shared__ int s_leaf[3 * 128];          // a CTA subtree of <= kSumBlockMax elements has at most 128 leaves
+    const uint64_t counter = (uint64_t)__ldcg(frame);
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < draw_B; j += gridDim.x * blockDim.x) u[j] = uniform_of(seed, counter, j);
     const unsigned id = blockIdx.x + 1;
     int64_t s, m; bool leaf = false;
@@ -413,7 +414,10 @@ __device__ void exact_pass(const float *p_alpha, int64_t n, float tot, double *c
 struct SearchArgs {
     const float *p_alpha; int64_t n; const double *u; int B; int *counters; int64_t *idx_out; int *flagged; int *ticket;
     double *carry_exact; const double *chunk_sum; const int *chunk_fine; int n_chunks;
-    float neg_beta; float *weights; int32_t *slots; float *isw_ws; int64_t *idx_copy;
+    float *weights; int32_t *slots; float *isw_ws; int64_t *idx_copy;
+    // beta = min(1, beta_start + frame * (1 - beta_start) / beta_frames) (replay_buffer.py:53) from the DEVICE copy of the frame counter, which
+    // the tail then advances: a captured learner step needs no per-step argument
+    int64_t *frame; double beta_start, one_minus_start, beta_frames;
 };
 // group sg of n_sg: 8 samples, one per warp; cr = chunk prefixes (shared or global), F = number of fine elements.  The last group to
 // finish runs the serial tail.  Returns true in that group only (after the tail).
@@ -421,7 +425,7 @@ __device__ __forceinline__ bool search_group(const SearchArgs &a, const double *
     const float *p_alpha = a.p_alpha; const int64_t n = a.n; const double *u = a.u; const int B = a.B, n_chunks = a.n_chunks;
     int *counters = a.counters; int64_t *idx_out = a.idx_out; int *flagged = a.flagged;
     double *carry_exact = a.carry_exact; const double *chunk_sum = a.chunk_sum; const int *chunk_fine = a.chunk_fine;
-    const float neg_beta = a.neg_beta; float *weights = a.weights; int32_t *slots = a.slots; float *isw_ws = a.isw_ws; int64_t *idx_copy = a.idx_copy;
+    float *weights = a.weights; int32_t *slots = a.slots; float *isw_ws = a.isw_ws; int64_t *idx_copy = a.idx_copy;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = sg * 8 + warp;
     if (j < B) {      // warp-uniform
@@ -504,6 +508,8 @@ __device__ __forceinline__ bool search_group(const SearchArgs &a, const double *
         __syncthreads();
     }
     __shared__ float s_max[32];
+    const int64_t frame = __ldcg(a.frame);
+    const float neg_beta = -(float)fmin(1.0, __dadd_rn(a.beta_start, __ddiv_rn(__dmul_rn((double)frame, a.one_minus_start), a.beta_frames)));
     float m = -INFINITY;
     for (int q = threadIdx.x; q < B; q += blockDim.x) {
         const int64_t ix = __ldcg(idx_out + q);
@@ -529,6 +535,7 @@ __device__ __forceinline__ bool search_group(const SearchArgs &a, const double *
         weights[q] = wn;
         if (isw_ws) isw_ws[q] = wn;
     }
+    if (threadIdx.x == 0) *a.frame = frame + 1;      // every reader of this call's value (uniform draws, beta) is done
     return true;
 }
 
@@ -587,7 +594,7 @@ __global__ void __launch_bounds__(256) per_chunk_search(const float *total, doub
 // association in every CTA, so every CTA holds the same float32 total) and runs its chunk pass; a search group waits for every chunk
 // group as above.  Waits only ever point at lower-numbered items, which were claimed by running CTAs: no deadlock whatever the residency.
 // queue[0] = next item, queue[32] = finished chunk groups, queue[64] = finished sum groups.
-struct SumArgs { int top_depth; float *top_vals; float *total; double *u; int draw_B; uint64_t seed, counter; };
+struct SumArgs { int top_depth; float *top_vals; float *total; double *u; int draw_B; uint64_t seed; const int64_t *frame; };
 __global__ void __launch_bounds__(256) per_sample_fused(SumArgs sm, double *chunk_sum, int *chunk_fine, double *carry, int *queue, SearchArgs a) {
     SACB_PDL_ENTER();
     __shared__ int s_item;
@@ -608,7 +615,8 @@ __global__ void __launch_bounds__(256) per_sample_fused(SumArgs sm, double *chun
         __shared__ float s_heap[kSumHeap];
         __shared__ unsigned char s_state[kSumHeap];
         __shared__ int s_leaf[3 * 128];
-        for (int j = item * blockDim.x + threadIdx.x; j < sm.draw_B; j += n_sum * blockDim.x) sm.u[j] = uniform_of(sm.seed, sm.counter, j);
+        const uint64_t counter = (uint64_t)__ldcg(sm.frame);
+        for (int j = item * blockDim.x + threadIdx.x; j < sm.draw_B; j += n_sum * blockDim.x) sm.u[j] = uniform_of(sm.seed, counter, j);
         const unsigned id = (unsigned)item + 1;
         int64_t s, m; bool leaf = false;
         if (pw_node(0, a.n, kSumBlockMax, id, s, m, leaf) && leaf) {      // CTA-uniform
@@ -1001,9 +1009,13 @@ int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B
     if (k > h->cfg.max_batch) return fail(SACB_ERR_ARG, "batch size exceeds max_batch");
     PerWs w = per_ws_of(h, 0);
     const bool pdl = h->use_pdl != 0;
-    const int64_t frame = h->per_frame[0];
-    const double beta = std::min(1.0, (double)h->cfg.per_beta_start + (double)frame * (1.0 - (double)h->cfg.per_beta_start) / (double)h->cfg.per_beta_frames);
-    h->per_frame[0] = frame + 1;
+    int64_t *frame_dev = reinterpret_cast<int64_t *>(w.counters + 8);
+    if (h->per_frame_dirty) {      // create / sacb_per_set_frame: the device copy follows the host's
+        SACB_CUDA(cudaMemcpyAsync(frame_dev, &h->per_frame[0], sizeof(int64_t), cudaMemcpyHostToDevice, st));
+        SACB_CUDA(cudaStreamSynchronize(st));
+        h->per_frame_dirty = false;
+    }
+    h->per_frame[0] += 1;      // host mirror (statistics, `frame` property); the kernels read and advance the device copy
     if (u) {      // host-drawn uniforms (np.random.random_sample inside np.random.choice): through pinned memory, no pageable staging
         if (!h->pin_u) {
             if (cudaMallocHost(&h->pin_u, sizeof(double) * h->cfg.max_batch) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_u, cudaEventDisableTiming) != cudaSuccess)
@@ -1028,11 +1040,12 @@ int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B
     SearchArgs sa;
     sa.p_alpha = pa; sa.n = n; sa.u = w.u; sa.B = (int)k; sa.counters = w.counters; sa.idx_out = w.idx; sa.flagged = w.flagged;
     sa.ticket = tickets + 2 * kTicketInts; sa.carry_exact = w.cdf_exact; sa.chunk_sum = w.chunk_sum; sa.chunk_fine = w.chunk_fine; sa.n_chunks = n_chunks;
-    sa.neg_beta = -(float)beta; sa.weights = w.weights; sa.slots = h->slots; sa.isw_ws = h->ws + h->L.isw; sa.idx_copy = h->last_idx_dev;
+    sa.weights = w.weights; sa.slots = h->slots; sa.isw_ws = h->ws + h->L.isw; sa.idx_copy = h->last_idx_dev;
+    sa.frame = frame_dev; sa.beta_start = (double)h->cfg.per_beta_start; sa.one_minus_start = 1.0 - (double)h->cfg.per_beta_start; sa.beta_frames = (double)h->cfg.per_beta_frames;
     if (n_chunks + 1 <= kCarrySmem && !split_launch && !two_launches) {
         // the whole call as ONE launch: CTAs claim sum groups, chunk groups, search groups, in that order, from a work queue
         SumArgs sm;
-        sm.top_depth = depth; sm.top_vals = w.block_vals; sm.total = w.total; sm.u = w.u; sm.draw_B = u ? 0 : (int)k; sm.seed = h->cfg.seed; sm.counter = (uint64_t)frame;
+        sm.top_depth = depth; sm.top_vals = w.block_vals; sm.total = w.total; sm.u = w.u; sm.draw_B = u ? 0 : (int)k; sm.seed = h->cfg.seed; sm.frame = frame_dev;
         SACB_CUDA(launch_pdl(per_sample_fused, dim3((2 << depth) - 1 + (n_chunks + 7) / 8 + (int)((k + 7) / 8)), dim3(256), 0, st, pdl, sm, w.chunk_sum, w.chunk_fine,
                              w.chunk_carry, tickets + kTicketInts, sa));
         h->kernel_launches += 1;
@@ -1042,7 +1055,7 @@ int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B
         return SACB_OK;
     }
     SACB_CUDA(launch_pdl(per_sum, dim3((2 << depth) - 1), dim3(256), 0, st, pdl, pa, n, depth, w.block_vals, w.total, tickets + 0,
-                         w.u, u ? 0 : (int)k, h->cfg.seed, (uint64_t)frame));
+                         w.u, u ? 0 : (int)k, h->cfg.seed, (const int64_t *)frame_dev));
     h->kernel_launches += 1;
     if (n_chunks + 1 <= kCarrySmem && !split_launch) {
         // chunk pass and search as ONE launch: CTAs claim chunk groups, then search groups, in order from a work queue
@@ -1151,5 +1164,6 @@ extern "C" int sacb_per_get_stats(sacb_handle h, int agent, sacb_per_stats *out)
 extern "C" int sacb_per_set_frame(sacb_handle h, int agent, int64_t frame) {
     if (!h || agent != 0) return fail(SACB_ERR_ARG, "bad argument");
     h->per_frame[0] = frame;
+    h->per_frame_dirty = true;
     return SACB_OK;
 }

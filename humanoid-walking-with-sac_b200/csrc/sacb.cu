@@ -448,13 +448,18 @@ static int per_step_enqueue(sacb_handle h, int64_t B) {
     if (rc) return rc;
     if ((rc = launch_program_part(h, *p, 0))) return rc;
     after_update_launch(h, key);
-    SACB_CUDA(cudaEventRecord(h->ev_td, h->stream));
-    SACB_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_td, 0));
-    if ((rc = per_writeback_launch(h, h->stream2, k))) return rc;
-    if ((rc = per_sample_launch(h, h->stream2, nullptr, B, nullptr))) return rc;
-    SACB_CUDA(cudaEventRecord(h->ev_sampled, h->stream2));
+    static const int exp_mode = getenv("SACB_EXP_PER_STEP") ? atoi(getenv("SACB_EXP_PER_STEP")) : 0;      // timing experiments only (1: no replay work, 2: no events either)
+    if (exp_mode < 2) {
+        SACB_CUDA(cudaEventRecord(h->ev_td, h->stream));
+        SACB_CUDA(cudaStreamWaitEvent(h->stream2, h->ev_td, 0));
+    }
+    if (exp_mode == 0) {
+        if ((rc = per_writeback_launch(h, h->stream2, k))) return rc;
+        if ((rc = per_sample_launch(h, h->stream2, nullptr, B, nullptr))) return rc;
+    }
+    if (exp_mode < 2) SACB_CUDA(cudaEventRecord(h->ev_sampled, h->stream2));
     if ((rc = launch_program_part(h, *p, 1))) return rc;
-    SACB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_sampled, 0));      // whatever follows on the main stream sees the new sample
+    if (exp_mode < 2) SACB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_sampled, 0));      // whatever follows on the main stream sees the new sample
     return SACB_OK;
 }
 
