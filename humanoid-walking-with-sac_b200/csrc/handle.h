@@ -104,6 +104,13 @@ struct ProgramInst {
     // sacb_per_step runs the priority write-back and the next prioritized sample on a second stream under the tail of the update
     cudaGraphExec_t graph_part[2] = {nullptr, nullptr};
     int split = -1;
+    bool parts_built = false;
+    // the whole pipelined learner step (sacb_per_step) as ONE graph: update stages on the main stream, priority write-back and the next
+    // sample forked onto the second stream in front of stage `split`, joined at the end (valid for one buffer length / batch size)
+    cudaGraphExec_t step_graph = nullptr;
+    int64_t step_graph_n = -1, step_graph_k = -1;
+    bool step_graph_failed = false;
+    int step_graph_launches = 0;
     int n_tiles_total = 0, max_stage_tiles = 0;
     int kernels_per_step = 0;
 };
@@ -190,7 +197,8 @@ int pick_variant(uint32_t task_types, uint32_t epilogues, bool allow_light_colsu
 // program.cu
 int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out);
 int launch_program(sacb_handle h, ProgramInst &p);
-int launch_program_part(sacb_handle h, ProgramInst &p, int part);   // 0: up to and including the critic-loss stage, 1: the rest
+int launch_program_part(sacb_handle h, ProgramInst &p, int part);
+int launch_per_step_graph(sacb_handle h, ProgramInst &p, int64_t B, int64_t k);      // SACB_OK, an error, or 1: not available (caller falls back)   // 0: up to and including the critic-loss stage, 1: the rest
 void free_programs(sacb_handle h);
 int check_error_flag(sacb_handle h);
 // the key of the program that serves the next update of this handle (fills ProgramKey::resident), and the bookkeeping behind its launch
@@ -201,5 +209,5 @@ int replay_create(sacb_handle h);
 void replay_destroy(sacb_handle h);
 int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B, int64_t *k_out);   // kernels of one sample() call
 int upload_ring_meta(sacb_handle h);                                                                   // (len, head) of every agent's ring -> device, if a push changed them
-int per_writeback_launch(sacb_handle h, cudaStream_t st, int64_t B);                                 // priorities <- |td| of the last update
+int per_writeback_launch(sacb_handle h, cudaStream_t st, int64_t B, bool pdl_ok = true);                                 // priorities <- |td| of the last update
 }  // namespace sacb

@@ -943,6 +943,7 @@ void free_programs(sacb_handle h) {
     for (auto &kv : h->programs) {
         if (kv.second.graph) cudaGraphExecDestroy(kv.second.graph);
         for (auto g : kv.second.graph_part) if (g) cudaGraphExecDestroy(g);
+        if (kv.second.step_graph) cudaGraphExecDestroy(kv.second.step_graph);
         cudaFree(kv.second.d_tasks); cudaFree(kv.second.d_stages);
     }
     h->programs.clear();
@@ -1159,24 +1160,71 @@ int launch_program(sacb_handle h, ProgramInst &p) {
     return record_step(h, p);
 }
 
+// The replay work may start anywhere behind the critic-loss stage (the TD errors exist from there on).  It is started in front
+// of the actor-loss stage: the stages from there on (losses, dL/da chain, sample backward, policy backward) leave 20-140 SMs
+// idle, so the sampler's kernels do not queue behind the wide critic-backward stages (step 0.2215 -> 0.2075 ms at C2).
+static int compute_split(ProgramInst &p) {
+    const int ns = (int)p.stages.size();
+    int td_stage = -1, actor_stage = -1;
+    for (int s = 0; s < ns; s++)
+        for (int k = p.stages[s].task_begin; k < p.stages[s].task_end; k++) {
+            if (p.tasks[k].type == T_TARGET_LOSS && td_stage < 0) td_stage = s;
+            if (p.tasks[k].type == T_ACTOR_LOSS && actor_stage < 0) actor_stage = s;
+        }
+    if (td_stage < 0) return fail(SACB_ERR_STATE, "program has no critic-loss stage");
+    p.split = actor_stage > td_stage ? actor_stage : td_stage + 1;
+    if (getenv("SACB_PER_SPLIT")) p.split = std::min(ns - 1, std::max(td_stage + 1, atoi(getenv("SACB_PER_SPLIT"))));      // experiment switch
+    return SACB_OK;
+}
+
+// sacb_per_step as one graph launch (two graph launches + two events cost ~8 us per step: 206 against 198 us with no replay work at all)
+int launch_per_step_graph(sacb_handle h, ProgramInst &p, int64_t B, int64_t k) {
+    static const bool off = getenv("SACB_NO_STEP_GRAPH") != nullptr;
+    if (off || h->cfg.launch_mode != SACB_LAUNCH_STAGED || p.step_graph_failed) return 1;
+    const int ns = (int)p.stages.size();
+    const int64_t n = h->r_len[0];
+    if (!p.step_graph || p.step_graph_n != n || p.step_graph_k != k) {
+        if (p.step_graph) { cudaGraphExecDestroy(p.step_graph); p.step_graph = nullptr; }
+        if (p.split < 0) { if (int rc = compute_split(p)) return rc; }
+        if (h->per_frame_dirty) return 1;      // the first (uncaptured) sample uploads the frame counter
+        // host-side bookkeeping of the launch helpers is replayed per graph launch below: undo what the capture pass does to it
+        const int64_t launches0 = h->kernel_launches, frame0 = h->per_frame[0];
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); p.step_graph_failed = true; return 1; }
+        int rc = SACB_OK;
+        for (int s = 0; s < p.split && rc == SACB_OK; s++) rc = launch_stage(h, p, s, h->use_pdl != 0);
+        if (rc == SACB_OK && (cudaEventRecord(h->ev_td, h->stream) != cudaSuccess || cudaStreamWaitEvent(h->stream2, h->ev_td, 0) != cudaSuccess)) rc = SACB_ERR_DEVICE;
+        if (rc == SACB_OK) rc = per_writeback_launch(h, h->stream2, k, false);      // first kernel of the forked branch: a full dependency
+        if (rc == SACB_OK) rc = per_sample_launch(h, h->stream2, nullptr, B, nullptr);
+        if (rc == SACB_OK && cudaEventRecord(h->ev_sampled, h->stream2) != cudaSuccess) rc = SACB_ERR_DEVICE;
+        for (int s = p.split; s < ns && rc == SACB_OK; s++) rc = launch_stage(h, p, s, h->use_pdl != 0);
+        if (rc == SACB_OK && cudaStreamWaitEvent(h->stream, h->ev_sampled, 0) != cudaSuccess) rc = SACB_ERR_DEVICE;
+        const cudaError_t e2 = cudaStreamEndCapture(h->stream, &graph);
+        p.step_graph_launches = ns + (int)(h->kernel_launches - launches0);      // the stage kernels + what the replay helpers counted
+        h->kernel_launches = launches0; h->per_frame[0] = frame0;
+        if (rc != SACB_OK || e2 != cudaSuccess || !graph || cudaGraphInstantiate(&p.step_graph, graph, 0) != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            p.step_graph = nullptr; p.step_graph_failed = true;
+            return 1;
+        }
+        cudaGraphDestroy(graph);
+        p.step_graph_n = n; p.step_graph_k = k;
+    }
+    SACB_CUDA(cudaGraphLaunch(p.step_graph, h->stream));
+    h->kernel_launches += p.step_graph_launches;
+    h->per_frame[0] += 1; h->sample_k = k; h->per_fused = true; h->prio_max_valid = true;
+    return SACB_OK;
+}
+
 int launch_program_part(sacb_handle h, ProgramInst &p, int part) {
     if (h->cfg.launch_mode != SACB_LAUNCH_STAGED) {      // a single cooperative launch cannot be split: part 0 is the whole step
         return part == 0 ? launch_program(h, p) : SACB_OK;
     }
     const int ns = (int)p.stages.size();
-    if (p.split < 0) {
-        // The replay work may start anywhere behind the critic-loss stage (the TD errors exist from there on).  It is started in front
-        // of the actor-loss stage: the stages from there on (losses, dL/da chain, sample backward, policy backward) leave 20-140 SMs
-        // idle, so the sampler's kernels do not queue behind the wide critic-backward stages (step 0.2215 -> 0.2075 ms at C2).
-        int td_stage = -1, actor_stage = -1;
-        for (int s = 0; s < ns; s++)
-            for (int k = p.stages[s].task_begin; k < p.stages[s].task_end; k++) {
-                if (p.tasks[k].type == T_TARGET_LOSS && td_stage < 0) td_stage = s;
-                if (p.tasks[k].type == T_ACTOR_LOSS && actor_stage < 0) actor_stage = s;
-            }
-        if (td_stage < 0) return fail(SACB_ERR_STATE, "program has no critic-loss stage");
-        p.split = actor_stage > td_stage ? actor_stage : td_stage + 1;
-        if (getenv("SACB_PER_SPLIT")) p.split = std::min(ns - 1, std::max(td_stage + 1, atoi(getenv("SACB_PER_SPLIT"))));      // experiment switch
+    if (!p.parts_built) {
+        p.parts_built = true;
+        if (p.split < 0) { if (int rc = compute_split(p)) return rc; }
         for (int part_i = 0; part_i < 2; part_i++) {
             const int s0 = part_i ? p.split : 0, s1 = part_i ? ns : p.split;
             cudaGraph_t graph = nullptr;

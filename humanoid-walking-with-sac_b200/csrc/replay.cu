@@ -5,8 +5,8 @@
 // contiguous ~2.9 KB read (Humanoid), gathered by one warp with coalesced loads.
 //
 // PER sampling reproduces np.random.choice(len, B, p=probs) bit-for-bit downstream of the p**alpha table:
-// One launch per sample() call (per_sample_fused: the three kinds of work below claimed in order as work items of ONE grid;
-// SACB_PER_TWO_LAUNCHES / SACB_PER_THREE_LAUNCHES keep the earlier forms: per_sum + per_chunk_search, per_sum + per_chunk + per_search):
+// Three launches per sample() call, chained with programmatic dependent launch (per_sum, per_chunk, per_search); the same work as one
+// launch of ordered work items (per_sample_fused, SACB_PER_ONE_LAUNCH=1) or as two (per_chunk_search, SACB_PER_TWO_LAUNCHES=1) is built too:
 //   per_sum      float32 total with numpy's pairwise-summation tree (exact same association): CTA subtrees, then the top (last CTA)
 //   chunk groups probs = p_alpha / total (float32), float64 chunk sums, count of "fine" elements
 //   search groups exclusive scan of the chunk sums (per group, shared memory), per-sample inverse-CDF search + provable ambiguity test
@@ -1031,11 +1031,14 @@ int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B
     if (depth > 11) return fail(SACB_ERR_ARG, "capacity too large for the summation heap");
     const float *pa = h->p_alpha;
     int *tickets = w.tickets;
-    static const bool split_launch = getenv("SACB_PER_THREE_LAUNCHES") != nullptr;      // A/B: the round-1 form (separate sum, chunk and search launches)
-    // default: the whole call as ONE launch (per_sample_fused).  sample(256) at N = 1 M on its own: 30.7 us, against 30.2 us for per_sum +
-    // per_chunk_search (SACB_PER_TWO_LAUNCHES=1) and 34.7 us for three launches; under the update (sacb_per_step, 4000 pipelined steps):
-    // 211.3 / 213.2 / 211.5 us per step
+    // Three launches (per_sum, per_chunk, per_search) are the default.  The same work as ONE launch of ordered work items (per_sample_fused,
+    // SACB_PER_ONE_LAUNCH=1) or two (per_sum + per_chunk_search, SACB_PER_TWO_LAUNCHES=1) is bit-exact and faster back to back -- 30.7 / 30.2
+    // against 34.7 us per sample(256) at N = 1 M -- but not where it counts: the trainer's sequence push -> sample -> update runs 306-311 /
+    // 306 against 301.6 us per step (the spinning search / chunk groups hold SMs and load L2 while the others work), the pipelined
+    // learner step 211.3 / 213.2 against 211.5 us.
+    static const bool one_launch = getenv("SACB_PER_ONE_LAUNCH") != nullptr;
     static const bool two_launches = getenv("SACB_PER_TWO_LAUNCHES") != nullptr;
+    const bool split_launch = !one_launch && !two_launches;
     const int n_chunks = (int)((n + kChunk - 1) / kChunk);
     SearchArgs sa;
     sa.p_alpha = pa; sa.n = n; sa.u = w.u; sa.B = (int)k; sa.counters = w.counters; sa.idx_out = w.idx; sa.flagged = w.flagged;
@@ -1075,8 +1078,8 @@ int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B
     return SACB_OK;
 }
 
-int per_writeback_launch(sacb_handle h, cudaStream_t st, int64_t B) {
-    SACB_CUDA(launch_pdl(per_update_kernel, dim3(1), dim3(1024), sizeof(int64_t) * B, st, h->use_pdl != 0, h->prio, h->p_alpha,
+int per_writeback_launch(sacb_handle h, cudaStream_t st, int64_t B, bool pdl_ok) {
+    SACB_CUDA(launch_pdl(per_update_kernel, dim3(1), dim3(1024), sizeof(int64_t) * B, st, h->use_pdl != 0 && pdl_ok, h->prio, h->p_alpha,
                          (const int64_t *)h->last_idx_dev, (const float *)(h->ws + h->L.td), (int)B, h->cfg.per_alpha, 0));
     h->kernel_launches++;
     per_refresh_max(h, st);      // for the next push; same stream, behind the write-back

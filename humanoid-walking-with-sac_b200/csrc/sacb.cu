@@ -446,6 +446,12 @@ static int per_step_enqueue(sacb_handle h, int64_t B) {
     ProgramInst *p;
     rc = get_program(h, key, &p);
     if (rc) return rc;
+    static const int exp_mode0 = getenv("SACB_EXP_PER_STEP") ? atoi(getenv("SACB_EXP_PER_STEP")) : 0;
+    if (exp_mode0 == 0) {      // the whole step -- update stages, forked write-back + next sample, join -- as ONE graph launch
+        rc = launch_per_step_graph(h, *p, B, k);
+        if (rc == SACB_OK) { after_update_launch(h, key); return SACB_OK; }
+        if (rc != 1) return rc;
+    }
     if ((rc = launch_program_part(h, *p, 0))) return rc;
     after_update_launch(h, key);
     static const int exp_mode = getenv("SACB_EXP_PER_STEP") ? atoi(getenv("SACB_EXP_PER_STEP")) : 0;      // timing experiments only (1: no replay work, 2: no events either)
