@@ -481,17 +481,19 @@ def run_ours(args):
     peaks, peak_src = measured_peaks()
     achieved_tf = FLOP_PER_UPDATE / (upd_ms.value * 1e-3) / 1e12
     peak_tf = float(peaks.get("bf16_tflops_sustained", 1400.0))
-    traffic = None      # DRAM bytes of one update program (26 stage kernels, warm caches) from the committed ncu capture
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_update_traffic.json")) as f:
-            traffic = float(json.load(f)["update_dram_bytes"])
-    except Exception:
-        pass
+    traffic, traffic_file = None, None      # DRAM bytes of one update program (its stage kernels, warm caches) from the committed ncu capture
+    for name in ("r02_update_traffic.json", "r01_update_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                traffic, traffic_file = float(json.load(f)["update_dram_bytes"]), name.replace("traffic.json", "stages_ncu.csv")
+            break
+        except Exception:
+            pass
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf, "traffic": traffic,
-                "traffic_source": "NOT measured in this run: constant read from the committed ncu capture profiles/r01_update_stages_ncu.csv: dram__bytes_read.sum + dram__bytes_write.sum summed over the stage kernels of one update (algorithmic bytes if streamed from HBM: 63.7e6; the state stays L2 resident)",
+                "traffic_source": "NOT measured in this run: constant read from the committed ncu capture profiles/%s: dram__bytes_read.sum + dram__bytes_write.sum summed over the stage kernels of one update (algorithmic bytes if streamed from HBM: 63.7e6; the state stays L2 resident)" % traffic_file,
                 "kernel": "sac_update_kernel (one fused update program: %d launches/step in '%s' mode)" % (1 if args.launch == "persistent" else n_st, args.launch),
                 "ms_per_launch_sum": upd_ms.value, "peak_source": peak_src + " bf16 dense, sustained (each product costs 3 bf16 MMAs: algorithmic FLOPs are counted once)",
-                "note": "single-agent B=256 is latency/occupancy bound (SURVEY 8d): 26 dependent stages of <=0.27 GFLOP, ~3 us of fixed cost each (profiles/r01_summary.md)",
+                "note": "single-agent B=256 is latency/occupancy bound (SURVEY 8d): 25 dependent stages of <=0.27 GFLOP, ~3 us of fixed cost each (profiles/r02_summary.md, 'Single agent')",
                 "stage_us": [round(float(stage_us[i]), 2) for i in range(max(0, min(n_st, 64)))],
                 "per_sample": {"ms_per_call": per_call_ms, "samples_per_s": B / (per_call_ms * 1e-3),
                                "achieved_GBps": (3 * 4.0 * CAPACITY + B * 4 * (2 * OBS + ACT + 2)) / (per_call_ms * 1e-3) / 1e9,
