@@ -21,7 +21,7 @@ LAUNCH_STAGED, LAUNCH_PERSISTENT = 0, 1
 NET_POLICY, NET_Q1, NET_Q2, NET_Q1_TARGET, NET_Q2_TARGET = range(5)
 SLOT_PARAM, SLOT_ADAM_M, SLOT_ADAM_V, SLOT_GRAD = range(4)
 REPLAY_UNIFORM, REPLAY_PER = 0, 1
-USE_LAST_SAMPLE, NO_LOSS_READBACK, EXPORT_GRADS, DEVICE_INDICES = 1, 2, 4, 8
+USE_LAST_SAMPLE, NO_LOSS_READBACK, EXPORT_GRADS, DEVICE_INDICES, WRITE_BACK_TD = 1, 2, 4, 8, 16
 
 
 class Config(ctypes.Structure):

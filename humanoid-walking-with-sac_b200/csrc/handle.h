@@ -111,6 +111,7 @@ struct ProgramInst {
     int64_t step_graph_n = -1, step_graph_k = -1;
     bool step_graph_failed = false;
     int step_graph_launches = 0;
+    bool step_graph_fused = false;       // which form of the sampler the capture recorded (sacb_handle_s::per_fused)
     int n_tiles_total = 0, max_stage_tiles = 0;
     int kernels_per_step = 0;
 };
@@ -168,6 +169,7 @@ struct sacb_handle_s {
     float *pin_rows = nullptr;           // packed minibatch rows of sacb_update_batch
     float *pin_hist = nullptr;           // [32 + 4 * kLossHist] scalar block + loss history of agent 0 (sacb_update_steps: ONE read-back for K updates)
     float *pin_small = nullptr;          // [16] losses + error flag read back with ONE synchronisation (finish_update)
+    cudaEvent_t ev_loss = nullptr;       // behind the loss copy: what the host waits for when more work (the |TD| write-back) is enqueued after it
     float *pin_push = nullptr;           // staging of small pushes (<= kPinPushRows rows): no synchronisation on the push path
     cudaEvent_t ev_push = nullptr;       // the H2D copy out of pin_push has completed
     bool push_in_flight = false;

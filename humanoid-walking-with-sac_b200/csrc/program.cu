@@ -1201,6 +1201,7 @@ int launch_per_step_graph(sacb_handle h, ProgramInst &p, int64_t B, int64_t k) {
         if (rc == SACB_OK && cudaStreamWaitEvent(h->stream, h->ev_sampled, 0) != cudaSuccess) rc = SACB_ERR_DEVICE;
         const cudaError_t e2 = cudaStreamEndCapture(h->stream, &graph);
         p.step_graph_launches = ns + (int)(h->kernel_launches - launches0);      // the stage kernels + what the replay helpers counted
+        p.step_graph_fused = h->per_fused;
         h->kernel_launches = launches0; h->per_frame[0] = frame0;
         if (rc != SACB_OK || e2 != cudaSuccess || !graph || cudaGraphInstantiate(&p.step_graph, graph, 0) != cudaSuccess) {
             if (graph) cudaGraphDestroy(graph);
@@ -1213,7 +1214,7 @@ int launch_per_step_graph(sacb_handle h, ProgramInst &p, int64_t B, int64_t k) {
     }
     SACB_CUDA(cudaGraphLaunch(p.step_graph, h->stream));
     h->kernel_launches += p.step_graph_launches;
-    h->per_frame[0] += 1; h->sample_k = k; h->per_fused = true; h->prio_max_valid = true;
+    h->per_frame[0] += 1; h->sample_k = k; h->per_fused = p.step_graph_fused; h->prio_max_valid = true;
     return SACB_OK;
 }
 

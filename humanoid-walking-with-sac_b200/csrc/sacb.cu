@@ -139,6 +139,7 @@ extern "C" int sacb_destroy(sacb_handle h) {
     if (h->pin_push) cudaFreeHost(h->pin_push);
     if (h->pin_u) cudaFreeHost(h->pin_u);
     if (h->ev_u) cudaEventDestroy(h->ev_u);
+    if (h->ev_loss) cudaEventDestroy(h->ev_loss);
     cudaFree(h->act_ws);
     if (h->pin_act) cudaFreeHost(h->pin_act);
     if (h->ev_push) cudaEventDestroy(h->ev_push);
@@ -317,13 +318,25 @@ static int upload_eps(sacb_handle h, int agent, int64_t B, const float *eps_next
     return SACB_OK;
 }
 
-static int finish_update(sacb_handle h, float *losses_out, uint32_t flags) {
-    if (flags & SACB_NO_LOSS_READBACK) return SACB_OK;
-    if (!losses_out) return sacb_synchronize(h);
+// write_back_B > 0: the |TD| priority write-back of the minibatch (replay_buffer.py:84-87) is enqueued BEHIND the loss copy and the host
+// waits for the copy only -- its launches cost the host nothing (the device is still busy with the update) and the device runs it
+// while the caller is back in Python
+static int finish_update(sacb_handle h, float *losses_out, uint32_t flags, int64_t write_back_B = 0) {
+    if ((flags & SACB_NO_LOSS_READBACK) || !losses_out) {
+        if (write_back_B > 0) { if (int rc = per_writeback_launch(h, h->stream, write_back_B)) return rc; }
+        return (flags & SACB_NO_LOSS_READBACK) ? SACB_OK : sacb_synchronize(h);
+    }
     // 3 floats D2H (the `.item()` calls of sac_imp.py:141-143) and the device error flag, into pinned memory, ONE synchronisation
     static_assert(SC_ERROR_FLAG == SC_LOSS_Q1 + 4, "losses and the flag copy are contiguous");
     SACB_CUDA(cudaMemcpyAsync(h->pin_small, h->arena + h->L.scalars + SC_LOSS_Q1, 5 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
-    SACB_CUDA(cudaStreamSynchronize(h->stream));
+    if (write_back_B > 0) {
+        if (!h->ev_loss) SACB_CUDA(cudaEventCreateWithFlags(&h->ev_loss, cudaEventDisableTiming));
+        SACB_CUDA(cudaEventRecord(h->ev_loss, h->stream));
+        if (int rc = per_writeback_launch(h, h->stream, write_back_B)) return rc;
+        SACB_CUDA(cudaEventSynchronize(h->ev_loss));
+    } else {
+        SACB_CUDA(cudaStreamSynchronize(h->stream));
+    }
     memcpy(losses_out, h->pin_small, 3 * sizeof(float));
     int32_t flag;
     memcpy(&flag, h->pin_small + 4, sizeof(flag));
@@ -417,7 +430,13 @@ extern "C" int sacb_update(sacb_handle h, int64_t B, const int64_t *idx, const f
     rc = launch_program(h, *p);
     if (rc) return rc;
     after_update_launch(h, key);
-    return finish_update(h, losses_out, flags);
+    int64_t write_back_B = 0;
+    if (flags & SACB_WRITE_BACK_TD) {
+        if (h->cfg.replay_kind != SACB_REPLAY_PER || h->cfg.n_agents != 1 || !(flags & SACB_USE_LAST_SAMPLE))
+            return fail(SACB_ERR_ARG, "SACB_WRITE_BACK_TD: needs the prioritized buffer and SACB_USE_LAST_SAMPLE");
+        write_back_B = B;
+    }
+    return finish_update(h, losses_out, flags, write_back_B);
 }
 
 // ---- test hook: read back a hidden activation matrix of the last update ----------------------------------------------

@@ -37,9 +37,7 @@ class _ArenaModule(nn.Module):
         for t, (name, p) in enumerate(list(self.named_parameters())):
             host = N.f32(p.detach().cpu().numpy())
             N.check(lib.sacb_import_tensor(owner._h, 0, net_id, N.SLOT_PARAM, t, N.ptr(host), host.size))
-            dev = N.ctypes.c_void_p()
-            N.check(lib.sacb_tensor_dev(owner._h, 0, net_id, N.SLOT_PARAM, t, N.ctypes.byref(dev)))
-            alias = torch.as_tensor(N.DevArray(dev.value, tuple(p.shape), owner), device=f"cuda:{owner._cfg.device}")
+            alias = owner._param_alias(net_id, t, p.shape)
             mod_name, _, leaf = name.rpartition(".")
             getattr(self, mod_name)._parameters[leaf] = nn.Parameter(alias, requires_grad=False)
         return self

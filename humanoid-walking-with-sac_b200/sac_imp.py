@@ -134,6 +134,7 @@ class SAC:
         cfg.seed = random.getrandbits(63) if seed is None else int(seed)
         self._cfg = cfg
         self._h = N.create(cfg)
+        self._arena_base = None
         for net_id, name in enumerate(_NETS):
             getattr(self, name)._bind(self, net_id)
 
@@ -148,17 +149,36 @@ class SAC:
                               if replay == "per" else ReplayBuffer(capacity))
         self.replay_buffer._bind(self)
         self._alpha_is_float = True        # python float until the first update (quirk Q1)
-        self._aliases = [p for n in _NETS for p in getattr(self, n).parameters()]
-        self._alias_versions = None
+        self._alias_version = None
+
+    def _param_alias(self, net_id, t, shape):
+        """Parameter tensor `t` of a network as a VIEW of one tensor spanning the parameter arena: every alias then shares that
+        tensor's version counter, and one integer tells whether anything was written through any of them."""
+        lib = N.lib()
+        if self._arena_base is None:
+            lo, hi = None, 0
+            for net in range(len(_NETS)):
+                for k in range(lib.sacb_num_tensors(self._h, net)):
+                    rows, cols, off, dev = ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_void_p()
+                    N.check(lib.sacb_tensor_info(self._h, net, k, ctypes.byref(rows), ctypes.byref(cols), ctypes.byref(off)))
+                    N.check(lib.sacb_tensor_dev(self._h, 0, net, N.SLOT_PARAM, k, ctypes.byref(dev)))
+                    lo = dev.value if lo is None else min(lo, dev.value)
+                    hi = max(hi, dev.value + 4 * rows.value * cols.value)
+            self._arena_base = (lo, torch.as_tensor(N.DevArray(lo, ((hi - lo) // 4,), self), device=f"cuda:{self._cfg.device}"))
+        dev = ctypes.c_void_p()
+        N.check(lib.sacb_tensor_dev(self._h, 0, net_id, N.SLOT_PARAM, t, ctypes.byref(dev)))
+        lo, base = self._arena_base
+        first, n = (dev.value - lo) // 4, int(np.prod(shape))
+        return base[first:first + n].view(tuple(shape))
 
     def _publish_alias_writes(self):
         """The GEMMs read bf16 hi/lo shadows that the update's own epilogues keep current.  A write through the torch aliases
-        (load_state_dict, `with torch.no_grad(): p.mul_(...)`, ...) bumps the tensors' version counters: the library is then told to
-        re-derive every shadow before the next update.  (`p.data` views have their own counter: call invalidate_shadows() after
-        writing through one.)"""
-        v = [p._version for p in self._aliases]
-        if v != self._alias_versions:
-            self._alias_versions = v
+        (load_state_dict, `with torch.no_grad(): p.mul_(...)`, ...) bumps the version counter the aliases share (they are views of
+        one tensor): the library is then told to re-derive every shadow before the next update.  (`p.data` views have their own
+        counter: call invalidate_shadows() after writing through one.)"""
+        v = self._arena_base[1]._version
+        if v != self._alias_version:
+            self._alias_version = v
             N.check(N.lib().sacb_invalidate_shadows(self._h))
 
     def invalidate_shadows(self):
@@ -262,9 +282,9 @@ class SAC:
         buf._flush()
         if per:
             N.check(lib.sacb_per_sample(self._h, 0, N.ptr(uu, ctypes.c_double), batch_size, None, None, None, None, None, None, None))
+            if self._cfg.per_weighted_loss:      # update_priorities(|q1 - y|): enqueued by the same call, behind the loss copy
+                flags |= N.WRITE_BACK_TD
             N.check(lib.sacb_update(self._h, n, None, N.ptr(e_next), N.ptr(e_cur), N.ptr(losses) if sync else None, flags | N.USE_LAST_SAMPLE))
-            if self._cfg.per_weighted_loss:
-                N.check(lib.sacb_per_update_from_td(self._h, 0, n))
         else:
             N.check(lib.sacb_update(self._h, ix.size, N.ptr(ix, ctypes.c_int64), N.ptr(e_next), N.ptr(e_cur), N.ptr(losses) if sync else None, flags))
         self._alpha_is_float = False

@@ -155,9 +155,12 @@ enum {
     SACB_USE_LAST_SAMPLE = 1,  /* minibatch = rows chosen by the last sacb_per_sample / sacb_stage_indices */
     SACB_NO_LOSS_READBACK = 2, /* do not sync / copy the three loss scalars (throughput mode)                 */
     SACB_EXPORT_GRADS = 4,     /* keep the critic/policy gradients in the SACB_SLOT_GRAD arena (tests)        */
-    SACB_DEVICE_INDICES = 8    /* uniform ring: the B positions are drawn on the device inside the gather stage (keyed bijection of
+    SACB_DEVICE_INDICES = 8,   /* uniform ring: the B positions are drawn on the device inside the gather stage (keyed bijection of
                                   [0, len): B distinct positions = sampling without replacement, replay_buffer.py:15); idx = NULL.
                                   Nothing of the step touches the host: population mode, K updates per call (sacb_update_steps) */
+    SACB_WRITE_BACK_TD = 16    /* prioritized buffer, with SACB_USE_LAST_SAMPLE: priorities of the minibatch <- |q1 - y| + 1e-6
+                                  (update_priorities, replay_buffer.py:84-87; = sacb_per_update_from_td) enqueued behind the loss copy:
+                                  the call returns when the losses have arrived, the write-back runs while the caller is back in Python */
 };
 /* idx: B logical indices (NULL => SACB_USE_LAST_SAMPLE, or the next index set pre-staged with sacb_stage_indices; otherwise SACB_ERR_ARG);
  * eps_next / eps_cur: [B, act] N(0,1) draws of the two policy.sample calls (sac_imp.py:89, :116), NULL => Philox;

@@ -217,6 +217,57 @@ def test_pipelined_step_equals_sequential(hw, launch):
     assert np.array_equal(la, lb) and np.all(np.isfinite(la))
 
 
+@pytest.mark.parametrize("weighted", [True, False])
+def test_update_parameters_equals_the_three_calls(hw, weighted):
+    """update_parameters over the prioritized buffer (sample, then sacb_update with SACB_WRITE_BACK_TD: the |TD| write-back enqueued by the
+    same call behind the loss copy) == sacb_per_sample / sacb_update / sacb_per_update_from_td in sequence, bitwise, with the trainer's
+    push in front of every step, while the ring still grows and after it has filled up."""
+    import ctypes
+    import torch
+    from tests.util import make_agent
+    N = hw._native
+    lib = N.lib()
+    case = cases.UPDATE_CASES["tiny_m2"]
+    B, n, cap, steps = case["batch"], 3040, 3072, 50
+    rng = np.random.RandomState(11)
+    S, A = rng.standard_normal((n + steps, case["obs"])).astype(np.float32), rng.uniform(-0.4, 0.4, (n + steps, case["act"])).astype(np.float32)
+    R, S2 = rng.standard_normal(n + steps).astype(np.float32), rng.standard_normal((n + steps, case["obs"])).astype(np.float32)
+    D = rng.uniform(size=n + steps) < 0.1
+    pri = np.zeros(cap, np.float32)
+    pri[:n] = np.abs(rng.standard_normal(n)) + 1e-6
+    agents = []
+    for _ in range(2):
+        agent, _st = make_agent(hw, case, math="bf16x3", launch="staged", capacity=cap, replay="per", per_weighted_loss=weighted)
+        agent.replay_buffer.push_many(S[:n], A[:n], R[:n], S2[:n], D[:n])
+        agent.replay_buffer.set_priorities(pri)
+        agents.append(agent)
+    seq, one = agents
+    for i in range(steps):
+        u = rng.random_sample(B)
+        t = n + i
+        for a in agents:
+            a.replay_buffer.push(S[t], A[t], float(R[t]), S2[t], bool(D[t]))
+        seq.replay_buffer._flush()
+        la = np.zeros(3, np.float32)
+        N.check(lib.sacb_per_sample(seq._h, 0, N.ptr(u, ctypes.c_double), B, None, None, None, None, None, None, None))
+        N.check(lib.sacb_update(seq._h, B, None, None, None, N.ptr(la), N.USE_LAST_SAMPLE))
+        if weighted:
+            N.check(lib.sacb_per_update_from_td(seq._h, 0, B))
+        out = one.update_parameters(B, u=u)
+        assert (float(la[0]), float(la[1]), float(la[2])) == (out["q1_loss"], out["q2_loss"], out["policy_loss"]), i
+    seq.synchronize(); one.synchronize()
+    for net in ("policy", "q1", "q2", "q1_target", "q2_target"):
+        a, b = getattr(seq, net).state_dict(), getattr(one, net).state_dict()
+        for k in a:
+            assert torch.equal(a[k], b[k]), (net, k)
+    pa, pb = np.empty(cap, np.float32), np.empty(cap, np.float32)
+    N.check(lib.sacb_per_get_priorities(seq._h, 0, N.ptr(pa), cap))
+    N.check(lib.sacb_per_get_priorities(one._h, 0, N.ptr(pb), cap))
+    assert np.array_equal(pa, pb)
+    assert weighted == (not np.array_equal(pa[100:n], pri[100:n]))      # (slots the pushes did not reach) the write-back happens exactly in the IS-weighted mode
+    assert seq.replay_buffer.frame == one.replay_buffer.frame
+
+
 @pytest.mark.parametrize("dist,n", [("floor1pct", 1000000), ("lognormal3", 1000000)])
 def test_per_many_calls_on_adversarial_priorities(hw, dist, n):
     """120 sample() calls (30 720 draws) on the priority sets with thousands of fine probabilities: every index equals numpy's, whether the
