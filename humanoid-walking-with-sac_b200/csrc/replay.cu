@@ -5,13 +5,16 @@
 // contiguous ~2.9 KB read (Humanoid), gathered by one warp with coalesced loads.
 //
 // PER sampling reproduces np.random.choice(len, B, p=probs) bit-for-bit downstream of the p**alpha table:
-// Three launches per sample() call, chained with programmatic dependent launch (per_sum, per_chunk, per_search); the same work as one
-// launch of ordered work items (per_sample_fused, SACB_PER_ONE_LAUNCH=1) or as two (per_chunk_search, SACB_PER_TWO_LAUNCHES=1) is built too:
-//   per_sum      float32 total with numpy's pairwise-summation tree (exact same association): CTA subtrees, then the top (last CTA)
-//   chunk groups probs = p_alpha / total (float32), float64 chunk sums, count of "fine" elements
-//   search groups exclusive scan of the chunk sums (per group, shared memory), per-sample inverse-CDF search + provable ambiguity test
-//                (see DESIGN.md "PER exactness"); the last group then runs the sequential float64 cumsum (numpy's own order) for
-//                samples the test could not certify, IS weights (N p)^-beta / max, logical indices, ring slots for the update's gather
+// Three launches per sample() call, chained with programmatic dependent launch and free of serial tails between them (capacity <= 2 M):
+//   per_sum           CTA subtrees of numpy's pairwise-summation tree over p_alpha (float32, the exact same association)
+//   per_chunk_notail  every CTA adds the top of that tree itself (<= 512 values) -> total; probs = p_alpha / total (float32), float64 chunk
+//                     sums, count of "fine" elements
+//   per_search_scan   every CTA scans the chunk sums itself (shared memory), per-sample inverse-CDF search + provable ambiguity test
+//                     (see DESIGN.md "PER exactness"); the last group then runs the sequential float64 cumsum (numpy's own order) for
+//                     samples the test could not certify, IS weights (N p)^-beta / max, logical indices, ring slots for the update's gather
+// The forms that finish the sum / the scan in the last CTA to arrive (per_sum(tail), per_chunk, per_search: SACB_PER_TAILS=1, and any capacity
+// above 2 M), and the same work as one launch of ordered work items (per_sample_fused, SACB_PER_ONE_LAUNCH=1) or as two (per_chunk_search,
+// SACB_PER_TWO_LAUNCHES=1) are built too; all are bit-identical.
 #include <cmath>
 #include <cstring>
 #include <algorithm>
@@ -193,8 +196,10 @@ __device__ float top_tree_sum(int64_t n, int top_depth, const float *top_vals) {
 
 // grid = top heap size; CTA id+1 = heap id of the top tree (leaf threshold kSumBlockMax).  The last CTA to finish adds the
 // top of the tree (numpy's association) and publishes the float32 total.  draw_B > 0: the B uniforms of this call are drawn here.
+// tail = 0: no finishing step here -- the CTAs of the next kernel (per_chunk_notail) each add the top of the tree themselves (<= 512 values, the
+// same function, the same association), which takes the completion ticket (two dependent atomics) and the one-CTA tail off the chain.
 __global__ void __launch_bounds__(256) per_sum(const float *p_alpha, int64_t n, int top_depth, float *top_vals, float *total, int *ticket,
-                                               double *u, int draw_B, uint64_t seed, const int64_t *frame) {
+                                               double *u, int draw_B, uint64_t seed, const int64_t *frame, int tail) {
     SACB_PDL_ENTER();
     __shared__ float s_heap[kSumHeap];
     __shared__ unsigned char s_state[kSumHeap];
@@ -207,7 +212,7 @@ __global__ void __launch_bounds__(256) per_sum(const float *p_alpha, int64_t n, 
         const float v = pw_block_sum(p_alpha, s, (int)m, s_heap, s_state, s_leaf);
         if (threadIdx.x == 0) top_vals[id] = v;
     }
-    if (!last_block_done(ticket)) return;
+    if (!tail || !last_block_done(ticket)) return;
     const float tot = top_tree_sum(n, top_depth, top_vals);
     if (threadIdx.x == 0) *total = tot;
 }
@@ -332,6 +337,16 @@ __global__ void __launch_bounds__(256) per_chunk(const float *p_alpha, int64_t n
     chunk_group(p_alpha, n, *total, (int)blockIdx.x, chunk_sum, chunk_fine);
     if (!last_block_done(ticket)) return;
     carry_scan(chunk_sum, chunk_fine, n_chunks, carry, counters);
+}
+
+// the same pass behind per_sum(tail = 0): every CTA first adds the top of the summation tree itself (CTA 0 publishes the total); no
+// completion ticket, no scan tail -- the search CTAs scan the chunk sums themselves (per_search_scan)
+__global__ void __launch_bounds__(256) per_chunk_notail(const float *p_alpha, int64_t n, int top_depth, const float *top_vals, float *total,
+                                                        double *chunk_sum, int *chunk_fine) {
+    SACB_PDL_ENTER();
+    const float tot = top_tree_sum(n, top_depth, top_vals);
+    if (blockIdx.x == 0 && threadIdx.x == 0) *total = tot;
+    chunk_group(p_alpha, n, tot, (int)blockIdx.x, chunk_sum, chunk_fine);
 }
 
 // numpy's own algorithm -- cdf = cumsum(float64(probs)) strictly left to right, cdf /= cdf[-1], searchsorted(side='right') --
@@ -548,6 +563,23 @@ __global__ void __launch_bounds__(256) per_search(const float *total, const doub
     if (staged) for (int i = threadIdx.x; i <= a.n_chunks; i += blockDim.x) s_carry[i] = carry[i];
     __syncthreads();
     search_group(a, staged ? s_carry : carry, a.counters[0], tot, (int)blockIdx.x, (int)gridDim.x);
+}
+
+// per_search behind per_chunk_notail (capacity <= 2 M: the chunk prefixes fit into shared memory): every search group scans the chunk sums
+// itself (1 K additions by carry_scan, the function the tail of per_chunk runs: same values) instead of reading prefixes a tail CTA wrote
+__global__ void __launch_bounds__(256) per_search_scan(const float *total, double *carry, SearchArgs a) {
+    SACB_PDL_ENTER();
+    const float tot = *total;
+    __shared__ double s_carry[kCarrySmem];
+    __shared__ int s_cnt[2];
+    carry_scan(a.chunk_sum, a.chunk_fine, a.n_chunks, s_carry, s_cnt);
+    __syncthreads();
+    if (blockIdx.x == 0) {      // the global copies (exact pass, statistics)
+        for (int i = threadIdx.x; i <= a.n_chunks; i += blockDim.x) carry[i] = s_carry[i];
+        if (threadIdx.x == 0) a.counters[0] = s_cnt[0];
+    }
+    if (!search_group(a, s_carry, s_cnt[0], tot, (int)blockIdx.x, (int)gridDim.x)) return;
+    if (threadIdx.x == 0) { a.counters[3] = a.counters[1]; a.counters[1] = 0; }      // flagged count of this call; reset for the next one
 }
 
 // per_chunk and per_search as ONE launch (capacity <= 2 M: the chunk prefixes fit into shared memory).  CTAs claim work items in order
@@ -1031,7 +1063,7 @@ int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B
     if (depth > 11) return fail(SACB_ERR_ARG, "capacity too large for the summation heap");
     const float *pa = h->p_alpha;
     int *tickets = w.tickets;
-    // Three launches (per_sum, per_chunk, per_search) are the default.  The same work as ONE launch of ordered work items (per_sample_fused,
+    // Three launches are the default.  The same work as ONE launch of ordered work items (per_sample_fused,
     // SACB_PER_ONE_LAUNCH=1) or two (per_sum + per_chunk_search, SACB_PER_TWO_LAUNCHES=1) is bit-exact and faster back to back -- 30.7 / 30.2
     // against 34.7 us per sample(256) at N = 1 M -- but not where it counts: the trainer's sequence push -> sample -> update runs 306-311 /
     // 306 against 301.6 us per step (the spinning search / chunk groups hold SMs and load L2 while the others work), the pipelined
@@ -1057,9 +1089,22 @@ int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B
         if (k_out) *k_out = k;
         return SACB_OK;
     }
+    // three launches, no serial tails between them (SACB_PER_TAILS=1: the forms that finish the sum / the scan in the last CTA to arrive)
+    static const bool tails = getenv("SACB_PER_TAILS") != nullptr;
+    const bool no_tails = split_launch && !tails && n_chunks + 1 <= kCarrySmem;
     SACB_CUDA(launch_pdl(per_sum, dim3((2 << depth) - 1), dim3(256), 0, st, pdl, pa, n, depth, w.block_vals, w.total, tickets + 0,
-                         w.u, u ? 0 : (int)k, h->cfg.seed, (const int64_t *)frame_dev));
+                         w.u, u ? 0 : (int)k, h->cfg.seed, (const int64_t *)frame_dev, no_tails ? 0 : 1));
     h->kernel_launches += 1;
+    if (no_tails) {
+        SACB_CUDA(launch_pdl(per_chunk_notail, dim3((n_chunks + 7) / 8), dim3(256), 0, st, pdl, pa, n, depth, (const float *)w.block_vals, w.total,
+                             w.chunk_sum, w.chunk_fine));
+        SACB_CUDA(launch_pdl(per_search_scan, dim3((int)((k + 7) / 8)), dim3(256), 0, st, pdl, (const float *)w.total, w.chunk_carry, sa));
+        h->kernel_launches += 2;
+        h->per_fused = true;      // the flagged count of the call is kept in counters[3]
+        h->sample_k = k;
+        if (k_out) *k_out = k;
+        return SACB_OK;
+    }
     if (n_chunks + 1 <= kCarrySmem && !split_launch) {
         // chunk pass and search as ONE launch: CTAs claim chunk groups, then search groups, in order from a work queue
         SACB_CUDA(launch_pdl(per_chunk_search, dim3((n_chunks + 7) / 8 + (int)((k + 7) / 8)), dim3(256), 0, st, pdl, (const float *)w.total, w.chunk_sum, w.chunk_fine,
