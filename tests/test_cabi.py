@@ -37,6 +37,15 @@ def test_config_struct_matches_header(hw):
     assert abs(cfg.per_alpha - 0.6) < 1e-7 and abs(cfg.per_beta_start - 0.4) < 1e-7 and cfg.per_beta_frames == 100000
 
 
+def test_enumerators_match_header(hw):
+    """every `SACB_<NAME> = <int>` of include/sacb200.h (status codes, modes, net / slot ids, update flags) has the same value in the binding"""
+    hdr = open(os.path.join(ROOT, "include", "sacb200.h")).read()
+    found = re.findall(r"\bSACB_([A-Z0-9_]+)\s*=\s*(-?\d+)", hdr)
+    assert len(found) >= 25
+    for name, val in found:
+        assert getattr(hw._native, name) == int(val), name
+
+
 def test_reference_signatures_are_mirrored(hw):
     """Positional parameters of the reference API (sac_imp.py:9-20, :54, :74; replay_buffer.py:7, :26)."""
     sig = inspect.signature(hw.SAC.__init__)
