@@ -210,6 +210,8 @@ struct Program {
     const float2 *adam_table;     // [kAdamTable] (step_size, sqrt(bc2)) of Adam step t+1 for t = index, computed on the host in float64
     unsigned long long *timeline; // optional [n_stages][4]: earliest CTA start, earliest dependency release, latest CTA end (profiling aid)
     unsigned long long *trace; // optional [grid][kTraceSlots] globaltimer stamps of each CTA's first tile (profiling aid), or null
+    float *host_losses;       // pinned HOST memory (addressable from the device), or null: T_FINISH of agent 0 stores the three losses, the
+                              // alpha loss and the error flag there as well, so that the caller's read-back needs no copy behind the step
 };
 
 // ---- tile geometry ----------------------------------------------------------------------------------------

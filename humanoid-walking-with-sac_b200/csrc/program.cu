@@ -1125,6 +1125,7 @@ int get_program(sacb_handle h, const ProgramKey &key, ProgramInst **out) {
     P.ring_meta = h->ring_meta;
     P.error_flag = h->error_flag;
     P.trace = nullptr; P.timeline = nullptr; P.adam_table = h->adam_table;
+    P.host_losses = h->cfg.n_agents == 1 ? h->pin_small : nullptr;
     p.kernels_per_step = h->cfg.launch_mode == SACB_LAUNCH_PERSISTENT ? 1 : (int)p.stages.size();
 
     // capture one step into a CUDA graph (stage kernels, or memset + the single cooperative launch)

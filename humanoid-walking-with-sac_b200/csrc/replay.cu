@@ -436,7 +436,8 @@ struct SearchArgs {
 };
 // group sg of n_sg: 8 samples, one per warp; cr = chunk prefixes (shared or global), F = number of fine elements.  The last group to
 // finish runs the serial tail.  Returns true in that group only (after the tail).
-__device__ __forceinline__ bool search_group(const SearchArgs &a, const double *cr, int F, float tot, int sg, int n_sg) {
+// uu_pre >= 0: this warp's uniform, fetched by the caller ahead of its prologue (host-drawn uniforms are read from pinned host memory)
+__device__ __forceinline__ bool search_group(const SearchArgs &a, const double *cr, int F, float tot, int sg, int n_sg, double uu_pre = -1.0) {
     const float *p_alpha = a.p_alpha; const int64_t n = a.n; const double *u = a.u; const int B = a.B, n_chunks = a.n_chunks;
     int *counters = a.counters; int64_t *idx_out = a.idx_out; int *flagged = a.flagged;
     double *carry_exact = a.carry_exact; const double *chunk_sum = a.chunk_sum; const int *chunk_fine = a.chunk_fine;
@@ -445,7 +446,7 @@ __device__ __forceinline__ bool search_group(const SearchArgs &a, const double *
     const int j = sg * 8 + warp;
     if (j < B) {      // warp-uniform
         const double last = cr[n_chunks];
-        const double uu = u[j];
+        const double uu = uu_pre >= 0.0 ? uu_pre : u[j];
         // cdf / last <= u (an IEEE divide per probed element, like numpy's cdf /= cdf[-1]) decided without the divide unless the
         // element is within 2^-49 relative of u * last: outside that band the rounded quotient cannot land on the other side of u
         const double t = __dmul_rn(uu, last), t_lo = __dmul_rn(t, 1.0 - 1.7763568394002505e-15), t_hi = __dmul_rn(t, 1.0 + 1.7763568394002505e-15);
@@ -570,6 +571,8 @@ __global__ void __launch_bounds__(256) per_search(const float *total, const doub
 __global__ void __launch_bounds__(256) per_search_scan(const float *total, double *carry, SearchArgs a) {
     SACB_PDL_ENTER();
     const float tot = *total;
+    const int j = (int)blockIdx.x * 8 + (int)(threadIdx.x >> 5);
+    const double uu_pre = j < a.B ? a.u[j] : -1.0;      // in flight during the scan
     __shared__ double s_carry[kCarrySmem];
     __shared__ int s_cnt[2];
     carry_scan(a.chunk_sum, a.chunk_fine, a.n_chunks, s_carry, s_cnt);
@@ -578,7 +581,7 @@ __global__ void __launch_bounds__(256) per_search_scan(const float *total, doubl
         for (int i = threadIdx.x; i <= a.n_chunks; i += blockDim.x) carry[i] = s_carry[i];
         if (threadIdx.x == 0) a.counters[0] = s_cnt[0];
     }
-    if (!search_group(a, s_carry, s_cnt[0], tot, (int)blockIdx.x, (int)gridDim.x)) return;
+    if (!search_group(a, s_carry, s_cnt[0], tot, (int)blockIdx.x, (int)gridDim.x, uu_pre)) return;
     if (threadIdx.x == 0) { a.counters[3] = a.counters[1]; a.counters[1] = 0; }      // flagged count of this call; reset for the next one
 }
 
@@ -719,8 +722,14 @@ __global__ void __launch_bounds__(1024) max_reduce_kernel(const float *x, int64_
     }
 }
 
+// src_rows != null: the `count` transitions themselves are moved here too, straight out of the pinned staging block (host memory is
+// addressable from the device): the trainer's one-transition push then costs the host one launch, no copy call
 __global__ void per_push_kernel(float *prio, float *p_alpha, const float *block_max, int n_blocks, int empty, int64_t pos, int64_t count,
-                                int64_t capacity, float alpha) {
+                                int64_t capacity, float alpha, const float4 *src_rows, float4 *ring, int row_vec4) {
+    if (src_rows) {      // pos + count <= capacity: a run never crosses the end of the ring
+        float4 *dst = ring + pos * row_vec4;
+        for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count * row_vec4; k += (int64_t)gridDim.x * blockDim.x) dst[k] = src_rows[k];
+    }
     float m = 1.0f;                                            // `if self.buffer else 1.0`
     if (!empty) { m = block_max[0]; for (int i = 1; i < n_blocks; i++) m = fmaxf(m, block_max[i]); }
     const float pa = powf(m, alpha);
@@ -893,12 +902,15 @@ static void per_refresh_max(sacb_handle h, cudaStream_t st) {
     h->prio_max_valid = true;
 }
 
-static int per_push_priorities(sacb_handle h, int64_t pos, int64_t count, bool empty) {
+static int per_push_priorities(sacb_handle h, int64_t pos, int64_t count, bool empty, const float *pinned_rows = nullptr) {
     PerWs w = per_ws_of(h, 0);
     const int nb = 128;
     if (!empty && !h->prio_max_valid) per_refresh_max(h, h->stream);
-    per_push_kernel<<<(int)std::min<int64_t>(64, (count + 255) / 256), 256, 0, h->stream>>>(h->prio, h->p_alpha, w.block_max, nb, empty ? 1 : 0, pos, count,
-                                                                                          h->cfg.capacity, h->cfg.per_alpha);
+    const int row_vec4 = (int)(h->ring_row / 4);
+    const int64_t work = pinned_rows ? std::max<int64_t>(count, count * row_vec4) : count;
+    per_push_kernel<<<(int)std::min<int64_t>(64, (work + 255) / 256), 256, 0, h->stream>>>(h->prio, h->p_alpha, w.block_max, nb, empty ? 1 : 0, pos, count,
+                                                                                         h->cfg.capacity, h->cfg.per_alpha, reinterpret_cast<const float4 *>(pinned_rows),
+                                                                                         reinterpret_cast<float4 *>(h->ring), row_vec4);
     h->kernel_launches++;
     if (empty) h->prio_max_valid = false;      // the first push writes 1.0 into an all-zero table: reduce again next time
     SACB_CUDA(cudaGetLastError());
@@ -964,9 +976,11 @@ extern "C" int sacb_push_rows(sacb_handle h, int agent, const float *rows, int64
         if (per) slot = h->r_pos[agent];
         else slot = h->r_len[agent] < cap ? (h->r_head[agent] + h->r_len[agent]) % cap : h->r_head[agent];
         const int64_t run = std::min(n - done_n, cap - slot);
-        SACB_CUDA(cudaMemcpyAsync(ring + slot * row, rows + done_n * row, sizeof(float) * row * run, cudaMemcpyHostToDevice, h->stream));
+        static const bool copy_calls = getenv("SACB_PINNED_COPIES") != nullptr;      // A/B: cudaMemcpyAsync out of the pinned blocks instead
+        const bool by_kernel = per && staged && agent == 0 && !copy_calls;      // the push kernel moves the rows out of the pinned block itself
+        if (!by_kernel) SACB_CUDA(cudaMemcpyAsync(ring + slot * row, rows + done_n * row, sizeof(float) * row * run, cudaMemcpyHostToDevice, h->stream));
         if (per) {
-            int rc = per_push_priorities(h, slot, run, h->r_len[agent] == 0);
+            int rc = per_push_priorities(h, slot, run, h->r_len[agent] == 0, by_kernel ? rows + done_n * row : nullptr);
             if (rc) return rc;
             h->r_pos[agent] = (slot + run) % cap;
             h->r_len[agent] = std::min(cap, h->r_len[agent] + run);
@@ -1053,12 +1067,18 @@ int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B
             if (cudaMallocHost(&h->pin_u, sizeof(double) * h->cfg.max_batch) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_u, cudaEventDisableTiming) != cudaSuccess)
                 return fail(SACB_ERR_NOMEM, "pinned allocation failed");
         }
-        if (h->u_in_flight) SACB_CUDA(cudaEventSynchronize(h->ev_u));      // the previous copy out of the block (long done)
-        memcpy(h->pin_u, u, sizeof(double) * k);
-        SACB_CUDA(cudaMemcpyAsync(w.u, h->pin_u, sizeof(double) * k, cudaMemcpyHostToDevice, st));
-        SACB_CUDA(cudaEventRecord(h->ev_u, st));
-        h->u_in_flight = true;
+        if (h->u_in_flight) SACB_CUDA(cudaEventSynchronize(h->ev_u));      // the previous call's search kernel has read the block (long done)
+        memcpy(h->pin_u, u, sizeof(double) * k);      // the search kernel reads them from here (host memory is addressable from the device): no copy call
     }
+    static const bool copy_calls = getenv("SACB_PINNED_COPIES") != nullptr;
+    if (u && copy_calls) SACB_CUDA(cudaMemcpyAsync(w.u, h->pin_u, sizeof(double) * k, cudaMemcpyHostToDevice, st));
+    const double *u_dev = u && !copy_calls ? h->pin_u : w.u;
+    auto sampled = [&]() -> int {      // behind the last kernel of the call
+        if (u) { SACB_CUDA(cudaEventRecord(h->ev_u, st)); h->u_in_flight = true; }
+        h->sample_k = k;
+        if (k_out) *k_out = k;
+        return SACB_OK;
+    };
     const int depth = top_depth_of(n);
     if (depth > 11) return fail(SACB_ERR_ARG, "capacity too large for the summation heap");
     const float *pa = h->p_alpha;
@@ -1073,7 +1093,7 @@ int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B
     const bool split_launch = !one_launch && !two_launches;
     const int n_chunks = (int)((n + kChunk - 1) / kChunk);
     SearchArgs sa;
-    sa.p_alpha = pa; sa.n = n; sa.u = w.u; sa.B = (int)k; sa.counters = w.counters; sa.idx_out = w.idx; sa.flagged = w.flagged;
+    sa.p_alpha = pa; sa.n = n; sa.u = u_dev; sa.B = (int)k; sa.counters = w.counters; sa.idx_out = w.idx; sa.flagged = w.flagged;
     sa.ticket = tickets + 2 * kTicketInts; sa.carry_exact = w.cdf_exact; sa.chunk_sum = w.chunk_sum; sa.chunk_fine = w.chunk_fine; sa.n_chunks = n_chunks;
     sa.weights = w.weights; sa.slots = h->slots; sa.isw_ws = h->ws + h->L.isw; sa.idx_copy = h->last_idx_dev;
     sa.frame = frame_dev; sa.beta_start = (double)h->cfg.per_beta_start; sa.one_minus_start = 1.0 - (double)h->cfg.per_beta_start; sa.beta_frames = (double)h->cfg.per_beta_frames;
@@ -1085,9 +1105,7 @@ int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B
                              w.chunk_carry, tickets + kTicketInts, sa));
         h->kernel_launches += 1;
         h->per_fused = true;
-        h->sample_k = k;
-        if (k_out) *k_out = k;
-        return SACB_OK;
+        return sampled();
     }
     // three launches, no serial tails between them (SACB_PER_TAILS=1: the forms that finish the sum / the scan in the last CTA to arrive)
     static const bool tails = getenv("SACB_PER_TAILS") != nullptr;
@@ -1101,9 +1119,7 @@ int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B
         SACB_CUDA(launch_pdl(per_search_scan, dim3((int)((k + 7) / 8)), dim3(256), 0, st, pdl, (const float *)w.total, w.chunk_carry, sa));
         h->kernel_launches += 2;
         h->per_fused = true;      // the flagged count of the call is kept in counters[3]
-        h->sample_k = k;
-        if (k_out) *k_out = k;
-        return SACB_OK;
+        return sampled();
     }
     if (n_chunks + 1 <= kCarrySmem && !split_launch) {
         // chunk pass and search as ONE launch: CTAs claim chunk groups, then search groups, in order from a work queue
@@ -1118,9 +1134,7 @@ int per_sample_launch(sacb_handle h, cudaStream_t st, const double *u, int64_t B
         h->kernel_launches += 2;
         h->per_fused = false;
     }
-    h->sample_k = k;
-    if (k_out) *k_out = k;
-    return SACB_OK;
+    return sampled();
 }
 
 int per_writeback_launch(sacb_handle h, cudaStream_t st, int64_t B, bool pdl_ok) {

@@ -326,9 +326,13 @@ static int finish_update(sacb_handle h, float *losses_out, uint32_t flags, int64
         if (write_back_B > 0) { if (int rc = per_writeback_launch(h, h->stream, write_back_B)) return rc; }
         return (flags & SACB_NO_LOSS_READBACK) ? SACB_OK : sacb_synchronize(h);
     }
-    // 3 floats D2H (the `.item()` calls of sac_imp.py:141-143) and the device error flag, into pinned memory, ONE synchronisation
+    // the three losses (the `.item()` calls of sac_imp.py:141-143) and the device error flag: the last stage of the step (T_FINISH) has
+    // stored them into the pinned block itself (Program::host_losses), ONE synchronisation and no copy behind the step.
+    // (population handles and SACB_PINNED_COPIES=1: one D2H copy of the five floats)
     static_assert(SC_ERROR_FLAG == SC_LOSS_Q1 + 4, "losses and the flag copy are contiguous");
-    SACB_CUDA(cudaMemcpyAsync(h->pin_small, h->arena + h->L.scalars + SC_LOSS_Q1, 5 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    static const bool copy_calls = getenv("SACB_PINNED_COPIES") != nullptr;
+    if (h->cfg.n_agents != 1 || copy_calls)
+        SACB_CUDA(cudaMemcpyAsync(h->pin_small, h->arena + h->L.scalars + SC_LOSS_Q1, 5 * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     if (write_back_B > 0) {
         if (!h->ev_loss) SACB_CUDA(cudaEventCreateWithFlags(&h->ev_loss, cudaEventDisableTiming));
         SACB_CUDA(cudaEventRecord(h->ev_loss, h->stream));

@@ -778,6 +778,8 @@ __device__ __forceinline__ void task_finish(const Task &t, const Program &P, int
     }
     __syncthreads();
     if (threadIdx.x < 32) scalars[threadIdx.x] = sc[threadIdx.x];
+    static_assert(SC_ERROR_FLAG == SC_LOSS_Q1 + 4, "losses and the flag are contiguous");
+    if (P.host_losses && agent == 0 && threadIdx.x < 5) P.host_losses[threadIdx.x] = sc[SC_LOSS_Q1 + threadIdx.x];
 }
 
 }  // namespace sacb
