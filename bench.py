@@ -568,7 +568,7 @@ def run_ours(args):
                 "data": "synthetic",
                 "config": bench_config(args, world),
                 "e2e": {"value": e2e, "unit": "updates/s", "h2d_bytes_per_step": row_bytes + 8 * B, "d2h_bytes_per_step": 12,
-                        "what": "the trainer's own call sequence (trainer.py:190-205): replay_buffer.push(one transition) + update_parameters(256) with host-drawn uniforms, three losses read back, every step",
+                        "what": "the trainer's own call sequence (trainer.py:190-205): replay_buffer.push(one transition) + update_parameters(256) with host-drawn uniforms, three losses read back, every step; the pushed row and the uniforms cross host->device out of pinned staging blocks (read there by the push / search kernels), the losses device->host into a pinned block (stored by the last stage), inside the timed region",
                         "batched_k8": {"value": e2e_k, "unit": "updates/s", "h2d_bytes_per_step": row_bytes, "d2h_bytes_per_step": 12,
                                        "what": "8 pushes + learner_steps(256, k=8): uniforms / eps drawn on the device, one read-back of the 8 loss triples per call"}},
                 "gpu_launches": int(launches), "clocks": clk.summary(), "roofline": roofline, "cpu_baseline": cpu, "eager_cuda_baseline": eager, "sharded": sharded,
