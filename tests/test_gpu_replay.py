@@ -268,6 +268,46 @@ def test_update_parameters_equals_the_three_calls(hw, weighted):
     assert seq.replay_buffer.frame == one.replay_buffer.frame
 
 
+def test_trainer_path_is_reproducible_over_many_steps(hw):
+    """1500 trainer steps (push + update_parameters, host uniforms, losses read back) on two handles fed the same data: identical
+    losses at every step and identical weights / priorities at the end.  The pushed row, the uniforms and the losses cross the bus
+    through pinned blocks that the kernels touch directly and the host reuses every step: a reuse before the device is done with a
+    block would show up here as a difference."""
+    import torch
+    from tests.util import make_agent
+    N = hw._native
+    lib = N.lib()
+    case = cases.UPDATE_CASES["tiny_m2"]
+    B, n, cap, steps = case["batch"], 2000, 2048, 1500
+    rng = np.random.RandomState(23)
+    S, A = rng.standard_normal((n, case["obs"])).astype(np.float32), rng.uniform(-0.4, 0.4, (n, case["act"])).astype(np.float32)
+    R, S2, D = rng.standard_normal(n).astype(np.float32), rng.standard_normal((n, case["obs"])).astype(np.float32), rng.uniform(size=n) < 0.1
+    agents = []
+    for _ in range(2):
+        agent, _st = make_agent(hw, case, math="bf16x3", launch="staged", capacity=cap, replay="per", per_weighted_loss=True)
+        agent.replay_buffer.push_many(S, A, R, S2, D)
+        agents.append(agent)
+    a0, a1 = agents
+    for i in range(steps):
+        u = rng.random_sample(B)
+        s, a, r, s2, d = rng.standard_normal(case["obs"]), rng.uniform(-0.4, 0.4, case["act"]), float(rng.standard_normal()), rng.standard_normal(case["obs"]), bool(rng.uniform() < 0.1)
+        outs = []
+        for ag in agents:
+            ag.replay_buffer.push(s, a, r, s2, d)
+            outs.append(ag.update_parameters(B, u=u))
+        assert outs[0] == outs[1], i
+        assert all(np.isfinite(v) for v in outs[0].values()), i
+    a0.synchronize(); a1.synchronize()
+    for net in ("policy", "q1", "q2", "q1_target", "q2_target"):
+        x, y = getattr(a0, net).state_dict(), getattr(a1, net).state_dict()
+        for k in x:
+            assert torch.equal(x[k], y[k]), (net, k)
+    pa, pb = np.empty(cap, np.float32), np.empty(cap, np.float32)
+    N.check(lib.sacb_per_get_priorities(a0._h, 0, N.ptr(pa), cap))
+    N.check(lib.sacb_per_get_priorities(a1._h, 0, N.ptr(pb), cap))
+    assert np.array_equal(pa, pb)
+
+
 @pytest.mark.parametrize("dist,n", [("floor1pct", 1000000), ("lognormal3", 1000000)])
 def test_per_many_calls_on_adversarial_priorities(hw, dist, n):
     """120 sample() calls (30 720 draws) on the priority sets with thousands of fine probabilities: every index equals numpy's, whether the
