@@ -189,6 +189,7 @@ extern "C" int sacb_dp_ipc_handle(sacb_handle h, void *handle_out_64_bytes) {
 extern "C" int sacb_dp_connect(sacb_handle h, int rank, int world, const void *handles) {
     if (!h || rank < 0 || world < 1 || world > 8 || rank >= world || (!handles && world > 1)) return fail(SACB_ERR_ARG, "data-parallel peer exchange serves 1..8 replicas on one node");
     if (h->cfg.n_agents != 1) return fail(SACB_ERR_ARG, "data-parallel mode drives a single agent");
+    if (h->cfg.layer_norm) return fail(SACB_ERR_ARG, "data-parallel mode does not serve the LayerNorm variant (its gradient exchange is not validated)");
     SACB_CUDA(cudaSetDevice(h->cfg.device));
     for (int p = 0; p < world; p++) {
         if (p == rank) { h->dp_peer_arena[p] = h->arena; continue; }
@@ -264,6 +265,7 @@ extern "C" int sacb_dp_grad_buffer(sacb_handle h, int phase, void **dev_ptr, int
 namespace sacb { int replay_stage_slots(sacb_handle h, const int64_t *idx, int64_t B); }
 
 extern "C" int sacb_dp_backward(sacb_handle h, int phase, int64_t B_local, const int64_t *idx, const float *eps_next, const float *eps_cur) {
+    if (h && h->cfg.layer_norm) return fail(SACB_ERR_ARG, "data-parallel mode does not serve the LayerNorm variant (its gradient exchange is not validated)");
     if (!h || phase < 0 || phase > 1 || h->cfg.n_agents != 1) return fail(SACB_ERR_ARG, "bad argument");
     if (B_local < 1 || B_local > h->L.maxB) return fail(SACB_ERR_ARG, "batch size out of range");
     if ((eps_next == nullptr) != (eps_cur == nullptr)) return fail(SACB_ERR_ARG, "pass both eps arrays or neither");

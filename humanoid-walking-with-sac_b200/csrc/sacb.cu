@@ -55,6 +55,7 @@ extern "C" int sacb_create(const sacb_config *cfg, sacb_handle *out) {
     if (cfg->n_hidden != 2 && cfg->n_hidden != 3) return fail(SACB_ERR_ARG, "n_hidden must be 2 (networks_model1) or 3 (networks_model2)");
     if (cfg->max_batch < 1 || cfg->n_agents < 1 || cfg->capacity < 1) return fail(SACB_ERR_ARG, "bad max_batch / n_agents / capacity");
     if (2 * cfg->act_dim > 256) return fail(SACB_ERR_ARG, "act_dim > 128 unsupported");
+    if (cfg->layer_norm && cfg->n_agents != 1) return fail(SACB_ERR_ARG, "layer_norm: single-agent handles only (the population programs are not validated with it)");
     if (cfg->layer_norm && cfg->hidden_dim > 1024) return fail(SACB_ERR_ARG, "layer_norm: hidden_dim > 1024 unsupported (a row is normalised in registers)");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || cfg->device >= ndev) { cudaGetLastError(); return fail(SACB_ERR_DEVICE, "no CUDA device: this library has no CPU fallback"); }

@@ -68,7 +68,8 @@ typedef struct {
     int32_t per_weighted_loss;     /* extension: IS-weighted critic loss + |td| priority write-back */
     int32_t layer_norm;            /* extension, default 0 (the reference has none: networks_model2.py:86 is a comment): LayerNorm with
                                       affine parameters between every hidden Linear and its ReLU of all five networks; parameter
-                                      tensors per hidden layer then are weight, bias, ln.weight, ln.bias.  No reference parity. */
+                                      tensors per hidden layer then are weight, bias, ln.weight, ln.bias.  No reference parity.  Single-agent
+                                      handles only (n_agents = 1, no sacb_dp_*): SACB_ERR_ARG otherwise. */
     int32_t reserved[6];
 } sacb_config;
 

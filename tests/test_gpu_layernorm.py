@@ -114,3 +114,17 @@ def test_layernorm_persistent_equals_staged_and_checkpoint_round_trip(hw, tmp_pa
     fresh.load_checkpoint(path)
     b = O.make_batch(case["obs"], case["act"], case["batch"], seed=950)
     assert fresh.update_from_batch(b, eps=(b["eps_next"], b["eps_cur"])) == a1.update_from_batch(b, eps=(b["eps_next"], b["eps_cur"]))
+
+
+def test_layernorm_is_refused_where_it_is_not_validated(hw):
+    """population handles and the data-parallel entry points refuse the LayerNorm variant instead of running unvalidated programs"""
+    import ctypes
+    N = hw._native
+    lib = N.lib()
+    cfg = N.default_config()
+    cfg.obs_dim, cfg.act_dim, cfg.hidden_dim, cfg.n_hidden, cfg.n_agents, cfg.layer_norm, cfg.capacity = 8, 2, 64, 2, 2, 1, 1024
+    h = ctypes.c_void_p()
+    assert lib.sacb_create(ctypes.byref(cfg), ctypes.byref(h)) == N.ERR_ARG
+    agent = hw.SAC(8, 2, 64, layer_norm=True, capacity=1024, seed=1)
+    with pytest.raises(ValueError):
+        hw.distributed.DataParallelSAC(agent)
