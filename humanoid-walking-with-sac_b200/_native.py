@@ -76,6 +76,7 @@ SIGNATURES = {
     "sacb_push": (I, [H, I, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p, I64]),
     "sacb_push_rows": (I, [H, I, c_f32p, I64]),
     "sacb_row_floats": (I64, [H]),
+    "sacb_host_first_distinct": (I64, [ctypes.c_char_p, I64, ctypes.c_uint64, I, c_i64p, I64, I64]),      # words: a bytes object, passed without a copy
     "sacb_len": (I64, [H, I]),
     "sacb_read_transitions": (I, [H, I, c_i64p, I64, c_f32p, c_f32p, c_f32p, c_f32p, c_f32p]),
     "sacb_clear_replay": (I, [H, I]),

@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstring>
 #include <algorithm>
+#include <vector>
 
 #include "handle.h"
 
@@ -955,6 +956,28 @@ extern "C" int sacb_push(sacb_handle h, int agent, const float *s, const float *
 }
 
 extern "C" int64_t sacb_row_floats(sacb_handle h) { return h ? h->ring_row : -1; }
+
+// host-side helper of ReplayBuffer's index draw (include/sacb200.h): append the first distinct values below n of a word stream
+extern "C" int64_t sacb_host_first_distinct(const uint32_t *words, int64_t n_words, uint64_t n, int shift, int64_t *picks, int64_t n_have, int64_t k) {
+    if (!words || !picks || n_words < 0 || n_have < 0 || k < n_have || shift < 0 || shift > 31) return -1;
+    // open addressing over the picks so far (k is a minibatch size: the table is a few KB and rebuilt per call)
+    int64_t cap = 16;
+    while (cap < 4 * k) cap <<= 1;
+    std::vector<int64_t> table((size_t)cap, -1);
+    auto insert = [&](int64_t v) -> bool {      // false: already present
+        uint64_t hsh = (uint64_t)v * 0x9E3779B97F4A7C15ull;
+        for (int64_t i = (int64_t)(hsh >> 32) & (cap - 1);; i = (i + 1) & (cap - 1)) {
+            if (table[(size_t)i] == v) return false;
+            if (table[(size_t)i] < 0) { table[(size_t)i] = v; return true; }
+        }
+    };
+    for (int64_t j = 0; j < n_have; j++) insert(picks[j]);
+    for (int64_t j = 0; j < n_words && n_have < k; j++) {
+        const uint64_t v = words[j] >> shift;
+        if (v < n && insert((int64_t)v)) picks[n_have++] = (int64_t)v;
+    }
+    return n_have;
+}
 
 extern "C" int sacb_push_rows(sacb_handle h, int agent, const float *rows, int64_t n) {
     if (!h || !rows || agent < 0 || agent >= h->cfg.n_agents || n < 0) return fail(SACB_ERR_ARG, "bad argument");

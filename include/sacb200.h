@@ -122,6 +122,11 @@ int sacb_read_transitions(sacb_handle h, int agent, const int64_t *idx, int64_t 
                           float *r, float *s2, float *done);
 int sacb_clear_replay(sacb_handle h, int agent);
 
+/* Host-side helper of that draw, no device work: random.sample(range(n), k) on CPython's set path is "the first k distinct values
+ * below n of the Mersenne-Twister word stream, each word shifted right by 32 - n.bit_length()".  The shim fetches words from the
+ * global `random` stream (exactly as many as picks are missing, so the stream never runs ahead) and hands them here: picks[0..n_have)
+ * are the picks so far, the accepted values of words[0..n_words) are appended in stream order; returns the new count (<= k). */
+int64_t sacb_host_first_distinct(const uint32_t *words, int64_t n_words, uint64_t n, int shift, int64_t *picks, int64_t n_have, int64_t k);
 /* ReplayBuffer.sample (replay_buffer.py:13-19): gather rows idx[0..B) (logical indices drawn by the caller,
  * e.g. random.sample(range(len), B) -- identical picks and RNG consumption to random.sample(deque, B)). */
 int sacb_sample_uniform(sacb_handle h, int agent, const int64_t *idx, int64_t B, float *s, float *a, float *r,
